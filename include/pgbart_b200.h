@@ -1,0 +1,171 @@
+/*
+ * pgbart_b200.h — C ABI of the B200-native PGBART sampler core
+ * (libpgbart_b200.so, built from pymc_bart_b200/csrc/ by __graft_entry__.build()).
+ *
+ * Drop-in boundary.  pymc-bart @4daa2e2 delegates its sampler to the un-vendored
+ * PyO3 package `bartrs` (requirements.txt:6).  The entry points below are what a
+ * binding for that path has to provide; each cites the reference site it stands
+ * in for (paths relative to /root/reference):
+ *
+ *   bk_query_bytes/bk_create  <- bartrs.PGBART([rv], num_particles=..) constructor
+ *                                (tests/test_bart.py:4,231-232) reading the op
+ *                                attributes X, Y, m, alpha, beta, split_prior,
+ *                                split_rules (pymc_bart/bart.py:141-158) and the
+ *                                native `PySampler(PyBartSettings)` it builds
+ *                                (pymc_bart/pymc_bart.py:2)
+ *   bk_step                   <- PGBART.astep: one particle-Gibbs sweep over a batch
+ *                                of trees; returns the new sum-of-trees value of the
+ *                                BART variable (tests/test_bart.py:121-123,197) and
+ *                                the per-draw variable-inclusion counts that the
+ *                                shell encodes with _encode_vi (pymc_bart/utils.py:1387-1398)
+ *   bk_export_forest          <- the (baseline_forest, batches) history published in
+ *                                op.all_trees (pymc_bart/utils.py:117,124-127)
+ *   bk_predict                <- PosteriorSampler.sample_posterior(X, draw_indices,
+ *                                excluded) (pymc_bart/utils.py:60-71,93-107)
+ *
+ * Conventions: plain pointers and sizes only; 0 = success, negative = error
+ * (message via bk_last_error); nothing throws across the boundary.  Device
+ * pointers are BORROWED (the Python host owns them as torch tensors); one handle
+ * drives `n_chains` independent chains on one GPU from one host thread.
+ */
+#ifndef PGBART_B200_H
+#define PGBART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BK_ABI_VERSION 1
+
+#define BK_OK 0
+#define BK_ERR_ARG (-1)
+#define BK_ERR_CUDA (-2)
+#define BK_ERR_STATE (-3)
+#define BK_ERR_TIMEOUT (-4)
+#define BK_ERR_UNSUPPORTED (-5)
+
+#define BK_RULE_CONTINUOUS 0 /* "ContinuousSplit": x <= s  (tests/test_bart.py:143) */
+#define BK_RULE_ONEHOT 1     /* "OneHotSplit":     x == s  (tests/test_bart.py:144) */
+
+typedef struct bk_handle_s bk_handle;
+
+typedef struct {
+  int32_t abi_version;   /* BK_ABI_VERSION */
+  int32_t n_rows;        /* N observations */
+  int32_t n_cols;        /* p covariates */
+  int32_t n_trees;       /* m (bart.py:120) */
+  int32_t n_particles;   /* P, PGBART(num_particles=) (tests/test_bart.py:231) */
+  int32_t n_chains;      /* chains batched on this GPU */
+  int32_t likelihood;    /* BK_LIK_NORMAL | BK_LIK_BERNOULLI_LOGIT (bk_spec.h) */
+  int32_t qshift;        /* fixed-point scale 2^qshift for the sufficient statistics */
+  int32_t batch_tune;    /* trees per step while tuning: max(1,int(m*batch[0])) */
+  int32_t batch_post;    /* trees per step after tuning */
+  uint32_t seed;         /* Philox key word 0 */
+  uint32_t chain_base;   /* global index of local chain 0 (Philox key word 1) */
+  float init_sum;        /* initial sum of trees = Y.mean() (bart.py:148) */
+  float init_leaf;       /* initial leaf value Y.mean()/m */
+  float leaf_sd_init;    /* Y.std()/sqrt(m), or 3/sqrt(m) for 0/1 data */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t trace_capacity;/* trace records per chain per step (0 = off) */
+  int32_t reserved;
+  const double* p_leaf;        /* [256] P(node at depth d stays a leaf) (bart.py:107-109) */
+  const double* split_prior;   /* [n_cols] positive weights (bart.py:139,155) */
+  const int32_t* split_rules;  /* [n_cols] BK_RULE_* (bart.py:156), NULL = all continuous */
+} bk_settings;
+
+/* per chain, per step */
+typedef struct {
+  int32_t tree_updates;   /* trees rewritten this step */
+  int32_t rounds;         /* grow rounds summed over the trees */
+  int32_t grow_events;    /* successful particle growths (G of BASELINE.md) */
+  int32_t grow_root;      /* ... of which at the root (no leaf-id read) */
+  int32_t count_passes;   /* member-count-only passes */
+  int32_t phases;         /* grid-wide phases executed */
+  int32_t trace_len;      /* trace records written */
+  int32_t error_flags;    /* 0 = clean */
+  float leaf_sd;          /* running leaf sd after the step */
+  int32_t iter;           /* tree updates since creation */
+  int32_t reserved[2];
+} bk_step_stats;
+
+/* one record per (tree update, round, particle>=1) plus one per tree update (kind 2) */
+typedef struct {
+  int32_t kind;       /* 1 = particle round record, 2 = tree committed */
+  int32_t tree;       /* tree id */
+  int32_t round;
+  int32_t particle;   /* slot index in this round (kind 2: winning slot) */
+  int32_t node;       /* popped node (-1: empty queue) */
+  int32_t var;        /* split variable (-1: stayed leaf / no growth) */
+  int32_t n_left;
+  int32_t n_right;
+  float split;
+  float val_left;
+  float val_right;
+  int32_t ancestor;   /* slot copied into this slot by the resampling that follows (-1: none) */
+  double log_w;       /* log-weight after the round */
+  double aux;         /* kind 2: leaf_sd after commit */
+} bk_trace_rec;
+
+/* flat forest node, 24 bytes (export + prediction format) */
+typedef struct {
+  int32_t var;      /* split variable, -1 = leaf */
+  float split;      /* split value */
+  int32_t left;     /* index of the left child; right = left + 1 */
+  float value;      /* leaf value (0 for split nodes) */
+  int32_t n;        /* training rows that reached the node ("nvalue") */
+  int32_t depth;
+} bk_node;
+
+int bk_abi_version(void);
+const char* bk_last_error(void);
+
+/* bytes of device workspace the host must allocate (as one torch.uint8 tensor) */
+int bk_query_bytes(const bk_settings* s, size_t* workspace_bytes);
+
+/* Row padding: every per-row array uses a leading dimension of
+ * ld = bk_padded_rows(n_rows) (n_rows rounded up to a multiple of 256) so that
+ * each column / chain starts 1 KiB-aligned for 128-bit loads. */
+int bk_padded_rows(int n_rows);
+
+/* X: [n_cols][ld] float32 (column-major copy of op.X, bart.py:209-210; padding
+ * rows may hold anything); y: [ld] float32 (padding 0); sum_trees: [n_chains][ld]
+ * float32 (written by every step: the value handed back to PyMC); workspace:
+ * bk_query_bytes bytes.  All four are device pointers that stay owned by the caller. */
+int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev,
+              float* sum_trees_dev, void* workspace_dev, bk_handle** out);
+void bk_destroy(bk_handle* h);
+
+/* One PGBART step for every chain.  sigma_host: [n_chains] likelihood scale of
+ * the current point (ignored for Bernoulli).  vi_counts_host: [n_chains][n_cols]
+ * split-variable usage of the trees rewritten by this step (the vector that
+ * pymc_bart/utils.py:1387 encodes).  stats_host: [n_chains] or NULL.
+ * Launches one persistent kernel on the handle's stream and waits for it. */
+int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_host,
+            bk_step_stats* stats_host);
+
+/* trace of the last step of one chain (host copy); returns records copied */
+int bk_read_trace(bk_handle* h, int chain, bk_trace_rec* out_host, int capacity);
+
+/* Current forest of a chain as flat nodes: nodes_host [n_trees][255], n_nodes_host [n_trees] */
+int bk_export_forest(bk_handle* h, int chain, bk_node* nodes_host, int32_t* n_nodes_host);
+
+/* leaf assignment of every training row in every tree: ids_host [n_trees][n_rows] uint8 */
+int bk_export_leaf_ids(bk_handle* h, int chain, uint8_t* ids_host);
+
+/* Posterior prediction (row N1).  forests_dev: [n_draws][n_trees][255] bk_node,
+ * n_nodes_dev: [n_draws][n_trees]; X_dev: [n][n_cols] float32 ROW-major new data;
+ * draw_idx_dev: [n_idx]; excluded_mask_dev: [n_cols] uint8 or NULL;
+ * split_rules_dev: [n_cols] BK_RULE_* or NULL (all continuous);
+ * out_dev: [n_idx][n] float32.  Runs on `stream` (cudaStream_t as void*). */
+int bk_predict(int device, void* stream, const bk_node* forests_dev, const int32_t* n_nodes_dev,
+               int n_trees, const float* X_dev, int n, int n_cols, const int32_t* draw_idx_dev,
+               int n_idx, const uint8_t* excluded_mask_dev, const int32_t* split_rules_dev,
+               float* out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGBART_B200_H */

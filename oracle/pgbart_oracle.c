@@ -1,0 +1,476 @@
+/*
+ * pgbart_oracle.c — CPU restatement of the PGBART step.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this; the product (pymc_bart_b200/) never does.
+ *
+ * PARITY UNPINNED.  pymc-bart @4daa2e2 holds no golden vector, known-answer test
+ * or fixture for the sampler, and the sampler arithmetic itself lives in the
+ * un-vendored Rust dependency `bartrs>=0.4.0` (requirements.txt:6, imported at
+ * pymc_bart/__init__.py:15, pymc_bart/pymc_bart.py:2, tests/test_bart.py:4) which
+ * cannot be built or imported offline.  This file therefore restates the published
+ * particle-Gibbs BART algorithm (Quiroga et al., arXiv:2206.03619; the pure-Python
+ * pymc-bart <= 0.12 `PGBART.astep`, summarised in SURVEY.md Appendix A) and is
+ * anchored on the reference's own call sites and statistical tests:
+ *   - inputs read from the op ............ pymc_bart/bart.py:141-158
+ *   - depth prior alpha*(1+d)^-beta ...... pymc_bart/bart.py:107-109 (table passed in)
+ *   - initial value Y.mean() ............. pymc_bart/bart.py:148
+ *   - split rules "ContinuousSplit"/"OneHotSplit" tests/test_bart.py:143-145
+ *   - variable_inclusion counts .......... pymc_bart/utils.py:1387-1398, tests/test_bart.py:59-64
+ *   - VI dominance / prediction self-consistency: tests/test_bart.py:44-64, tests/test_utils.py:24-32
+ * The only exact fixture the reference has for this path — the varint/base64 codec
+ * round trip (tests/test_utils.py:101-113) — is checked in tests/test_codec.py.
+ *
+ * Structure: a deliberately plain, sequential, one-chain implementation with
+ * explicit per-particle leaf-id arrays that are deep-copied on resampling.  It
+ * shares with the kernels only include/bk_spec.h (RNG, fixed point, scalar
+ * closed forms).  Everything order-dependent is written out here independently.
+ *
+ * Algorithm steps, per tree update:
+ *   B1  r = y - (sum_trees - predict(old tree)), quantise r and sum_trees
+ *   B2  particle 0 = old tree (never grows); 1..P-1 = stumps
+ *   B3  pop one node per particle and round: stay leaf w.p. p_leaf[depth];
+ *       variable ~ split prior; split value = X[k-th member, var]
+ *   B4  partition the node's rows (x <= s / x == s)
+ *   B5  leaf value = mean(sum_trees over members)/m + z * leaf_sd
+ *   B6  log-weight = Gaussian log-likelihood from per-leaf (n, sum r, sum r^2)
+ *   B7  w = exp(lw - max) + 1e-12, normalised
+ *   B8  systematic resampling of particles 1..P-1
+ *   B9  final systematic resampling over all P + uniform pick; commit
+ *   B10 batch of max(1,int(m*batch)) trees per step, round robin
+ *
+ * Build: see oracle/Makefile (gcc -O2 -march=x86-64-v3 -ffp-contract=off).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "bk_spec.h"
+#include "pgbart_b200.h"
+
+typedef struct {
+  int32_t var;   /* -1 leaf */
+  float split;
+  int32_t left;  /* right = left + 1 */
+  int32_t depth;
+  float value;
+  bk_stats st;
+} o_node;
+
+typedef struct {
+  int32_t n_nodes;
+  int32_t q_head; /* expansion queue = nodes [q_head, n_nodes) in creation order */
+  double ssq;
+  double lw;
+  o_node nodes[BK_MAX_NODES];
+  uint8_t* ids; /* [N] leaf id per row */
+} o_particle;
+
+typedef struct bko_s {
+  bk_settings s;
+  int chain;
+  int N, p, m, P;
+  const float* X; /* [p][N] borrowed */
+  const float* y;
+  double p_leaf[BK_MAX_DEPTH_TABLE];
+  double* alpha_vec; /* split prior + tuned usage counts */
+  double* cum;       /* normalised cumulative split prior in use */
+  int32_t* rules;
+  float qscale;
+  double inv_qscale;
+  float* st;      /* sum of trees */
+  int32_t* qr;
+  int32_t* qst;
+  float* noi;
+  o_particle* forest; /* m trees, ids = leaf assignment */
+  o_particle* parts;  /* P */
+  o_particle* tmp;    /* P scratch for resampling */
+  float* wf_mean;
+  float* wf_m2;
+  int32_t wf_count;
+  float leaf_sd;
+  int32_t iter;
+  int32_t lower;
+  int32_t draw;
+  bk_trace_rec* trace;
+  int32_t trace_len, trace_cap;
+  double* w;
+  int32_t* anc;
+  long long bytes_touched; /* rough algorithmic byte counter for the CPU baseline */
+} bko;
+
+static void part_alloc(o_particle* q, int N) { q->ids = (uint8_t*)malloc((size_t)N); }
+static void part_copy(o_particle* dst, const o_particle* src, int N) {
+  uint8_t* keep = dst->ids;
+  dst->n_nodes = src->n_nodes; dst->q_head = src->q_head; dst->ssq = src->ssq; dst->lw = src->lw;
+  memcpy(dst->nodes, src->nodes, sizeof(o_node) * (size_t)src->n_nodes);
+  dst->ids = keep;
+  memcpy(dst->ids, src->ids, (size_t)N);
+}
+
+static void rebuild_cum(bko* o) {
+  double tot = 0.0;
+  for (int v = 0; v < o->p; ++v) tot = BK_DADD(tot, o->alpha_vec[v]);
+  double run = 0.0;
+  for (int v = 0; v < o->p; ++v) {
+    run = BK_DADD(run, o->alpha_vec[v]);
+    o->cum[v] = BK_DDIV(run, tot);
+  }
+}
+
+int bko_create(const bk_settings* s, const float* X, const float* y, int chain_local, bko** out) {
+  if (!s || !X || !y || !out) return BK_ERR_ARG;
+  if (s->n_particles < 2 || s->n_rows < 1 || s->n_trees < 1) return BK_ERR_ARG;
+  bko* o = (bko*)calloc(1, sizeof(bko));
+  o->s = *s; o->chain = chain_local;
+  o->N = s->n_rows; o->p = s->n_cols; o->m = s->n_trees; o->P = s->n_particles;
+  o->X = X; o->y = y;
+  memcpy(o->p_leaf, s->p_leaf, sizeof(double) * BK_MAX_DEPTH_TABLE);
+  o->alpha_vec = (double*)malloc(sizeof(double) * (size_t)o->p);
+  o->cum = (double*)malloc(sizeof(double) * (size_t)o->p);
+  o->rules = (int32_t*)calloc((size_t)o->p, sizeof(int32_t));
+  for (int v = 0; v < o->p; ++v) {
+    o->alpha_vec[v] = s->split_prior[v];
+    if (s->split_rules) o->rules[v] = s->split_rules[v];
+  }
+  rebuild_cum(o);
+  o->qscale = ldexpf(1.0f, s->qshift);
+  o->inv_qscale = ldexp(1.0, -s->qshift);
+  int N = o->N;
+  o->st = (float*)malloc(sizeof(float) * (size_t)N);
+  o->noi = (float*)malloc(sizeof(float) * (size_t)N);
+  o->qr = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+  o->qst = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+  o->wf_mean = (float*)calloc((size_t)N, sizeof(float));
+  o->wf_m2 = (float*)calloc((size_t)N, sizeof(float));
+  for (int i = 0; i < N; ++i) o->st[i] = s->init_sum;
+  o->forest = (o_particle*)calloc((size_t)o->m, sizeof(o_particle));
+  for (int t = 0; t < o->m; ++t) {
+    o_particle* f = &o->forest[t];
+    part_alloc(f, N);
+    memset(f->ids, 0, (size_t)N);
+    f->n_nodes = 1; f->q_head = 1;
+    f->nodes[0].var = -1; f->nodes[0].left = -1; f->nodes[0].depth = 0;
+    f->nodes[0].value = s->init_leaf; f->nodes[0].st.n = N;
+  }
+  o->parts = (o_particle*)calloc((size_t)o->P, sizeof(o_particle));
+  o->tmp = (o_particle*)calloc((size_t)o->P, sizeof(o_particle));
+  for (int q = 0; q < o->P; ++q) { part_alloc(&o->parts[q], N); part_alloc(&o->tmp[q], N); }
+  o->leaf_sd = s->leaf_sd_init;
+  o->trace_cap = s->trace_capacity;
+  if (o->trace_cap > 0) o->trace = (bk_trace_rec*)calloc((size_t)o->trace_cap, sizeof(bk_trace_rec));
+  o->w = (double*)malloc(sizeof(double) * (size_t)o->P);
+  o->anc = (int32_t*)malloc(sizeof(int32_t) * (size_t)o->P);
+  *out = o;
+  return BK_OK;
+}
+
+void bko_destroy(bko* o) {
+  if (!o) return;
+  for (int t = 0; t < o->m; ++t) free(o->forest[t].ids);
+  for (int q = 0; q < o->P; ++q) { free(o->parts[q].ids); free(o->tmp[q].ids); }
+  free(o->forest); free(o->parts); free(o->tmp);
+  free(o->alpha_vec); free(o->cum); free(o->rules);
+  free(o->st); free(o->noi); free(o->qr); free(o->qst); free(o->wf_mean); free(o->wf_m2);
+  free(o->trace); free(o->w); free(o->anc);
+  free(o);
+}
+
+static bk_trace_rec* trace_slot(bko* o) {
+  if (!o->trace || o->trace_len >= o->trace_cap) { if (o->trace) o->trace_len++; return NULL; }
+  bk_trace_rec* r = &o->trace[o->trace_len++];
+  memset(r, 0, sizeof(*r));
+  return r;
+}
+
+/* Gaussian log-likelihood of a whole particle from its per-leaf statistics,
+ * leaves visited in node-index order */
+static double particle_ssq(const bko* o, const o_particle* q) {
+  double ssq = 0.0;
+  for (int k = 0; k < q->n_nodes; ++k)
+    if (q->nodes[k].var < 0) ssq = BK_DADD(ssq, bk_leaf_ssq(q->nodes[k].st, q->nodes[k].value, o->inv_qscale));
+  return ssq;
+}
+
+/* systematic resampling: indices[i] = inverse cdf of (u+i)/L over weights w[0..L) */
+static void systematic(const double* w, int L, double u, int32_t* idx_out) {
+  int idx = 0;
+  double a = w[0];
+  for (int i = 0; i < L; ++i) {
+    double point = BK_DDIV(BK_DADD(u, (double)i), (double)L);
+    while (point > a && idx < L - 1) { idx += 1; a = BK_DADD(a, w[idx]); }
+    idx_out[i] = idx;
+  }
+}
+
+static void normalise(const o_particle* parts, int first, int count, double* w) {
+  double mx = parts[first].lw;
+  for (int i = 1; i < count; ++i) if (parts[first + i].lw > mx) mx = parts[first + i].lw;
+  double tot = 0.0;
+  for (int i = 0; i < count; ++i) { w[i] = bk_weight_term(parts[first + i].lw, mx); tot = BK_DADD(tot, w[i]); }
+  for (int i = 0; i < count; ++i) w[i] = BK_DDIV(w[i], tot);
+}
+
+static int draw_variable(const bko* o, double u) {
+  for (int v = 0; v < o->p; ++v) if (u < o->cum[v]) return v;
+  return o->p - 1;
+}
+
+/* one grow attempt of particle slot `pi` at round `round`; returns 1 if it grew */
+static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* rec) {
+  o_particle* q = &o->parts[pi];
+  const int N = o->N;
+  if (rec) { rec->node = -1; rec->var = -1; }
+  if (q->q_head >= q->n_nodes) return 0;
+  int j = q->q_head++;
+  if (rec) rec->node = j;
+  o_node* nd = &q->nodes[j];
+  uint32_t S = o->s.seed, C = o->s.chain_base + (uint32_t)o->chain, D = (uint32_t)o->draw;
+  int depth = nd->depth;
+  double pl = depth < BK_MAX_DEPTH_TABLE ? o->p_leaf[depth] : 1.0;
+  double u1 = bk_u01(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_LEAF).v[0]);
+  if (!(u1 > pl)) return 0;                       /* stays a leaf */
+  if (q->n_nodes + 2 > BK_MAX_NODES) return 0;    /* node budget of one byte ids */
+  double u2 = bk_u01(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAR).v[0]);
+  int v = draw_variable(o, u2);
+  int n = nd->st.n;
+  if (n < 2) return 0;                            /* fewer than two candidate split values */
+  uint32_t k = bk_index(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAL).v[0], (uint32_t)n);
+  const float* xc = o->X + (size_t)v * (size_t)N;
+  /* k-th member of node j in ascending row index */
+  float s = 0.0f;
+  {
+    uint32_t seen = 0; int found = 0;
+    for (int i = 0; i < N; ++i) {
+      if (q->ids[i] == (uint8_t)j) { if (seen == k) { s = xc[i]; found = 1; break; } seen++; }
+    }
+    if (!found) return 0; /* cannot happen: n counts the members */
+  }
+  int L = q->n_nodes, R = q->n_nodes + 1;
+  bk_stats sl, sr;
+  memset(&sl, 0, sizeof(sl)); memset(&sr, 0, sizeof(sr));
+  const int onehot = o->rules[v] == BK_RULE_ONEHOT;
+  for (int i = 0; i < N; ++i) {
+    if (q->ids[i] != (uint8_t)j) continue;
+    float x = xc[i];
+    int left = onehot ? (x == s) : (x <= s);
+    bk_stats* t = left ? &sl : &sr;
+    q->ids[i] = (uint8_t)(left ? L : R);
+    int64_t a = (int64_t)o->qr[i];
+    t->n += 1; t->sst += (int64_t)o->qst[i]; t->sr += a;
+    t->sr2 = bk_u128_add(t->sr2, bk_u128_make(0, (uint64_t)(a * a)));
+  }
+  o->bytes_touched += (long long)N * 14;
+  double zl = bk_normal(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_LEFT));
+  double zr = bk_normal(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_RIGHT));
+  float vl = bk_leaf_value(sl.n, sl.sst, o->inv_qscale, (double)o->m, zl, o->leaf_sd);
+  float vr = bk_leaf_value(sr.n, sr.sst, o->inv_qscale, (double)o->m, zr, o->leaf_sd);
+  double c_parent = bk_leaf_ssq(nd->st, nd->value, o->inv_qscale);
+  nd->var = v; nd->split = s; nd->left = L;
+  o_node* nl = &q->nodes[L]; o_node* nr = &q->nodes[R];
+  nl->var = -1; nl->split = 0.0f; nl->left = -1; nl->depth = depth + 1; nl->value = vl; nl->st = sl;
+  nr->var = -1; nr->split = 0.0f; nr->left = -1; nr->depth = depth + 1; nr->value = vr; nr->st = sr;
+  q->n_nodes += 2;
+  q->ssq = BK_DADD(BK_DADD(BK_DSUB(q->ssq, c_parent), bk_leaf_ssq(sl, vl, o->inv_qscale)), bk_leaf_ssq(sr, vr, o->inv_qscale));
+  q->lw = bk_normal_loglik(q->ssq, sigma, (double)N);
+  if (rec) { rec->var = v; rec->split = s; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
+  return 1;
+}
+
+int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* stats) {
+  if (o->s.likelihood != BK_LIK_NORMAL) return BK_ERR_UNSUPPORTED;
+  const int N = o->N, P = o->P, m = o->m;
+  bk_step_stats loc; memset(&loc, 0, sizeof(loc));
+  o->trace_len = 0;
+  if (vi_counts) memset(vi_counts, 0, sizeof(int32_t) * (size_t)o->p);
+  int T = tune ? o->s.batch_tune : o->s.batch_post;
+  int upper = o->lower + T < m ? o->lower + T : m;
+  uint32_t S = o->s.seed, C = o->s.chain_base + (uint32_t)o->chain, D = (uint32_t)o->draw;
+  for (int t = o->lower; t < upper; ++t) {
+    o->iter += 1;
+    o_particle* old = &o->forest[t];
+    /* B1: residual without tree t, fixed-point copies */
+    bk_stats tot; memset(&tot, 0, sizeof(tot));
+    for (int k = 0; k < old->n_nodes; ++k) { bk_stats z; memset(&z, 0, sizeof(z)); z.n = old->nodes[k].st.n; old->nodes[k].st = z; }
+    for (int i = 0; i < N; ++i) {
+      float oldp = old->ids[i] == BK_LIMBO ? 0.0f : old->nodes[old->ids[i]].value;
+      float noi = BK_FSUB(o->st[i], oldp);
+      float r = BK_FSUB(o->y[i], noi);
+      o->noi[i] = noi;
+      int32_t a = bk_quant(r, o->qscale), b = bk_quant(o->st[i], o->qscale);
+      o->qr[i] = a; o->qst[i] = b;
+      bk_u128 sq = bk_u128_make(0, (uint64_t)((int64_t)a * (int64_t)a));
+      tot.n += 1; tot.sst += b; tot.sr += a; tot.sr2 = bk_u128_add(tot.sr2, sq);
+      if (old->ids[i] != BK_LIMBO) {
+        bk_stats* ls = &old->nodes[old->ids[i]].st;
+        ls->sr += a; ls->sr2 = bk_u128_add(ls->sr2, sq);
+      }
+    }
+    o->bytes_touched += (long long)N * 23;
+    /* B2: particles */
+    part_copy(&o->parts[0], old, N);
+    o->parts[0].q_head = o->parts[0].n_nodes;
+    o->parts[0].ssq = particle_ssq(o, &o->parts[0]);
+    o->parts[0].lw = bk_normal_loglik(o->parts[0].ssq, sigma, (double)N);
+    for (int q = 1; q < P; ++q) {
+      o_particle* pq = &o->parts[q];
+      pq->n_nodes = 1; pq->q_head = 0;
+      pq->nodes[0].var = -1; pq->nodes[0].split = 0.0f; pq->nodes[0].left = -1; pq->nodes[0].depth = 0;
+      pq->nodes[0].value = o->s.init_leaf; pq->nodes[0].st = tot;
+      memset(pq->ids, 0, (size_t)N);
+      pq->ssq = bk_leaf_ssq(tot, o->s.init_leaf, o->inv_qscale);
+      pq->lw = bk_normal_loglik(pq->ssq, sigma, (double)N);
+    }
+    /* B3-B8: grow rounds */
+    int round = 0;
+    for (;; ++round) {
+      int tr0 = o->trace_len;
+      for (int q = 1; q < P; ++q) {
+        bk_trace_rec* rec = trace_slot(o);
+        if (rec) { rec->kind = 1; rec->tree = t; rec->round = round; rec->particle = q; rec->ancestor = -1; }
+        int was_root = o->parts[q].q_head == 0;
+        if (grow(o, t, round, q, sigma, rec)) { loc.grow_events++; if (was_root) loc.grow_root++; }
+        if (rec) rec->log_w = o->parts[q].lw;
+      }
+      loc.rounds++;
+      int live = 0;
+      for (int q = 1; q < P; ++q) if (o->parts[q].q_head < o->parts[q].n_nodes) live = 1;
+      if (!live) break;
+      normalise(o->parts, 1, P - 1, o->w);
+      double u = bk_u01(bk_rng(S, C, D, 0, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0]);
+      systematic(o->w, P - 1, u, o->anc);
+      for (int q = 1; q < P; ++q) part_copy(&o->tmp[q], &o->parts[o->anc[q - 1] + 1], N);
+      for (int q = 1; q < P; ++q) {
+        o_particle sw = o->parts[q]; o->parts[q] = o->tmp[q]; o->tmp[q] = sw;
+        if (o->trace && tr0 + q - 1 < o->trace_cap) o->trace[tr0 + q - 1].ancestor = o->anc[q - 1] + 1;
+      }
+    }
+    /* B9: final selection */
+    normalise(o->parts, 0, P, o->w);
+    double uf = bk_u01(bk_rng(S, C, D, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
+    systematic(o->w, P, uf, o->anc);
+    uint32_t pick = bk_index(bk_rng(S, C, D, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P);
+    int win = o->anc[pick];
+    o_particle* nw = &o->parts[win];
+    /* commit: sum_trees = noi + predict(new) */
+    double sd_acc_q = 0.0; int64_t sd_sum = 0;
+    int do_wf = tune;
+    if (do_wf) o->wf_count += 1;
+    for (int i = 0; i < N; ++i) {
+      float newp = nw->ids[i] == BK_LIMBO ? 0.0f : nw->nodes[nw->ids[i]].value;
+      o->st[i] = BK_FADD(o->noi[i], newp);
+      if (do_wf) {
+        float cnt = (float)o->wf_count;
+        float delta = BK_FSUB(newp, o->wf_mean[i]);
+        float mean = BK_FADD(o->wf_mean[i], BK_FDIV(delta, cnt));
+        float delta2 = BK_FSUB(newp, mean);
+        float m2 = BK_FFMA(delta, delta2, o->wf_m2[i]);
+        o->wf_mean[i] = mean; o->wf_m2[i] = m2;
+        float sd = BK_FSQRT(BK_FDIV(m2, cnt));
+        sd_sum += (int64_t)bk_quant(sd, o->qscale);
+      }
+    }
+    (void)sd_acc_q;
+    o->bytes_touched += (long long)N * (do_wf ? 26 : 10);
+    if (tune) {
+      if (o->iter > m) rebuild_cum(o);
+      for (int k = 0; k < nw->n_nodes; ++k) if (nw->nodes[k].var >= 0) o->alpha_vec[nw->nodes[k].var] = BK_DADD(o->alpha_vec[nw->nodes[k].var], 1.0);
+      if (o->iter > 2) o->leaf_sd = (float)BK_DDIV(BK_DMUL((double)sd_sum, o->inv_qscale), (double)N);
+    } else if (vi_counts) {
+      for (int k = 0; k < nw->n_nodes; ++k) if (nw->nodes[k].var >= 0) vi_counts[nw->nodes[k].var] += 1;
+    }
+    bk_trace_rec* rec = trace_slot(o);
+    if (rec) { rec->kind = 2; rec->tree = t; rec->round = round; rec->particle = win; rec->node = nw->n_nodes; rec->var = -1; rec->ancestor = (int32_t)pick; rec->log_w = nw->lw; rec->aux = (double)o->leaf_sd; }
+    part_copy(old, nw, N);
+    old->q_head = old->n_nodes;
+    loc.tree_updates++;
+  }
+  o->lower = upper < m ? upper : 0;
+  o->draw += 1;
+  loc.trace_len = o->trace_len; loc.leaf_sd = o->leaf_sd; loc.iter = o->iter;
+  if (o->trace && o->trace_len > o->trace_cap) loc.error_flags |= 1;
+  if (stats) *stats = loc;
+  return BK_OK;
+}
+
+int bko_sum_trees(const bko* o, float* out) { memcpy(out, o->st, sizeof(float) * (size_t)o->N); return BK_OK; }
+
+int bko_read_trace(const bko* o, bk_trace_rec* out, int capacity) {
+  int n = o->trace_len < o->trace_cap ? o->trace_len : o->trace_cap;
+  if (n > capacity) n = capacity;
+  if (n > 0) memcpy(out, o->trace, sizeof(bk_trace_rec) * (size_t)n);
+  return n;
+}
+
+int bko_export_forest(const bko* o, bk_node* nodes, int32_t* n_nodes) {
+  for (int t = 0; t < o->m; ++t) {
+    const o_particle* f = &o->forest[t];
+    n_nodes[t] = f->n_nodes;
+    for (int k = 0; k < BK_MAX_NODES; ++k) {
+      bk_node* d = &nodes[(size_t)t * BK_MAX_NODES + k];
+      memset(d, 0, sizeof(*d));
+      if (k < f->n_nodes) {
+        d->var = f->nodes[k].var; d->split = f->nodes[k].split; d->left = f->nodes[k].left;
+        d->value = f->nodes[k].var < 0 ? f->nodes[k].value : 0.0f; d->n = f->nodes[k].st.n; d->depth = f->nodes[k].depth;
+      }
+    }
+  }
+  return BK_OK;
+}
+
+int bko_export_leaf_ids(const bko* o, uint8_t* ids) {
+  for (int t = 0; t < o->m; ++t) memcpy(ids + (size_t)t * (size_t)o->N, o->forest[t].ids, (size_t)o->N);
+  return BK_OK;
+}
+
+long long bko_bytes_touched(const bko* o) { return o->bytes_touched; }
+float bko_leaf_sd(const bko* o) { return o->leaf_sd; }
+
+/* ------------------------------------------------------------------------
+ * Posterior prediction restatement (boundary:
+ * pymc_bart/utils.py:60-71).  Row-major X_new [n][p]; weighted descent when the
+ * split variable is excluded; NaN compares false (goes right).
+ */
+static double predict_tree(const bk_node* nodes, const float* x, const uint8_t* excl, const int32_t* rules) {
+  /* explicit stack of (node, weight); the right child is pushed first so the left is visited first */
+  int sn[48]; double sw[48]; int sp = 1;
+  sn[0] = 0; sw[0] = 1.0;
+  double tv = 0.0;
+  while (sp > 0) {
+    --sp;
+    int k = sn[sp]; double w = sw[sp];
+    const bk_node* nd = &nodes[k];
+    if (nd->var < 0) { tv = BK_DFMA(w, (double)nd->value, tv); continue; }
+    int l = nd->left, r = nd->left + 1;
+    if (excl && excl[nd->var]) {
+      double tot = (double)nodes[l].n + (double)nodes[r].n;
+      if (!(tot > 0.0) || sp + 2 > 48) continue;
+      double wl = BK_DDIV((double)nodes[l].n, tot);
+      double wr = BK_DSUB(1.0, wl);
+      sn[sp] = r; sw[sp] = BK_DMUL(w, wr); ++sp;
+      sn[sp] = l; sw[sp] = BK_DMUL(w, wl); ++sp;
+    } else {
+      float xv = x[nd->var];
+      int left = (rules && rules[nd->var] == BK_RULE_ONEHOT) ? (xv == nd->split) : (xv <= nd->split);
+      sn[sp] = left ? l : r; sw[sp] = w; ++sp;
+    }
+  }
+  return tv;
+}
+
+int bko_predict(const bk_node* forests, const int32_t* n_nodes, int n_trees, const float* X, int n, int n_cols,
+                const int32_t* draw_idx, int n_idx, const uint8_t* excluded_mask, const int32_t* rules, float* out) {
+  (void)n_nodes;
+  for (int d = 0; d < n_idx; ++d) {
+    const bk_node* f = forests + (size_t)draw_idx[d] * (size_t)n_trees * BK_MAX_NODES;
+    for (int i = 0; i < n; ++i) {
+      double acc = 0.0;
+      for (int t = 0; t < n_trees; ++t)
+        acc = BK_DADD(acc, predict_tree(f + (size_t)t * BK_MAX_NODES, X + (size_t)i * (size_t)n_cols, excluded_mask, rules));
+      out[(size_t)d * (size_t)n + i] = (float)acc;
+    }
+  }
+  return BK_OK;
+}

@@ -1,0 +1,1225 @@
+// pgbart_b200.cu — B200 (sm_100a) PGBART step: one persistent cooperative kernel
+// per step + the C ABI of include/pgbart_b200.h.
+//
+// Hot path (pymc-bart's PGBART.astep; reference sites cited in include/pgbart_b200.h
+// and SURVEY.md §8a rows B1-B10).  One launch runs the whole step for every chain
+// batched on this GPU.  The kernel alternates two kinds of grid-wide phases,
+// separated by a release/acquire grid barrier:
+//
+//   CONTROL  (one CTA per chain; scalar work, O(P) per round): leaf values, log
+//            weights, systematic resampling, queue pops, split-variable and split
+//            index draws, k-th-member selection (per-tile counts + one tile scan),
+//            row allocation, job descriptors.
+//   DATA     (all CTAs; the O(P*N) streams):
+//     ROUND  one warp walks 256 rows x up to 16 particles: the tile's fixed-point
+//            residual/sum-of-trees stay in registers, per particle it reads 8 leaf
+//            ids/lane (one 64-bit load) and the split column (two 128-bit loads),
+//            routes members left/right, writes the new leaf-id row, reduces the
+//            left child's (n, sum q_st, sum q_r, sum q_r^2) with warp shuffles and
+//            issues one 64-bit RED per statistic, and counts the members of the
+//            particle's next queue node per tile (feeds the next selection).
+//     SWEEP  fused commit of tree t (sum_trees = noi + new prediction, leaf-id row,
+//            Welford running sd) and prologue of tree t+1 (residual, fixed-point
+//            copies, per-leaf statistics of the old tree).
+//
+// All reductions are integer (bk_spec.h), so results do not depend on the grid
+// size, the reduction order, or the number of GPUs; every float op is an explicit
+// round-to-nearest intrinsic in a fixed order.  No tensor cores: there is no dense
+// contraction on this path (HBM/L2-bound integer and compare work).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "pgbart_device.cuh"
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile_i32(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+  atomicAdd(p, v);  // result unused -> RED.E.ADD.64
+}
+
+// ~4 s at 1.9 GHz: a barrier that is not reached means a bug; every CTA bails out
+#define BK_BARRIER_TIMEOUT_CYCLES (8000000000LL)
+
+struct CtlShared {
+  double w[BK_MAX_PARTICLES];
+  double lw[BK_MAX_PARTICLES];
+  int anc[BK_MAX_PARTICLES];
+  int s_kind[BK_MAX_PARTICLES];   // 0 nothing, 1 grow, 2 only needs a count
+  int s_j[BK_MAX_PARTICLES];
+  int s_v[BK_MAX_PARTICLES];
+  unsigned s_k[BK_MAX_PARTICLES];
+  int s_next[BK_MAX_PARTICLES];
+  int s_row[BK_MAX_PARTICLES];
+  int s_nn[BK_MAX_PARTICLES];
+  float s_split[BK_MAX_PARTICLES];
+  unsigned char row_used[2 * BK_MAX_PARTICLES];
+  int live;
+  int win;
+  unsigned pick;
+};
+
+struct DataShared {
+  int cmd[64];
+  int njobs[64];
+  int ngroups[64];
+  int ru_base[65];   // prefix of round units
+  int su_base[65];   // prefix of sweep units
+  int group;
+  int all_done;
+  float old_vals[256];
+  float new_vals[256];
+  float pro_vals[256];
+  unsigned long long leaf_acc[256 * 3];
+  unsigned long long tot_acc[8];
+};
+
+union __align__(16) KernelShared {
+  CtlShared ctl;
+  DataShared data;
+};
+
+// ------------------------------------------------------------------ grid barrier
+__device__ __forceinline__ bool grid_sync(const Params& P, unsigned& target, int* s_abort) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    red_release_add_u32(P.barrier, 1u);
+    long long t0 = clock64();
+    int ab = 0;
+    while (ld_acquire_u32(P.barrier) < target) {
+      if (ld_volatile_i32(P.abort_flag)) { ab = 1; break; }
+      if (clock64() - t0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); ab = 1; break; }
+    }
+    if (!ab && ld_volatile_i32(P.abort_flag)) ab = 1;
+    __threadfence();
+    *s_abort = ab;
+  }
+  __syncthreads();
+  return *s_abort != 0;
+}
+
+// ------------------------------------------------------------------ small device utils
+__device__ __forceinline__ DParticle* part_ptr(const Params& P, int c, int buf, int q) {
+  return P.parts + ((size_t)c * 2 + buf) * P.P + q;
+}
+__device__ __forceinline__ bk_stats node_stats(const DNode& nd) {
+  bk_stats s; s.n = nd.n; s.sst = nd.sst; s.sr = nd.sr; s.sr2 = bk_u128_make(nd.sr2_hi, nd.sr2_lo); return s;
+}
+__device__ __forceinline__ void set_node_stats(DNode& nd, const bk_stats& s) {
+  nd.n = s.n; nd.sst = s.sst; nd.sr = s.sr; nd.sr2_hi = s.sr2.hi; nd.sr2_lo = s.sr2.lo;
+}
+__device__ __forceinline__ bk_trace_rec* trace_at(const Params& P, int c, int pos) {
+  if (P.trace_cap <= 0 || pos < 0 || pos >= P.trace_cap) return nullptr;
+  return P.trace + (size_t)c * P.trace_cap + pos;
+}
+
+// k-th member (ascending row index) of `node` in pool row `row`; executed by one warp.
+__device__ float select_split(const Params& P, int c, int row, int node, unsigned k, int var, int* err) {
+  const int lane = threadIdx.x & 31;
+  const unsigned* cnt = P.rowcnt + ((size_t)c * P.R + row) * P.ntiles;
+  unsigned run = 0, off = 0;
+  int tile = -1;
+  for (int t0 = 0; t0 < P.ntiles; t0 += 32) {
+    int t = t0 + lane;
+    unsigned v = t < P.ntiles ? __ldcg(cnt + t) : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += nb;
+    }
+    unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (k < run + total) {
+      unsigned excl = incl - v;
+      bool here = (k >= run + excl) && (k < run + incl);
+      unsigned b = __ballot_sync(0xffffffffu, here);
+      int src = __ffs(b) - 1;
+      tile = t0 + src;
+      off = k - (run + __shfl_sync(0xffffffffu, excl, src));
+      break;
+    }
+    run += total;
+  }
+  if (tile < 0) { if (lane == 0) *err |= 2; return 0.0f; }
+  const uint8_t* rp = P.rows + ((size_t)c * P.R + row) * P.Npad + (size_t)tile * BK_WARP_TILE + lane * BK_ROWS_PER_LANE;
+  unsigned long long ids = __ldcg(reinterpret_cast<const unsigned long long*>(rp));
+  unsigned mm = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) mm |= (((unsigned)(ids >> (8 * e)) & 255u) == (unsigned)node) ? (1u << e) : 0u;
+  unsigned v = __popc(mm), incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += nb;
+  }
+  unsigned excl = incl - v;
+  bool here = (off >= excl) && (off < incl);
+  unsigned b = __ballot_sync(0xffffffffu, here);
+  if (b == 0) { if (lane == 0) *err |= 4; return 0.0f; }
+  int src = __ffs(b) - 1;
+  int pos = -1;
+  if (lane == src) {
+    unsigned want = off - excl, seen = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (mm & (1u << e)) { if (seen == want && pos < 0) pos = e; seen++; }
+    }
+  }
+  pos = __shfl_sync(0xffffffffu, pos, src);
+  size_t i = (size_t)tile * BK_WARP_TILE + (size_t)src * BK_ROWS_PER_LANE + (size_t)pos;
+  return __ldg(P.X + (size_t)var * P.Npad + i);
+}
+
+// normalise sh.lw[first..first+count) into sh.w, then systematic resampling into sh.anc
+// (block-wide; thread 0 does the order-dependent scalar parts in the oracle's order)
+__device__ void normalise_and_resample(CtlShared& sh, int first, int count, double u) {
+  __shared__ double s_max;
+  if (threadIdx.x == 0) {
+    double mx = sh.lw[first];
+    for (int i = 1; i < count; ++i) if (sh.lw[first + i] > mx) mx = sh.lw[first + i];
+    s_max = mx;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < count) sh.w[threadIdx.x] = bk_weight_term(sh.lw[first + threadIdx.x], s_max);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < count; ++i) tot = BK_DADD(tot, sh.w[i]);
+    int idx = 0;
+    double a = BK_DDIV(sh.w[0], tot);
+    for (int i = 0; i < count; ++i) {
+      double point = BK_DDIV(BK_DADD(u, (double)i), (double)count);
+      while (point > a && idx < count - 1) { idx += 1; a = BK_DADD(a, BK_DDIV(sh.w[idx], tot)); }
+      sh.anc[i] = idx;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ void zero_acc0(const Params& P, int c) {
+  unsigned long long* a = P.acc0 + (size_t)c * BK_ACC0_WORDS;
+  for (int i = threadIdx.x; i < BK_ACC0_WORDS; i += blockDim.x) a[i] = 0ull;
+}
+
+__device__ void rebuild_cum_dev(const Params& P, int c) {  // thread 0 only
+  double* av = P.alpha_vec + (size_t)c * P.p;
+  double* cum = P.cum + (size_t)c * P.p;
+  double tot = 0.0;
+  for (int v = 0; v < P.p; ++v) tot = BK_DADD(tot, av[v]);
+  double run = 0.0;
+  for (int v = 0; v < P.p; ++v) { run = BK_DADD(run, av[v]); cum[v] = BK_DDIV(run, tot); }
+}
+
+// ------------------------------------------------------------------ control phase
+__device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
+  const int t = ctl->cur_tree;
+  const unsigned long long* a0 = P.acc0 + (size_t)c * BK_ACC0_WORDS;
+  const DNode* ft = P.forest + ((size_t)c * P.m + t) * BK_MAX_NODES;
+  const int nn = P.forest_nn[(size_t)c * P.m + t];
+  DParticle* p0 = part_ptr(P, c, 0, 0);
+  for (int k = threadIdx.x; k < nn; k += blockDim.x) {
+    DNode nd = ft[k];
+    nd.sst = 0;
+    nd.sr = (int64_t)__ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 0);
+    bk_u128 s2 = bk_u128_from_split(__ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 2), __ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 1));
+    nd.sr2_hi = s2.hi; nd.sr2_lo = s2.lo;
+    p0->nodes[k] = nd;
+  }
+  for (int r = threadIdx.x; r < P.R; r += blockDim.x) ctl->row_cnt_node[r] = -1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ssq = 0.0;
+    for (int k = 0; k < nn; ++k) {
+      const DNode& nd = p0->nodes[k];
+      if (nd.var < 0) ssq = BK_DADD(ssq, bk_leaf_ssq(node_stats(nd), nd.value, P.inv_qscale));
+    }
+    p0->n_nodes = nn; p0->q_head = nn; p0->row = BK_ROW_FOREST;
+    p0->ssq = ssq; p0->lw = bk_normal_loglik(ssq, ctl->sigma, (double)P.N);
+    ctl->buf = 0; ctl->round = 0;
+  }
+  const int q = threadIdx.x;
+  if (q >= 1 && q < P.P) {
+    bk_stats tot;
+    tot.n = P.N;
+    tot.sr = (int64_t)__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 0);
+    tot.sr2 = bk_u128_from_split(__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 2), __ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 1));
+    tot.sst = (int64_t)__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 3);
+    DParticle* S = part_ptr(P, c, 0, q);
+    DNode nd;
+    nd.var = -1; nd.split = 0.0f; nd.left = -1; nd.depth = 0; nd.value = P.init_leaf; nd.pad = 0;
+    set_node_stats(nd, tot);
+    S->nodes[0] = nd;
+    S->n_nodes = 1; S->q_head = 0; S->row = BK_ROW_VIRTUAL;
+    S->ssq = bk_leaf_ssq(tot, P.init_leaf, P.inv_qscale);
+    S->lw = bk_normal_loglik(S->ssq, ctl->sigma, (double)P.N);
+  }
+  __syncthreads();
+}
+
+// pops, grow decisions, split selection, job list.  Returns (uniformly) the job count.
+__device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
+  const int buf = ctl->buf, round = ctl->round, t = ctl->cur_tree;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)ctl->draw;
+  const int q = threadIdx.x;
+  if (q < P.P) { sh.s_kind[q] = 0; sh.s_next[q] = -1; sh.s_j[q] = -1; }
+  if (q >= 1 && q < P.P) {
+    DParticle* S = part_ptr(P, c, buf, q);
+    int nn = S->n_nodes, qh = S->q_head, row = S->row;
+    int kind = 0, j = -1, v = -1, next = -1;
+    unsigned k = 0;
+    if (qh < nn) {
+      j = qh; qh += 1; S->q_head = qh;
+      const int depth = S->nodes[j].depth;
+      const int n = S->nodes[j].n;
+      double pl = depth < BK_MAX_DEPTH_TABLE ? P.p_leaf[depth] : 1.0;
+      double u1 = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
+      if (u1 > pl && nn + 2 <= BK_MAX_NODES) {
+        double u2 = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAR).v[0]);
+        const double* cum = P.cum + (size_t)c * P.p;
+        int lo = 0, hi = P.p - 1;  // first index with u2 < cum[idx], else p-1
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (u2 < cum[mid]) hi = mid; else lo = mid + 1; }
+        v = lo;
+        if (n >= 2) {
+          k = bk_index(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAL).v[0], (uint32_t)n);
+          kind = 1;
+        }
+      }
+      if (kind == 1) next = qh;            // a queued node, or one of the two children being made
+      else { next = qh < nn ? qh : -1; if (next >= 0) kind = 2; }
+    }
+    sh.s_kind[q] = kind; sh.s_j[q] = j; sh.s_v[q] = v; sh.s_k[q] = k; sh.s_next[q] = next; sh.s_row[q] = row; sh.s_nn[q] = nn;
+    bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + q - 1);
+    if (rec) {
+      bk_trace_rec r; memset(&r, 0, sizeof(r));
+      r.kind = 1; r.tree = t; r.round = round; r.particle = q; r.node = j; r.var = -1; r.ancestor = -1;
+      *rec = r;
+    }
+  }
+  __syncthreads();
+  // split values: one warp per growing particle
+  {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    __shared__ int s_err;
+    if (threadIdx.x == 0) s_err = 0;
+    __syncthreads();
+    for (int s = 1 + warp; s < P.P; s += nwarps) {
+      if (sh.s_kind[s] != 1) continue;
+      float sv;
+      if (sh.s_row[s] == BK_ROW_VIRTUAL) {
+        sv = __ldg(P.X + (size_t)sh.s_v[s] * P.Npad + sh.s_k[s]);
+      } else {
+        int err = 0;
+        if (ctl->row_cnt_node[sh.s_row[s]] != sh.s_j[s]) err |= 1;
+        sv = select_split(P, c, sh.s_row[s], sh.s_j[s], sh.s_k[s], sh.s_v[s], &err);
+        if (lane == 0 && err) atomicOr(&s_err, err);
+      }
+      if (lane == 0) sh.s_split[s] = sv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_err) ctl->c_err |= s_err;
+  }
+  // rows + job list (sequential: deterministic placement)
+  __shared__ int s_njobs;
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < P.R; ++r) sh.row_used[r] = 0;
+    for (int s = 0; s < P.P; ++s) { int r = part_ptr(P, c, buf, s)->row; if (r >= 0) sh.row_used[r] = 1; }
+    int nj = 0, free_r = 0;
+    for (int s = 1; s < P.P; ++s) {
+      if (sh.s_kind[s] == 1) {
+        while (free_r < P.R && sh.row_used[free_r]) free_r++;
+        Job jb; memset(&jb, 0, sizeof(jb));
+        jb.kind = BK_JOB_PARTITION; jb.slot = s; jb.src_row = sh.s_row[s]; jb.dst_row = free_r;
+        jb.node = sh.s_j[s]; jb.var = sh.s_v[s]; jb.split = sh.s_split[s]; jb.left_id = sh.s_nn[s];
+        jb.next_node = sh.s_next[s]; jb.rule = P.rules[sh.s_v[s]];
+        if (free_r >= P.R) { ctl->c_err |= 8; jb.dst_row = 0; }
+        else { sh.row_used[free_r] = 1; ctl->row_cnt_node[free_r] = jb.next_node; }
+        ctl->jobs[nj++] = jb;
+      } else if (sh.s_kind[s] == 2) {
+        int r = sh.s_row[s];
+        if (r >= 0 && ctl->row_cnt_node[r] != sh.s_next[s]) {
+          Job jb; memset(&jb, 0, sizeof(jb));
+          jb.kind = BK_JOB_COUNT; jb.slot = s; jb.src_row = r; jb.dst_row = r; jb.node = -1; jb.var = 0;
+          jb.next_node = sh.s_next[s];
+          ctl->row_cnt_node[r] = sh.s_next[s];
+          ctl->jobs[nj++] = jb;
+          ctl->c_count_passes += 1;
+        }
+      }
+    }
+    ctl->n_jobs = nj;
+    s_njobs = nj;
+  }
+  __syncthreads();
+  return s_njobs;
+}
+
+// apply the statistics of the finished ROUND to the particles that grew
+__device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl) {
+  const int buf = ctl->buf, round = ctl->round, t = ctl->cur_tree;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)ctl->draw;
+  const int nj = ctl->n_jobs;
+  const int ji = threadIdx.x;
+  if (ji < nj && ctl->jobs[ji].kind == BK_JOB_PARTITION) {
+    const Job jb = ctl->jobs[ji];
+    const int q = jb.slot;
+    DParticle* S = part_ptr(P, c, buf, q);
+    unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
+    bk_stats sl;
+    sl.n = (int32_t)__ldcg(acc + BK_ACC_N);
+    sl.sst = (int64_t)__ldcg(acc + BK_ACC_SST);
+    sl.sr = (int64_t)__ldcg(acc + BK_ACC_SR);
+    sl.sr2 = bk_u128_from_split(__ldcg(acc + BK_ACC_SR2HI), __ldcg(acc + BK_ACC_SR2LO));
+#pragma unroll
+    for (int e = 0; e < 5; ++e) acc[e] = 0ull;
+    DNode parent = S->nodes[jb.node];
+    bk_stats sp = node_stats(parent);
+    bk_stats sr = bk_stats_sub(sp, sl);
+    double zl = bk_normal(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
+    double zr = bk_normal(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
+    float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qscale, (double)P.m, zl, ctl->leaf_sd);
+    float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qscale, (double)P.m, zr, ctl->leaf_sd);
+    double c_parent = bk_leaf_ssq(sp, parent.value, P.inv_qscale);
+    const int nn = S->n_nodes;
+    parent.var = jb.var; parent.split = jb.split; parent.left = nn;
+    S->nodes[jb.node] = parent;
+    DNode nl; nl.var = -1; nl.split = 0.0f; nl.left = -1; nl.depth = parent.depth + 1; nl.value = vl; nl.pad = 0;
+    set_node_stats(nl, sl);
+    DNode nr = nl; nr.value = vr; set_node_stats(nr, sr);
+    S->nodes[nn] = nl; S->nodes[nn + 1] = nr;
+    S->n_nodes = nn + 2;
+    double ssq = BK_DADD(BK_DADD(BK_DSUB(S->ssq, c_parent), bk_leaf_ssq(sl, vl, P.inv_qscale)), bk_leaf_ssq(sr, vr, P.inv_qscale));
+    S->ssq = ssq;
+    S->lw = bk_normal_loglik(ssq, ctl->sigma, (double)P.N);
+    S->row = jb.dst_row;
+    atomicAdd(&ctl->c_grow, 1);
+    if (jb.src_row == BK_ROW_VIRTUAL) atomicAdd(&ctl->c_grow_root, 1);
+    bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + q - 1);
+    if (rec) { rec->var = jb.var; rec->split = jb.split; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
+  }
+  __syncthreads();
+}
+
+__device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot /* smem, [P] */) {
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (int s = warp; s < P.P; s += nwarps) {
+    const DParticle* src = part_ptr(P, c, buf, anc_of_slot[s]);
+    DParticle* dst = part_ptr(P, c, buf ^ 1, s);
+    const int nn = src->n_nodes;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const int words = 2 + nn * 4;
+    for (int i = lane; i < words; i += 32) d4[i] = s4[i];
+  }
+  __syncthreads();
+}
+
+__device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
+  const int buf = ctl->buf, t = ctl->cur_tree;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)ctl->draw;
+  if ((int)threadIdx.x < P.P) sh.lw[threadIdx.x] = part_ptr(P, c, buf, threadIdx.x)->lw;
+  __syncthreads();
+  double uf = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
+  normalise_and_resample(sh, 0, P.P, uf);
+  if (threadIdx.x == 0) {
+    unsigned pick = bk_index(bk_rng(S0, C0, D0, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P.P);
+    sh.pick = pick; sh.win = sh.anc[pick];
+  }
+  __syncthreads();
+  const int win = sh.win;
+  const DParticle* W = part_ptr(P, c, buf, win);
+  DNode* ft = P.forest + ((size_t)c * P.m + t) * BK_MAX_NODES;
+  const int old_nn = P.forest_nn[(size_t)c * P.m + t];
+  const int new_nn = W->n_nodes;
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+    ctl->old_vals[k] = (k < old_nn && ft[k].var < 0) ? ft[k].value : 0.0f;
+    ctl->new_vals[k] = (k < new_nn && W->nodes[k].var < 0) ? W->nodes[k].value : 0.0f;
+  }
+  __syncthreads();
+  {
+    const uint4* s4 = reinterpret_cast<const uint4*>(W->nodes);
+    uint4* d4 = reinterpret_cast<uint4*>(ft);
+    for (int i = threadIdx.x; i < new_nn * 4; i += blockDim.x) d4[i] = s4[i];
+  }
+  zero_acc0(P, c);
+  if (threadIdx.x == 0) {
+    P.forest_nn[(size_t)c * P.m + t] = new_nn;
+    double* av = P.alpha_vec + (size_t)c * P.p;
+    if (ctl->tune) {
+      if (ctl->iter > P.m) rebuild_cum_dev(P, c);
+      for (int k = 0; k < new_nn; ++k) { int v = W->nodes[k].var; if (v >= 0) av[v] = BK_DADD(av[v], 1.0); }
+    } else {
+      int32_t* vi = P.vi + (size_t)c * P.p;
+      for (int k = 0; k < new_nn; ++k) { int v = W->nodes[k].var; if (v >= 0) vi[v] += 1; }
+    }
+    SweepJob sj; memset(&sj, 0, sizeof(sj));
+    sj.do_commit = 1; sj.commit_tree = t; sj.new_row = W->row; sj.do_welford = ctl->tune ? 1 : 0;
+    sj.wf_count = ctl->wf_count + (ctl->tune ? 1 : 0);
+    sj.do_prologue = (t + 1 < ctl->tree_hi) ? 1 : 0; sj.prologue_tree = t + 1;
+    ctl->sweep = sj;
+    ctl->cmd = BK_CMD_SWEEP; ctl->stage = BK_ST_WAIT_SWEEP;
+    // kind-2 trace record is completed after the sweep (leaf_sd); stash its fields now
+    bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base);
+    if (rec) {
+      bk_trace_rec r; memset(&r, 0, sizeof(r));
+      r.kind = 2; r.tree = t; r.round = ctl->round; r.particle = win; r.node = new_nn; r.var = -1;
+      r.ancestor = (int32_t)sh.pick; r.log_w = W->lw;
+      *rec = r;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ void control_step(const Params& P, int c, int first_phase, int tune, const float* sigma_in, CtlShared& sh) {
+  ChainCtl* ctl = P.ctl + c;
+  __shared__ int s_stage;
+  if (threadIdx.x == 0) {
+    if (first_phase) {
+      ctl->stage = BK_ST_START; ctl->tune = tune; ctl->sigma = sigma_in[c];
+    }
+    s_stage = ctl->stage;
+  }
+  __syncthreads();
+  int stage = s_stage;
+  if (stage == BK_ST_DONE) return;
+  if (threadIdx.x == 0) ctl->c_phases += 1;
+
+  if (stage == BK_ST_START) {
+    for (int v = threadIdx.x; v < P.p; v += blockDim.x) P.vi[(size_t)c * P.p + v] = 0;
+    zero_acc0(P, c);
+    if (threadIdx.x == 0) {
+      int T = ctl->tune ? P.batch_tune : P.batch_post;
+      int lo = ctl->lower, hi = lo + T < P.m ? lo + T : P.m;
+      ctl->tree_lo = lo; ctl->tree_hi = hi; ctl->cur_tree = lo;
+      ctl->c_tree_updates = 0; ctl->c_rounds = 0; ctl->c_grow = 0; ctl->c_grow_root = 0;
+      ctl->c_count_passes = 0; ctl->c_phases = 1; ctl->c_err = 0;
+      ctl->trace_len = 0; ctl->trace_round_base = 0;
+      SweepJob sj; memset(&sj, 0, sizeof(sj));
+      sj.do_prologue = 1; sj.prologue_tree = lo;
+      ctl->sweep = sj; ctl->cmd = BK_CMD_SWEEP; ctl->stage = BK_ST_WAIT_SWEEP;
+    }
+    __syncthreads();
+    return;
+  }
+
+  bool have_round = false;
+  if (stage == BK_ST_WAIT_SWEEP) {
+    __shared__ int s_more;
+    if (threadIdx.x == 0) {
+      const SweepJob sj = ctl->sweep;
+      if (sj.do_commit) {
+        if (ctl->tune) {
+          ctl->wf_count = sj.wf_count;
+          if (ctl->iter > 2) {
+            long long sd_sum = (long long)__ldcg(P.acc0 + (size_t)c * BK_ACC0_WORDS + (size_t)256 * BK_ACC0_STRIDE);
+            ctl->leaf_sd = (float)BK_DDIV(BK_DMUL((double)sd_sum, P.inv_qscale), (double)P.N);
+          }
+        }
+        ctl->c_tree_updates += 1;
+        bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base);
+        if (rec) rec->aux = (double)ctl->leaf_sd;
+        ctl->trace_round_base += 1;
+      }
+      if (sj.do_prologue) {
+        ctl->iter += 1; ctl->cur_tree = sj.prologue_tree; s_more = 1;
+      } else {
+        s_more = 0;
+        ctl->lower = ctl->tree_hi < P.m ? ctl->tree_hi : 0;
+        ctl->draw += 1;
+        ctl->cmd = BK_CMD_DONE; ctl->stage = BK_ST_DONE;
+        bk_step_stats st; memset(&st, 0, sizeof(st));
+        st.tree_updates = ctl->c_tree_updates; st.rounds = ctl->c_rounds; st.grow_events = ctl->c_grow;
+        st.grow_root = ctl->c_grow_root; st.count_passes = ctl->c_count_passes; st.phases = ctl->c_phases;
+        st.trace_len = ctl->trace_round_base; st.error_flags = ctl->c_err | (ctl->trace_round_base > P.trace_cap && P.trace_cap > 0 ? 1 : 0);
+        st.leaf_sd = ctl->leaf_sd; st.iter = ctl->iter;
+        P.stats[c] = st;
+      }
+    }
+    __syncthreads();
+    if (!s_more) return;
+    init_particles(P, c, ctl, sh);
+  } else {  // BK_ST_WAIT_ROUND
+    finalize_grows(P, c, ctl);
+    have_round = true;
+  }
+
+  for (;;) {
+    if (have_round) {
+      // the round ctl->round is complete: log weights, liveness, resampling
+      const int buf = ctl->buf;
+      if (threadIdx.x == 0) { sh.live = 0; ctl->c_rounds += 1; }
+      __syncthreads();
+      if (threadIdx.x >= 1 && (int)threadIdx.x < P.P) {
+        const DParticle* S = part_ptr(P, c, buf, threadIdx.x);
+        sh.lw[threadIdx.x] = S->lw;
+        if (S->q_head < S->n_nodes) sh.live = 1;
+        bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + threadIdx.x - 1);
+        if (rec) rec->log_w = S->lw;
+      }
+      __syncthreads();
+      const int live = sh.live;
+      const int rbase = ctl->trace_round_base;
+      __syncthreads();
+      if (threadIdx.x == 0) ctl->trace_round_base = rbase + (P.P - 1);
+      if (!live) { __syncthreads(); finish_tree(P, c, ctl, sh); return; }
+      double u = bk_u01(bk_rng(P.seed, P.chain_base + (uint32_t)c, (uint32_t)ctl->draw, 0, (uint32_t)ctl->cur_tree,
+                               (uint32_t)ctl->round, 0, BK_U_RESAMPLE).v[0]);
+      normalise_and_resample(sh, 1, P.P - 1, u);
+      // anc[i] indexes particles 1..P-1; convert to slot -> source slot
+      __shared__ int s_src[BK_MAX_PARTICLES];
+      if ((int)threadIdx.x < P.P) {
+        int s = threadIdx.x;
+        s_src[s] = s == 0 ? 0 : sh.anc[s - 1] + 1;
+        if (s >= 1) { bk_trace_rec* rec = trace_at(P, c, rbase + s - 1); if (rec) rec->ancestor = s_src[s]; }
+      }
+      __syncthreads();
+      copy_particles(P, c, buf, s_src);
+      if (threadIdx.x == 0) { ctl->buf = buf ^ 1; ctl->round += 1; }
+      __syncthreads();
+    }
+    int nj = propose(P, c, ctl, sh);
+    have_round = true;
+    if (nj > 0) {
+      if (threadIdx.x == 0) { ctl->cmd = BK_CMD_ROUND; ctl->stage = BK_ST_WAIT_ROUND; }
+      __syncthreads();
+      return;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ data phase: ROUND
+__device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi) {
+  const int lane = threadIdx.x & 31;
+  const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
+  const ChainCtl* ctl = P.ctl + c;
+  int q_r[8], q_s[8];
+  {
+    const int4* a = reinterpret_cast<const int4*>(P.qr + (size_t)c * P.Npad + base);
+    const int4* b = reinterpret_cast<const int4*>(P.qst + (size_t)c * P.Npad + base);
+    int4 a0 = __ldcg(a), a1 = __ldcg(a + 1), b0 = __ldcg(b), b1 = __ldcg(b + 1);
+    q_r[0] = a0.x; q_r[1] = a0.y; q_r[2] = a0.z; q_r[3] = a0.w; q_r[4] = a1.x; q_r[5] = a1.y; q_r[6] = a1.z; q_r[7] = a1.w;
+    q_s[0] = b0.x; q_s[1] = b0.y; q_s[2] = b0.z; q_s[3] = b0.w; q_s[4] = b1.x; q_s[5] = b1.y; q_s[6] = b1.z; q_s[7] = b1.w;
+  }
+  for (int ji = job_lo; ji < job_hi; ++ji) {
+    const int4* jp = reinterpret_cast<const int4*>(&ctl->jobs[ji]);
+    const int4 j0 = __ldcg(jp), j1 = __ldcg(jp + 1), j2 = __ldcg(jp + 2);
+    const int kind = j0.x, slot = j0.y, src_row = j0.z, dst_row = j0.w;
+    const int node = j1.x, var = j1.y; const float split = __int_as_float(j1.z); const int left_id = j1.w;
+    const int next_node = j2.x, rule = j2.y;
+    unsigned long long ids;
+    if (src_row == BK_ROW_VIRTUAL) {
+      ids = 0ull;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) if (base + e >= (size_t)P.N) ids |= 0xFFull << (8 * e);
+    } else {
+      ids = __ldcg(reinterpret_cast<const unsigned long long*>(P.rows + ((size_t)c * P.R + src_row) * P.Npad + base));
+    }
+    unsigned cnt_next = 0;
+    if (kind == BK_JOB_PARTITION) {
+      unsigned mm = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mm |= (((unsigned)(ids >> (8 * e)) & 255u) == (unsigned)node) ? (1u << e) : 0u;
+      unsigned lm = 0;
+      if (mm) {
+        const float4* xp = reinterpret_cast<const float4*>(P.X + (size_t)var * P.Npad + base);
+        const float4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
+        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          bool l = rule == BK_RULE_ONEHOT ? (xs[e] == split) : (xs[e] <= split);
+          lm |= l ? (1u << e) : 0u;
+        }
+        lm &= mm;
+      }
+      unsigned long long nids = 0ull;
+      int cl = 0;
+      long long a_st = 0, a_r = 0;
+      unsigned long long a_r2 = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        unsigned id = (unsigned)(ids >> (8 * e)) & 255u;
+        const bool mem = (mm >> e) & 1u, l = (lm >> e) & 1u;
+        unsigned nid = mem ? (unsigned)(l ? left_id : left_id + 1) : id;
+        nids |= (unsigned long long)nid << (8 * e);
+        cnt_next += (nid == (unsigned)next_node) ? 1u : 0u;
+        const int qm = l ? q_r[e] : 0;
+        cl += l ? 1 : 0;
+        a_st += l ? (long long)q_s[e] : 0ll;
+        a_r += (long long)qm;
+        a_r2 += (unsigned long long)((long long)qm * (long long)qm);
+      }
+      __stcg(reinterpret_cast<unsigned long long*>(P.rows + ((size_t)c * P.R + dst_row) * P.Npad + base), nids);
+      if (__any_sync(0xffffffffu, lm != 0)) {
+        unsigned n_tot = __reduce_add_sync(0xffffffffu, (unsigned)cl);
+        unsigned long long s_st = warp_sum_u64((unsigned long long)a_st);
+        unsigned long long s_r = warp_sum_u64((unsigned long long)a_r);
+        unsigned long long s_lo = warp_sum_u64(a_r2 & 0xFFFFFFFFull);
+        unsigned long long s_hi = warp_sum_u64(a_r2 >> 32);
+        if (lane == 0) {
+          unsigned long long* acc = P.accL + ((size_t)c * P.P + slot) * BK_ACC_STRIDE;
+          red_add_u64(acc + BK_ACC_N, (unsigned long long)n_tot);
+          red_add_u64(acc + BK_ACC_SST, s_st);
+          red_add_u64(acc + BK_ACC_SR, s_r);
+          red_add_u64(acc + BK_ACC_SR2LO, s_lo);
+          red_add_u64(acc + BK_ACC_SR2HI, s_hi);
+        }
+      }
+      if (next_node >= 0) {
+        unsigned tot = __reduce_add_sync(0xffffffffu, cnt_next);
+        if (lane == 0) P.rowcnt[((size_t)c * P.R + dst_row) * P.ntiles + tile] = tot;
+      }
+    } else {  // BK_JOB_COUNT
+#pragma unroll
+      for (int e = 0; e < 8; ++e) cnt_next += (((unsigned)(ids >> (8 * e)) & 255u) == (unsigned)next_node) ? 1u : 0u;
+      unsigned tot = __reduce_add_sync(0xffffffffu, cnt_next);
+      if (lane == 0) P.rowcnt[((size_t)c * P.R + src_row) * P.ntiles + tile] = tot;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ data phase: SWEEP
+// CTA-wide: 1024 threads x 4 rows.  Fuses commit of tree A with prologue of tree B.
+__device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
+  const ChainCtl* ctl = P.ctl + c;
+  const int4 s0 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep));
+  const int4 s1 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep) + 1);
+  const int do_commit = s0.x, commit_tree = s0.y, new_row = s0.z, do_wf = s0.w;
+  const int do_pro = s1.x, pro_tree = s1.y, wf_count = s1.z;
+  // stage leaf-value tables
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+    sh.old_vals[k] = do_commit ? __ldcg(&ctl->old_vals[k]) : 0.0f;
+    sh.new_vals[k] = do_commit ? __ldcg(&ctl->new_vals[k]) : 0.0f;
+    float pv = 0.0f;
+    if (do_pro && k < 255) {
+      const DNode* nd = P.forest + ((size_t)c * P.m + pro_tree) * BK_MAX_NODES + k;
+      int nn = __ldcg(P.forest_nn + (size_t)c * P.m + pro_tree);
+      if (k < nn) { int var = __ldcg(&nd->var); pv = var < 0 ? __ldcg(&nd->value) : 0.0f; }
+    }
+    sh.pro_vals[k] = pv;
+  }
+  for (int k = threadIdx.x; k < 256 * 3; k += blockDim.x) sh.leaf_acc[k] = 0ull;
+  if (threadIdx.x < 8) sh.tot_acc[threadIdx.x] = 0ull;
+  __syncthreads();
+
+  const size_t base = (size_t)ctile * BK_COMMIT_TILE + (size_t)threadIdx.x * 4;
+  long long t_sst = 0, t_sr = 0, t_sd = 0;
+  unsigned long long t_r2 = 0;
+  if (base < (size_t)P.Npad) {
+    float* stp = P.st + (size_t)c * P.Npad + base;
+    float4 st4 = __ldcg(reinterpret_cast<const float4*>(stp));
+    float stv[4] = {st4.x, st4.y, st4.z, st4.w};
+    if (do_commit) {
+      uint8_t* idp = P.ids_tree + ((size_t)c * P.m + commit_tree) * P.Npad + base;
+      unsigned oid4 = __ldcg(reinterpret_cast<const unsigned*>(idp));
+      unsigned nid4;
+      if (new_row == BK_ROW_FOREST) nid4 = oid4;
+      else if (new_row == BK_ROW_VIRTUAL) {
+        nid4 = 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (base + e >= (size_t)P.N) nid4 |= 0xFFu << (8 * e);
+      } else nid4 = __ldcg(reinterpret_cast<const unsigned*>(P.rows + ((size_t)c * P.R + new_row) * P.Npad + base));
+      float4 mean4, m24;
+      float* mp = P.wf_mean + (size_t)c * P.Npad + base;
+      float* m2p = P.wf_m2 + (size_t)c * P.Npad + base;
+      if (do_wf) { mean4 = __ldcg(reinterpret_cast<const float4*>(mp)); m24 = __ldcg(reinterpret_cast<const float4*>(m2p)); }
+      float mean[4] = {mean4.x, mean4.y, mean4.z, mean4.w}, m2[4] = {m24.x, m24.y, m24.z, m24.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        unsigned oid = (oid4 >> (8 * e)) & 255u, nid = (nid4 >> (8 * e)) & 255u;
+        float oldp = sh.old_vals[oid], newp = sh.new_vals[nid];  // entry 255 (limbo) is 0
+        float noi = BK_FSUB(stv[e], oldp);
+        stv[e] = BK_FADD(noi, newp);
+        if (do_wf && base + e < (size_t)P.N) {
+          float cntf = (float)wf_count;
+          float delta = BK_FSUB(newp, mean[e]);
+          float mn = BK_FADD(mean[e], BK_FDIV(delta, cntf));
+          float delta2 = BK_FSUB(newp, mn);
+          float mm2 = BK_FFMA(delta, delta2, m2[e]);
+          mean[e] = mn; m2[e] = mm2;
+          float sd = BK_FSQRT(BK_FDIV(mm2, cntf));
+          t_sd += (long long)bk_quant(sd, P.qscale);
+        }
+      }
+      __stcg(reinterpret_cast<float4*>(stp), make_float4(stv[0], stv[1], stv[2], stv[3]));
+      if (new_row != BK_ROW_FOREST) __stcg(reinterpret_cast<unsigned*>(idp), nid4);
+      if (do_wf) {
+        __stcg(reinterpret_cast<float4*>(mp), make_float4(mean[0], mean[1], mean[2], mean[3]));
+        __stcg(reinterpret_cast<float4*>(m2p), make_float4(m2[0], m2[1], m2[2], m2[3]));
+      }
+    }
+    if (do_pro) {
+      unsigned pid4 = __ldcg(reinterpret_cast<const unsigned*>(P.ids_tree + ((size_t)c * P.m + pro_tree) * P.Npad + base));
+      float4 y4 = __ldg(reinterpret_cast<const float4*>(P.y + base));
+      float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+      int qrv[4], qsv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        unsigned pid = (pid4 >> (8 * e)) & 255u;
+        float oldp = sh.pro_vals[pid];
+        float noi = BK_FSUB(stv[e], oldp);
+        float r = BK_FSUB(yv[e], noi);
+        int a = bk_quant(r, P.qscale), b = bk_quant(stv[e], P.qscale);
+        if (base + e >= (size_t)P.N) { a = 0; b = 0; }
+        qrv[e] = a; qsv[e] = b;
+        if (base + e < (size_t)P.N) {
+          unsigned long long sq = (unsigned long long)((long long)a * (long long)a);
+          t_sst += b; t_sr += a; t_r2 += sq;
+          if (pid != BK_LIMBO) {
+            atomicAdd(&sh.leaf_acc[pid * 3 + 0], (unsigned long long)(long long)a);
+            atomicAdd(&sh.leaf_acc[pid * 3 + 1], sq & 0xFFFFFFFFull);
+            atomicAdd(&sh.leaf_acc[pid * 3 + 2], sq >> 32);
+          }
+        }
+      }
+      __stcg(reinterpret_cast<int4*>(P.qr + (size_t)c * P.Npad + base), make_int4(qrv[0], qrv[1], qrv[2], qrv[3]));
+      __stcg(reinterpret_cast<int4*>(P.qst + (size_t)c * P.Npad + base), make_int4(qsv[0], qsv[1], qsv[2], qsv[3]));
+    }
+  }
+  // block totals
+  {
+    unsigned long long v0 = warp_sum_u64((unsigned long long)t_sr);
+    unsigned long long v1 = warp_sum_u64(t_r2 & 0xFFFFFFFFull);
+    unsigned long long v2 = warp_sum_u64(t_r2 >> 32);
+    unsigned long long v3 = warp_sum_u64((unsigned long long)t_sst);
+    unsigned long long v4 = warp_sum_u64((unsigned long long)t_sd);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sh.tot_acc[0], v0); atomicAdd(&sh.tot_acc[1], v1); atomicAdd(&sh.tot_acc[2], v2);
+      atomicAdd(&sh.tot_acc[3], v3); atomicAdd(&sh.tot_acc[4], v4);
+    }
+  }
+  __syncthreads();
+  unsigned long long* a0 = P.acc0 + (size_t)c * BK_ACC0_WORDS;
+  if (do_pro) {
+    for (int k = threadIdx.x; k < 255 * 3; k += blockDim.x) {
+      unsigned long long v = sh.leaf_acc[k];
+      if (v) red_add_u64(a0 + (size_t)(k / 3) * BK_ACC0_STRIDE + (k % 3), v);
+    }
+    if (threadIdx.x < 4) { unsigned long long v = sh.tot_acc[threadIdx.x]; if (v) red_add_u64(a0 + (size_t)255 * BK_ACC0_STRIDE + threadIdx.x, v); }
+  }
+  if (do_commit && do_wf && threadIdx.x == 0) { unsigned long long v = sh.tot_acc[4]; if (v) red_add_u64(a0 + (size_t)256 * BK_ACC0_STRIDE, v); }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ the step kernel
+__global__ void __launch_bounds__(BK_CTA_THREADS, 1)
+pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sigma_in, const int max_phases) {
+  __shared__ KernelShared sh;
+  __shared__ int s_abort;
+  unsigned target = 0;
+  const int nwarps_cta = blockDim.x >> 5;
+  const int total_warps = gridDim.x * nwarps_cta;
+  const int gwarp = blockIdx.x * nwarps_cta + (threadIdx.x >> 5);
+  const int sweep_tiles = (P.Npad + BK_COMMIT_TILE - 1) / BK_COMMIT_TILE;
+
+  for (int phase = 0; phase < max_phases; ++phase) {
+    // ---- control
+    for (int c = blockIdx.x; c < P.C; c += gridDim.x) control_step(P, c, phase == 0, tune, sigma_in, sh.ctl);
+    if (grid_sync(P, target, &s_abort)) return;
+    // ---- plan the data phase (every CTA builds the same small table)
+    if (threadIdx.x == 0) {
+      int done = 1, ru = 0, su = 0;
+      long long pt = 0;
+      for (int c = 0; c < P.C; ++c) {
+        int cmd = __ldcg(&P.ctl[c].cmd);
+        int nj = cmd == BK_CMD_ROUND ? __ldcg(&P.ctl[c].n_jobs) : 0;
+        sh.data.cmd[c] = cmd; sh.data.njobs[c] = nj;
+        if (cmd != BK_CMD_DONE) done = 0;
+        pt += (long long)nj * P.ntiles;
+      }
+      long long g = pt / (2ll * total_warps);
+      int G = g < 1 ? 1 : (g > BK_MAX_GROUP ? BK_MAX_GROUP : (int)g);
+      for (int c = 0; c < P.C; ++c) {
+        int ng = (sh.data.njobs[c] + G - 1) / G;
+        sh.data.ngroups[c] = ng;
+        sh.data.ru_base[c] = ru; ru += ng * P.ntiles;
+        sh.data.su_base[c] = su; su += sh.data.cmd[c] == BK_CMD_SWEEP ? sweep_tiles : 0;
+      }
+      sh.data.ru_base[P.C] = ru; sh.data.su_base[P.C] = su;
+      sh.data.group = G; sh.data.all_done = done;
+    }
+    __syncthreads();
+    if (sh.data.all_done) break;
+    // ---- data: sweeps (CTA granular)
+    {
+      const int su_total = sh.data.su_base[P.C];
+      for (int u = blockIdx.x; u < su_total; u += gridDim.x) {
+        int c = 0;
+        while (u >= sh.data.su_base[c + 1]) ++c;
+        sweep_unit(P, c, u - sh.data.su_base[c], sh.data);
+      }
+    }
+    // ---- data: rounds (warp granular)
+    {
+      const int ru_total = sh.data.ru_base[P.C];
+      const int G = sh.data.group;
+      for (int u = gwarp; u < ru_total; u += total_warps) {
+        int c = 0;
+        while (u >= sh.data.ru_base[c + 1]) ++c;
+        const int local = u - sh.data.ru_base[c];
+        const int tile = local % P.ntiles, g = local / P.ntiles;
+        const int lo = g * G;
+        const int hi = lo + G < sh.data.njobs[c] ? lo + G : sh.data.njobs[c];
+        round_unit(P, c, tile, lo, hi);
+      }
+    }
+    if (grid_sync(P, target, &s_abort)) return;
+  }
+}
+
+// ------------------------------------------------------------------ init kernel
+__global__ void pgbart_init_kernel(const Params P, const float init_sum, const float leaf_sd_init,
+                                   const double* __restrict__ split_prior) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nth = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = tid; i < (size_t)P.C * P.Npad; i += nth) {
+    size_t r = i % P.Npad;
+    P.st[i] = r < (size_t)P.N ? init_sum : 0.0f;
+    P.wf_mean[i] = 0.0f; P.wf_m2[i] = 0.0f; P.qr[i] = 0; P.qst[i] = 0;
+  }
+  for (size_t i = tid; i < (size_t)P.C * P.m * P.Npad; i += nth) {
+    size_t r = i % P.Npad;
+    P.ids_tree[i] = r < (size_t)P.N ? 0 : BK_LIMBO;
+  }
+  for (size_t i = tid; i < (size_t)P.C * P.R * P.ntiles; i += nth) P.rowcnt[i] = 0u;
+  for (size_t i = tid; i < (size_t)P.C * P.P * BK_ACC_STRIDE; i += nth) P.accL[i] = 0ull;
+  for (size_t i = tid; i < (size_t)P.C * BK_ACC0_WORDS; i += nth) P.acc0[i] = 0ull;
+  for (size_t i = tid; i < (size_t)P.C * P.m; i += nth) {
+    P.forest_nn[i] = 1;
+    DNode nd; memset(&nd, 0, sizeof(nd));
+    nd.var = -1; nd.left = -1; nd.value = P.init_leaf; nd.n = P.N;
+    P.forest[i * BK_MAX_NODES] = nd;
+  }
+  for (size_t i = tid; i < (size_t)P.C * P.p; i += nth) { P.alpha_vec[i] = split_prior[i % P.p]; P.vi[i] = 0; }
+  for (size_t c = tid; c < (size_t)P.C; c += nth) {
+    ChainCtl* ctl = P.ctl + c;
+    ctl->tune = 1; ctl->sigma = 1.0f; ctl->iter = 0; ctl->lower = 0; ctl->draw = 0; ctl->wf_count = 0;
+    ctl->leaf_sd = leaf_sd_init; ctl->stage = BK_ST_DONE; ctl->cmd = BK_CMD_DONE; ctl->n_jobs = 0;
+    ctl->c_err = 0; ctl->trace_round_base = 0;
+    memset(&P.stats[c], 0, sizeof(bk_step_stats));
+  }
+  if (tid == 0) { *P.barrier = 0u; *P.abort_flag = 0; }
+}
+__global__ void pgbart_init_cum_kernel(const Params P) {
+  int c = blockIdx.x;
+  if (threadIdx.x == 0 && c < P.C) rebuild_cum_dev(P, c);
+}
+
+// ------------------------------------------------------------------ prediction kernel (row N1)
+// one thread per (draw, row); iterative weighted descent with a small explicit stack
+__global__ void pgbart_predict_kernel(const bk_node* __restrict__ forests, int n_trees, const float* __restrict__ X,
+                                      int n, int n_cols, const int32_t* __restrict__ draw_idx, int n_idx,
+                                      const uint8_t* __restrict__ excl, const int32_t* __restrict__ rules,
+                                      float* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)n_idx * n) return;
+  const int d = (int)(gid / n), i = (int)(gid % n);
+  const bk_node* f = forests + (size_t)draw_idx[d] * n_trees * BK_MAX_NODES;
+  const float* x = X + (size_t)i * n_cols;
+  double acc = 0.0;
+  for (int t = 0; t < n_trees; ++t) {
+    const bk_node* nodes = f + (size_t)t * BK_MAX_NODES;
+    // explicit post-order evaluation: value(node) = wl*value(l) + wr*value(r) only at excluded splits.
+    // Stack entries: (node, weight) — equivalent to the recursion because the map is linear.
+    int sn[48]; double sw[48]; int sp = 0;
+    sn[0] = 0; sw[0] = 1.0; sp = 1;
+    double tv = 0.0;
+    // NOTE: summation order differs from a recursive formulation only when >1 excluded split is met;
+    // the oracle uses the same stack discipline (left pushed last, popped first).
+    while (sp > 0) {
+      --sp; int k = sn[sp]; double w = sw[sp];
+      const bk_node nd = nodes[k];
+      if (nd.var < 0) { tv = BK_DFMA(w, (double)nd.value, tv); continue; }
+      const int l = nd.left, r = nd.left + 1;
+      if (excl && excl[nd.var]) {
+        double tot = (double)nodes[l].n + (double)nodes[r].n;
+        if (!(tot > 0.0) || sp + 2 > 48) continue;
+        double wl = BK_DDIV((double)nodes[l].n, tot);
+        double wr = BK_DSUB(1.0, wl);
+        sn[sp] = r; sw[sp] = BK_DMUL(w, wr); ++sp;
+        sn[sp] = l; sw[sp] = BK_DMUL(w, wl); ++sp;
+      } else {
+        float xv = x[nd.var];
+        bool left = (rules && rules[nd.var] == BK_RULE_ONEHOT) ? (xv == nd.split) : (xv <= nd.split);
+        sn[sp] = left ? l : r; sw[sp] = w; ++sp;
+      }
+    }
+    acc = BK_DADD(acc, tv);
+  }
+  out[(size_t)d * n + i] = (float)acc;
+}
+
+// ==================================================================== host side / C ABI
+static thread_local char g_err[512] = "";
+static void set_err(const char* fmt, const char* a = "", const char* b = "") { snprintf(g_err, sizeof(g_err), fmt, a, b); }
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) { set_err("CUDA error %s at %s", cudaGetErrorString(e_), #call); return BK_ERR_CUDA; } \
+  } while (0)
+
+struct bk_handle_s {
+  bk_settings s;
+  Params P;
+  cudaStream_t stream;
+  int grid;
+  int max_phases;
+  float* sigma_dev;
+  double* split_prior_dev;
+  int32_t* vi_pinned;
+  bk_step_stats* stats_pinned;
+  float* sigma_pinned;
+  int32_t* abort_pinned;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+  size_t qr, qst, ids_tree, rows, rowcnt, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, alpha_vec, cum,
+      p_leaf, rules, vi, stats, trace, barrier, abort_flag, sigma, split_prior, total;
+  int Npad, ntiles, R;
+};
+
+static int make_layout(const bk_settings* s, Layout* L) {
+  if (!s || s->abi_version != BK_ABI_VERSION) { set_err("bk_settings.abi_version mismatch"); return BK_ERR_ARG; }
+  if (s->n_rows < 1 || s->n_cols < 1 || s->n_trees < 1 || s->n_chains < 1) { set_err("empty problem"); return BK_ERR_ARG; }
+  if (s->n_particles < 2 || s->n_particles > BK_MAX_PARTICLES) { set_err("n_particles must be in [2,128]"); return BK_ERR_ARG; }
+  if (s->n_chains > 64) { set_err("at most 64 chains per handle"); return BK_ERR_ARG; }
+  if (s->n_trees > 65535) { set_err("n_trees must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
+  if (s->likelihood != BK_LIK_NORMAL) { set_err("likelihood not implemented on the device (no CPU fallback)"); return BK_ERR_UNSUPPORTED; }
+  if (!s->p_leaf || !s->split_prior) { set_err("p_leaf and split_prior are required"); return BK_ERR_ARG; }
+  const size_t C = s->n_chains, P = s->n_particles, m = s->n_trees, p = s->n_cols;
+  L->Npad = (int)align_up((size_t)s->n_rows, BK_WARP_TILE);
+  L->ntiles = L->Npad / BK_WARP_TILE;
+  L->R = 2 * s->n_particles;
+  const size_t Npad = L->Npad, R = L->R;
+  size_t o = 0;
+#define CARVE(name, bytes) L->name = o; o = align_up(o + (bytes), 256)
+  CARVE(qr, C * Npad * 4);
+  CARVE(qst, C * Npad * 4);
+  CARVE(ids_tree, C * m * Npad);
+  CARVE(rows, C * R * Npad);
+  CARVE(rowcnt, C * R * (size_t)L->ntiles * 4);
+  CARVE(wf_mean, C * Npad * 4);
+  CARVE(wf_m2, C * Npad * 4);
+  CARVE(parts, C * 2 * P * sizeof(DParticle));
+  CARVE(forest, C * m * BK_MAX_NODES * sizeof(DNode));
+  CARVE(forest_nn, C * m * 4);
+  CARVE(ctl, C * sizeof(ChainCtl));
+  CARVE(accL, C * P * BK_ACC_STRIDE * 8);
+  CARVE(acc0, C * BK_ACC0_WORDS * 8);
+  CARVE(alpha_vec, C * p * 8);
+  CARVE(cum, C * p * 8);
+  CARVE(p_leaf, 256 * 8);
+  CARVE(rules, p * 4);
+  CARVE(vi, C * p * 4);
+  CARVE(stats, C * sizeof(bk_step_stats));
+  CARVE(trace, C * (size_t)(s->trace_capacity > 0 ? s->trace_capacity : 0) * sizeof(bk_trace_rec));
+  CARVE(barrier, 256);
+  CARVE(abort_flag, 256);
+  CARVE(sigma, C * 4);
+  CARVE(split_prior, p * 8);
+#undef CARVE
+  L->total = o;
+  return BK_OK;
+}
+
+extern "C" {
+
+int bk_abi_version(void) { return BK_ABI_VERSION; }
+int bk_padded_rows(int n_rows) { return n_rows < 1 ? 0 : (int)align_up((size_t)n_rows, BK_WARP_TILE); }
+const char* bk_last_error(void) { return g_err; }
+
+int bk_query_bytes(const bk_settings* s, size_t* workspace_bytes) {
+  Layout L;
+  int rc = make_layout(s, &L);
+  if (rc != BK_OK) return rc;
+  if (!workspace_bytes) { set_err("workspace_bytes is NULL"); return BK_ERR_ARG; }
+  *workspace_bytes = L.total;
+  return BK_OK;
+}
+
+int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, float* sum_trees_dev, void* workspace_dev,
+              bk_handle** out) {
+  Layout L;
+  int rc = make_layout(s, &L);
+  if (rc != BK_OK) return rc;
+  if (!X_dev || !y_dev || !sum_trees_dev || !workspace_dev || !out) { set_err("NULL device pointer"); return BK_ERR_ARG; }
+  if (((uintptr_t)X_dev | (uintptr_t)y_dev | (uintptr_t)sum_trees_dev | (uintptr_t)workspace_dev) & 15) {
+    set_err("device pointers must be 16-byte aligned"); return BK_ERR_ARG;
+  }
+  CK(cudaSetDevice(s->device));
+  bk_handle* h = new (std::nothrow) bk_handle();
+  if (!h) { set_err("out of host memory"); return BK_ERR_ARG; }
+  memset(h, 0, sizeof(*h));
+  h->s = *s;
+  char* w = (char*)workspace_dev;
+  Params& P = h->P;
+  P.N = s->n_rows; P.Npad = L.Npad; P.p = s->n_cols; P.m = s->n_trees; P.P = s->n_particles; P.C = s->n_chains;
+  P.R = L.R; P.ntiles = L.ntiles; P.lik = s->likelihood; P.trace_cap = s->trace_capacity > 0 ? s->trace_capacity : 0;
+  P.batch_tune = s->batch_tune < 1 ? 1 : s->batch_tune; P.batch_post = s->batch_post < 1 ? 1 : s->batch_post;
+  P.qscale = ldexpf(1.0f, s->qshift); P.inv_qscale = ldexp(1.0, -s->qshift); P.init_leaf = s->init_leaf;
+  P.seed = s->seed; P.chain_base = s->chain_base;
+  P.X = X_dev; P.y = y_dev; P.st = sum_trees_dev;
+  P.qr = (int32_t*)(w + L.qr); P.qst = (int32_t*)(w + L.qst); P.ids_tree = (uint8_t*)(w + L.ids_tree);
+  P.rows = (uint8_t*)(w + L.rows); P.rowcnt = (uint32_t*)(w + L.rowcnt);
+  P.wf_mean = (float*)(w + L.wf_mean); P.wf_m2 = (float*)(w + L.wf_m2);
+  P.parts = (DParticle*)(w + L.parts); P.forest = (DNode*)(w + L.forest); P.forest_nn = (int32_t*)(w + L.forest_nn);
+  P.ctl = (ChainCtl*)(w + L.ctl); P.accL = (unsigned long long*)(w + L.accL); P.acc0 = (unsigned long long*)(w + L.acc0);
+  P.alpha_vec = (double*)(w + L.alpha_vec); P.cum = (double*)(w + L.cum); P.p_leaf = (double*)(w + L.p_leaf);
+  P.rules = (int32_t*)(w + L.rules); P.vi = (int32_t*)(w + L.vi); P.stats = (bk_step_stats*)(w + L.stats);
+  P.trace = (bk_trace_rec*)(w + L.trace); P.barrier = (unsigned int*)(w + L.barrier); P.abort_flag = (int32_t*)(w + L.abort_flag);
+  h->sigma_dev = (float*)(w + L.sigma); h->split_prior_dev = (double*)(w + L.split_prior);
+
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaMemcpyAsync(P.p_leaf, s->p_leaf, 256 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->split_prior_dev, s->split_prior, (size_t)P.p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  {
+    int32_t* rules_h = (int32_t*)calloc((size_t)P.p, sizeof(int32_t));
+    if (s->split_rules) memcpy(rules_h, s->split_rules, (size_t)P.p * sizeof(int32_t));
+    cudaError_t e = cudaMemcpyAsync(P.rules, rules_h, (size_t)P.p * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    free(rules_h);
+    CK(e);
+  }
+  CK(cudaMallocHost(&h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t)));
+  CK(cudaMallocHost(&h->stats_pinned, (size_t)P.C * sizeof(bk_step_stats)));
+  CK(cudaMallocHost(&h->sigma_pinned, (size_t)P.C * sizeof(float)));
+  CK(cudaMallocHost(&h->abort_pinned, sizeof(int32_t)));
+
+  int dev = s->device, n_sm = 0, coop = 0, occ = 0;
+  CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop) { set_err("device lacks cooperative launch"); return BK_ERR_UNSUPPORTED; }
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgbart_step_kernel, BK_CTA_THREADS, 0));
+  if (occ < 1) { set_err("step kernel does not fit on an SM"); return BK_ERR_CUDA; }
+  h->grid = n_sm;  // one persistent CTA per SM (148 on B200)
+  h->max_phases = 1 << 20;
+
+  pgbart_init_kernel<<<n_sm * 2, 512, 0, h->stream>>>(P, s->init_sum, s->leaf_sd_init, h->split_prior_dev);
+  pgbart_init_cum_kernel<<<P.C, 32, 0, h->stream>>>(P);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return BK_OK;
+}
+
+void bk_destroy(bk_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->s.device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->vi_pinned) cudaFreeHost(h->vi_pinned);
+  if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
+  if (h->sigma_pinned) cudaFreeHost(h->sigma_pinned);
+  if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
+  delete h;
+}
+
+int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_host, bk_step_stats* stats_host) {
+  if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
+  CK(cudaSetDevice(h->s.device));
+  Params& P = h->P;
+  for (int c = 0; c < P.C; ++c) {
+    float sg = sigma_host ? sigma_host[c] : 1.0f;
+    if (!(sg > 0.0f)) { set_err("sigma must be positive"); return BK_ERR_ARG; }
+    h->sigma_pinned[c] = sg;
+  }
+  CK(cudaMemcpyAsync(h->sigma_dev, h->sigma_pinned, (size_t)P.C * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(P.barrier, 0, sizeof(unsigned int), h->stream));
+  int tune_i = tune ? 1 : 0;
+  const float* sig = h->sigma_dev;
+  int maxp = h->max_phases;
+  void* args[] = {(void*)&P, (void*)&tune_i, (void*)&sig, (void*)&maxp};
+  CK(cudaLaunchCooperativeKernel((const void*)pgbart_step_kernel, dim3(h->grid), dim3(BK_CTA_THREADS), args, 0, h->stream));
+  CK(cudaMemcpyAsync(h->vi_pinned, P.vi, (size_t)P.C * P.p * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->stats_pinned, P.stats, (size_t)P.C * sizeof(bk_step_stats), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->abort_pinned, P.abort_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (*h->abort_pinned) { set_err("grid barrier timed out inside the step kernel"); return BK_ERR_TIMEOUT; }
+  if (vi_counts_host) memcpy(vi_counts_host, h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t));
+  if (stats_host) memcpy(stats_host, h->stats_pinned, (size_t)P.C * sizeof(bk_step_stats));
+  for (int c = 0; c < P.C; ++c)
+    if (h->stats_pinned[c].error_flags & ~1) { set_err("device-side consistency check failed"); return BK_ERR_STATE; }
+  return BK_OK;
+}
+
+int bk_read_trace(bk_handle* h, int chain, bk_trace_rec* out_host, int capacity) {
+  if (!h || chain < 0 || chain >= h->P.C || !out_host) { set_err("bad argument"); return BK_ERR_ARG; }
+  if (cudaSetDevice(h->s.device) != cudaSuccess) return BK_ERR_CUDA;
+  int n = h->stats_pinned[chain].trace_len;
+  if (n > h->P.trace_cap) n = h->P.trace_cap;
+  if (n > capacity) n = capacity;
+  if (n <= 0) return 0;
+  cudaError_t e = cudaMemcpy(out_host, h->P.trace + (size_t)chain * h->P.trace_cap, (size_t)n * sizeof(bk_trace_rec), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { set_err("CUDA error %s in bk_read_trace", cudaGetErrorString(e)); return BK_ERR_CUDA; }
+  return n;
+}
+
+int bk_export_forest(bk_handle* h, int chain, bk_node* nodes_host, int32_t* n_nodes_host) {
+  if (!h || chain < 0 || chain >= h->P.C || !nodes_host || !n_nodes_host) { set_err("bad argument"); return BK_ERR_ARG; }
+  CK(cudaSetDevice(h->s.device));
+  const Params& P = h->P;
+  size_t cnt = (size_t)P.m * BK_MAX_NODES;
+  DNode* tmp = (DNode*)malloc(cnt * sizeof(DNode));
+  if (!tmp) { set_err("out of host memory"); return BK_ERR_ARG; }
+  cudaError_t e = cudaMemcpy(tmp, P.forest + (size_t)chain * cnt, cnt * sizeof(DNode), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(n_nodes_host, P.forest_nn + (size_t)chain * P.m, (size_t)P.m * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(tmp); set_err("CUDA error %s in bk_export_forest", cudaGetErrorString(e)); return BK_ERR_CUDA; }
+  for (int t = 0; t < P.m; ++t)
+    for (int k = 0; k < BK_MAX_NODES; ++k) {
+      bk_node* d = &nodes_host[(size_t)t * BK_MAX_NODES + k];
+      memset(d, 0, sizeof(*d));
+      if (k < n_nodes_host[t]) {
+        const DNode& sN = tmp[(size_t)t * BK_MAX_NODES + k];
+        d->var = sN.var; d->split = sN.split; d->left = sN.left; d->value = sN.var < 0 ? sN.value : 0.0f; d->n = sN.n; d->depth = sN.depth;
+      }
+    }
+  free(tmp);
+  return BK_OK;
+}
+
+int bk_export_leaf_ids(bk_handle* h, int chain, uint8_t* ids_host) {
+  if (!h || chain < 0 || chain >= h->P.C || !ids_host) { set_err("bad argument"); return BK_ERR_ARG; }
+  CK(cudaSetDevice(h->s.device));
+  const Params& P = h->P;
+  CK(cudaMemcpy2D(ids_host, (size_t)P.N, P.ids_tree + (size_t)chain * P.m * P.Npad, (size_t)P.Npad, (size_t)P.N, (size_t)P.m,
+                  cudaMemcpyDeviceToHost));
+  return BK_OK;
+}
+
+int bk_predict(int device, void* stream, const bk_node* forests_dev, const int32_t* n_nodes_dev, int n_trees, const float* X_dev,
+               int n, int n_cols, const int32_t* draw_idx_dev, int n_idx, const uint8_t* excluded_mask_dev,
+               const int32_t* split_rules_dev, float* out_dev) {
+  (void)n_nodes_dev;
+  if (!forests_dev || !X_dev || !draw_idx_dev || !out_dev || n < 0 || n_idx < 0) { set_err("bad argument"); return BK_ERR_ARG; }
+  CK(cudaSetDevice(device));
+  long long total = (long long)n * n_idx;
+  if (total == 0) return BK_OK;
+  int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  pgbart_predict_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(forests_dev, n_trees, X_dev, n, n_cols, draw_idx_dev,
+                                                                               n_idx, excluded_mask_dev, split_rules_dev, out_dev);
+  CK(cudaGetLastError());
+  return BK_OK;
+}
+
+}  // extern "C"

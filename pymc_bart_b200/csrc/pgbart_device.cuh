@@ -1,0 +1,166 @@
+// pgbart_device.cuh — device-side data layout of the B200 PGBART sampler.
+//
+// Everything a chain needs lives in HBM inside ONE workspace allocation that the
+// Python host owns as a torch.uint8 tensor (see bk_query_bytes / bk_create in
+// pgbart_b200.cu).  Names follow the reference's domain: forest, tree, node,
+// particle, leaf id, split variable, not ML vocabulary.
+#pragma once
+
+#include <stdint.h>
+
+#include "bk_spec.h"
+#include "pgbart_b200.h"
+
+#define BK_MAX_PARTICLES 128
+#define BK_WARP_TILE 256           // rows per warp pass: 32 lanes x 8 rows
+#define BK_ROWS_PER_LANE 8
+#define BK_CTA_THREADS 1024
+#define BK_COMMIT_TILE 4096        // rows per CTA pass in the commit/prologue sweep: 1024 x 4
+#define BK_MAX_GROUP 16            // particles that share one register-resident (q_r, q_st) tile
+
+// leaf-id row references
+#define BK_ROW_VIRTUAL (-1)  // stump: every real row is in node 0
+#define BK_ROW_FOREST (-2)   // particle 0: the current tree's row in ids_tree
+
+// per-chain command for the next grid-wide data phase
+#define BK_CMD_IDLE 0
+#define BK_CMD_ROUND 1
+#define BK_CMD_SWEEP 2   // commit of tree A and/or prologue of tree B, fused
+#define BK_CMD_DONE 3
+
+// chain state machine
+#define BK_ST_START 0
+#define BK_ST_WAIT_SWEEP 1
+#define BK_ST_WAIT_ROUND 2
+#define BK_ST_DONE 3
+
+#define BK_JOB_PARTITION 1
+#define BK_JOB_COUNT 2
+
+struct __align__(16) DNode {
+  int32_t var;   // -1 = leaf
+  float split;
+  int32_t left;  // right = left + 1
+  int32_t depth;
+  float value;
+  int32_t n;
+  int64_t sst;
+  int64_t sr;
+  uint64_t sr2_hi;
+  uint64_t sr2_lo;
+  int64_t pad;
+};
+static_assert(sizeof(DNode) == 64, "DNode must be 64 bytes");
+
+struct __align__(16) DParticle {
+  int32_t n_nodes;
+  int32_t q_head;  // expansion queue = nodes [q_head, n_nodes)
+  int32_t row;     // leaf-id row reference
+  int32_t pad;
+  double ssq;
+  double lw;
+  DNode nodes[BK_MAX_NODES];
+};
+static_assert(sizeof(DParticle) == 32 + 64 * BK_MAX_NODES, "DParticle layout");
+
+struct __align__(16) Job {
+  int32_t kind;
+  int32_t slot;       // particle slot (accumulator index)
+  int32_t src_row;
+  int32_t dst_row;
+  int32_t node;       // node being split (partition) / unused (count)
+  int32_t var;
+  float split;
+  int32_t left_id;    // id of the new left child; right = left_id + 1
+  int32_t next_node;  // node whose members are counted per tile (-1: none)
+  int32_t rule;
+  int32_t pad[2];
+};
+static_assert(sizeof(Job) == 48, "Job layout");
+
+struct __align__(16) SweepJob {
+  int32_t do_commit;
+  int32_t commit_tree;
+  int32_t new_row;      // row holding the winning particle's leaf ids
+  int32_t do_welford;
+  int32_t do_prologue;
+  int32_t prologue_tree;
+  int32_t wf_count;
+  int32_t pad;
+};
+
+struct __align__(16) ChainCtl {
+  // --- inputs set by the host before each step
+  int32_t tune;
+  float sigma;
+  // --- persistent sampler state
+  int32_t iter;      // tree updates so far
+  int32_t lower;     // first tree of the next batch
+  int32_t draw;      // steps so far (Philox counter word 0)
+  int32_t wf_count;  // Welford count
+  float leaf_sd;
+  // --- state of the running step
+  int32_t stage;
+  int32_t tree_lo, tree_hi, cur_tree;
+  int32_t round;
+  int32_t buf;       // particle ping-pong index
+  int32_t trace_len;
+  int32_t trace_round_base;
+  // --- command + descriptors for the next data phase
+  int32_t cmd;
+  int32_t n_jobs;
+  SweepJob sweep;
+  // --- counters (bk_step_stats)
+  int32_t c_tree_updates, c_rounds, c_grow, c_grow_root, c_count_passes, c_phases, c_err;
+  int32_t pad0;
+  int32_t row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds
+  float old_vals[256];  // leaf values of the tree being replaced
+  float new_vals[256];  // leaf values of the winning particle
+  Job jobs[BK_MAX_PARTICLES];
+};
+
+// accumulator slots per particle (u64 each)
+#define BK_ACC_N 0
+#define BK_ACC_SST 1
+#define BK_ACC_SR 2
+#define BK_ACC_SR2LO 3
+#define BK_ACC_SR2HI 4
+#define BK_ACC_STRIDE 8
+
+// acc0 layout per chain: [256][4]: leaf k -> (sr, sr2lo, sr2hi, n); entry 255 = totals
+// (sr, sr2lo, sr2hi, sst); then [4]: (wf sd sum, -, -, -)
+#define BK_ACC0_STRIDE 4
+#define BK_ACC0_WORDS (257 * BK_ACC0_STRIDE)
+
+struct Params {
+  int32_t N, Npad, p, m, P, C, R, ntiles;
+  int32_t lik, trace_cap, batch_tune, batch_post;
+  float qscale, init_leaf;
+  double inv_qscale;
+  uint32_t seed, chain_base;
+  const float* X;   // [p][Npad]
+  const float* y;   // [Npad]
+  float* st;        // [C][Npad] sum of trees
+  int32_t* qr;      // [C][Npad]
+  int32_t* qst;     // [C][Npad]
+  uint8_t* ids_tree;   // [C][m][Npad]
+  uint8_t* rows;       // [C][R][Npad]
+  uint32_t* rowcnt;    // [C][R][ntiles]
+  float* wf_mean;      // [C][Npad]
+  float* wf_m2;        // [C][Npad]
+  DParticle* parts;    // [C][2][P]
+  DNode* forest;       // [C][m][255]
+  int32_t* forest_nn;  // [C][m]
+  ChainCtl* ctl;       // [C]
+  unsigned long long* accL;  // [C][P][BK_ACC_STRIDE]
+  unsigned long long* acc0;  // [C][BK_ACC0_WORDS]
+  double* alpha_vec;   // [C][p]
+  double* cum;         // [C][p]
+  double* p_leaf;      // [256]
+  int32_t* rules;      // [p]
+  int32_t* vi;         // [C][p]
+  bk_step_stats* stats;  // [C]
+  bk_trace_rec* trace;   // [C][trace_cap]
+  unsigned int* barrier;
+  int32_t* abort_flag;
+};

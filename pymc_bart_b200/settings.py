@@ -1,0 +1,150 @@
+"""Host-side derivation of the sampler settings from the BART op attributes.
+
+Mirrors what the reference's step constructor reads from the per-variable op
+(pymc_bart/bart.py:141-158): X, Y, m, alpha, beta, split_prior, split_rules.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _cabi
+
+SPLIT_RULE_CODES = {
+    None: _cabi.BK_RULE_CONTINUOUS,
+    "ContinuousSplit": _cabi.BK_RULE_CONTINUOUS,   # tests/test_bart.py:143
+    "ContinuousSplitRule": _cabi.BK_RULE_CONTINUOUS,
+    "OneHotSplit": _cabi.BK_RULE_ONEHOT,           # tests/test_bart.py:144
+    "OneHotSplitRule": _cabi.BK_RULE_ONEHOT,
+}
+
+
+def depth_prior_table(alpha: float, beta: float, depth_offset: int = 0) -> np.ndarray:
+    """P(node at depth d stays a leaf), d = 0..255.
+
+    depth_offset=0: documented prior, a node at depth d is non-terminal with
+    probability alpha*(1+d)^-beta (pymc_bart/bart.py:107-109).
+    depth_offset=1: the historical pure-Python indexing:
+    the root always attempts a split and depth d>=1 uses alpha*d^-beta.
+    """
+    d = np.arange(256, dtype=np.float64)
+    if depth_offset == 0:
+        t = 1.0 - alpha * np.power(1.0 + d, -beta)
+    elif depth_offset == 1:
+        t = np.empty(256)
+        t[0] = 0.0
+        t[1:] = 1.0 - alpha * np.power(d[1:], -beta)
+    else:
+        raise ValueError("depth_offset must be 0 or 1")
+    return np.ascontiguousarray(np.clip(t, 0.0, 1.0))
+
+
+def choose_qshift(abs_max: float) -> int:
+    """Fixed-point scale 2^qshift with 4x head-room over max|Y| inside 29 bits."""
+    b = max(float(abs_max), 1e-30)
+    k = int(math.floor(math.log2((2.0**29 - 1.0) / (4.0 * b))))
+    return max(-60, min(60, k))
+
+
+@dataclass
+class SamplerSettings:
+    n_rows: int
+    n_cols: int
+    n_trees: int
+    n_particles: int
+    n_chains: int
+    likelihood: int
+    qshift: int
+    batch_tune: int
+    batch_post: int
+    seed: int
+    chain_base: int
+    init_sum: float
+    init_leaf: float
+    leaf_sd_init: float
+    device: int
+    trace_capacity: int
+    p_leaf: np.ndarray
+    split_prior: np.ndarray
+    split_rules: np.ndarray
+    _keep: list = field(default_factory=list, repr=False)
+
+    def to_c(self) -> _cabi.BkSettings:
+        s = _cabi.BkSettings()
+        s.abi_version = _cabi.BK_ABI_VERSION
+        for name in ("n_rows", "n_cols", "n_trees", "n_particles", "n_chains", "likelihood", "qshift", "batch_tune",
+                     "batch_post", "seed", "chain_base", "device", "trace_capacity"):
+            setattr(s, name, int(getattr(self, name)))
+        s.init_sum = float(self.init_sum)
+        s.init_leaf = float(self.init_leaf)
+        s.leaf_sd_init = float(self.leaf_sd_init)
+        self.p_leaf = np.ascontiguousarray(self.p_leaf, dtype=np.float64)
+        self.split_prior = np.ascontiguousarray(self.split_prior, dtype=np.float64)
+        self.split_rules = np.ascontiguousarray(self.split_rules, dtype=np.int32)
+        s.p_leaf = self.p_leaf.ctypes.data_as(C.POINTER(C.c_double))
+        s.split_prior = self.split_prior.ctypes.data_as(C.POINTER(C.c_double))
+        s.split_rules = self.split_rules.ctypes.data_as(C.POINTER(C.c_int32))
+        return s
+
+
+def make_settings(
+    X: np.ndarray,
+    Y: np.ndarray,
+    m: int = 50,
+    alpha: float = 0.95,
+    beta: float = 2.0,
+    split_prior=None,
+    split_rules=None,
+    num_particles: int = 10,
+    batch=(0.1, 0.1),
+    n_chains: int = 1,
+    seed: int = 0,
+    chain_base: int = 0,
+    likelihood: int = _cabi.BK_LIK_NORMAL,
+    depth_offset: int = 0,
+    device: int = 0,
+    trace_capacity: int = 0,
+) -> SamplerSettings:
+    X = np.asarray(X)
+    Y = np.asarray(Y, dtype=np.float64)
+    n, p = X.shape
+    if not (0.0 < alpha < 1.0):
+        raise ValueError("alpha must be in (0, 1)")
+    if beta <= 0:
+        raise ValueError("beta must be positive")
+    if split_prior is None or len(np.atleast_1d(split_prior)) == 0:  # bart.py:139
+        sp = np.ones(p, dtype=np.float64)
+    else:
+        sp = np.asarray(split_prior, dtype=np.float64)
+        if sp.shape != (p,) or np.any(sp < 0) or sp.sum() <= 0:
+            raise ValueError("split_prior must hold one non-negative weight per column")
+    if split_rules is None:
+        rules = np.zeros(p, dtype=np.int32)
+    else:
+        if len(split_rules) != p:
+            raise ValueError("split_rules must hold one rule per column")
+        try:
+            rules = np.array([SPLIT_RULE_CODES[r if (r is None or isinstance(r, str)) else type(r).__name__] for r in split_rules], dtype=np.int32)
+        except KeyError as e:
+            raise NotImplementedError(f"split rule {e} has no device implementation") from None
+    ymean = float(Y.mean())
+    uniq = np.unique(Y)
+    if uniq.size == 2 and set(uniq.tolist()) == {0.0, 1.0}:
+        leaf_sd = 3.0 / math.sqrt(m)
+    else:
+        leaf_sd = float(Y.std()) / math.sqrt(m)
+    bt = max(1, int(m * batch[0]))
+    bp = max(1, int(m * batch[1]))
+    init_sum = np.float32(ymean)
+    init_leaf = np.float32(ymean / m)
+    return SamplerSettings(
+        n_rows=n, n_cols=p, n_trees=int(m), n_particles=int(num_particles), n_chains=int(n_chains),
+        likelihood=int(likelihood), qshift=choose_qshift(max(float(np.abs(Y).max()), abs(ymean))),
+        batch_tune=bt, batch_post=bp, seed=int(seed) & 0xFFFFFFFF, chain_base=int(chain_base),
+        init_sum=float(init_sum), init_leaf=float(init_leaf), leaf_sd_init=float(np.float32(leaf_sd)),
+        device=int(device), trace_capacity=int(trace_capacity),
+        p_leaf=depth_prior_table(alpha, beta, depth_offset), split_prior=sp, split_rules=rules,
+    )
