@@ -1,0 +1,108 @@
+"""Device-resident sampler core: torch tensors own HBM, the C ABI drives the kernels.
+
+Host side of SURVEY.md §8b's boundary: this object is what the PGBART step class
+holds per GPU.  X (column-major, padded), y, the sum-of-trees matrix and one
+workspace blob are torch CUDA tensors; libpgbart_b200.so borrows their pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from .settings import SamplerSettings
+
+
+class DeviceSampler:
+    def __init__(self, settings: SamplerSettings, X: np.ndarray, Y: np.ndarray):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("pymc_bart_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = _cabi.load()
+        self.torch = torch
+        self.settings = settings
+        self.device = torch.device("cuda", settings.device)
+        N, p, Cn = settings.n_rows, settings.n_cols, settings.n_chains
+        self.N, self.p, self.m, self.C = N, p, settings.n_trees, Cn
+        self.ld = int(self.lib.bk_padded_rows(N))
+        # host staging in pinned memory, column-major fp32 (bart.py:209-210 hands over f64 row-major)
+        Xh = torch.zeros((p, self.ld), dtype=torch.float32).pin_memory()
+        Xh[:, :N] = torch.from_numpy(np.ascontiguousarray(np.asarray(X, dtype=np.float32).T))
+        yh = torch.zeros((self.ld,), dtype=torch.float32).pin_memory()
+        yh[:N] = torch.from_numpy(np.asarray(Y, dtype=np.float32))
+        self.h2d_bytes = Xh.numel() * 4 + yh.numel() * 4
+        with torch.cuda.device(self.device):
+            self.X_dev = Xh.to(self.device, non_blocking=True)
+            self.y_dev = yh.to(self.device, non_blocking=True)
+            self.sum_trees_dev = torch.empty((Cn, self.ld), dtype=torch.float32, device=self.device)
+            self._cs = settings.to_c()
+            nbytes = C.c_size_t()
+            _cabi.check(self.lib.bk_query_bytes(C.byref(self._cs), C.byref(nbytes)), "bk_query_bytes")
+            self.workspace_bytes = int(nbytes.value)
+            self.workspace = torch.empty((self.workspace_bytes,), dtype=torch.uint8, device=self.device)
+            torch.cuda.synchronize(self.device)
+            h = C.c_void_p()
+            _cabi.check(
+                self.lib.bk_create(C.byref(self._cs), self.X_dev.data_ptr(), self.y_dev.data_ptr(),
+                                   self.sum_trees_dev.data_ptr(), self.workspace.data_ptr(), C.byref(h)),
+                "bk_create",
+            )
+        self.h = h
+        self._vi = np.zeros((Cn, p), dtype=np.int32)
+        self._stats = (_cabi.BkStepStats * Cn)()
+        self._sigma = np.ones(Cn, dtype=np.float32)
+        self._host_out = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, tune: bool, sigma=1.0):
+        """One PGBART step of every chain; returns (vi_counts [C,p] int32, stats)."""
+        self._sigma[...] = np.asarray(sigma, dtype=np.float32)
+        _cabi.check(
+            self.lib.bk_step(self.h, int(bool(tune)), self._sigma.ctypes.data, self._vi.ctypes.data,
+                             C.cast(self._stats, C.c_void_p)),
+            "bk_step",
+        )
+        return self._vi, self._stats
+
+    def sum_trees(self):
+        """torch view [C, N] of the current sum of trees (device)."""
+        return self.sum_trees_dev[:, : self.N]
+
+    def sum_trees_host(self) -> np.ndarray:
+        """D2H copy of the sum of trees into pinned memory (the value handed to PyMC)."""
+        torch = self.torch
+        if self._host_out is None:
+            self._host_out = torch.empty((self.C, self.N), dtype=torch.float32).pin_memory()
+        self._host_out.copy_(self.sum_trees_dev[:, : self.N], non_blocking=False)
+        return self._host_out.numpy()
+
+    def trace(self, chain: int = 0) -> np.ndarray:
+        cap = max(1, self.settings.trace_capacity)
+        buf = np.zeros(cap, dtype=_cabi.TRACE_DTYPE)
+        n = self.lib.bk_read_trace(self.h, int(chain), buf.ctypes.data, cap)
+        if n < 0:
+            _cabi.check(n, "bk_read_trace")
+        return buf[:n]
+
+    def forest(self, chain: int = 0):
+        nodes = np.zeros((self.m, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
+        nn = np.zeros(self.m, dtype=np.int32)
+        _cabi.check(self.lib.bk_export_forest(self.h, int(chain), nodes.ctypes.data, nn.ctypes.data), "bk_export_forest")
+        return nodes, nn
+
+    def leaf_ids(self, chain: int = 0) -> np.ndarray:
+        ids = np.zeros((self.m, self.N), dtype=np.uint8)
+        _cabi.check(self.lib.bk_export_leaf_ids(self.h, int(chain), ids.ctypes.data), "bk_export_leaf_ids")
+        return ids

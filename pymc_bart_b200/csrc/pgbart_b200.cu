@@ -28,11 +28,34 @@
 // contraction on this path (HBM/L2-bound integer and compare work).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
 
 #include "pgbart_device.cuh"
+
+// Bring-up aid: per-warp progress markers in device memory (compile with -DBK_DEBUG_MARKS and
+// run with BK_DEBUG_MARKERS=1; tests/gpu_debug.py dumps them when a step hangs).
+#ifdef BK_DEBUG_MARKS
+#define MARK(code)                                                                                  \
+  do {                                                                                              \
+    if (P.marker && (threadIdx.x & 31) == 0)                                                        \
+      ((volatile int*)P.marker)[blockIdx.x * 33 + (threadIdx.x >> 5)] = (code) | (phase << 12);    \
+  } while (0)
+#else
+#define MARK(code) do { } while (0)
+#endif
+
+// Block barrier = PTX `barrier.sync` WITHOUT .aligned.  The control phase runs long scalar
+// sections in thread 0 (weights, resampling, row allocation) while lanes 1..31 of warp 0 idle;
+// `bar.sync`/__syncthreads() is the .aligned form, which requires every warp to reach the SAME
+// barrier instruction converged — with this kernel's control flow ptxas emitted paths where lane 0
+// arrived apart from its warp, the hardware counted warp 0 twice and the block dead-locked
+// (compute-sanitizer synccheck: "Divergent thread(s) in warp" at a __syncthreads).  The non-aligned
+// form has per-thread arrival semantics and is legal under intra-warp divergence.
+#define BLOCK_SYNC() asm volatile("barrier.sync 0;" ::: "memory")
+
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -99,8 +122,10 @@ union __align__(16) KernelShared {
 };
 
 // ------------------------------------------------------------------ grid barrier
-__device__ __forceinline__ bool grid_sync(const Params& P, unsigned& target, int* s_abort) {
-  __syncthreads();
+__device__ __forceinline__ bool grid_sync(const Params& P, unsigned& target, int* s_abort, int phase) {
+  MARK(20);
+  BLOCK_SYNC();
+  MARK(21);
   if (threadIdx.x == 0) {
     target += gridDim.x;
     __threadfence();
@@ -115,8 +140,11 @@ __device__ __forceinline__ bool grid_sync(const Params& P, unsigned& target, int
     __threadfence();
     *s_abort = ab;
   }
-  __syncthreads();
-  return *s_abort != 0;
+  BLOCK_SYNC();
+  MARK(23);
+  const bool r = *s_abort != 0;
+  if (r) MARK(99);
+  return r;
 }
 
 // ------------------------------------------------------------------ small device utils
@@ -193,16 +221,16 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
 
 // normalise sh.lw[first..first+count) into sh.w, then systematic resampling into sh.anc
 // (block-wide; thread 0 does the order-dependent scalar parts in the oracle's order)
-__device__ void normalise_and_resample(CtlShared& sh, int first, int count, double u) {
+__device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, double u) {
   __shared__ double s_max;
   if (threadIdx.x == 0) {
     double mx = sh.lw[first];
     for (int i = 1; i < count; ++i) if (sh.lw[first + i] > mx) mx = sh.lw[first + i];
     s_max = mx;
   }
-  __syncthreads();
+  BLOCK_SYNC();
   if ((int)threadIdx.x < count) sh.w[threadIdx.x] = bk_weight_term(sh.lw[first + threadIdx.x], s_max);
-  __syncthreads();
+  BLOCK_SYNC();
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int i = 0; i < count; ++i) tot = BK_DADD(tot, sh.w[i]);
@@ -214,7 +242,7 @@ __device__ void normalise_and_resample(CtlShared& sh, int first, int count, doub
       sh.anc[i] = idx;
     }
   }
-  __syncthreads();
+  BLOCK_SYNC();
 }
 
 __device__ void zero_acc0(const Params& P, int c) {
@@ -247,7 +275,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared&
     p0->nodes[k] = nd;
   }
   for (int r = threadIdx.x; r < P.R; r += blockDim.x) ctl->row_cnt_node[r] = -1;
-  __syncthreads();
+  BLOCK_SYNC();
   if (threadIdx.x == 0) {
     double ssq = 0.0;
     for (int k = 0; k < nn; ++k) {
@@ -274,7 +302,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared&
     S->ssq = bk_leaf_ssq(tot, P.init_leaf, P.inv_qscale);
     S->lw = bk_normal_loglik(S->ssq, ctl->sigma, (double)P.N);
   }
-  __syncthreads();
+  BLOCK_SYNC();
 }
 
 // pops, grow decisions, split selection, job list.  Returns (uniformly) the job count.
@@ -316,13 +344,13 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       *rec = r;
     }
   }
-  __syncthreads();
+  BLOCK_SYNC();
   // split values: one warp per growing particle
   {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
     __shared__ int s_err;
     if (threadIdx.x == 0) s_err = 0;
-    __syncthreads();
+    BLOCK_SYNC();
     for (int s = 1 + warp; s < P.P; s += nwarps) {
       if (sh.s_kind[s] != 1) continue;
       float sv;
@@ -336,8 +364,8 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       }
       if (lane == 0) sh.s_split[s] = sv;
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_err) ctl->c_err |= s_err;
+      BLOCK_SYNC();
+      if (threadIdx.x == 0 && s_err) ctl->c_err |= s_err;
   }
   // rows + job list (sequential: deterministic placement)
   __shared__ int s_njobs;
@@ -370,7 +398,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
     ctl->n_jobs = nj;
     s_njobs = nj;
   }
-  __syncthreads();
+  BLOCK_SYNC();
   return s_njobs;
 }
 
@@ -417,7 +445,7 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl) {
     bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + q - 1);
     if (rec) { rec->var = jb.var; rec->split = jb.split; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
   }
-  __syncthreads();
+  BLOCK_SYNC();
 }
 
 __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot /* smem, [P] */) {
@@ -431,21 +459,21 @@ __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_o
     const int words = 2 + nn * 4;
     for (int i = lane; i < words; i += 32) d4[i] = s4[i];
   }
-  __syncthreads();
+  BLOCK_SYNC();
 }
 
 __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
   const int buf = ctl->buf, t = ctl->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)ctl->draw;
   if ((int)threadIdx.x < P.P) sh.lw[threadIdx.x] = part_ptr(P, c, buf, threadIdx.x)->lw;
-  __syncthreads();
+  BLOCK_SYNC();
   double uf = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
-  normalise_and_resample(sh, 0, P.P, uf);
+  normalise_and_resample(P, sh, 0, P.P, uf);
   if (threadIdx.x == 0) {
     unsigned pick = bk_index(bk_rng(S0, C0, D0, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P.P);
     sh.pick = pick; sh.win = sh.anc[pick];
   }
-  __syncthreads();
+  BLOCK_SYNC();
   const int win = sh.win;
   const DParticle* W = part_ptr(P, c, buf, win);
   DNode* ft = P.forest + ((size_t)c * P.m + t) * BK_MAX_NODES;
@@ -455,7 +483,7 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, CtlShared& sh
     ctl->old_vals[k] = (k < old_nn && ft[k].var < 0) ? ft[k].value : 0.0f;
     ctl->new_vals[k] = (k < new_nn && W->nodes[k].var < 0) ? W->nodes[k].value : 0.0f;
   }
-  __syncthreads();
+  BLOCK_SYNC();
   {
     const uint4* s4 = reinterpret_cast<const uint4*>(W->nodes);
     uint4* d4 = reinterpret_cast<uint4*>(ft);
@@ -487,10 +515,11 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, CtlShared& sh
       *rec = r;
     }
   }
-  __syncthreads();
+  BLOCK_SYNC();
 }
 
-__device__ void control_step(const Params& P, int c, int first_phase, int tune, const float* sigma_in, CtlShared& sh) {
+__device__ void control_step(const Params& P, int c, int phase, int tune, const float* sigma_in, CtlShared& sh) {
+  const int first_phase = phase == 0;
   ChainCtl* ctl = P.ctl + c;
   __shared__ int s_stage;
   if (threadIdx.x == 0) {
@@ -499,8 +528,9 @@ __device__ void control_step(const Params& P, int c, int first_phase, int tune, 
     }
     s_stage = ctl->stage;
   }
-  __syncthreads();
+  BLOCK_SYNC();
   int stage = s_stage;
+  MARK(100 + stage);
   if (stage == BK_ST_DONE) return;
   if (threadIdx.x == 0) ctl->c_phases += 1;
 
@@ -518,7 +548,7 @@ __device__ void control_step(const Params& P, int c, int first_phase, int tune, 
       sj.do_prologue = 1; sj.prologue_tree = lo;
       ctl->sweep = sj; ctl->cmd = BK_CMD_SWEEP; ctl->stage = BK_ST_WAIT_SWEEP;
     }
-    __syncthreads();
+    BLOCK_SYNC();
     return;
   }
 
@@ -555,11 +585,15 @@ __device__ void control_step(const Params& P, int c, int first_phase, int tune, 
         P.stats[c] = st;
       }
     }
-    __syncthreads();
+    BLOCK_SYNC();
     if (!s_more) return;
+    MARK(110);
     init_particles(P, c, ctl, sh);
+    MARK(111);
   } else {  // BK_ST_WAIT_ROUND
+    MARK(120);
     finalize_grows(P, c, ctl);
+    MARK(121);
     have_round = true;
   }
 
@@ -568,7 +602,7 @@ __device__ void control_step(const Params& P, int c, int first_phase, int tune, 
       // the round ctl->round is complete: log weights, liveness, resampling
       const int buf = ctl->buf;
       if (threadIdx.x == 0) { sh.live = 0; ctl->c_rounds += 1; }
-      __syncthreads();
+      BLOCK_SYNC();
       if (threadIdx.x >= 1 && (int)threadIdx.x < P.P) {
         const DParticle* S = part_ptr(P, c, buf, threadIdx.x);
         sh.lw[threadIdx.x] = S->lw;
@@ -576,15 +610,18 @@ __device__ void control_step(const Params& P, int c, int first_phase, int tune, 
         bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + threadIdx.x - 1);
         if (rec) rec->log_w = S->lw;
       }
-      __syncthreads();
+      BLOCK_SYNC();
       const int live = sh.live;
       const int rbase = ctl->trace_round_base;
-      __syncthreads();
+      BLOCK_SYNC();
       if (threadIdx.x == 0) ctl->trace_round_base = rbase + (P.P - 1);
-      if (!live) { __syncthreads(); finish_tree(P, c, ctl, sh); return; }
+      MARK(130 + live);
+      if (!live) { BLOCK_SYNC(); finish_tree(P, c, ctl, sh); MARK(139); return; }
       double u = bk_u01(bk_rng(P.seed, P.chain_base + (uint32_t)c, (uint32_t)ctl->draw, 0, (uint32_t)ctl->cur_tree,
                                (uint32_t)ctl->round, 0, BK_U_RESAMPLE).v[0]);
-      normalise_and_resample(sh, 1, P.P - 1, u);
+      MARK(132);
+      normalise_and_resample(P, sh, 1, P.P - 1, u);
+      MARK(133);
       // anc[i] indexes particles 1..P-1; convert to slot -> source slot
       __shared__ int s_src[BK_MAX_PARTICLES];
       if ((int)threadIdx.x < P.P) {
@@ -592,16 +629,20 @@ __device__ void control_step(const Params& P, int c, int first_phase, int tune, 
         s_src[s] = s == 0 ? 0 : sh.anc[s - 1] + 1;
         if (s >= 1) { bk_trace_rec* rec = trace_at(P, c, rbase + s - 1); if (rec) rec->ancestor = s_src[s]; }
       }
-      __syncthreads();
+      BLOCK_SYNC();
+      MARK(134);
       copy_particles(P, c, buf, s_src);
+      MARK(135);
       if (threadIdx.x == 0) { ctl->buf = buf ^ 1; ctl->round += 1; }
-      __syncthreads();
+      BLOCK_SYNC();
     }
+    MARK(140);
     int nj = propose(P, c, ctl, sh);
+    MARK(141);
     have_round = true;
     if (nj > 0) {
       if (threadIdx.x == 0) { ctl->cmd = BK_CMD_ROUND; ctl->stage = BK_ST_WAIT_ROUND; }
-      __syncthreads();
+      BLOCK_SYNC();
       return;
     }
   }
@@ -719,7 +760,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
   }
   for (int k = threadIdx.x; k < 256 * 3; k += blockDim.x) sh.leaf_acc[k] = 0ull;
   if (threadIdx.x < 8) sh.tot_acc[threadIdx.x] = 0ull;
-  __syncthreads();
+  BLOCK_SYNC();
 
   const size_t base = (size_t)ctile * BK_COMMIT_TILE + (size_t)threadIdx.x * 4;
   long long t_sst = 0, t_sr = 0, t_sd = 0;
@@ -738,7 +779,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) if (base + e >= (size_t)P.N) nid4 |= 0xFFu << (8 * e);
       } else nid4 = __ldcg(reinterpret_cast<const unsigned*>(P.rows + ((size_t)c * P.R + new_row) * P.Npad + base));
-      float4 mean4, m24;
+      float4 mean4 = make_float4(0.f, 0.f, 0.f, 0.f), m24 = make_float4(0.f, 0.f, 0.f, 0.f);
       float* mp = P.wf_mean + (size_t)c * P.Npad + base;
       float* m2p = P.wf_m2 + (size_t)c * P.Npad + base;
       if (do_wf) { mean4 = __ldcg(reinterpret_cast<const float4*>(mp)); m24 = __ldcg(reinterpret_cast<const float4*>(m2p)); }
@@ -807,7 +848,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
       atomicAdd(&sh.tot_acc[3], v3); atomicAdd(&sh.tot_acc[4], v4);
     }
   }
-  __syncthreads();
+  BLOCK_SYNC();
   unsigned long long* a0 = P.acc0 + (size_t)c * BK_ACC0_WORDS;
   if (do_pro) {
     for (int k = threadIdx.x; k < 255 * 3; k += blockDim.x) {
@@ -817,7 +858,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
     if (threadIdx.x < 4) { unsigned long long v = sh.tot_acc[threadIdx.x]; if (v) red_add_u64(a0 + (size_t)255 * BK_ACC0_STRIDE + threadIdx.x, v); }
   }
   if (do_commit && do_wf && threadIdx.x == 0) { unsigned long long v = sh.tot_acc[4]; if (v) red_add_u64(a0 + (size_t)256 * BK_ACC0_STRIDE, v); }
-  __syncthreads();
+  BLOCK_SYNC();
 }
 
 // ------------------------------------------------------------------ the step kernel
@@ -833,8 +874,11 @@ pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sig
 
   for (int phase = 0; phase < max_phases; ++phase) {
     // ---- control
-    for (int c = blockIdx.x; c < P.C; c += gridDim.x) control_step(P, c, phase == 0, tune, sigma_in, sh.ctl);
-    if (grid_sync(P, target, &s_abort)) return;
+    MARK(1);
+    for (int c = blockIdx.x; c < P.C; c += gridDim.x) control_step(P, c, phase, tune, sigma_in, sh.ctl);
+    MARK(2);
+    if (grid_sync(P, target, &s_abort, phase)) return;
+    MARK(3);
     // ---- plan the data phase (every CTA builds the same small table)
     if (threadIdx.x == 0) {
       int done = 1, ru = 0, su = 0;
@@ -857,8 +901,15 @@ pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sig
       sh.data.ru_base[P.C] = ru; sh.data.su_base[P.C] = su;
       sh.data.group = G; sh.data.all_done = done;
     }
-    __syncthreads();
+    BLOCK_SYNC();
+    if (P.debug == 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+      const ChainCtl* d = P.ctl;
+      printf("[bk] phase %d cmd %d stage %d njobs %d round %d tree %d ru %d su %d G %d done %d err %d\n", phase, sh.data.cmd[0],
+             d->stage, sh.data.njobs[0], d->round, d->cur_tree, sh.data.ru_base[P.C], sh.data.su_base[P.C], sh.data.group,
+             sh.data.all_done, d->c_err);
+    }
     if (sh.data.all_done) break;
+    MARK(4);
     // ---- data: sweeps (CTA granular)
     {
       const int su_total = sh.data.su_base[P.C];
@@ -868,6 +919,7 @@ pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sig
         sweep_unit(P, c, u - sh.data.su_base[c], sh.data);
       }
     }
+    MARK(5);
     // ---- data: rounds (warp granular)
     {
       const int ru_total = sh.data.ru_base[P.C];
@@ -882,7 +934,9 @@ pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sig
         round_unit(P, c, tile, lo, hi);
       }
     }
-    if (grid_sync(P, target, &s_abort)) return;
+    MARK(6);
+    if (grid_sync(P, target, &s_abort, phase)) return;
+    MARK(7);
   }
 }
 
@@ -989,6 +1043,8 @@ struct bk_handle_s {
   bk_step_stats* stats_pinned;
   float* sigma_pinned;
   int32_t* abort_pinned;
+  int32_t* marker_host;
+  int marker_count;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1113,6 +1169,14 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgbart_step_kernel, BK_CTA_THREADS, 0));
   if (occ < 1) { set_err("step kernel does not fit on an SM"); return BK_ERR_CUDA; }
   h->grid = n_sm;  // one persistent CTA per SM (148 on B200)
+  if (getenv("BK_DEBUG_MARKERS")) {
+    h->marker_count = 4736 + n_sm * 64 + 64;
+    h->marker_host = (int32_t*)calloc((size_t)h->marker_count, sizeof(int32_t));
+    int32_t* dptr = nullptr;
+    CK(cudaMalloc(&dptr, (size_t)h->marker_count * sizeof(int32_t)));
+    CK(cudaMemset(dptr, 0, (size_t)h->marker_count * sizeof(int32_t)));
+    P.marker = dptr;
+  }
   h->max_phases = 1 << 20;
 
   pgbart_init_kernel<<<n_sm * 2, 512, 0, h->stream>>>(P, s->init_sum, s->leaf_sd_init, h->split_prior_dev);
@@ -1148,6 +1212,11 @@ int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_
   int tune_i = tune ? 1 : 0;
   const float* sig = h->sigma_dev;
   int maxp = h->max_phases;
+  {
+    const char* dbg = getenv("BK_DEBUG");
+    P.debug = dbg ? atoi(dbg) : 0;
+
+  }
   void* args[] = {(void*)&P, (void*)&tune_i, (void*)&sig, (void*)&maxp};
   CK(cudaLaunchCooperativeKernel((const void*)pgbart_step_kernel, dim3(h->grid), dim3(BK_CTA_THREADS), args, 0, h->stream));
   CK(cudaMemcpyAsync(h->vi_pinned, P.vi, (size_t)P.C * P.p * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1160,6 +1229,19 @@ int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_
   for (int c = 0; c < P.C; ++c)
     if (h->stats_pinned[c].error_flags & ~1) { set_err("device-side consistency check failed"); return BK_ERR_STATE; }
   return BK_OK;
+}
+
+/* debug only (not part of the public header): host view of the per-warp progress markers */
+int32_t* bk_debug_markers(bk_handle* h, int* count) {
+  if (!h) return nullptr;
+  if (count) *count = h->marker_count;
+  if (!h->P.marker) return nullptr;
+  cudaStream_t s2;
+  cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+  cudaMemcpyAsync(h->marker_host, h->P.marker, (size_t)h->marker_count * sizeof(int32_t), cudaMemcpyDeviceToHost, s2);
+  cudaStreamSynchronize(s2);
+  cudaStreamDestroy(s2);
+  return h->marker_host;
 }
 
 int bk_read_trace(bk_handle* h, int chain, bk_trace_rec* out_host, int capacity) {

@@ -14,8 +14,10 @@
 #define BK_MAX_PARTICLES 128
 #define BK_WARP_TILE 256           // rows per warp pass: 32 lanes x 8 rows
 #define BK_ROWS_PER_LANE 8
+#ifndef BK_CTA_THREADS
 #define BK_CTA_THREADS 1024
-#define BK_COMMIT_TILE 4096        // rows per CTA pass in the commit/prologue sweep: 1024 x 4
+#endif
+#define BK_COMMIT_TILE (BK_CTA_THREADS * 4)  // rows per CTA pass in the commit/prologue sweep
 #define BK_MAX_GROUP 16            // particles that share one register-resident (q_r, q_st) tile
 
 // leaf-id row references
@@ -163,4 +165,6 @@ struct Params {
   bk_trace_rec* trace;   // [C][trace_cap]
   unsigned int* barrier;
   int32_t* abort_flag;
+  int32_t debug;
+  int32_t* marker;  // debug: mapped host memory, one int per warp
 };
