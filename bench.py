@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — PGBART draws/sec on synthetic Friedman data (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C1|C5]
+
+One "step" = one PGBART step (astep) of every chain batched on a GPU = one draw per chain.
+At N=1 the workload is BASELINE.json configs[1] (C2: N=100k, p=10, m=50, 40 particles, 4 chains
+on one B200).  With --gpus N (launched by torchrun) every rank runs its own 4 chains (weak
+scaling: chains are independent, no data-path collective); the one NCCL all-gather of the run
+(posterior mean of each chain) is inside the timed region.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    #        N        p   m    P   chains seed
+    "C1": (200, 5, 10, 20, 1, 1),
+    "C2": (100_000, 10, 50, 40, 4, 2),
+    "C5": (1_000_000, 50, 200, 60, 8, 5),
+}
+
+
+def friedman(N, p, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0, 1, (N, p)).astype(np.float32)
+    f = 10 * np.sin(np.pi * X[:, 0] * X[:, 1]) + 20 * (X[:, 2] - 0.5) ** 2 + 10 * X[:, 3] + 5 * X[:, 4]
+    y = (f + rng.normal(0, 1, N)).astype(np.float32)
+    return X, y
+
+
+def algorithmic_bytes(N, grow_events, tree_updates, tune_updates):
+    """per grow event 14N; per tree update 23N (+16N while tuning)."""
+    return 14.0 * N * grow_events + 23.0 * N * tree_updates + 16.0 * N * tune_updates
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = str(gpu_index)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", self.gpu], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, cfg):
+    """The reference's CPU path: oracle/ port (bartrs is not installable offline), one chain per host thread."""
+    from oracle.oracle_py import OracleChain
+    from pymc_bart_b200.settings import make_settings
+
+    N, p, m, P, chains, seed = cfg
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, y = friedman(N, p, seed)
+    threads = min(os.cpu_count() or 1, chains * max(1, args.gpus))
+    n_chains = chains * max(1, args.gpus)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1)
+    Xc = np.ascontiguousarray(X.T)
+    orcs = [OracleChain(s, Xc, y, chain=c) for c in range(n_chains)]
+    steps, warm = args.steps, args.warmup
+
+    def work(o, n, tune):
+        for _ in range(n):
+            o.step(tune, 1.0)
+
+    def run_all(n, tune):
+        sem = threading.Semaphore(threads)
+        ths = []
+        for o in orcs:
+            def job(o=o):
+                with sem:
+                    work(o, n, tune)
+            t = threading.Thread(target=job); t.start(); ths.append(t)
+        for t in ths:
+            t.join()
+
+    run_all(warm, True)
+    t0 = time.perf_counter()
+    run_all(steps, True)
+    dt = time.perf_counter() - t0
+    val = n_chains * steps / dt
+    line = {
+        "impl": "reference", "metric": "PGBART draws/sec", "value": val, "unit": "draws/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+i64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: Friedman N={N} p={p} m={m} particles={P} chains={n_chains} (tuning draws)",
+                   "note": "CPU restatement oracle/pgbart_oracle.c (bartrs unavailable offline), ctypes releases the GIL"},
+        "cpu_baseline": {"value": val, "unit": "draws/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} tuning draws x {n_chains} chains after {warm} warm-up"},
+        "e2e": {"value": val, "unit": "draws/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--cpu-draws", type=int, default=None, help="CPU baseline sample size (draws per chain)")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        if args.impl == "reference" and args.steps > 12 and args.config != "C1":
+            args.steps, args.warmup = min(args.steps, 6), min(args.warmup, 1)   # bounded sample (minutes, not hours)
+        run_reference(args, cfg)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from pymc_bart_b200.core import DeviceSampler
+    from pymc_bart_b200.settings import make_settings
+
+    N, p, m, P, chains, seed = cfg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    steps, warm = args.steps, max(3, args.warmup)
+    X, y = friedman(N, p, seed)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains, chain_base=rank * chains, device=local)
+    dev = DeviceSampler(s, X, y)
+    stream = dev.stream()
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    n_tune = steps // 2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (value): K steps, CUDA events on the launch stream
+    for i in range(warm):
+        dev.step(True, 1.0)
+    sync_all()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    grow = tupd = tune_upd = rounds = phases = 0
+    post_mean = torch.zeros((chains, N), dtype=torch.float32, device="cuda")
+    for i in range(steps):
+        tune = i < n_tune
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(i & 0xFF)   # untimed: evicts the working set from the 126 MB L2
+        ev[i][0].record(stream)
+        dev.step_launch(tune, 1.0)
+        ev[i][1].record(stream)
+        _, st = dev.step_wait()
+        for c in range(chains):
+            grow += st[c].grow_events; tupd += st[c].tree_updates; rounds += st[c].rounds
+            tune_upd += st[c].tree_updates if tune else 0
+        phases += st[0].phases
+        if not tune:
+            with torch.cuda.stream(stream):
+                post_mean += dev.sum_trees()
+    t_gather0 = torch.cuda.Event(enable_timing=True); t_gather1 = torch.cuda.Event(enable_timing=True)
+    t_gather0.record(stream)
+    if world > 1:  # the run's single collective: all-gather of the chains' posterior means
+        stream.synchronize()
+        gathered = [torch.empty_like(post_mean) for _ in range(world)]
+        dist.all_gather(gathered, post_mean)
+    t_gather1.record(stream)
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms)) + (t_gather0.elapsed_time(t_gather1) if world > 1 else 0.0)
+    tm = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([float(grow), float(tupd), float(tune_upd)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    total_ms_max = float(tm.item())
+    g_all, t_all, tu_all = [float(v) for v in agg.tolist()]
+    value = world * chains * steps / (total_ms_max / 1e3)
+
+    # ---------------- end to end through the public step API (host buffers, copies inside the timed region)
+    from pymc_bart_b200 import BART
+    from pymc_bart_b200.pgbart import PGBART
+
+    dev.close()
+    del dev
+    torch.cuda.synchronize()
+    e2e_steps = max(10, steps // 4)
+    t0 = time.perf_counter()
+    rv = BART("mu", X, y, m=m)
+    stp = PGBART([rv], num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=False)
+    t_build = time.perf_counter() - t0
+    for i in range(3):
+        stp.astep()
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        if i == e2e_steps // 2:
+            stp.stop_tuning()
+        val_host, stats = stp.astep()      # H2D sigma, step kernel, D2H sum-of-trees + VI counts + stats
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * chains * e2e_steps / float(e2e_t.item())
+    h2d = chains * 4
+    d2h = chains * N * 4 + chains * p * 4 + chains * 48 + 4
+    h2d_once = stp.core.h2d_bytes
+    stp.close()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # roofline of the dominant (only) kernel: pgbart_step_kernel, one launch per step
+        ms_kernel = float(np.mean(step_ms))
+        bytes_per_launch = algorithmic_bytes(N, grow / steps, tupd / steps, tune_upd / steps)
+        achieved = bytes_per_launch / (ms_kernel / 1e3) / 1e9
+        line = {
+            "metric": "PGBART draws/sec", "value": value, "unit": "draws/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i64", "data": "synthetic",
+            "config": {
+                "workload": f"{args.config}: Friedman N={N} p={p} m={m} trees particles={P} chains/GPU={chains} sigma=1 fixed, "
+                            f"batch=(0.1,0.1) -> {s.batch_tune} trees/draw, depth prior alpha(1+d)^-beta (bart.py:107-109); "
+                            f"{n_tune} tuning + {steps - n_tune} post-tuning draws timed",
+                "l2": "256 MB fill between timed steps (L2 flushed)" if flush is not None else "no flush (working set stays in L2)",
+                "grow_events_per_tree_update": g_all / max(t_all, 1.0),
+                "rounds_per_tree_update": rounds / max(tupd, 1),
+                "grid_phases_per_step": phases / steps,
+            },
+            "gpu_launches": steps,
+            "e2e": {"value": e2e_val, "unit": "draws/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel": "pgbart_step_kernel",
+                         "kernel_ms": ms_kernel},
+            "clocks": clk,
+        }
+        # ---------------- CPU baseline: the oracle on the host cores, bounded sample of the same workload
+        try:
+            from oracle.oracle_py import OracleChain
+
+            s1 = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1)
+            Xc = np.ascontiguousarray(X.T)
+            ncpu = min(os.cpu_count() or 1, chains)
+            orcs = [OracleChain(s1, Xc, y, chain=c) for c in range(ncpu)]
+            nd = args.cpu_draws or (3 if N >= 100_000 else 100)
+            t0 = time.perf_counter()
+            ths = [threading.Thread(target=lambda o=o: [o.step(True, 1.0) for _ in range(nd)]) for o in orcs]
+            [t.start() for t in ths]; [t.join() for t in ths]
+            cdt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": ncpu * nd / cdt, "unit": "draws/s", "cores": ncpu, "kind": "port",
+                                    "sample": f"{nd} tuning draws x {ncpu} chains of {args.config}, one chain per host thread "
+                                              f"(oracle/pgbart_oracle.c; bartrs is not installable offline)"}
+        except Exception as e:  # noqa
+            line["cpu_baseline"] = {"value": None, "unit": "draws/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

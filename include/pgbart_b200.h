@@ -146,11 +146,22 @@ void bk_destroy(bk_handle* h);
 int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_host,
             bk_step_stats* stats_host);
 
+/* Asynchronous form: bk_step_launch enqueues the H2D of sigma, the step kernel and the D2H of
+ * the per-step outputs on the handle's stream and returns; bk_step_wait blocks until they are
+ * done and copies them out (same outputs as bk_step).  bk_stream returns the handle's
+ * cudaStream_t (as void*) so the host can record events on it or order its own copies after it. */
+int bk_step_launch(bk_handle* h, int tune, const float* sigma_host);
+int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host);
+void* bk_stream(bk_handle* h);
+
 /* trace of the last step of one chain (host copy); returns records copied */
 int bk_read_trace(bk_handle* h, int chain, bk_trace_rec* out_host, int capacity);
 
 /* Current forest of a chain as flat nodes: nodes_host [n_trees][255], n_nodes_host [n_trees] */
 int bk_export_forest(bk_handle* h, int chain, bk_node* nodes_host, int32_t* n_nodes_host);
+
+/* `count` consecutive trees starting at `first` (the batch a step rewrote), same layout */
+int bk_export_trees(bk_handle* h, int chain, int first, int count, bk_node* nodes_host, int32_t* n_nodes_host);
 
 /* leaf assignment of every training row in every tree: ids_host [n_trees][n_rows] uint8 */
 int bk_export_leaf_ids(bk_handle* h, int chain, uint8_t* ids_host);

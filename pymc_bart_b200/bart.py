@@ -1,0 +1,106 @@
+"""BART random variable: PyMC-free mirror of pymc_bart/bart.py (reference @4daa2e2).
+
+The reference builds a per-variable ``BART_{name}`` RandomVariable op whose CLASS
+ATTRIBUTES carry everything the step method needs (pymc_bart/bart.py:141-158):
+``X, Y, m, alpha, beta, response, split_prior, split_rules, initval, all_trees``.
+This module reproduces that object without PyMC/PyTensor so that the PGBART step
+(pgbart.py) can be constructed from it exactly as ``bartrs.PGBART([rv], ...)`` is
+(tests/test_bart.py:231).  When PyMC is importable, ``pymc_bart_b200.pymc_adapter``
+wraps the same op into a real ``pm.Distribution``.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+__all__ = ["BART", "BARTRV", "preprocess_xy"]
+
+
+def preprocess_xy(X, Y):
+    """pandas / polars / array -> float64 numpy (pymc_bart/bart.py:193-212)."""
+    for mod in ("pandas", "polars"):
+        try:
+            m = __import__(mod)
+        except ImportError:
+            continue
+        if isinstance(X, (m.Series, m.DataFrame)):
+            X = X.to_numpy()
+        if isinstance(Y, (m.Series, m.DataFrame)):
+            Y = Y.to_numpy()
+    return np.asarray(X).astype(float), np.asarray(Y).astype(float)
+
+
+class BARTRV:
+    """Base class of the per-variable op (pymc_bart/bart.py:35-68)."""
+
+    name = "BART"
+    signature = "(m,n),(m),(),(),() -> (m)"
+    dtype = "floatX"
+
+    @classmethod
+    def rng_fn(cls, rng=None, X=None, Y=None, m=None, alpha=None, beta=None, size=None):
+        """Prior/posterior draw of the variable (pymc_bart/bart.py:47-68)."""
+        from .utils import _get_posterior_sampler, _sample_posterior
+
+        if not size:
+            size = None
+        if not getattr(cls, "all_trees", None):
+            Yv = cls.Y
+            if size is not None:
+                return np.full((size[0], Yv.shape[0]), Yv.mean())
+            return np.full(Yv.shape[0], Yv.mean())
+        shape = size[0] if size is not None else 1
+        sampler = _get_posterior_sampler(cls)
+        pred = _sample_posterior(sampler, cls.X if X is None else X, rng=rng or np.random.default_rng(), size=shape)
+        return pred.squeeze().T
+
+
+class _Owner:
+    def __init__(self, op):
+        self.op = op
+
+
+class BARTVariable:
+    """What ``pmb.BART(...)`` hands back when no PyMC model is involved."""
+
+    def __init__(self, name, op, shape):
+        self.name = name
+        self.owner = _Owner(op)
+        self.shape = shape
+
+    def __repr__(self):
+        return f"BART({self.name}, shape={self.shape})"
+
+
+def BART(name, X, Y, m=50, alpha=0.95, beta=2.0, response="constant", split_rules=None, split_prior=None,
+         shape=None, separate_trees=False, **kwargs):
+    """Same signature as ``pmb.BART`` (pymc_bart/bart.py:115-127) plus ``separate_trees``
+    (dropped from the reference at this commit; BASELINE.json config 4 asks for it)."""
+    if response in ("linear", "mix"):
+        warnings.warn("Options linear and mix are experimental and still not well tested\nUse with caution.")
+    Xn, Yn = preprocess_xy(X, Y)
+    sp = np.array([]) if split_prior is None else np.asarray(split_prior)
+    op_type = type(
+        f"BART_{name}",
+        (BARTRV,),
+        {
+            "name": "BART",
+            "all_trees": [],          # reference: multiprocessing.Manager().list() (bart.py:134-135)
+            "inplace": False,
+            "initval": Yn.mean(),
+            "X": Xn,
+            "Y": Yn,
+            "m": int(m),
+            "response": response,
+            "alpha": alpha,
+            "beta": beta,
+            "split_prior": sp,
+            "split_rules": split_rules,
+            "separate_trees": bool(separate_trees),
+        },
+    )
+    op = op_type()
+    n = Xn.shape[0]
+    shp = (n,) if shape is None else tuple(np.atleast_1d(shape))
+    return BARTVariable(name, op, shp)

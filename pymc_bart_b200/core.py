@@ -76,6 +76,25 @@ class DeviceSampler:
         )
         return self._vi, self._stats
 
+    def step_launch(self, tune: bool, sigma=1.0):
+        """Enqueue one step on the sampler's stream (returns immediately)."""
+        self._sigma[...] = np.asarray(sigma, dtype=np.float32)
+        _cabi.check(self.lib.bk_step_launch(self.h, int(bool(tune)), self._sigma.ctypes.data), "bk_step_launch")
+
+    def step_wait(self):
+        _cabi.check(self.lib.bk_step_wait(self.h, self._vi.ctypes.data, C.cast(self._stats, C.c_void_p)), "bk_step_wait")
+        return self._vi, self._stats
+
+    def stream(self):
+        """torch view of the sampler's CUDA stream (for events and ordered copies)."""
+        return self.torch.cuda.ExternalStream(int(self.lib.bk_stream(self.h)), device=self.device)
+
+    def trees(self, chain: int, first: int, count: int):
+        nodes = np.zeros((count, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
+        nn = np.zeros(count, dtype=np.int32)
+        _cabi.check(self.lib.bk_export_trees(self.h, int(chain), int(first), int(count), nodes.ctypes.data, nn.ctypes.data), "bk_export_trees")
+        return nodes, nn
+
     def sum_trees(self):
         """torch view [C, N] of the current sum of trees (device)."""
         return self.sum_trees_dev[:, : self.N]

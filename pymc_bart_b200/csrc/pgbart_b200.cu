@@ -1198,7 +1198,7 @@ void bk_destroy(bk_handle* h) {
   delete h;
 }
 
-int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_host, bk_step_stats* stats_host) {
+int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
   CK(cudaSetDevice(h->s.device));
   Params& P = h->P;
@@ -1215,13 +1215,19 @@ int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_
   {
     const char* dbg = getenv("BK_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;
-
   }
   void* args[] = {(void*)&P, (void*)&tune_i, (void*)&sig, (void*)&maxp};
   CK(cudaLaunchCooperativeKernel((const void*)pgbart_step_kernel, dim3(h->grid), dim3(BK_CTA_THREADS), args, 0, h->stream));
   CK(cudaMemcpyAsync(h->vi_pinned, P.vi, (size_t)P.C * P.p * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->stats_pinned, P.stats, (size_t)P.C * sizeof(bk_step_stats), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->abort_pinned, P.abort_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  return BK_OK;
+}
+
+int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host) {
+  if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
+  CK(cudaSetDevice(h->s.device));
+  Params& P = h->P;
   CK(cudaStreamSynchronize(h->stream));
   if (*h->abort_pinned) { set_err("grid barrier timed out inside the step kernel"); return BK_ERR_TIMEOUT; }
   if (vi_counts_host) memcpy(vi_counts_host, h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t));
@@ -1230,6 +1236,14 @@ int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_
     if (h->stats_pinned[c].error_flags & ~1) { set_err("device-side consistency check failed"); return BK_ERR_STATE; }
   return BK_OK;
 }
+
+int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_host, bk_step_stats* stats_host) {
+  int rc = bk_step_launch(h, tune, sigma_host);
+  if (rc != BK_OK) return rc;
+  return bk_step_wait(h, vi_counts_host, stats_host);
+}
+
+void* bk_stream(bk_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 /* debug only (not part of the public header): host view of the per-warp progress markers */
 int32_t* bk_debug_markers(bk_handle* h, int* count) {
@@ -1254,6 +1268,30 @@ int bk_read_trace(bk_handle* h, int chain, bk_trace_rec* out_host, int capacity)
   cudaError_t e = cudaMemcpy(out_host, h->P.trace + (size_t)chain * h->P.trace_cap, (size_t)n * sizeof(bk_trace_rec), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { set_err("CUDA error %s in bk_read_trace", cudaGetErrorString(e)); return BK_ERR_CUDA; }
   return n;
+}
+
+int bk_export_trees(bk_handle* h, int chain, int first, int count, bk_node* nodes_host, int32_t* n_nodes_host) {
+  if (!h || chain < 0 || chain >= h->P.C || !nodes_host || !n_nodes_host || first < 0 || count < 0 || first + count > h->P.m) {
+    set_err("bad argument"); return BK_ERR_ARG;
+  }
+  if (count == 0) return BK_OK;
+  CK(cudaSetDevice(h->s.device));
+  const Params& P = h->P;
+  CK(cudaMemcpy(n_nodes_host, P.forest_nn + (size_t)chain * P.m + first, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  DNode* tmp = (DNode*)malloc((size_t)BK_MAX_NODES * sizeof(DNode));
+  if (!tmp) { set_err("out of host memory"); return BK_ERR_ARG; }
+  for (int t = 0; t < count; ++t) {
+    int nn = n_nodes_host[t];
+    cudaError_t e = cudaMemcpy(tmp, P.forest + ((size_t)chain * P.m + first + t) * BK_MAX_NODES, (size_t)nn * sizeof(DNode), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { free(tmp); set_err("CUDA error %s in bk_export_trees", cudaGetErrorString(e)); return BK_ERR_CUDA; }
+    for (int k = 0; k < BK_MAX_NODES; ++k) {
+      bk_node* d = &nodes_host[(size_t)t * BK_MAX_NODES + k];
+      memset(d, 0, sizeof(*d));
+      if (k < nn) { d->var = tmp[k].var; d->split = tmp[k].split; d->left = tmp[k].left; d->value = tmp[k].var < 0 ? tmp[k].value : 0.0f; d->n = tmp[k].n; d->depth = tmp[k].depth; }
+    }
+  }
+  free(tmp);
+  return BK_OK;
 }
 
 int bk_export_forest(bk_handle* h, int chain, bk_node* nodes_host, int32_t* n_nodes_host) {

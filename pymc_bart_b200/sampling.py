@@ -1,0 +1,51 @@
+"""Minimal PyMC-free driver: tune + draws through PGBART.astep, chains sharded one group per
+GPU (torch.distributed / NCCL), ONE all-gather of the posterior draws at the end.
+
+Stands in for ``pm.sample(tune, draws, chains, step=[PGBART(...)])`` (tests/test_bart.py:58,235)
+when PyMC is absent; the likelihood scale is held fixed (or supplied per draw by ``sigma_fn``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1), sigma=1.0, seed=0,
+           likelihood="normal", sigma_fn=None, keep_draws=True, **step_kwargs):
+    """Returns a dict: posterior (chains_total, draws, N) float32 [if keep_draws],
+    variable_inclusion (chains_total, draws) of base64 strings, and the step object."""
+    import torch
+    import torch.distributed as dist
+
+    from .pgbart import PGBART
+
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if distributed else 0
+    world = dist.get_world_size() if distributed else 1
+    device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    step = PGBART([rv], num_particles=num_particles, batch=batch, likelihood=likelihood, sigma=sigma, chains=chains,
+                  chain_base=rank * chains, seed=seed, device=device, **step_kwargs)
+    N = step.n_rows
+    post = np.empty((chains, draws, N), dtype=np.float32) if keep_draws else None
+    vi = [[None] * draws for _ in range(chains)]
+    for d in range(tune + draws):
+        if d == tune:
+            step.stop_tuning()
+        if sigma_fn is not None:
+            step.sigma = sigma_fn(d, step)
+        value, stats = step.astep()
+        if d >= tune:
+            v = value if chains > 1 else value[None]
+            s = stats if chains > 1 else [stats[0]]
+            if keep_draws:
+                post[:, d - tune] = v
+            for c in range(chains):
+                vi[c][d - tune] = s[c]["variable_inclusion"]
+    step.publish_history()
+    out = {"step": step, "variable_inclusion": vi, "posterior": post, "rank": rank, "world": world}
+    if distributed and world > 1 and keep_draws:
+        # the single collective of the run: all-gather of the posterior draws over NVLink
+        loc = torch.from_numpy(post).cuda()
+        gathered = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(gathered, loc)
+        out["posterior"] = torch.cat(gathered, dim=0).cpu().numpy()
+    return out
