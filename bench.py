@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-draws", type=int, default=None, help="CPU baseline sample size (draws per chain)")
+    ap.add_argument("--profile-only", action="store_true", help="device-timed leg only (for ncu runs)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -223,6 +224,10 @@ def main():
     g_all, t_all, tu_all = [float(v) for v in agg.tolist()]
     value = world * chains * steps / (total_ms_max / 1e3)
 
+    if args.profile_only:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "value": value, "ms_per_step": total_ms_max / steps}), flush=True)
+        return
     # ---------------- end to end through the public step API (host buffers, copies inside the timed region)
     from pymc_bart_b200 import BART
     from pymc_bart_b200.pgbart import PGBART

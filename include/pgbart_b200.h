@@ -88,6 +88,10 @@ typedef struct {
   int32_t error_flags;    /* 0 = clean */
   float leaf_sd;          /* running leaf sd after the step */
   int32_t iter;           /* tree updates since creation */
+  int32_t us_control;     /* wall time (us) this chain's control CTA spent in control phases */
+  int32_t us_data;        /* ... in data phases (its own share of the streams) */
+  int32_t us_sync;        /* ... waiting at the two grid barriers per phase */
+  int32_t us_total;       /* kernel wall time seen by the control CTA */
   int32_t reserved[2];
 } bk_step_stats;
 

@@ -58,6 +58,10 @@ class BkStepStats(C.Structure):
         ("error_flags", C.c_int32),
         ("leaf_sd", C.c_float),
         ("iter", C.c_int32),
+        ("us_control", C.c_int32),
+        ("us_data", C.c_int32),
+        ("us_sync", C.c_int32),
+        ("us_total", C.c_int32),
         ("reserved", C.c_int32 * 2),
     ]
 

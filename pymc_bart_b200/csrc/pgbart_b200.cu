@@ -27,6 +27,7 @@
 // round-to-nearest intrinsic in a fixed order.  No tensor cores: there is no dense
 // contraction on this path (HBM/L2-bound integer and compare work).
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -55,14 +56,33 @@
 // (compute-sanitizer synccheck: "Divergent thread(s) in warp" at a __syncthreads).  The non-aligned
 // form has per-thread arrival semantics and is legal under intra-warp divergence.
 #define BLOCK_SYNC() asm volatile("barrier.sync 0;" ::: "memory")
+#define TSUB(i)                                                              \
+  do {                                                                       \
+    if (threadIdx.x == 0) {                                                  \
+      unsigned long long now_ = globaltimer_ns();                            \
+      ctl->t_sub[i] += now_ - ctl->t_sub_last;                               \
+      ctl->t_sub_last = now_;                                                \
+    }                                                                        \
+  } while (0)
 
 
 // ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -96,6 +116,9 @@ struct CtlShared {
   int s_nn[BK_MAX_PARTICLES];
   float s_split[BK_MAX_PARTICLES];
   unsigned char row_used[2 * BK_MAX_PARTICLES];
+  int row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds (persists across phases)
+  Job jobs[BK_MAX_PARTICLES];               // staged here, copied to global by the whole CTA
+  double cum_w[BK_MAX_PARTICLES];
   int live;
   int win;
   unsigned pick;
@@ -116,7 +139,7 @@ struct DataShared {
   unsigned long long tot_acc[8];
 };
 
-union __align__(16) KernelShared {
+struct __align__(16) KernelShared {   // not a union: the control CTA's row bookkeeping persists across phases
   CtlShared ctl;
   DataShared data;
 };
@@ -128,16 +151,20 @@ __device__ __forceinline__ bool grid_sync(const Params& P, unsigned& target, int
   MARK(21);
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
+    // release: everything this CTA wrote (ordered before by the block barrier) becomes visible
+    // to whoever acquires the counter; polling is relaxed, one acquire fence at the end
     red_release_add_u32(P.barrier, 1u);
     long long t0 = clock64();
     int ab = 0;
-    while (ld_acquire_u32(P.barrier) < target) {
-      if (ld_volatile_i32(P.abort_flag)) { ab = 1; break; }
-      if (clock64() - t0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); ab = 1; break; }
+    unsigned spins = 0;
+    while (ld_relaxed_u32(P.barrier) < target) {
+      if ((++spins & 63u) == 0) {
+        if (ld_volatile_i32(P.abort_flag)) { ab = 1; break; }
+        if (clock64() - t0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); ab = 1; break; }
+      }
     }
+    fence_acq_rel_gpu();
     if (!ab && ld_volatile_i32(P.abort_flag)) ab = 1;
-    __threadfence();
     *s_abort = ab;
   }
   BLOCK_SYNC();
@@ -222,7 +249,8 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
 // normalise sh.lw[first..first+count) into sh.w, then systematic resampling into sh.anc
 // (block-wide; thread 0 does the order-dependent scalar parts in the oracle's order)
 __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, double u) {
-  __shared__ double s_max;
+  __shared__ double s_max, s_tot;
+  __shared__ double s_point[BK_MAX_PARTICLES];
   if (threadIdx.x == 0) {
     double mx = sh.lw[first];
     for (int i = 1; i < count; ++i) if (sh.lw[first + i] > mx) mx = sh.lw[first + i];
@@ -234,13 +262,26 @@ __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first
   if (threadIdx.x == 0) {
     double tot = 0.0;
     for (int i = 0; i < count; ++i) tot = BK_DADD(tot, sh.w[i]);
+    s_tot = tot;
+  }
+  BLOCK_SYNC();
+  if ((int)threadIdx.x < count) {   // the (slow) fp64 divisions in parallel, same values as the sequential form
+    sh.w[threadIdx.x] = BK_DDIV(sh.w[threadIdx.x], s_tot);
+    s_point[threadIdx.x] = BK_DDIV(BK_DADD(u, (double)threadIdx.x), (double)count);
+  }
+  BLOCK_SYNC();
+  if (threadIdx.x == 0) {   // sequential prefix sums (fixed order), nothing else
+    double a = sh.w[0];
+    sh.cum_w[0] = a;
+    for (int i = 1; i < count; ++i) { a = BK_DADD(a, sh.w[i]); sh.cum_w[i] = a; }
+  }
+  BLOCK_SYNC();
+  if ((int)threadIdx.x < count) {
+    // inverse CDF: first index whose running sum reaches the point (the walk `while (point > a) idx++`)
+    const double point = s_point[threadIdx.x];
     int idx = 0;
-    double a = BK_DDIV(sh.w[0], tot);
-    for (int i = 0; i < count; ++i) {
-      double point = BK_DDIV(BK_DADD(u, (double)i), (double)count);
-      while (point > a && idx < count - 1) { idx += 1; a = BK_DADD(a, BK_DDIV(sh.w[idx], tot)); }
-      sh.anc[i] = idx;
-    }
+    while (idx < count - 1 && point > sh.cum_w[idx]) ++idx;
+    sh.anc[threadIdx.x] = idx;
   }
   BLOCK_SYNC();
 }
@@ -274,7 +315,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared&
     nd.sr2_hi = s2.hi; nd.sr2_lo = s2.lo;
     p0->nodes[k] = nd;
   }
-  for (int r = threadIdx.x; r < P.R; r += blockDim.x) ctl->row_cnt_node[r] = -1;
+  for (int r = threadIdx.x; r < P.R; r += blockDim.x) sh.row_cnt_node[r] = -1;
   BLOCK_SYNC();
   if (threadIdx.x == 0) {
     double ssq = 0.0;
@@ -345,6 +386,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
     }
   }
   BLOCK_SYNC();
+  TSUB(4);
   // split values: one warp per growing particle
   {
     const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
@@ -358,7 +400,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
         sv = __ldg(P.X + (size_t)sh.s_v[s] * P.Npad + sh.s_k[s]);
       } else {
         int err = 0;
-        if (ctl->row_cnt_node[sh.s_row[s]] != sh.s_j[s]) err |= 1;
+        if (sh.row_cnt_node[sh.s_row[s]] != sh.s_j[s]) err |= 1;
         sv = select_split(P, c, sh.s_row[s], sh.s_j[s], sh.s_k[s], sh.s_v[s], &err);
         if (lane == 0 && err) atomicOr(&s_err, err);
       }
@@ -367,38 +409,53 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       BLOCK_SYNC();
       if (threadIdx.x == 0 && s_err) ctl->c_err |= s_err;
   }
-  // rows + job list (sequential: deterministic placement)
+  // rows + job list (sequential: deterministic placement; shared memory only)
   __shared__ int s_njobs;
+  if ((int)threadIdx.x < P.R) sh.row_used[threadIdx.x] = 0;
+  BLOCK_SYNC();
+  if (threadIdx.x >= 1 && (int)threadIdx.x < P.P && sh.s_row[threadIdx.x] >= 0) sh.row_used[sh.s_row[threadIdx.x]] = 1;
+  BLOCK_SYNC();
   if (threadIdx.x == 0) {
-    for (int r = 0; r < P.R; ++r) sh.row_used[r] = 0;
-    for (int s = 0; s < P.P; ++s) { int r = part_ptr(P, c, buf, s)->row; if (r >= 0) sh.row_used[r] = 1; }
-    int nj = 0, free_r = 0;
+    int nj = 0, free_r = 0, errs = 0, cnt_passes = 0;
     for (int s = 1; s < P.P; ++s) {
-      if (sh.s_kind[s] == 1) {
+      const int kind = sh.s_kind[s];
+      if (kind == 1) {
         while (free_r < P.R && sh.row_used[free_r]) free_r++;
-        Job jb; memset(&jb, 0, sizeof(jb));
+        Job jb;
         jb.kind = BK_JOB_PARTITION; jb.slot = s; jb.src_row = sh.s_row[s]; jb.dst_row = free_r;
         jb.node = sh.s_j[s]; jb.var = sh.s_v[s]; jb.split = sh.s_split[s]; jb.left_id = sh.s_nn[s];
-        jb.next_node = sh.s_next[s]; jb.rule = P.rules[sh.s_v[s]];
-        if (free_r >= P.R) { ctl->c_err |= 8; jb.dst_row = 0; }
-        else { sh.row_used[free_r] = 1; ctl->row_cnt_node[free_r] = jb.next_node; }
-        ctl->jobs[nj++] = jb;
-      } else if (sh.s_kind[s] == 2) {
-        int r = sh.s_row[s];
-        if (r >= 0 && ctl->row_cnt_node[r] != sh.s_next[s]) {
-          Job jb; memset(&jb, 0, sizeof(jb));
-          jb.kind = BK_JOB_COUNT; jb.slot = s; jb.src_row = r; jb.dst_row = r; jb.node = -1; jb.var = 0;
-          jb.next_node = sh.s_next[s];
-          ctl->row_cnt_node[r] = sh.s_next[s];
-          ctl->jobs[nj++] = jb;
-          ctl->c_count_passes += 1;
+        jb.next_node = sh.s_next[s]; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
+        if (free_r >= P.R) { errs |= 8; jb.dst_row = 0; }
+        else { sh.row_used[free_r] = 1; sh.row_cnt_node[free_r] = jb.next_node; }
+        sh.jobs[nj++] = jb;
+      } else if (kind == 2) {
+        const int r = sh.s_row[s];
+        if (r >= 0 && sh.row_cnt_node[r] != sh.s_next[s]) {
+          Job jb;
+          jb.kind = BK_JOB_COUNT; jb.slot = s; jb.src_row = r; jb.dst_row = r; jb.node = -1; jb.var = 0; jb.split = 0.0f;
+          jb.left_id = 0; jb.next_node = sh.s_next[s]; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
+          sh.row_cnt_node[r] = sh.s_next[s];
+          sh.jobs[nj++] = jb;
+          cnt_passes += 1;
         }
       }
     }
     ctl->n_jobs = nj;
+    if (cnt_passes) ctl->c_count_passes += cnt_passes;
+    if (errs) ctl->c_err |= errs;
     s_njobs = nj;
   }
   BLOCK_SYNC();
+  {  // publish the job list: split rule looked up and 48-byte descriptors stored by many threads
+    const int nj = s_njobs;
+    if ((int)threadIdx.x < nj && sh.jobs[threadIdx.x].kind == BK_JOB_PARTITION) sh.jobs[threadIdx.x].rule = P.rules[sh.jobs[threadIdx.x].var];
+    BLOCK_SYNC();
+    const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
+    uint4* d4 = reinterpret_cast<uint4*>(ctl->jobs);
+    for (int i = threadIdx.x; i < nj * 3; i += blockDim.x) d4[i] = s4[i];
+  }
+  BLOCK_SYNC();
+  TSUB(6);
   return s_njobs;
 }
 
@@ -530,6 +587,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
   }
   BLOCK_SYNC();
   int stage = s_stage;
+  if (threadIdx.x == 0) { ctl->t_sub_last = globaltimer_ns(); if (first_phase) for (int i = 0; i < 8; ++i) ctl->t_sub[i] = 0; }
   MARK(100 + stage);
   if (stage == BK_ST_DONE) return;
   if (threadIdx.x == 0) ctl->c_phases += 1;
@@ -582,6 +640,8 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
         st.grow_root = ctl->c_grow_root; st.count_passes = ctl->c_count_passes; st.phases = ctl->c_phases;
         st.trace_len = ctl->trace_round_base; st.error_flags = ctl->c_err | (ctl->trace_round_base > P.trace_cap && P.trace_cap > 0 ? 1 : 0);
         st.leaf_sd = ctl->leaf_sd; st.iter = ctl->iter;
+        st.us_control = (int32_t)(ctl->t_control / 1000ull); st.us_data = (int32_t)(ctl->t_data / 1000ull);
+        st.us_sync = (int32_t)(ctl->t_sync / 1000ull); st.us_total = (int32_t)((globaltimer_ns() - ctl->t_start) / 1000ull);
         P.stats[c] = st;
       }
     }
@@ -589,10 +649,12 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     if (!s_more) return;
     MARK(110);
     init_particles(P, c, ctl, sh);
+    TSUB(7);
     MARK(111);
   } else {  // BK_ST_WAIT_ROUND
     MARK(120);
     finalize_grows(P, c, ctl);
+    TSUB(0);
     MARK(121);
     have_round = true;
   }
@@ -616,11 +678,13 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       BLOCK_SYNC();
       if (threadIdx.x == 0) ctl->trace_round_base = rbase + (P.P - 1);
       MARK(130 + live);
-      if (!live) { BLOCK_SYNC(); finish_tree(P, c, ctl, sh); MARK(139); return; }
+      TSUB(1);
+      if (!live) { BLOCK_SYNC(); finish_tree(P, c, ctl, sh); TSUB(7); MARK(139); return; }
       double u = bk_u01(bk_rng(P.seed, P.chain_base + (uint32_t)c, (uint32_t)ctl->draw, 0, (uint32_t)ctl->cur_tree,
                                (uint32_t)ctl->round, 0, BK_U_RESAMPLE).v[0]);
       MARK(132);
       normalise_and_resample(P, sh, 1, P.P - 1, u);
+      TSUB(2);
       MARK(133);
       // anc[i] indexes particles 1..P-1; convert to slot -> source slot
       __shared__ int s_src[BK_MAX_PARTICLES];
@@ -632,6 +696,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       BLOCK_SYNC();
       MARK(134);
       copy_particles(P, c, buf, s_src);
+      TSUB(3);
       MARK(135);
       if (threadIdx.x == 0) { ctl->buf = buf ^ 1; ctl->round += 1; }
       BLOCK_SYNC();
@@ -765,6 +830,9 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
   const size_t base = (size_t)ctile * BK_COMMIT_TILE + (size_t)threadIdx.x * 4;
   long long t_sst = 0, t_sr = 0, t_sd = 0;
   unsigned long long t_r2 = 0;
+  unsigned pro_pid4 = 0xFFFFFFFFu;
+  int pro_valid = 0;
+  int pro_q[4] = {0, 0, 0, 0};
   if (base < (size_t)P.Npad) {
     float* stp = P.st + (size_t)c * P.Npad + base;
     float4 st4 = __ldcg(reinterpret_cast<const float4*>(stp));
@@ -825,15 +893,38 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
         if (base + e < (size_t)P.N) {
           unsigned long long sq = (unsigned long long)((long long)a * (long long)a);
           t_sst += b; t_sr += a; t_r2 += sq;
-          if (pid != BK_LIMBO) {
-            atomicAdd(&sh.leaf_acc[pid * 3 + 0], (unsigned long long)(long long)a);
-            atomicAdd(&sh.leaf_acc[pid * 3 + 1], sq & 0xFFFFFFFFull);
-            atomicAdd(&sh.leaf_acc[pid * 3 + 2], sq >> 32);
-          }
         }
       }
+      pro_pid4 = pid4; pro_valid = 1;
+      pro_q[0] = qrv[0]; pro_q[1] = qrv[1]; pro_q[2] = qrv[2]; pro_q[3] = qrv[3];
       __stcg(reinterpret_cast<int4*>(P.qr + (size_t)c * P.Npad + base), make_int4(qrv[0], qrv[1], qrv[2], qrv[3]));
       __stcg(reinterpret_cast<int4*>(P.qst + (size_t)c * P.Npad + base), make_int4(qsv[0], qsv[1], qsv[2], qsv[3]));
+    }
+  }
+  // per-leaf statistics of the old tree: lanes holding the same leaf id are grouped with
+  // match.any and summed with redux.sync on 16-bit chunks (exact), one shared-memory atomic
+  // per (warp, leaf) instead of one per row
+  if (do_pro) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned pid = (pro_pid4 >> (8 * e)) & 255u;
+      const bool ok = pro_valid && pid != BK_LIMBO && base + e < (size_t)P.N;
+      const unsigned key = ok ? pid : 0x100u;
+      const unsigned grp = __match_any_sync(0xffffffffu, key);
+      const int a = ok ? pro_q[e] : 0;
+      const unsigned long long sq = (unsigned long long)((long long)a * (long long)a);
+      const unsigned r_lo = __reduce_add_sync(grp, (unsigned)a & 0xFFFFu);
+      const int r_hi = __reduce_add_sync(grp, a >> 16);
+      const unsigned c0 = __reduce_add_sync(grp, (unsigned)(sq & 0xFFFFull));
+      const unsigned c1 = __reduce_add_sync(grp, (unsigned)((sq >> 16) & 0xFFFFull));
+      const unsigned c2 = __reduce_add_sync(grp, (unsigned)((sq >> 32) & 0xFFFFull));
+      const unsigned c3 = __reduce_add_sync(grp, (unsigned)(sq >> 48));
+      if (ok && (int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+        const long long sr = (long long)r_hi * 65536ll + (long long)r_lo;
+        atomicAdd(&sh.leaf_acc[pid * 3 + 0], (unsigned long long)sr);
+        atomicAdd(&sh.leaf_acc[pid * 3 + 1], (unsigned long long)c0 + ((unsigned long long)c1 << 16));
+        atomicAdd(&sh.leaf_acc[pid * 3 + 2], (unsigned long long)c2 + ((unsigned long long)c3 << 16));
+      }
     }
   }
   // block totals
@@ -875,9 +966,14 @@ pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sig
   for (int phase = 0; phase < max_phases; ++phase) {
     // ---- control
     MARK(1);
+    const bool timing = blockIdx.x < P.C && threadIdx.x == 0;
+    unsigned long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
+    if (timing) tq0 = globaltimer_ns();
     for (int c = blockIdx.x; c < P.C; c += gridDim.x) control_step(P, c, phase, tune, sigma_in, sh.ctl);
     MARK(2);
+    if (timing) tq1 = globaltimer_ns();
     if (grid_sync(P, target, &s_abort, phase)) return;
+    if (timing) tq2 = globaltimer_ns();
     MARK(3);
     // ---- plan the data phase (every CTA builds the same small table)
     if (threadIdx.x == 0) {
@@ -935,7 +1031,14 @@ pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sig
       }
     }
     MARK(6);
+    if (timing) tq3 = globaltimer_ns();
     if (grid_sync(P, target, &s_abort, phase)) return;
+    if (timing) {
+      ChainCtl* tc = P.ctl + blockIdx.x;
+      unsigned long long tq4 = globaltimer_ns();
+      if (phase == 0) { tc->t_control = 0; tc->t_data = 0; tc->t_sync = 0; tc->t_start = tq0; }
+      tc->t_control += tq1 - tq0; tc->t_sync += (tq2 - tq1) + (tq4 - tq3); tc->t_data += tq3 - tq2;
+    }
     MARK(7);
   }
 }
@@ -1244,6 +1347,13 @@ int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_
 }
 
 void* bk_stream(bk_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+/* debug only: control sub-step timers (ns) of the last step */
+int bk_debug_timers(bk_handle* h, int chain, unsigned long long* out8) {
+  if (!h || chain < 0 || chain >= h->P.C) return BK_ERR_ARG;
+  ChainCtl* c = h->P.ctl + chain;
+  return cudaMemcpy(out8, (char*)c + offsetof(ChainCtl, t_sub), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? BK_OK : BK_ERR_CUDA;
+}
 
 /* debug only (not part of the public header): host view of the per-warp progress markers */
 int32_t* bk_debug_markers(bk_handle* h, int* count) {

@@ -115,6 +115,9 @@ struct __align__(16) ChainCtl {
   // --- counters (bk_step_stats)
   int32_t c_tree_updates, c_rounds, c_grow, c_grow_root, c_count_passes, c_phases, c_err;
   int32_t pad0;
+  unsigned long long t_control, t_data, t_sync, t_start;  // ns (globaltimer), control CTA only
+  unsigned long long t_sub_last;
+  unsigned long long t_sub[8];  // control sub-steps: finalize, weights, resample, copy, propose, select, jobs, finish/init
   int32_t row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds
   float old_vals[256];  // leaf values of the tree being replaced
   float new_vals[256];  // leaf values of the winning particle
