@@ -9,6 +9,25 @@ from __future__ import annotations
 import numpy as np
 
 
+def chain_base_for_rank(rank: int, chains_per_rank: int) -> int:
+    """Global index of a rank's first chain: chain c of rank r draws from Philox key (seed, r*C + c),
+    so a chain's stream does not depend on which GPU runs it."""
+    return int(rank) * int(chains_per_rank)
+
+
+def gather_posterior(local, world: int):
+    """The single collective of a run: all-gather of per-rank draws [C, ...] -> [world*C, ...].
+    `local` is a torch tensor on the backend's device (CUDA for NCCL, CPU for gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    if world <= 1:
+        return local
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local.contiguous())
+    return torch.cat(gathered, dim=0)
+
+
 def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1), sigma=1.0, seed=0,
            likelihood="normal", sigma_fn=None, keep_draws=True, **step_kwargs):
     """Returns a dict: posterior (chains_total, draws, N) float32 [if keep_draws],
@@ -23,7 +42,7 @@ def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1)
     world = dist.get_world_size() if distributed else 1
     device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     step = PGBART([rv], num_particles=num_particles, batch=batch, likelihood=likelihood, sigma=sigma, chains=chains,
-                  chain_base=rank * chains, seed=seed, device=device, **step_kwargs)
+                  chain_base=chain_base_for_rank(rank, chains), seed=seed, device=device, **step_kwargs)
     N = step.n_rows
     post = np.empty((chains, draws, N), dtype=np.float32) if keep_draws else None
     vi = [[None] * draws for _ in range(chains)]
@@ -44,8 +63,5 @@ def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1)
     out = {"step": step, "variable_inclusion": vi, "posterior": post, "rank": rank, "world": world}
     if distributed and world > 1 and keep_draws:
         # the single collective of the run: all-gather of the posterior draws over NVLink
-        loc = torch.from_numpy(post).cuda()
-        gathered = [torch.empty_like(loc) for _ in range(world)]
-        dist.all_gather(gathered, loc)
-        out["posterior"] = torch.cat(gathered, dim=0).cpu().numpy()
+        out["posterior"] = gather_posterior(torch.from_numpy(post).cuda(), world).cpu().numpy()
     return out

@@ -69,18 +69,24 @@ class PosteriorSampler:
         if split_rules is not None:
             self.rules_dev = torch.from_numpy(np.ascontiguousarray(split_rules, dtype=np.int32)).to(self.device)
 
-    @classmethod
-    def from_history(cls, batches, baseline_forest, m, n_outputs, split_rules=None, device: int = 0):
-        """Rebuild per-draw forests from the initial forest plus per-draw deltas
-        (pymc_bart/utils.py:124-127; CHANGELOG.md:23 "Better tree storage")."""
+    @staticmethod
+    def rebuild_forests(batches, baseline_forest, m) -> np.ndarray:
+        """Initial forest + per-draw deltas -> [n_draws][m][255] nodes (pure numpy)."""
         base_nodes, _ = baseline_forest
         cur = np.array(base_nodes, dtype=_cabi.NODE_DTYPE, copy=True)
-        assert cur.shape[0] == m
+        if cur.shape[0] != m:
+            raise ValueError("baseline forest does not hold m trees")
         forests = np.zeros((len(batches), m, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
         for d, (first, nodes, _nn) in enumerate(batches):
             cur[first:first + nodes.shape[0]] = nodes
             forests[d] = cur
-        return cls(forests, n_outputs=n_outputs, split_rules=split_rules, device=device)
+        return forests
+
+    @classmethod
+    def from_history(cls, batches, baseline_forest, m, n_outputs, split_rules=None, device: int = 0):
+        """Rebuild per-draw forests from the initial forest plus per-draw deltas
+        (pymc_bart/utils.py:124-127; CHANGELOG.md:23 "Better tree storage")."""
+        return cls(cls.rebuild_forests(batches, baseline_forest, m), n_outputs=n_outputs, split_rules=split_rules, device=device)
 
     @property
     def n_draws(self) -> int:

@@ -1,0 +1,47 @@
+"""Generates tests/golden/*.npz with the CPU oracle (run from the repo root:
+`python tests/golden/make_golden.py`).  The reference itself cannot produce vectors here:
+its sampler is the un-vendored `bartrs` (requirements.txt:6) and `import pymc` fails offline,
+so these fixtures pin OUR restatement (parity with the reference stays "unpinned").
+They let the GPU tests check the CUDA path against stored outputs even without rebuilding the oracle.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+from helpers import friedman  # noqa: E402
+from oracle.oracle_py import OracleChain  # noqa: E402
+from pymc_bart_b200.settings import make_settings  # noqa: E402
+
+CASES = {
+    # name: (N, p, m, P, draws, seed, depth_offset)
+    "c1_n200_p5_m10_P20": (200, 5, 10, 20, 40, 1, 0),
+    "ragged_n777_p7_m12_P9": (777, 7, 12, 9, 20, 3, 0),
+    "hist_n300_p4_m6_P16": (300, 4, 6, 16, 20, 5, 1),
+}
+
+
+def run_case(N, p, m, P, draws, seed, depth_offset):
+    X, y, _ = friedman(N, p, seed)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=depth_offset, trace_capacity=20000)
+    o = OracleChain(s, X.T.copy(), y)
+    traces, sums, vis, sds = [], [], [], []
+    for d in range(draws):
+        vi, st = o.step(d < draws // 2, 1.0)
+        traces.append(o.trace().copy())
+        sums.append(o.sum_trees().copy())
+        vis.append(vi.copy())
+        sds.append(np.float32(st.leaf_sd))
+    nodes, nn = o.forest()
+    return dict(trace=np.concatenate(traces), trace_len=np.array([len(t) for t in traces]), sum_trees=np.stack(sums),
+                vi=np.stack(vis), leaf_sd=np.array(sds, dtype=np.float32), forest=nodes, forest_nn=nn, leaf_ids=o.leaf_ids())
+
+
+if __name__ == "__main__":
+    out = os.path.dirname(os.path.abspath(__file__))
+    for name, cfg in CASES.items():
+        np.savez_compressed(os.path.join(out, name + ".npz"), cfg=np.array(cfg), **run_case(*cfg))
+        print("wrote", name)

@@ -1,0 +1,150 @@
+"""The CPU oracle against (a) its committed golden fixtures, (b) published Philox known answers,
+(c) libm for the hand-written transcendental kernels, (d) the reference's statistical tests
+re-expressed without PyMC (tests/test_bart.py:44-64 VI dominance; tests/test_utils.py:24-32
+prediction self-consistency)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import assert_trace_equal, friedman
+from oracle import oracle_py
+from oracle.oracle_py import OracleChain
+from pymc_bart_b200 import _cabi
+from pymc_bart_b200.settings import make_settings
+from pymc_bart_b200.utils import _decode_vi, _encode_vi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("name", ["c1_n200_p5_m10_P20", "ragged_n777_p7_m12_P9", "hist_n300_p4_m6_P16"])
+def test_oracle_matches_golden(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    N, p, m, P, draws, seed, off = [int(v) for v in g["cfg"]]
+    X, y, _ = friedman(N, p, seed)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=off, trace_capacity=20000)
+    o = OracleChain(s, X.T.copy(), y)
+    pos = 0
+    for d in range(draws):
+        vi, st = o.step(d < draws // 2, 1.0)
+        n = int(g["trace_len"][d])
+        assert_trace_equal(o.trace(), g["trace"][pos:pos + n], f"{name} draw {d}")
+        pos += n
+        assert np.array_equal(o.sum_trees().view(np.uint32), g["sum_trees"][d].view(np.uint32))
+        assert np.array_equal(vi, g["vi"][d])
+    nodes, nn = o.forest()
+    assert np.array_equal(nn, g["forest_nn"]) and np.array_equal(nodes.view(np.uint8), g["forest"].view(np.uint8))
+    assert np.array_equal(o.leaf_ids(), g["leaf_ids"])
+
+
+def _spec_probe():
+    """Small C program over include/bk_spec.h: Philox KATs + max error of the math kernels vs libm."""
+    src = r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "bk_spec.h"
+int main(void){
+  bk_u32x4 a=bk_philox(0,0,0,0,0,0), b=bk_philox(0xffffffffu,0xffffffffu,0xffffffffu,0xffffffffu,0xffffffffu,0xffffffffu);
+  bk_u32x4 c=bk_philox(0xa4093822u,0x299f31d0u,0x243f6a88u,0x85a308d3u,0x13198a2eu,0x03707344u);
+  printf("%08x %08x %08x %08x\n%08x %08x %08x %08x\n%08x %08x %08x %08x\n",a.v[0],a.v[1],a.v[2],a.v[3],b.v[0],b.v[1],b.v[2],b.v[3],c.v[0],c.v[1],c.v[2],c.v[3]);
+  double me=0,ml=0,mc=0; srand(7);
+  for(int i=0;i<400000;i++){ double x=-700.0*rand()/RAND_MAX, e=fabs(bk_exp(x)-exp(x))/exp(x); if(e>me)me=e;
+    double y=exp(-40+80.0*rand()/RAND_MAX), l=fabs(bk_log(y)-log(y)); if(l>ml)ml=l;
+    uint32_t u=(uint32_t)rand()*2u+(rand()&1u); double d=fabs(bk_cos2pi(u)-cos(2*M_PI*(u/4294967296.0))); if(d>mc)mc=d; }
+  printf("%.3e %.3e %.3e\n",me,ml,mc);
+  double s=0,s2=0; int n=400000; for(int i=0;i<n;i++){ double z=bk_normal(bk_rng(1,2,i,0,0,0,0,3)); s+=z; s2+=z*z; }
+  printf("%.5f %.5f\n", s/n, s2/n);
+  printf("%d %d\n", bk_quant(1.0f, 1024.0f), bk_quant(-1e30f, 1024.0f));
+  return 0; }
+'''
+    d = os.path.join(ROOT, "oracle", "_probe")
+    os.makedirs(d, exist_ok=True)
+    cfile, exe = os.path.join(d, "probe.c"), os.path.join(d, "probe")
+    open(cfile, "w").write(src)
+    subprocess.run(["gcc", "-O2", "-march=x86-64-v3", "-ffp-contract=off", f"-I{ROOT}/include", cfile, "-o", exe, "-lm"], check=True)
+    return subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+
+
+def test_spec_header_known_answers():
+    out = _spec_probe()
+    # Random123 known-answer vectors for Philox4x32-10
+    assert out[0] == "6627e8d5 e169c58d bc57ac4c 9b00dbd8"
+    assert out[1] == "408f276d 41c83b0e a20bc7c6 6d5451fd"
+    assert out[2] == "d16cfe09 94fdcceb 5001e420 24126ea1"
+    me, ml, mc = [float(v) for v in out[3].split()]
+    assert me < 1e-15 and ml < 1e-14 and mc < 2e-15
+    mean, var = [float(v) for v in out[4].split()]
+    assert abs(mean) < 0.01 and abs(var - 1) < 0.01
+    assert out[5].split() == ["1024", str(-(2**29 - 1))]
+
+
+def test_vi_dominance_statistical():
+    """tests/test_bart.py:44-64 without PyMC: X[:,0] ~ Y => variable 0 dominates the inclusion counts."""
+    rng = np.random.default_rng(3415)
+    X = rng.normal(0, 1, size=(250, 3))
+    Y = rng.normal(0, 1, size=250)
+    X[:, 0] = rng.normal(Y, 0.1)
+    s = make_settings(X, Y, m=10, num_particles=10, seed=3415)
+    o = OracleChain(s, np.ascontiguousarray(X.T, dtype=np.float32), Y.astype(np.float32))
+    tot = np.zeros(3, dtype=np.int64)
+    for d in range(400):
+        vi, _ = o.step(d < 200, 1.0)
+        if d >= 200:
+            tot += np.asarray(_decode_vi(_encode_vi(vi.tolist()), 3))
+    frac = tot / tot.sum()
+    assert frac[0] > frac[1:].sum()
+
+
+def test_fit_improves_and_is_deterministic():
+    X, y, f = friedman(1500, 8, 21)
+    s = make_settings(X, y, m=30, num_particles=12, seed=21)
+    a = OracleChain(s, X.T.copy(), y)
+    b = OracleChain(s, X.T.copy(), y)
+    r0 = float(np.sqrt(np.mean((a.sum_trees() - f) ** 2)))
+    for d in range(120):
+        a.step(d < 60, 1.0); b.step(d < 60, 1.0)
+    assert np.array_equal(a.sum_trees(), b.sum_trees())
+    r1 = float(np.sqrt(np.mean((a.sum_trees() - f) ** 2)))
+    assert r1 < 0.45 * r0
+    # chains differ only through the Philox key
+    c = OracleChain(s, X.T.copy(), y, chain=1)
+    c.step(True, 1.0)
+    b2 = OracleChain(s, X.T.copy(), y, chain=0)
+    b2.step(True, 1.0)
+    assert not np.array_equal(c.sum_trees(), b2.sum_trees())
+
+
+def test_prediction_self_consistency_and_in_sample():
+    """tests/test_utils.py:24-32: predicting X[:10] equals the first 10 rows of predicting X;
+    additionally the stored forest reproduces the sampler's own in-sample sum of trees."""
+    X, y, _ = friedman(300, 5, 9)
+    s = make_settings(X, y, m=8, num_particles=8, seed=9)
+    o = OracleChain(s, X.T.copy(), y)
+    for d in range(30):
+        o.step(d < 15, 1.0)
+    nodes, _ = o.forest()
+    forests = nodes[None]
+    all_ = oracle_py.predict(forests, X, [0])
+    first = oracle_py.predict(forests, X[:10], [0])
+    assert np.array_equal(all_[0, :10], first[0])
+    np.testing.assert_allclose(all_[0], o.sum_trees(), rtol=0, atol=2e-4)
+    # excluding every variable collapses each tree to its training-weighted mean leaf
+    ex = oracle_py.predict(forests, X[:5], [0], excluded_mask=np.ones(5, np.uint8))
+    assert np.allclose(ex[0], ex[0][0])
+
+
+def test_edge_cases():
+    # N smaller than a tile, constant response, two rows
+    for N, p, m, P in [(2, 1, 2, 3), (5, 3, 1, 2)]:
+        X = np.random.default_rng(N).uniform(size=(N, p)).astype(np.float32)
+        y = np.zeros(N, dtype=np.float32) + 3.0
+        s = make_settings(X, y, m=m, num_particles=P, seed=1)
+        o = OracleChain(s, X.T.copy(), y)
+        for d in range(10):
+            vi, st = o.step(d < 5, 1.0)
+            assert st.error_flags == 0
+        assert np.all(np.isfinite(o.sum_trees()))
