@@ -335,12 +335,18 @@ BK_HD double bk_leaf_ssq(bk_stats s, float mu, double inv_qscale) {
   double t = BK_DFMA(m, (double)s.n, BK_DMUL(-2.0, r1));
   return BK_DFMA(m, t, r2);
 }
-/* Gaussian log-likelihood of all N rows given the summed per-leaf ssq */
-BK_HD double bk_normal_loglik(double ssq, float sigma, double n_rows) {
+/* Gaussian log-likelihood of all N rows given the summed per-leaf ssq:
+ * lw = -ssq * inv2s2 + c with the two per-step constants below */
+BK_HD double bk_normal_inv2s2(float sigma) {
   double s = (double)sigma;
-  double inv2s2 = BK_DDIV(0.5, BK_DMUL(s, s));
-  double c = BK_DMUL(-n_rows, BK_DADD(bk_log(s), BK_HALF_LOG_2PI));
-  return BK_DFMA(-ssq, inv2s2, c);
+  return BK_DDIV(0.5, BK_DMUL(s, s));
+}
+BK_HD double bk_normal_const(float sigma, double n_rows) {
+  return BK_DMUL(-n_rows, BK_DADD(bk_log((double)sigma), BK_HALF_LOG_2PI));
+}
+BK_HD double bk_normal_loglik_pre(double ssq, double inv2s2, double c) { return BK_DFMA(-ssq, inv2s2, c); }
+BK_HD double bk_normal_loglik(double ssq, float sigma, double n_rows) {
+  return bk_normal_loglik_pre(ssq, bk_normal_inv2s2(sigma), bk_normal_const(sigma, n_rows));
 }
 
 /* Bernoulli-logit per-row term y*f - softplus(f), in float with a fixed

@@ -103,6 +103,7 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 // ~4 s at 1.9 GHz: a barrier that is not reached means a bug; every CTA bails out
 #define BK_BARRIER_TIMEOUT_CYCLES (8000000000LL)
 
+#define BK_CUM_SMEM 1024
 struct CtlShared {
   double w[BK_MAX_PARTICLES];
   double lw[BK_MAX_PARTICLES];
@@ -119,6 +120,7 @@ struct CtlShared {
   int row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds (persists across phases)
   Job jobs[BK_MAX_PARTICLES];               // staged here, copied to global by the whole CTA
   double cum_w[BK_MAX_PARTICLES];
+  double cum_prior[BK_CUM_SMEM];   // normalised cumulative split prior (first BK_CUM_SMEM columns)
   int live;
   int win;
   unsigned pick;
@@ -195,26 +197,33 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
   const unsigned* cnt = P.rowcnt + ((size_t)c * P.R + row) * P.ntiles;
   unsigned run = 0, off = 0;
   int tile = -1;
-  for (int t0 = 0; t0 < P.ntiles; t0 += 32) {
-    int t = t0 + lane;
-    unsigned v = t < P.ntiles ? __ldcg(cnt + t) : 0u;
-    unsigned incl = v;
+  // eight 32-tile chunks of counts are fetched together (independent L2 loads), then scanned in order
+  for (int t0 = 0; t0 < P.ntiles && tile < 0; t0 += 256) {
+    unsigned vv[8];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += nb;
+    for (int j = 0; j < 8; ++j) { int t = t0 + j * 32 + lane; vv[j] = t < P.ntiles ? __ldcg(cnt + t) : 0u; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (tile >= 0) break;
+      const unsigned v = vv[j];
+      unsigned incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+      }
+      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+      if (k < run + total) {
+        const unsigned excl = incl - v;
+        const bool here = (k >= run + excl) && (k < run + incl);
+        const unsigned b = __ballot_sync(0xffffffffu, here);
+        const int src = __ffs(b) - 1;
+        tile = t0 + j * 32 + src;
+        off = k - (run + __shfl_sync(0xffffffffu, excl, src));
+      } else {
+        run += total;
+      }
     }
-    unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    if (k < run + total) {
-      unsigned excl = incl - v;
-      bool here = (k >= run + excl) && (k < run + incl);
-      unsigned b = __ballot_sync(0xffffffffu, here);
-      int src = __ffs(b) - 1;
-      tile = t0 + src;
-      off = k - (run + __shfl_sync(0xffffffffu, excl, src));
-      break;
-    }
-    run += total;
   }
   if (tile < 0) { if (lane == 0) *err |= 2; return 0.0f; }
   const uint8_t* rp = P.rows + ((size_t)c * P.R + row) * P.Npad + (size_t)tile * BK_WARP_TILE + lane * BK_ROWS_PER_LANE;
@@ -248,40 +257,36 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
 
 // normalise sh.lw[first..first+count) into sh.w, then systematic resampling into sh.anc
 // (block-wide; thread 0 does the order-dependent scalar parts in the oracle's order)
+// normalise sh.lw[first..first+count) and resample systematically into sh.anc[0..count).
+// Runs in warp 0 (count <= 128: four values per lane); order-dependent parts (sum, prefix sums)
+// are done by lane 0 in the oracle's order, the rest is lane-parallel.  Ends with a block barrier.
 __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, double u) {
-  __shared__ double s_max, s_tot;
-  __shared__ double s_point[BK_MAX_PARTICLES];
-  if (threadIdx.x == 0) {
-    double mx = sh.lw[first];
-    for (int i = 1; i < count; ++i) if (sh.lw[first + i] > mx) mx = sh.lw[first + i];
-    s_max = mx;
-  }
-  BLOCK_SYNC();
-  if ((int)threadIdx.x < count) sh.w[threadIdx.x] = bk_weight_term(sh.lw[first + threadIdx.x], s_max);
-  BLOCK_SYNC();
-  if (threadIdx.x == 0) {
+  if ((threadIdx.x >> 5) == 0) {
+    const int lane = threadIdx.x & 31;
+    double mx = -1.7976931348623157e308;
+    for (int i = lane; i < count; i += 32) { double v = sh.lw[first + i]; mx = v > mx ? v : mx; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { double ov = __shfl_xor_sync(0xffffffffu, mx, o); mx = ov > mx ? ov : mx; }
+    for (int i = lane; i < count; i += 32) sh.w[i] = bk_weight_term(sh.lw[first + i], mx);
+    __syncwarp();
     double tot = 0.0;
-    for (int i = 0; i < count; ++i) tot = BK_DADD(tot, sh.w[i]);
-    s_tot = tot;
-  }
-  BLOCK_SYNC();
-  if ((int)threadIdx.x < count) {   // the (slow) fp64 divisions in parallel, same values as the sequential form
-    sh.w[threadIdx.x] = BK_DDIV(sh.w[threadIdx.x], s_tot);
-    s_point[threadIdx.x] = BK_DDIV(BK_DADD(u, (double)threadIdx.x), (double)count);
-  }
-  BLOCK_SYNC();
-  if (threadIdx.x == 0) {   // sequential prefix sums (fixed order), nothing else
-    double a = sh.w[0];
-    sh.cum_w[0] = a;
-    for (int i = 1; i < count; ++i) { a = BK_DADD(a, sh.w[i]); sh.cum_w[i] = a; }
-  }
-  BLOCK_SYNC();
-  if ((int)threadIdx.x < count) {
-    // inverse CDF: first index whose running sum reaches the point (the walk `while (point > a) idx++`)
-    const double point = s_point[threadIdx.x];
-    int idx = 0;
-    while (idx < count - 1 && point > sh.cum_w[idx]) ++idx;
-    sh.anc[threadIdx.x] = idx;
+    if (lane == 0) for (int i = 0; i < count; ++i) tot = BK_DADD(tot, sh.w[i]);
+    tot = __shfl_sync(0xffffffffu, tot, 0);
+    for (int i = lane; i < count; i += 32) sh.w[i] = BK_DDIV(sh.w[i], tot);
+    __syncwarp();
+    if (lane == 0) {
+      double a = sh.w[0];
+      sh.cum_w[0] = a;
+      for (int i = 1; i < count; ++i) { a = BK_DADD(a, sh.w[i]); sh.cum_w[i] = a; }
+    }
+    __syncwarp();
+    for (int i = lane; i < count; i += 32) {
+      // inverse CDF: first index whose running sum reaches the point (the walk `while (point > a) idx++`)
+      const double point = BK_DDIV(BK_DADD(u, (double)i), (double)count);
+      int idx = 0;
+      while (idx < count - 1 && point > sh.cum_w[idx]) ++idx;
+      sh.anc[i] = idx;
+    }
   }
   BLOCK_SYNC();
 }
@@ -316,6 +321,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared&
     p0->nodes[k] = nd;
   }
   for (int r = threadIdx.x; r < P.R; r += blockDim.x) sh.row_cnt_node[r] = -1;
+  for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += blockDim.x) sh.cum_prior[v] = P.cum[(size_t)c * P.p + v];
   BLOCK_SYNC();
   if (threadIdx.x == 0) {
     double ssq = 0.0;
@@ -324,7 +330,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared&
       if (nd.var < 0) ssq = BK_DADD(ssq, bk_leaf_ssq(node_stats(nd), nd.value, P.inv_qscale));
     }
     p0->n_nodes = nn; p0->q_head = nn; p0->row = BK_ROW_FOREST;
-    p0->ssq = ssq; p0->lw = bk_normal_loglik(ssq, ctl->sigma, (double)P.N);
+    p0->ssq = ssq; p0->lw = bk_normal_loglik_pre(ssq, ctl->ll_inv2s2, ctl->ll_c);
     ctl->buf = 0; ctl->round = 0;
   }
   const int q = threadIdx.x;
@@ -341,7 +347,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared&
     S->nodes[0] = nd;
     S->n_nodes = 1; S->q_head = 0; S->row = BK_ROW_VIRTUAL;
     S->ssq = bk_leaf_ssq(tot, P.init_leaf, P.inv_qscale);
-    S->lw = bk_normal_loglik(S->ssq, ctl->sigma, (double)P.N);
+    S->lw = bk_normal_loglik_pre(S->ssq, ctl->ll_inv2s2, ctl->ll_c);
   }
   BLOCK_SYNC();
 }
@@ -367,7 +373,11 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
         double u2 = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAR).v[0]);
         const double* cum = P.cum + (size_t)c * P.p;
         int lo = 0, hi = P.p - 1;  // first index with u2 < cum[idx], else p-1
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (u2 < cum[mid]) hi = mid; else lo = mid + 1; }
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          const double cv = mid < BK_CUM_SMEM ? sh.cum_prior[mid] : cum[mid];
+          if (u2 < cv) hi = mid; else lo = mid + 1;
+        }
         v = lo;
         if (n >= 2) {
           k = bk_index(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAL).v[0], (uint32_t)n);
@@ -495,7 +505,7 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl) {
     S->n_nodes = nn + 2;
     double ssq = BK_DADD(BK_DADD(BK_DSUB(S->ssq, c_parent), bk_leaf_ssq(sl, vl, P.inv_qscale)), bk_leaf_ssq(sr, vr, P.inv_qscale));
     S->ssq = ssq;
-    S->lw = bk_normal_loglik(ssq, ctl->sigma, (double)P.N);
+    S->lw = bk_normal_loglik_pre(ssq, ctl->ll_inv2s2, ctl->ll_c);
     S->row = jb.dst_row;
     atomicAdd(&ctl->c_grow, 1);
     if (jb.src_row == BK_ROW_VIRTUAL) atomicAdd(&ctl->c_grow_root, 1);
@@ -582,6 +592,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
   if (threadIdx.x == 0) {
     if (first_phase) {
       ctl->stage = BK_ST_START; ctl->tune = tune; ctl->sigma = sigma_in[c];
+      ctl->ll_inv2s2 = bk_normal_inv2s2(ctl->sigma); ctl->ll_c = bk_normal_const(ctl->sigma, (double)P.N);
     }
     s_stage = ctl->stage;
   }

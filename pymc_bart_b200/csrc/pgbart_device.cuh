@@ -115,6 +115,7 @@ struct __align__(16) ChainCtl {
   // --- counters (bk_step_stats)
   int32_t c_tree_updates, c_rounds, c_grow, c_grow_root, c_count_passes, c_phases, c_err;
   int32_t pad0;
+  double ll_inv2s2, ll_c;   // per-step constants of the Gaussian log-likelihood
   unsigned long long t_control, t_data, t_sync, t_start;  // ns (globaltimer), control CTA only
   unsigned long long t_sub_last;
   unsigned long long t_sub[8];  // control sub-steps: finalize, weights, resample, copy, propose, select, jobs, finish/init
