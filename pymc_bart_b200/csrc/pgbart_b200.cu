@@ -3,8 +3,11 @@
 //
 // Hot path (pymc-bart's PGBART.astep; reference sites cited in include/pgbart_b200.h
 // and SURVEY.md §8a rows B1-B10).  One launch runs the whole step for every chain
-// batched on this GPU.  The kernel alternates two kinds of grid-wide phases,
-// separated by a release/acquire grid barrier:
+// batched on this GPU as a per-chain DATAFLOW (no grid-wide barrier): CTA c (c < chains) is chain
+// c's control CTA, every other CTA is a worker.  A control CTA publishes an "epoch" = one batch of
+// data units (release store of a ticket word); workers claim units with acquire fetch-adds, run
+// them and release-add a done counter the control CTA polls.  Chains are independent, so one
+// chain's scalar control overlaps the other chains' streaming work.  Two kinds of work:
 //
 //   CONTROL  (one CTA per chain; scalar work, O(P) per round): leaf values, log
 //            weights, systematic resampling, queue pops, split-variable and split
@@ -146,33 +149,21 @@ struct __align__(16) KernelShared {   // not a union: the control CTA's row book
   DataShared data;
 };
 
-// ------------------------------------------------------------------ grid barrier
-__device__ __forceinline__ bool grid_sync(const Params& P, unsigned& target, int* s_abort, int phase) {
-  MARK(20);
-  BLOCK_SYNC();
-  MARK(21);
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    // release: everything this CTA wrote (ordered before by the block barrier) becomes visible
-    // to whoever acquires the counter; polling is relaxed, one acquire fence at the end
-    red_release_add_u32(P.barrier, 1u);
-    long long t0 = clock64();
-    int ab = 0;
-    unsigned spins = 0;
-    while (ld_relaxed_u32(P.barrier) < target) {
-      if ((++spins & 63u) == 0) {
-        if (ld_volatile_i32(P.abort_flag)) { ab = 1; break; }
-        if (clock64() - t0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); ab = 1; break; }
-      }
-    }
-    fence_acq_rel_gpu();
-    if (!ab && ld_volatile_i32(P.abort_flag)) ab = 1;
-    *s_abort = ab;
-  }
-  BLOCK_SYNC();
-  MARK(23);
-  const bool r = *s_abort != 0;
-  if (r) MARK(99);
+// ------------------------------------------------------------------ dataflow sync helpers
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long atom_acquire_add_u64(unsigned long long* p, unsigned long long v) {
+  unsigned long long r;
+  asm volatile("atom.acquire.gpu.global.add.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(v) : "memory");
   return r;
 }
 
@@ -651,8 +642,6 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
         st.grow_root = ctl->c_grow_root; st.count_passes = ctl->c_count_passes; st.phases = ctl->c_phases;
         st.trace_len = ctl->trace_round_base; st.error_flags = ctl->c_err | (ctl->trace_round_base > P.trace_cap && P.trace_cap > 0 ? 1 : 0);
         st.leaf_sd = ctl->leaf_sd; st.iter = ctl->iter;
-        st.us_control = (int32_t)(ctl->t_control / 1000ull); st.us_data = (int32_t)(ctl->t_data / 1000ull);
-        st.us_sync = (int32_t)(ctl->t_sync / 1000ull); st.us_total = (int32_t)((globaltimer_ns() - ctl->t_start) / 1000ull);
         P.stats[c] = st;
       }
     }
@@ -964,94 +953,159 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
 }
 
 // ------------------------------------------------------------------ the step kernel
+// work claimed by a worker CTA (broadcast through shared memory)
+struct Claim {
+  int chain;       // -1: nothing claimed
+  int cmd;
+  int first, count;  // units [first, first+count)
+  int njobs, group;
+  int exit_now;
+};
+
+// ---- worker: claim units of any chain with published work, run them, report completion
+__device__ void worker_loop(const Params& P, DataShared& sh) {
+  __shared__ Claim s_claim;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  int start = blockIdx.x % P.C;
+  long long t_idle0 = clock64();
+  for (;;) {
+    if (threadIdx.x == 0) {
+      Claim cl; cl.chain = -1; cl.exit_now = 0; cl.cmd = 0; cl.first = 0; cl.count = 0; cl.njobs = 0; cl.group = 1;
+      int n_finished = 0;
+      for (int k = 0; k < P.C && cl.chain < 0; ++k) {
+        const int c = (start + k) % P.C;
+        ChainSync* sy = P.sync + c;
+        if (ld_relaxed_u32(&sy->finished)) { n_finished++; continue; }
+        const unsigned long long t = ld_relaxed_u64(&sy->ticket);
+        const unsigned ep = (unsigned)(t >> 32), u = (unsigned)t;
+        if (ep == 0) continue;                                   // nothing published yet
+        const ChainCtl* ctl = P.ctl + c;
+        if (u >= (unsigned)__ldcg(&ctl->ep_total)) continue;     // hint only; validated after the claim
+        const int want = __ldcg(&ctl->ep_cmd) == BK_CMD_ROUND ? nwarps : 1;
+        const unsigned long long t2 = atom_acquire_add_u64(&sy->ticket, (unsigned long long)want);
+        const unsigned u2 = (unsigned)t2;
+        const unsigned ep2 = (unsigned)(t2 >> 32);
+        if (ep2 == 0) continue;
+        // the descriptor is rewritten BEFORE the next epoch's ticket is published: a claim that landed on
+        // the previous epoch's (exhausted) counter can observe the newer descriptor and must be dropped
+        if (__ldcg(&ctl->ep_id) != ep2) continue;
+        const int total = __ldcg(&ctl->ep_total);                // belongs to the claimed epoch (acquire above)
+        if (u2 >= (unsigned)total) continue;
+        cl.chain = c; cl.cmd = __ldcg(&ctl->ep_cmd); cl.first = (int)u2;
+        cl.count = (int)u2 + want <= total ? want : total - (int)u2;
+        cl.njobs = __ldcg(&ctl->ep_njobs); cl.group = __ldcg(&ctl->ep_group);
+      }
+      if (cl.chain < 0) {
+        if (n_finished == P.C) cl.exit_now = 1;
+        else if (ld_volatile_i32(P.abort_flag)) cl.exit_now = 1;
+        else if (clock64() - t_idle0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); cl.exit_now = 1; }
+      } else {
+        start = (cl.chain + 1) % P.C;
+      }
+      s_claim = cl;
+    }
+    BLOCK_SYNC();
+    const Claim cl = s_claim;
+    if (cl.exit_now) return;
+    if (cl.chain >= 0) {
+      if (cl.cmd == BK_CMD_ROUND) {
+        if (warp < cl.count) {
+          const int u = cl.first + warp;
+          const int tile = u % P.ntiles, g = u / P.ntiles;
+          const int lo = g * cl.group;
+          const int hi = lo + cl.group < cl.njobs ? lo + cl.group : cl.njobs;
+          round_unit(P, cl.chain, tile, lo, hi);
+        }
+      } else if (cl.cmd == BK_CMD_SWEEP) {
+        // the claim size was chosen from a hint that may predate this epoch: run every claimed unit
+        for (int u = cl.first; u < cl.first + cl.count; ++u) sweep_unit(P, cl.chain, u, sh);
+      }
+      BLOCK_SYNC();   // every warp's stores are ordered before the release below
+      if (threadIdx.x == 0) { red_release_add_u32(&P.sync[cl.chain].done, (unsigned)cl.count); t_idle0 = clock64(); }
+    }
+  }
+}
+
+// ---- control CTA of chain c: wait for the previous epoch, run the state machine, publish the next
+__device__ bool control_loop(const Params& P, int c, int tune, const float* sigma_in, int max_phases, CtlShared& sh) {
+  __shared__ int s_flag;
+  ChainCtl* ctl = P.ctl + c;
+  ChainSync* sy = P.sync + c;
+  unsigned issued = 0, epoch = 0;
+  const int worker_warps = (gridDim.x - P.C) * (blockDim.x >> 5);
+  const int sweep_tiles = (P.Npad + BK_COMMIT_TILE - 1) / BK_COMMIT_TILE;
+  unsigned long long t_wait = 0, t_ctrl = 0, t_pub = 0, t_begin = 0;
+  if (threadIdx.x == 0) t_begin = globaltimer_ns();
+  for (int phase = 0; phase < max_phases; ++phase) {
+    unsigned long long q0 = 0, q1 = 0, q2 = 0;
+    if (threadIdx.x == 0) {
+      q0 = globaltimer_ns();
+      int ab = 0;
+      long long t0 = clock64();
+      unsigned spins = 0;
+      while (ld_relaxed_u32(&sy->done) < issued) {
+        if ((++spins & 63u) == 0) {
+          if (ld_volatile_i32(P.abort_flag)) { ab = 1; break; }
+          if (clock64() - t0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); ab = 1; break; }
+        }
+      }
+      fence_acq_rel_gpu();
+      if (!ab && ld_volatile_i32(P.abort_flag)) ab = 1;
+      s_flag = ab;
+      q1 = globaltimer_ns();
+    }
+    BLOCK_SYNC();
+    if (s_flag) return false;
+    control_step(P, c, phase, tune, sigma_in, sh);
+    BLOCK_SYNC();
+    if (threadIdx.x == 0) {
+      q2 = globaltimer_ns();
+      const int cmd = ctl->cmd;
+      int fin = 0;
+      if (cmd == BK_CMD_DONE) {
+        fin = 1;
+      } else {
+        int total = 0, G = 1;
+        const int nj = ctl->n_jobs;
+        if (cmd == BK_CMD_ROUND) {
+          long long pt = (long long)nj * P.ntiles;
+          long long g = pt * P.C / (2ll * (worker_warps > 0 ? worker_warps : 1));
+          G = g < 1 ? 1 : (g > BK_MAX_GROUP ? BK_MAX_GROUP : (int)g);
+          total = ((nj + G - 1) / G) * P.ntiles;
+        } else {
+          total = sweep_tiles;
+        }
+        ctl->ep_cmd = cmd; ctl->ep_njobs = nj; ctl->ep_group = G; ctl->ep_total = total;
+        issued += (unsigned)total; epoch += 1;
+        ctl->ep_id = epoch;
+        st_release_u64(&sy->ticket, (unsigned long long)epoch << 32);   // publishes jobs + descriptor
+      }
+      s_flag = fin;
+      const unsigned long long q3 = globaltimer_ns();
+      t_wait += q1 - q0; t_ctrl += q2 - q1; t_pub += q3 - q2;
+      if (fin) {
+        bk_step_stats* st = P.stats + c;
+        st->us_control = (int32_t)(t_ctrl / 1000ull); st->us_data = (int32_t)(t_wait / 1000ull);
+        st->us_sync = (int32_t)(t_pub / 1000ull); st->us_total = (int32_t)((q3 - t_begin) / 1000ull);
+        __threadfence();
+        st_release_u32(&sy->finished, 1u);
+      }
+    }
+    BLOCK_SYNC();
+    if (s_flag) return true;
+  }
+  if (threadIdx.x == 0) { atomicExch(P.abort_flag, 1); }
+  return false;
+}
+
+// ------------------------------------------------------------------ the step kernel
 __global__ void __launch_bounds__(BK_CTA_THREADS, 1)
 pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sigma_in, const int max_phases) {
   __shared__ KernelShared sh;
-  __shared__ int s_abort;
-  unsigned target = 0;
-  const int nwarps_cta = blockDim.x >> 5;
-  const int total_warps = gridDim.x * nwarps_cta;
-  const int gwarp = blockIdx.x * nwarps_cta + (threadIdx.x >> 5);
-  const int sweep_tiles = (P.Npad + BK_COMMIT_TILE - 1) / BK_COMMIT_TILE;
-
-  for (int phase = 0; phase < max_phases; ++phase) {
-    // ---- control
-    MARK(1);
-    const bool timing = blockIdx.x < P.C && threadIdx.x == 0;
-    unsigned long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
-    if (timing) tq0 = globaltimer_ns();
-    for (int c = blockIdx.x; c < P.C; c += gridDim.x) control_step(P, c, phase, tune, sigma_in, sh.ctl);
-    MARK(2);
-    if (timing) tq1 = globaltimer_ns();
-    if (grid_sync(P, target, &s_abort, phase)) return;
-    if (timing) tq2 = globaltimer_ns();
-    MARK(3);
-    // ---- plan the data phase (every CTA builds the same small table)
-    if (threadIdx.x == 0) {
-      int done = 1, ru = 0, su = 0;
-      long long pt = 0;
-      for (int c = 0; c < P.C; ++c) {
-        int cmd = __ldcg(&P.ctl[c].cmd);
-        int nj = cmd == BK_CMD_ROUND ? __ldcg(&P.ctl[c].n_jobs) : 0;
-        sh.data.cmd[c] = cmd; sh.data.njobs[c] = nj;
-        if (cmd != BK_CMD_DONE) done = 0;
-        pt += (long long)nj * P.ntiles;
-      }
-      long long g = pt / (2ll * total_warps);
-      int G = g < 1 ? 1 : (g > BK_MAX_GROUP ? BK_MAX_GROUP : (int)g);
-      for (int c = 0; c < P.C; ++c) {
-        int ng = (sh.data.njobs[c] + G - 1) / G;
-        sh.data.ngroups[c] = ng;
-        sh.data.ru_base[c] = ru; ru += ng * P.ntiles;
-        sh.data.su_base[c] = su; su += sh.data.cmd[c] == BK_CMD_SWEEP ? sweep_tiles : 0;
-      }
-      sh.data.ru_base[P.C] = ru; sh.data.su_base[P.C] = su;
-      sh.data.group = G; sh.data.all_done = done;
-    }
-    BLOCK_SYNC();
-    if (P.debug == 1 && blockIdx.x == 0 && threadIdx.x == 0) {
-      const ChainCtl* d = P.ctl;
-      printf("[bk] phase %d cmd %d stage %d njobs %d round %d tree %d ru %d su %d G %d done %d err %d\n", phase, sh.data.cmd[0],
-             d->stage, sh.data.njobs[0], d->round, d->cur_tree, sh.data.ru_base[P.C], sh.data.su_base[P.C], sh.data.group,
-             sh.data.all_done, d->c_err);
-    }
-    if (sh.data.all_done) break;
-    MARK(4);
-    // ---- data: sweeps (CTA granular)
-    {
-      const int su_total = sh.data.su_base[P.C];
-      for (int u = blockIdx.x; u < su_total; u += gridDim.x) {
-        int c = 0;
-        while (u >= sh.data.su_base[c + 1]) ++c;
-        sweep_unit(P, c, u - sh.data.su_base[c], sh.data);
-      }
-    }
-    MARK(5);
-    // ---- data: rounds (warp granular)
-    {
-      const int ru_total = sh.data.ru_base[P.C];
-      const int G = sh.data.group;
-      for (int u = gwarp; u < ru_total; u += total_warps) {
-        int c = 0;
-        while (u >= sh.data.ru_base[c + 1]) ++c;
-        const int local = u - sh.data.ru_base[c];
-        const int tile = local % P.ntiles, g = local / P.ntiles;
-        const int lo = g * G;
-        const int hi = lo + G < sh.data.njobs[c] ? lo + G : sh.data.njobs[c];
-        round_unit(P, c, tile, lo, hi);
-      }
-    }
-    MARK(6);
-    if (timing) tq3 = globaltimer_ns();
-    if (grid_sync(P, target, &s_abort, phase)) return;
-    if (timing) {
-      ChainCtl* tc = P.ctl + blockIdx.x;
-      unsigned long long tq4 = globaltimer_ns();
-      if (phase == 0) { tc->t_control = 0; tc->t_data = 0; tc->t_sync = 0; tc->t_start = tq0; }
-      tc->t_control += tq1 - tq0; tc->t_sync += (tq2 - tq1) + (tq4 - tq3); tc->t_data += tq3 - tq2;
-    }
-    MARK(7);
+  if ((int)blockIdx.x < P.C) {
+    if (!control_loop(P, blockIdx.x, tune, sigma_in, max_phases, sh.ctl)) return;
   }
+  worker_loop(P, sh.data);   // control CTAs help once their chain is done
 }
 
 // ------------------------------------------------------------------ init kernel
@@ -1085,7 +1139,8 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
     ctl->c_err = 0; ctl->trace_round_base = 0;
     memset(&P.stats[c], 0, sizeof(bk_step_stats));
   }
-  if (tid == 0) { *P.barrier = 0u; *P.abort_flag = 0; }
+  if (tid == 0) *P.abort_flag = 0;
+  for (size_t i = tid; i < (size_t)P.C * (sizeof(ChainSync) / 4); i += nth) reinterpret_cast<unsigned int*>(P.sync)[i] = 0u;
 }
 __global__ void pgbart_init_cum_kernel(const Params P) {
   int c = blockIdx.x;
@@ -1165,7 +1220,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   size_t qr, qst, ids_tree, rows, rowcnt, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, alpha_vec, cum,
-      p_leaf, rules, vi, stats, trace, barrier, abort_flag, sigma, split_prior, total;
+      p_leaf, rules, vi, stats, trace, sync, abort_flag, sigma, split_prior, total;
   int Npad, ntiles, R;
 };
 
@@ -1204,7 +1259,7 @@ static int make_layout(const bk_settings* s, Layout* L) {
   CARVE(vi, C * p * 4);
   CARVE(stats, C * sizeof(bk_step_stats));
   CARVE(trace, C * (size_t)(s->trace_capacity > 0 ? s->trace_capacity : 0) * sizeof(bk_trace_rec));
-  CARVE(barrier, 256);
+  CARVE(sync, C * sizeof(ChainSync));
   CARVE(abort_flag, 256);
   CARVE(sigma, C * 4);
   CARVE(split_prior, p * 8);
@@ -1257,7 +1312,7 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   P.ctl = (ChainCtl*)(w + L.ctl); P.accL = (unsigned long long*)(w + L.accL); P.acc0 = (unsigned long long*)(w + L.acc0);
   P.alpha_vec = (double*)(w + L.alpha_vec); P.cum = (double*)(w + L.cum); P.p_leaf = (double*)(w + L.p_leaf);
   P.rules = (int32_t*)(w + L.rules); P.vi = (int32_t*)(w + L.vi); P.stats = (bk_step_stats*)(w + L.stats);
-  P.trace = (bk_trace_rec*)(w + L.trace); P.barrier = (unsigned int*)(w + L.barrier); P.abort_flag = (int32_t*)(w + L.abort_flag);
+  P.trace = (bk_trace_rec*)(w + L.trace); P.sync = (ChainSync*)(w + L.sync); P.abort_flag = (int32_t*)(w + L.abort_flag);
   h->sigma_dev = (float*)(w + L.sigma); h->split_prior_dev = (double*)(w + L.split_prior);
 
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -1282,7 +1337,8 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   if (!coop) { set_err("device lacks cooperative launch"); return BK_ERR_UNSUPPORTED; }
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgbart_step_kernel, BK_CTA_THREADS, 0));
   if (occ < 1) { set_err("step kernel does not fit on an SM"); return BK_ERR_CUDA; }
-  h->grid = n_sm;  // one persistent CTA per SM (148 on B200)
+  h->grid = n_sm;  // one persistent CTA per SM (148 on B200): chains control CTAs + workers
+  if (h->grid <= P.C) { set_err("more chains than SMs minus one"); return BK_ERR_ARG; }
   if (getenv("BK_DEBUG_MARKERS")) {
     h->marker_count = 4736 + n_sm * 64 + 64;
     h->marker_host = (int32_t*)calloc((size_t)h->marker_count, sizeof(int32_t));
@@ -1322,7 +1378,7 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
     h->sigma_pinned[c] = sg;
   }
   CK(cudaMemcpyAsync(h->sigma_dev, h->sigma_pinned, (size_t)P.C * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(P.barrier, 0, sizeof(unsigned int), h->stream));
+  CK(cudaMemsetAsync(P.sync, 0, (size_t)P.C * sizeof(ChainSync), h->stream));
   int tune_i = tune ? 1 : 0;
   const float* sig = h->sigma_dev;
   int maxp = h->max_phases;
@@ -1343,11 +1399,14 @@ int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_hos
   CK(cudaSetDevice(h->s.device));
   Params& P = h->P;
   CK(cudaStreamSynchronize(h->stream));
-  if (*h->abort_pinned) { set_err("grid barrier timed out inside the step kernel"); return BK_ERR_TIMEOUT; }
+  if (*h->abort_pinned) { set_err("a dataflow wait timed out inside the step kernel"); return BK_ERR_TIMEOUT; }
   if (vi_counts_host) memcpy(vi_counts_host, h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t));
   if (stats_host) memcpy(stats_host, h->stats_pinned, (size_t)P.C * sizeof(bk_step_stats));
   for (int c = 0; c < P.C; ++c)
-    if (h->stats_pinned[c].error_flags & ~1) { set_err("device-side consistency check failed"); return BK_ERR_STATE; }
+    if (h->stats_pinned[c].error_flags & ~1) {
+      char buf[64]; snprintf(buf, sizeof(buf), "chain %d flags 0x%x", c, h->stats_pinned[c].error_flags);
+      set_err("device-side consistency check failed: %s", buf); return BK_ERR_STATE;
+    }
   return BK_OK;
 }
 

@@ -116,6 +116,9 @@ struct __align__(16) ChainCtl {
   int32_t c_tree_updates, c_rounds, c_grow, c_grow_root, c_count_passes, c_phases, c_err;
   int32_t pad0;
   double ll_inv2s2, ll_c;   // per-step constants of the Gaussian log-likelihood
+  // --- descriptor of the published epoch (one batch of data units for the workers)
+  int32_t ep_cmd, ep_njobs, ep_group, ep_total;
+  uint32_t ep_id; int32_t ep_pad[3];
   unsigned long long t_control, t_data, t_sync, t_start;  // ns (globaltimer), control CTA only
   unsigned long long t_sub_last;
   unsigned long long t_sub[8];  // control sub-steps: finalize, weights, resample, copy, propose, select, jobs, finish/init
@@ -137,6 +140,18 @@ struct __align__(16) ChainCtl {
 // (sr, sr2lo, sr2hi, sst); then [4]: (wf sd sum, -, -, -)
 #define BK_ACC0_STRIDE 4
 #define BK_ACC0_WORDS (257 * BK_ACC0_STRIDE)
+
+// Per-chain dataflow synchronisation words (own 128-byte line each).
+//   ticket: (epoch << 32) | next unclaimed unit.  The chain's control CTA publishes an epoch with a
+//           release store; workers claim units with an acquire fetch-add.
+//   done:   units completed since the step began (workers: release add; control: acquire poll).
+struct __align__(128) ChainSync {
+  unsigned long long ticket;
+  unsigned int done;
+  unsigned int finished;
+  unsigned int pad[28];
+};
+static_assert(sizeof(ChainSync) == 128, "ChainSync layout");
 
 struct Params {
   int32_t N, Npad, p, m, P, C, R, ntiles;
@@ -167,7 +182,7 @@ struct Params {
   int32_t* vi;         // [C][p]
   bk_step_stats* stats;  // [C]
   bk_trace_rec* trace;   // [C][trace_cap]
-  unsigned int* barrier;
+  ChainSync* sync;   // [C]
   int32_t* abort_flag;
   int32_t debug;
   int32_t* marker;  // debug: mapped host memory, one int per warp
