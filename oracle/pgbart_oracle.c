@@ -34,7 +34,7 @@
  *   B4  partition the node's rows (x <= s / x == s)
  *   B5  leaf value = mean(sum_trees over members)/m + z * leaf_sd
  *   B6  log-weight = Gaussian log-likelihood from per-leaf (n, sum r, sum r^2)
- *   B7  w = exp(lw - max) + 1e-12, normalised
+ *   B7  w = exp(lw - max) + 1e-12; cumulative weights c_i = (w_0+..+w_i)/(w_0+..+w_L-1)
  *   B8  systematic resampling of particles 1..P-1
  *   B9  final systematic resampling over all P + uniform pick; commit
  *   B10 batch of max(1,int(m*batch)) trees per step, round robin
@@ -194,23 +194,25 @@ static double particle_ssq(const bko* o, const o_particle* q) {
   return ssq;
 }
 
-/* systematic resampling: indices[i] = inverse cdf of (u+i)/L over weights w[0..L) */
-static void systematic(const double* w, int L, double u, int32_t* idx_out) {
-  int idx = 0;
-  double a = w[0];
-  for (int i = 0; i < L; ++i) {
-    double point = BK_DDIV(BK_DADD(u, (double)i), (double)L);
-    while (point > a && idx < L - 1) { idx += 1; a = BK_DADD(a, w[idx]); }
-    idx_out[i] = idx;
-  }
-}
-
-static void normalise(const o_particle* parts, int first, int count, double* w) {
+/* Weight terms w_i = exp(lw_i - max) + 1e-12 (App. A.7), their sequential running sums S_i, and
+ * the normalised cumulative weights c_i = S_i / S_last.  Systematic resampling: index of point
+ * (u+i)/L = first j with point <= c_j (the inverse-CDF walk), capped at L-1. */
+static void normalise_cum(const o_particle* parts, int first, int count, double* cum) {
   double mx = parts[first].lw;
   for (int i = 1; i < count; ++i) if (parts[first + i].lw > mx) mx = parts[first + i].lw;
-  double tot = 0.0;
-  for (int i = 0; i < count; ++i) { w[i] = bk_weight_term(parts[first + i].lw, mx); tot = BK_DADD(tot, w[i]); }
-  for (int i = 0; i < count; ++i) w[i] = BK_DDIV(w[i], tot);
+  double run = 0.0;
+  for (int i = 0; i < count; ++i) { run = BK_DADD(run, bk_weight_term(parts[first + i].lw, mx)); cum[i] = run; }
+  const double tot = cum[count - 1];
+  for (int i = 0; i < count; ++i) cum[i] = BK_DDIV(cum[i], tot);
+}
+
+static void systematic(const double* cum, int L, double u, int32_t* idx_out) {
+  int idx = 0;
+  for (int i = 0; i < L; ++i) {
+    double point = BK_DDIV(BK_DADD(u, (double)i), (double)L);
+    while (point > cum[idx] && idx < L - 1) idx += 1;
+    idx_out[i] = idx;
+  }
 }
 
 static int draw_variable(const bko* o, double u) {
@@ -338,7 +340,7 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       int live = 0;
       for (int q = 1; q < P; ++q) if (o->parts[q].q_head < o->parts[q].n_nodes) live = 1;
       if (!live) break;
-      normalise(o->parts, 1, P - 1, o->w);
+      normalise_cum(o->parts, 1, P - 1, o->w);
       double u = bk_u01(bk_rng(S, C, D, 0, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0]);
       systematic(o->w, P - 1, u, o->anc);
       for (int q = 1; q < P; ++q) part_copy(&o->tmp[q], &o->parts[o->anc[q - 1] + 1], N);
@@ -348,7 +350,7 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       }
     }
     /* B9: final selection */
-    normalise(o->parts, 0, P, o->w);
+    normalise_cum(o->parts, 0, P, o->w);
     double uf = bk_u01(bk_rng(S, C, D, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
     systematic(o->w, P, uf, o->anc);
     uint32_t pick = bk_index(bk_rng(S, C, D, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P);

@@ -118,6 +118,7 @@ struct CtlShared {
   int s_next[BK_MAX_PARTICLES];
   int s_row[BK_MAX_PARTICLES];
   int s_nn[BK_MAX_PARTICLES];
+  int s_sparse[BK_MAX_PARTICLES];
   float s_split[BK_MAX_PARTICLES];
   unsigned char row_used[2 * BK_MAX_PARTICLES];
   int row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds (persists across phases)
@@ -130,6 +131,7 @@ struct CtlShared {
 };
 
 struct DataShared {
+  Job jobs[BK_MAX_PARTICLES];   // this claim's job list (staged from the chain's descriptor)
   int cmd[64];
   int njobs[64];
   int ngroups[64];
@@ -249,8 +251,9 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
 // normalise sh.lw[first..first+count) into sh.w, then systematic resampling into sh.anc
 // (block-wide; thread 0 does the order-dependent scalar parts in the oracle's order)
 // normalise sh.lw[first..first+count) and resample systematically into sh.anc[0..count).
-// Runs in warp 0 (count <= 128: four values per lane); order-dependent parts (sum, prefix sums)
-// are done by lane 0 in the oracle's order, the rest is lane-parallel.  Ends with a block barrier.
+// Runs in warp 0 (count <= 128: four values per lane).  The only order-dependent part, the running
+// sums of the weight terms, is done by lane 0 in index order (the oracle's order); the maximum, the
+// exponentials, the divisions and the inverse-CDF searches are lane-parallel.  Ends with a block barrier.
 __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, double u) {
   if ((threadIdx.x >> 5) == 0) {
     const int lane = threadIdx.x & 31;
@@ -260,23 +263,29 @@ __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first
     for (int o = 16; o > 0; o >>= 1) { double ov = __shfl_xor_sync(0xffffffffu, mx, o); mx = ov > mx ? ov : mx; }
     for (int i = lane; i < count; i += 32) sh.w[i] = bk_weight_term(sh.lw[first + i], mx);
     __syncwarp();
-    double tot = 0.0;
-    if (lane == 0) for (int i = 0; i < count; ++i) tot = BK_DADD(tot, sh.w[i]);
-    tot = __shfl_sync(0xffffffffu, tot, 0);
-    for (int i = lane; i < count; i += 32) sh.w[i] = BK_DDIV(sh.w[i], tot);
-    __syncwarp();
     if (lane == 0) {
-      double a = sh.w[0];
-      sh.cum_w[0] = a;
-      for (int i = 1; i < count; ++i) { a = BK_DADD(a, sh.w[i]); sh.cum_w[i] = a; }
+      double run = 0.0;
+      int i = 0;
+      for (; i + 8 <= count; i += 8) {   // loads batched ahead of the dependent adds
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = sh.w[i + j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { run = BK_DADD(run, v[j]); sh.cum_w[i + j] = run; }
+      }
+      for (; i < count; ++i) { run = BK_DADD(run, sh.w[i]); sh.cum_w[i] = run; }
     }
     __syncwarp();
+    const double tot = sh.cum_w[count - 1];
+    __syncwarp();
+    for (int i = lane; i < count; i += 32) sh.cum_w[i] = BK_DDIV(sh.cum_w[i], tot);
+    __syncwarp();
     for (int i = lane; i < count; i += 32) {
-      // inverse CDF: first index whose running sum reaches the point (the walk `while (point > a) idx++`)
+      // first index whose cumulative weight reaches the point (= the walk `while (point > c[idx]) idx++`)
       const double point = BK_DDIV(BK_DADD(u, (double)i), (double)count);
-      int idx = 0;
-      while (idx < count - 1 && point > sh.cum_w[idx]) ++idx;
-      sh.anc[i] = idx;
+      int lo = 0, hi = count - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (point > sh.cum_w[mid]) lo = mid + 1; else hi = mid; }
+      sh.anc[i] = lo;
     }
   }
   BLOCK_SYNC();
@@ -378,6 +387,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       if (kind == 1) next = qh;            // a queued node, or one of the two children being made
       else { next = qh < nn ? qh : -1; if (next >= 0) kind = 2; }
     }
+    sh.s_sparse[q] = (j >= 0 && (long long)S->nodes[j].n * 8 < (long long)P.N) ? 1 : 0;
     sh.s_kind[q] = kind; sh.s_j[q] = j; sh.s_v[q] = v; sh.s_k[q] = k; sh.s_next[q] = next; sh.s_row[q] = row; sh.s_nn[q] = nn;
     bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + q - 1);
     if (rec) {
@@ -410,47 +420,78 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       BLOCK_SYNC();
       if (threadIdx.x == 0 && s_err) ctl->c_err |= s_err;
   }
-  // rows + job list (sequential: deterministic placement; shared memory only)
+  // rows + job list, built in parallel in shared memory:
+  //   free rows: ranks of the unused pool rows; growers: rank among the growing slots -> dst row;
+  //   count-only jobs are de-duplicated per source row with an exchange on row_cnt_node.
   __shared__ int s_njobs;
+  __shared__ int s_free[2 * BK_MAX_PARTICLES];
+  __shared__ int s_warp_cnt[3][8];
   if ((int)threadIdx.x < P.R) sh.row_used[threadIdx.x] = 0;
   BLOCK_SYNC();
   if (threadIdx.x >= 1 && (int)threadIdx.x < P.P && sh.s_row[threadIdx.x] >= 0) sh.row_used[sh.s_row[threadIdx.x]] = 1;
   BLOCK_SYNC();
-  if (threadIdx.x == 0) {
-    int nj = 0, free_r = 0, errs = 0, cnt_passes = 0;
-    for (int s = 1; s < P.P; ++s) {
-      const int kind = sh.s_kind[s];
-      if (kind == 1) {
-        while (free_r < P.R && sh.row_used[free_r]) free_r++;
-        Job jb;
-        jb.kind = BK_JOB_PARTITION; jb.slot = s; jb.src_row = sh.s_row[s]; jb.dst_row = free_r;
-        jb.node = sh.s_j[s]; jb.var = sh.s_v[s]; jb.split = sh.s_split[s]; jb.left_id = sh.s_nn[s];
-        jb.next_node = sh.s_next[s]; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
-        if (free_r >= P.R) { errs |= 8; jb.dst_row = 0; }
-        else { sh.row_used[free_r] = 1; sh.row_cnt_node[free_r] = jb.next_node; }
-        sh.jobs[nj++] = jb;
-      } else if (kind == 2) {
-        const int r = sh.s_row[s];
-        if (r >= 0 && sh.row_cnt_node[r] != sh.s_next[s]) {
-          Job jb;
-          jb.kind = BK_JOB_COUNT; jb.slot = s; jb.src_row = r; jb.dst_row = r; jb.node = -1; jb.var = 0; jb.split = 0.0f;
-          jb.left_id = 0; jb.next_node = sh.s_next[s]; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
-          sh.row_cnt_node[r] = sh.s_next[s];
-          sh.jobs[nj++] = jb;
-          cnt_passes += 1;
-        }
+  {
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    // (i) count-job de-duplication, (ii) per-thread flags
+    int is_grow = 0, is_cnt = 0, is_free = 0;
+    if (t >= 1 && t < P.P) {
+      if (sh.s_kind[t] == 1) is_grow = 1;
+      else if (sh.s_kind[t] == 2 && sh.s_row[t] >= 0) {
+        const int old = atomicExch(&sh.row_cnt_node[sh.s_row[t]], sh.s_next[t]);
+        is_cnt = old != sh.s_next[t];
       }
     }
-    ctl->n_jobs = nj;
-    if (cnt_passes) ctl->c_count_passes += cnt_passes;
-    if (errs) ctl->c_err |= errs;
-    s_njobs = nj;
+    if (t < P.R) is_free = sh.row_used[t] ? 0 : 1;
+    if (t < 256) {   // R <= 256 and P <= 128: eight warps cover both index ranges
+      const unsigned bg = __ballot_sync(0xffffffffu, is_grow), bc = __ballot_sync(0xffffffffu, is_cnt),
+                     bf = __ballot_sync(0xffffffffu, is_free);
+      if (lane == 0) { s_warp_cnt[0][w] = __popc(bg); s_warp_cnt[1][w] = __popc(bc); s_warp_cnt[2][w] = __popc(bf); }
+      const unsigned below = (1u << lane) - 1u;
+      // stash intra-warp ranks in registers via shared scratch after the barrier below
+      s_free[t] = (__popc(bf & below) << 16) | (__popc(bg & below) << 8) | __popc(bc & below);
+    }
+    BLOCK_SYNC();
+    if (t < 256) {
+      int off_g = 0, off_c = 0, off_f = 0, tot_g = 0;
+      for (int k = 0; k < 8; ++k) {
+        if (k < w) { off_g += s_warp_cnt[0][k]; off_c += s_warp_cnt[1][k]; off_f += s_warp_cnt[2][k]; }
+        tot_g += s_warp_cnt[0][k];
+      }
+      const int packed = s_free[t];
+      const int rank_f = off_f + (packed >> 16), rank_g = off_g + ((packed >> 8) & 0xFF), rank_c = off_c + (packed & 0xFF);
+      BLOCK_SYNC();   // everyone has read its packed ranks; s_free is reused as the free-row list
+      if (is_free) s_free[rank_f] = t;
+      BLOCK_SYNC();
+      if (is_grow) {
+        Job jb;
+        jb.kind = BK_JOB_PARTITION; jb.slot = t; jb.src_row = sh.s_row[t]; jb.dst_row = s_free[rank_g];
+        jb.node = sh.s_j[t]; jb.var = sh.s_v[t]; jb.split = sh.s_split[t]; jb.left_id = sh.s_nn[t];
+        jb.next_node = sh.s_next[t]; jb.rule = P.rules[sh.s_v[t]]; jb.pad[0] = sh.s_sparse[t]; jb.pad[1] = 0;
+        sh.row_cnt_node[jb.dst_row] = jb.next_node;
+        sh.jobs[rank_g] = jb;
+      } else if (is_cnt) {
+        Job jb;
+        jb.kind = BK_JOB_COUNT; jb.slot = t; jb.src_row = sh.s_row[t]; jb.dst_row = sh.s_row[t]; jb.node = -1; jb.var = 0;
+        jb.split = 0.0f; jb.left_id = 0; jb.next_node = sh.s_next[t]; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
+        sh.jobs[tot_g + rank_c] = jb;
+      }
+      if (t == 0) {
+        int tot_c = 0, tot_f = 0;
+        for (int k = 0; k < 8; ++k) { tot_c += s_warp_cnt[1][k]; tot_f += s_warp_cnt[2][k]; }
+        const int nj = tot_g + tot_c;
+        ctl->n_jobs = nj;
+        if (tot_c) ctl->c_count_passes += tot_c;
+        if (tot_g > tot_f) ctl->c_err |= 8;
+        s_njobs = nj;
+      }
+    } else {
+      BLOCK_SYNC();
+      BLOCK_SYNC();
+    }
   }
   BLOCK_SYNC();
-  {  // publish the job list: split rule looked up and 48-byte descriptors stored by many threads
+  {  // publish the job list: 48-byte descriptors stored by many threads
     const int nj = s_njobs;
-    if ((int)threadIdx.x < nj && sh.jobs[threadIdx.x].kind == BK_JOB_PARTITION) sh.jobs[threadIdx.x].rule = P.rules[sh.jobs[threadIdx.x].var];
-    BLOCK_SYNC();
     const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
     uint4* d4 = reinterpret_cast<uint4*>(ctl->jobs);
     for (int i = threadIdx.x; i < nj * 3; i += blockDim.x) d4[i] = s4[i];
@@ -714,7 +755,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
 }
 
 // ------------------------------------------------------------------ data phase: ROUND
-__device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi) {
+__device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs) {
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
   const ChainCtl* ctl = P.ctl + c;
@@ -727,11 +768,11 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     q_s[0] = b0.x; q_s[1] = b0.y; q_s[2] = b0.z; q_s[3] = b0.w; q_s[4] = b1.x; q_s[5] = b1.y; q_s[6] = b1.z; q_s[7] = b1.w;
   }
   for (int ji = job_lo; ji < job_hi; ++ji) {
-    const int4* jp = reinterpret_cast<const int4*>(&ctl->jobs[ji]);
-    const int4 j0 = __ldcg(jp), j1 = __ldcg(jp + 1), j2 = __ldcg(jp + 2);
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // shared-memory copy staged by the CTA
+    const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
     const int kind = j0.x, slot = j0.y, src_row = j0.z, dst_row = j0.w;
     const int node = j1.x, var = j1.y; const float split = __int_as_float(j1.z); const int left_id = j1.w;
-    const int next_node = j2.x, rule = j2.y;
+    const int next_node = j2.x, rule = j2.y, sparse = j2.z;
     unsigned long long ids;
     if (src_row == BK_ROW_VIRTUAL) {
       ids = 0ull;
@@ -746,7 +787,9 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
 #pragma unroll
       for (int e = 0; e < 8; ++e) mm |= (((unsigned)(ids >> (8 * e)) & 255u) == (unsigned)node) ? (1u << e) : 0u;
       unsigned lm = 0;
-      if (mm) {
+      // dense nodes: the column load is issued together with the leaf-id load (one L2/HBM round trip
+      // per job); sparse nodes (few members) keep it dependent on the ids to save the bytes
+      if (!sparse || mm) {
         const float4* xp = reinterpret_cast<const float4*>(P.X + (size_t)var * P.Npad + base);
         const float4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
         const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
@@ -1009,12 +1052,18 @@ __device__ void worker_loop(const Params& P, DataShared& sh) {
     if (cl.exit_now) return;
     if (cl.chain >= 0) {
       if (cl.cmd == BK_CMD_ROUND) {
+        {
+          const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[cl.chain].jobs);
+          uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
+          for (int i = threadIdx.x; i < cl.njobs * 3; i += blockDim.x) d4[i] = __ldcg(g4 + i);
+        }
+        BLOCK_SYNC();
         if (warp < cl.count) {
           const int u = cl.first + warp;
           const int tile = u % P.ntiles, g = u / P.ntiles;
           const int lo = g * cl.group;
           const int hi = lo + cl.group < cl.njobs ? lo + cl.group : cl.njobs;
-          round_unit(P, cl.chain, tile, lo, hi);
+          round_unit(P, cl.chain, tile, lo, hi, sh.jobs);
         }
       } else if (cl.cmd == BK_CMD_SWEEP) {
         // the claim size was chosen from a hint that may predate this epoch: run every claimed unit
@@ -1069,7 +1118,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
         const int nj = ctl->n_jobs;
         if (cmd == BK_CMD_ROUND) {
           long long pt = (long long)nj * P.ntiles;
-          long long g = pt * P.C / (2ll * (worker_warps > 0 ? worker_warps : 1));
+          long long g = pt / (worker_warps > 0 ? worker_warps : 1);   // about one unit per worker warp
           G = g < 1 ? 1 : (g > BK_MAX_GROUP ? BK_MAX_GROUP : (int)g);
           total = ((nj + G - 1) / G) * P.ntiles;
         } else {
