@@ -5,7 +5,7 @@
 // and SURVEY.md §8a rows B1-B10).  One launch runs the whole step for every chain
 // batched on this GPU as a per-chain DATAFLOW (no grid-wide barrier): CTA c (c < chains) is chain
 // c's control CTA, every other CTA is a worker.  A control CTA publishes an "epoch" = one batch of
-// data units (release store of a ticket word); workers claim units with acquire fetch-adds, run
+// data units (16-byte descriptor + release store of a ticket word); workers claim units with acquire fetch-adds, run
 // them and release-add a done counter the control CTA polls.  Chains are independent, so one
 // chain's scalar control overlaps the other chains' streaming work.  Two kinds of work:
 //
@@ -162,6 +162,14 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ unsigned long long atom_acquire_add_u64(unsigned long long* p, unsigned long long v) {
   unsigned long long r;
@@ -996,47 +1004,45 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
 }
 
 // ------------------------------------------------------------------ the step kernel
-// work claimed by a worker CTA (broadcast through shared memory)
+// units claimed by a worker CTA (broadcast through shared memory)
 struct Claim {
   int chain;       // -1: nothing claimed
-  int cmd;
+  int cmd, njobs, group;
   int first, count;  // units [first, first+count)
-  int njobs, group;
   int exit_now;
 };
 
 // ---- worker: claim units of any chain with published work, run them, report completion
 __device__ void worker_loop(const Params& P, DataShared& sh) {
   __shared__ Claim s_claim;
+  __shared__ unsigned char s_fin[64];
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  int start = blockIdx.x % P.C;
+  if ((int)threadIdx.x < 64) s_fin[threadIdx.x] = 0;
+  BLOCK_SYNC();
+  int start = blockIdx.x % P.C, n_finished = 0;
   long long t_idle0 = clock64();
   for (;;) {
     if (threadIdx.x == 0) {
       Claim cl; cl.chain = -1; cl.exit_now = 0; cl.cmd = 0; cl.first = 0; cl.count = 0; cl.njobs = 0; cl.group = 1;
-      int n_finished = 0;
       for (int k = 0; k < P.C && cl.chain < 0; ++k) {
         const int c = (start + k) % P.C;
+        if (s_fin[c]) continue;
         ChainSync* sy = P.sync + c;
-        if (ld_relaxed_u32(&sy->finished)) { n_finished++; continue; }
+        uint4 d = ld_volatile_v4(&sy->desc);                       // same 128-byte line as the ticket
         const unsigned long long t = ld_relaxed_u64(&sy->ticket);
-        const unsigned ep = (unsigned)(t >> 32), u = (unsigned)t;
-        if (ep == 0) continue;                                   // nothing published yet
-        const ChainCtl* ctl = P.ctl + c;
-        if (u >= (unsigned)__ldcg(&ctl->ep_total)) continue;     // hint only; validated after the claim
-        const int want = __ldcg(&ctl->ep_cmd) == BK_CMD_ROUND ? nwarps : 1;
+        if (d.x == 0) continue;                                    // nothing published yet
+        if ((d.y & 0xFFu) == BK_CMD_DONE) { s_fin[c] = 1; n_finished++; continue; }
+        if ((unsigned)(t >> 32) != d.x || (unsigned)t >= d.w) continue;   // in transition, or exhausted
+        const int want = (d.y & 0xFFu) == BK_CMD_ROUND ? nwarps : 1;
         const unsigned long long t2 = atom_acquire_add_u64(&sy->ticket, (unsigned long long)want);
-        const unsigned u2 = (unsigned)t2;
-        const unsigned ep2 = (unsigned)(t2 >> 32);
-        if (ep2 == 0) continue;
-        // the descriptor is rewritten BEFORE the next epoch's ticket is published: a claim that landed on
-        // the previous epoch's (exhausted) counter can observe the newer descriptor and must be dropped
-        if (__ldcg(&ctl->ep_id) != ep2) continue;
-        const int total = __ldcg(&ctl->ep_total);                // belongs to the claimed epoch (acquire above)
-        if (u2 >= (unsigned)total) continue;
-        cl.chain = c; cl.cmd = __ldcg(&ctl->ep_cmd); cl.first = (int)u2;
-        cl.count = (int)u2 + want <= total ? want : total - (int)u2;
-        cl.njobs = __ldcg(&ctl->ep_njobs); cl.group = __ldcg(&ctl->ep_group);
+        const unsigned ep2 = (unsigned)(t2 >> 32), u2 = (unsigned)t2;
+        if (ep2 != d.x) {            // a newer epoch was published in between: its descriptor is visible now
+          d = ld_volatile_v4(&sy->desc);
+          if (d.x != ep2 || (d.y & 0xFFu) == BK_CMD_DONE) continue;
+        }
+        if (u2 >= d.w) continue;     // lost the race for the last units
+        cl.chain = c; cl.cmd = (int)(d.y & 0xFFu); cl.group = (int)(d.y >> 8); cl.njobs = (int)d.z;
+        cl.first = (int)u2; cl.count = u2 + (unsigned)want <= d.w ? want : (int)(d.w - u2);
       }
       if (cl.chain < 0) {
         if (n_finished == P.C) cl.exit_now = 1;
@@ -1050,28 +1056,26 @@ __device__ void worker_loop(const Params& P, DataShared& sh) {
     BLOCK_SYNC();
     const Claim cl = s_claim;
     if (cl.exit_now) return;
-    if (cl.chain >= 0) {
-      if (cl.cmd == BK_CMD_ROUND) {
-        {
-          const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[cl.chain].jobs);
-          uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
-          for (int i = threadIdx.x; i < cl.njobs * 3; i += blockDim.x) d4[i] = __ldcg(g4 + i);
-        }
-        BLOCK_SYNC();
-        if (warp < cl.count) {
-          const int u = cl.first + warp;
-          const int tile = u % P.ntiles, g = u / P.ntiles;
-          const int lo = g * cl.group;
-          const int hi = lo + cl.group < cl.njobs ? lo + cl.group : cl.njobs;
-          round_unit(P, cl.chain, tile, lo, hi, sh.jobs);
-        }
-      } else if (cl.cmd == BK_CMD_SWEEP) {
-        // the claim size was chosen from a hint that may predate this epoch: run every claimed unit
-        for (int u = cl.first; u < cl.first + cl.count; ++u) sweep_unit(P, cl.chain, u, sh);
+    if (cl.chain < 0) continue;
+    if (cl.cmd == BK_CMD_ROUND) {
+      {
+        const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[cl.chain].jobs);
+        uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
+        for (int i = threadIdx.x; i < cl.njobs * 3; i += blockDim.x) d4[i] = __ldcg(g4 + i);
       }
-      BLOCK_SYNC();   // every warp's stores are ordered before the release below
-      if (threadIdx.x == 0) { red_release_add_u32(&P.sync[cl.chain].done, (unsigned)cl.count); t_idle0 = clock64(); }
+      BLOCK_SYNC();
+      if (warp < cl.count) {
+        const int u = cl.first + warp;
+        const int tile = u % P.ntiles, g = u / P.ntiles;
+        const int lo = g * cl.group;
+        const int hi = lo + cl.group < cl.njobs ? lo + cl.group : cl.njobs;
+        round_unit(P, cl.chain, tile, lo, hi, sh.jobs);
+      }
+    } else {  // BK_CMD_SWEEP (the claim may hold several CTA-granular units)
+      for (int u = cl.first; u < cl.first + cl.count; ++u) sweep_unit(P, cl.chain, u, sh);
     }
+    BLOCK_SYNC();   // every warp's stores are ordered before the release below
+    if (threadIdx.x == 0) { red_release_add_u32(&P.sync[cl.chain].done, (unsigned)cl.count); t_idle0 = clock64(); }
   }
 }
 
@@ -1113,6 +1117,10 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       int fin = 0;
       if (cmd == BK_CMD_DONE) {
         fin = 1;
+        epoch += 1;
+        fence_acq_rel_gpu();
+        st_volatile_v4(&sy->desc, make_uint4(epoch, (unsigned)BK_CMD_DONE, 0u, 0u));   // tells the workers this chain is finished
+        st_release_u64(&sy->ticket, (unsigned long long)epoch << 32);
       } else {
         int total = 0, G = 1;
         const int nj = ctl->n_jobs;
@@ -1124,10 +1132,10 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
         } else {
           total = sweep_tiles;
         }
-        ctl->ep_cmd = cmd; ctl->ep_njobs = nj; ctl->ep_group = G; ctl->ep_total = total;
         issued += (unsigned)total; epoch += 1;
-        ctl->ep_id = epoch;
-        st_release_u64(&sy->ticket, (unsigned long long)epoch << 32);   // publishes jobs + descriptor
+        fence_acq_rel_gpu();   // jobs, accumulators, rows bookkeeping written by this CTA happen-before the descriptor
+        st_volatile_v4(&sy->desc, make_uint4(epoch, (unsigned)cmd | ((unsigned)G << 8), (unsigned)nj, (unsigned)total));
+        st_release_u64(&sy->ticket, (unsigned long long)epoch << 32);
       }
       s_flag = fin;
       const unsigned long long q3 = globaltimer_ns();
@@ -1137,7 +1145,6 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
         st->us_control = (int32_t)(t_ctrl / 1000ull); st->us_data = (int32_t)(t_wait / 1000ull);
         st->us_sync = (int32_t)(t_pub / 1000ull); st->us_total = (int32_t)((q3 - t_begin) / 1000ull);
         __threadfence();
-        st_release_u32(&sy->finished, 1u);
       }
     }
     BLOCK_SYNC();
@@ -1152,9 +1159,10 @@ __global__ void __launch_bounds__(BK_CTA_THREADS, 1)
 pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sigma_in, const int max_phases) {
   __shared__ KernelShared sh;
   if ((int)blockIdx.x < P.C) {
-    if (!control_loop(P, blockIdx.x, tune, sigma_in, max_phases, sh.ctl)) return;
+    control_loop(P, blockIdx.x, tune, sigma_in, max_phases, sh.ctl);
+    return;
   }
-  worker_loop(P, sh.data);   // control CTAs help once their chain is done
+  worker_loop(P, sh.data);
 }
 
 // ------------------------------------------------------------------ init kernel

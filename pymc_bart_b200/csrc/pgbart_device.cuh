@@ -141,15 +141,17 @@ struct __align__(16) ChainCtl {
 #define BK_ACC0_STRIDE 4
 #define BK_ACC0_WORDS (257 * BK_ACC0_STRIDE)
 
-// Per-chain dataflow synchronisation words (own 128-byte line each).
-//   ticket: (epoch << 32) | next unclaimed unit.  The chain's control CTA publishes an epoch with a
-//           release store; workers claim units with an acquire fetch-add.
-//   done:   units completed since the step began (workers: release add; control: acquire poll).
+// Per-chain dataflow synchronisation (own 128-byte line each).
+//   desc:   {epoch id, cmd | group << 8, n_jobs, total units}: ONE 16-byte store by the chain's control
+//           CTA (after a release fence), read by workers with one 16-byte load.
+//   ticket: (epoch << 32) | next unclaimed unit: release store by the control CTA after `desc`; workers
+//           claim units with an acquire fetch-add (dynamic balancing across chains).
+//   done:   units completed since the step began (workers: release add; control: polls, then fences).
 struct __align__(128) ChainSync {
+  uint4 desc;
   unsigned long long ticket;
   unsigned int done;
-  unsigned int finished;
-  unsigned int pad[28];
+  unsigned int pad[25];
 };
 static_assert(sizeof(ChainSync) == 128, "ChainSync layout");
 
