@@ -66,7 +66,8 @@ class PGBART:
         self._batches = [[] for _ in range(self.chains)]
         self._published = False
         self.last_stats = None
-        op.n_outputs = 1
+        # read back through the CLASS by BARTRV.rng_fn -> _get_posterior_sampler(cls) (bart.py:65, utils.py:125)
+        (op if isinstance(op, type) else type(op)).n_outputs = 1
 
     # ---- step-method protocol -------------------------------------------------
     @staticmethod
