@@ -59,14 +59,22 @@
 // (compute-sanitizer synccheck: "Divergent thread(s) in warp" at a __syncthreads).  The non-aligned
 // form has per-thread arrival semantics and is legal under intra-warp divergence.
 #define BLOCK_SYNC() asm volatile("barrier.sync 0;" ::: "memory")
+// The control CTA of a chain runs with its first 256 threads only (the other warps exit at once):
+// barrier 1 with an explicit count, so a control-stage barrier waits for 8 warps, not 32.
+#define BK_CTRL_THREADS 256
+#define CTRL_SYNC() asm volatile("barrier.sync 1, 256;" ::: "memory")
+#ifndef BK_PROFILE_CTRL
+#define TSUB(i) do { } while (0)
+#else
 #define TSUB(i)                                                              \
   do {                                                                       \
     if (threadIdx.x == 0) {                                                  \
       unsigned long long now_ = globaltimer_ns();                            \
-      ctl->t_sub[i] += now_ - ctl->t_sub_last;                               \
-      ctl->t_sub_last = now_;                                                \
+      hot->t_sub[i] += now_ - hot->t_sub_last;                               \
+      hot->t_sub_last = now_;                                                \
     }                                                                        \
   } while (0)
+#endif
 
 
 // ------------------------------------------------------------------ PTX helpers
@@ -178,8 +186,28 @@ __device__ __forceinline__ unsigned long long atom_acquire_add_u64(unsigned long
 }
 
 // ------------------------------------------------------------------ small device utils
-__device__ __forceinline__ DParticle* part_ptr(const Params& P, int c, int buf, int q) {
-  return P.parts + ((size_t)c * 2 + buf) * P.P + q;
+// Particle states of the chain a control CTA owns live in its dynamic shared memory: header + the
+// first P.fastF nodes of every particle (both ping-pong buffers); nodes beyond fastF (rare deep trees)
+// overflow to the global `parts` array.  All control-phase particle traffic is then ~30-cycle shared
+// memory instead of ~600-cycle L2 round trips.
+extern __shared__ __align__(16) unsigned char bk_dyn_smem[];
+struct PHdr { int32_t n_nodes, q_head, row, pad; double ssq, lw; };
+static_assert(sizeof(PHdr) == 32, "PHdr layout");
+struct PRef {
+  PHdr* h;
+  DNode* fast;
+  DNode* slow;
+  int F;
+  __device__ __forceinline__ DNode& node(int k) const { return k < F ? fast[k] : slow[k]; }
+};
+__device__ __forceinline__ PRef pref(const Params& P, int c, int buf, int q) {
+  unsigned char* base = bk_dyn_smem + ((size_t)buf * P.P + q) * P.fast_stride;
+  PRef r;
+  r.h = reinterpret_cast<PHdr*>(base);
+  r.fast = reinterpret_cast<DNode*>(base + sizeof(PHdr));
+  r.slow = (P.parts + ((size_t)c * 2 + buf) * P.P + q)->nodes;
+  r.F = P.fastF;
+  return r;
 }
 __device__ __forceinline__ bk_stats node_stats(const DNode& nd) {
   bk_stats s; s.n = nd.n; s.sst = nd.sst; s.sr = nd.sr; s.sr2 = bk_u128_make(nd.sr2_hi, nd.sr2_lo); return s;
@@ -296,12 +324,12 @@ __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first
       sh.anc[i] = lo;
     }
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
 }
 
 __device__ void zero_acc0(const Params& P, int c) {
   unsigned long long* a = P.acc0 + (size_t)c * BK_ACC0_WORDS;
-  for (int i = threadIdx.x; i < BK_ACC0_WORDS; i += blockDim.x) a[i] = 0ull;
+  for (int i = threadIdx.x; i < BK_ACC0_WORDS; i += BK_CTRL_THREADS) a[i] = 0ull;
 }
 
 __device__ void rebuild_cum_dev(const Params& P, int c) {  // thread 0 only
@@ -314,32 +342,32 @@ __device__ void rebuild_cum_dev(const Params& P, int c) {  // thread 0 only
 }
 
 // ------------------------------------------------------------------ control phase
-__device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
-  const int t = ctl->cur_tree;
+__device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
+  const int t = hot->cur_tree;
   const unsigned long long* a0 = P.acc0 + (size_t)c * BK_ACC0_WORDS;
   const DNode* ft = P.forest + ((size_t)c * P.m + t) * BK_MAX_NODES;
   const int nn = P.forest_nn[(size_t)c * P.m + t];
-  DParticle* p0 = part_ptr(P, c, 0, 0);
-  for (int k = threadIdx.x; k < nn; k += blockDim.x) {
+  const PRef p0 = pref(P, c, 0, 0);
+  for (int k = threadIdx.x; k < nn; k += BK_CTRL_THREADS) {
     DNode nd = ft[k];
     nd.sst = 0;
     nd.sr = (int64_t)__ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 0);
     bk_u128 s2 = bk_u128_from_split(__ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 2), __ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 1));
     nd.sr2_hi = s2.hi; nd.sr2_lo = s2.lo;
-    p0->nodes[k] = nd;
+    p0.node(k) = nd;
   }
-  for (int r = threadIdx.x; r < P.R; r += blockDim.x) sh.row_cnt_node[r] = -1;
-  for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += blockDim.x) sh.cum_prior[v] = P.cum[(size_t)c * P.p + v];
-  BLOCK_SYNC();
+  for (int r = threadIdx.x; r < P.R; r += BK_CTRL_THREADS) sh.row_cnt_node[r] = -1;
+  for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += BK_CTRL_THREADS) sh.cum_prior[v] = P.cum[(size_t)c * P.p + v];
+  CTRL_SYNC();
   if (threadIdx.x == 0) {
     double ssq = 0.0;
     for (int k = 0; k < nn; ++k) {
-      const DNode& nd = p0->nodes[k];
+      const DNode& nd = p0.node(k);
       if (nd.var < 0) ssq = BK_DADD(ssq, bk_leaf_ssq(node_stats(nd), nd.value, P.inv_qscale));
     }
-    p0->n_nodes = nn; p0->q_head = nn; p0->row = BK_ROW_FOREST;
-    p0->ssq = ssq; p0->lw = bk_normal_loglik_pre(ssq, ctl->ll_inv2s2, ctl->ll_c);
-    ctl->buf = 0; ctl->round = 0;
+    p0.h->n_nodes = nn; p0.h->q_head = nn; p0.h->row = BK_ROW_FOREST;
+    p0.h->ssq = ssq; p0.h->lw = bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
+    hot->buf = 0; hot->round = 0;
   }
   const int q = threadIdx.x;
   if (q >= 1 && q < P.P) {
@@ -348,33 +376,33 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, CtlShared&
     tot.sr = (int64_t)__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 0);
     tot.sr2 = bk_u128_from_split(__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 2), __ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 1));
     tot.sst = (int64_t)__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 3);
-    DParticle* S = part_ptr(P, c, 0, q);
+    const PRef S = pref(P, c, 0, q);
     DNode nd;
     nd.var = -1; nd.split = 0.0f; nd.left = -1; nd.depth = 0; nd.value = P.init_leaf; nd.pad = 0;
     set_node_stats(nd, tot);
-    S->nodes[0] = nd;
-    S->n_nodes = 1; S->q_head = 0; S->row = BK_ROW_VIRTUAL;
-    S->ssq = bk_leaf_ssq(tot, P.init_leaf, P.inv_qscale);
-    S->lw = bk_normal_loglik_pre(S->ssq, ctl->ll_inv2s2, ctl->ll_c);
+    S.node(0) = nd;
+    S.h->n_nodes = 1; S.h->q_head = 0; S.h->row = BK_ROW_VIRTUAL;
+    S.h->ssq = bk_leaf_ssq(tot, P.init_leaf, P.inv_qscale);
+    S.h->lw = bk_normal_loglik_pre(S.h->ssq, hot->ll_inv2s2, hot->ll_c);
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
 }
 
 // pops, grow decisions, split selection, job list.  Returns (uniformly) the job count.
-__device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
-  const int buf = ctl->buf, round = ctl->round, t = ctl->cur_tree;
-  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)ctl->draw;
+__device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
+  const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)hot->draw;
   const int q = threadIdx.x;
   if (q < P.P) { sh.s_kind[q] = 0; sh.s_next[q] = -1; sh.s_j[q] = -1; }
   if (q >= 1 && q < P.P) {
-    DParticle* S = part_ptr(P, c, buf, q);
-    int nn = S->n_nodes, qh = S->q_head, row = S->row;
+    const PRef S = pref(P, c, buf, q);
+    int nn = S.h->n_nodes, qh = S.h->q_head, row = S.h->row;
     int kind = 0, j = -1, v = -1, next = -1;
     unsigned k = 0;
     if (qh < nn) {
-      j = qh; qh += 1; S->q_head = qh;
-      const int depth = S->nodes[j].depth;
-      const int n = S->nodes[j].n;
+      j = qh; qh += 1; S.h->q_head = qh;
+      const int depth = S.node(j).depth;
+      const int n = S.node(j).n;
       double pl = depth < BK_MAX_DEPTH_TABLE ? P.p_leaf[depth] : 1.0;
       double u1 = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
       if (u1 > pl && nn + 2 <= BK_MAX_NODES) {
@@ -395,23 +423,23 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       if (kind == 1) next = qh;            // a queued node, or one of the two children being made
       else { next = qh < nn ? qh : -1; if (next >= 0) kind = 2; }
     }
-    sh.s_sparse[q] = (j >= 0 && (long long)S->nodes[j].n * 8 < (long long)P.N) ? 1 : 0;
+    sh.s_sparse[q] = (j >= 0 && (long long)S.node(j).n * 8 < (long long)P.N) ? 1 : 0;
     sh.s_kind[q] = kind; sh.s_j[q] = j; sh.s_v[q] = v; sh.s_k[q] = k; sh.s_next[q] = next; sh.s_row[q] = row; sh.s_nn[q] = nn;
-    bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + q - 1);
+    bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + q - 1);
     if (rec) {
       bk_trace_rec r; memset(&r, 0, sizeof(r));
       r.kind = 1; r.tree = t; r.round = round; r.particle = q; r.node = j; r.var = -1; r.ancestor = -1;
       *rec = r;
     }
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
   TSUB(4);
   // split values: one warp per growing particle
   {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, nwarps = BK_CTRL_THREADS >> 5, lane = threadIdx.x & 31;
     __shared__ int s_err;
     if (threadIdx.x == 0) s_err = 0;
-    BLOCK_SYNC();
+    CTRL_SYNC();
     for (int s = 1 + warp; s < P.P; s += nwarps) {
       if (sh.s_kind[s] != 1) continue;
       float sv;
@@ -425,8 +453,8 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       }
       if (lane == 0) sh.s_split[s] = sv;
     }
-      BLOCK_SYNC();
-      if (threadIdx.x == 0 && s_err) ctl->c_err |= s_err;
+      CTRL_SYNC();
+      if (threadIdx.x == 0 && s_err) hot->c_err |= s_err;
   }
   // rows + job list, built in parallel in shared memory:
   //   free rows: ranks of the unused pool rows; growers: rank among the growing slots -> dst row;
@@ -435,9 +463,9 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
   __shared__ int s_free[2 * BK_MAX_PARTICLES];
   __shared__ int s_warp_cnt[3][8];
   if ((int)threadIdx.x < P.R) sh.row_used[threadIdx.x] = 0;
-  BLOCK_SYNC();
+  CTRL_SYNC();
   if (threadIdx.x >= 1 && (int)threadIdx.x < P.P && sh.s_row[threadIdx.x] >= 0) sh.row_used[sh.s_row[threadIdx.x]] = 1;
-  BLOCK_SYNC();
+  CTRL_SYNC();
   {
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     // (i) count-job de-duplication, (ii) per-thread flags
@@ -458,7 +486,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       // stash intra-warp ranks in registers via shared scratch after the barrier below
       s_free[t] = (__popc(bf & below) << 16) | (__popc(bg & below) << 8) | __popc(bc & below);
     }
-    BLOCK_SYNC();
+    CTRL_SYNC();
     if (t < 256) {
       int off_g = 0, off_c = 0, off_f = 0, tot_g = 0;
       for (int k = 0; k < 8; ++k) {
@@ -467,9 +495,9 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
       }
       const int packed = s_free[t];
       const int rank_f = off_f + (packed >> 16), rank_g = off_g + ((packed >> 8) & 0xFF), rank_c = off_c + (packed & 0xFF);
-      BLOCK_SYNC();   // everyone has read its packed ranks; s_free is reused as the free-row list
+      CTRL_SYNC();   // everyone has read its packed ranks; s_free is reused as the free-row list
       if (is_free) s_free[rank_f] = t;
-      BLOCK_SYNC();
+      CTRL_SYNC();
       if (is_grow) {
         Job jb;
         jb.kind = BK_JOB_PARTITION; jb.slot = t; jb.src_row = sh.s_row[t]; jb.dst_row = s_free[rank_g];
@@ -487,38 +515,38 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
         int tot_c = 0, tot_f = 0;
         for (int k = 0; k < 8; ++k) { tot_c += s_warp_cnt[1][k]; tot_f += s_warp_cnt[2][k]; }
         const int nj = tot_g + tot_c;
-        ctl->n_jobs = nj;
-        if (tot_c) ctl->c_count_passes += tot_c;
-        if (tot_g > tot_f) ctl->c_err |= 8;
+        hot->n_jobs = nj;
+        if (tot_c) hot->c_count_passes += tot_c;
+        if (tot_g > tot_f) hot->c_err |= 8;
         s_njobs = nj;
       }
     } else {
-      BLOCK_SYNC();
-      BLOCK_SYNC();
+      CTRL_SYNC();
+      CTRL_SYNC();
     }
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
   {  // publish the job list: 48-byte descriptors stored by many threads
     const int nj = s_njobs;
     const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
     uint4* d4 = reinterpret_cast<uint4*>(ctl->jobs);
-    for (int i = threadIdx.x; i < nj * 3; i += blockDim.x) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < nj * 3; i += BK_CTRL_THREADS) d4[i] = s4[i];
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
   TSUB(6);
   return s_njobs;
 }
 
 // apply the statistics of the finished ROUND to the particles that grew
-__device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl) {
-  const int buf = ctl->buf, round = ctl->round, t = ctl->cur_tree;
-  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)ctl->draw;
-  const int nj = ctl->n_jobs;
+__device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
+  const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)hot->draw;
+  const int nj = hot->n_jobs;
   const int ji = threadIdx.x;
-  if (ji < nj && ctl->jobs[ji].kind == BK_JOB_PARTITION) {
-    const Job jb = ctl->jobs[ji];
+  if (ji < nj && sh.jobs[ji].kind == BK_JOB_PARTITION) {   // the job list staged by propose() is still in shared memory
+    const Job jb = sh.jobs[ji];
     const int q = jb.slot;
-    DParticle* S = part_ptr(P, c, buf, q);
+    const PRef S = pref(P, c, buf, q);
     unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
     bk_stats sl;
     sl.n = (int32_t)__ldcg(acc + BK_ACC_N);
@@ -527,137 +555,142 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl) {
     sl.sr2 = bk_u128_from_split(__ldcg(acc + BK_ACC_SR2HI), __ldcg(acc + BK_ACC_SR2LO));
 #pragma unroll
     for (int e = 0; e < 5; ++e) acc[e] = 0ull;
-    DNode parent = S->nodes[jb.node];
+    DNode parent = S.node(jb.node);
     bk_stats sp = node_stats(parent);
     bk_stats sr = bk_stats_sub(sp, sl);
     double zl = bk_normal(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
     double zr = bk_normal(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
-    float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qscale, (double)P.m, zl, ctl->leaf_sd);
-    float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qscale, (double)P.m, zr, ctl->leaf_sd);
+    float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qscale, (double)P.m, zl, hot->leaf_sd);
+    float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qscale, (double)P.m, zr, hot->leaf_sd);
     double c_parent = bk_leaf_ssq(sp, parent.value, P.inv_qscale);
-    const int nn = S->n_nodes;
+    const int nn = S.h->n_nodes;
     parent.var = jb.var; parent.split = jb.split; parent.left = nn;
-    S->nodes[jb.node] = parent;
+    S.node(jb.node) = parent;
     DNode nl; nl.var = -1; nl.split = 0.0f; nl.left = -1; nl.depth = parent.depth + 1; nl.value = vl; nl.pad = 0;
     set_node_stats(nl, sl);
     DNode nr = nl; nr.value = vr; set_node_stats(nr, sr);
-    S->nodes[nn] = nl; S->nodes[nn + 1] = nr;
-    S->n_nodes = nn + 2;
-    double ssq = BK_DADD(BK_DADD(BK_DSUB(S->ssq, c_parent), bk_leaf_ssq(sl, vl, P.inv_qscale)), bk_leaf_ssq(sr, vr, P.inv_qscale));
-    S->ssq = ssq;
-    S->lw = bk_normal_loglik_pre(ssq, ctl->ll_inv2s2, ctl->ll_c);
-    S->row = jb.dst_row;
-    atomicAdd(&ctl->c_grow, 1);
-    if (jb.src_row == BK_ROW_VIRTUAL) atomicAdd(&ctl->c_grow_root, 1);
-    bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + q - 1);
+    S.node(nn) = nl; S.node(nn + 1) = nr;
+    S.h->n_nodes = nn + 2;
+    double ssq = BK_DADD(BK_DADD(BK_DSUB(S.h->ssq, c_parent), bk_leaf_ssq(sl, vl, P.inv_qscale)), bk_leaf_ssq(sr, vr, P.inv_qscale));
+    S.h->ssq = ssq;
+    S.h->lw = bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
+    S.h->row = jb.dst_row;
+    atomicAdd(&hot->c_grow, 1);
+    if (jb.src_row == BK_ROW_VIRTUAL) atomicAdd(&hot->c_grow_root, 1);
+    bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + q - 1);
     if (rec) { rec->var = jb.var; rec->split = jb.split; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
 }
 
 __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot /* smem, [P] */) {
-  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, nwarps = BK_CTRL_THREADS >> 5, lane = threadIdx.x & 31;
   for (int s = warp; s < P.P; s += nwarps) {
-    const DParticle* src = part_ptr(P, c, buf, anc_of_slot[s]);
-    DParticle* dst = part_ptr(P, c, buf ^ 1, s);
-    const int nn = src->n_nodes;
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    const int words = 2 + nn * 4;
+    const PRef src = pref(P, c, buf, anc_of_slot[s]);
+    const PRef dst = pref(P, c, buf ^ 1, s);
+    const int nn = src.h->n_nodes;
+    const int nfast = nn < P.fastF ? nn : P.fastF;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src.h);
+    uint4* d4 = reinterpret_cast<uint4*>(dst.h);
+    const int words = 2 + nfast * 4;   // 32-byte header + 64-byte nodes, contiguous in shared memory
     for (int i = lane; i < words; i += 32) d4[i] = s4[i];
+    if (nn > P.fastF) {                // overflow nodes live in global memory
+      const uint4* g4 = reinterpret_cast<const uint4*>(src.slow + P.fastF);
+      uint4* h4 = reinterpret_cast<uint4*>(dst.slow + P.fastF);
+      for (int i = lane; i < (nn - P.fastF) * 4; i += 32) h4[i] = g4[i];
+    }
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
 }
 
-__device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, CtlShared& sh) {
-  const int buf = ctl->buf, t = ctl->cur_tree;
-  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)ctl->draw;
-  if ((int)threadIdx.x < P.P) sh.lw[threadIdx.x] = part_ptr(P, c, buf, threadIdx.x)->lw;
-  BLOCK_SYNC();
+__device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
+  const int buf = hot->buf, t = hot->cur_tree;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)hot->draw;
+  if ((int)threadIdx.x < P.P) sh.lw[threadIdx.x] = pref(P, c, buf, threadIdx.x).h->lw;
+  CTRL_SYNC();
   double uf = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
   normalise_and_resample(P, sh, 0, P.P, uf);
   if (threadIdx.x == 0) {
     unsigned pick = bk_index(bk_rng(S0, C0, D0, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P.P);
     sh.pick = pick; sh.win = sh.anc[pick];
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
   const int win = sh.win;
-  const DParticle* W = part_ptr(P, c, buf, win);
+  const PRef W = pref(P, c, buf, win);
   DNode* ft = P.forest + ((size_t)c * P.m + t) * BK_MAX_NODES;
   const int old_nn = P.forest_nn[(size_t)c * P.m + t];
-  const int new_nn = W->n_nodes;
-  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+  const int new_nn = W.h->n_nodes;
+  for (int k = threadIdx.x; k < 256; k += BK_CTRL_THREADS) {
     ctl->old_vals[k] = (k < old_nn && ft[k].var < 0) ? ft[k].value : 0.0f;
-    ctl->new_vals[k] = (k < new_nn && W->nodes[k].var < 0) ? W->nodes[k].value : 0.0f;
+    ctl->new_vals[k] = (k < new_nn && W.node(k).var < 0) ? W.node(k).value : 0.0f;
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
   {
-    const uint4* s4 = reinterpret_cast<const uint4*>(W->nodes);
     uint4* d4 = reinterpret_cast<uint4*>(ft);
-    for (int i = threadIdx.x; i < new_nn * 4; i += blockDim.x) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < new_nn * 4; i += BK_CTRL_THREADS) d4[i] = reinterpret_cast<const uint4*>(&W.node(i >> 2))[i & 3];
   }
   zero_acc0(P, c);
   if (threadIdx.x == 0) {
     P.forest_nn[(size_t)c * P.m + t] = new_nn;
     double* av = P.alpha_vec + (size_t)c * P.p;
-    if (ctl->tune) {
-      if (ctl->iter > P.m) rebuild_cum_dev(P, c);
-      for (int k = 0; k < new_nn; ++k) { int v = W->nodes[k].var; if (v >= 0) av[v] = BK_DADD(av[v], 1.0); }
+    if (hot->tune) {
+      if (hot->iter > P.m) rebuild_cum_dev(P, c);
+      for (int k = 0; k < new_nn; ++k) { int v = W.node(k).var; if (v >= 0) av[v] = BK_DADD(av[v], 1.0); }
     } else {
       int32_t* vi = P.vi + (size_t)c * P.p;
-      for (int k = 0; k < new_nn; ++k) { int v = W->nodes[k].var; if (v >= 0) vi[v] += 1; }
+      for (int k = 0; k < new_nn; ++k) { int v = W.node(k).var; if (v >= 0) vi[v] += 1; }
     }
     SweepJob sj; memset(&sj, 0, sizeof(sj));
-    sj.do_commit = 1; sj.commit_tree = t; sj.new_row = W->row; sj.do_welford = ctl->tune ? 1 : 0;
-    sj.wf_count = ctl->wf_count + (ctl->tune ? 1 : 0);
-    sj.do_prologue = (t + 1 < ctl->tree_hi) ? 1 : 0; sj.prologue_tree = t + 1;
+    sj.do_commit = 1; sj.commit_tree = t; sj.new_row = W.h->row; sj.do_welford = hot->tune ? 1 : 0;
+    sj.wf_count = hot->wf_count + (hot->tune ? 1 : 0);
+    sj.do_prologue = (t + 1 < hot->tree_hi) ? 1 : 0; sj.prologue_tree = t + 1;
     ctl->sweep = sj;
-    ctl->cmd = BK_CMD_SWEEP; ctl->stage = BK_ST_WAIT_SWEEP;
+    hot->cmd = BK_CMD_SWEEP; hot->stage = BK_ST_WAIT_SWEEP;
     // kind-2 trace record is completed after the sweep (leaf_sd); stash its fields now
-    bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base);
+    bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base);
     if (rec) {
       bk_trace_rec r; memset(&r, 0, sizeof(r));
-      r.kind = 2; r.tree = t; r.round = ctl->round; r.particle = win; r.node = new_nn; r.var = -1;
-      r.ancestor = (int32_t)sh.pick; r.log_w = W->lw;
+      r.kind = 2; r.tree = t; r.round = hot->round; r.particle = win; r.node = new_nn; r.var = -1;
+      r.ancestor = (int32_t)sh.pick; r.log_w = W.h->lw;
       *rec = r;
     }
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
 }
 
-__device__ void control_step(const Params& P, int c, int phase, int tune, const float* sigma_in, CtlShared& sh) {
+__device__ void control_step(const Params& P, int c, int phase, int tune, const float* sigma_in, ChainHot* hot, CtlShared& sh) {
   const int first_phase = phase == 0;
   ChainCtl* ctl = P.ctl + c;
   __shared__ int s_stage;
   if (threadIdx.x == 0) {
     if (first_phase) {
-      ctl->stage = BK_ST_START; ctl->tune = tune; ctl->sigma = sigma_in[c];
-      ctl->ll_inv2s2 = bk_normal_inv2s2(ctl->sigma); ctl->ll_c = bk_normal_const(ctl->sigma, (double)P.N);
+      hot->stage = BK_ST_START; hot->tune = tune; hot->sigma = sigma_in[c];
+      hot->ll_inv2s2 = bk_normal_inv2s2(hot->sigma); hot->ll_c = bk_normal_const(hot->sigma, (double)P.N);
     }
-    s_stage = ctl->stage;
+    s_stage = hot->stage;
   }
-  BLOCK_SYNC();
+  CTRL_SYNC();
   int stage = s_stage;
-  if (threadIdx.x == 0) { ctl->t_sub_last = globaltimer_ns(); if (first_phase) for (int i = 0; i < 8; ++i) ctl->t_sub[i] = 0; }
+  if (threadIdx.x == 0) { hot->t_sub_last = globaltimer_ns(); if (first_phase) for (int i = 0; i < 8; ++i) hot->t_sub[i] = 0; }
   MARK(100 + stage);
   if (stage == BK_ST_DONE) return;
-  if (threadIdx.x == 0) ctl->c_phases += 1;
+  if (threadIdx.x == 0) hot->c_phases += 1;
 
   if (stage == BK_ST_START) {
-    for (int v = threadIdx.x; v < P.p; v += blockDim.x) P.vi[(size_t)c * P.p + v] = 0;
+    for (int v = threadIdx.x; v < P.p; v += BK_CTRL_THREADS) P.vi[(size_t)c * P.p + v] = 0;
     zero_acc0(P, c);
     if (threadIdx.x == 0) {
-      int T = ctl->tune ? P.batch_tune : P.batch_post;
-      int lo = ctl->lower, hi = lo + T < P.m ? lo + T : P.m;
-      ctl->tree_lo = lo; ctl->tree_hi = hi; ctl->cur_tree = lo;
-      ctl->c_tree_updates = 0; ctl->c_rounds = 0; ctl->c_grow = 0; ctl->c_grow_root = 0;
-      ctl->c_count_passes = 0; ctl->c_phases = 1; ctl->c_err = 0;
-      ctl->trace_len = 0; ctl->trace_round_base = 0;
+      int T = hot->tune ? P.batch_tune : P.batch_post;
+      int lo = hot->lower, hi = lo + T < P.m ? lo + T : P.m;
+      hot->tree_lo = lo; hot->tree_hi = hi; hot->cur_tree = lo;
+      hot->c_tree_updates = 0; hot->c_rounds = 0; hot->c_grow = 0; hot->c_grow_root = 0;
+      hot->c_count_passes = 0; hot->c_phases = 1; hot->c_err = 0;
+      hot->trace_len = 0; hot->trace_round_base = 0;
       SweepJob sj; memset(&sj, 0, sizeof(sj));
       sj.do_prologue = 1; sj.prologue_tree = lo;
-      ctl->sweep = sj; ctl->cmd = BK_CMD_SWEEP; ctl->stage = BK_ST_WAIT_SWEEP;
+      ctl->sweep = sj; hot->cmd = BK_CMD_SWEEP; hot->stage = BK_ST_WAIT_SWEEP;
     }
-    BLOCK_SYNC();
+    CTRL_SYNC();
     return;
   }
 
@@ -667,42 +700,42 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     if (threadIdx.x == 0) {
       const SweepJob sj = ctl->sweep;
       if (sj.do_commit) {
-        if (ctl->tune) {
-          ctl->wf_count = sj.wf_count;
-          if (ctl->iter > 2) {
+        if (hot->tune) {
+          hot->wf_count = sj.wf_count;
+          if (hot->iter > 2) {
             long long sd_sum = (long long)__ldcg(P.acc0 + (size_t)c * BK_ACC0_WORDS + (size_t)256 * BK_ACC0_STRIDE);
-            ctl->leaf_sd = (float)BK_DDIV(BK_DMUL((double)sd_sum, P.inv_qscale), (double)P.N);
+            hot->leaf_sd = (float)BK_DDIV(BK_DMUL((double)sd_sum, P.inv_qscale), (double)P.N);
           }
         }
-        ctl->c_tree_updates += 1;
-        bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base);
-        if (rec) rec->aux = (double)ctl->leaf_sd;
-        ctl->trace_round_base += 1;
+        hot->c_tree_updates += 1;
+        bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base);
+        if (rec) rec->aux = (double)hot->leaf_sd;
+        hot->trace_round_base += 1;
       }
       if (sj.do_prologue) {
-        ctl->iter += 1; ctl->cur_tree = sj.prologue_tree; s_more = 1;
+        hot->iter += 1; hot->cur_tree = sj.prologue_tree; s_more = 1;
       } else {
         s_more = 0;
-        ctl->lower = ctl->tree_hi < P.m ? ctl->tree_hi : 0;
-        ctl->draw += 1;
-        ctl->cmd = BK_CMD_DONE; ctl->stage = BK_ST_DONE;
+        hot->lower = hot->tree_hi < P.m ? hot->tree_hi : 0;
+        hot->draw += 1;
+        hot->cmd = BK_CMD_DONE; hot->stage = BK_ST_DONE;
         bk_step_stats st; memset(&st, 0, sizeof(st));
-        st.tree_updates = ctl->c_tree_updates; st.rounds = ctl->c_rounds; st.grow_events = ctl->c_grow;
-        st.grow_root = ctl->c_grow_root; st.count_passes = ctl->c_count_passes; st.phases = ctl->c_phases;
-        st.trace_len = ctl->trace_round_base; st.error_flags = ctl->c_err | (ctl->trace_round_base > P.trace_cap && P.trace_cap > 0 ? 1 : 0);
-        st.leaf_sd = ctl->leaf_sd; st.iter = ctl->iter;
+        st.tree_updates = hot->c_tree_updates; st.rounds = hot->c_rounds; st.grow_events = hot->c_grow;
+        st.grow_root = hot->c_grow_root; st.count_passes = hot->c_count_passes; st.phases = hot->c_phases;
+        st.trace_len = hot->trace_round_base; st.error_flags = hot->c_err | (hot->trace_round_base > P.trace_cap && P.trace_cap > 0 ? 1 : 0);
+        st.leaf_sd = hot->leaf_sd; st.iter = hot->iter;
         P.stats[c] = st;
       }
     }
-    BLOCK_SYNC();
+    CTRL_SYNC();
     if (!s_more) return;
     MARK(110);
-    init_particles(P, c, ctl, sh);
+    init_particles(P, c, ctl, hot, sh);
     TSUB(7);
     MARK(111);
   } else {  // BK_ST_WAIT_ROUND
     MARK(120);
-    finalize_grows(P, c, ctl);
+    finalize_grows(P, c, ctl, hot, sh);
     TSUB(0);
     MARK(121);
     have_round = true;
@@ -710,27 +743,27 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
 
   for (;;) {
     if (have_round) {
-      // the round ctl->round is complete: log weights, liveness, resampling
-      const int buf = ctl->buf;
-      if (threadIdx.x == 0) { sh.live = 0; ctl->c_rounds += 1; }
-      BLOCK_SYNC();
+      // the round hot->round is complete: log weights, liveness, resampling
+      const int buf = hot->buf;
+      if (threadIdx.x == 0) { sh.live = 0; hot->c_rounds += 1; }
+      CTRL_SYNC();
       if (threadIdx.x >= 1 && (int)threadIdx.x < P.P) {
-        const DParticle* S = part_ptr(P, c, buf, threadIdx.x);
-        sh.lw[threadIdx.x] = S->lw;
-        if (S->q_head < S->n_nodes) sh.live = 1;
-        bk_trace_rec* rec = trace_at(P, c, ctl->trace_round_base + threadIdx.x - 1);
-        if (rec) rec->log_w = S->lw;
+        const PRef S = pref(P, c, buf, threadIdx.x);
+        sh.lw[threadIdx.x] = S.h->lw;
+        if (S.h->q_head < S.h->n_nodes) sh.live = 1;
+        bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + threadIdx.x - 1);
+        if (rec) rec->log_w = S.h->lw;
       }
-      BLOCK_SYNC();
+      CTRL_SYNC();
       const int live = sh.live;
-      const int rbase = ctl->trace_round_base;
-      BLOCK_SYNC();
-      if (threadIdx.x == 0) ctl->trace_round_base = rbase + (P.P - 1);
+      const int rbase = hot->trace_round_base;
+      CTRL_SYNC();
+      if (threadIdx.x == 0) hot->trace_round_base = rbase + (P.P - 1);
       MARK(130 + live);
       TSUB(1);
-      if (!live) { BLOCK_SYNC(); finish_tree(P, c, ctl, sh); TSUB(7); MARK(139); return; }
-      double u = bk_u01(bk_rng(P.seed, P.chain_base + (uint32_t)c, (uint32_t)ctl->draw, 0, (uint32_t)ctl->cur_tree,
-                               (uint32_t)ctl->round, 0, BK_U_RESAMPLE).v[0]);
+      if (!live) { CTRL_SYNC(); finish_tree(P, c, ctl, hot, sh); TSUB(7); MARK(139); return; }
+      double u = bk_u01(bk_rng(P.seed, P.chain_base + (uint32_t)c, (uint32_t)hot->draw, 0, (uint32_t)hot->cur_tree,
+                               (uint32_t)hot->round, 0, BK_U_RESAMPLE).v[0]);
       MARK(132);
       normalise_and_resample(P, sh, 1, P.P - 1, u);
       TSUB(2);
@@ -742,21 +775,21 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
         s_src[s] = s == 0 ? 0 : sh.anc[s - 1] + 1;
         if (s >= 1) { bk_trace_rec* rec = trace_at(P, c, rbase + s - 1); if (rec) rec->ancestor = s_src[s]; }
       }
-      BLOCK_SYNC();
+      CTRL_SYNC();
       MARK(134);
       copy_particles(P, c, buf, s_src);
       TSUB(3);
       MARK(135);
-      if (threadIdx.x == 0) { ctl->buf = buf ^ 1; ctl->round += 1; }
-      BLOCK_SYNC();
+      if (threadIdx.x == 0) { hot->buf = buf ^ 1; hot->round += 1; }
+      CTRL_SYNC();
     }
     MARK(140);
-    int nj = propose(P, c, ctl, sh);
+    int nj = propose(P, c, ctl, hot, sh);
     MARK(141);
     have_round = true;
     if (nj > 0) {
-      if (threadIdx.x == 0) { ctl->cmd = BK_CMD_ROUND; ctl->stage = BK_ST_WAIT_ROUND; }
-      BLOCK_SYNC();
+      if (threadIdx.x == 0) { hot->cmd = BK_CMD_ROUND; hot->stage = BK_ST_WAIT_ROUND; }
+      CTRL_SYNC();
       return;
     }
   }
@@ -1003,7 +1036,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
   BLOCK_SYNC();
 }
 
-// ------------------------------------------------------------------ the step kernel
+// ------------------------------------------------------------------ dataflow scheduling
 // units claimed by a worker CTA (broadcast through shared memory)
 struct Claim {
   int chain;       // -1: nothing claimed
@@ -1082,10 +1115,14 @@ __device__ void worker_loop(const Params& P, DataShared& sh) {
 // ---- control CTA of chain c: wait for the previous epoch, run the state machine, publish the next
 __device__ bool control_loop(const Params& P, int c, int tune, const float* sigma_in, int max_phases, CtlShared& sh) {
   __shared__ int s_flag;
+  __shared__ ChainHot s_hot;
   ChainCtl* ctl = P.ctl + c;
+  ChainHot* hot = &s_hot;
   ChainSync* sy = P.sync + c;
+  if (threadIdx.x == 0) s_hot = ctl->hot;   // persistent scalars -> shared memory for the whole step
+  CTRL_SYNC();
   unsigned issued = 0, epoch = 0;
-  const int worker_warps = (gridDim.x - P.C) * (blockDim.x >> 5);
+  const int worker_warps = (gridDim.x - P.C) * (BK_CTA_THREADS >> 5);
   const int sweep_tiles = (P.Npad + BK_COMMIT_TILE - 1) / BK_COMMIT_TILE;
   unsigned long long t_wait = 0, t_ctrl = 0, t_pub = 0, t_begin = 0;
   if (threadIdx.x == 0) t_begin = globaltimer_ns();
@@ -1107,13 +1144,13 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       s_flag = ab;
       q1 = globaltimer_ns();
     }
-    BLOCK_SYNC();
+    CTRL_SYNC();
     if (s_flag) return false;
-    control_step(P, c, phase, tune, sigma_in, sh);
-    BLOCK_SYNC();
+    control_step(P, c, phase, tune, sigma_in, hot, sh);
+    CTRL_SYNC();
     if (threadIdx.x == 0) {
       q2 = globaltimer_ns();
-      const int cmd = ctl->cmd;
+      const int cmd = hot->cmd;
       int fin = 0;
       if (cmd == BK_CMD_DONE) {
         fin = 1;
@@ -1123,7 +1160,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
         st_release_u64(&sy->ticket, (unsigned long long)epoch << 32);
       } else {
         int total = 0, G = 1;
-        const int nj = ctl->n_jobs;
+        const int nj = hot->n_jobs;
         if (cmd == BK_CMD_ROUND) {
           long long pt = (long long)nj * P.ntiles;
           long long g = pt / (worker_warps > 0 ? worker_warps : 1);   // about one unit per worker warp
@@ -1141,13 +1178,14 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       const unsigned long long q3 = globaltimer_ns();
       t_wait += q1 - q0; t_ctrl += q2 - q1; t_pub += q3 - q2;
       if (fin) {
+        ctl->hot = s_hot;                   // write the scalar state back
         bk_step_stats* st = P.stats + c;
         st->us_control = (int32_t)(t_ctrl / 1000ull); st->us_data = (int32_t)(t_wait / 1000ull);
         st->us_sync = (int32_t)(t_pub / 1000ull); st->us_total = (int32_t)((q3 - t_begin) / 1000ull);
         __threadfence();
       }
     }
-    BLOCK_SYNC();
+    CTRL_SYNC();
     if (s_flag) return true;
   }
   if (threadIdx.x == 0) { atomicExch(P.abort_flag, 1); }
@@ -1159,7 +1197,7 @@ __global__ void __launch_bounds__(BK_CTA_THREADS, 1)
 pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sigma_in, const int max_phases) {
   __shared__ KernelShared sh;
   if ((int)blockIdx.x < P.C) {
-    control_loop(P, blockIdx.x, tune, sigma_in, max_phases, sh.ctl);
+    if (threadIdx.x < BK_CTRL_THREADS) control_loop(P, blockIdx.x, tune, sigma_in, max_phases, sh.ctl);
     return;
   }
   worker_loop(P, sh.data);
@@ -1191,9 +1229,9 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
   for (size_t i = tid; i < (size_t)P.C * P.p; i += nth) { P.alpha_vec[i] = split_prior[i % P.p]; P.vi[i] = 0; }
   for (size_t c = tid; c < (size_t)P.C; c += nth) {
     ChainCtl* ctl = P.ctl + c;
-    ctl->tune = 1; ctl->sigma = 1.0f; ctl->iter = 0; ctl->lower = 0; ctl->draw = 0; ctl->wf_count = 0;
-    ctl->leaf_sd = leaf_sd_init; ctl->stage = BK_ST_DONE; ctl->cmd = BK_CMD_DONE; ctl->n_jobs = 0;
-    ctl->c_err = 0; ctl->trace_round_base = 0;
+    ctl->hot.tune = 1; ctl->hot.sigma = 1.0f; ctl->hot.iter = 0; ctl->hot.lower = 0; ctl->hot.draw = 0; ctl->hot.wf_count = 0;
+    ctl->hot.leaf_sd = leaf_sd_init; ctl->hot.stage = BK_ST_DONE; ctl->hot.cmd = BK_CMD_DONE; ctl->hot.n_jobs = 0;
+    ctl->hot.c_err = 0; ctl->hot.trace_round_base = 0;
     memset(&P.stats[c], 0, sizeof(bk_step_stats));
   }
   if (tid == 0) *P.abort_flag = 0;
@@ -1263,6 +1301,7 @@ struct bk_handle_s {
   cudaStream_t stream;
   int grid;
   int max_phases;
+  size_t dyn_smem;
   float* sigma_dev;
   double* split_prior_dev;
   int32_t* vi_pinned;
@@ -1392,9 +1431,20 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) { set_err("device lacks cooperative launch"); return BK_ERR_UNSUPPORTED; }
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgbart_step_kernel, BK_CTA_THREADS, 0));
-  if (occ < 1) { set_err("step kernel does not fit on an SM"); return BK_ERR_CUDA; }
+  
+  {
+    // dynamic shared memory of the control CTAs: both particle buffers, header + fastF nodes each
+    const int budget = 168 * 1024;
+    int F = (budget / (2 * P.P) - (int)sizeof(PHdr)) / (int)sizeof(DNode);
+    F = F > 63 ? 63 : F;
+    if (F < 3) { set_err("too many particles for the shared-memory particle store"); return BK_ERR_ARG; }
+    P.fastF = F; P.fast_stride = (int)sizeof(PHdr) + F * (int)sizeof(DNode);
+    h->dyn_smem = (size_t)2 * P.P * P.fast_stride;
+    CK(cudaFuncSetAttribute(pgbart_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+  }
   h->grid = n_sm;  // one persistent CTA per SM (148 on B200): chains control CTAs + workers
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pgbart_step_kernel, BK_CTA_THREADS, h->dyn_smem));
+  if (occ < 1) { set_err("step kernel does not fit on an SM"); return BK_ERR_CUDA; }
   if (h->grid <= P.C) { set_err("more chains than SMs minus one"); return BK_ERR_ARG; }
   if (getenv("BK_DEBUG_MARKERS")) {
     h->marker_count = 4736 + n_sm * 64 + 64;
@@ -1444,7 +1494,7 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
     P.debug = dbg ? atoi(dbg) : 0;
   }
   void* args[] = {(void*)&P, (void*)&tune_i, (void*)&sig, (void*)&maxp};
-  CK(cudaLaunchCooperativeKernel((const void*)pgbart_step_kernel, dim3(h->grid), dim3(BK_CTA_THREADS), args, 0, h->stream));
+  CK(cudaLaunchCooperativeKernel((const void*)pgbart_step_kernel, dim3(h->grid), dim3(BK_CTA_THREADS), args, h->dyn_smem, h->stream));
   CK(cudaMemcpyAsync(h->vi_pinned, P.vi, (size_t)P.C * P.p * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->stats_pinned, P.stats, (size_t)P.C * sizeof(bk_step_stats), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->abort_pinned, P.abort_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1479,7 +1529,7 @@ void* bk_stream(bk_handle* h) { return h ? (void*)h->stream : nullptr; }
 int bk_debug_timers(bk_handle* h, int chain, unsigned long long* out8) {
   if (!h || chain < 0 || chain >= h->P.C) return BK_ERR_ARG;
   ChainCtl* c = h->P.ctl + chain;
-  return cudaMemcpy(out8, (char*)c + offsetof(ChainCtl, t_sub), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? BK_OK : BK_ERR_CUDA;
+  return cudaMemcpy(out8, (char*)c + offsetof(ChainCtl, hot) + offsetof(ChainHot, t_sub), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? BK_OK : BK_ERR_CUDA;
 }
 
 /* debug only (not part of the public header): host view of the per-warp progress markers */

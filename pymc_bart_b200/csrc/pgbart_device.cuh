@@ -91,38 +91,34 @@ struct __align__(16) SweepJob {
   int32_t pad;
 };
 
-struct __align__(16) ChainCtl {
-  // --- inputs set by the host before each step
+// Scalar state of a chain.  The persistent part lives in global memory between steps; during a
+// step the chain's control CTA works on a shared-memory copy (every access is ~30 cycles instead
+// of an L2 round trip) and writes it back when the step is done.
+struct __align__(16) ChainHot {
   int32_t tune;
   float sigma;
-  // --- persistent sampler state
-  int32_t iter;      // tree updates so far
-  int32_t lower;     // first tree of the next batch
-  int32_t draw;      // steps so far (Philox counter word 0)
-  int32_t wf_count;  // Welford count
-  float leaf_sd;
-  // --- state of the running step
+  int32_t iter;      // tree updates so far                  (persistent)
+  int32_t lower;     // first tree of the next batch          (persistent)
+  int32_t draw;      // steps so far (Philox counter word 0)  (persistent)
+  int32_t wf_count;  // Welford count                         (persistent)
+  float leaf_sd;     //                                       (persistent)
   int32_t stage;
   int32_t tree_lo, tree_hi, cur_tree;
   int32_t round;
   int32_t buf;       // particle ping-pong index
   int32_t trace_len;
   int32_t trace_round_base;
-  // --- command + descriptors for the next data phase
   int32_t cmd;
   int32_t n_jobs;
-  SweepJob sweep;
-  // --- counters (bk_step_stats)
   int32_t c_tree_updates, c_rounds, c_grow, c_grow_root, c_count_passes, c_phases, c_err;
-  int32_t pad0;
   double ll_inv2s2, ll_c;   // per-step constants of the Gaussian log-likelihood
-  // --- descriptor of the published epoch (one batch of data units for the workers)
-  int32_t ep_cmd, ep_njobs, ep_group, ep_total;
-  uint32_t ep_id; int32_t ep_pad[3];
-  unsigned long long t_control, t_data, t_sync, t_start;  // ns (globaltimer), control CTA only
   unsigned long long t_sub_last;
-  unsigned long long t_sub[8];  // control sub-steps: finalize, weights, resample, copy, propose, select, jobs, finish/init
-  int32_t row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds
+  unsigned long long t_sub[8];  // optional control sub-step timers (ns), -DBK_PROFILE_CTRL
+};
+
+struct __align__(16) ChainCtl {
+  ChainHot hot;         // global home of the scalar state
+  SweepJob sweep;       // descriptor of the next SWEEP epoch (read by the workers)
   float old_vals[256];  // leaf values of the tree being replaced
   float new_vals[256];  // leaf values of the winning particle
   Job jobs[BK_MAX_PARTICLES];
@@ -157,6 +153,7 @@ static_assert(sizeof(ChainSync) == 128, "ChainSync layout");
 
 struct Params {
   int32_t N, Npad, p, m, P, C, R, ntiles;
+  int32_t fastF, fast_stride;   // nodes per particle kept in the control CTA's shared memory; bytes per particle there
   int32_t lik, trace_cap, batch_tune, batch_post;
   float qscale, init_leaf;
   double inv_qscale;
