@@ -70,7 +70,7 @@ typedef struct {
   float leaf_sd_init;    /* Y.std()/sqrt(m), or 3/sqrt(m) for 0/1 data */
   int32_t device;        /* CUDA device ordinal */
   int32_t trace_capacity;/* trace records per chain per step (0 = off) */
-  int32_t reserved;
+  int32_t n_groups;      /* output groups with separate trees (BART(shape=(k,n), separate_trees=True)); 0/1 = single output */
   const double* p_leaf;        /* [256] P(node at depth d stays a leaf) (bart.py:107-109) */
   const double* split_prior;   /* [n_cols] positive weights (bart.py:139,155) */
   const int32_t* split_rules;  /* [n_cols] BK_RULE_* (bart.py:156), NULL = all continuous */
@@ -135,15 +135,16 @@ int bk_query_bytes(const bk_settings* s, size_t* workspace_bytes);
 int bk_padded_rows(int n_rows);
 
 /* X: [n_cols][ld] float32 (column-major copy of op.X, bart.py:209-210; padding
- * rows may hold anything); y: [ld] float32 (padding 0); sum_trees: [n_chains][ld]
- * float32 (written by every step: the value handed back to PyMC); workspace:
+ * rows may hold anything); y: [n_groups][ld] float32 (padding 0); sum_trees:
+ * [n_chains][n_groups][ld] float32 (written by every step: the value handed back to PyMC); workspace:
  * bk_query_bytes bytes.  All four are device pointers that stay owned by the caller. */
 int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev,
               float* sum_trees_dev, void* workspace_dev, bk_handle** out);
 void bk_destroy(bk_handle* h);
 
-/* One PGBART step for every chain.  sigma_host: [n_chains] likelihood scale of
- * the current point (ignored for Bernoulli).  vi_counts_host: [n_chains][n_cols]
+/* One PGBART step for every chain.  Per-chain arrays below have n_chains*n_groups entries
+ * (index chain*n_groups + group).  sigma_host: likelihood scale of
+ * the current point (ignored for Bernoulli).  vi_counts_host: [..][n_cols]
  * split-variable usage of the trees rewritten by this step (the vector that
  * pymc_bart/utils.py:1387 encodes).  stats_host: [n_chains] or NULL.
  * Launches one persistent kernel on the handle's stream and waits for it. */

@@ -38,7 +38,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         build()
     lib = C.CDLL(LIB_PATH)
-    lib.bko_create.argtypes = [C.POINTER(_cabi.BkSettings), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.bko_create.argtypes = [C.POINTER(_cabi.BkSettings), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.bko_destroy.argtypes = [C.c_void_p]
     lib.bko_destroy.restype = None
     lib.bko_step.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
@@ -59,15 +59,15 @@ def load():
 class OracleChain:
     """One chain of the CPU restatement.  X is column-major [p][N] float32."""
 
-    def __init__(self, settings: SamplerSettings, X_colmajor: np.ndarray, y: np.ndarray, chain: int = 0):
+    def __init__(self, settings: SamplerSettings, X_colmajor: np.ndarray, y: np.ndarray, chain: int = 0, group: int = 0):
         self.lib = load()
         self.settings = settings
         self.X = np.ascontiguousarray(X_colmajor, dtype=np.float32)
-        self.y = np.ascontiguousarray(y, dtype=np.float32)
-        assert self.X.shape == (settings.n_cols, settings.n_rows)
+        self.y = np.ascontiguousarray(np.atleast_2d(np.asarray(y, dtype=np.float32)))   # [n_groups][N]
+        assert self.X.shape == (settings.n_cols, settings.n_rows) and self.y.shape[1] == settings.n_rows
         self._cs = settings.to_c()
         h = C.c_void_p()
-        rc = self.lib.bko_create(C.byref(self._cs), self.X.ctypes.data, self.y.ctypes.data, int(chain), C.byref(h))
+        rc = self.lib.bko_create(C.byref(self._cs), self.X.ctypes.data, self.y.ctypes.data, int(chain), int(group), C.byref(h))
         if rc != 0:
             raise RuntimeError(f"bko_create failed: {rc}")
         self.h = h

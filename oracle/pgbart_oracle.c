@@ -70,7 +70,7 @@ typedef struct {
 
 typedef struct bko_s {
   bk_settings s;
-  int chain;
+  int chain, group;
   int N, p, m, P;
   const float* X; /* [p][N] borrowed */
   const float* y;
@@ -120,13 +120,14 @@ static void rebuild_cum(bko* o) {
   }
 }
 
-int bko_create(const bk_settings* s, const float* X, const float* y, int chain_local, bko** out) {
+/* y: [n_groups][n_rows]; (chain_local, group) selects one chain and one output group (separate trees) */
+int bko_create(const bk_settings* s, const float* X, const float* y, int chain_local, int group, bko** out) {
   if (!s || !X || !y || !out) return BK_ERR_ARG;
   if (s->n_particles < 2 || s->n_rows < 1 || s->n_trees < 1) return BK_ERR_ARG;
   bko* o = (bko*)calloc(1, sizeof(bko));
   o->s = *s; o->chain = chain_local;
   o->N = s->n_rows; o->p = s->n_cols; o->m = s->n_trees; o->P = s->n_particles;
-  o->X = X; o->y = y;
+  o->X = X; o->y = y + (size_t)group * (size_t)s->n_rows; o->group = group;
   memcpy(o->p_leaf, s->p_leaf, sizeof(double) * BK_MAX_DEPTH_TABLE);
   o->alpha_vec = (double*)malloc(sizeof(double) * (size_t)o->p);
   o->cum = (double*)malloc(sizeof(double) * (size_t)o->p);
@@ -232,14 +233,14 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
   uint32_t S = o->s.seed, C = o->s.chain_base + (uint32_t)o->chain, D = (uint32_t)o->draw;
   int depth = nd->depth;
   double pl = depth < BK_MAX_DEPTH_TABLE ? o->p_leaf[depth] : 1.0;
-  double u1 = bk_u01(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_LEAF).v[0]);
+  double u1 = bk_u01(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_LEAF).v[0]);
   if (!(u1 > pl)) return 0;                       /* stays a leaf */
   if (q->n_nodes + 2 > BK_MAX_NODES) return 0;    /* node budget of one byte ids */
-  double u2 = bk_u01(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAR).v[0]);
+  double u2 = bk_u01(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAR).v[0]);
   int v = draw_variable(o, u2);
   int n = nd->st.n;
   if (n < 2) return 0;                            /* fewer than two candidate split values */
-  uint32_t k = bk_index(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAL).v[0], (uint32_t)n);
+  uint32_t k = bk_index(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAL).v[0], (uint32_t)n);
   const float* xc = o->X + (size_t)v * (size_t)N;
   /* k-th member of node j in ascending row index */
   float s = 0.0f;
@@ -265,8 +266,8 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
     t->sr2 = bk_u128_add(t->sr2, bk_u128_make(0, (uint64_t)(a * a)));
   }
   o->bytes_touched += (long long)N * 14;
-  double zl = bk_normal(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_LEFT));
-  double zr = bk_normal(bk_rng(S, C, D, 0, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_RIGHT));
+  double zl = bk_normal(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_LEFT));
+  double zr = bk_normal(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_RIGHT));
   float vl = bk_leaf_value(sl.n, sl.sst, o->inv_qscale, (double)o->m, zl, o->leaf_sd);
   float vr = bk_leaf_value(sr.n, sr.sst, o->inv_qscale, (double)o->m, zr, o->leaf_sd);
   double c_parent = bk_leaf_ssq(nd->st, nd->value, o->inv_qscale);
@@ -341,7 +342,7 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       for (int q = 1; q < P; ++q) if (o->parts[q].q_head < o->parts[q].n_nodes) live = 1;
       if (!live) break;
       normalise_cum(o->parts, 1, P - 1, o->w);
-      double u = bk_u01(bk_rng(S, C, D, 0, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0]);
+      double u = bk_u01(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0]);
       systematic(o->w, P - 1, u, o->anc);
       for (int q = 1; q < P; ++q) part_copy(&o->tmp[q], &o->parts[o->anc[q - 1] + 1], N);
       for (int q = 1; q < P; ++q) {
@@ -351,9 +352,9 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
     }
     /* B9: final selection */
     normalise_cum(o->parts, 0, P, o->w);
-    double uf = bk_u01(bk_rng(S, C, D, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
+    double uf = bk_u01(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
     systematic(o->w, P, uf, o->anc);
-    uint32_t pick = bk_index(bk_rng(S, C, D, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P);
+    uint32_t pick = bk_index(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P);
     int win = o->anc[pick];
     o_particle* nw = &o->parts[win];
     /* commit: sum_trees = noi + predict(new) */

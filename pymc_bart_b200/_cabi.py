@@ -39,7 +39,7 @@ class BkSettings(C.Structure):
         ("leaf_sd_init", C.c_float),
         ("device", C.c_int32),
         ("trace_capacity", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_groups", C.c_int32),
         ("p_leaf", C.POINTER(C.c_double)),
         ("split_prior", C.POINTER(C.c_double)),
         ("split_rules", C.POINTER(C.c_int32)),

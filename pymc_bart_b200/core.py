@@ -24,14 +24,18 @@ class DeviceSampler:
         self.torch = torch
         self.settings = settings
         self.device = torch.device("cuda", settings.device)
-        N, p, Cn = settings.n_rows, settings.n_cols, settings.n_chains
-        self.N, self.p, self.m, self.C = N, p, settings.n_trees, Cn
+        G = max(1, settings.n_groups)
+        N, p, Cn = settings.n_rows, settings.n_cols, settings.n_chains * G   # Cn: chains x output groups
+        self.N, self.p, self.m, self.C, self.G = N, p, settings.n_trees, Cn, G
         self.ld = int(self.lib.bk_padded_rows(N))
         # host staging in pinned memory, column-major fp32 (bart.py:209-210 hands over f64 row-major)
         Xh = torch.zeros((p, self.ld), dtype=torch.float32).pin_memory()
         Xh[:, :N] = torch.from_numpy(np.ascontiguousarray(np.asarray(X, dtype=np.float32).T))
-        yh = torch.zeros((self.ld,), dtype=torch.float32).pin_memory()
-        yh[:N] = torch.from_numpy(np.asarray(Y, dtype=np.float32))
+        yh = torch.zeros((G, self.ld), dtype=torch.float32).pin_memory()
+        Y2 = np.atleast_2d(np.asarray(Y, dtype=np.float32))
+        if Y2.shape != (G, N):
+            raise ValueError(f"Y must have shape ({G}, {N}) for {G} output groups")
+        yh[:, :N] = torch.from_numpy(np.ascontiguousarray(Y2))
         self.h2d_bytes = Xh.numel() * 4 + yh.numel() * 4
         with torch.cuda.device(self.device):
             self.X_dev = Xh.to(self.device, non_blocking=True)

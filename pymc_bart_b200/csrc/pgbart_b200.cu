@@ -391,7 +391,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
 // pops, grow decisions, split selection, job list.  Returns (uniformly) the job count.
 __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
-  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)hot->draw;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   const int q = threadIdx.x;
   if (q < P.P) { sh.s_kind[q] = 0; sh.s_next[q] = -1; sh.s_j[q] = -1; }
   if (q >= 1 && q < P.P) {
@@ -404,9 +404,9 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       const int depth = S.node(j).depth;
       const int n = S.node(j).n;
       double pl = depth < BK_MAX_DEPTH_TABLE ? P.p_leaf[depth] : 1.0;
-      double u1 = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
+      double u1 = bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
       if (u1 > pl && nn + 2 <= BK_MAX_NODES) {
-        double u2 = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAR).v[0]);
+        double u2 = bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAR).v[0]);
         const double* cum = P.cum + (size_t)c * P.p;
         int lo = 0, hi = P.p - 1;  // first index with u2 < cum[idx], else p-1
         while (lo < hi) {
@@ -416,7 +416,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
         }
         v = lo;
         if (n >= 2) {
-          k = bk_index(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAL).v[0], (uint32_t)n);
+          k = bk_index(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAL).v[0], (uint32_t)n);
           kind = 1;
         }
       }
@@ -540,7 +540,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
 // apply the statistics of the finished ROUND to the particles that grew
 __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
-  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)hot->draw;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   const int nj = hot->n_jobs;
   const int ji = threadIdx.x;
   if (ji < nj && sh.jobs[ji].kind == BK_JOB_PARTITION) {   // the job list staged by propose() is still in shared memory
@@ -558,8 +558,8 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     DNode parent = S.node(jb.node);
     bk_stats sp = node_stats(parent);
     bk_stats sr = bk_stats_sub(sp, sl);
-    double zl = bk_normal(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
-    double zr = bk_normal(bk_rng(S0, C0, D0, 0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
+    double zl = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
+    double zr = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
     float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qscale, (double)P.m, zl, hot->leaf_sd);
     float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qscale, (double)P.m, zr, hot->leaf_sd);
     double c_parent = bk_leaf_ssq(sp, parent.value, P.inv_qscale);
@@ -605,13 +605,13 @@ __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_o
 
 __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int buf = hot->buf, t = hot->cur_tree;
-  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)hot->draw;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   if ((int)threadIdx.x < P.P) sh.lw[threadIdx.x] = pref(P, c, buf, threadIdx.x).h->lw;
   CTRL_SYNC();
-  double uf = bk_u01(bk_rng(S0, C0, D0, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
+  double uf = bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
   normalise_and_resample(P, sh, 0, P.P, uf);
   if (threadIdx.x == 0) {
-    unsigned pick = bk_index(bk_rng(S0, C0, D0, 0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P.P);
+    unsigned pick = bk_index(bk_rng(S0, C0, D0, G0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P.P);
     sh.pick = pick; sh.win = sh.anc[pick];
   }
   CTRL_SYNC();
@@ -762,7 +762,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       MARK(130 + live);
       TSUB(1);
       if (!live) { CTRL_SYNC(); finish_tree(P, c, ctl, hot, sh); TSUB(7); MARK(139); return; }
-      double u = bk_u01(bk_rng(P.seed, P.chain_base + (uint32_t)c, (uint32_t)hot->draw, 0, (uint32_t)hot->cur_tree,
+      double u = bk_u01(bk_rng(P.seed, P.chain_base + (uint32_t)(c / P.G), (uint32_t)hot->draw, (uint32_t)(c % P.G), (uint32_t)hot->cur_tree,
                                (uint32_t)hot->round, 0, BK_U_RESAMPLE).v[0]);
       MARK(132);
       normalise_and_resample(P, sh, 1, P.P - 1, u);
@@ -962,7 +962,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
     }
     if (do_pro) {
       unsigned pid4 = __ldcg(reinterpret_cast<const unsigned*>(P.ids_tree + ((size_t)c * P.m + pro_tree) * P.Npad + base));
-      float4 y4 = __ldg(reinterpret_cast<const float4*>(P.y + base));
+      float4 y4 = __ldg(reinterpret_cast<const float4*>(P.y + (size_t)(c % P.G) * P.Npad + base));
       float yv[4] = {y4.x, y4.y, y4.z, y4.w};
       int qrv[4], qsv[4];
 #pragma unroll
@@ -1324,11 +1324,12 @@ static int make_layout(const bk_settings* s, Layout* L) {
   if (!s || s->abi_version != BK_ABI_VERSION) { set_err("bk_settings.abi_version mismatch"); return BK_ERR_ARG; }
   if (s->n_rows < 1 || s->n_cols < 1 || s->n_trees < 1 || s->n_chains < 1) { set_err("empty problem"); return BK_ERR_ARG; }
   if (s->n_particles < 2 || s->n_particles > BK_MAX_PARTICLES) { set_err("n_particles must be in [2,128]"); return BK_ERR_ARG; }
-  if (s->n_chains > 64) { set_err("at most 64 chains per handle"); return BK_ERR_ARG; }
+  if ((long long)s->n_chains * (s->n_groups > 1 ? s->n_groups : 1) > 64) { set_err("at most 64 chains x groups per handle"); return BK_ERR_ARG; }
+  if (s->n_groups > 0xFFFF) { set_err("n_groups must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
   if (s->n_trees > 65535) { set_err("n_trees must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
   if (s->likelihood != BK_LIK_NORMAL) { set_err("likelihood not implemented on the device (no CPU fallback)"); return BK_ERR_UNSUPPORTED; }
   if (!s->p_leaf || !s->split_prior) { set_err("p_leaf and split_prior are required"); return BK_ERR_ARG; }
-  const size_t C = s->n_chains, P = s->n_particles, m = s->n_trees, p = s->n_cols;
+  const size_t C = (size_t)s->n_chains * (s->n_groups > 1 ? s->n_groups : 1), P = s->n_particles, m = s->n_trees, p = s->n_cols;
   L->Npad = (int)align_up((size_t)s->n_rows, BK_WARP_TILE);
   L->ntiles = L->Npad / BK_WARP_TILE;
   L->R = 2 * s->n_particles;
@@ -1395,7 +1396,9 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   h->s = *s;
   char* w = (char*)workspace_dev;
   Params& P = h->P;
-  P.N = s->n_rows; P.Npad = L.Npad; P.p = s->n_cols; P.m = s->n_trees; P.P = s->n_particles; P.C = s->n_chains;
+  P.N = s->n_rows; P.Npad = L.Npad; P.p = s->n_cols; P.m = s->n_trees; P.P = s->n_particles;
+  P.C = s->n_chains * (s->n_groups > 1 ? s->n_groups : 1);
+  P.G = s->n_groups > 1 ? s->n_groups : 1;
   P.R = L.R; P.ntiles = L.ntiles; P.lik = s->likelihood; P.trace_cap = s->trace_capacity > 0 ? s->trace_capacity : 0;
   P.batch_tune = s->batch_tune < 1 ? 1 : s->batch_tune; P.batch_post = s->batch_post < 1 ? 1 : s->batch_post;
   P.qscale = ldexpf(1.0f, s->qshift); P.inv_qscale = ldexp(1.0, -s->qshift); P.init_leaf = s->init_leaf;

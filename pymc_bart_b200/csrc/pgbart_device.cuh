@@ -152,7 +152,8 @@ struct __align__(128) ChainSync {
 static_assert(sizeof(ChainSync) == 128, "ChainSync layout");
 
 struct Params {
-  int32_t N, Npad, p, m, P, C, R, ntiles;
+  int32_t N, Npad, p, m, P, C, R, ntiles;   // C = chains * groups ("virtual chains": one forest + one sum-of-trees row each)
+  int32_t G;                               // output groups per chain (separate trees); y has G rows
   int32_t fastF, fast_stride;   // nodes per particle kept in the control CTA's shared memory; bytes per particle there
   int32_t lik, trace_cap, batch_tune, batch_post;
   float qscale, init_leaf;

@@ -45,6 +45,16 @@ class PGBART:
             raise NotImplementedError("NaN covariates have no device implementation yet")
         if likelihood not in LIKELIHOODS:
             raise NotImplementedError(f"likelihood {likelihood!r} has no device implementation")
+        # multi-output: BART(shape=(k, n), separate_trees=True) = k output groups, each with its own forest and
+        # its own response row (independent likelihood per output); shared-tree multi-output has no device form
+        shape = tuple(getattr(rv, "shape", (np.asarray(op.X).shape[0],)))
+        groups = int(shape[0]) if len(shape) == 2 else 1
+        if groups > 1 and not getattr(op, "separate_trees", False):
+            raise NotImplementedError("multi-output BART needs separate_trees=True on the device (shared trees are not implemented)")
+        Yarr = np.asarray(op.Y, dtype=np.float64)
+        if groups > 1 and Yarr.ndim == 1:
+            Yarr = np.broadcast_to(Yarr, (groups, Yarr.shape[0]))
+        self.groups = groups
         self.op = op
         self.vars = [rv]
         self.num_particles = int(num_particles)
@@ -55,19 +65,20 @@ class PGBART:
         self.sigma_name = sigma_name
         self.store_history = bool(store_history)
         self.settings = make_settings(
-            op.X, op.Y, m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
+            op.X, Yarr, m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
             num_particles=num_particles, batch=batch, n_chains=chains, seed=seed, chain_base=chain_base,
             likelihood=LIKELIHOODS[likelihood], depth_offset=depth_offset, device=device, trace_capacity=trace_capacity,
+            n_groups=groups,
         )
-        self.core = DeviceSampler(self.settings, op.X, op.Y)
+        self.core = DeviceSampler(self.settings, op.X, Yarr)
         self.n_rows, self.n_cols, self.m = self.core.N, self.core.p, self.core.m
         self._lower = 0
         self._baseline = None   # per chain: (nodes [m,255], n_nodes [m])
-        self._batches = [[] for _ in range(self.chains)]
+        self._batches = [[] for _ in range(self.chains * self.groups)]
         self._published = False
         self.last_stats = None
         # read back through the CLASS by BARTRV.rng_fn -> _get_posterior_sampler(cls) (bart.py:65, utils.py:125)
-        (op if isinstance(op, type) else type(op)).n_outputs = 1
+        (op if isinstance(op, type) else type(op)).n_outputs = groups
 
     # ---- step-method protocol -------------------------------------------------
     @staticmethod
@@ -83,17 +94,22 @@ class PGBART:
         T = self.settings.batch_tune if tune else self.settings.batch_post
         lo = self._lower
         hi = min(lo + T, self.m)
+        nvc = self.chains * self.groups          # "virtual chains": chain-major, group-minor
         if not tune and self.store_history and self._baseline is None:
-            self._baseline = [self.core.forest(c) for c in range(self.chains)]
+            self._baseline = [self.core.forest(c) for c in range(nvc)]
         vi, stats = self.core.step(tune, self.sigma)
         self.last_stats = stats
         self._lower = hi if hi < self.m else 0
         value = self.core.sum_trees_host()
         if not tune and self.store_history:
-            for c in range(self.chains):
+            for c in range(nvc):
                 nodes, nn = self.core.trees(c, lo, hi - lo)
                 self._batches[c].append((lo, nodes, nn))
-        out_stats = [{"variable_inclusion": _encode_vi(vi[c].tolist()), "tune": tune} for c in range(self.chains)]
+        vic = vi.reshape(self.chains, self.groups, -1).sum(axis=1)       # one inclusion vector per BART variable
+        out_stats = [{"variable_inclusion": _encode_vi(vic[c].tolist()), "tune": tune} for c in range(self.chains)]
+        value = value.reshape(self.chains, self.groups, -1)
+        if self.groups == 1:
+            value = value[:, 0]
         if self.chains == 1:
             return value[0].copy(), [out_stats[0]]
         return value.copy(), out_stats
@@ -113,7 +129,12 @@ class PGBART:
         if self._published or self._baseline is None:
             return
         for c in range(self.chains):
-            self.op.all_trees.append((self._baseline[c], list(self._batches[c])))
+            if self.groups == 1:
+                self.op.all_trees.append((self._baseline[c], list(self._batches[c])))
+            else:   # one (baseline, batches) pair per output group inside the chain's entry
+                g0 = c * self.groups
+                self.op.all_trees.append(([self._baseline[g0 + g] for g in range(self.groups)],
+                                          [list(self._batches[g0 + g]) for g in range(self.groups)]))
         self._published = True
 
     def close(self):

@@ -67,6 +67,7 @@ class SamplerSettings:
     leaf_sd_init: float
     device: int
     trace_capacity: int
+    n_groups: int
     p_leaf: np.ndarray
     split_prior: np.ndarray
     split_rules: np.ndarray
@@ -76,7 +77,7 @@ class SamplerSettings:
         s = _cabi.BkSettings()
         s.abi_version = _cabi.BK_ABI_VERSION
         for name in ("n_rows", "n_cols", "n_trees", "n_particles", "n_chains", "likelihood", "qshift", "batch_tune",
-                     "batch_post", "seed", "chain_base", "device", "trace_capacity"):
+                     "batch_post", "seed", "chain_base", "device", "trace_capacity", "n_groups"):
             setattr(s, name, int(getattr(self, name)))
         s.init_sum = float(self.init_sum)
         s.init_leaf = float(self.init_leaf)
@@ -107,6 +108,7 @@ def make_settings(
     depth_offset: int = 0,
     device: int = 0,
     trace_capacity: int = 0,
+    n_groups: int = 1,
 ) -> SamplerSettings:
     X = np.asarray(X)
     Y = np.asarray(Y, dtype=np.float64)
@@ -145,6 +147,6 @@ def make_settings(
         likelihood=int(likelihood), qshift=choose_qshift(max(float(np.abs(Y).max()), abs(ymean))),
         batch_tune=bt, batch_post=bp, seed=int(seed) & 0xFFFFFFFF, chain_base=int(chain_base),
         init_sum=float(init_sum), init_leaf=float(init_leaf), leaf_sd_init=float(np.float32(leaf_sd)),
-        device=int(device), trace_capacity=int(trace_capacity),
+        device=int(device), trace_capacity=int(trace_capacity), n_groups=max(1, int(n_groups)),
         p_leaf=depth_prior_table(alpha, beta, depth_offset), split_prior=sp, split_rules=rules,
     )

@@ -85,7 +85,11 @@ class PosteriorSampler:
     @classmethod
     def from_history(cls, batches, baseline_forest, m, n_outputs, split_rules=None, device: int = 0):
         """Rebuild per-draw forests from the initial forest plus per-draw deltas
-        (pymc_bart/utils.py:124-127; CHANGELOG.md:23 "Better tree storage")."""
+        (pymc_bart/utils.py:124-127; CHANGELOG.md:23 "Better tree storage").  With n_outputs > 1
+        (separate trees) `baseline_forest` and `batches` are lists with one entry per output group."""
+        if n_outputs > 1:
+            return _MultiOutputSampler([cls(cls.rebuild_forests(batches[g], baseline_forest[g], m), n_outputs=1,
+                                            split_rules=split_rules, device=device) for g in range(n_outputs)])
         return cls(cls.rebuild_forests(batches, baseline_forest, m), n_outputs=n_outputs, split_rules=split_rules, device=device)
 
     @property
@@ -120,6 +124,24 @@ class PosteriorSampler:
             _cabi.check(rc, "bk_predict")
             res = out.cpu().numpy()
         return res.reshape(di.size, 1, n).astype(np.float64)
+
+
+class _MultiOutputSampler:
+    """k single-output samplers (separate trees) presented as one sampler with n_outputs = k."""
+
+    def __init__(self, parts):
+        self.parts = parts
+
+    @property
+    def n_draws(self):
+        return self.parts[0].n_draws
+
+    @property
+    def n_outputs(self):
+        return len(self.parts)
+
+    def sample_posterior(self, X, draw_indices, excluded=None):
+        return np.concatenate([p.sample_posterior(X, draw_indices, excluded) for p in self.parts], axis=1)
 
 
 def _sample_posterior(sampler, X, rng, size=None, excluded=None):

@@ -108,3 +108,26 @@ def test_unsupported_options_raise_not_fallback():
         pmb.PGBART([pmb.BART("b", Xn, Y, m=3)])
     with pytest.raises(NotImplementedError):
         pmb.PGBART([pmb.BART("c", X, Y, m=3)], likelihood="poisson")
+
+
+def test_multi_output_api_shapes_and_prediction():
+    """pmb.BART(..., shape=(3, n), separate_trees=True): value (3, n), one VI vector per variable, prediction (.., 3, n)."""
+    import pymc_bart_b200 as pmb
+    from pymc_bart_b200.utils import _get_posterior_sampler, _sample_posterior
+
+    X, y, _ = friedman(300, 5, 8)
+    Y = np.stack([y, -y, 0.5 * y])
+    mu = pmb.BART("w", X, Y, m=6, shape=(3, 300), separate_trees=True)
+    out = pmb.sample(mu, tune=60, draws=10, chains=1, num_particles=8, seed=8)
+    assert out["posterior"].shape == (1, 10, 3, 300)
+    op = mu.owner.op
+    assert type(op).n_outputs == 3 and len(op.all_trees) == 1
+    sampler = _get_posterior_sampler(op)
+    pred = _sample_posterior(sampler, X[:7], rng=np.random.default_rng(0), size=4)
+    assert pred.shape == (4, 7, 3)
+    # outputs 0 and 1 were fitted to y and -y: their posterior means must be strongly anti-correlated
+    m0, m1 = out["posterior"][0, :, 0].mean(0), out["posterior"][0, :, 1].mean(0)
+    assert np.corrcoef(m0, m1)[0, 1] < -0.25 and np.corrcoef(m0, y)[0, 1] > 0.4 and np.corrcoef(m1, -y)[0, 1] > 0.4
+    with pytest.raises(NotImplementedError):
+        pmb.PGBART([pmb.BART("s", X, y, m=3, shape=(2, 300))])       # shared-tree multi-output
+    out["step"].close()
