@@ -389,6 +389,17 @@ BK_HD float bk_bernoulli_logit_term(float y, float f) {
   return BK_FSUB(BK_FMUL(y, f), sp);
 }
 
+/* Bernoulli-logit likelihood in fixed point (sum_i y_i*f_i - softplus(f_i)).
+ * The row's linear predictor is f = noi + leaf value, one float add; its log-likelihood term is
+ * quantised to a multiple of 2^-BK_LL_QSHIFT and summed as int64, so a node's / particle's
+ * log-likelihood is an exact integer whatever the reduction order.  |term| <= 512 after clamping. */
+#define BK_LL_QSHIFT 20
+BK_HD int32_t bk_bern_q(float y, float noi, float value) {
+  return bk_quant(bk_bernoulli_logit_term(y, BK_FADD(noi, value)), 1048576.0f);
+}
+/* log-likelihood of a particle from the integer sum of its leaves' terms (exact: |llq| < 2^53) */
+BK_HD double bk_bern_loglik(double llq) { return BK_DMUL(llq, 9.5367431640625e-07); }
+
 /* weight normalisation term exp(lw - max) + 1e-12 */
 BK_HD double bk_weight_term(double lw, double lw_max) {
   return BK_DADD(bk_exp(BK_DSUB(lw, lw_max)), 1e-12);

@@ -33,7 +33,8 @@
  *       variable ~ split prior; split value = X[k-th member, var]
  *   B4  partition the node's rows (x <= s / x == s)
  *   B5  leaf value = mean(sum_trees over members)/m + z * leaf_sd
- *   B6  log-weight = Gaussian log-likelihood from per-leaf (n, sum r, sum r^2)
+ *   B6  log-weight = Gaussian log-likelihood from per-leaf (n, sum r, sum r^2), or Bernoulli-logit
+ *       log-likelihood from a second pass over the rows of the two new leaves (fixed-point terms)
  *   B7  w = exp(lw - max) + 1e-12; cumulative weights c_i = (w_0+..+w_i)/(w_0+..+w_L-1)
  *   B8  systematic resampling of particles 1..P-1
  *   B9  final systematic resampling over all P + uniform pick; commit
@@ -57,12 +58,14 @@ typedef struct {
   int32_t depth;
   float value;
   bk_stats st;
+  int64_t ll;    /* Bernoulli: sum over member rows of the quantised log-likelihood terms at `value` */
 } o_node;
 
 typedef struct {
   int32_t n_nodes;
   int32_t q_head; /* expansion queue = nodes [q_head, n_nodes) in creation order */
   double ssq;
+  int64_t llq;    /* Bernoulli: sum of the leaves' ll */
   double lw;
   o_node nodes[BK_MAX_NODES];
   uint8_t* ids; /* [N] leaf id per row */
@@ -104,7 +107,7 @@ typedef struct bko_s {
 static void part_alloc(o_particle* q, int N) { q->ids = (uint8_t*)malloc((size_t)N); }
 static void part_copy(o_particle* dst, const o_particle* src, int N) {
   uint8_t* keep = dst->ids;
-  dst->n_nodes = src->n_nodes; dst->q_head = src->q_head; dst->ssq = src->ssq; dst->lw = src->lw;
+  dst->n_nodes = src->n_nodes; dst->q_head = src->q_head; dst->ssq = src->ssq; dst->llq = src->llq; dst->lw = src->lw;
   memcpy(dst->nodes, src->nodes, sizeof(o_node) * (size_t)src->n_nodes);
   dst->ids = keep;
   memcpy(dst->ids, src->ids, (size_t)N);
@@ -276,14 +279,28 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
   nl->var = -1; nl->split = 0.0f; nl->left = -1; nl->depth = depth + 1; nl->value = vl; nl->st = sl;
   nr->var = -1; nr->split = 0.0f; nr->left = -1; nr->depth = depth + 1; nr->value = vr; nr->st = sr;
   q->n_nodes += 2;
-  q->ssq = BK_DADD(BK_DADD(BK_DSUB(q->ssq, c_parent), bk_leaf_ssq(sl, vl, o->inv_qscale)), bk_leaf_ssq(sr, vr, o->inv_qscale));
-  q->lw = bk_normal_loglik(q->ssq, sigma, (double)N);
+  if (o->s.likelihood == BK_LIK_BERNOULLI_LOGIT) {
+    /* no sufficient statistic: second pass over the rows of the two new leaves (+9N bytes) */
+    int64_t ll_l = 0, ll_r = 0;
+    for (int i = 0; i < N; ++i) {
+      if (q->ids[i] == (uint8_t)L) ll_l += (int64_t)bk_bern_q(o->y[i], o->noi[i], vl);
+      else if (q->ids[i] == (uint8_t)R) ll_r += (int64_t)bk_bern_q(o->y[i], o->noi[i], vr);
+    }
+    o->bytes_touched += (long long)N * 9;
+    nl->ll = ll_l; nr->ll = ll_r;
+    q->llq = q->llq - nd->ll + ll_l + ll_r;
+    q->lw = bk_bern_loglik((double)q->llq);
+  } else {
+    q->ssq = BK_DADD(BK_DADD(BK_DSUB(q->ssq, c_parent), bk_leaf_ssq(sl, vl, o->inv_qscale)), bk_leaf_ssq(sr, vr, o->inv_qscale));
+    q->lw = bk_normal_loglik(q->ssq, sigma, (double)N);
+  }
   if (rec) { rec->var = v; rec->split = s; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
   return 1;
 }
 
 int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* stats) {
-  if (o->s.likelihood != BK_LIK_NORMAL) return BK_ERR_UNSUPPORTED;
+  const int bern = o->s.likelihood == BK_LIK_BERNOULLI_LOGIT;
+  if (!bern && o->s.likelihood != BK_LIK_NORMAL) return BK_ERR_UNSUPPORTED;
   const int N = o->N, P = o->P, m = o->m;
   bk_step_stats loc; memset(&loc, 0, sizeof(loc));
   o->trace_len = 0;
@@ -296,12 +313,18 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
     o_particle* old = &o->forest[t];
     /* B1: residual without tree t, fixed-point copies */
     bk_stats tot; memset(&tot, 0, sizeof(tot));
-    for (int k = 0; k < old->n_nodes; ++k) { bk_stats z; memset(&z, 0, sizeof(z)); z.n = old->nodes[k].st.n; old->nodes[k].st = z; }
+    for (int k = 0; k < old->n_nodes; ++k) { bk_stats z; memset(&z, 0, sizeof(z)); z.n = old->nodes[k].st.n; old->nodes[k].st = z; old->nodes[k].ll = 0; }
+    int64_t tot_ll = 0;
     for (int i = 0; i < N; ++i) {
       float oldp = old->ids[i] == BK_LIMBO ? 0.0f : old->nodes[old->ids[i]].value;
       float noi = BK_FSUB(o->st[i], oldp);
       float r = BK_FSUB(o->y[i], noi);
       o->noi[i] = noi;
+      if (bern) {   /* per-row terms of the old tree's leaf and of the root-only stump */
+        if (old->ids[i] != BK_LIMBO) old->nodes[old->ids[i]].ll += (int64_t)bk_bern_q(o->y[i], noi, oldp);
+        tot_ll += (int64_t)bk_bern_q(o->y[i], noi, o->s.init_leaf);
+        r = 0.0f;   /* the Gaussian residual statistics are not used */
+      }
       int32_t a = bk_quant(r, o->qscale), b = bk_quant(o->st[i], o->qscale);
       o->qr[i] = a; o->qst[i] = b;
       bk_u128 sq = bk_u128_make(0, (uint64_t)((int64_t)a * (int64_t)a));
@@ -315,16 +338,27 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
     /* B2: particles */
     part_copy(&o->parts[0], old, N);
     o->parts[0].q_head = o->parts[0].n_nodes;
-    o->parts[0].ssq = particle_ssq(o, &o->parts[0]);
-    o->parts[0].lw = bk_normal_loglik(o->parts[0].ssq, sigma, (double)N);
+    if (bern) {
+      int64_t llq = 0;
+      for (int k = 0; k < old->n_nodes; ++k) if (old->nodes[k].var < 0) llq += old->nodes[k].ll;
+      o->parts[0].ssq = 0.0; o->parts[0].llq = llq; o->parts[0].lw = bk_bern_loglik((double)llq);
+    } else {
+      o->parts[0].ssq = particle_ssq(o, &o->parts[0]);
+      o->parts[0].llq = 0;
+      o->parts[0].lw = bk_normal_loglik(o->parts[0].ssq, sigma, (double)N);
+    }
     for (int q = 1; q < P; ++q) {
       o_particle* pq = &o->parts[q];
       pq->n_nodes = 1; pq->q_head = 0;
       pq->nodes[0].var = -1; pq->nodes[0].split = 0.0f; pq->nodes[0].left = -1; pq->nodes[0].depth = 0;
-      pq->nodes[0].value = o->s.init_leaf; pq->nodes[0].st = tot;
+      pq->nodes[0].value = o->s.init_leaf; pq->nodes[0].st = tot; pq->nodes[0].ll = tot_ll;
       memset(pq->ids, 0, (size_t)N);
-      pq->ssq = bk_leaf_ssq(tot, o->s.init_leaf, o->inv_qscale);
-      pq->lw = bk_normal_loglik(pq->ssq, sigma, (double)N);
+      if (bern) { pq->ssq = 0.0; pq->llq = tot_ll; pq->lw = bk_bern_loglik((double)tot_ll); }
+      else {
+        pq->llq = 0;
+        pq->ssq = bk_leaf_ssq(tot, o->s.init_leaf, o->inv_qscale);
+        pq->lw = bk_normal_loglik(pq->ssq, sigma, (double)N);
+      }
     }
     /* B3-B8: grow rounds */
     int round = 0;

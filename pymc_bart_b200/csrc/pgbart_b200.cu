@@ -359,14 +359,15 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
   for (int r = threadIdx.x; r < P.R; r += BK_CTRL_THREADS) sh.row_cnt_node[r] = -1;
   for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += BK_CTRL_THREADS) sh.cum_prior[v] = P.cum[(size_t)c * P.p + v];
   CTRL_SYNC();
+  const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
   if (threadIdx.x == 0) {
-    double ssq = 0.0;
+    double ssq = 0.0;   // Bernoulli: integer sum of the leaves' quantised log-likelihood terms (exact in double)
     for (int k = 0; k < nn; ++k) {
       const DNode& nd = p0.node(k);
-      if (nd.var < 0) ssq = BK_DADD(ssq, bk_leaf_ssq(node_stats(nd), nd.value, P.inv_qscale));
+      if (nd.var < 0) ssq = BK_DADD(ssq, bern ? (double)nd.sr : bk_leaf_ssq(node_stats(nd), nd.value, P.inv_qscale));
     }
     p0.h->n_nodes = nn; p0.h->q_head = nn; p0.h->row = BK_ROW_FOREST;
-    p0.h->ssq = ssq; p0.h->lw = bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
+    p0.h->ssq = ssq; p0.h->lw = bern ? bk_bern_loglik(ssq) : bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
     hot->buf = 0; hot->round = 0;
   }
   const int q = threadIdx.x;
@@ -382,8 +383,8 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     set_node_stats(nd, tot);
     S.node(0) = nd;
     S.h->n_nodes = 1; S.h->q_head = 0; S.h->row = BK_ROW_VIRTUAL;
-    S.h->ssq = bk_leaf_ssq(tot, P.init_leaf, P.inv_qscale);
-    S.h->lw = bk_normal_loglik_pre(S.h->ssq, hot->ll_inv2s2, hot->ll_c);
+    S.h->ssq = bern ? (double)tot.sr : bk_leaf_ssq(tot, P.init_leaf, P.inv_qscale);
+    S.h->lw = bern ? bk_bern_loglik(S.h->ssq) : bk_normal_loglik_pre(S.h->ssq, hot->ll_inv2s2, hot->ll_c);
   }
   CTRL_SYNC();
 }
@@ -515,7 +516,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
         int tot_c = 0, tot_f = 0;
         for (int k = 0; k < 8; ++k) { tot_c += s_warp_cnt[1][k]; tot_f += s_warp_cnt[2][k]; }
         const int nj = tot_g + tot_c;
-        hot->n_jobs = nj;
+        hot->n_jobs = nj; hot->n_grow = tot_g;
         if (tot_c) hot->c_count_passes += tot_c;
         if (tot_g > tot_f) hot->c_err |= 8;
         s_njobs = nj;
@@ -543,6 +544,7 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   const int nj = hot->n_jobs;
   const int ji = threadIdx.x;
+  const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
   if (ji < nj && sh.jobs[ji].kind == BK_JOB_PARTITION) {   // the job list staged by propose() is still in shared memory
     const Job jb = sh.jobs[ji];
     const int q = jb.slot;
@@ -558,6 +560,7 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     DNode parent = S.node(jb.node);
     bk_stats sp = node_stats(parent);
     bk_stats sr = bk_stats_sub(sp, sl);
+    if (bern) { sl.sr = 0; sr.sr = 0; }   // the children's log-likelihood sums arrive with the LL epoch
     double zl = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
     double zr = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
     float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qscale, (double)P.m, zl, hot->leaf_sd);
@@ -571,14 +574,40 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     DNode nr = nl; nr.value = vr; set_node_stats(nr, sr);
     S.node(nn) = nl; S.node(nn + 1) = nr;
     S.h->n_nodes = nn + 2;
-    double ssq = BK_DADD(BK_DADD(BK_DSUB(S.h->ssq, c_parent), bk_leaf_ssq(sl, vl, P.inv_qscale)), bk_leaf_ssq(sr, vr, P.inv_qscale));
-    S.h->ssq = ssq;
-    S.h->lw = bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
+    if (!bern) {
+      double ssq = BK_DADD(BK_DADD(BK_DSUB(S.h->ssq, c_parent), bk_leaf_ssq(sl, vl, P.inv_qscale)), bk_leaf_ssq(sr, vr, P.inv_qscale));
+      S.h->ssq = ssq;
+      S.h->lw = bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
+    } else {   // turn the partition job into the LL job of the same particle (same list position)
+      Job lj = jb;
+      lj.kind = BK_JOB_LL; lj.src_row = jb.dst_row; lj.split = vl; lj.rule = __float_as_int(vr);
+      sh.jobs[ji] = lj;
+    }
     S.h->row = jb.dst_row;
     atomicAdd(&hot->c_grow, 1);
     if (jb.src_row == BK_ROW_VIRTUAL) atomicAdd(&hot->c_grow_root, 1);
     bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + q - 1);
     if (rec) { rec->var = jb.var; rec->split = jb.split; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
+  }
+  CTRL_SYNC();
+}
+
+// Bernoulli: the LL epoch summed the quantised log-likelihood terms of the rows of every new leaf pair
+__device__ void finalize_ll(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
+  const int buf = hot->buf;
+  const int ji = threadIdx.x;
+  if (ji < hot->n_jobs && sh.jobs[ji].kind == BK_JOB_LL) {
+    const Job jb = sh.jobs[ji];
+    const PRef S = pref(P, c, buf, jb.slot);
+    unsigned long long* acc = P.accL + ((size_t)c * P.P + jb.slot) * BK_ACC_STRIDE;
+    const long long ll_l = (long long)__ldcg(acc + BK_ACC_LLL), ll_r = (long long)__ldcg(acc + BK_ACC_LLR);
+    acc[BK_ACC_LLL] = 0ull; acc[BK_ACC_LLR] = 0ull;
+    const long long ll_parent = S.node(jb.node).sr;
+    S.node(jb.left_id).sr = ll_l;
+    S.node(jb.left_id + 1).sr = ll_r;
+    const double llq = BK_DADD(BK_DSUB(S.h->ssq, (double)ll_parent), (double)(ll_l + ll_r));   // integers: exact
+    S.h->ssq = llq;
+    S.h->lw = bk_bern_loglik(llq);
   }
   CTRL_SYNC();
 }
@@ -733,11 +762,26 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     init_particles(P, c, ctl, hot, sh);
     TSUB(7);
     MARK(111);
-  } else {  // BK_ST_WAIT_ROUND
+  } else if (stage == BK_ST_WAIT_ROUND) {
     MARK(120);
     finalize_grows(P, c, ctl, hot, sh);
     TSUB(0);
     MARK(121);
+    if (P.lik == BK_LIK_BERNOULLI_LOGIT && hot->n_grow > 0) {
+      // leaf values are known now: publish the LL jobs (the first n_grow list entries) and wait for their sums
+      const int ng = hot->n_grow;
+      const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
+      uint4* d4 = reinterpret_cast<uint4*>(ctl->jobs);
+      for (int i = threadIdx.x; i < ng * 3; i += BK_CTRL_THREADS) d4[i] = s4[i];
+      CTRL_SYNC();
+      if (threadIdx.x == 0) { hot->n_jobs = ng; hot->cmd = BK_CMD_LL; hot->stage = BK_ST_WAIT_LL; }
+      CTRL_SYNC();
+      return;
+    }
+    have_round = true;
+  } else {  // BK_ST_WAIT_LL
+    finalize_ll(P, c, ctl, hot, sh);
+    TSUB(0);
     have_round = true;
   }
 
@@ -862,16 +906,20 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       if (__any_sync(0xffffffffu, lm != 0)) {
         unsigned n_tot = __reduce_add_sync(0xffffffffu, (unsigned)cl);
         unsigned long long s_st = warp_sum_u64((unsigned long long)a_st);
-        unsigned long long s_r = warp_sum_u64((unsigned long long)a_r);
-        unsigned long long s_lo = warp_sum_u64(a_r2 & 0xFFFFFFFFull);
-        unsigned long long s_hi = warp_sum_u64(a_r2 >> 32);
+        unsigned long long* acc = P.accL + ((size_t)c * P.P + slot) * BK_ACC_STRIDE;
         if (lane == 0) {
-          unsigned long long* acc = P.accL + ((size_t)c * P.P + slot) * BK_ACC_STRIDE;
           red_add_u64(acc + BK_ACC_N, (unsigned long long)n_tot);
           red_add_u64(acc + BK_ACC_SST, s_st);
-          red_add_u64(acc + BK_ACC_SR, s_r);
-          red_add_u64(acc + BK_ACC_SR2LO, s_lo);
-          red_add_u64(acc + BK_ACC_SR2HI, s_hi);
+        }
+        if (P.lik == BK_LIK_NORMAL) {   // Gaussian sufficient statistics of the residual (Bernoulli: q_r holds noi bits)
+          unsigned long long s_r = warp_sum_u64((unsigned long long)a_r);
+          unsigned long long s_lo = warp_sum_u64(a_r2 & 0xFFFFFFFFull);
+          unsigned long long s_hi = warp_sum_u64(a_r2 >> 32);
+          if (lane == 0) {
+            red_add_u64(acc + BK_ACC_SR, s_r);
+            red_add_u64(acc + BK_ACC_SR2LO, s_lo);
+            red_add_u64(acc + BK_ACC_SR2HI, s_hi);
+          }
         }
       }
       if (next_node >= 0) {
@@ -883,6 +931,49 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       for (int e = 0; e < 8; ++e) cnt_next += (((unsigned)(ids >> (8 * e)) & 255u) == (unsigned)next_node) ? 1u : 0u;
       unsigned tot = __reduce_add_sync(0xffffffffu, cnt_next);
       if (lane == 0) P.rowcnt[((size_t)c * P.R + src_row) * P.ntiles + tile] = tot;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ data phase: LL (Bernoulli)
+// Same unit shape as ROUND: one warp, 256 rows, a group of jobs.  noi (float bits kept in the qr array) and
+// y stay in registers; per job the particle's new leaf-id row is read and the rows of the two new leaves
+// contribute their quantised log-likelihood term at the leaf's value (+9N bytes per grow event).
+__device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs) {
+  const int lane = threadIdx.x & 31;
+  const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
+  float noi[8], yv[8];
+  {
+    const int4* a = reinterpret_cast<const int4*>(P.qr + (size_t)c * P.Npad + base);
+    const float4* b = reinterpret_cast<const float4*>(P.y + (size_t)(c % P.G) * P.Npad + base);
+    const int4 a0 = __ldcg(a), a1 = __ldcg(a + 1);
+    const float4 b0 = __ldg(b), b1 = __ldg(b + 1);
+    noi[0] = __int_as_float(a0.x); noi[1] = __int_as_float(a0.y); noi[2] = __int_as_float(a0.z); noi[3] = __int_as_float(a0.w);
+    noi[4] = __int_as_float(a1.x); noi[5] = __int_as_float(a1.y); noi[6] = __int_as_float(a1.z); noi[7] = __int_as_float(a1.w);
+    yv[0] = b0.x; yv[1] = b0.y; yv[2] = b0.z; yv[3] = b0.w; yv[4] = b1.x; yv[5] = b1.y; yv[6] = b1.z; yv[7] = b1.w;
+  }
+  for (int ji = job_lo; ji < job_hi; ++ji) {
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
+    const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
+    const int slot = j0.y, src_row = j0.z;
+    const float vl = __int_as_float(j1.z), vr = __int_as_float(j2.y);
+    const unsigned left_id = (unsigned)j1.w;
+    const unsigned long long ids = __ldcg(reinterpret_cast<const unsigned long long*>(P.rows + ((size_t)c * P.R + src_row) * P.Npad + base));
+    long long s_l = 0, s_r = 0;
+    bool any = false;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const unsigned id = (unsigned)(ids >> (8 * e)) & 255u;
+      if (id == left_id) { s_l += (long long)bk_bern_q(yv[e], noi[e], vl); any = true; }
+      else if (id == left_id + 1u) { s_r += (long long)bk_bern_q(yv[e], noi[e], vr); any = true; }
+    }
+    if (__any_sync(0xffffffffu, any)) {
+      const unsigned long long t_l = warp_sum_u64((unsigned long long)s_l), t_r = warp_sum_u64((unsigned long long)s_r);
+      if (lane == 0) {
+        unsigned long long* acc = P.accL + ((size_t)c * P.P + slot) * BK_ACC_STRIDE;
+        if (t_l) red_add_u64(acc + BK_ACC_LLL, t_l);
+        if (t_r) red_add_u64(acc + BK_ACC_LLR, t_r);
+      }
     }
   }
 }
@@ -970,17 +1061,24 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
         unsigned pid = (pid4 >> (8 * e)) & 255u;
         float oldp = sh.pro_vals[pid];
         float noi = BK_FSUB(stv[e], oldp);
-        float r = BK_FSUB(yv[e], noi);
-        int a = bk_quant(r, P.qscale), b = bk_quant(stv[e], P.qscale);
-        if (base + e >= (size_t)P.N) { a = 0; b = 0; }
-        qrv[e] = a; qsv[e] = b;
-        if (base + e < (size_t)P.N) {
-          unsigned long long sq = (unsigned long long)((long long)a * (long long)a);
-          t_sst += b; t_sr += a; t_r2 += sq;
+        const bool real = base + e < (size_t)P.N;
+        int b = real ? bk_quant(stv[e], P.qscale) : 0;
+        qsv[e] = b;
+        if (P.lik == BK_LIK_NORMAL) {
+          float r = BK_FSUB(yv[e], noi);
+          int a = real ? bk_quant(r, P.qscale) : 0;
+          qrv[e] = a; pro_q[e] = a;
+          if (real) {
+            unsigned long long sq = (unsigned long long)((long long)a * (long long)a);
+            t_sst += b; t_sr += a; t_r2 += sq;
+          }
+        } else {   // Bernoulli: keep noi itself; terms of the old tree's leaf (per leaf) and of the stump (total)
+          qrv[e] = real ? __float_as_int(noi) : 0;
+          pro_q[e] = real ? bk_bern_q(yv[e], noi, oldp) : 0;
+          if (real) { t_sst += b; t_sr += bk_bern_q(yv[e], noi, P.init_leaf); }
         }
       }
       pro_pid4 = pid4; pro_valid = 1;
-      pro_q[0] = qrv[0]; pro_q[1] = qrv[1]; pro_q[2] = qrv[2]; pro_q[3] = qrv[3];
       __stcg(reinterpret_cast<int4*>(P.qr + (size_t)c * P.Npad + base), make_int4(qrv[0], qrv[1], qrv[2], qrv[3]));
       __stcg(reinterpret_cast<int4*>(P.qst + (size_t)c * P.Npad + base), make_int4(qsv[0], qsv[1], qsv[2], qsv[3]));
     }
@@ -996,7 +1094,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
       const unsigned key = ok ? pid : 0x100u;
       const unsigned grp = __match_any_sync(0xffffffffu, key);
       const int a = ok ? pro_q[e] : 0;
-      const unsigned long long sq = (unsigned long long)((long long)a * (long long)a);
+      const unsigned long long sq = P.lik == BK_LIK_NORMAL ? (unsigned long long)((long long)a * (long long)a) : 0ull;
       const unsigned r_lo = __reduce_add_sync(grp, (unsigned)a & 0xFFFFu);
       const int r_hi = __reduce_add_sync(grp, a >> 16);
       const unsigned c0 = __reduce_add_sync(grp, (unsigned)(sq & 0xFFFFull));
@@ -1066,7 +1164,7 @@ __device__ void worker_loop(const Params& P, DataShared& sh) {
         if (d.x == 0) continue;                                    // nothing published yet
         if ((d.y & 0xFFu) == BK_CMD_DONE) { s_fin[c] = 1; n_finished++; continue; }
         if ((unsigned)(t >> 32) != d.x || (unsigned)t >= d.w) continue;   // in transition, or exhausted
-        const int want = (d.y & 0xFFu) == BK_CMD_ROUND ? nwarps : 1;
+        const int want = (d.y & 0xFFu) == BK_CMD_SWEEP ? 1 : nwarps;
         const unsigned long long t2 = atom_acquire_add_u64(&sy->ticket, (unsigned long long)want);
         const unsigned ep2 = (unsigned)(t2 >> 32), u2 = (unsigned)t2;
         if (ep2 != d.x) {            // a newer epoch was published in between: its descriptor is visible now
@@ -1090,7 +1188,7 @@ __device__ void worker_loop(const Params& P, DataShared& sh) {
     const Claim cl = s_claim;
     if (cl.exit_now) return;
     if (cl.chain < 0) continue;
-    if (cl.cmd == BK_CMD_ROUND) {
+    if (cl.cmd == BK_CMD_ROUND || cl.cmd == BK_CMD_LL) {
       {
         const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[cl.chain].jobs);
         uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
@@ -1102,7 +1200,8 @@ __device__ void worker_loop(const Params& P, DataShared& sh) {
         const int tile = u % P.ntiles, g = u / P.ntiles;
         const int lo = g * cl.group;
         const int hi = lo + cl.group < cl.njobs ? lo + cl.group : cl.njobs;
-        round_unit(P, cl.chain, tile, lo, hi, sh.jobs);
+        if (cl.cmd == BK_CMD_ROUND) round_unit(P, cl.chain, tile, lo, hi, sh.jobs);
+        else ll_unit(P, cl.chain, tile, lo, hi, sh.jobs);
       }
     } else {  // BK_CMD_SWEEP (the claim may hold several CTA-granular units)
       for (int u = cl.first; u < cl.first + cl.count; ++u) sweep_unit(P, cl.chain, u, sh);
@@ -1161,7 +1260,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       } else {
         int total = 0, G = 1;
         const int nj = hot->n_jobs;
-        if (cmd == BK_CMD_ROUND) {
+        if (cmd == BK_CMD_ROUND || cmd == BK_CMD_LL) {
           long long pt = (long long)nj * P.ntiles;
           long long g = pt / (worker_warps > 0 ? worker_warps : 1);   // about one unit per worker warp
           G = g < 1 ? 1 : (g > BK_MAX_GROUP ? BK_MAX_GROUP : (int)g);
@@ -1327,7 +1426,7 @@ static int make_layout(const bk_settings* s, Layout* L) {
   if ((long long)s->n_chains * (s->n_groups > 1 ? s->n_groups : 1) > 64) { set_err("at most 64 chains x groups per handle"); return BK_ERR_ARG; }
   if (s->n_groups > 0xFFFF) { set_err("n_groups must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
   if (s->n_trees > 65535) { set_err("n_trees must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
-  if (s->likelihood != BK_LIK_NORMAL) { set_err("likelihood not implemented on the device (no CPU fallback)"); return BK_ERR_UNSUPPORTED; }
+  if (s->likelihood != BK_LIK_NORMAL && s->likelihood != BK_LIK_BERNOULLI_LOGIT) { set_err("likelihood not implemented on the device (no CPU fallback)"); return BK_ERR_UNSUPPORTED; }
   if (!s->p_leaf || !s->split_prior) { set_err("p_leaf and split_prior are required"); return BK_ERR_ARG; }
   const size_t C = (size_t)s->n_chains * (s->n_groups > 1 ? s->n_groups : 1), P = s->n_particles, m = s->n_trees, p = s->n_cols;
   L->Npad = (int)align_up((size_t)s->n_rows, BK_WARP_TILE);

@@ -29,15 +29,18 @@
 #define BK_CMD_ROUND 1
 #define BK_CMD_SWEEP 2   // commit of tree A and/or prologue of tree B, fused
 #define BK_CMD_DONE 3
+#define BK_CMD_LL 4      // Bernoulli: log-likelihood terms of the rows of freshly made leaves
 
 // chain state machine
 #define BK_ST_START 0
 #define BK_ST_WAIT_SWEEP 1
 #define BK_ST_WAIT_ROUND 2
 #define BK_ST_DONE 3
+#define BK_ST_WAIT_LL 4
 
 #define BK_JOB_PARTITION 1
 #define BK_JOB_COUNT 2
+#define BK_JOB_LL 3   // src_row = the particle's new row, left_id, split = left leaf value, rule = bits of the right leaf value
 
 struct __align__(16) DNode {
   int32_t var;   // -1 = leaf
@@ -110,6 +113,7 @@ struct __align__(16) ChainHot {
   int32_t trace_round_base;
   int32_t cmd;
   int32_t n_jobs;
+  int32_t n_grow;    // partition jobs among them (listed first)
   int32_t c_tree_updates, c_rounds, c_grow, c_grow_root, c_count_passes, c_phases, c_err;
   double ll_inv2s2, ll_c;   // per-step constants of the Gaussian log-likelihood
   unsigned long long t_sub_last;
@@ -130,6 +134,8 @@ struct __align__(16) ChainCtl {
 #define BK_ACC_SR 2
 #define BK_ACC_SR2LO 3
 #define BK_ACC_SR2HI 4
+#define BK_ACC_LLL 5    // Bernoulli: quantised log-likelihood of the new left / right leaf
+#define BK_ACC_LLR 6
 #define BK_ACC_STRIDE 8
 
 // acc0 layout per chain: [256][4]: leaf k -> (sr, sr2lo, sr2hi, n); entry 255 = totals

@@ -138,13 +138,19 @@ def make_settings(
         leaf_sd = 3.0 / math.sqrt(m)
     else:
         leaf_sd = float(Y.std()) / math.sqrt(m)
+    if int(likelihood) == _cabi.BK_LIK_BERNOULLI_LOGIT:
+        if not np.all((Y == 0.0) | (Y == 1.0)):
+            raise ValueError("the Bernoulli likelihood needs a 0/1 response")
+        qshift = choose_qshift(16.0)    # the sum of trees is a logit: fixed-point range +-64
+    else:
+        qshift = choose_qshift(max(float(np.abs(Y).max()), abs(ymean)))
     bt = max(1, int(m * batch[0]))
     bp = max(1, int(m * batch[1]))
     init_sum = np.float32(ymean)
     init_leaf = np.float32(ymean / m)
     return SamplerSettings(
         n_rows=n, n_cols=p, n_trees=int(m), n_particles=int(num_particles), n_chains=int(n_chains),
-        likelihood=int(likelihood), qshift=choose_qshift(max(float(np.abs(Y).max()), abs(ymean))),
+        likelihood=int(likelihood), qshift=qshift,
         batch_tune=bt, batch_post=bp, seed=int(seed) & 0xFFFFFFFF, chain_base=int(chain_base),
         init_sum=float(init_sum), init_leaf=float(init_leaf), leaf_sd_init=float(np.float32(leaf_sd)),
         device=int(device), trace_capacity=int(trace_capacity), n_groups=max(1, int(n_groups)),

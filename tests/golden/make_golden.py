@@ -21,12 +21,14 @@ CASES = {
     "c1_n200_p5_m10_P20": (200, 5, 10, 20, 40, 1, 0),
     "ragged_n777_p7_m12_P9": (777, 7, 12, 9, 20, 3, 0),
     "hist_n300_p4_m6_P16": (300, 4, 6, 16, 20, 5, 1),
+    # Bernoulli-logit likelihood (8th field = likelihood code)
+    "bern_n500_p6_m8_P12": (500, 6, 8, 12, 24, 7, 0, 1),
 }
 
 
-def run_case(N, p, m, P, draws, seed, depth_offset):
-    X, y, _ = friedman(N, p, seed)
-    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=depth_offset, trace_capacity=20000)
+def run_case(N, p, m, P, draws, seed, depth_offset, lik=0):
+    X, y, _ = friedman(N, p, seed, kind="bernoulli" if lik else "normal")
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=depth_offset, trace_capacity=20000, likelihood=lik)
     o = OracleChain(s, X.T.copy(), y)
     traces, sums, vis, sds = [], [], [], []
     for d in range(draws):
@@ -42,6 +44,9 @@ def run_case(N, p, m, P, draws, seed, depth_offset):
 
 if __name__ == "__main__":
     out = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]
     for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
         np.savez_compressed(os.path.join(out, name + ".npz"), cfg=np.array(cfg), **run_case(*cfg))
         print("wrote", name)

@@ -21,12 +21,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-@pytest.mark.parametrize("name", ["c1_n200_p5_m10_P20", "ragged_n777_p7_m12_P9", "hist_n300_p4_m6_P16"])
+@pytest.mark.parametrize("name", ["c1_n200_p5_m10_P20", "ragged_n777_p7_m12_P9", "hist_n300_p4_m6_P16", "bern_n500_p6_m8_P12"])
 def test_oracle_matches_golden(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    N, p, m, P, draws, seed, off = [int(v) for v in g["cfg"]]
-    X, y, _ = friedman(N, p, seed)
-    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=off, trace_capacity=20000)
+    N, p, m, P, draws, seed, off = [int(v) for v in g["cfg"][:7]]
+    lik = int(g["cfg"][7]) if len(g["cfg"]) > 7 else 0
+    X, y, _ = friedman(N, p, seed, kind="bernoulli" if lik else "normal")
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=off, trace_capacity=20000, likelihood=lik)
     o = OracleChain(s, X.T.copy(), y)
     pos = 0
     for d in range(draws):
@@ -59,6 +60,9 @@ int main(void){
   double s=0,s2=0; int n=400000; for(int i=0;i<n;i++){ double z=bk_normal(bk_rng(1,2,i,0,0,0,0,3)); s+=z; s2+=z*z; }
   printf("%.5f %.5f\n", s/n, s2/n);
   printf("%d %d\n", bk_quant(1.0f, 1024.0f), bk_quant(-1e30f, 1024.0f));
+  double mb=0; for(int i=0;i<400000;i++){ float f=(float)(-60.0+120.0*rand()/RAND_MAX); float yy=(float)(i&1);
+    double ex=(double)yy*f-(f>0?f+log1p(exp(-(double)f)):log1p(exp((double)f))); double d=fabs((double)bk_bernoulli_logit_term(yy,f)-ex)/(1.0+fabs(ex)); if(d>mb)mb=d; }
+  printf("%.3e %d\n", mb, bk_bern_q(1.0f, 0.25f, -0.25f));
   return 0; }
 '''
     d = os.path.join(ROOT, "oracle", "_probe")
@@ -80,6 +84,9 @@ def test_spec_header_known_answers():
     mean, var = [float(v) for v in out[4].split()]
     assert abs(mean) < 0.01 and abs(var - 1) < 0.01
     assert out[5].split() == ["1024", str(-(2**29 - 1))]
+    mb, q0 = out[6].split()
+    assert float(mb) < 1e-6                       # Bernoulli-logit term (float kernel) vs libm in double
+    assert abs(int(q0) - round(-np.log(2.0) * 2**20)) <= 1  # y=1, f=0: -log 2 in units of 2^-20
 
 
 def test_vi_dominance_statistical():
@@ -135,6 +142,25 @@ def test_prediction_self_consistency_and_in_sample():
     # excluding every variable collapses each tree to its training-weighted mean leaf
     ex = oracle_py.predict(forests, X[:5], [0], excluded_mask=np.ones(5, np.uint8))
     assert np.allclose(ex[0], ex[0][0])
+
+
+def test_bernoulli_oracle_recovers_the_logit():
+    """tests/test_bart.py:150-164 style check for the non-Gaussian path: the fitted logit tracks the truth and the
+    in-sample Bernoulli log-likelihood approaches the data-generating one."""
+    X, y, f = friedman(4000, 8, 3, kind="bernoulli")
+    s = make_settings(X, y, m=30, num_particles=12, seed=3, likelihood=_cabi.BK_LIK_BERNOULLI_LOGIT)
+    o = OracleChain(s, X.T.copy(), y)
+    ll = lambda st: float(np.mean(y * st - np.logaddexp(0, st)))
+    l0 = ll(o.sum_trees())
+    for d in range(120):
+        o.step(d < 60, 1.0)
+    pr = 1 / (1 + np.exp(-(f - 14.4) / 4.9))
+    l_true = float(np.mean(y * np.log(pr) + (1 - y) * np.log(1 - pr)))
+    l1 = ll(o.sum_trees())
+    assert l1 > l0 + 0.08 and abs(l1 - l_true) < 0.03
+    assert np.corrcoef(o.sum_trees(), f)[0, 1] > 0.8
+    with pytest.raises(ValueError):
+        make_settings(X, y + 0.5, m=5, likelihood=_cabi.BK_LIK_BERNOULLI_LOGIT)
 
 
 def test_edge_cases():
