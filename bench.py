@@ -25,24 +25,37 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 CONFIGS = {
-    #        N        p   m    P   chains seed
-    "C1": (200, 5, 10, 20, 1, 1),
-    "C2": (100_000, 10, 50, 40, 4, 2),
-    "C5": (1_000_000, 50, 200, 60, 8, 5),
+    # BASELINE.json configs[0..4]:  N, p, m, P, chains per GPU, seed, likelihood (0 Normal, 1 Bernoulli-logit), output groups
+    "C1": (200, 5, 10, 20, 1, 1, 0, 1),
+    "C2": (100_000, 10, 50, 40, 4, 2, 0, 1),
+    "C3": (50_000, 20, 100, 40, 4, 3, 1, 1),
+    "C4": (50_000, 15, 50, 40, 1, 4, 0, 3),
+    "C5": (1_000_000, 50, 200, 60, 1, 5, 0, 1),   # 8 chains = one per GPU on the 8xB200 box
 }
 
 
-def friedman(N, p, seed):
+def friedman(N, p, seed, lik=0, groups=1):
+    """SURVEY.md §8(d) synthetic inputs (Friedman; Bernoulli: centred/scaled logit; multi-output: column permutations)."""
     rng = np.random.default_rng(seed)
     X = rng.uniform(0, 1, (N, p)).astype(np.float32)
-    f = 10 * np.sin(np.pi * X[:, 0] * X[:, 1]) + 20 * (X[:, 2] - 0.5) ** 2 + 10 * X[:, 3] + 5 * X[:, 4]
-    y = (f + rng.normal(0, 1, N)).astype(np.float32)
+
+    def fr(Z):
+        return 10 * np.sin(np.pi * Z[:, 0] * Z[:, 1]) + 20 * (Z[:, 2] - 0.5) ** 2 + 10 * Z[:, 3] + 5 * Z[:, 4]
+
+    if groups > 1:
+        y = np.stack([fr(X[:, np.roll(np.arange(p), j)]) + rng.normal(0, 1, N) for j in range(groups)]).astype(np.float32)
+    elif lik == 1:
+        pr = 1.0 / (1.0 + np.exp(-(fr(X) - 14.4) / 4.9))
+        y = (rng.uniform(0, 1, N) < pr).astype(np.float32)
+    else:
+        y = (fr(X) + rng.normal(0, 1, N)).astype(np.float32)
     return X, y
 
 
-def algorithmic_bytes(N, grow_events, tree_updates, tune_updates):
-    """per grow event 14N; per tree update 23N (+16N while tuning)."""
-    return 14.0 * N * grow_events + 23.0 * N * tree_updates + 16.0 * N * tune_updates
+def algorithmic_bytes(N, grow_events, tree_updates, tune_updates, lik=0):
+    """per grow event 14N (+9N second pass for non-Gaussian likelihoods); per tree update 23N
+    (+16N while tuning)."""
+    return (14.0 + (9.0 if lik else 0.0)) * N * grow_events + 23.0 * N * tree_updates + 16.0 * N * tune_updates
 
 
 class ClockSampler:
@@ -89,16 +102,16 @@ def run_reference(args, cfg):
     from oracle.oracle_py import OracleChain
     from pymc_bart_b200.settings import make_settings
 
-    N, p, m, P, chains, seed = cfg
+    N, p, m, P, chains, seed, lik, groups = cfg
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    X, y = friedman(N, p, seed)
-    threads = min(os.cpu_count() or 1, chains * max(1, args.gpus))
+    X, y = friedman(N, p, seed, lik, groups)
     n_chains = chains * max(1, args.gpus)
-    s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1)
+    threads = min(os.cpu_count() or 1, n_chains * groups)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1, likelihood=lik, n_groups=groups)
     Xc = np.ascontiguousarray(X.T)
-    orcs = [OracleChain(s, Xc, y, chain=c) for c in range(n_chains)]
+    orcs = [OracleChain(s, Xc, y, chain=c, group=g) for c in range(n_chains) for g in range(groups)]
     steps, warm = args.steps, args.warmup
 
     def work(o, n, tune):
@@ -158,7 +171,7 @@ def main():
     from pymc_bart_b200.core import DeviceSampler
     from pymc_bart_b200.settings import make_settings
 
-    N, p, m, P, chains, seed = cfg
+    N, p, m, P, chains, seed, lik, groups = cfg
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -166,8 +179,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     steps, warm = args.steps, max(3, args.warmup)
-    X, y = friedman(N, p, seed)
-    s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains, chain_base=rank * chains, device=local)
+    X, y = friedman(N, p, seed, lik, groups)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains, chain_base=rank * chains, device=local,
+                      likelihood=lik, n_groups=groups)
     dev = DeviceSampler(s, X, y)
     stream = dev.stream()
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -187,7 +201,8 @@ def main():
     clocks.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     grow = tupd = tune_upd = rounds = phases = 0
-    post_mean = torch.zeros((chains, N), dtype=torch.float32, device="cuda")
+    nvc = chains * groups   # (chain, output group) pairs: one forest and one sum-of-trees row each
+    post_mean = torch.zeros((nvc, N), dtype=torch.float32, device="cuda")
     for i in range(steps):
         tune = i < n_tune
         if flush is not None:
@@ -197,7 +212,7 @@ def main():
         dev.step_launch(tune, 1.0)
         ev[i][1].record(stream)
         _, st = dev.step_wait()
-        for c in range(chains):
+        for c in range(nvc):
             grow += st[c].grow_events; tupd += st[c].tree_updates; rounds += st[c].rounds
             tune_upd += st[c].tree_updates if tune else 0
         phases += st[0].phases
@@ -237,8 +252,9 @@ def main():
     torch.cuda.synchronize()
     e2e_steps = max(10, steps // 4)
     t0 = time.perf_counter()
-    rv = BART("mu", X, y, m=m)
-    stp = PGBART([rv], num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=False)
+    rv = BART("mu", X, y, m=m, shape=(groups, N) if groups > 1 else None, separate_trees=groups > 1)
+    stp = PGBART([rv], num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=False,
+                 likelihood="bernoulli" if lik else "normal")
     t_build = time.perf_counter() - t0
     for i in range(3):
         stp.astep()
@@ -254,8 +270,8 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_val = world * chains * e2e_steps / float(e2e_t.item())
-    h2d = chains * 4
-    d2h = chains * N * 4 + chains * p * 4 + chains * 48 + 4
+    h2d = nvc * 4
+    d2h = nvc * N * 4 + nvc * p * 4 + nvc * 64 + 4
     h2d_once = stp.core.h2d_bytes
     stp.close()
 
@@ -269,14 +285,15 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         # roofline of the dominant (only) kernel: pgbart_step_kernel, one launch per step
         ms_kernel = float(np.mean(step_ms))
-        bytes_per_launch = algorithmic_bytes(N, grow / steps, tupd / steps, tune_upd / steps)
+        bytes_per_launch = algorithmic_bytes(N, grow / steps, tupd / steps, tune_upd / steps, lik)
         achieved = bytes_per_launch / (ms_kernel / 1e3) / 1e9
         line = {
             "metric": "PGBART draws/sec", "value": value, "unit": "draws/s", "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i64", "data": "synthetic",
             "config": {
-                "workload": f"{args.config}: Friedman N={N} p={p} m={m} trees particles={P} chains/GPU={chains} sigma=1 fixed, "
+                "workload": f"{args.config}: Friedman N={N} p={p} m={m} trees particles={P} chains/GPU={chains} "
+                            f"{'Bernoulli-logit' if lik else 'Normal'} likelihood{f', {groups} outputs with separate trees' if groups > 1 else ''}, sigma=1 fixed, "
                             f"batch=(0.1,0.1) -> {s.batch_tune} trees/draw, depth prior alpha(1+d)^-beta (bart.py:107-109); "
                             f"{n_tune} tuning + {steps - n_tune} post-tuning draws timed",
                 "l2": "256 MB fill between timed steps (L2 flushed)" if flush is not None else "no flush (working set stays in L2)",
@@ -297,16 +314,16 @@ def main():
         try:
             from oracle.oracle_py import OracleChain
 
-            s1 = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1)
+            s1 = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1, likelihood=lik, n_groups=groups)
             Xc = np.ascontiguousarray(X.T)
-            ncpu = min(os.cpu_count() or 1, chains)
-            orcs = [OracleChain(s1, Xc, y, chain=c) for c in range(ncpu)]
-            nd = args.cpu_draws or (3 if N >= 100_000 else 100)
+            ncpu = max(1, min((os.cpu_count() or 1) // groups, chains))   # chains sampled; each needs `groups` threads
+            orcs = [OracleChain(s1, Xc, y, chain=c, group=g) for c in range(ncpu) for g in range(groups)]
+            nd = args.cpu_draws or (3 if N >= 100_000 else (20 if N >= 10_000 else 100))
             t0 = time.perf_counter()
             ths = [threading.Thread(target=lambda o=o: [o.step(True, 1.0) for _ in range(nd)]) for o in orcs]
             [t.start() for t in ths]; [t.join() for t in ths]
             cdt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": ncpu * nd / cdt, "unit": "draws/s", "cores": ncpu, "kind": "port",
+            line["cpu_baseline"] = {"value": ncpu * nd / cdt, "unit": "draws/s", "cores": ncpu * groups, "kind": "port",
                                     "sample": f"{nd} tuning draws x {ncpu} chains of {args.config}, one chain per host thread "
                                               f"(oracle/pgbart_oracle.c; bartrs is not installable offline)"}
         except Exception as e:  # noqa

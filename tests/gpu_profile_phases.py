@@ -8,10 +8,10 @@ from pymc_bart_b200.core import DeviceSampler
 from pymc_bart_b200.settings import make_settings
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-N, p, m, P, chains, seed = CONFIGS[cfg]
+N, p, m, P, chains, seed, lik, groups = CONFIGS[cfg]
 if len(sys.argv) > 3: chains = int(sys.argv[3])
-X, y = friedman(N, p, seed)
-s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains)
+X, y = friedman(N, p, seed, lik, groups)
+s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains, likelihood=lik, n_groups=groups)
 dev = DeviceSampler(s, X, y)
 for i in range(5): dev.step(True, 1.0)
 import ctypes
