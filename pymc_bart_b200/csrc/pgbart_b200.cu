@@ -63,6 +63,8 @@
 // barrier 1 with an explicit count, so a control-stage barrier waits for 8 warps, not 32.
 #define BK_CTRL_THREADS 256
 #define CTRL_SYNC() asm volatile("barrier.sync 1, 256;" ::: "memory")
+// worker group g uses barrier 2+g with BK_GROUP_THREADS arrivals
+#define GROUP_SYNC(g) asm volatile("barrier.sync %0, %1;" ::"r"(2 + (g)), "n"(BK_GROUP_THREADS) : "memory")
 #ifndef BK_PROFILE_CTRL
 #define TSUB(i) do { } while (0)
 #else
@@ -114,6 +116,21 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 // ~4 s at 1.9 GHz: a barrier that is not reached means a bug; every CTA bails out
 #define BK_BARRIER_TIMEOUT_CYCLES (8000000000LL)
 
+#ifdef BK_PROFILE_CTRL
+// worker-side latency sums (ns) per CTA: [0] publish->claimed, [1] ->jobs staged, [2] ->units done, [3] ->done added, [4] claims
+__device__ unsigned long long g_wdbg[256][16];
+// cycle stamp that waits for `dep` (a freshly loaded / computed register)
+// (the clock read is predicated on `dep`, so it cannot issue before the value has arrived)
+#define UTICK(dep) ({ long long t_ = 0; asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0x7fffffff; @p mov.u64 %0, %%clock64; }" : "+l"(t_) : "r"((int)(dep)) : "memory"); t_; })
+#define UACC(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_wdbg[blockIdx.x][i], (unsigned long long)(v)); } while (0)
+#define WDBG(i, t0)                                                              \
+  do { if (threadIdx.x == 0) g_wdbg[blockIdx.x][i] += globaltimer_ns() - (t0); } while (0)
+#else
+#define WDBG(i, t0) do { } while (0)
+#define UTICK(dep) 0ll
+#define UACC(i, v) do { } while (0)
+#endif
+
 #define BK_CUM_SMEM 1024
 struct CtlShared {
   double w[BK_MAX_PARTICLES];
@@ -138,25 +155,35 @@ struct CtlShared {
   unsigned pick;
 };
 
-struct DataShared {
-  Job jobs[BK_MAX_PARTICLES];   // this claim's job list (staged from the chain's descriptor)
-  int cmd[64];
-  int njobs[64];
-  int ngroups[64];
-  int ru_base[65];   // prefix of round units
-  int su_base[65];   // prefix of sweep units
-  int group;
-  int all_done;
+// A worker CTA is split into BK_NGROUPS independent groups of BK_GROUP_THREADS threads.  Each group serves its own
+// chain(s) with its own poller, barrier and shared-memory area, so the epochs of different chains run CONCURRENTLY on
+// every SM (one chain's unit is a ~500-instruction dependent stream; several chains interleaved hide that latency).
+struct Work {
+  int chain;       // -1: nothing new
+  int cmd, njobs, total;
+  unsigned lo, hi; // this group's range of (tile, job) pairs / first sweep tile and stride
+  int exit_now;
+};
+
+struct GroupShared {
+  // partial sums of a ROUND / LL epoch, [job][BK_ACC_STRIDE]: warps add here (shared-memory atomics), the group then
+  // issues ONE global atomic per (job, statistic) — the L2 sees groups x jobs x 5 atomics per epoch instead of
+  // tiles x jobs x 5 on a handful of lines
+  unsigned long long acc[BK_MAX_PARTICLES * BK_ACC_STRIDE];
+  Job jobs[BK_MAX_PARTICLES];   // the epoch's job list, one copy per group
   float old_vals[256];
   float new_vals[256];
   float pro_vals[256];
   unsigned long long leaf_acc[256 * 3];
   unsigned long long tot_acc[8];
+  Work work;
+  unsigned seen[64];            // last epoch of each chain this group has executed
+  unsigned char fin[64];
 };
+static_assert(sizeof(GroupShared) * BK_NGROUPS <= 160 * 1024, "worker groups must fit the dynamic shared memory of the launch");
 
-struct __align__(16) KernelShared {   // not a union: the control CTA's row bookkeeping persists across phases
+struct __align__(16) KernelShared {   // static shared memory of a control CTA (workers use the dynamic area)
   CtlShared ctl;
-  DataShared data;
 };
 
 // ------------------------------------------------------------------ dataflow sync helpers
@@ -183,6 +210,12 @@ __device__ __forceinline__ unsigned long long atom_acquire_add_u64(unsigned long
   unsigned long long r;
   asm volatile("atom.acquire.gpu.global.add.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(v) : "memory");
   return r;
+}
+
+__device__ __forceinline__ int4 ld_ca_v4(const int4* p) {   // ordinary (weak, L1-cached) 16-byte load, never the .nc path
+  int4 v;
+  asm volatile("ld.global.ca.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
 }
 
 // ------------------------------------------------------------------ small device utils
@@ -457,6 +490,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       CTRL_SYNC();
       if (threadIdx.x == 0 && s_err) hot->c_err |= s_err;
   }
+  TSUB(5);
   // rows + job list, built in parallel in shared memory:
   //   free rows: ranks of the unused pool rows; growers: rank among the growing slots -> dst row;
   //   count-only jobs are de-duplicated per source row with an exchange on row_cnt_node.
@@ -530,8 +564,8 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
   {  // publish the job list: 48-byte descriptors stored by many threads
     const int nj = s_njobs;
     const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
-    uint4* d4 = reinterpret_cast<uint4*>(ctl->jobs);
-    for (int i = threadIdx.x; i < nj * 3; i += BK_CTRL_THREADS) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < nj * 3 * BK_JOB_COPIES; i += BK_CTRL_THREADS)
+      reinterpret_cast<uint4*>(ctl->jobs[i / (nj * 3)])[i % (nj * 3)] = s4[i % (nj * 3)];
   }
   CTRL_SYNC();
   TSUB(6);
@@ -771,8 +805,8 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       // leaf values are known now: publish the LL jobs (the first n_grow list entries) and wait for their sums
       const int ng = hot->n_grow;
       const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
-      uint4* d4 = reinterpret_cast<uint4*>(ctl->jobs);
-      for (int i = threadIdx.x; i < ng * 3; i += BK_CTRL_THREADS) d4[i] = s4[i];
+      for (int i = threadIdx.x; i < ng * 3 * BK_JOB_COPIES; i += BK_CTRL_THREADS)
+        reinterpret_cast<uint4*>(ctl->jobs[i / (ng * 3)])[i % (ng * 3)] = s4[i % (ng * 3)];
       CTRL_SYNC();
       if (threadIdx.x == 0) { hot->n_jobs = ng; hot->cmd = BK_CMD_LL; hot->stage = BK_ST_WAIT_LL; }
       CTRL_SYNC();
@@ -840,96 +874,135 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
 }
 
 // ------------------------------------------------------------------ data phase: ROUND
-__device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs) {
+// Byte-parallel helpers: leaf ids are one byte, a lane holds 8 of them in two 32-bit words.
+// 0x80 in every byte of w that equals the corresponding byte of pat4
+__device__ __forceinline__ unsigned bytes_eq_msb(unsigned w, unsigned pat4) {
+  const unsigned x = w ^ pat4;
+  const unsigned t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;   // MSB set where the byte differs
+  return ~t & 0x80808080u;
+}
+// 0xFF in every such byte (PRMT replicates the MSB over the byte)
+__device__ __forceinline__ unsigned bytes_eq(unsigned w, unsigned pat4) {
+  unsigned d;   // prmt selector nibble 8+i = byte i with its sign bit replicated (__byte_perm ignores that mode bit)
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(bytes_eq_msb(w, pat4)), "r"(0u), "r"(0xBA98u));
+  return d;
+}
+// exact warp sums through REDUX on 16-bit chunks
+__device__ __forceinline__ long long warp_sum_s48(long long v) {   // |v| < 2^47
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xFFFFu);
+  const int hi = __reduce_add_sync(0xffffffffu, (int)(v >> 16));
+  return (long long)hi * 65536ll + (long long)lo;
+}
+
+__device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
+                                           unsigned long long* __restrict__ sacc) {
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
-  const ChainCtl* ctl = P.ctl + c;
+  const bool gauss = P.lik == BK_LIK_NORMAL;
+  const long long u_t0 = UTICK(lane);
   int q_r[8], q_s[8];
   {
     const int4* a = reinterpret_cast<const int4*>(P.qr + (size_t)c * P.Npad + base);
     const int4* b = reinterpret_cast<const int4*>(P.qst + (size_t)c * P.Npad + base);
-    int4 a0 = __ldcg(a), a1 = __ldcg(a + 1), b0 = __ldcg(b), b1 = __ldcg(b + 1);
+    // L1-cached on purpose: the warps of this CTA share a few tiles (fresh after the epoch's acquire fence)
+    int4 a0 = ld_ca_v4(a), a1 = ld_ca_v4(a + 1), b0 = ld_ca_v4(b), b1 = ld_ca_v4(b + 1);
+    const long long u_i = UTICK(lane);          // the four loads have issued
+    const long long u_q0 = UTICK(a0.x);         // first one has arrived
+    const long long u_q1 = UTICK(a1.w);
+    const long long u_q2 = UTICK(b0.x);
+    const long long u_q3 = UTICK(b1.w);
+    UACC(5, u_i - u_t0); UACC(6, u_q0 - u_i); UACC(7, u_q1 - u_i); UACC(14, u_q2 - u_i); UACC(15, u_q3 - u_i);
     q_r[0] = a0.x; q_r[1] = a0.y; q_r[2] = a0.z; q_r[3] = a0.w; q_r[4] = a1.x; q_r[5] = a1.y; q_r[6] = a1.z; q_r[7] = a1.w;
     q_s[0] = b0.x; q_s[1] = b0.y; q_s[2] = b0.z; q_s[3] = b0.w; q_s[4] = b1.x; q_s[5] = b1.y; q_s[6] = b1.z; q_s[7] = b1.w;
   }
+  // leaf ids of a stump: 0 for real rows, 0xFF (limbo) for the padding rows of the last tile
+  unsigned vw0 = 0u, vw1 = 0u;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (base + e >= (size_t)P.N) vw0 |= 0xFFu << (8 * e);
+    if (base + 4 + e >= (size_t)P.N) vw1 |= 0xFFu << (8 * e);
+  }
   for (int ji = job_lo; ji < job_hi; ++ji) {
-    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // shared-memory copy staged by the CTA
+    // The chain's job list is read with ordinary L1-cached loads: thousands of warps read the same few lines at the
+    // same instant, and through L2 alone that hot spot cost ~4000 cycles per unit.  Fresh data is guaranteed by the
+    // acquire fence thread 0 of this CTA executed for this epoch (gpu-scope fence = L1 invalidate) + the CTA barrier.
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
     const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
-    const int kind = j0.x, slot = j0.y, src_row = j0.z, dst_row = j0.w;
+    const int kind = j0.x, src_row = j0.z, dst_row = j0.w;
     const int node = j1.x, var = j1.y; const float split = __int_as_float(j1.z); const int left_id = j1.w;
     const int next_node = j2.x, rule = j2.y, sparse = j2.z;
-    unsigned long long ids;
-    if (src_row == BK_ROW_VIRTUAL) {
-      ids = 0ull;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) if (base + e >= (size_t)P.N) ids |= 0xFFull << (8 * e);
-    } else {
-      ids = __ldcg(reinterpret_cast<const unsigned long long*>(P.rows + ((size_t)c * P.R + src_row) * P.Npad + base));
+    const long long u_tj = UTICK(j2.x ^ j1.x ^ j0.x);       // job descriptor has arrived
+    const long long u_t1 = UTICK(j2.x ^ q_r[7] ^ q_s[7] ^ q_r[0] ^ q_s[0]);   // q tile and job descriptor have arrived
+    UACC(12, u_t1 - u_tj);
+    unsigned w0 = vw0, w1 = vw1;
+    if (src_row != BK_ROW_VIRTUAL) {
+      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(P.rows + ((size_t)c * P.R + src_row) * P.Npad + base));
+      w0 = v.x; w1 = v.y;
     }
-    unsigned cnt_next = 0;
+    const unsigned next4 = (unsigned)next_node * 0x01010101u;   // next_node < 0 never matches a used id pattern check below
     if (kind == BK_JOB_PARTITION) {
-      unsigned mm = 0;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) mm |= (((unsigned)(ids >> (8 * e)) & 255u) == (unsigned)node) ? (1u << e) : 0u;
-      unsigned lm = 0;
+      const unsigned node4 = (unsigned)node * 0x01010101u;
+      const unsigned mem0 = bytes_eq(w0, node4), mem1 = bytes_eq(w1, node4);
+      unsigned lb0 = 0u, lb1 = 0u;
       // dense nodes: the column load is issued together with the leaf-id load (one L2/HBM round trip
       // per job); sparse nodes (few members) keep it dependent on the ids to save the bytes
-      if (!sparse || mm) {
+      if (!sparse || (mem0 | mem1)) {
         const float4* xp = reinterpret_cast<const float4*>(P.X + (size_t)var * P.Npad + base);
         const float4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
-        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          bool l = rule == BK_RULE_ONEHOT ? (xs[e] == split) : (xs[e] <= split);
-          lm |= l ? (1u << e) : 0u;
+        if (rule == BK_RULE_ONEHOT) {
+          if (x0.x == split) lb0 |= 0x000000FFu; if (x0.y == split) lb0 |= 0x0000FF00u;
+          if (x0.z == split) lb0 |= 0x00FF0000u; if (x0.w == split) lb0 |= 0xFF000000u;
+          if (x1.x == split) lb1 |= 0x000000FFu; if (x1.y == split) lb1 |= 0x0000FF00u;
+          if (x1.z == split) lb1 |= 0x00FF0000u; if (x1.w == split) lb1 |= 0xFF000000u;
+        } else {
+          if (x0.x <= split) lb0 |= 0x000000FFu; if (x0.y <= split) lb0 |= 0x0000FF00u;
+          if (x0.z <= split) lb0 |= 0x00FF0000u; if (x0.w <= split) lb0 |= 0xFF000000u;
+          if (x1.x <= split) lb1 |= 0x000000FFu; if (x1.y <= split) lb1 |= 0x0000FF00u;
+          if (x1.z <= split) lb1 |= 0x00FF0000u; if (x1.w <= split) lb1 |= 0xFF000000u;
         }
-        lm &= mm;
       }
-      unsigned long long nids = 0ull;
-      int cl = 0;
-      long long a_st = 0, a_r = 0;
-      unsigned long long a_r2 = 0;
+      const unsigned lm0 = lb0 & mem0, lm1 = lb1 & mem1;           // 0xFF where the row goes to the left child
+      const long long u_t2 = UTICK(lm0 ^ lm1);                     // leaf ids and the column have arrived
+      const unsigned L4 = (unsigned)left_id * 0x01010101u, R4 = L4 + 0x01010101u;
+      const unsigned n0 = (w0 & ~mem0) | (mem0 & ((lm0 & L4) | (~lm0 & R4)));
+      const unsigned n1 = (w1 & ~mem1) | (mem1 & ((lm1 & L4) | (~lm1 & R4)));
+      __stcg(reinterpret_cast<uint2*>(P.rows + ((size_t)c * P.R + dst_row) * P.Npad + base), make_uint2(n0, n1));
+      if (__any_sync(0xffffffffu, (lm0 | lm1) != 0u)) {
+        // per-lane sums over at most 4 rows fit 32 bits (|q| < 2^29); squares go to 64 bits
+        int s_a = 0, s_b = 0, r_a = 0, r_b = 0;
+        unsigned long long r2 = 0ull;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        unsigned id = (unsigned)(ids >> (8 * e)) & 255u;
-        const bool mem = (mm >> e) & 1u, l = (lm >> e) & 1u;
-        unsigned nid = mem ? (unsigned)(l ? left_id : left_id + 1) : id;
-        nids |= (unsigned long long)nid << (8 * e);
-        cnt_next += (nid == (unsigned)next_node) ? 1u : 0u;
-        const int qm = l ? q_r[e] : 0;
-        cl += l ? 1 : 0;
-        a_st += l ? (long long)q_s[e] : 0ll;
-        a_r += (long long)qm;
-        a_r2 += (unsigned long long)((long long)qm * (long long)qm);
-      }
-      __stcg(reinterpret_cast<unsigned long long*>(P.rows + ((size_t)c * P.R + dst_row) * P.Npad + base), nids);
-      if (__any_sync(0xffffffffu, lm != 0)) {
-        unsigned n_tot = __reduce_add_sync(0xffffffffu, (unsigned)cl);
-        unsigned long long s_st = warp_sum_u64((unsigned long long)a_st);
-        unsigned long long* acc = P.accL + ((size_t)c * P.P + slot) * BK_ACC_STRIDE;
-        if (lane == 0) {
-          red_add_u64(acc + BK_ACC_N, (unsigned long long)n_tot);
-          red_add_u64(acc + BK_ACC_SST, s_st);
+        for (int e = 0; e < 4; ++e) {
+          if (lm0 & (1u << (8 * e))) { s_a += q_s[e]; r_a += q_r[e]; r2 += (unsigned long long)((long long)q_r[e] * (long long)q_r[e]); }
+          if (lm1 & (1u << (8 * e))) { s_b += q_s[4 + e]; r_b += q_r[4 + e]; r2 += (unsigned long long)((long long)q_r[4 + e] * (long long)q_r[4 + e]); }
         }
-        if (P.lik == BK_LIK_NORMAL) {   // Gaussian sufficient statistics of the residual (Bernoulli: q_r holds noi bits)
-          unsigned long long s_r = warp_sum_u64((unsigned long long)a_r);
-          unsigned long long s_lo = warp_sum_u64(a_r2 & 0xFFFFFFFFull);
-          unsigned long long s_hi = warp_sum_u64(a_r2 >> 32);
-          if (lane == 0) {
-            red_add_u64(acc + BK_ACC_SR, s_r);
-            red_add_u64(acc + BK_ACC_SR2LO, s_lo);
-            red_add_u64(acc + BK_ACC_SR2HI, s_hi);
-          }
+        const unsigned cl = (unsigned)(__popc(lm0) + __popc(lm1)) >> 3;
+        const unsigned n_tot = __reduce_add_sync(0xffffffffu, cl);
+        const long long s_st = warp_sum_s48((long long)s_a + (long long)s_b);
+        unsigned long long* acc = sacc + ji * BK_ACC_STRIDE;   // the sums are warp-uniform: one lane per statistic
+        if (lane == 0) atomicAdd(acc + BK_ACC_N, (unsigned long long)n_tot);
+        if (lane == 1) atomicAdd(acc + BK_ACC_SST, (unsigned long long)s_st);
+        if (gauss) {   // Gaussian sufficient statistics of the residual (Bernoulli: q_r holds noi bits)
+          const long long s_r = warp_sum_s48((long long)r_a + (long long)r_b);
+          const unsigned c0 = __reduce_add_sync(0xffffffffu, (unsigned)(r2 & 0xFFFFull));
+          const unsigned c1 = __reduce_add_sync(0xffffffffu, (unsigned)((r2 >> 16) & 0xFFFFull));
+          const unsigned c2 = __reduce_add_sync(0xffffffffu, (unsigned)((r2 >> 32) & 0xFFFFull));
+          const unsigned c3 = __reduce_add_sync(0xffffffffu, (unsigned)(r2 >> 48));
+          if (lane == 2) atomicAdd(acc + BK_ACC_SR, (unsigned long long)s_r);
+          if (lane == 3) atomicAdd(acc + BK_ACC_SR2LO, (unsigned long long)c0 + ((unsigned long long)c1 << 16));   // sum of the low 32-bit halves
+          if (lane == 4) atomicAdd(acc + BK_ACC_SR2HI, (unsigned long long)c2 + ((unsigned long long)c3 << 16));   // sum of the high halves
         }
       }
       if (next_node >= 0) {
-        unsigned tot = __reduce_add_sync(0xffffffffu, cnt_next);
+        const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(n0, next4)) + __popc(bytes_eq_msb(n1, next4)));
+        const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) P.rowcnt[((size_t)c * P.R + dst_row) * P.ntiles + tile] = tot;
       }
+      const long long u_t3 = UTICK(lane + (int)n0);
+      UACC(8, u_t1 - u_t0); UACC(9, u_t2 - u_t1); UACC(10, u_t3 - u_t2); UACC(11, 1);
     } else {  // BK_JOB_COUNT
-#pragma unroll
-      for (int e = 0; e < 8; ++e) cnt_next += (((unsigned)(ids >> (8 * e)) & 255u) == (unsigned)next_node) ? 1u : 0u;
-      unsigned tot = __reduce_add_sync(0xffffffffu, cnt_next);
+      const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(w0, next4)) + __popc(bytes_eq_msb(w1, next4)));
+      const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
       if (lane == 0) P.rowcnt[((size_t)c * P.R + src_row) * P.ntiles + tile] = tot;
     }
   }
@@ -939,7 +1012,8 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
 // Same unit shape as ROUND: one warp, 256 rows, a group of jobs.  noi (float bits kept in the qr array) and
 // y stay in registers; per job the particle's new leaf-id row is read and the rows of the two new leaves
 // contribute their quantised log-likelihood term at the leaf's value (+9N bytes per grow event).
-__device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs) {
+__device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
+                                        unsigned long long* __restrict__ sacc) {
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
   float noi[8], yv[8];
@@ -953,9 +1027,9 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
     yv[0] = b0.x; yv[1] = b0.y; yv[2] = b0.z; yv[3] = b0.w; yv[4] = b1.x; yv[5] = b1.y; yv[6] = b1.z; yv[7] = b1.w;
   }
   for (int ji = job_lo; ji < job_hi; ++ji) {
-    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // L1-cached, see round_unit
     const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
-    const int slot = j0.y, src_row = j0.z;
+    const int src_row = j0.z;
     const float vl = __int_as_float(j1.z), vr = __int_as_float(j2.y);
     const unsigned left_id = (unsigned)j1.w;
     const unsigned long long ids = __ldcg(reinterpret_cast<const unsigned long long*>(P.rows + ((size_t)c * P.R + src_row) * P.Npad + base));
@@ -970,24 +1044,24 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
     if (__any_sync(0xffffffffu, any)) {
       const unsigned long long t_l = warp_sum_u64((unsigned long long)s_l), t_r = warp_sum_u64((unsigned long long)s_r);
       if (lane == 0) {
-        unsigned long long* acc = P.accL + ((size_t)c * P.P + slot) * BK_ACC_STRIDE;
-        if (t_l) red_add_u64(acc + BK_ACC_LLL, t_l);
-        if (t_r) red_add_u64(acc + BK_ACC_LLR, t_r);
+        unsigned long long* acc = sacc + ji * BK_ACC_STRIDE;
+        if (t_l) atomicAdd(acc + BK_ACC_LLL, t_l);
+        if (t_r) atomicAdd(acc + BK_ACC_LLR, t_r);
       }
     }
   }
 }
 
 // ------------------------------------------------------------------ data phase: SWEEP
-// CTA-wide: 1024 threads x 4 rows.  Fuses commit of tree A with prologue of tree B.
-__device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
+// Group-wide: BK_GROUP_THREADS threads x 4 rows.  Fuses commit of tree A with prologue of tree B.
+__device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, const int g, const int tid) {
   const ChainCtl* ctl = P.ctl + c;
   const int4 s0 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep));
   const int4 s1 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep) + 1);
   const int do_commit = s0.x, commit_tree = s0.y, new_row = s0.z, do_wf = s0.w;
   const int do_pro = s1.x, pro_tree = s1.y, wf_count = s1.z;
   // stage leaf-value tables
-  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+  for (int k = tid; k < 256; k += BK_GROUP_THREADS) {
     sh.old_vals[k] = do_commit ? __ldcg(&ctl->old_vals[k]) : 0.0f;
     sh.new_vals[k] = do_commit ? __ldcg(&ctl->new_vals[k]) : 0.0f;
     float pv = 0.0f;
@@ -998,11 +1072,11 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
     }
     sh.pro_vals[k] = pv;
   }
-  for (int k = threadIdx.x; k < 256 * 3; k += blockDim.x) sh.leaf_acc[k] = 0ull;
-  if (threadIdx.x < 8) sh.tot_acc[threadIdx.x] = 0ull;
-  BLOCK_SYNC();
+  for (int k = tid; k < 256 * 3; k += BK_GROUP_THREADS) sh.leaf_acc[k] = 0ull;
+  if (tid < 8) sh.tot_acc[tid] = 0ull;
+  GROUP_SYNC(g);
 
-  const size_t base = (size_t)ctile * BK_COMMIT_TILE + (size_t)threadIdx.x * 4;
+  const size_t base = (size_t)ctile * BK_COMMIT_TILE + (size_t)tid * 4;
   long long t_sst = 0, t_sr = 0, t_sd = 0;
   unsigned long long t_r2 = 0;
   unsigned pro_pid4 = 0xFFFFFFFFu;
@@ -1101,7 +1175,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
       const unsigned c1 = __reduce_add_sync(grp, (unsigned)((sq >> 16) & 0xFFFFull));
       const unsigned c2 = __reduce_add_sync(grp, (unsigned)((sq >> 32) & 0xFFFFull));
       const unsigned c3 = __reduce_add_sync(grp, (unsigned)(sq >> 48));
-      if (ok && (int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+      if (ok && (int)(tid & 31) == __ffs(grp) - 1) {
         const long long sr = (long long)r_hi * 65536ll + (long long)r_lo;
         atomicAdd(&sh.leaf_acc[pid * 3 + 0], (unsigned long long)sr);
         atomicAdd(&sh.leaf_acc[pid * 3 + 1], (unsigned long long)c0 + ((unsigned long long)c1 << 16));
@@ -1116,98 +1190,131 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, DataShared& sh) {
     unsigned long long v2 = warp_sum_u64(t_r2 >> 32);
     unsigned long long v3 = warp_sum_u64((unsigned long long)t_sst);
     unsigned long long v4 = warp_sum_u64((unsigned long long)t_sd);
-    if ((threadIdx.x & 31) == 0) {
+    if ((tid & 31) == 0) {
       atomicAdd(&sh.tot_acc[0], v0); atomicAdd(&sh.tot_acc[1], v1); atomicAdd(&sh.tot_acc[2], v2);
       atomicAdd(&sh.tot_acc[3], v3); atomicAdd(&sh.tot_acc[4], v4);
     }
   }
-  BLOCK_SYNC();
+  GROUP_SYNC(g);
   unsigned long long* a0 = P.acc0 + (size_t)c * BK_ACC0_WORDS;
   if (do_pro) {
-    for (int k = threadIdx.x; k < 255 * 3; k += blockDim.x) {
+    for (int k = tid; k < 255 * 3; k += BK_GROUP_THREADS) {
       unsigned long long v = sh.leaf_acc[k];
       if (v) red_add_u64(a0 + (size_t)(k / 3) * BK_ACC0_STRIDE + (k % 3), v);
     }
-    if (threadIdx.x < 4) { unsigned long long v = sh.tot_acc[threadIdx.x]; if (v) red_add_u64(a0 + (size_t)255 * BK_ACC0_STRIDE + threadIdx.x, v); }
+    if (tid < 4) { unsigned long long v = sh.tot_acc[tid]; if (v) red_add_u64(a0 + (size_t)255 * BK_ACC0_STRIDE + tid, v); }
   }
-  if (do_commit && do_wf && threadIdx.x == 0) { unsigned long long v = sh.tot_acc[4]; if (v) red_add_u64(a0 + (size_t)256 * BK_ACC0_STRIDE, v); }
-  BLOCK_SYNC();
+  if (do_commit && do_wf && tid == 0) { unsigned long long v = sh.tot_acc[4]; if (v) red_add_u64(a0 + (size_t)256 * BK_ACC0_STRIDE, v); }
+  GROUP_SYNC(g);
 }
 
 // ------------------------------------------------------------------ dataflow scheduling
-// units claimed by a worker CTA (broadcast through shared memory)
-struct Claim {
-  int chain;       // -1: nothing claimed
-  int cmd, njobs, group;
-  int first, count;  // units [first, first+count)
-  int exit_now;
-};
+// Which groups serve chain c: with C >= BK_NGROUPS chains, group g serves the chains c = g (mod BK_NGROUPS); with
+// fewer chains, group g serves chain g mod C, so chain c has servers_of(c) groups per worker CTA.
+__device__ __forceinline__ int servers_of(int C, int c) { return C >= BK_NGROUPS ? 1 : (BK_NGROUPS - c + C - 1) / C; }
 
-// ---- worker: claim units of any chain with published work, run them, report completion
-__device__ void worker_loop(const Params& P, DataShared& sh) {
-  __shared__ Claim s_claim;
-  __shared__ unsigned char s_fin[64];
-  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  if ((int)threadIdx.x < 64) s_fin[threadIdx.x] = 0;
-  BLOCK_SYNC();
-  int start = blockIdx.x % P.C, n_finished = 0;
+// An epoch of a chain is split STATICALLY: the (tile, job) pairs of a ROUND / LL epoch are flattened tile-major,
+// worker CTA w of W takes the contiguous range [w*T/W, (w+1)*T/W) (a few whole tiles: its warps re-read the same
+// residual tiles through L1), the chain's groups in that CTA split the range, and each warp takes a contiguous
+// chunk.  No claim atomics.  Every serving group reports each epoch exactly once (release add), so the control CTA
+// waits for `workers x servers_of(chain)` per epoch.
+__device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
+  const int tid = threadIdx.x & (BK_GROUP_THREADS - 1), warp = tid >> 5;
+  const int W = gridDim.x - P.C, w = blockIdx.x - P.C;
+  const int c_first = P.C >= BK_NGROUPS ? g : g % P.C, c_step = P.C >= BK_NGROUPS ? BK_NGROUPS : P.C;
+  const int my_rank = P.C >= BK_NGROUPS ? 0 : g / P.C;      // index of this group among the servers of its chain
+  int n_mine = 0;
+  for (int c = c_first; c < P.C; c += c_step) n_mine++;
+  if (P.C < BK_NGROUPS) n_mine = 1;
+  if (tid < 64) { sh.fin[tid] = 0; sh.seen[tid] = 0u; }
+  for (int i = tid; i < BK_MAX_PARTICLES * BK_ACC_STRIDE; i += BK_GROUP_THREADS) sh.acc[i] = 0ull;
+  GROUP_SYNC(g);
+  int next = 0, n_finished = 0;
   long long t_idle0 = clock64();
+  unsigned long long t_pub = 0; (void)t_pub;
   for (;;) {
-    if (threadIdx.x == 0) {
-      Claim cl; cl.chain = -1; cl.exit_now = 0; cl.cmd = 0; cl.first = 0; cl.count = 0; cl.njobs = 0; cl.group = 1;
-      for (int k = 0; k < P.C && cl.chain < 0; ++k) {
-        const int c = (start + k) % P.C;
-        if (s_fin[c]) continue;
+    if (tid == 0) {   // the group's poller: spins until one of its chains has a new epoch (the other warps wait at the barrier)
+      Work wk; wk.chain = -1; wk.exit_now = 0; wk.cmd = 0; wk.njobs = 0; wk.total = 0; wk.lo = 0u; wk.hi = 0u;
+      unsigned spins = 0;
+      while (wk.chain < 0 && !wk.exit_now) {
+      for (int k = 0; k < n_mine && wk.chain < 0; ++k) {
+        const int idx = (next + k) % n_mine;
+        const int c = P.C >= BK_NGROUPS ? c_first + idx * c_step : c_first;
+        if (sh.fin[c]) continue;
         ChainSync* sy = P.sync + c;
-        uint4 d = ld_volatile_v4(&sy->desc);                       // same 128-byte line as the ticket
-        const unsigned long long t = ld_relaxed_u64(&sy->ticket);
-        if (d.x == 0) continue;                                    // nothing published yet
-        if ((d.y & 0xFFu) == BK_CMD_DONE) { s_fin[c] = 1; n_finished++; continue; }
-        if ((unsigned)(t >> 32) != d.x || (unsigned)t >= d.w) continue;   // in transition, or exhausted
-        const int want = (d.y & 0xFFu) == BK_CMD_SWEEP ? 1 : nwarps;
-        const unsigned long long t2 = atom_acquire_add_u64(&sy->ticket, (unsigned long long)want);
-        const unsigned ep2 = (unsigned)(t2 >> 32), u2 = (unsigned)t2;
-        if (ep2 != d.x) {            // a newer epoch was published in between: its descriptor is visible now
-          d = ld_volatile_v4(&sy->desc);
-          if (d.x != ep2 || (d.y & 0xFFu) == BK_CMD_DONE) continue;
+        const unsigned ep = ld_relaxed_u32(reinterpret_cast<const unsigned*>(&sy->ticket));   // epoch word, released after desc
+        if (ep == sh.seen[c]) continue;
+        fence_acq_rel_gpu();   // acquire (pairs with the control CTA's release store); also drops this SM's stale L1 lines
+        const uint4 d = ld_volatile_v4(&sy->desc);
+        if (d.x != ep) continue;                                    // a newer epoch is being published: next poll
+        sh.seen[c] = ep;
+        if ((d.y & 0xFFu) == BK_CMD_DONE) { sh.fin[c] = 1; n_finished++; continue; }
+        wk.chain = c; wk.cmd = (int)(d.y & 0xFFu); wk.njobs = (int)d.z; wk.total = (int)d.w;
+        const unsigned ns = (unsigned)servers_of(P.C, c);
+        if (wk.cmd == BK_CMD_SWEEP) {
+          wk.lo = (unsigned)w * ns + (unsigned)my_rank;             // first row tile of this group; stride W * ns
+          wk.hi = (unsigned)W * ns;
+        } else {
+          const unsigned clo = (unsigned)((unsigned long long)w * d.w / (unsigned)W);          // the CTA's pairs ...
+          const unsigned chi = (unsigned)((unsigned long long)(w + 1) * d.w / (unsigned)W);
+          wk.lo = clo + (unsigned)((unsigned long long)(chi - clo) * (unsigned)my_rank / ns);        // ... split over its groups
+          wk.hi = clo + (unsigned)((unsigned long long)(chi - clo) * (unsigned)(my_rank + 1) / ns);
         }
-        if (u2 >= d.w) continue;     // lost the race for the last units
-        cl.chain = c; cl.cmd = (int)(d.y & 0xFFu); cl.group = (int)(d.y >> 8); cl.njobs = (int)d.z;
-        cl.first = (int)u2; cl.count = u2 + (unsigned)want <= d.w ? want : (int)(d.w - u2);
+        next = (idx + 1) % n_mine;
+#ifdef BK_PROFILE_CTRL
+        t_pub = *reinterpret_cast<volatile unsigned long long*>(&sy->pad[1]);
+        if (wk.cmd == BK_CMD_ROUND && g == 0) { g_wdbg[blockIdx.x][0] += globaltimer_ns() - t_pub; g_wdbg[blockIdx.x][4] += 1; }
+#endif
       }
-      if (cl.chain < 0) {
-        if (n_finished == P.C) cl.exit_now = 1;
-        else if (ld_volatile_i32(P.abort_flag)) cl.exit_now = 1;
-        else if (clock64() - t_idle0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); cl.exit_now = 1; }
-      } else {
-        start = (cl.chain + 1) % P.C;
+      if (wk.chain < 0) {
+        if (n_finished == n_mine) wk.exit_now = 1;
+        else if ((++spins & 15u) == 0) {
+          if (ld_volatile_i32(P.abort_flag)) wk.exit_now = 1;
+          else if (clock64() - t_idle0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); wk.exit_now = 1; }
+        }
       }
-      s_claim = cl;
+      }
+      sh.work = wk;
     }
-    BLOCK_SYNC();
-    const Claim cl = s_claim;
-    if (cl.exit_now) return;
-    if (cl.chain < 0) continue;
-    if (cl.cmd == BK_CMD_ROUND || cl.cmd == BK_CMD_LL) {
+    GROUP_SYNC(g);
+    const Work wk = sh.work;
+    if (wk.exit_now) return;
+    if (wk.cmd == BK_CMD_ROUND || wk.cmd == BK_CMD_LL) {
       {
-        const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[cl.chain].jobs);
+        const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[wk.chain].jobs[(w * BK_NGROUPS + g) % BK_JOB_COPIES]);   // readers spread over the copies
         uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
-        for (int i = threadIdx.x; i < cl.njobs * 3; i += blockDim.x) d4[i] = __ldcg(g4 + i);
+        for (int i = tid; i < wk.njobs * 3; i += BK_GROUP_THREADS) d4[i] = __ldcg(g4 + i);
       }
-      BLOCK_SYNC();
-      if (warp < cl.count) {
-        const int u = cl.first + warp;
-        const int tile = u % P.ntiles, g = u / P.ntiles;
-        const int lo = g * cl.group;
-        const int hi = lo + cl.group < cl.njobs ? lo + cl.group : cl.njobs;
-        if (cl.cmd == BK_CMD_ROUND) round_unit(P, cl.chain, tile, lo, hi, sh.jobs);
-        else ll_unit(P, cl.chain, tile, lo, hi, sh.jobs);
+      GROUP_SYNC(g);
+      const Job* jobs = sh.jobs;
+      const unsigned nwarp = BK_GROUP_THREADS >> 5;
+      const unsigned chunk = (wk.hi - wk.lo + nwarp - 1u) / nwarp;   // pairs per warp
+      unsigned lo = wk.lo + (unsigned)warp * chunk;
+      const unsigned hi = lo + chunk < wk.hi ? lo + chunk : wk.hi;
+      while (lo < hi) {     // one call per tile segment of this warp's range
+        const unsigned tile = lo / (unsigned)wk.njobs, j0 = lo - tile * (unsigned)wk.njobs;
+        const unsigned seg = (unsigned)wk.njobs - j0 < hi - lo ? (unsigned)wk.njobs - j0 : hi - lo;
+        if (wk.cmd == BK_CMD_ROUND) round_unit(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
+        else ll_unit(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
+        lo += seg;
       }
-    } else {  // BK_CMD_SWEEP (the claim may hold several CTA-granular units)
-      for (int u = cl.first; u < cl.first + cl.count; ++u) sweep_unit(P, cl.chain, u, sh);
+      GROUP_SYNC(g);
+      // flush the group's partial sums: one global atomic per non-zero (job, statistic); leaves sh.acc zeroed
+      for (int i = tid; i < wk.njobs * BK_ACC_STRIDE; i += BK_GROUP_THREADS) {
+        const unsigned long long v = sh.acc[i];
+        if (v) {
+          sh.acc[i] = 0ull;
+          const int slot = jobs[i / BK_ACC_STRIDE].slot;
+          red_add_u64(P.accL + ((size_t)wk.chain * P.P + slot) * BK_ACC_STRIDE + (i % BK_ACC_STRIDE), v);
+        }
+      }
+    } else {  // BK_CMD_SWEEP: group-wide row tiles, round robin over all serving groups
+      for (unsigned u = wk.lo; u < (unsigned)wk.total; u += wk.hi) sweep_unit(P, wk.chain, (int)u, sh, g, tid);
     }
-    BLOCK_SYNC();   // every warp's stores are ordered before the release below
-    if (threadIdx.x == 0) { red_release_add_u32(&P.sync[cl.chain].done, (unsigned)cl.count); t_idle0 = clock64(); }
+    GROUP_SYNC(g);   // every warp's stores are ordered before the release below
+    if (wk.cmd == BK_CMD_ROUND && g == 0) WDBG(2, t_pub);
+    if (tid == 0) { red_release_add_u32(&P.sync[wk.chain].done, 1u); t_idle0 = clock64(); }
+    if (wk.cmd == BK_CMD_ROUND && g == 0) WDBG(3, t_pub);
   }
 }
 
@@ -1221,7 +1328,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
   if (threadIdx.x == 0) s_hot = ctl->hot;   // persistent scalars -> shared memory for the whole step
   CTRL_SYNC();
   unsigned issued = 0, epoch = 0;
-  const int worker_warps = (gridDim.x - P.C) * (BK_CTA_THREADS >> 5);
+  const int n_workers = (gridDim.x - P.C) * servers_of(P.C, c);   // serving groups: each reports every epoch once
   const int sweep_tiles = (P.Npad + BK_COMMIT_TILE - 1) / BK_COMMIT_TILE;
   unsigned long long t_wait = 0, t_ctrl = 0, t_pub = 0, t_begin = 0;
   if (threadIdx.x == 0) t_begin = globaltimer_ns();
@@ -1254,24 +1361,19 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       if (cmd == BK_CMD_DONE) {
         fin = 1;
         epoch += 1;
-        fence_acq_rel_gpu();
         st_volatile_v4(&sy->desc, make_uint4(epoch, (unsigned)BK_CMD_DONE, 0u, 0u));   // tells the workers this chain is finished
-        st_release_u64(&sy->ticket, (unsigned long long)epoch << 32);
+        st_release_u32(reinterpret_cast<unsigned*>(&sy->ticket), epoch);
       } else {
-        int total = 0, G = 1;
         const int nj = hot->n_jobs;
-        if (cmd == BK_CMD_ROUND || cmd == BK_CMD_LL) {
-          long long pt = (long long)nj * P.ntiles;
-          long long g = pt / (worker_warps > 0 ? worker_warps : 1);   // about one unit per worker warp
-          G = g < 1 ? 1 : (g > BK_MAX_GROUP ? BK_MAX_GROUP : (int)g);
-          total = ((nj + G - 1) / G) * P.ntiles;
-        } else {
-          total = sweep_tiles;
-        }
-        issued += (unsigned)total; epoch += 1;
-        fence_acq_rel_gpu();   // jobs, accumulators, rows bookkeeping written by this CTA happen-before the descriptor
-        st_volatile_v4(&sy->desc, make_uint4(epoch, (unsigned)cmd | ((unsigned)G << 8), (unsigned)nj, (unsigned)total));
-        st_release_u64(&sy->ticket, (unsigned long long)epoch << 32);
+        const int total = (cmd == BK_CMD_ROUND || cmd == BK_CMD_LL) ? nj * P.ntiles : sweep_tiles;
+        issued += (unsigned)n_workers; epoch += 1;
+#ifdef BK_PROFILE_CTRL
+        *reinterpret_cast<volatile unsigned long long*>(&sy->pad[1]) = globaltimer_ns();
+#endif
+        // jobs, accumulators, rows bookkeeping written by this CTA happen-before the epoch word (release, cumulative
+        // over the CTA barrier above); the descriptor is complete before the epoch word changes
+        st_volatile_v4(&sy->desc, make_uint4(epoch, (unsigned)cmd, (unsigned)nj, (unsigned)total));
+        st_release_u32(reinterpret_cast<unsigned*>(&sy->ticket), epoch);
       }
       s_flag = fin;
       const unsigned long long q3 = globaltimer_ns();
@@ -1294,12 +1396,13 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
 // ------------------------------------------------------------------ the step kernel
 __global__ void __launch_bounds__(BK_CTA_THREADS, 1)
 pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sigma_in, const int max_phases) {
-  __shared__ KernelShared sh;
   if ((int)blockIdx.x < P.C) {
+    __shared__ KernelShared sh;
     if (threadIdx.x < BK_CTRL_THREADS) control_loop(P, blockIdx.x, tune, sigma_in, max_phases, sh.ctl);
     return;
   }
-  worker_loop(P, sh.data);
+  const int g = threadIdx.x / BK_GROUP_THREADS;
+  worker_loop(P, reinterpret_cast<GroupShared*>(bk_dyn_smem)[g], g);
 }
 
 // ------------------------------------------------------------------ init kernel
@@ -1542,6 +1645,7 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
     if (F < 3) { set_err("too many particles for the shared-memory particle store"); return BK_ERR_ARG; }
     P.fastF = F; P.fast_stride = (int)sizeof(PHdr) + F * (int)sizeof(DNode);
     h->dyn_smem = (size_t)2 * P.P * P.fast_stride;
+    if (h->dyn_smem < sizeof(GroupShared) * BK_NGROUPS) h->dyn_smem = sizeof(GroupShared) * BK_NGROUPS;   // worker CTAs carve their groups out of it
     CK(cudaFuncSetAttribute(pgbart_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
   }
   h->grid = n_sm;  // one persistent CTA per SM (148 on B200): chains control CTAs + workers
@@ -1632,6 +1736,18 @@ int bk_debug_timers(bk_handle* h, int chain, unsigned long long* out8) {
   if (!h || chain < 0 || chain >= h->P.C) return BK_ERR_ARG;
   ChainCtl* c = h->P.ctl + chain;
   return cudaMemcpy(out8, (char*)c + offsetof(ChainCtl, hot) + offsetof(ChainHot, t_sub), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? BK_OK : BK_ERR_CUDA;
+}
+
+/* debug only: worker-side latency sums of the last steps, [grid][8] u64 (zeroed after reading); needs -DBK_PROFILE_CTRL */
+int bk_debug_worker_timers(bk_handle* h, unsigned long long* out, int n_cta) {
+#ifdef BK_PROFILE_CTRL
+  if (!h || n_cta > 256) return BK_ERR_ARG;
+  if (cudaMemcpyFromSymbol(out, g_wdbg, (size_t)n_cta * 16 * sizeof(unsigned long long)) != cudaSuccess) return BK_ERR_CUDA;
+  static unsigned long long zeros[256 * 16];
+  return cudaMemcpyToSymbol(g_wdbg, zeros, sizeof(zeros)) == cudaSuccess ? BK_OK : BK_ERR_CUDA;
+#else
+  (void)h; (void)out; (void)n_cta; return BK_ERR_UNSUPPORTED;
+#endif
 }
 
 /* debug only (not part of the public header): host view of the per-warp progress markers */

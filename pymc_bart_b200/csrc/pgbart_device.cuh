@@ -17,7 +17,9 @@
 #ifndef BK_CTA_THREADS
 #define BK_CTA_THREADS 1024
 #endif
-#define BK_COMMIT_TILE (BK_CTA_THREADS * 4)  // rows per CTA pass in the commit/prologue sweep
+#define BK_NGROUPS 4                         // independent worker groups per worker CTA
+#define BK_GROUP_THREADS (BK_CTA_THREADS / BK_NGROUPS)
+#define BK_COMMIT_TILE (BK_GROUP_THREADS * 4)  // rows per group pass in the commit/prologue sweep
 #define BK_MAX_GROUP 16            // particles that share one register-resident (q_r, q_st) tile
 
 // leaf-id row references
@@ -38,6 +40,9 @@
 #define BK_ST_DONE 3
 #define BK_ST_WAIT_LL 4
 
+#ifndef BK_JOB_COPIES
+#define BK_JOB_COPIES 8
+#endif
 #define BK_JOB_PARTITION 1
 #define BK_JOB_COUNT 2
 #define BK_JOB_LL 3   // src_row = the particle's new row, left_id, split = left leaf value, rule = bits of the right leaf value
@@ -125,7 +130,7 @@ struct __align__(16) ChainCtl {
   SweepJob sweep;       // descriptor of the next SWEEP epoch (read by the workers)
   float old_vals[256];  // leaf values of the tree being replaced
   float new_vals[256];  // leaf values of the winning particle
-  Job jobs[BK_MAX_PARTICLES];
+  Job jobs[BK_JOB_COPIES][BK_MAX_PARTICLES];   // identical copies: ~150 worker CTAs read the list at the same instant
 };
 
 // accumulator slots per particle (u64 each)
