@@ -166,10 +166,10 @@ struct Work {
 };
 
 struct GroupShared {
-  // partial sums of a ROUND / LL epoch, [job][BK_ACC_STRIDE]: warps add here (shared-memory atomics), the group then
-  // issues ONE global atomic per (job, statistic) — the L2 sees groups x jobs x 5 atomics per epoch instead of
-  // tiles x jobs x 5 on a handful of lines
-  unsigned long long acc[BK_MAX_PARTICLES * BK_ACC_STRIDE];
+  // partial sums of a ROUND / LL epoch: warps add here (shared-memory atomics), the group then issues ONE global
+  // atomic per (job, statistic) — the L2 sees groups x jobs x 5 atomics per epoch instead of tiles x jobs x 5 on a
+  // handful of lines
+  unsigned acc[BK_MAX_PARTICLES * 16];   // [job][BK_LIMBS] 32-bit limbs, see round_unit
   Job jobs[BK_MAX_PARTICLES];   // the epoch's job list, one copy per group
   float old_vals[256];
   float new_vals[256];
@@ -887,15 +887,43 @@ __device__ __forceinline__ unsigned bytes_eq(unsigned w, unsigned pat4) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(bytes_eq_msb(w, pat4)), "r"(0u), "r"(0xBA98u));
   return d;
 }
-// exact warp sums through REDUX on 16-bit chunks
-__device__ __forceinline__ long long warp_sum_s48(long long v) {   // |v| < 2^47
-  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xFFFFu);
-  const int hi = __reduce_add_sync(0xffffffffu, (int)(v >> 16));
-  return (long long)hi * 65536ll + (long long)lo;
+// Shared-memory accumulator of one job: 32-bit limbs so that a warp adds ALL its statistics with one native
+// shared-memory atomic instruction (lane k adds limb k; 64-bit shared atomics would be CAS loops).  The limbs are the
+// REDUX partial sums themselves: a signed 48-bit sum v is (hi, lo) = (sum of v >> 16, sum of v & 0xFFFF), the
+// 64-bit sum of squares is four 16-bit chunks.  A limb absorbs < 2^11 warp contributions per epoch without overflow
+// (bk_create caps n_rows accordingly); the flush recombines them exactly.
+#define BK_LIMB_N 0
+#define BK_LIMB_ST_LO 1
+#define BK_LIMB_ST_HI 2
+#define BK_LIMB_SR_LO 3
+#define BK_LIMB_SR_HI 4
+#define BK_LIMB_C0 5
+#define BK_LIMB_C1 6
+#define BK_LIMB_C2 7
+#define BK_LIMB_C3 8
+#define BK_LIMB_LLL_LO 9
+#define BK_LIMB_LLL_HI 10
+#define BK_LIMB_LLR_LO 11
+#define BK_LIMB_LLR_HI 12
+#define BK_LIMBS 16   // per job (64 bytes)
+// statistic k (BK_ACC_* index) of a job from its limbs
+__device__ __forceinline__ unsigned long long limbs_to_stat(const unsigned* L, int k) {
+  switch (k) {
+    case BK_ACC_N: return (unsigned long long)L[BK_LIMB_N];
+    case BK_ACC_SST: return (unsigned long long)((long long)(int)L[BK_LIMB_ST_HI] * 65536ll + (long long)L[BK_LIMB_ST_LO]);
+    case BK_ACC_SR: return (unsigned long long)((long long)(int)L[BK_LIMB_SR_HI] * 65536ll + (long long)L[BK_LIMB_SR_LO]);
+    case BK_ACC_SR2LO: return (unsigned long long)L[BK_LIMB_C0] + ((unsigned long long)L[BK_LIMB_C1] << 16);
+    case BK_ACC_SR2HI: return (unsigned long long)L[BK_LIMB_C2] + ((unsigned long long)L[BK_LIMB_C3] << 16);
+    case BK_ACC_LLL: return (unsigned long long)((long long)(int)L[BK_LIMB_LLL_HI] * 65536ll + (long long)L[BK_LIMB_LLL_LO]);
+    case BK_ACC_LLR: return (unsigned long long)((long long)(int)L[BK_LIMB_LLR_HI] * 65536ll + (long long)L[BK_LIMB_LLR_LO]);
+    default: return 0ull;
+  }
 }
+// byte e (0..3) of a 0x00/0xFF byte mask widened to a 32-bit mask
+#define BK_ROWMASK(m, e) __byte_perm((m), 0u, 0x1111u * (e))
 
 __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
-                                           unsigned long long* __restrict__ sacc) {
+                                           unsigned* __restrict__ sacc) {
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
   const bool gauss = P.lik == BK_LIK_NORMAL;
@@ -906,40 +934,35 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     const int4* b = reinterpret_cast<const int4*>(P.qst + (size_t)c * P.Npad + base);
     // L1-cached on purpose: the warps of this CTA share a few tiles (fresh after the epoch's acquire fence)
     int4 a0 = ld_ca_v4(a), a1 = ld_ca_v4(a + 1), b0 = ld_ca_v4(b), b1 = ld_ca_v4(b + 1);
-    const long long u_i = UTICK(lane);          // the four loads have issued
-    const long long u_q0 = UTICK(a0.x);         // first one has arrived
-    const long long u_q1 = UTICK(a1.w);
-    const long long u_q2 = UTICK(b0.x);
-    const long long u_q3 = UTICK(b1.w);
-    UACC(5, u_i - u_t0); UACC(6, u_q0 - u_i); UACC(7, u_q1 - u_i); UACC(14, u_q2 - u_i); UACC(15, u_q3 - u_i);
     q_r[0] = a0.x; q_r[1] = a0.y; q_r[2] = a0.z; q_r[3] = a0.w; q_r[4] = a1.x; q_r[5] = a1.y; q_r[6] = a1.z; q_r[7] = a1.w;
     q_s[0] = b0.x; q_s[1] = b0.y; q_s[2] = b0.z; q_s[3] = b0.w; q_s[4] = b1.x; q_s[5] = b1.y; q_s[6] = b1.z; q_s[7] = b1.w;
   }
+  // per-unit address bases (the per-job part is one multiply-add)
+  const uint8_t* rows_c = P.rows + (size_t)c * P.R * P.Npad + base;
+  const float* x_b = P.X + base;
+  unsigned* cnt_c = P.rowcnt + (size_t)c * P.R * P.ntiles + tile;
   // leaf ids of a stump: 0 for real rows, 0xFF (limbo) for the padding rows of the last tile
   unsigned vw0 = 0u, vw1 = 0u;
+  if (base + 8 > (size_t)P.N) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (base + e >= (size_t)P.N) vw0 |= 0xFFu << (8 * e);
-    if (base + 4 + e >= (size_t)P.N) vw1 |= 0xFFu << (8 * e);
+    for (int e = 0; e < 4; ++e) {
+      if (base + e >= (size_t)P.N) vw0 |= 0xFFu << (8 * e);
+      if (base + 4 + e >= (size_t)P.N) vw1 |= 0xFFu << (8 * e);
+    }
   }
   for (int ji = job_lo; ji < job_hi; ++ji) {
-    // The chain's job list is read with ordinary L1-cached loads: thousands of warps read the same few lines at the
-    // same instant, and through L2 alone that hot spot cost ~4000 cycles per unit.  Fresh data is guaranteed by the
-    // acquire fence thread 0 of this CTA executed for this epoch (gpu-scope fence = L1 invalidate) + the CTA barrier.
-    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // the group's shared-memory copy of the job list
     const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
     const int kind = j0.x, src_row = j0.z, dst_row = j0.w;
     const int node = j1.x, var = j1.y; const float split = __int_as_float(j1.z); const int left_id = j1.w;
     const int next_node = j2.x, rule = j2.y, sparse = j2.z;
-    const long long u_tj = UTICK(j2.x ^ j1.x ^ j0.x);       // job descriptor has arrived
     const long long u_t1 = UTICK(j2.x ^ q_r[7] ^ q_s[7] ^ q_r[0] ^ q_s[0]);   // q tile and job descriptor have arrived
-    UACC(12, u_t1 - u_tj);
     unsigned w0 = vw0, w1 = vw1;
     if (src_row != BK_ROW_VIRTUAL) {
-      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(P.rows + ((size_t)c * P.R + src_row) * P.Npad + base));
+      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(rows_c + (size_t)src_row * P.Npad));
       w0 = v.x; w1 = v.y;
     }
-    const unsigned next4 = (unsigned)next_node * 0x01010101u;   // next_node < 0 never matches a used id pattern check below
+    const unsigned next4 = (unsigned)next_node * 0x01010101u;
     if (kind == BK_JOB_PARTITION) {
       const unsigned node4 = (unsigned)node * 0x01010101u;
       const unsigned mem0 = bytes_eq(w0, node4), mem1 = bytes_eq(w1, node4);
@@ -947,7 +970,7 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       // dense nodes: the column load is issued together with the leaf-id load (one L2/HBM round trip
       // per job); sparse nodes (few members) keep it dependent on the ids to save the bytes
       if (!sparse || (mem0 | mem1)) {
-        const float4* xp = reinterpret_cast<const float4*>(P.X + (size_t)var * P.Npad + base);
+        const float4* xp = reinterpret_cast<const float4*>(x_b + (size_t)var * P.Npad);
         const float4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
         if (rule == BK_RULE_ONEHOT) {
           if (x0.x == split) lb0 |= 0x000000FFu; if (x0.y == split) lb0 |= 0x0000FF00u;
@@ -966,44 +989,59 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       const unsigned L4 = (unsigned)left_id * 0x01010101u, R4 = L4 + 0x01010101u;
       const unsigned n0 = (w0 & ~mem0) | (mem0 & ((lm0 & L4) | (~lm0 & R4)));
       const unsigned n1 = (w1 & ~mem1) | (mem1 & ((lm1 & L4) | (~lm1 & R4)));
-      __stcg(reinterpret_cast<uint2*>(P.rows + ((size_t)c * P.R + dst_row) * P.Npad + base), make_uint2(n0, n1));
+      __stcg(reinterpret_cast<uint2*>(const_cast<uint8_t*>(rows_c) + (size_t)dst_row * P.Npad), make_uint2(n0, n1));
       if (__any_sync(0xffffffffu, (lm0 | lm1) != 0u)) {
-        // per-lane sums over at most 4 rows fit 32 bits (|q| < 2^29); squares go to 64 bits
+        // masked per-lane sums: 4 rows fit 32 bits (|q| < 2^29); squares accumulate in 64 bits
         int s_a = 0, s_b = 0, r_a = 0, r_b = 0;
         unsigned long long r2 = 0ull;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          if (lm0 & (1u << (8 * e))) { s_a += q_s[e]; r_a += q_r[e]; r2 += (unsigned long long)((long long)q_r[e] * (long long)q_r[e]); }
-          if (lm1 & (1u << (8 * e))) { s_b += q_s[4 + e]; r_b += q_r[4 + e]; r2 += (unsigned long long)((long long)q_r[4 + e] * (long long)q_r[4 + e]); }
+          const int ma = (int)BK_ROWMASK(lm0, e), mb = (int)BK_ROWMASK(lm1, e);
+          s_a += q_s[e] & ma; s_b += q_s[4 + e] & mb;
+          if (gauss) {
+            const int qa = q_r[e] & ma, qb = q_r[4 + e] & mb;
+            r_a += qa; r_b += qb;
+            r2 += (unsigned long long)((long long)qa * (long long)qa);
+            r2 += (unsigned long long)((long long)qb * (long long)qb);
+          }
         }
         const unsigned cl = (unsigned)(__popc(lm0) + __popc(lm1)) >> 3;
-        const unsigned n_tot = __reduce_add_sync(0xffffffffu, cl);
-        const long long s_st = warp_sum_s48((long long)s_a + (long long)s_b);
-        unsigned long long* acc = sacc + ji * BK_ACC_STRIDE;   // the sums are warp-uniform: one lane per statistic
-        if (lane == 0) atomicAdd(acc + BK_ACC_N, (unsigned long long)n_tot);
-        if (lane == 1) atomicAdd(acc + BK_ACC_SST, (unsigned long long)s_st);
+        const long long st = (long long)s_a + (long long)s_b, sr = (long long)r_a + (long long)r_b;
+        // REDUX partial sums = the limbs.  The member count shares a word with the top chunk of the squares.
+        const unsigned pk = __reduce_add_sync(0xffffffffu, (unsigned)(r2 >> 48) | (cl << 20));   // chunk < 2^13 per lane
+        unsigned v = pk >> 20;                                                                    // lane 0: BK_LIMB_N
+        const unsigned st_lo = __reduce_add_sync(0xffffffffu, (unsigned)st & 0xFFFFu);
+        const int st_hi = __reduce_add_sync(0xffffffffu, (int)(st >> 16));
+        v = lane == BK_LIMB_ST_LO ? st_lo : v;
+        v = lane == BK_LIMB_ST_HI ? (unsigned)st_hi : v;
+        int nl = 3;
         if (gauss) {   // Gaussian sufficient statistics of the residual (Bernoulli: q_r holds noi bits)
-          const long long s_r = warp_sum_s48((long long)r_a + (long long)r_b);
+          const unsigned sr_lo = __reduce_add_sync(0xffffffffu, (unsigned)sr & 0xFFFFu);
+          const int sr_hi = __reduce_add_sync(0xffffffffu, (int)(sr >> 16));
           const unsigned c0 = __reduce_add_sync(0xffffffffu, (unsigned)(r2 & 0xFFFFull));
           const unsigned c1 = __reduce_add_sync(0xffffffffu, (unsigned)((r2 >> 16) & 0xFFFFull));
           const unsigned c2 = __reduce_add_sync(0xffffffffu, (unsigned)((r2 >> 32) & 0xFFFFull));
-          const unsigned c3 = __reduce_add_sync(0xffffffffu, (unsigned)(r2 >> 48));
-          if (lane == 2) atomicAdd(acc + BK_ACC_SR, (unsigned long long)s_r);
-          if (lane == 3) atomicAdd(acc + BK_ACC_SR2LO, (unsigned long long)c0 + ((unsigned long long)c1 << 16));   // sum of the low 32-bit halves
-          if (lane == 4) atomicAdd(acc + BK_ACC_SR2HI, (unsigned long long)c2 + ((unsigned long long)c3 << 16));   // sum of the high halves
+          v = lane == BK_LIMB_SR_LO ? sr_lo : v;
+          v = lane == BK_LIMB_SR_HI ? (unsigned)sr_hi : v;
+          v = lane == BK_LIMB_C0 ? c0 : v;
+          v = lane == BK_LIMB_C1 ? c1 : v;
+          v = lane == BK_LIMB_C2 ? c2 : v;
+          v = lane == BK_LIMB_C3 ? (pk & 0xFFFFFu) : v;
+          nl = 9;
         }
+        if (lane < nl) atomicAdd(sacc + ji * BK_LIMBS + lane, v);   // one shared-memory atomic instruction per job
       }
       if (next_node >= 0) {
         const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(n0, next4)) + __popc(bytes_eq_msb(n1, next4)));
         const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0) P.rowcnt[((size_t)c * P.R + dst_row) * P.ntiles + tile] = tot;
+        if (lane == 0) cnt_c[(size_t)dst_row * P.ntiles] = tot;
       }
       const long long u_t3 = UTICK(lane + (int)n0);
       UACC(8, u_t1 - u_t0); UACC(9, u_t2 - u_t1); UACC(10, u_t3 - u_t2); UACC(11, 1);
     } else {  // BK_JOB_COUNT
       const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(w0, next4)) + __popc(bytes_eq_msb(w1, next4)));
       const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
-      if (lane == 0) P.rowcnt[((size_t)c * P.R + src_row) * P.ntiles + tile] = tot;
+      if (lane == 0) cnt_c[(size_t)src_row * P.ntiles] = tot;
     }
   }
 }
@@ -1013,7 +1051,7 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
 // y stay in registers; per job the particle's new leaf-id row is read and the rows of the two new leaves
 // contribute their quantised log-likelihood term at the leaf's value (+9N bytes per grow event).
 __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
-                                        unsigned long long* __restrict__ sacc) {
+                                        unsigned* __restrict__ sacc) {
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
   float noi[8], yv[8];
@@ -1027,7 +1065,7 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
     yv[0] = b0.x; yv[1] = b0.y; yv[2] = b0.z; yv[3] = b0.w; yv[4] = b1.x; yv[5] = b1.y; yv[6] = b1.z; yv[7] = b1.w;
   }
   for (int ji = job_lo; ji < job_hi; ++ji) {
-    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // L1-cached, see round_unit
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
     const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
     const int src_row = j0.z;
     const float vl = __int_as_float(j1.z), vr = __int_as_float(j2.y);
@@ -1041,13 +1079,14 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
       if (id == left_id) { s_l += (long long)bk_bern_q(yv[e], noi[e], vl); any = true; }
       else if (id == left_id + 1u) { s_r += (long long)bk_bern_q(yv[e], noi[e], vr); any = true; }
     }
-    if (__any_sync(0xffffffffu, any)) {
-      const unsigned long long t_l = warp_sum_u64((unsigned long long)s_l), t_r = warp_sum_u64((unsigned long long)s_r);
-      if (lane == 0) {
-        unsigned long long* acc = sacc + ji * BK_ACC_STRIDE;
-        if (t_l) atomicAdd(acc + BK_ACC_LLL, t_l);
-        if (t_r) atomicAdd(acc + BK_ACC_LLR, t_r);
-      }
+    if (__any_sync(0xffffffffu, any)) {   // |s| <= 8 * 2^29 per lane: (hi, lo) limbs as in round_unit
+      const unsigned l_lo = __reduce_add_sync(0xffffffffu, (unsigned)s_l & 0xFFFFu), r_lo = __reduce_add_sync(0xffffffffu, (unsigned)s_r & 0xFFFFu);
+      const int l_hi = __reduce_add_sync(0xffffffffu, (int)(s_l >> 16)), r_hi = __reduce_add_sync(0xffffffffu, (int)(s_r >> 16));
+      unsigned v = l_lo;
+      v = lane == 1 ? (unsigned)l_hi : v;
+      v = lane == 2 ? r_lo : v;
+      v = lane == 3 ? (unsigned)r_hi : v;
+      if (lane < 4) atomicAdd(sacc + ji * BK_LIMBS + BK_LIMB_LLL_LO + lane, v);
     }
   }
 }
@@ -1227,7 +1266,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
   for (int c = c_first; c < P.C; c += c_step) n_mine++;
   if (P.C < BK_NGROUPS) n_mine = 1;
   if (tid < 64) { sh.fin[tid] = 0; sh.seen[tid] = 0u; }
-  for (int i = tid; i < BK_MAX_PARTICLES * BK_ACC_STRIDE; i += BK_GROUP_THREADS) sh.acc[i] = 0ull;
+  for (int i = tid; i < BK_MAX_PARTICLES * BK_LIMBS; i += BK_GROUP_THREADS) sh.acc[i] = 0u;
   GROUP_SYNC(g);
   int next = 0, n_finished = 0;
   long long t_idle0 = clock64();
@@ -1301,13 +1340,12 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
       GROUP_SYNC(g);
       // flush the group's partial sums: one global atomic per non-zero (job, statistic); leaves sh.acc zeroed
       for (int i = tid; i < wk.njobs * BK_ACC_STRIDE; i += BK_GROUP_THREADS) {
-        const unsigned long long v = sh.acc[i];
-        if (v) {
-          sh.acc[i] = 0ull;
-          const int slot = jobs[i / BK_ACC_STRIDE].slot;
-          red_add_u64(P.accL + ((size_t)wk.chain * P.P + slot) * BK_ACC_STRIDE + (i % BK_ACC_STRIDE), v);
-        }
+        const int ji = i / BK_ACC_STRIDE, k = i % BK_ACC_STRIDE;
+        const unsigned long long v = limbs_to_stat(sh.acc + ji * BK_LIMBS, k);
+        if (v) red_add_u64(P.accL + ((size_t)wk.chain * P.P + jobs[ji].slot) * BK_ACC_STRIDE + k, v);
       }
+      GROUP_SYNC(g);
+      for (int i = tid; i < wk.njobs * BK_LIMBS; i += BK_GROUP_THREADS) sh.acc[i] = 0u;
     } else {  // BK_CMD_SWEEP: group-wide row tiles, round robin over all serving groups
       for (unsigned u = wk.lo; u < (unsigned)wk.total; u += wk.hi) sweep_unit(P, wk.chain, (int)u, sh, g, tid);
     }
@@ -1529,6 +1567,7 @@ static int make_layout(const bk_settings* s, Layout* L) {
   if ((long long)s->n_chains * (s->n_groups > 1 ? s->n_groups : 1) > 64) { set_err("at most 64 chains x groups per handle"); return BK_ERR_ARG; }
   if (s->n_groups > 0xFFFF) { set_err("n_groups must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
   if (s->n_trees > 65535) { set_err("n_trees must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
+  if (s->n_rows > (1 << 25)) { set_err("n_rows above 2^25 would overflow the 32-bit partial-sum limbs of a worker group"); return BK_ERR_ARG; }
   if (s->likelihood != BK_LIK_NORMAL && s->likelihood != BK_LIK_BERNOULLI_LOGIT) { set_err("likelihood not implemented on the device (no CPU fallback)"); return BK_ERR_UNSUPPORTED; }
   if (!s->p_leaf || !s->split_prior) { set_err("p_leaf and split_prior are required"); return BK_ERR_ARG; }
   const size_t C = (size_t)s->n_chains * (s->n_groups > 1 ? s->n_groups : 1), P = s->n_particles, m = s->n_trees, p = s->n_cols;
