@@ -318,12 +318,12 @@ BK_HD bk_stats bk_stats_sub(bk_stats a, bk_stats b) {
 }
 
 /* leaf value: mean(sum_trees over members)/m + z*leaf_sd, 0 for an empty leaf
- *  */
-BK_HD float bk_leaf_value(int32_t n, int64_t sst, double inv_qscale, double m,
-                          double z, float leaf_sd) {
+ * (SURVEY.md App. A.5).  inv_qm = 2^-qshift / m (one rounded double, computed once by the caller).
+ * The only division is a correctly rounded float one: fp64 division costs ~1000 cycles on a B200 SM. */
+BK_HD float bk_leaf_value(int32_t n, int64_t sst, double inv_qm, double z, float leaf_sd) {
   if (n <= 0) return 0.0f;
-  double mean = BK_DDIV(BK_DMUL((double)sst, inv_qscale), (double)n);
-  double v = BK_DFMA(z, (double)leaf_sd, BK_DDIV(mean, m));
+  float mean = BK_FDIV((float)BK_DMUL((double)sst, inv_qm), (float)n);
+  double v = BK_DFMA(z, (double)leaf_sd, (double)mean);
   return (float)v;
 }
 
@@ -400,9 +400,42 @@ BK_HD int32_t bk_bern_q(float y, float noi, float value) {
 /* log-likelihood of a particle from the integer sum of its leaves' terms (exact: |llq| < 2^53) */
 BK_HD double bk_bern_loglik(double llq) { return BK_DMUL(llq, 9.5367431640625e-07); }
 
-/* weight normalisation term exp(lw - max) + 1e-12 */
-BK_HD double bk_weight_term(double lw, double lw_max) {
-  return BK_DADD(bk_exp(BK_DSUB(lw, lw_max)), 1e-12);
+/* Particle weights and systematic resampling in FIXED POINT (w = exp(lw - max) + 1e-12,
+ * normalise, inverse-CDF walk over the points (u + i)/L).
+ *   W_i   = rint(exp(-(max - lw_i)) * 2^40) + 1       exp in float (bk_exp_neg_f); the +1 (2^-40 ~ 9e-13) is the floor
+ *   S_j   = W_0 + ... + W_j                           exact 64-bit integers: any scan order gives the same bits
+ *   point i of L:  A_i = i * 2^32 + u32               (u32 = the raw 32-bit uniform)
+ *   ancestor(i) = first j with  A_i * S_last <= S_j * L * 2^32   (128-bit integers), capped at L - 1
+ * which is the walk `while (point > cum[idx]) idx++` on cum_j = S_j / S_last, point = (u + i)/L without a single
+ * rounding.  No fp64 division or exponential is left on the per-round critical path. */
+#define BK_W_SHIFT 40
+BK_HD uint64_t bk_weight_fix(double lw, double lw_max) {
+  float t = (float)BK_DSUB(lw_max, lw);             /* >= 0 */
+  float e = bk_exp_neg_f(t < 0.0f ? 0.0f : t);      /* (0, 1] or 0 after underflow */
+  /* e * 2^40 is exact in float; round-to-nearest-even conversion on both sides */
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__float2ull_rn(BK_FMUL(e, 1099511627776.0f)) + 1u;
+#else
+  return (uint64_t)llrintf(BK_FMUL(e, 1099511627776.0f)) + 1u;
+#endif
+}
+BK_HD uint64_t bk_mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+/* left-hand side of the ancestor test for point i: A_i * S_last as (hi, lo) */
+BK_HD bk_u128 bk_resample_point(uint32_t i, uint32_t u32, uint64_t s_last) {
+  uint64_t a = ((uint64_t)i << 32) | (uint64_t)u32;
+  return bk_u128_make(bk_mulhi64(a, s_last), a * s_last);
+}
+/* point <= S_j * L * 2^32 ?   (S_j * L < 2^63 for L <= 128) */
+BK_HD int bk_resample_le(bk_u128 point, uint64_t s_j, uint32_t L) {
+  uint64_t sl = s_j * (uint64_t)L;
+  uint64_t hi = sl >> 32, lo = sl << 32;
+  return point.hi < hi || (point.hi == hi && point.lo <= lo);
 }
 
 #endif /* BK_SPEC_H */

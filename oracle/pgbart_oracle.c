@@ -35,7 +35,7 @@
  *   B5  leaf value = mean(sum_trees over members)/m + z * leaf_sd
  *   B6  log-weight = Gaussian log-likelihood from per-leaf (n, sum r, sum r^2), or Bernoulli-logit
  *       log-likelihood from a second pass over the rows of the two new leaves (fixed-point terms)
- *   B7  w = exp(lw - max) + 1e-12; cumulative weights c_i = (w_0+..+w_i)/(w_0+..+w_L-1)
+ *   B7  w = exp(lw - max) + 1e-12 in fixed point; exact integer running sums
  *   B8  systematic resampling of particles 1..P-1
  *   B9  final systematic resampling over all P + uniform pick; commit
  *   B10 batch of max(1,int(m*batch)) trees per step, round robin
@@ -83,6 +83,7 @@ typedef struct bko_s {
   int32_t* rules;
   float qscale;
   double inv_qscale;
+  double inv_qm;  /* 2^-qshift / m */
   float* st;      /* sum of trees */
   int32_t* qr;
   int32_t* qst;
@@ -99,7 +100,7 @@ typedef struct bko_s {
   int32_t draw;
   bk_trace_rec* trace;
   int32_t trace_len, trace_cap;
-  double* w;
+  uint64_t* w;   /* running sums of the fixed-point weights */
   int32_t* anc;
   long long bytes_touched; /* rough algorithmic byte counter for the CPU baseline */
 } bko;
@@ -142,6 +143,7 @@ int bko_create(const bk_settings* s, const float* X, const float* y, int chain_l
   rebuild_cum(o);
   o->qscale = ldexpf(1.0f, s->qshift);
   o->inv_qscale = ldexp(1.0, -s->qshift);
+  o->inv_qm = BK_DDIV(o->inv_qscale, (double)o->m);
   int N = o->N;
   o->st = (float*)malloc(sizeof(float) * (size_t)N);
   o->noi = (float*)malloc(sizeof(float) * (size_t)N);
@@ -165,7 +167,7 @@ int bko_create(const bk_settings* s, const float* X, const float* y, int chain_l
   o->leaf_sd = s->leaf_sd_init;
   o->trace_cap = s->trace_capacity;
   if (o->trace_cap > 0) o->trace = (bk_trace_rec*)calloc((size_t)o->trace_cap, sizeof(bk_trace_rec));
-  o->w = (double*)malloc(sizeof(double) * (size_t)o->P);
+  o->w = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)o->P);
   o->anc = (int32_t*)malloc(sizeof(int32_t) * (size_t)o->P);
   *out = o;
   return BK_OK;
@@ -198,23 +200,21 @@ static double particle_ssq(const bko* o, const o_particle* q) {
   return ssq;
 }
 
-/* Weight terms w_i = exp(lw_i - max) + 1e-12 (App. A.7), their sequential running sums S_i, and
- * the normalised cumulative weights c_i = S_i / S_last.  Systematic resampling: index of point
- * (u+i)/L = first j with point <= c_j (the inverse-CDF walk), capped at L-1. */
-static void normalise_cum(const o_particle* parts, int first, int count, double* cum) {
+/* Fixed-point weights W_i (bk_weight_fix), their exact integer running sums S_j, and systematic resampling:
+ * ancestor of point (u + i)/L = first j with (i*2^32 + u32) * S_last <= S_j * L * 2^32, capped at L-1
+ * (the inverse-CDF walk of App. A.7 without roundings; see bk_spec.h). */
+static void weight_sums(const o_particle* parts, int first, int count, uint64_t* S) {
   double mx = parts[first].lw;
   for (int i = 1; i < count; ++i) if (parts[first + i].lw > mx) mx = parts[first + i].lw;
-  double run = 0.0;
-  for (int i = 0; i < count; ++i) { run = BK_DADD(run, bk_weight_term(parts[first + i].lw, mx)); cum[i] = run; }
-  const double tot = cum[count - 1];
-  for (int i = 0; i < count; ++i) cum[i] = BK_DDIV(cum[i], tot);
+  uint64_t run = 0;
+  for (int i = 0; i < count; ++i) { run += bk_weight_fix(parts[first + i].lw, mx); S[i] = run; }
 }
 
-static void systematic(const double* cum, int L, double u, int32_t* idx_out) {
+static void systematic(const uint64_t* S, int L, uint32_t u32, int32_t* idx_out) {
   int idx = 0;
   for (int i = 0; i < L; ++i) {
-    double point = BK_DDIV(BK_DADD(u, (double)i), (double)L);
-    while (point > cum[idx] && idx < L - 1) idx += 1;
+    bk_u128 point = bk_resample_point((uint32_t)i, u32, S[L - 1]);
+    while (!bk_resample_le(point, S[idx], (uint32_t)L) && idx < L - 1) idx += 1;
     idx_out[i] = idx;
   }
 }
@@ -271,8 +271,8 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
   o->bytes_touched += (long long)N * 14;
   double zl = bk_normal(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_LEFT));
   double zr = bk_normal(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_RIGHT));
-  float vl = bk_leaf_value(sl.n, sl.sst, o->inv_qscale, (double)o->m, zl, o->leaf_sd);
-  float vr = bk_leaf_value(sr.n, sr.sst, o->inv_qscale, (double)o->m, zr, o->leaf_sd);
+  float vl = bk_leaf_value(sl.n, sl.sst, o->inv_qm, zl, o->leaf_sd);
+  float vr = bk_leaf_value(sr.n, sr.sst, o->inv_qm, zr, o->leaf_sd);
   double c_parent = bk_leaf_ssq(nd->st, nd->value, o->inv_qscale);
   nd->var = v; nd->split = s; nd->left = L;
   o_node* nl = &q->nodes[L]; o_node* nr = &q->nodes[R];
@@ -375,8 +375,8 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       int live = 0;
       for (int q = 1; q < P; ++q) if (o->parts[q].q_head < o->parts[q].n_nodes) live = 1;
       if (!live) break;
-      normalise_cum(o->parts, 1, P - 1, o->w);
-      double u = bk_u01(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0]);
+      weight_sums(o->parts, 1, P - 1, o->w);
+      uint32_t u = bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0];
       systematic(o->w, P - 1, u, o->anc);
       for (int q = 1; q < P; ++q) part_copy(&o->tmp[q], &o->parts[o->anc[q - 1] + 1], N);
       for (int q = 1; q < P; ++q) {
@@ -385,8 +385,8 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       }
     }
     /* B9: final selection */
-    normalise_cum(o->parts, 0, P, o->w);
-    double uf = bk_u01(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
+    weight_sums(o->parts, 0, P, o->w);
+    uint32_t uf = bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0];
     systematic(o->w, P, uf, o->anc);
     uint32_t pick = bk_index(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P);
     int win = o->anc[pick];

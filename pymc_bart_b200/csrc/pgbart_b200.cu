@@ -123,17 +123,24 @@ __device__ unsigned long long g_wdbg[256][16];
 // (the clock read is predicated on `dep`, so it cannot issue before the value has arrived)
 #define UTICK(dep) ({ long long t_ = 0; asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0x7fffffff; @p mov.u64 %0, %%clock64; }" : "+l"(t_) : "r"((int)(dep)) : "memory"); t_; })
 #define UACC(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_wdbg[blockIdx.x][i], (unsigned long long)(v)); } while (0)
+// control-side cycle split (thread 0 of chain 0's control CTA): CT0 starts a section, CT(i, dep) closes part i
+// (accumulated in shared memory, flushed to g_cdbg once per step, so that a stamp costs a few cycles)
+__device__ unsigned long long g_cdbg[32];
+__shared__ unsigned long long s_cdbg[32];
+#define CT0() long long ct_last_ = clock64()
+#define CT(i, dep) do { if (threadIdx.x == 32) { const long long n_ = UTICK(dep); s_cdbg[i] += (unsigned long long)(n_ - ct_last_); ct_last_ = n_; } } while (0)
 #define WDBG(i, t0)                                                              \
   do { if (threadIdx.x == 0) g_wdbg[blockIdx.x][i] += globaltimer_ns() - (t0); } while (0)
 #else
 #define WDBG(i, t0) do { } while (0)
 #define UTICK(dep) 0ll
 #define UACC(i, v) do { } while (0)
+#define CT0() do { } while (0)
+#define CT(i, dep) do { } while (0)
 #endif
 
 #define BK_CUM_SMEM 1024
 struct CtlShared {
-  double w[BK_MAX_PARTICLES];
   double lw[BK_MAX_PARTICLES];
   int anc[BK_MAX_PARTICLES];
   int s_kind[BK_MAX_PARTICLES];   // 0 nothing, 1 grow, 2 only needs a count
@@ -148,7 +155,7 @@ struct CtlShared {
   unsigned char row_used[2 * BK_MAX_PARTICLES];
   int row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds (persists across phases)
   Job jobs[BK_MAX_PARTICLES];               // staged here, copied to global by the whole CTA
-  double cum_w[BK_MAX_PARTICLES];
+  unsigned long long cum_s[BK_MAX_PARTICLES];   // running sums of the fixed-point weights
   double cum_prior[BK_CUM_SMEM];   // normalised cumulative split prior (first BK_CUM_SMEM columns)
   int live;
   int win;
@@ -317,45 +324,48 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
   return __ldg(P.X + (size_t)var * P.Npad + i);
 }
 
-// normalise sh.lw[first..first+count) into sh.w, then systematic resampling into sh.anc
-// (block-wide; thread 0 does the order-dependent scalar parts in the oracle's order)
-// normalise sh.lw[first..first+count) and resample systematically into sh.anc[0..count).
-// Runs in warp 0 (count <= 128: four values per lane).  The only order-dependent part, the running
-// sums of the weight terms, is done by lane 0 in index order (the oracle's order); the maximum, the
-// exponentials, the divisions and the inverse-CDF searches are lane-parallel.  Ends with a block barrier.
-__device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, double u) {
-  if ((threadIdx.x >> 5) == 0) {
+// Fixed-point weights of sh.lw[first..first+count) and systematic resampling into sh.anc[0..count) (bk_spec.h:
+// bk_weight_fix / bk_resample_*).  Runs in warp 0 (count <= 128: element i lives in lane i % 32, slot i / 32).
+// Everything is integer after the float exponential, so the warp-parallel scan gives the oracle's sequential sums
+// bit for bit.  Ends with a block barrier.
+// Runs in warp 1, not warp 0: lane 0 of warp 0 executes the chain's scalar sections alone and (non-aligned barriers)
+// can leave that warp split, and a split warp takes the WARPSYNC slow path on EVERY shuffle (~200 cycles each,
+// measured); warps 1..7 never diverge across a barrier, so their collectives stay on the fast path.
+__device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int o) {
+  const unsigned lo = __shfl_up_sync(0xffffffffu, (unsigned)v, o), hi = __shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), o);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, uint32_t u32) {
+  if ((threadIdx.x >> 5) == 1) {
     const int lane = threadIdx.x & 31;
+    CT0();
     double mx = -1.7976931348623157e308;
     for (int i = lane; i < count; i += 32) { double v = sh.lw[first + i]; mx = v > mx ? v : mx; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { double ov = __shfl_xor_sync(0xffffffffu, mx, o); mx = ov > mx ? ov : mx; }
-    for (int i = lane; i < count; i += 32) sh.w[i] = bk_weight_term(sh.lw[first + i], mx);
-    __syncwarp();
-    if (lane == 0) {
-      double run = 0.0;
-      int i = 0;
-      for (; i + 8 <= count; i += 8) {   // loads batched ahead of the dependent adds
-        double v[8];
+    CT(0, __double2loint(mx));
+    unsigned long long run = 0ull;                       // sum of all earlier 32-element slices
+    for (int k0 = 0; k0 < count; k0 += 32) {
+      const int i = k0 + lane;
+      unsigned long long s = i < count ? bk_weight_fix(sh.lw[first + i], mx) : 0ull;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = sh.w[i + j];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { run = BK_DADD(run, v[j]); sh.cum_w[i + j] = run; }
-      }
-      for (; i < count; ++i) { run = BK_DADD(run, sh.w[i]); sh.cum_w[i] = run; }
+      for (int o = 1; o < 32; o <<= 1) { const unsigned long long nb = shfl_up_u64(s, o); if (lane >= o) s += nb; }
+      s += run;
+      if (i < count) sh.cum_s[i] = s;
+      run = ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(s >> 32), 31) << 32) | __shfl_sync(0xffffffffu, (unsigned)s, 31);
+
     }
     __syncwarp();
-    const double tot = sh.cum_w[count - 1];
-    __syncwarp();
-    for (int i = lane; i < count; i += 32) sh.cum_w[i] = BK_DDIV(sh.cum_w[i], tot);
-    __syncwarp();
+    CT(1, (int)run);
+    const unsigned long long s_last = run;               // = S[count - 1]
     for (int i = lane; i < count; i += 32) {
-      // first index whose cumulative weight reaches the point (= the walk `while (point > c[idx]) idx++`)
-      const double point = BK_DDIV(BK_DADD(u, (double)i), (double)count);
+      // first index whose running sum reaches the point (= the walk `while (point > c[idx]) idx++`)
+      const bk_u128 point = bk_resample_point((uint32_t)i, u32, s_last);
       int lo = 0, hi = count - 1;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (point > sh.cum_w[mid]) lo = mid + 1; else hi = mid; }
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (!bk_resample_le(point, sh.cum_s[mid], (uint32_t)count)) lo = mid + 1; else hi = mid; }
       sh.anc[i] = lo;
     }
+    CT(4, sh.anc[lane < count ? lane : 0]);
   }
   CTRL_SYNC();
 }
@@ -474,7 +484,8 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
     __shared__ int s_err;
     if (threadIdx.x == 0) s_err = 0;
     CTRL_SYNC();
-    for (int s = 1 + warp; s < P.P; s += nwarps) {
+    // warps 1..7 only: warp 0 can be split (see normalise_and_resample) and would crawl through the shuffles
+    for (int s = warp; s < P.P && warp > 0; s += nwarps - 1) {
       if (sh.s_kind[s] != 1) continue;
       float sv;
       if (sh.s_row[s] == BK_ROW_VIRTUAL) {
@@ -513,6 +524,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       }
     }
     if (t < P.R) is_free = sh.row_used[t] ? 0 : 1;
+    __syncwarp();
     if (t < 256) {   // R <= 256 and P <= 128: eight warps cover both index ranges
       const unsigned bg = __ballot_sync(0xffffffffu, is_grow), bc = __ballot_sync(0xffffffffu, is_cnt),
                      bf = __ballot_sync(0xffffffffu, is_free);
@@ -597,8 +609,8 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     if (bern) { sl.sr = 0; sr.sr = 0; }   // the children's log-likelihood sums arrive with the LL epoch
     double zl = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
     double zr = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
-    float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qscale, (double)P.m, zl, hot->leaf_sd);
-    float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qscale, (double)P.m, zr, hot->leaf_sd);
+    float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qm, zl, hot->leaf_sd);
+    float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qm, zr, hot->leaf_sd);
     double c_parent = bk_leaf_ssq(sp, parent.value, P.inv_qscale);
     const int nn = S.h->n_nodes;
     parent.var = jb.var; parent.split = jb.split; parent.left = nn;
@@ -671,7 +683,7 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   if ((int)threadIdx.x < P.P) sh.lw[threadIdx.x] = pref(P, c, buf, threadIdx.x).h->lw;
   CTRL_SYNC();
-  double uf = bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0]);
+  const uint32_t uf = bk_rng(S0, C0, D0, G0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0];
   normalise_and_resample(P, sh, 0, P.P, uf);
   if (threadIdx.x == 0) {
     unsigned pick = bk_index(bk_rng(S0, C0, D0, G0, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P.P);
@@ -840,8 +852,8 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       MARK(130 + live);
       TSUB(1);
       if (!live) { CTRL_SYNC(); finish_tree(P, c, ctl, hot, sh); TSUB(7); MARK(139); return; }
-      double u = bk_u01(bk_rng(P.seed, P.chain_base + (uint32_t)(c / P.G), (uint32_t)hot->draw, (uint32_t)(c % P.G), (uint32_t)hot->cur_tree,
-                               (uint32_t)hot->round, 0, BK_U_RESAMPLE).v[0]);
+      const uint32_t u = bk_rng(P.seed, P.chain_base + (uint32_t)(c / P.G), (uint32_t)hot->draw, (uint32_t)(c % P.G), (uint32_t)hot->cur_tree,
+                                (uint32_t)hot->round, 0, BK_U_RESAMPLE).v[0];
       MARK(132);
       normalise_and_resample(P, sh, 1, P.P - 1, u);
       TSUB(2);
@@ -1272,48 +1284,54 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
   long long t_idle0 = clock64();
   unsigned long long t_pub = 0; (void)t_pub;
   for (;;) {
-    if (tid == 0) {   // the group's poller: spins until one of its chains has a new epoch (the other warps wait at the barrier)
+    if (warp == 0) {
+      // The group's poller is its whole first warp, in lock step: every lane issues the same loads (one transaction)
+      // and takes the same decisions, so the warp never splits.  (A single polling lane leaves its warp split after
+      // the barrier below, and a split warp pays a WARPSYNC slow path on every REDUX / vote of its units.)
+      const int lane = tid;
       Work wk; wk.chain = -1; wk.exit_now = 0; wk.cmd = 0; wk.njobs = 0; wk.total = 0; wk.lo = 0u; wk.hi = 0u;
       unsigned spins = 0;
       while (wk.chain < 0 && !wk.exit_now) {
-      for (int k = 0; k < n_mine && wk.chain < 0; ++k) {
-        const int idx = (next + k) % n_mine;
-        const int c = P.C >= BK_NGROUPS ? c_first + idx * c_step : c_first;
-        if (sh.fin[c]) continue;
-        ChainSync* sy = P.sync + c;
-        const unsigned ep = ld_relaxed_u32(reinterpret_cast<const unsigned*>(&sy->ticket));   // epoch word, released after desc
-        if (ep == sh.seen[c]) continue;
-        fence_acq_rel_gpu();   // acquire (pairs with the control CTA's release store); also drops this SM's stale L1 lines
-        const uint4 d = ld_volatile_v4(&sy->desc);
-        if (d.x != ep) continue;                                    // a newer epoch is being published: next poll
-        sh.seen[c] = ep;
-        if ((d.y & 0xFFu) == BK_CMD_DONE) { sh.fin[c] = 1; n_finished++; continue; }
-        wk.chain = c; wk.cmd = (int)(d.y & 0xFFu); wk.njobs = (int)d.z; wk.total = (int)d.w;
-        const unsigned ns = (unsigned)servers_of(P.C, c);
-        if (wk.cmd == BK_CMD_SWEEP) {
-          wk.lo = (unsigned)w * ns + (unsigned)my_rank;             // first row tile of this group; stride W * ns
-          wk.hi = (unsigned)W * ns;
-        } else {
-          const unsigned clo = (unsigned)((unsigned long long)w * d.w / (unsigned)W);          // the CTA's pairs ...
-          const unsigned chi = (unsigned)((unsigned long long)(w + 1) * d.w / (unsigned)W);
-          wk.lo = clo + (unsigned)((unsigned long long)(chi - clo) * (unsigned)my_rank / ns);        // ... split over its groups
-          wk.hi = clo + (unsigned)((unsigned long long)(chi - clo) * (unsigned)(my_rank + 1) / ns);
-        }
-        next = (idx + 1) % n_mine;
+        for (int k = 0; k < n_mine && wk.chain < 0; ++k) {
+          const int idx = (next + k) % n_mine;
+          const int c = P.C >= BK_NGROUPS ? c_first + idx * c_step : c_first;
+          if (sh.fin[c]) continue;
+          ChainSync* sy = P.sync + c;
+          const unsigned ep = ld_relaxed_u32(reinterpret_cast<const unsigned*>(&sy->ticket));   // epoch word, released after desc
+          if (ep == sh.seen[c]) continue;
+          if (lane == 0) fence_acq_rel_gpu();   // acquire (pairs with the control CTA's release store); drops stale L1 lines
+          __syncwarp();
+          const uint4 d = ld_volatile_v4(&sy->desc);
+          if (d.x != ep) continue;                                    // a newer epoch is being published: next poll
+          sh.seen[c] = ep;                                            // (all lanes store the same value)
+          if ((d.y & 0xFFu) == BK_CMD_DONE) { sh.fin[c] = 1; n_finished++; continue; }
+          wk.chain = c; wk.cmd = (int)(d.y & 0xFFu); wk.njobs = (int)d.z; wk.total = (int)d.w;
+          const unsigned ns = (unsigned)servers_of(P.C, c);
+          if (wk.cmd == BK_CMD_SWEEP) {
+            wk.lo = (unsigned)w * ns + (unsigned)my_rank;             // first row tile of this group; stride W * ns
+            wk.hi = (unsigned)W * ns;
+          } else {
+            const unsigned clo = (unsigned)((unsigned long long)w * d.w / (unsigned)W);          // the CTA's pairs ...
+            const unsigned chi = (unsigned)((unsigned long long)(w + 1) * d.w / (unsigned)W);
+            wk.lo = clo + (unsigned)((unsigned long long)(chi - clo) * (unsigned)my_rank / ns);        // ... split over its groups
+            wk.hi = clo + (unsigned)((unsigned long long)(chi - clo) * (unsigned)(my_rank + 1) / ns);
+          }
+          next = (idx + 1) % n_mine;
 #ifdef BK_PROFILE_CTRL
-        t_pub = *reinterpret_cast<volatile unsigned long long*>(&sy->pad[1]);
-        if (wk.cmd == BK_CMD_ROUND && g == 0) { g_wdbg[blockIdx.x][0] += globaltimer_ns() - t_pub; g_wdbg[blockIdx.x][4] += 1; }
+          t_pub = *reinterpret_cast<volatile unsigned long long*>(&sy->pad[1]);
+          if (wk.cmd == BK_CMD_ROUND && g == 0 && lane == 0) { g_wdbg[blockIdx.x][0] += globaltimer_ns() - t_pub; g_wdbg[blockIdx.x][4] += 1; }
 #endif
-      }
-      if (wk.chain < 0) {
-        if (n_finished == n_mine) wk.exit_now = 1;
-        else if ((++spins & 15u) == 0) {
-          if (ld_volatile_i32(P.abort_flag)) wk.exit_now = 1;
-          else if (clock64() - t_idle0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); wk.exit_now = 1; }
+        }
+        if (wk.chain < 0) {
+          if (n_finished == n_mine) wk.exit_now = 1;
+          else if ((++spins & 15u) == 0) {
+            int stop = ld_volatile_i32(P.abort_flag) != 0;
+            if (!stop && clock64() - t_idle0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); stop = 1; }
+            if (__any_sync(0xffffffffu, stop)) wk.exit_now = 1;
+          }
         }
       }
-      }
-      sh.work = wk;
+      if (lane == 0) sh.work = wk;
     }
     GROUP_SYNC(g);
     const Work wk = sh.work;
@@ -1351,7 +1369,8 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
     }
     GROUP_SYNC(g);   // every warp's stores are ordered before the release below
     if (wk.cmd == BK_CMD_ROUND && g == 0) WDBG(2, t_pub);
-    if (tid == 0) { red_release_add_u32(&P.sync[wk.chain].done, 1u); t_idle0 = clock64(); }
+    if (tid == 0) red_release_add_u32(&P.sync[wk.chain].done, 1u);
+    t_idle0 = clock64();
     if (wk.cmd == BK_CMD_ROUND && g == 0) WDBG(3, t_pub);
   }
 }
@@ -1364,6 +1383,9 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
   ChainHot* hot = &s_hot;
   ChainSync* sy = P.sync + c;
   if (threadIdx.x == 0) s_hot = ctl->hot;   // persistent scalars -> shared memory for the whole step
+#ifdef BK_PROFILE_CTRL
+  if (threadIdx.x < 32) s_cdbg[threadIdx.x] = 0ull;
+#endif
   CTRL_SYNC();
   unsigned issued = 0, epoch = 0;
   const int n_workers = (gridDim.x - P.C) * servers_of(P.C, c);   // serving groups: each reports every epoch once
@@ -1418,6 +1440,9 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       t_wait += q1 - q0; t_ctrl += q2 - q1; t_pub += q3 - q2;
       if (fin) {
         ctl->hot = s_hot;                   // write the scalar state back
+#ifdef BK_PROFILE_CTRL
+        if (c == 0) for (int i = 0; i < 32; ++i) g_cdbg[i] += s_cdbg[i];
+#endif
         bk_step_stats* st = P.stats + c;
         st->us_control = (int32_t)(t_ctrl / 1000ull); st->us_data = (int32_t)(t_wait / 1000ull);
         st->us_sync = (int32_t)(t_pub / 1000ull); st->us_total = (int32_t)((q3 - t_begin) / 1000ull);
@@ -1643,6 +1668,7 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   P.R = L.R; P.ntiles = L.ntiles; P.lik = s->likelihood; P.trace_cap = s->trace_capacity > 0 ? s->trace_capacity : 0;
   P.batch_tune = s->batch_tune < 1 ? 1 : s->batch_tune; P.batch_post = s->batch_post < 1 ? 1 : s->batch_post;
   P.qscale = ldexpf(1.0f, s->qshift); P.inv_qscale = ldexp(1.0, -s->qshift); P.init_leaf = s->init_leaf;
+  P.inv_qm = P.inv_qscale / (double)s->n_trees;
   P.seed = s->seed; P.chain_base = s->chain_base;
   P.X = X_dev; P.y = y_dev; P.st = sum_trees_dev;
   P.qr = (int32_t*)(w + L.qr); P.qst = (int32_t*)(w + L.qst); P.ids_tree = (uint8_t*)(w + L.ids_tree);
@@ -1782,6 +1808,8 @@ int bk_debug_worker_timers(bk_handle* h, unsigned long long* out, int n_cta) {
 #ifdef BK_PROFILE_CTRL
   if (!h || n_cta > 256) return BK_ERR_ARG;
   if (cudaMemcpyFromSymbol(out, g_wdbg, (size_t)n_cta * 16 * sizeof(unsigned long long)) != cudaSuccess) return BK_ERR_CUDA;
+  if (cudaMemcpyFromSymbol(out + (size_t)n_cta * 16, g_cdbg, sizeof(g_cdbg)) != cudaSuccess) return BK_ERR_CUDA;
+  { static unsigned long long z32[32]; cudaMemcpyToSymbol(g_cdbg, z32, sizeof(z32)); }
   static unsigned long long zeros[256 * 16];
   return cudaMemcpyToSymbol(g_wdbg, zeros, sizeof(zeros)) == cudaSuccess ? BK_OK : BK_ERR_CUDA;
 #else

@@ -169,6 +169,7 @@ struct Params {
   int32_t lik, trace_cap, batch_tune, batch_post;
   float qscale, init_leaf;
   double inv_qscale;
+  double inv_qm;     // 2^-qshift / m (leaf mean scale)
   uint32_t seed, chain_base;
   const float* X;   // [p][Npad]
   const float* y;   // [Npad]

@@ -31,10 +31,11 @@ print(f"{cfg} chains={chains}: per step us control={acc[0]:.0f} data={acc[1]:.0f
 sub /= steps
 print("control sub-steps us/step: finalize=%.0f weights=%.0f resample=%.0f copy=%.0f pop=%.0f select=%.0f jobs=%.0f finish+init=%.0f" % tuple(sub))
 
-wd = (ctypes.c_ulonglong * (148 * 16))()
+wd = (ctypes.c_ulonglong * (148 * 16 + 32))()
 dev.lib.bk_debug_worker_timers.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 if dev.lib.bk_debug_worker_timers(dev.h, wd, 148) == 0:
-    w = np.array(list(wd), dtype=np.float64).reshape(148, 16)
+    cd = np.array(list(wd)[148 * 16:], dtype=np.float64)
+    w = np.array(list(wd)[:148 * 16], dtype=np.float64).reshape(148, 16)
     w = w[w[:, 4] > 0]
     n = w[:, 4].sum()
     print("worker ROUND claims: %d per step; mean ns after publish: claimed=%.0f staged=%.0f units_done=%.0f done_added=%.0f; "
@@ -47,3 +48,4 @@ if dev.lib.bk_debug_worker_timers(dev.h, wd, 148) == 0:
     print("stage barrier: cycles from work broadcast to staged jobs visible: warp0 %.0f warp5 %.0f" % (w[:, 13].sum() / n, w[:, 14].sum() / n))
     print("q loads: issue %.0f cycles, first arrival after issue %.0f cycles" % (w[:, 5].sum() / nu * 0 + w[:, 5].sum() / max(w[:, 11].sum(), 1), w[:, 6].sum() / max(w[:, 11].sum(), 1)))
     print("q arrivals after issue: a1 %.0f b0 %.0f b1 %.0f" % tuple(w[:, k].sum() / max(w[:, 11].sum(), 1) for k in (7, 14, 15)))
+    print("control cycle split per step (chain 0, thread 0):", " ".join("%d:%.0f" % (i, v / (steps + 5)) for i, v in enumerate(cd) if v > 0))
