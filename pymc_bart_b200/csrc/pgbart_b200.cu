@@ -156,6 +156,16 @@ struct CtlShared {
   int row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds (persists across phases)
   Job jobs[BK_MAX_PARTICLES];               // staged here, copied to global by the whole CTA
   unsigned long long cum_s[BK_MAX_PARTICLES];   // running sums of the fixed-point weights
+  // Random draws computed in the SHADOW of a data epoch (while the workers stream): Philox counters do not depend on
+  // the particle state, so the next round's proposal draws, this round's leaf-value normals and resampling uniform
+  // are ready when the epoch completes.  Tagged with (tree, round); a consumer that finds another tag computes inline.
+  double pre_u1[BK_MAX_PARTICLES];
+  int pre_v[BK_MAX_PARTICLES];
+  uint32_t pre_u3[BK_MAX_PARTICLES];
+  double pre_zl[BK_MAX_PARTICLES], pre_zr[BK_MAX_PARTICLES];
+  uint32_t pre_ures;
+  int pre_prop_tree, pre_prop_round;   // tag of pre_u1 / pre_v / pre_u3
+  int pre_z_tree, pre_z_round;         // tag of pre_zl / pre_zr / pre_ures
   double cum_prior[BK_CUM_SMEM];   // normalised cumulative split prior (first BK_CUM_SMEM columns)
   int live;
   int win;
@@ -261,36 +271,56 @@ __device__ __forceinline__ bk_trace_rec* trace_at(const Params& P, int c, int po
 }
 
 // k-th member (ascending row index) of `node` in pool row `row`; executed by one warp.
+// Two-level search over the per-tile member counts the workers left in rowcnt: every lane sums a contiguous chunk of
+// tiles (128-bit loads), one warp scan finds the chunk, a second scan over that chunk's 4-tile groups finds the tile —
+// about a dozen shuffles and three dependent L2 round trips whatever N is.
+__device__ __forceinline__ unsigned warp_incl_scan_u32(unsigned v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
+  return v;
+}
 __device__ float select_split(const Params& P, int c, int row, int node, unsigned k, int var, int* err) {
   const int lane = threadIdx.x & 31;
-  const unsigned* cnt = P.rowcnt + ((size_t)c * P.R + row) * P.ntiles;
-  unsigned run = 0, off = 0;
+  const uint4* cnt4 = reinterpret_cast<const uint4*>(P.rowcnt + ((size_t)c * P.R + row) * P.cnt_stride);
+  const int n4 = P.cnt_stride >> 2;                 // 4-tile groups in the row (padding tiles count 0)
+  const int per = (n4 + 31) >> 5;                   // groups per lane
+  unsigned off = k;
   int tile = -1;
-  // eight 32-tile chunks of counts are fetched together (independent L2 loads), then scanned in order
-  for (int t0 = 0; t0 < P.ntiles && tile < 0; t0 += 256) {
-    unsigned vv[8];
+  {
+    unsigned sum = 0u;
+    for (int j0 = 0; j0 < per; j0 += 8) {   // eight independent 128-bit loads in flight per lane
+      uint4 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { int t = t0 + j * 32 + lane; vv[j] = t < P.ntiles ? __ldcg(cnt + t) : 0u; }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (tile >= 0) break;
-      const unsigned v = vv[j];
-      unsigned incl = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += nb;
+      for (int u = 0; u < 8; ++u) {
+        const int i4 = lane * per + j0 + u;
+        v[u] = (j0 + u < per && i4 < n4) ? __ldcg(cnt4 + i4) : make_uint4(0u, 0u, 0u, 0u);
       }
-      const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-      if (k < run + total) {
-        const unsigned excl = incl - v;
-        const bool here = (k >= run + excl) && (k < run + incl);
-        const unsigned b = __ballot_sync(0xffffffffu, here);
-        const int src = __ffs(b) - 1;
-        tile = t0 + j * 32 + src;
-        off = k - (run + __shfl_sync(0xffffffffu, excl, src));
-      } else {
-        run += total;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sum += v[u].x + v[u].y + v[u].z + v[u].w;
+    }
+    const unsigned incl = warp_incl_scan_u32(sum, lane), excl = incl - sum;
+    const unsigned b = __ballot_sync(0xffffffffu, off >= excl && off < incl);
+    if (b != 0u) {
+      const int src = __ffs(b) - 1;
+      off -= __shfl_sync(0xffffffffu, excl, src);
+      // second level: the `per` groups of lane src's chunk, 32 at a time
+      for (int j0 = 0; j0 < per && tile < 0; j0 += 32) {
+        const int i4 = src * per + j0 + lane;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (j0 + lane < per && i4 < n4) v = __ldcg(cnt4 + i4);
+        const unsigned s4 = v.x + v.y + v.z + v.w;
+        const unsigned in2 = warp_incl_scan_u32(s4, lane), ex2 = in2 - s4;
+        const unsigned b2 = __ballot_sync(0xffffffffu, off >= ex2 && off < in2);
+        if (b2 != 0u) {
+          const int l2 = __ffs(b2) - 1;
+          unsigned o2 = off - ex2;          // valid in lane l2
+          int t = 0;
+          if (o2 >= v.x) { o2 -= v.x; t = 1; if (o2 >= v.y) { o2 -= v.y; t = 2; if (o2 >= v.z) { o2 -= v.z; t = 3; } } }
+          tile = __shfl_sync(0xffffffffu, (src * per + j0 + l2) * 4 + t, l2);
+          off = __shfl_sync(0xffffffffu, o2, l2);
+        } else {
+          off -= __shfl_sync(0xffffffffu, in2, 31);
+        }
       }
     }
   }
@@ -432,6 +462,43 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
   CTRL_SYNC();
 }
 
+// first index with u2 < cum[idx], else p-1 (split variable ~ split prior; bart.py:139,155)
+__device__ __forceinline__ int draw_variable_dev(const Params& P, int c, const CtlShared& sh, double u2) {
+  const double* cum = P.cum + (size_t)c * P.p;
+  int lo = 0, hi = P.p - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const double cv = mid < BK_CUM_SMEM ? sh.cum_prior[mid] : cum[mid];
+    if (u2 < cv) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// Runs right after a ROUND epoch has been published (all control threads), overlapping the workers.
+__device__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& sh) {
+  const int round = hot->round, t = hot->cur_tree;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
+  const int q = threadIdx.x;
+  if (q >= 1 && q < P.P) {
+    // leaf-value normals of this round (used by finalize_grows when the epoch is done) for the slots that grow
+    if (sh.s_kind[q] == 1) {
+      sh.pre_zl[q] = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
+      sh.pre_zr[q] = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
+    }
+    // proposal draws of the NEXT round for every slot
+    const uint32_t r1 = (uint32_t)(round + 1);
+    sh.pre_u1[q] = bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, r1, (uint32_t)q, BK_U_LEAF).v[0]);
+    sh.pre_v[q] = draw_variable_dev(P, c, sh, bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, r1, (uint32_t)q, BK_U_VAR).v[0]));
+    sh.pre_u3[q] = bk_rng(S0, C0, D0, G0, (uint32_t)t, r1, (uint32_t)q, BK_U_VAL).v[0];
+  }
+  if (q == 0) {
+    sh.pre_ures = bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0];
+    sh.pre_prop_tree = t; sh.pre_prop_round = round + 1;
+    sh.pre_z_tree = t; sh.pre_z_round = round;
+  }
+  CTRL_SYNC();
+}
+
 // pops, grow decisions, split selection, job list.  Returns (uniformly) the job count.
 __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
@@ -448,19 +515,13 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       const int depth = S.node(j).depth;
       const int n = S.node(j).n;
       double pl = depth < BK_MAX_DEPTH_TABLE ? P.p_leaf[depth] : 1.0;
-      double u1 = bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
+      const bool pre = sh.pre_prop_tree == t && sh.pre_prop_round == round;   // draws made in the shadow of the last epoch
+      double u1 = pre ? sh.pre_u1[q] : bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
       if (u1 > pl && nn + 2 <= BK_MAX_NODES) {
-        double u2 = bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAR).v[0]);
-        const double* cum = P.cum + (size_t)c * P.p;
-        int lo = 0, hi = P.p - 1;  // first index with u2 < cum[idx], else p-1
-        while (lo < hi) {
-          int mid = (lo + hi) >> 1;
-          const double cv = mid < BK_CUM_SMEM ? sh.cum_prior[mid] : cum[mid];
-          if (u2 < cv) hi = mid; else lo = mid + 1;
-        }
-        v = lo;
+        v = pre ? sh.pre_v[q]
+                : draw_variable_dev(P, c, sh, bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAR).v[0]));
         if (n >= 2) {
-          k = bk_index(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAL).v[0], (uint32_t)n);
+          k = bk_index(pre ? sh.pre_u3[q] : bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAL).v[0], (uint32_t)n);
           kind = 1;
         }
       }
@@ -607,8 +668,9 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     bk_stats sp = node_stats(parent);
     bk_stats sr = bk_stats_sub(sp, sl);
     if (bern) { sl.sr = 0; sr.sr = 0; }   // the children's log-likelihood sums arrive with the LL epoch
-    double zl = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
-    double zr = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
+    const bool pre = sh.pre_z_tree == t && sh.pre_z_round == round;
+    double zl = pre ? sh.pre_zl[q] : bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
+    double zr = pre ? sh.pre_zr[q] : bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
     float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qm, zl, hot->leaf_sd);
     float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qm, zr, hot->leaf_sd);
     double c_parent = bk_leaf_ssq(sp, parent.value, P.inv_qscale);
@@ -852,8 +914,10 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       MARK(130 + live);
       TSUB(1);
       if (!live) { CTRL_SYNC(); finish_tree(P, c, ctl, hot, sh); TSUB(7); MARK(139); return; }
-      const uint32_t u = bk_rng(P.seed, P.chain_base + (uint32_t)(c / P.G), (uint32_t)hot->draw, (uint32_t)(c % P.G), (uint32_t)hot->cur_tree,
-                                (uint32_t)hot->round, 0, BK_U_RESAMPLE).v[0];
+      const uint32_t u = (sh.pre_z_tree == hot->cur_tree && sh.pre_z_round == hot->round)
+                             ? sh.pre_ures
+                             : bk_rng(P.seed, P.chain_base + (uint32_t)(c / P.G), (uint32_t)hot->draw, (uint32_t)(c % P.G),
+                                      (uint32_t)hot->cur_tree, (uint32_t)hot->round, 0, BK_U_RESAMPLE).v[0];
       MARK(132);
       normalise_and_resample(P, sh, 1, P.P - 1, u);
       TSUB(2);
@@ -952,7 +1016,7 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
   // per-unit address bases (the per-job part is one multiply-add)
   const uint8_t* rows_c = P.rows + (size_t)c * P.R * P.Npad + base;
   const float* x_b = P.X + base;
-  unsigned* cnt_c = P.rowcnt + (size_t)c * P.R * P.ntiles + tile;
+  unsigned* cnt_c = P.rowcnt + (size_t)c * P.R * P.cnt_stride + tile;
   // leaf ids of a stump: 0 for real rows, 0xFF (limbo) for the padding rows of the last tile
   unsigned vw0 = 0u, vw1 = 0u;
   if (base + 8 > (size_t)P.N) {
@@ -1046,14 +1110,14 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       if (next_node >= 0) {
         const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(n0, next4)) + __popc(bytes_eq_msb(n1, next4)));
         const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0) cnt_c[(size_t)dst_row * P.ntiles] = tot;
+        if (lane == 0) cnt_c[(size_t)dst_row * P.cnt_stride] = tot;
       }
       const long long u_t3 = UTICK(lane + (int)n0);
       UACC(8, u_t1 - u_t0); UACC(9, u_t2 - u_t1); UACC(10, u_t3 - u_t2); UACC(11, 1);
     } else {  // BK_JOB_COUNT
       const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(w0, next4)) + __popc(bytes_eq_msb(w1, next4)));
       const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
-      if (lane == 0) cnt_c[(size_t)src_row * P.ntiles] = tot;
+      if (lane == 0) cnt_c[(size_t)src_row * P.cnt_stride] = tot;
     }
   }
 }
@@ -1382,7 +1446,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
   ChainCtl* ctl = P.ctl + c;
   ChainHot* hot = &s_hot;
   ChainSync* sy = P.sync + c;
-  if (threadIdx.x == 0) s_hot = ctl->hot;   // persistent scalars -> shared memory for the whole step
+  if (threadIdx.x == 0) { s_hot = ctl->hot; sh.pre_prop_tree = -1; sh.pre_z_tree = -1; }   // persistent scalars -> shared memory for the whole step
 #ifdef BK_PROFILE_CTRL
   if (threadIdx.x < 32) s_cdbg[threadIdx.x] = 0ull;
 #endif
@@ -1451,6 +1515,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
     }
     CTRL_SYNC();
     if (s_flag) return true;
+    if (hot->cmd == BK_CMD_ROUND) shadow_round(P, c, hot, sh);   // overlaps the epoch just published
   }
   if (threadIdx.x == 0) { atomicExch(P.abort_flag, 1); }
   return false;
@@ -1482,7 +1547,7 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
     size_t r = i % P.Npad;
     P.ids_tree[i] = r < (size_t)P.N ? 0 : BK_LIMBO;
   }
-  for (size_t i = tid; i < (size_t)P.C * P.R * P.ntiles; i += nth) P.rowcnt[i] = 0u;
+  for (size_t i = tid; i < (size_t)P.C * P.R * P.cnt_stride; i += nth) P.rowcnt[i] = 0u;
   for (size_t i = tid; i < (size_t)P.C * P.P * BK_ACC_STRIDE; i += nth) P.accL[i] = 0ull;
   for (size_t i = tid; i < (size_t)P.C * BK_ACC0_WORDS; i += nth) P.acc0[i] = 0ull;
   for (size_t i = tid; i < (size_t)P.C * P.m; i += nth) {
@@ -1606,7 +1671,7 @@ static int make_layout(const bk_settings* s, Layout* L) {
   CARVE(qst, C * Npad * 4);
   CARVE(ids_tree, C * m * Npad);
   CARVE(rows, C * R * Npad);
-  CARVE(rowcnt, C * R * (size_t)L->ntiles * 4);
+  CARVE(rowcnt, C * R * (size_t)((L->ntiles + 3) & ~3) * 4);   // rows padded to 16 bytes for 128-bit loads
   CARVE(wf_mean, C * Npad * 4);
   CARVE(wf_m2, C * Npad * 4);
   CARVE(parts, C * 2 * P * sizeof(DParticle));
@@ -1665,7 +1730,7 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   P.N = s->n_rows; P.Npad = L.Npad; P.p = s->n_cols; P.m = s->n_trees; P.P = s->n_particles;
   P.C = s->n_chains * (s->n_groups > 1 ? s->n_groups : 1);
   P.G = s->n_groups > 1 ? s->n_groups : 1;
-  P.R = L.R; P.ntiles = L.ntiles; P.lik = s->likelihood; P.trace_cap = s->trace_capacity > 0 ? s->trace_capacity : 0;
+  P.R = L.R; P.ntiles = L.ntiles; P.cnt_stride = (L.ntiles + 3) & ~3; P.lik = s->likelihood; P.trace_cap = s->trace_capacity > 0 ? s->trace_capacity : 0;
   P.batch_tune = s->batch_tune < 1 ? 1 : s->batch_tune; P.batch_post = s->batch_post < 1 ? 1 : s->batch_post;
   P.qscale = ldexpf(1.0f, s->qshift); P.inv_qscale = ldexp(1.0, -s->qshift); P.init_leaf = s->init_leaf;
   P.inv_qm = P.inv_qscale / (double)s->n_trees;

@@ -165,6 +165,7 @@ static_assert(sizeof(ChainSync) == 128, "ChainSync layout");
 struct Params {
   int32_t N, Npad, p, m, P, C, R, ntiles;   // C = chains * groups ("virtual chains": one forest + one sum-of-trees row each)
   int32_t G;                               // output groups per chain (separate trees); y has G rows
+  int32_t cnt_stride;                      // ntiles rounded up to a multiple of 4 (row stride of rowcnt)
   int32_t fastF, fast_stride;   // nodes per particle kept in the control CTA's shared memory; bytes per particle there
   int32_t lik, trace_cap, batch_tune, batch_post;
   float qscale, init_leaf;
@@ -178,7 +179,7 @@ struct Params {
   int32_t* qst;     // [C][Npad]
   uint8_t* ids_tree;   // [C][m][Npad]
   uint8_t* rows;       // [C][R][Npad]
-  uint32_t* rowcnt;    // [C][R][ntiles]
+  uint32_t* rowcnt;    // [C][R][cnt_stride]
   float* wf_mean;      // [C][Npad]
   float* wf_m2;        // [C][Npad]
   DParticle* parts;    // [C][2][P]
