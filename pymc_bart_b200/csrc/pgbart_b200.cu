@@ -61,8 +61,8 @@
 #define BLOCK_SYNC() asm volatile("barrier.sync 0;" ::: "memory")
 // The control CTA of a chain runs with its first 256 threads only (the other warps exit at once):
 // barrier 1 with an explicit count, so a control-stage barrier waits for 8 warps, not 32.
-#define BK_CTRL_THREADS 256
-#define CTRL_SYNC() asm volatile("barrier.sync 1, 256;" ::: "memory")
+#define BK_CTRL_THREADS 512
+#define CTRL_SYNC() asm volatile("barrier.sync 1, 512;" ::: "memory")
 // worker group g uses barrier 2+g with BK_GROUP_THREADS arrivals
 #define GROUP_SYNC(g) asm volatile("barrier.sync %0, %1;" ::"r"(2 + (g)), "n"(BK_GROUP_THREADS) : "memory")
 #ifndef BK_PROFILE_CTRL
