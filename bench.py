@@ -287,6 +287,11 @@ def main():
         ms_kernel = float(np.mean(step_ms))
         bytes_per_launch = algorithmic_bytes(N, grow / steps, tupd / steps, tune_upd / steps, lik)
         achieved = bytes_per_launch / (ms_kernel / 1e3) / 1e9
+        traffic = None
+        try:   # DRAM bytes per launch of the same command under `ncu --set full` (profiles/, committed)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         line = {
             "metric": "PGBART draws/sec", "value": value, "unit": "draws/s", "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -305,7 +310,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "draws/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "kernel": "pgbart_step_kernel",
                          "kernel_ms": ms_kernel},
             "clocks": clk,
