@@ -187,7 +187,6 @@ struct GroupShared {
   // atomic per (job, statistic) — the L2 sees groups x jobs x 5 atomics per epoch instead of tiles x jobs x 5 on a
   // handful of lines
   unsigned acc[BK_MAX_PARTICLES * 16];   // [job][BK_LIMBS] 32-bit limbs, see round_unit
-  Job jobs[BK_MAX_PARTICLES];   // the epoch's job list, one copy per group
   float old_vals[256];
   float new_vals[256];
   float pro_vals[256];
@@ -1027,8 +1026,8 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     }
   }
   for (int ji = job_lo; ji < job_hi; ++ji) {
-    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // the group's shared-memory copy of the job list
-    const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // the chain's job list in L2, issued with the tile loads
+    const int4 j0 = __ldcg(jp), j1 = __ldcg(jp + 1), j2 = __ldcg(jp + 2);
     const int kind = j0.x, src_row = j0.z, dst_row = j0.w;
     const int node = j1.x, var = j1.y; const float split = __int_as_float(j1.z); const int left_id = j1.w;
     const int next_node = j2.x, rule = j2.y, sparse = j2.z;
@@ -1142,7 +1141,7 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
   }
   for (int ji = job_lo; ji < job_hi; ++ji) {
     const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
-    const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
+    const int4 j0 = __ldcg(jp), j1 = __ldcg(jp + 1), j2 = __ldcg(jp + 2);
     const int src_row = j0.z;
     const float vl = __int_as_float(j1.z), vr = __int_as_float(j2.y);
     const unsigned left_id = (unsigned)j1.w;
@@ -1361,13 +1360,13 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
           const int c = P.C >= BK_NGROUPS ? c_first + idx * c_step : c_first;
           if (sh.fin[c]) continue;
           ChainSync* sy = P.sync + c;
-          const unsigned ep = ld_relaxed_u32(reinterpret_cast<const unsigned*>(&sy->ticket));   // epoch word, released after desc
-          if (ep == sh.seen[c]) continue;
-          if (lane == 0) fence_acq_rel_gpu();   // acquire (pairs with the control CTA's release store); drops stale L1 lines
-          __syncwarp();
+          // the descriptor {epoch, cmd, jobs, units} is ONE aligned 16-byte word, stored and loaded whole: a single
+          // L2 round trip tells the group that an epoch started and what it is
           const uint4 d = ld_volatile_v4(&sy->desc);
-          if (d.x != ep) continue;                                    // a newer epoch is being published: next poll
-          sh.seen[c] = ep;                                            // (all lanes store the same value)
+          if (d.x == sh.seen[c]) continue;
+          if (lane == 0) fence_acq_rel_gpu();   // acquire (pairs with the control CTA's release fence); drops stale L1 lines
+          __syncwarp();
+          sh.seen[c] = d.x;                                           // (all lanes store the same value)
           if ((d.y & 0xFFu) == BK_CMD_DONE) { sh.fin[c] = 1; n_finished++; continue; }
           wk.chain = c; wk.cmd = (int)(d.y & 0xFFu); wk.njobs = (int)d.z; wk.total = (int)d.w;
           const unsigned ns = (unsigned)servers_of(P.C, c);
@@ -1375,10 +1374,12 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
             wk.lo = (unsigned)w * ns + (unsigned)my_rank;             // first row tile of this group; stride W * ns
             wk.hi = (unsigned)W * ns;
           } else {
-            const unsigned clo = (unsigned)((unsigned long long)w * d.w / (unsigned)W);          // the CTA's pairs ...
-            const unsigned chi = (unsigned)((unsigned long long)(w + 1) * d.w / (unsigned)W);
-            wk.lo = clo + (unsigned)((unsigned long long)(chi - clo) * (unsigned)my_rank / ns);        // ... split over its groups
-            wk.hi = clo + (unsigned)((unsigned long long)(chi - clo) * (unsigned)(my_rank + 1) / ns);
+            // floor(w * T / W) in 32-bit arithmetic: T = q * W + r
+            const unsigned Tq = d.w / (unsigned)W, Tr = d.w - Tq * (unsigned)W;
+            const unsigned clo = (unsigned)w * Tq + ((unsigned)w * Tr) / (unsigned)W;            // the CTA's pairs ...
+            const unsigned chi = (unsigned)(w + 1) * Tq + ((unsigned)(w + 1) * Tr) / (unsigned)W;
+            wk.lo = clo + ((chi - clo) * (unsigned)my_rank) / ns;                                    // ... split over its groups
+            wk.hi = clo + ((chi - clo) * (unsigned)(my_rank + 1)) / ns;
           }
           next = (idx + 1) % n_mine;
 #ifdef BK_PROFILE_CTRL
@@ -1401,13 +1402,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
     const Work wk = sh.work;
     if (wk.exit_now) return;
     if (wk.cmd == BK_CMD_ROUND || wk.cmd == BK_CMD_LL) {
-      {
-        const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[wk.chain].jobs[(w * BK_NGROUPS + g) % BK_JOB_COPIES]);   // readers spread over the copies
-        uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
-        for (int i = tid; i < wk.njobs * 3; i += BK_GROUP_THREADS) d4[i] = __ldcg(g4 + i);
-      }
-      GROUP_SYNC(g);
-      const Job* jobs = sh.jobs;
+      const Job* jobs = P.ctl[wk.chain].jobs[(w * BK_NGROUPS + g) % BK_JOB_COPIES];   // readers spread over the copies (L2)
       const unsigned nwarp = BK_GROUP_THREADS >> 5;
       const unsigned chunk = (wk.hi - wk.lo + nwarp - 1u) / nwarp;   // pairs per warp
       unsigned lo = wk.lo + (unsigned)warp * chunk;
@@ -1424,7 +1419,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
       for (int i = tid; i < wk.njobs * BK_ACC_STRIDE; i += BK_GROUP_THREADS) {
         const int ji = i / BK_ACC_STRIDE, k = i % BK_ACC_STRIDE;
         const unsigned long long v = limbs_to_stat(sh.acc + ji * BK_LIMBS, k);
-        if (v) red_add_u64(P.accL + ((size_t)wk.chain * P.P + jobs[ji].slot) * BK_ACC_STRIDE + k, v);
+        if (v) red_add_u64(P.accL + ((size_t)wk.chain * P.P + __ldcg(&jobs[ji].slot)) * BK_ACC_STRIDE + k, v);
       }
       GROUP_SYNC(g);
       for (int i = tid; i < wk.njobs * BK_LIMBS; i += BK_GROUP_THREADS) sh.acc[i] = 0u;
@@ -1486,7 +1481,6 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
         fin = 1;
         epoch += 1;
         st_volatile_v4(&sy->desc, make_uint4(epoch, (unsigned)BK_CMD_DONE, 0u, 0u));   // tells the workers this chain is finished
-        st_release_u32(reinterpret_cast<unsigned*>(&sy->ticket), epoch);
       } else {
         const int nj = hot->n_jobs;
         const int total = (cmd == BK_CMD_ROUND || cmd == BK_CMD_LL) ? nj * P.ntiles : sweep_tiles;
@@ -1494,10 +1488,10 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
 #ifdef BK_PROFILE_CTRL
         *reinterpret_cast<volatile unsigned long long*>(&sy->pad[1]) = globaltimer_ns();
 #endif
-        // jobs, accumulators, rows bookkeeping written by this CTA happen-before the epoch word (release, cumulative
-        // over the CTA barrier above); the descriptor is complete before the epoch word changes
+        // jobs, accumulators, rows bookkeeping written by this CTA happen-before the descriptor: release fence
+        // (cumulative over the CTA barrier above), then one 16-byte store
+        fence_acq_rel_gpu();
         st_volatile_v4(&sy->desc, make_uint4(epoch, (unsigned)cmd, (unsigned)nj, (unsigned)total));
-        st_release_u32(reinterpret_cast<unsigned*>(&sy->ticket), epoch);
       }
       s_flag = fin;
       const unsigned long long q3 = globaltimer_ns();
