@@ -187,6 +187,7 @@ struct GroupShared {
   // atomic per (job, statistic) — the L2 sees groups x jobs x 5 atomics per epoch instead of tiles x jobs x 5 on a
   // handful of lines
   unsigned acc[BK_MAX_PARTICLES * 16];   // [job][BK_LIMBS] 32-bit limbs, see round_unit
+  Job jobs[BK_MAX_PARTICLES];   // the epoch's job list, one copy per group
   float old_vals[256];
   float new_vals[256];
   float pro_vals[256];
@@ -1026,8 +1027,8 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     }
   }
   for (int ji = job_lo; ji < job_hi; ++ji) {
-    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // the chain's job list in L2, issued with the tile loads
-    const int4 j0 = __ldcg(jp), j1 = __ldcg(jp + 1), j2 = __ldcg(jp + 2);
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);   // the group's shared-memory copy of the job list
+    const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
     const int kind = j0.x, src_row = j0.z, dst_row = j0.w;
     const int node = j1.x, var = j1.y; const float split = __int_as_float(j1.z); const int left_id = j1.w;
     const int next_node = j2.x, rule = j2.y, sparse = j2.z;
@@ -1141,7 +1142,7 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
   }
   for (int ji = job_lo; ji < job_hi; ++ji) {
     const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
-    const int4 j0 = __ldcg(jp), j1 = __ldcg(jp + 1), j2 = __ldcg(jp + 2);
+    const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
     const int src_row = j0.z;
     const float vl = __int_as_float(j1.z), vr = __int_as_float(j2.y);
     const unsigned left_id = (unsigned)j1.w;
@@ -1402,7 +1403,13 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
     const Work wk = sh.work;
     if (wk.exit_now) return;
     if (wk.cmd == BK_CMD_ROUND || wk.cmd == BK_CMD_LL) {
-      const Job* jobs = P.ctl[wk.chain].jobs[(w * BK_NGROUPS + g) % BK_JOB_COPIES];   // readers spread over the copies (L2)
+      {
+        const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[wk.chain].jobs[(w * BK_NGROUPS + g) % BK_JOB_COPIES]);   // readers spread over the copies
+        uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
+        for (int i = tid; i < wk.njobs * 3; i += BK_GROUP_THREADS) d4[i] = __ldcg(g4 + i);
+      }
+      GROUP_SYNC(g);
+      const Job* jobs = sh.jobs;
       const unsigned nwarp = BK_GROUP_THREADS >> 5;
       const unsigned chunk = (wk.hi - wk.lo + nwarp - 1u) / nwarp;   // pairs per warp
       unsigned lo = wk.lo + (unsigned)warp * chunk;
@@ -1419,7 +1426,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
       for (int i = tid; i < wk.njobs * BK_ACC_STRIDE; i += BK_GROUP_THREADS) {
         const int ji = i / BK_ACC_STRIDE, k = i % BK_ACC_STRIDE;
         const unsigned long long v = limbs_to_stat(sh.acc + ji * BK_LIMBS, k);
-        if (v) red_add_u64(P.accL + ((size_t)wk.chain * P.P + __ldcg(&jobs[ji].slot)) * BK_ACC_STRIDE + k, v);
+        if (v) red_add_u64(P.accL + ((size_t)wk.chain * P.P + jobs[ji].slot) * BK_ACC_STRIDE + k, v);
       }
       GROUP_SYNC(g);
       for (int i = tid; i < wk.njobs * BK_LIMBS; i += BK_GROUP_THREADS) sh.acc[i] = 0u;

@@ -131,3 +131,24 @@ def test_multi_output_api_shapes_and_prediction():
     with pytest.raises(NotImplementedError):
         pmb.PGBART([pmb.BART("s", X, y, m=3, shape=(2, 300))])       # shared-tree multi-output
     out["step"].close()
+
+
+def test_bernoulli_api_recovers_the_logit():
+    """BASELINE.json configs[2] through the public API: 0/1 response, PGBART(likelihood="bernoulli"); the posterior
+    mean of the BART variable is the logit (tests/test_bart.py:150-164 checks recovery the same way)."""
+    import pymc_bart_b200 as pmb
+
+    X, y, f = friedman(4000, 8, 3, kind="bernoulli")
+    mu = pmb.BART("mu", X, y, m=30)
+    out = pmb.sample(mu, tune=80, draws=40, chains=2, num_particles=12, seed=3, likelihood="bernoulli")
+    logit = out["posterior"].mean(axis=(0, 1))
+    assert logit.shape == (4000,) and np.all(np.isfinite(logit))
+    pr = 1 / (1 + np.exp(-(f - 14.4) / 4.9))
+    ll = float(np.mean(y * logit - np.logaddexp(0, logit)))
+    ll_true = float(np.mean(y * np.log(pr) + (1 - y) * np.log(1 - pr)))
+    ll0 = float(np.mean(y * 0.5 - np.logaddexp(0, 0.5)))             # the initial constant fit (Y.mean() as a logit)
+    assert ll > ll0 + 0.08 and abs(ll - ll_true) < 0.03
+    assert np.corrcoef(logit, f)[0, 1] > 0.8
+    with pytest.raises(ValueError):
+        pmb.PGBART([pmb.BART("bad", X, y + 0.25, m=5)], likelihood="bernoulli")
+    out["step"].close()
