@@ -1456,7 +1456,8 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
   unsigned issued = 0, epoch = 0;
   const int n_workers = (gridDim.x - P.C) * servers_of(P.C, c);   // serving groups: each reports every epoch once
   const int sweep_tiles = (P.Npad + BK_COMMIT_TILE - 1) / BK_COMMIT_TILE;
-  unsigned long long t_wait = 0, t_ctrl = 0, t_pub = 0, t_begin = 0;
+  unsigned long long t_wait = 0, t_ctrl = 0, t_pub = 0, t_begin = 0, t_wait_sweep = 0;
+  int last_cmd = BK_CMD_IDLE;
   if (threadIdx.x == 0) t_begin = globaltimer_ns();
   for (int phase = 0; phase < max_phases; ++phase) {
     unsigned long long q0 = 0, q1 = 0, q2 = 0;
@@ -1503,6 +1504,8 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       s_flag = fin;
       const unsigned long long q3 = globaltimer_ns();
       t_wait += q1 - q0; t_ctrl += q2 - q1; t_pub += q3 - q2;
+      if (last_cmd == BK_CMD_SWEEP) t_wait_sweep += q1 - q0;
+      last_cmd = cmd;
       if (fin) {
         ctl->hot = s_hot;                   // write the scalar state back
 #ifdef BK_PROFILE_CTRL
@@ -1511,6 +1514,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
         bk_step_stats* st = P.stats + c;
         st->us_control = (int32_t)(t_ctrl / 1000ull); st->us_data = (int32_t)(t_wait / 1000ull);
         st->us_sync = (int32_t)(t_pub / 1000ull); st->us_total = (int32_t)((q3 - t_begin) / 1000ull);
+        st->reserved[0] = (int32_t)(t_wait_sweep / 1000ull);   // part of us_data spent waiting for SWEEP epochs
         __threadfence();
       }
     }

@@ -15,7 +15,7 @@ s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains, likeli
 dev = DeviceSampler(s, X, y)
 for i in range(5): dev.step(True, 1.0)
 import ctypes
-acc = np.zeros(8)
+acc = np.zeros(9)
 sub = np.zeros(8)
 for i in range(steps):
     _, st = dev.step(i < steps // 2, 1.0)
@@ -23,10 +23,10 @@ for i in range(steps):
     dev.lib.bk_debug_timers.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     dev.lib.bk_debug_timers(dev.h, 0, buf)
     sub += np.array(list(buf), dtype=np.float64) / 1e3
-    acc += [st[0].us_control, st[0].us_data, st[0].us_sync, st[0].us_total, st[0].phases, st[0].rounds, st[0].grow_events, st[0].count_passes]
+    acc += [st[0].us_control, st[0].us_data, st[0].us_sync, st[0].us_total, st[0].phases, st[0].rounds, st[0].grow_events, st[0].count_passes, st[0].reserved[0]]
 acc /= steps
 print(f"{cfg} chains={chains}: per step us control={acc[0]:.0f} data={acc[1]:.0f} sync={acc[2]:.0f} total={acc[3]:.0f} phases={acc[4]:.1f} "
-      f"rounds={acc[5]:.1f} grow={acc[6]:.1f} count_passes={acc[7]:.1f}; per phase us control={acc[0]/acc[4]:.1f} data={acc[1]/acc[4]:.1f} sync={acc[2]/acc[4]:.1f}")
+      f"rounds={acc[5]:.1f} grow={acc[6]:.1f} count_passes={acc[7]:.1f} sweep_wait={acc[8]:.0f}us; per phase us control={acc[0]/acc[4]:.1f} data={acc[1]/acc[4]:.1f} sync={acc[2]/acc[4]:.1f}")
 
 sub /= steps
 print("control sub-steps us/step: finalize=%.0f weights=%.0f resample=%.0f copy=%.0f pop=%.0f select=%.0f jobs=%.0f finish+init=%.0f" % tuple(sub))
