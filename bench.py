@@ -52,6 +52,14 @@ def friedman(N, p, seed, lik=0, groups=1):
     return X, y
 
 
+def workload_name(name, cfg, trees_per_draw):
+    """One string for both arms (ours and --impl reference), so that the driver compares like with like."""
+    N, p, m, P, chains, seed, lik, groups = cfg
+    return (f"{name}: Friedman N={N} p={p} m={m} trees particles={P} chains/GPU={chains} "
+            f"{'Bernoulli-logit' if lik else 'Normal'} likelihood{f', {groups} outputs with separate trees' if groups > 1 else ''}, "
+            f"sigma=1 fixed, batch=(0.1,0.1) -> {trees_per_draw} trees/draw, depth prior alpha(1+d)^-beta (bart.py:107-109)")
+
+
 def algorithmic_bytes(N, grow_events, tree_updates, tune_updates, lik=0):
     """per grow event 14N (+9N second pass for non-Gaussian likelihoods); per tree update 23N
     (+16N while tuning)."""
@@ -138,8 +146,9 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": "PGBART draws/sec", "value": val, "unit": "draws/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+i64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: Friedman N={N} p={p} m={m} particles={P} chains={n_chains} (tuning draws)",
-                   "note": "CPU restatement oracle/pgbart_oracle.c (bartrs unavailable offline), ctypes releases the GIL"},
+        "config": {"workload": workload_name(args.config, cfg, s.batch_tune),
+                   "note": f"CPU restatement oracle/pgbart_oracle.c (bartrs unavailable offline), {n_chains} chains x {groups} output "
+                           f"groups on {threads} host threads (ctypes releases the GIL), tuning draws only"},
         "cpu_baseline": {"value": val, "unit": "draws/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} tuning draws x {n_chains} chains after {warm} warm-up"},
         "e2e": {"value": val, "unit": "draws/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -297,10 +306,8 @@ def main():
             "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i64", "data": "synthetic",
             "config": {
-                "workload": f"{args.config}: Friedman N={N} p={p} m={m} trees particles={P} chains/GPU={chains} "
-                            f"{'Bernoulli-logit' if lik else 'Normal'} likelihood{f', {groups} outputs with separate trees' if groups > 1 else ''}, sigma=1 fixed, "
-                            f"batch=(0.1,0.1) -> {s.batch_tune} trees/draw, depth prior alpha(1+d)^-beta (bart.py:107-109); "
-                            f"{n_tune} tuning + {steps - n_tune} post-tuning draws timed",
+                "workload": workload_name(args.config, cfg, s.batch_tune),
+                "draws_timed": f"{n_tune} tuning + {steps - n_tune} post-tuning",
                 "l2": "256 MB fill between timed steps (L2 flushed)" if flush is not None else "no flush (working set stays in L2)",
                 "grow_events_per_tree_update": g_all / max(t_all, 1.0),
                 "rounds_per_tree_update": rounds / max(tupd, 1),
