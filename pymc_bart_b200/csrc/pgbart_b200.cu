@@ -166,7 +166,15 @@ struct CtlShared {
   uint32_t pre_ures;
   int pre_prop_tree, pre_prop_round;   // tag of pre_u1 / pre_v / pre_u3
   int pre_z_tree, pre_z_round;         // tag of pre_zl / pre_zr / pre_ures
+  // Deferred particle copy: after resampling, propose() reads every slot's state THROUGH src_slot (its ancestor in
+  // the current buffer) and only records the new queue head; the copy into the other buffer happens in the shadow
+  // of the epoch it published (apply_pending_copy).
+  int copy_pending;
+  int src_slot[BK_MAX_PARTICLES];
+  int s_qh[BK_MAX_PARTICLES];
   double cum_prior[BK_CUM_SMEM];   // normalised cumulative split prior (first BK_CUM_SMEM columns)
+  double p_leaf[64];               // depth prior table, depths 0..63 (deeper: global)
+  signed char rules[BK_CUM_SMEM];  // split rule of the first BK_CUM_SMEM columns
   int live;
   int win;
   unsigned pick;
@@ -286,7 +294,36 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
   const int per = (n4 + 31) >> 5;                   // groups per lane
   unsigned off = k;
   int tile = -1;
-  {
+  if (per <= 4) {
+    // small N: a lane keeps its (at most 16) tile counts in registers, so the lane that owns the k-th member walks
+    // them itself — one L2 round trip for the whole search
+    uint4 v[4];
+    unsigned sum = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i4 = lane * per + u;
+      v[u] = (u < per && i4 < n4) ? __ldcg(cnt4 + i4) : make_uint4(0u, 0u, 0u, 0u);
+      sum += v[u].x + v[u].y + v[u].z + v[u].w;
+    }
+    const unsigned incl = warp_incl_scan_u32(sum, lane), excl = incl - sum;
+    const unsigned b = __ballot_sync(0xffffffffu, off >= excl && off < incl);
+    if (b != 0u) {
+      const int src = __ffs(b) - 1;
+      unsigned o2 = off - excl;     // valid in lane src
+      int t = 0;
+      bool found = false;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned cs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!found) { if (o2 < cs[e]) { found = true; t = u * 4 + e; } else o2 -= cs[e]; }
+        }
+      }
+      tile = __shfl_sync(0xffffffffu, src * per * 4 + t, src);
+      off = __shfl_sync(0xffffffffu, o2, src);
+    }
+  } else {
     unsigned sum = 0u;
     for (int j0 = 0; j0 < per; j0 += 8) {   // eight independent 128-bit loads in flight per lane
       uint4 v[8];
@@ -474,10 +511,24 @@ __device__ __forceinline__ int draw_variable_dev(const Params& P, int c, const C
   return lo;
 }
 
+__device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot);
+
+// Executes a deferred particle copy (see CtlShared::copy_pending): buffer `buf` -> `buf ^ 1` through src_slot, then
+// the queue heads propose() recorded; flips the buffer.  All control threads.
+__device__ void apply_pending_copy(const Params& P, int c, ChainHot* hot, CtlShared& sh) {
+  if (!sh.copy_pending) return;     // (uniform: shared flag, read after a barrier)
+  const int buf = hot->buf;
+  copy_particles(P, c, buf, sh.src_slot);
+  if (threadIdx.x >= 1 && (int)threadIdx.x < P.P) pref(P, c, buf ^ 1, threadIdx.x).h->q_head = sh.s_qh[threadIdx.x];
+  if (threadIdx.x == 0) { hot->buf = buf ^ 1; sh.copy_pending = 0; }
+  CTRL_SYNC();
+}
+
 // Runs right after a ROUND epoch has been published (all control threads), overlapping the workers.
 __device__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& sh) {
   const int round = hot->round, t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
+  apply_pending_copy(P, c, hot, sh);
   const int q = threadIdx.x;
   if (q >= 1 && q < P.P) {
     // leaf-value normals of this round (used by finalize_grows when the epoch is done) for the slots that grow
@@ -506,15 +557,17 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
   const int q = threadIdx.x;
   if (q < P.P) { sh.s_kind[q] = 0; sh.s_next[q] = -1; sh.s_j[q] = -1; }
   if (q >= 1 && q < P.P) {
-    const PRef S = pref(P, c, buf, q);
+    const bool deferred = sh.copy_pending != 0;
+    const PRef S = pref(P, c, buf, deferred ? sh.src_slot[q] : q);   // the slot's state-to-be = its ancestor's state
     int nn = S.h->n_nodes, qh = S.h->q_head, row = S.h->row;
     int kind = 0, j = -1, v = -1, next = -1;
     unsigned k = 0;
     if (qh < nn) {
-      j = qh; qh += 1; S.h->q_head = qh;
+      j = qh; qh += 1;
+      if (!deferred) S.h->q_head = qh;   // (deferred: several slots may share this ancestor; written after the copy)
       const int depth = S.node(j).depth;
       const int n = S.node(j).n;
-      double pl = depth < BK_MAX_DEPTH_TABLE ? P.p_leaf[depth] : 1.0;
+      double pl = depth < 64 ? sh.p_leaf[depth] : (depth < BK_MAX_DEPTH_TABLE ? P.p_leaf[depth] : 1.0);
       const bool pre = sh.pre_prop_tree == t && sh.pre_prop_round == round;   // draws made in the shadow of the last epoch
       double u1 = pre ? sh.pre_u1[q] : bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
       if (u1 > pl && nn + 2 <= BK_MAX_NODES) {
@@ -529,6 +582,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       else { next = qh < nn ? qh : -1; if (next >= 0) kind = 2; }
     }
     sh.s_sparse[q] = (j >= 0 && (long long)S.node(j).n * 8 < (long long)P.N) ? 1 : 0;
+    sh.s_qh[q] = qh;
     sh.s_kind[q] = kind; sh.s_j[q] = j; sh.s_v[q] = v; sh.s_k[q] = k; sh.s_next[q] = next; sh.s_row[q] = row; sh.s_nn[q] = nn;
     bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + q - 1);
     if (rec) {
@@ -610,7 +664,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
         Job jb;
         jb.kind = BK_JOB_PARTITION; jb.slot = t; jb.src_row = sh.s_row[t]; jb.dst_row = s_free[rank_g];
         jb.node = sh.s_j[t]; jb.var = sh.s_v[t]; jb.split = sh.s_split[t]; jb.left_id = sh.s_nn[t];
-        jb.next_node = sh.s_next[t]; jb.rule = P.rules[sh.s_v[t]]; jb.pad[0] = sh.s_sparse[t]; jb.pad[1] = 0;
+        jb.next_node = sh.s_next[t]; jb.rule = sh.s_v[t] < BK_CUM_SMEM ? (int)sh.rules[sh.s_v[t]] : P.rules[sh.s_v[t]]; jb.pad[0] = sh.s_sparse[t]; jb.pad[1] = 0;
         sh.row_cnt_node[jb.dst_row] = jb.next_node;
         sh.jobs[rank_g] = jb;
       } else if (is_cnt) {
@@ -923,19 +977,15 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       TSUB(2);
       MARK(133);
       // anc[i] indexes particles 1..P-1; convert to slot -> source slot
-      __shared__ int s_src[BK_MAX_PARTICLES];
       if ((int)threadIdx.x < P.P) {
         int s = threadIdx.x;
-        s_src[s] = s == 0 ? 0 : sh.anc[s - 1] + 1;
-        if (s >= 1) { bk_trace_rec* rec = trace_at(P, c, rbase + s - 1); if (rec) rec->ancestor = s_src[s]; }
+        sh.src_slot[s] = s == 0 ? 0 : sh.anc[s - 1] + 1;
+        if (s >= 1) { bk_trace_rec* rec = trace_at(P, c, rbase + s - 1); if (rec) rec->ancestor = sh.src_slot[s]; }
       }
+      if (threadIdx.x == 0) { sh.copy_pending = 1; hot->round += 1; }   // the copy itself runs in the epoch's shadow
       CTRL_SYNC();
-      MARK(134);
-      copy_particles(P, c, buf, s_src);
       TSUB(3);
-      MARK(135);
-      if (threadIdx.x == 0) { hot->buf = buf ^ 1; hot->round += 1; }
-      CTRL_SYNC();
+      (void)buf;
     }
     MARK(140);
     int nj = propose(P, c, ctl, hot, sh);
@@ -946,6 +996,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       CTRL_SYNC();
       return;
     }
+    apply_pending_copy(P, c, hot, sh);   // no epoch to hide behind: the next round starts right away
   }
 }
 
@@ -1448,7 +1499,11 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
   ChainCtl* ctl = P.ctl + c;
   ChainHot* hot = &s_hot;
   ChainSync* sy = P.sync + c;
-  if (threadIdx.x == 0) { s_hot = ctl->hot; sh.pre_prop_tree = -1; sh.pre_z_tree = -1; }   // persistent scalars -> shared memory for the whole step
+  if (threadIdx.x == 0) { s_hot = ctl->hot; sh.pre_prop_tree = -1; sh.pre_z_tree = -1; sh.copy_pending = 0; }   // persistent scalars -> shared memory for the whole step
+  // read-only tables of the round path: the control CTA's L1 is dropped by every acquire fence, so a global table
+  // costs an L2 round trip per phase
+  if (threadIdx.x < 64) sh.p_leaf[threadIdx.x] = P.p_leaf[threadIdx.x];
+  for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += BK_CTRL_THREADS) sh.rules[v] = (signed char)P.rules[v];
 #ifdef BK_PROFILE_CTRL
   if (threadIdx.x < 32) s_cdbg[threadIdx.x] = 0ull;
 #endif
