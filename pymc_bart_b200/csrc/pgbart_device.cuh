@@ -17,7 +17,10 @@
 #ifndef BK_CTA_THREADS
 #define BK_CTA_THREADS 1024
 #endif
-#define BK_NGROUPS 4                         // independent worker groups per worker CTA
+#ifndef BK_NGROUPS
+#define BK_NGROUPS 4
+#endif
+//                       // independent worker groups per worker CTA
 #define BK_GROUP_THREADS (BK_CTA_THREADS / BK_NGROUPS)
 #define BK_COMMIT_TILE (BK_GROUP_THREADS * 4)  // rows per group pass in the commit/prologue sweep
 #define BK_MAX_GROUP 16            // particles that share one register-resident (q_r, q_st) tile
@@ -41,7 +44,7 @@
 #define BK_ST_WAIT_LL 4
 
 #ifndef BK_JOB_COPIES
-#define BK_JOB_COPIES 8
+#define BK_JOB_COPIES 1
 #endif
 #define BK_JOB_PARTITION 1
 #define BK_JOB_COUNT 2
