@@ -593,100 +593,97 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
   }
   CTRL_SYNC();
   TSUB(4);
-  // split values: one warp per growing particle
-  {
-    const int warp = threadIdx.x >> 5, nwarps = BK_CTRL_THREADS >> 5, lane = threadIdx.x & 31;
-    __shared__ int s_err;
-    if (threadIdx.x == 0) s_err = 0;
-    CTRL_SYNC();
-    // warps 1..7 only: warp 0 can be split (see normalise_and_resample) and would crawl through the shuffles
-    for (int s = warp; s < P.P && warp > 0; s += nwarps - 1) {
-      if (sh.s_kind[s] != 1) continue;
-      float sv;
-      if (sh.s_row[s] == BK_ROW_VIRTUAL) {
-        sv = __ldg(P.X + (size_t)sh.s_v[s] * P.Npad + sh.s_k[s]);
-      } else {
-        int err = 0;
-        if (sh.row_cnt_node[sh.s_row[s]] != sh.s_j[s]) err |= 1;
-        sv = select_split(P, c, sh.s_row[s], sh.s_j[s], sh.s_k[s], sh.s_v[s], &err);
-        if (lane == 0 && err) atomicOr(&s_err, err);
-      }
-      if (lane == 0) sh.s_split[s] = sv;
-    }
-      CTRL_SYNC();
-      if (threadIdx.x == 0 && s_err) hot->c_err |= s_err;
-  }
-  TSUB(5);
-  // rows + job list, built in parallel in shared memory:
-  //   free rows: ranks of the unused pool rows; growers: rank among the growing slots -> dst row;
-  //   count-only jobs are de-duplicated per source row with an exchange on row_cnt_node.
-  __shared__ int s_njobs;
+  // Two teams work side by side.  Team J (threads 0..255) allocates rows and assembles the job list in shared memory
+  // (free rows = ranks of the unused pool rows; growers: rank among the growing slots -> dst row; count-only jobs are
+  // de-duplicated per source row with an exchange on row_cnt_node), synchronising on its own named barrier.  Every
+  // other warp — and team J's warps 1..7 once they are done — takes growing slots from a shared counter and finds
+  // their split value (k-th member).  The split values are patched into the jobs after the joint barrier.
+  // Warp 0 never runs a selection: it can be split (see normalise_and_resample) and would crawl through the shuffles.
+#define J_SYNC() asm volatile("barrier.sync 14, 256;" ::: "memory")
+  __shared__ int s_njobs, s_err, s_next_sel;
   __shared__ int s_free[2 * BK_MAX_PARTICLES];
   __shared__ int s_warp_cnt[3][8];
-  if ((int)threadIdx.x < P.R) sh.row_used[threadIdx.x] = 0;
+  const int tx = threadIdx.x, lane = tx & 31, w = tx >> 5;
+  if (tx == 0) { s_err = 0; s_next_sel = 1; }
+  if (tx < P.R) sh.row_used[tx] = 0;
   CTRL_SYNC();
-  if (threadIdx.x >= 1 && (int)threadIdx.x < P.P && sh.s_row[threadIdx.x] >= 0) sh.row_used[sh.s_row[threadIdx.x]] = 1;
-  CTRL_SYNC();
-  {
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    // (i) count-job de-duplication, (ii) per-thread flags
-    int is_grow = 0, is_cnt = 0, is_free = 0;
-    if (t >= 1 && t < P.P) {
-      if (sh.s_kind[t] == 1) is_grow = 1;
-      else if (sh.s_kind[t] == 2 && sh.s_row[t] >= 0) {
-        const int old = atomicExch(&sh.row_cnt_node[sh.s_row[t]], sh.s_next[t]);
-        is_cnt = old != sh.s_next[t];
+  int is_grow = 0, is_cnt = 0, is_free = 0, rank_g = 0;
+  if (tx < 256) {   // ---- team J (R <= 256 and P <= 128: eight warps cover both index ranges)
+    if (tx >= 1 && tx < P.P) {
+      if (sh.s_row[tx] >= 0) sh.row_used[sh.s_row[tx]] = 1;
+      if (sh.s_kind[tx] == 1 && sh.s_row[tx] != BK_ROW_VIRTUAL && sh.row_cnt_node[sh.s_row[tx]] != sh.s_j[tx]) atomicOr(&s_err, 1);
+    }
+    J_SYNC();
+    if (tx >= 1 && tx < P.P) {
+      if (sh.s_kind[tx] == 1) is_grow = 1;
+      else if (sh.s_kind[tx] == 2 && sh.s_row[tx] >= 0) {
+        const int old = atomicExch(&sh.row_cnt_node[sh.s_row[tx]], sh.s_next[tx]);
+        is_cnt = old != sh.s_next[tx];
       }
     }
-    if (t < P.R) is_free = sh.row_used[t] ? 0 : 1;
+    if (tx < P.R) is_free = sh.row_used[tx] ? 0 : 1;
     __syncwarp();
-    if (t < 256) {   // R <= 256 and P <= 128: eight warps cover both index ranges
-      const unsigned bg = __ballot_sync(0xffffffffu, is_grow), bc = __ballot_sync(0xffffffffu, is_cnt),
-                     bf = __ballot_sync(0xffffffffu, is_free);
-      if (lane == 0) { s_warp_cnt[0][w] = __popc(bg); s_warp_cnt[1][w] = __popc(bc); s_warp_cnt[2][w] = __popc(bf); }
-      const unsigned below = (1u << lane) - 1u;
-      // stash intra-warp ranks in registers via shared scratch after the barrier below
-      s_free[t] = (__popc(bf & below) << 16) | (__popc(bg & below) << 8) | __popc(bc & below);
+    const unsigned bg = __ballot_sync(0xffffffffu, is_grow), bc = __ballot_sync(0xffffffffu, is_cnt),
+                   bf = __ballot_sync(0xffffffffu, is_free);
+    if (lane == 0) { s_warp_cnt[0][w] = __popc(bg); s_warp_cnt[1][w] = __popc(bc); s_warp_cnt[2][w] = __popc(bf); }
+    const unsigned below = (1u << lane) - 1u;
+    const int in_f = __popc(bf & below), in_g = __popc(bg & below), in_c = __popc(bc & below);
+    J_SYNC();
+    int off_g = 0, off_c = 0, off_f = 0, tot_g = 0;
+    for (int k = 0; k < 8; ++k) {
+      if (k < w) { off_g += s_warp_cnt[0][k]; off_c += s_warp_cnt[1][k]; off_f += s_warp_cnt[2][k]; }
+      tot_g += s_warp_cnt[0][k];
     }
-    CTRL_SYNC();
-    if (t < 256) {
-      int off_g = 0, off_c = 0, off_f = 0, tot_g = 0;
-      for (int k = 0; k < 8; ++k) {
-        if (k < w) { off_g += s_warp_cnt[0][k]; off_c += s_warp_cnt[1][k]; off_f += s_warp_cnt[2][k]; }
-        tot_g += s_warp_cnt[0][k];
-      }
-      const int packed = s_free[t];
-      const int rank_f = off_f + (packed >> 16), rank_g = off_g + ((packed >> 8) & 0xFF), rank_c = off_c + (packed & 0xFF);
-      CTRL_SYNC();   // everyone has read its packed ranks; s_free is reused as the free-row list
-      if (is_free) s_free[rank_f] = t;
-      CTRL_SYNC();
-      if (is_grow) {
-        Job jb;
-        jb.kind = BK_JOB_PARTITION; jb.slot = t; jb.src_row = sh.s_row[t]; jb.dst_row = s_free[rank_g];
-        jb.node = sh.s_j[t]; jb.var = sh.s_v[t]; jb.split = sh.s_split[t]; jb.left_id = sh.s_nn[t];
-        jb.next_node = sh.s_next[t]; jb.rule = sh.s_v[t] < BK_CUM_SMEM ? (int)sh.rules[sh.s_v[t]] : P.rules[sh.s_v[t]]; jb.pad[0] = sh.s_sparse[t]; jb.pad[1] = 0;
-        sh.row_cnt_node[jb.dst_row] = jb.next_node;
-        sh.jobs[rank_g] = jb;
-      } else if (is_cnt) {
-        Job jb;
-        jb.kind = BK_JOB_COUNT; jb.slot = t; jb.src_row = sh.s_row[t]; jb.dst_row = sh.s_row[t]; jb.node = -1; jb.var = 0;
-        jb.split = 0.0f; jb.left_id = 0; jb.next_node = sh.s_next[t]; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
-        sh.jobs[tot_g + rank_c] = jb;
-      }
-      if (t == 0) {
-        int tot_c = 0, tot_f = 0;
-        for (int k = 0; k < 8; ++k) { tot_c += s_warp_cnt[1][k]; tot_f += s_warp_cnt[2][k]; }
-        const int nj = tot_g + tot_c;
-        hot->n_jobs = nj; hot->n_grow = tot_g;
-        if (tot_c) hot->c_count_passes += tot_c;
-        if (tot_g > tot_f) hot->c_err |= 8;
-        s_njobs = nj;
-      }
-    } else {
-      CTRL_SYNC();
-      CTRL_SYNC();
+    const int rank_f = off_f + in_f, rank_c = off_c + in_c;
+    rank_g = off_g + in_g;
+    if (is_free) s_free[rank_f] = tx;
+    J_SYNC();
+    if (is_grow) {
+      Job jb;
+      jb.kind = BK_JOB_PARTITION; jb.slot = tx; jb.src_row = sh.s_row[tx]; jb.dst_row = s_free[rank_g];
+      jb.node = sh.s_j[tx]; jb.var = sh.s_v[tx]; jb.split = 0.0f; jb.left_id = sh.s_nn[tx];
+      jb.next_node = sh.s_next[tx]; jb.rule = sh.s_v[tx] < BK_CUM_SMEM ? (int)sh.rules[sh.s_v[tx]] : P.rules[sh.s_v[tx]]; jb.pad[0] = sh.s_sparse[tx]; jb.pad[1] = 0;
+      sh.row_cnt_node[jb.dst_row] = jb.next_node;
+      sh.jobs[rank_g] = jb;
+    } else if (is_cnt) {
+      Job jb;
+      jb.kind = BK_JOB_COUNT; jb.slot = tx; jb.src_row = sh.s_row[tx]; jb.dst_row = sh.s_row[tx]; jb.node = -1; jb.var = 0;
+      jb.split = 0.0f; jb.left_id = 0; jb.next_node = sh.s_next[tx]; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
+      sh.jobs[tot_g + rank_c] = jb;
+    }
+    if (tx == 0) {
+      int tot_c = 0, tot_f = 0;
+      for (int k = 0; k < 8; ++k) { tot_c += s_warp_cnt[1][k]; tot_f += s_warp_cnt[2][k]; }
+      const int nj = tot_g + tot_c;
+      hot->n_jobs = nj; hot->n_grow = tot_g;
+      if (tot_c) hot->c_count_passes += tot_c;
+      if (tot_g > tot_f) hot->c_err |= 8;
+      s_njobs = nj;
     }
   }
+  if (w > 0) {   // ---- split values: warps take growing slots from the shared counter
+    for (;;) {
+      int sl = 0;
+      if (lane == 0) sl = atomicAdd(&s_next_sel, 1);
+      sl = __shfl_sync(0xffffffffu, sl, 0);
+      if (sl >= P.P) break;
+      if (sh.s_kind[sl] != 1) continue;
+      float sv;
+      if (sh.s_row[sl] == BK_ROW_VIRTUAL) {
+        sv = __ldg(P.X + (size_t)sh.s_v[sl] * P.Npad + sh.s_k[sl]);
+      } else {
+        int err = 0;
+        sv = select_split(P, c, sh.s_row[sl], sh.s_j[sl], sh.s_k[sl], sh.s_v[sl], &err);
+        if (lane == 0 && err) atomicOr(&s_err, err);
+      }
+      if (lane == 0) sh.s_split[sl] = sv;
+    }
+  }
+  CTRL_SYNC();
+  if (is_grow) sh.jobs[rank_g].split = sh.s_split[tx];
+  if (tx == 0 && s_err) hot->c_err |= s_err;
+  TSUB(5);
+#undef J_SYNC
   CTRL_SYNC();
   {  // publish the job list: 48-byte descriptors stored by many threads
     const int nj = s_njobs;
