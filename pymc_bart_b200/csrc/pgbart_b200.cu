@@ -478,7 +478,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     }
     p0.h->n_nodes = nn; p0.h->q_head = nn; p0.h->row = BK_ROW_FOREST;
     p0.h->ssq = ssq; p0.h->lw = bern ? bk_bern_loglik(ssq) : bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
-    hot->buf = 0; hot->round = 0;
+    hot->buf = 0; hot->round = 0; sh.live = 0;
   }
   const int q = threadIdx.x;
   if (q >= 1 && q < P.P) {
@@ -555,7 +555,12 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
   const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   const int q = threadIdx.x;
+  __shared__ int s_njobs, s_err, s_next_sel;
+  __shared__ int s_free[2 * BK_MAX_PARTICLES];
+  __shared__ int s_warp_cnt[3][8];
   if (q < P.P) { sh.s_kind[q] = 0; sh.s_next[q] = -1; sh.s_j[q] = -1; }
+  if (q == 0) { s_err = 0; s_next_sel = 1; sh.live = 0; }
+  if (q < P.R) sh.row_used[q] = 0;
   if (q >= 1 && q < P.P) {
     const bool deferred = sh.copy_pending != 0;
     const PRef S = pref(P, c, buf, deferred ? sh.src_slot[q] : q);   // the slot's state-to-be = its ancestor's state
@@ -600,13 +605,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
   // their split value (k-th member).  The split values are patched into the jobs after the joint barrier.
   // Warp 0 never runs a selection: it can be split (see normalise_and_resample) and would crawl through the shuffles.
 #define J_SYNC() asm volatile("barrier.sync 14, 256;" ::: "memory")
-  __shared__ int s_njobs, s_err, s_next_sel;
-  __shared__ int s_free[2 * BK_MAX_PARTICLES];
-  __shared__ int s_warp_cnt[3][8];
   const int tx = threadIdx.x, lane = tx & 31, w = tx >> 5;
-  if (tx == 0) { s_err = 0; s_next_sel = 1; }
-  if (tx < P.R) sh.row_used[tx] = 0;
-  CTRL_SYNC();
   int is_grow = 0, is_cnt = 0, is_free = 0, rank_g = 0;
   if (tx < 256) {   // ---- team J (R <= 256 and P <= 128: eight warps cover both index ranges)
     if (tx >= 1 && tx < P.P) {
@@ -660,6 +659,13 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       if (tot_g > tot_f) hot->c_err |= 8;
       s_njobs = nj;
     }
+    J_SYNC();
+    {  // publish the job list (48-byte descriptors; the split values of the growers follow below)
+      const int nj = s_njobs;
+      const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
+      for (int i = tx; i < nj * 3 * BK_JOB_COPIES; i += 256)
+        reinterpret_cast<uint4*>(ctl->jobs[i / (nj * 3)])[i % (nj * 3)] = s4[i % (nj * 3)];
+    }
   }
   if (w > 0) {   // ---- split values: warps take growing slots from the shared counter
     for (;;) {
@@ -680,20 +686,16 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
     }
   }
   CTRL_SYNC();
-  if (is_grow) sh.jobs[rank_g].split = sh.s_split[tx];
+  if (is_grow) {
+    const float sv = sh.s_split[tx];
+    sh.jobs[rank_g].split = sv;
+    for (int k = 0; k < BK_JOB_COPIES; ++k) ctl->jobs[k][rank_g].split = sv;
+  }
   if (tx == 0 && s_err) hot->c_err |= s_err;
   TSUB(5);
 #undef J_SYNC
-  CTRL_SYNC();
-  {  // publish the job list: 48-byte descriptors stored by many threads
-    const int nj = s_njobs;
-    const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
-    for (int i = threadIdx.x; i < nj * 3 * BK_JOB_COPIES; i += BK_CTRL_THREADS)
-      reinterpret_cast<uint4*>(ctl->jobs[i / (nj * 3)])[i % (nj * 3)] = s4[i % (nj * 3)];
-  }
-  CTRL_SYNC();
   TSUB(6);
-  return s_njobs;
+  return s_njobs;   // (the caller's barrier orders the patched list before thread 0 publishes the epoch)
 }
 
 // apply the statistics of the finished ROUND to the particles that grew
@@ -849,16 +851,16 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
 __device__ void control_step(const Params& P, int c, int phase, int tune, const float* sigma_in, ChainHot* hot, CtlShared& sh) {
   const int first_phase = phase == 0;
   ChainCtl* ctl = P.ctl + c;
-  __shared__ int s_stage;
-  if (threadIdx.x == 0) {
-    if (first_phase) {
+  if (first_phase) {
+    if (threadIdx.x == 0) {
       hot->stage = BK_ST_START; hot->tune = tune; hot->sigma = sigma_in[c];
       hot->ll_inv2s2 = bk_normal_inv2s2(hot->sigma); hot->ll_c = bk_normal_const(hot->sigma, (double)P.N);
     }
-    s_stage = hot->stage;
+    CTRL_SYNC();
   }
-  CTRL_SYNC();
-  int stage = s_stage;
+  // (hot lives in shared memory; the caller's barrier ordered the previous phase's writes, and thread 0 changes the
+  // stage again only after a later barrier)
+  const int stage = hot->stage;
   if (threadIdx.x == 0) { hot->t_sub_last = globaltimer_ns(); if (first_phase) for (int i = 0; i < 8; ++i) hot->t_sub[i] = 0; }
   MARK(100 + stage);
   if (stage == BK_ST_DONE) return;
@@ -948,20 +950,17 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     if (have_round) {
       // the round hot->round is complete: log weights, liveness, resampling
       const int buf = hot->buf;
-      if (threadIdx.x == 0) { sh.live = 0; hot->c_rounds += 1; }
-      CTRL_SYNC();
-      if (threadIdx.x >= 1 && (int)threadIdx.x < P.P) {
+      const int rbase = hot->trace_round_base;   // (thread 0 moves it on only after the barrier below)
+      if (threadIdx.x >= 1 && (int)threadIdx.x < P.P) {   // sh.live was cleared by propose() / init_particles()
         const PRef S = pref(P, c, buf, threadIdx.x);
         sh.lw[threadIdx.x] = S.h->lw;
         if (S.h->q_head < S.h->n_nodes) sh.live = 1;
-        bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + threadIdx.x - 1);
+        bk_trace_rec* rec = trace_at(P, c, rbase + threadIdx.x - 1);
         if (rec) rec->log_w = S.h->lw;
       }
       CTRL_SYNC();
       const int live = sh.live;
-      const int rbase = hot->trace_round_base;
-      CTRL_SYNC();
-      if (threadIdx.x == 0) hot->trace_round_base = rbase + (P.P - 1);
+      if (threadIdx.x == 0) { hot->c_rounds += 1; hot->trace_round_base = rbase + (P.P - 1); }
       MARK(130 + live);
       TSUB(1);
       if (!live) { CTRL_SYNC(); finish_tree(P, c, ctl, hot, sh); TSUB(7); MARK(139); return; }
@@ -990,8 +989,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     have_round = true;
     if (nj > 0) {
       if (threadIdx.x == 0) { hot->cmd = BK_CMD_ROUND; hot->stage = BK_ST_WAIT_ROUND; }
-      CTRL_SYNC();
-      return;
+      return;   // (control_loop's barrier follows)
     }
     apply_pending_copy(P, c, hot, sh);   // no epoch to hide behind: the next round starts right away
   }
