@@ -139,6 +139,10 @@ __shared__ unsigned long long s_cdbg[32];
 #define CT(i, dep) do { } while (0)
 #endif
 
+// a node with fewer than N / BK_SPARSE_DIV members loads the split column only in lanes that hold members
+#ifndef BK_SPARSE_DIV
+#define BK_SPARSE_DIV 8
+#endif
 #define BK_CUM_SMEM 1024
 struct CtlShared {
   double lw[BK_MAX_PARTICLES];
@@ -586,7 +590,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       if (kind == 1) next = qh;            // a queued node, or one of the two children being made
       else { next = qh < nn ? qh : -1; if (next >= 0) kind = 2; }
     }
-    sh.s_sparse[q] = (j >= 0 && (long long)S.node(j).n * 8 < (long long)P.N) ? 1 : 0;
+    sh.s_sparse[q] = (j >= 0 && (long long)S.node(j).n * BK_SPARSE_DIV < (long long)P.N) ? 1 : 0;
     sh.s_qh[q] = qh;
     sh.s_kind[q] = kind; sh.s_j[q] = j; sh.s_v[q] = v; sh.s_k[q] = k; sh.s_next[q] = next; sh.s_row[q] = row; sh.s_nn[q] = nn;
     bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + q - 1);
