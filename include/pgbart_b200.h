@@ -159,6 +159,13 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host);
 int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host);
 void* bk_stream(bk_handle* h);
 
+/* Host copy of the value (tests/test_bart.py:121-123,197: the step returns the new value of the BART variable as a
+ * host array).  With bk_set_host_output(h, 1) every step also copies the sum of trees into a pinned host buffer
+ * [n_chains*n_groups][n_rows] behind the kernel on the handle's stream; bk_sum_trees_host returns that buffer (valid
+ * after bk_step / bk_step_wait until the next launch; NULL when disabled). */
+int bk_set_host_output(bk_handle* h, int enable);
+const float* bk_sum_trees_host(bk_handle* h);
+
 /* trace of the last step of one chain (host copy); returns records copied */
 int bk_read_trace(bk_handle* h, int chain, bk_trace_rec* out_host, int capacity);
 

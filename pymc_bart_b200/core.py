@@ -58,6 +58,7 @@ class DeviceSampler:
         self._stats = (_cabi.BkStepStats * Cn)()
         self._sigma = np.ones(Cn, dtype=np.float32)
         self._host_out = None
+        self._host_view = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -103,8 +104,19 @@ class DeviceSampler:
         """torch view [C, N] of the current sum of trees (device)."""
         return self.sum_trees_dev[:, : self.N]
 
+    def enable_host_output(self, enable: bool = True):
+        """Every step also copies the sum of trees to pinned host memory behind the kernel (the value handed to PyMC)."""
+        _cabi.check(self.lib.bk_set_host_output(self.h, int(bool(enable))), "bk_set_host_output")
+        self._host_view = None
+        if enable:
+            ptr = self.lib.bk_sum_trees_host(self.h)
+            self._host_view = np.ctypeslib.as_array(ptr, shape=(self.C, self.N))
+
     def sum_trees_host(self) -> np.ndarray:
-        """D2H copy of the sum of trees into pinned memory (the value handed to PyMC)."""
+        """Host view [C, N] of the sum of trees after the last step: the library's pinned buffer when host output is
+        enabled (no extra copy), otherwise a blocking D2H copy."""
+        if getattr(self, "_host_view", None) is not None:
+            return self._host_view
         torch = self.torch
         if self._host_out is None:
             self._host_out = torch.empty((self.C, self.N), dtype=torch.float32).pin_memory()

@@ -1697,6 +1697,8 @@ struct bk_handle_s {
   bk_step_stats* stats_pinned;
   float* sigma_pinned;
   int32_t* abort_pinned;
+  float* st_pinned;       // [C][n_rows] host copy of the sum of trees (bk_set_host_output)
+  int host_output;
   int32_t* marker_host;
   int marker_count;
 };
@@ -1867,6 +1869,7 @@ void bk_destroy(bk_handle* h) {
   if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
   if (h->sigma_pinned) cudaFreeHost(h->sigma_pinned);
   if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
+  if (h->st_pinned) cudaFreeHost(h->st_pinned);
   delete h;
 }
 
@@ -1893,8 +1896,21 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
   CK(cudaMemcpyAsync(h->vi_pinned, P.vi, (size_t)P.C * P.p * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->stats_pinned, P.stats, (size_t)P.C * sizeof(bk_step_stats), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->abort_pinned, P.abort_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (h->host_output)   // the value handed back to PyMC: strided device rows -> dense pinned host rows, behind the kernel
+    CK(cudaMemcpy2DAsync(h->st_pinned, (size_t)P.N * sizeof(float), P.st, (size_t)P.Npad * sizeof(float), (size_t)P.N * sizeof(float),
+                         (size_t)P.C, cudaMemcpyDeviceToHost, h->stream));
   return BK_OK;
 }
+
+int bk_set_host_output(bk_handle* h, int enable) {
+  if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
+  CK(cudaSetDevice(h->s.device));
+  if (enable && !h->st_pinned) CK(cudaMallocHost(&h->st_pinned, (size_t)h->P.C * h->P.N * sizeof(float)));
+  h->host_output = enable ? 1 : 0;
+  return BK_OK;
+}
+
+const float* bk_sum_trees_host(bk_handle* h) { return (h && h->host_output) ? h->st_pinned : nullptr; }
 
 int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }

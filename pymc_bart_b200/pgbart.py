@@ -71,6 +71,7 @@ class PGBART:
             n_groups=groups,
         )
         self.core = DeviceSampler(self.settings, op.X, Yarr)
+        self.core.enable_host_output(True)   # astep returns a host array every draw (the trace stores it)
         self.n_rows, self.n_cols, self.m = self.core.N, self.core.p, self.core.m
         self._lower = 0
         self._baseline = None   # per chain: (nodes [m,255], n_nodes [m])
