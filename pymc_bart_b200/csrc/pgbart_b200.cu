@@ -3,32 +3,33 @@
 //
 // Hot path (pymc-bart's PGBART.astep; reference sites cited in include/pgbart_b200.h
 // and SURVEY.md §8a rows B1-B10).  One launch runs the whole step for every chain
-// batched on this GPU as a per-chain DATAFLOW (no grid-wide barrier): CTA c (c < chains) is chain
-// c's control CTA, every other CTA is a worker.  A control CTA publishes an "epoch" = one batch of
-// data units (16-byte descriptor + release store of a ticket word); workers claim units with acquire fetch-adds, run
-// them and release-add a done counter the control CTA polls.  Chains are independent, so one
-// chain's scalar control overlaps the other chains' streaming work.  Two kinds of work:
+// batched on this GPU as a per-chain DATAFLOW (no grid-wide barrier): CTA c (c < chains) is
+// chain c's control CTA, every other CTA is a worker CTA split into BK_NGROUPS independent groups.
+// A control CTA publishes an "epoch" = one batch of data units (a 16-byte descriptor behind a
+// release fence); the groups serving that chain split the epoch statically, run their units and
+// release-add a done counter the control CTA polls.  Chains are independent: group g serves chain
+// g mod BK_NGROUPS, so the epochs of different chains overlap on every SM, and one chain's scalar
+// control overlaps the other chains' streaming work.
 //
-//   CONTROL  (one CTA per chain; scalar work, O(P) per round): leaf values, log
-//            weights, systematic resampling, queue pops, split-variable and split
-//            index draws, k-th-member selection (per-tile counts + one tile scan),
-//            row allocation, job descriptors.
-//   DATA     (all CTAs; the O(P*N) streams):
-//     ROUND  one warp walks 256 rows x up to 16 particles: the tile's fixed-point
-//            residual/sum-of-trees stay in registers, per particle it reads 8 leaf
-//            ids/lane (one 64-bit load) and the split column (two 128-bit loads),
-//            routes members left/right, writes the new leaf-id row, reduces the
-//            left child's (n, sum q_st, sum q_r, sum q_r^2) with warp shuffles and
-//            issues one 64-bit RED per statistic, and counts the members of the
-//            particle's next queue node per tile (feeds the next selection).
-//     SWEEP  fused commit of tree t (sum_trees = noi + new prediction, leaf-id row,
-//            Welford running sd) and prologue of tree t+1 (residual, fixed-point
-//            copies, per-leaf statistics of the old tree).
+//   CONTROL  (one CTA per chain, 16 warps; O(P) per round): leaf values, log weights, fixed-point
+//            systematic resampling, queue pops, split-variable and split-index draws, k-th-member
+//            selection (two-level search over per-tile counts), row allocation, job descriptors.
+//            Random draws and the particle copy run in the SHADOW of the epoch just published.
+//   DATA     (worker groups; the O(P*N) streams):
+//     ROUND  one warp walks 256 rows x its jobs: the tile's fixed-point residual/sum-of-trees stay
+//            in registers, per job it reads 8 leaf ids/lane (one 64-bit load) and the split column
+//            (two 128-bit loads), routes members left/right with byte-parallel logic, writes the
+//            new leaf-id row, forms the left child's (n, sum q_st, sum q_r, sum q_r^2) as REDUX
+//            partial sums = 32-bit limbs added to shared memory with ONE atomic instruction, and
+//            counts the members of the particle's next queue node per tile (feeds the selection).
+//     LL     Bernoulli likelihood: per-row log-likelihood terms of the rows of freshly made leaves.
+//     SWEEP  fused commit of tree t (sum_trees = noi + new prediction, leaf-id row, Welford running
+//            sd) and prologue of tree t+1 (residual, fixed-point copies, per-leaf statistics).
 //
-// All reductions are integer (bk_spec.h), so results do not depend on the grid
-// size, the reduction order, or the number of GPUs; every float op is an explicit
-// round-to-nearest intrinsic in a fixed order.  No tensor cores: there is no dense
-// contraction on this path (HBM/L2-bound integer and compare work).
+// All reductions are integer (bk_spec.h), so results do not depend on the grid size, the
+// reduction order, or the number of GPUs; every float op is an explicit round-to-nearest
+// intrinsic in a fixed order.  No tensor cores: there is no dense contraction on this path
+// (HBM/L2-bound integer and compare work).
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdio.h>
@@ -84,11 +85,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
-}
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
@@ -216,17 +212,6 @@ struct __align__(16) KernelShared {   // static shared memory of a control CTA (
 };
 
 // ------------------------------------------------------------------ dataflow sync helpers
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
   uint4 v;
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -234,11 +219,6 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
 }
 __device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ unsigned long long atom_acquire_add_u64(unsigned long long* p, unsigned long long v) {
-  unsigned long long r;
-  asm volatile("atom.acquire.gpu.global.add.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(v) : "memory");
-  return r;
 }
 
 __device__ __forceinline__ int4 ld_ca_v4(const int4* p) {   // ordinary (weak, L1-cached) 16-byte load, never the .nc path
@@ -1032,18 +1012,27 @@ __device__ __forceinline__ unsigned bytes_eq(unsigned w, unsigned pat4) {
 #define BK_LIMB_LLR_LO 11
 #define BK_LIMB_LLR_HI 12
 #define BK_LIMBS 16   // per job (64 bytes)
-// statistic k (BK_ACC_* index) of a job from its limbs
-__device__ __forceinline__ unsigned long long limbs_to_stat(const unsigned* L, int k) {
+// statistic k (BK_ACC_* index) of a job from its limbs; the limbs of a statistic belong to it alone and are cleared
+__device__ __forceinline__ unsigned long long take_stat(unsigned* L, int k) {
+  int lo, hi;   // limb indices; hi < 0: single limb
+  bool sgn = true;
   switch (k) {
-    case BK_ACC_N: return (unsigned long long)L[BK_LIMB_N];
-    case BK_ACC_SST: return (unsigned long long)((long long)(int)L[BK_LIMB_ST_HI] * 65536ll + (long long)L[BK_LIMB_ST_LO]);
-    case BK_ACC_SR: return (unsigned long long)((long long)(int)L[BK_LIMB_SR_HI] * 65536ll + (long long)L[BK_LIMB_SR_LO]);
-    case BK_ACC_SR2LO: return (unsigned long long)L[BK_LIMB_C0] + ((unsigned long long)L[BK_LIMB_C1] << 16);
-    case BK_ACC_SR2HI: return (unsigned long long)L[BK_LIMB_C2] + ((unsigned long long)L[BK_LIMB_C3] << 16);
-    case BK_ACC_LLL: return (unsigned long long)((long long)(int)L[BK_LIMB_LLL_HI] * 65536ll + (long long)L[BK_LIMB_LLL_LO]);
-    case BK_ACC_LLR: return (unsigned long long)((long long)(int)L[BK_LIMB_LLR_HI] * 65536ll + (long long)L[BK_LIMB_LLR_LO]);
+    case BK_ACC_N: lo = BK_LIMB_N; hi = -1; break;
+    case BK_ACC_SST: lo = BK_LIMB_ST_LO; hi = BK_LIMB_ST_HI; break;
+    case BK_ACC_SR: lo = BK_LIMB_SR_LO; hi = BK_LIMB_SR_HI; break;
+    case BK_ACC_SR2LO: lo = BK_LIMB_C0; hi = BK_LIMB_C1; sgn = false; break;
+    case BK_ACC_SR2HI: lo = BK_LIMB_C2; hi = BK_LIMB_C3; sgn = false; break;
+    case BK_ACC_LLL: lo = BK_LIMB_LLL_LO; hi = BK_LIMB_LLL_HI; break;
+    case BK_ACC_LLR: lo = BK_LIMB_LLR_LO; hi = BK_LIMB_LLR_HI; break;
     default: return 0ull;
   }
+  const unsigned vlo = L[lo];
+  L[lo] = 0u;
+  if (hi < 0) return (unsigned long long)vlo;
+  const unsigned vhi = L[hi];
+  L[hi] = 0u;
+  return sgn ? (unsigned long long)((long long)(int)vhi * 65536ll + (long long)vlo)
+             : (unsigned long long)vlo + ((unsigned long long)vhi << 16);
 }
 // byte e (0..3) of a 0x00/0xFF byte mask widened to a 32-bit mask
 #define BK_ROWMASK(m, e) __byte_perm((m), 0u, 0x1111u * (e))
@@ -1053,7 +1042,6 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
   const bool gauss = P.lik == BK_LIK_NORMAL;
-  const long long u_t0 = UTICK(lane);
   int q_r[8], q_s[8];
   {
     const int4* a = reinterpret_cast<const int4*>(P.qr + (size_t)c * P.Npad + base);
@@ -1082,7 +1070,6 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     const int kind = j0.x, src_row = j0.z, dst_row = j0.w;
     const int node = j1.x, var = j1.y; const float split = __int_as_float(j1.z); const int left_id = j1.w;
     const int next_node = j2.x, rule = j2.y, sparse = j2.z;
-    const long long u_t1 = UTICK(j2.x ^ q_r[7] ^ q_s[7] ^ q_r[0] ^ q_s[0]);   // q tile and job descriptor have arrived
     unsigned w0 = vw0, w1 = vw1;
     if (src_row != BK_ROW_VIRTUAL) {
       const uint2 v = __ldcg(reinterpret_cast<const uint2*>(rows_c + (size_t)src_row * P.Npad));
@@ -1111,7 +1098,6 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
         }
       }
       const unsigned lm0 = lb0 & mem0, lm1 = lb1 & mem1;           // 0xFF where the row goes to the left child
-      const long long u_t2 = UTICK(lm0 ^ lm1);                     // leaf ids and the column have arrived
       const unsigned L4 = (unsigned)left_id * 0x01010101u, R4 = L4 + 0x01010101u;
       const unsigned n0 = (w0 & ~mem0) | (mem0 & ((lm0 & L4) | (~lm0 & R4)));
       const unsigned n1 = (w1 & ~mem1) | (mem1 & ((lm1 & L4) | (~lm1 & R4)));
@@ -1162,8 +1148,6 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
         const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) cnt_c[(size_t)dst_row * P.cnt_stride] = tot;
       }
-      const long long u_t3 = UTICK(lane + (int)n0);
-      UACC(8, u_t1 - u_t0); UACC(9, u_t2 - u_t1); UACC(10, u_t3 - u_t2); UACC(11, 1);
     } else {  // BK_JOB_COUNT
       const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(w0, next4)) + __popc(bytes_eq_msb(w1, next4)));
       const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
@@ -1396,7 +1380,9 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
   GROUP_SYNC(g);
   int next = 0, n_finished = 0;
   long long t_idle0 = clock64();
-  unsigned long long t_pub = 0; (void)t_pub;
+#ifdef BK_PROFILE_CTRL
+  unsigned long long t_pub = 0;
+#endif
   for (;;) {
     if (warp == 0) {
       // The group's poller is its whole first warp, in lock step: every lane issues the same loads (one transaction)
@@ -1475,11 +1461,9 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
       // flush the group's partial sums: one global atomic per non-zero (job, statistic); leaves sh.acc zeroed
       for (int i = tid; i < wk.njobs * BK_ACC_STRIDE; i += BK_GROUP_THREADS) {
         const int ji = i / BK_ACC_STRIDE, k = i % BK_ACC_STRIDE;
-        const unsigned long long v = limbs_to_stat(sh.acc + ji * BK_LIMBS, k);
+        const unsigned long long v = take_stat(sh.acc + ji * BK_LIMBS, k);
         if (v) red_add_u64(P.accL + ((size_t)wk.chain * P.P + jobs[ji].slot) * BK_ACC_STRIDE + k, v);
       }
-      GROUP_SYNC(g);
-      for (int i = tid; i < wk.njobs * BK_LIMBS; i += BK_GROUP_THREADS) sh.acc[i] = 0u;
     } else {  // BK_CMD_SWEEP: group-wide row tiles, round robin over all serving groups
       for (unsigned u = wk.lo; u < (unsigned)wk.total; u += wk.hi) sweep_unit(P, wk.chain, (int)u, sh, g, tid);
     }

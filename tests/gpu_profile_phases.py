@@ -41,11 +41,4 @@ if dev.lib.bk_debug_worker_timers(dev.h, wd, 148) == 0:
     print("worker ROUND claims: %d per step; mean ns after publish: claimed=%.0f staged=%.0f units_done=%.0f done_added=%.0f; "
           "slowest CTA mean done_added=%.0f" % (n / (steps + 5), w[:, 0].sum() / n, w[:, 1].sum() / n, w[:, 2].sum() / n, w[:, 3].sum() / n,
                                              (w[:, 3] / w[:, 4]).max()))
-    nu = w[:, 11].sum()
-    if nu > 0:
-        print("partition jobs in units: %d per step; mean cycles: q after job=%.0f, (barrier-skewed) start->q+job=%.0f, ids+column=%.0f, compute+reduce+store=%.0f"
-              % (nu / (steps + 5), w[:, 12].sum() / nu, w[:, 8].sum() / nu, w[:, 9].sum() / nu, w[:, 10].sum() / nu))
-    print("stage barrier: cycles from work broadcast to staged jobs visible: warp0 %.0f warp5 %.0f" % (w[:, 13].sum() / n, w[:, 14].sum() / n))
-    print("q loads: issue %.0f cycles, first arrival after issue %.0f cycles" % (w[:, 5].sum() / nu * 0 + w[:, 5].sum() / max(w[:, 11].sum(), 1), w[:, 6].sum() / max(w[:, 11].sum(), 1)))
-    print("q arrivals after issue: a1 %.0f b0 %.0f b1 %.0f" % tuple(w[:, k].sum() / max(w[:, 11].sum(), 1) for k in (7, 14, 15)))
     print("control cycle split per step (chain 0, thread 0):", " ".join("%d:%.0f" % (i, v / (steps + 5)) for i, v in enumerate(cd) if v > 0))
