@@ -687,9 +687,9 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
   const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   const int nj = hot->n_jobs;
-  const int ji = threadIdx.x;
+  const int ji = (int)threadIdx.x - 32;   // job threads start at warp 1: warp 0 is the scalar warp and may run split
   const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
-  if (ji < nj && sh.jobs[ji].kind == BK_JOB_PARTITION) {   // the job list staged by propose() is still in shared memory
+  if (ji >= 0 && ji < nj && sh.jobs[ji].kind == BK_JOB_PARTITION) {   // the job list staged by propose() is still in shared memory
     const Job jb = sh.jobs[ji];
     const int q = jb.slot;
     const PRef S = pref(P, c, buf, q);
@@ -740,8 +740,8 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
 // Bernoulli: the LL epoch summed the quantised log-likelihood terms of the rows of every new leaf pair
 __device__ void finalize_ll(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int buf = hot->buf;
-  const int ji = threadIdx.x;
-  if (ji < hot->n_jobs && sh.jobs[ji].kind == BK_JOB_LL) {
+  const int ji = (int)threadIdx.x - 32;
+  if (ji >= 0 && ji < hot->n_jobs && sh.jobs[ji].kind == BK_JOB_LL) {
     const Job jb = sh.jobs[ji];
     const PRef S = pref(P, c, buf, jb.slot);
     unsigned long long* acc = P.accL + ((size_t)c * P.P + jb.slot) * BK_ACC_STRIDE;
