@@ -63,6 +63,12 @@
 // The control CTA of a chain runs with its first 256 threads only (the other warps exit at once):
 // barrier 1 with an explicit count, so a control-stage barrier waits for 8 warps, not 32.
 #define BK_CTRL_THREADS 512
+// Warp 0 of a control CTA is the SCALAR warp: thread 0 runs the sequential sections, lanes 1..31 only meet barriers.
+// (Lane 0's long solo sections leave that warp split across the non-aligned barriers; a split warp executes any
+// shared work twice and every *_sync collective through the WARPSYNC slow path, and the CTA waits for it.)  All
+// per-particle / per-row / strided work therefore runs on threads 32.. : BK_WTID is the index among those.
+#define BK_WTID ((int)threadIdx.x - 32)
+#define BK_WTHREADS (BK_CTRL_THREADS - 32)
 #define CTRL_SYNC() asm volatile("barrier.sync 1, 512;" ::: "memory")
 // worker group g uses barrier 2+g with BK_GROUP_THREADS arrivals
 #define GROUP_SYNC(g) asm volatile("barrier.sync %0, %1;" ::"r"(2 + (g)), "n"(BK_GROUP_THREADS) : "memory")
@@ -423,7 +429,7 @@ __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first
 
 __device__ void zero_acc0(const Params& P, int c) {
   unsigned long long* a = P.acc0 + (size_t)c * BK_ACC0_WORDS;
-  for (int i = threadIdx.x; i < BK_ACC0_WORDS; i += BK_CTRL_THREADS) a[i] = 0ull;
+  for (int i = BK_WTID; i >= 0 && i < BK_ACC0_WORDS; i += BK_WTHREADS) a[i] = 0ull;
 }
 
 __device__ void rebuild_cum_dev(const Params& P, int c) {  // thread 0 only
@@ -442,7 +448,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
   const DNode* ft = P.forest + ((size_t)c * P.m + t) * BK_MAX_NODES;
   const int nn = P.forest_nn[(size_t)c * P.m + t];
   const PRef p0 = pref(P, c, 0, 0);
-  for (int k = threadIdx.x; k < nn; k += BK_CTRL_THREADS) {
+  for (int k = BK_WTID; k >= 0 && k < nn; k += BK_WTHREADS) {
     DNode nd = ft[k];
     nd.sst = 0;
     nd.sr = (int64_t)__ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 0);
@@ -450,8 +456,8 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     nd.sr2_hi = s2.hi; nd.sr2_lo = s2.lo;
     p0.node(k) = nd;
   }
-  for (int r = threadIdx.x; r < P.R; r += BK_CTRL_THREADS) sh.row_cnt_node[r] = -1;
-  for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += BK_CTRL_THREADS) sh.cum_prior[v] = P.cum[(size_t)c * P.p + v];
+  for (int r = BK_WTID; r >= 0 && r < P.R; r += BK_WTHREADS) sh.row_cnt_node[r] = -1;
+  for (int v = BK_WTID; v >= 0 && v < P.p && v < BK_CUM_SMEM; v += BK_WTHREADS) sh.cum_prior[v] = P.cum[(size_t)c * P.p + v];
   CTRL_SYNC();
   const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
   if (threadIdx.x == 0) {
@@ -464,7 +470,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     p0.h->ssq = ssq; p0.h->lw = bern ? bk_bern_loglik(ssq) : bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
     hot->buf = 0; hot->round = 0; sh.live = 0;
   }
-  const int q = threadIdx.x;
+  const int q = BK_WTID;
   if (q >= 1 && q < P.P) {
     bk_stats tot;
     tot.n = P.N;
@@ -503,7 +509,7 @@ __device__ void apply_pending_copy(const Params& P, int c, ChainHot* hot, CtlSha
   if (!sh.copy_pending) return;     // (uniform: shared flag, read after a barrier)
   const int buf = hot->buf;
   copy_particles(P, c, buf, sh.src_slot);
-  if (threadIdx.x >= 1 && (int)threadIdx.x < P.P) pref(P, c, buf ^ 1, threadIdx.x).h->q_head = sh.s_qh[threadIdx.x];
+  if (BK_WTID >= 1 && BK_WTID < P.P) pref(P, c, buf ^ 1, BK_WTID).h->q_head = sh.s_qh[BK_WTID];
   if (threadIdx.x == 0) { hot->buf = buf ^ 1; sh.copy_pending = 0; }
   CTRL_SYNC();
 }
@@ -513,7 +519,7 @@ __device__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& s
   const int round = hot->round, t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   apply_pending_copy(P, c, hot, sh);
-  const int q = threadIdx.x;
+  const int q = BK_WTID;
   if (q >= 1 && q < P.P) {
     // leaf-value normals of this round (used by finalize_grows when the epoch is done) for the slots that grow
     if (sh.s_kind[q] == 1) {
@@ -526,7 +532,7 @@ __device__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& s
     sh.pre_v[q] = draw_variable_dev(P, c, sh, bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, r1, (uint32_t)q, BK_U_VAR).v[0]));
     sh.pre_u3[q] = bk_rng(S0, C0, D0, G0, (uint32_t)t, r1, (uint32_t)q, BK_U_VAL).v[0];
   }
-  if (q == 0) {
+  if (threadIdx.x == 0) {
     sh.pre_ures = bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0];
     sh.pre_prop_tree = t; sh.pre_prop_round = round + 1;
     sh.pre_z_tree = t; sh.pre_z_round = round;
@@ -538,13 +544,13 @@ __device__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& s
 __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
-  const int q = threadIdx.x;
+  const int q = BK_WTID;
   __shared__ int s_njobs, s_err, s_next_sel;
   __shared__ int s_free[2 * BK_MAX_PARTICLES];
   __shared__ int s_warp_cnt[3][8];
-  if (q < P.P) { sh.s_kind[q] = 0; sh.s_next[q] = -1; sh.s_j[q] = -1; }
-  if (q == 0) { s_err = 0; s_next_sel = 1; sh.live = 0; }
-  if (q < P.R) sh.row_used[q] = 0;
+  if (q >= 0 && q < P.P) { sh.s_kind[q] = 0; sh.s_next[q] = -1; sh.s_j[q] = -1; }
+  if (threadIdx.x == 0) { s_err = 0; s_next_sel = 1; sh.live = 0; }
+  if (q >= 0 && q < P.R) sh.row_used[q] = 0;
   if (q >= 1 && q < P.P) {
     const bool deferred = sh.copy_pending != 0;
     const PRef S = pref(P, c, buf, deferred ? sh.src_slot[q] : q);   // the slot's state-to-be = its ancestor's state
@@ -589,9 +595,9 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
   // their split value (k-th member).  The split values are patched into the jobs after the joint barrier.
   // Warp 0 never runs a selection: it can be split (see normalise_and_resample) and would crawl through the shuffles.
 #define J_SYNC() asm volatile("barrier.sync 14, 256;" ::: "memory")
-  const int tx = threadIdx.x, lane = tx & 31, w = tx >> 5;
+  const int tx = BK_WTID, lane = threadIdx.x & 31, w = tx >> 5;   // team J = threads 32..287 (warps 1..8)
   int is_grow = 0, is_cnt = 0, is_free = 0, rank_g = 0;
-  if (tx < 256) {   // ---- team J (R <= 256 and P <= 128: eight warps cover both index ranges)
+  if (tx >= 0 && tx < 256) {   // ---- team J (R <= 256 and P <= 128: eight warps cover both index ranges)
     if (tx >= 1 && tx < P.P) {
       if (sh.s_row[tx] >= 0) sh.row_used[sh.s_row[tx]] = 1;
       if (sh.s_kind[tx] == 1 && sh.s_row[tx] != BK_ROW_VIRTUAL && sh.row_cnt_node[sh.s_row[tx]] != sh.s_j[tx]) atomicOr(&s_err, 1);
@@ -651,7 +657,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
         reinterpret_cast<uint4*>(ctl->jobs[i / (nj * 3)])[i % (nj * 3)] = s4[i % (nj * 3)];
     }
   }
-  if (w > 0) {   // ---- split values: warps take growing slots from the shared counter
+  if (threadIdx.x >= 32) {   // ---- split values: warps 1.. take growing slots from the shared counter
     for (;;) {
       int sl = 0;
       if (lane == 0) sl = atomicAdd(&s_next_sel, 1);
@@ -675,7 +681,7 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
     sh.jobs[rank_g].split = sv;
     for (int k = 0; k < BK_JOB_COPIES; ++k) ctl->jobs[k][rank_g].split = sv;
   }
-  if (tx == 0 && s_err) hot->c_err |= s_err;
+  if (threadIdx.x == 0 && s_err) hot->c_err |= s_err;
   TSUB(5);
 #undef J_SYNC
   TSUB(6);
@@ -758,8 +764,8 @@ __device__ void finalize_ll(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
 }
 
 __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot /* smem, [P] */) {
-  const int warp = threadIdx.x >> 5, nwarps = BK_CTRL_THREADS >> 5, lane = threadIdx.x & 31;
-  for (int s = warp; s < P.P; s += nwarps) {
+  const int warp = (int)(threadIdx.x >> 5) - 1, nwarps = (BK_CTRL_THREADS >> 5) - 1, lane = threadIdx.x & 31;   // warps 1..15
+  for (int s = warp; s >= 0 && s < P.P; s += nwarps) {
     const PRef src = pref(P, c, buf, anc_of_slot[s]);
     const PRef dst = pref(P, c, buf ^ 1, s);
     const int nn = src.h->n_nodes;
@@ -780,7 +786,7 @@ __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_o
 __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int buf = hot->buf, t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
-  if ((int)threadIdx.x < P.P) sh.lw[threadIdx.x] = pref(P, c, buf, threadIdx.x).h->lw;
+  if (BK_WTID >= 0 && BK_WTID < P.P) sh.lw[BK_WTID] = pref(P, c, buf, BK_WTID).h->lw;
   CTRL_SYNC();
   const uint32_t uf = bk_rng(S0, C0, D0, G0, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0];
   normalise_and_resample(P, sh, 0, P.P, uf);
@@ -794,14 +800,14 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
   DNode* ft = P.forest + ((size_t)c * P.m + t) * BK_MAX_NODES;
   const int old_nn = P.forest_nn[(size_t)c * P.m + t];
   const int new_nn = W.h->n_nodes;
-  for (int k = threadIdx.x; k < 256; k += BK_CTRL_THREADS) {
+  for (int k = BK_WTID; k >= 0 && k < 256; k += BK_WTHREADS) {
     ctl->old_vals[k] = (k < old_nn && ft[k].var < 0) ? ft[k].value : 0.0f;
     ctl->new_vals[k] = (k < new_nn && W.node(k).var < 0) ? W.node(k).value : 0.0f;
   }
   CTRL_SYNC();
   {
     uint4* d4 = reinterpret_cast<uint4*>(ft);
-    for (int i = threadIdx.x; i < new_nn * 4; i += BK_CTRL_THREADS) d4[i] = reinterpret_cast<const uint4*>(&W.node(i >> 2))[i & 3];
+    for (int i = BK_WTID; i >= 0 && i < new_nn * 4; i += BK_WTHREADS) d4[i] = reinterpret_cast<const uint4*>(&W.node(i >> 2))[i & 3];
   }
   zero_acc0(P, c);
   if (threadIdx.x == 0) {
@@ -851,7 +857,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
   if (threadIdx.x == 0) hot->c_phases += 1;
 
   if (stage == BK_ST_START) {
-    for (int v = threadIdx.x; v < P.p; v += BK_CTRL_THREADS) P.vi[(size_t)c * P.p + v] = 0;
+    for (int v = BK_WTID; v >= 0 && v < P.p; v += BK_WTHREADS) P.vi[(size_t)c * P.p + v] = 0;
     zero_acc0(P, c);
     if (threadIdx.x == 0) {
       int T = hot->tune ? P.batch_tune : P.batch_post;
@@ -916,7 +922,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       // leaf values are known now: publish the LL jobs (the first n_grow list entries) and wait for their sums
       const int ng = hot->n_grow;
       const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
-      for (int i = threadIdx.x; i < ng * 3 * BK_JOB_COPIES; i += BK_CTRL_THREADS)
+      for (int i = BK_WTID; i >= 0 && i < ng * 3 * BK_JOB_COPIES; i += BK_WTHREADS)
         reinterpret_cast<uint4*>(ctl->jobs[i / (ng * 3)])[i % (ng * 3)] = s4[i % (ng * 3)];
       CTRL_SYNC();
       if (threadIdx.x == 0) { hot->n_jobs = ng; hot->cmd = BK_CMD_LL; hot->stage = BK_ST_WAIT_LL; }
@@ -935,11 +941,11 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       // the round hot->round is complete: log weights, liveness, resampling
       const int buf = hot->buf;
       const int rbase = hot->trace_round_base;   // (thread 0 moves it on only after the barrier below)
-      if (threadIdx.x >= 1 && (int)threadIdx.x < P.P) {   // sh.live was cleared by propose() / init_particles()
-        const PRef S = pref(P, c, buf, threadIdx.x);
-        sh.lw[threadIdx.x] = S.h->lw;
+      if (BK_WTID >= 1 && BK_WTID < P.P) {   // sh.live was cleared by propose() / init_particles()
+        const PRef S = pref(P, c, buf, BK_WTID);
+        sh.lw[BK_WTID] = S.h->lw;
         if (S.h->q_head < S.h->n_nodes) sh.live = 1;
-        bk_trace_rec* rec = trace_at(P, c, rbase + threadIdx.x - 1);
+        bk_trace_rec* rec = trace_at(P, c, rbase + BK_WTID - 1);
         if (rec) rec->log_w = S.h->lw;
       }
       CTRL_SYNC();
@@ -957,8 +963,8 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       TSUB(2);
       MARK(133);
       // anc[i] indexes particles 1..P-1; convert to slot -> source slot
-      if ((int)threadIdx.x < P.P) {
-        int s = threadIdx.x;
+      if (BK_WTID >= 0 && BK_WTID < P.P) {
+        int s = BK_WTID;
         sh.src_slot[s] = s == 0 ? 0 : sh.anc[s - 1] + 1;
         if (s >= 1) { bk_trace_rec* rec = trace_at(P, c, rbase + s - 1); if (rec) rec->ancestor = sh.src_slot[s]; }
       }
