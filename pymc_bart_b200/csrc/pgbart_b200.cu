@@ -825,7 +825,7 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
     sj.wf_count = hot->wf_count + (hot->tune ? 1 : 0);
     sj.do_prologue = (t + 1 < hot->tree_hi) ? 1 : 0; sj.prologue_tree = t + 1;
     ctl->sweep = sj;
-    hot->cmd = BK_CMD_SWEEP; hot->stage = BK_ST_WAIT_SWEEP;
+    hot->cmd = BK_CMD_SWEEP; hot->stage_next = BK_ST_WAIT_SWEEP;
     // kind-2 trace record is completed after the sweep (leaf_sd); stash its fields now
     bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base);
     if (rec) {
@@ -843,13 +843,13 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
   ChainCtl* ctl = P.ctl + c;
   if (first_phase) {
     if (threadIdx.x == 0) {
-      hot->stage = BK_ST_START; hot->tune = tune; hot->sigma = sigma_in[c];
+      hot->stage = BK_ST_START; hot->stage_next = BK_ST_START; hot->tune = tune; hot->sigma = sigma_in[c];
       hot->ll_inv2s2 = bk_normal_inv2s2(hot->sigma); hot->ll_c = bk_normal_const(hot->sigma, (double)P.N);
     }
     CTRL_SYNC();
   }
-  // (hot lives in shared memory; the caller's barrier ordered the previous phase's writes, and thread 0 changes the
-  // stage again only after a later barrier)
+  // hot lives in shared memory.  Every thread reads the stage here; thread 0 records the NEXT stage in stage_next and
+  // control_loop moves it into `stage` between two barriers, so no thread can see it change under its feet.
   const int stage = hot->stage;
   if (threadIdx.x == 0) { hot->t_sub_last = globaltimer_ns(); if (first_phase) for (int i = 0; i < 8; ++i) hot->t_sub[i] = 0; }
   MARK(100 + stage);
@@ -868,7 +868,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       hot->trace_len = 0; hot->trace_round_base = 0;
       SweepJob sj; memset(&sj, 0, sizeof(sj));
       sj.do_prologue = 1; sj.prologue_tree = lo;
-      ctl->sweep = sj; hot->cmd = BK_CMD_SWEEP; hot->stage = BK_ST_WAIT_SWEEP;
+      ctl->sweep = sj; hot->cmd = BK_CMD_SWEEP; hot->stage_next = BK_ST_WAIT_SWEEP;
     }
     CTRL_SYNC();
     return;
@@ -898,7 +898,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
         s_more = 0;
         hot->lower = hot->tree_hi < P.m ? hot->tree_hi : 0;
         hot->draw += 1;
-        hot->cmd = BK_CMD_DONE; hot->stage = BK_ST_DONE;
+        hot->cmd = BK_CMD_DONE; hot->stage_next = BK_ST_DONE;
         bk_step_stats st; memset(&st, 0, sizeof(st));
         st.tree_updates = hot->c_tree_updates; st.rounds = hot->c_rounds; st.grow_events = hot->c_grow;
         st.grow_root = hot->c_grow_root; st.count_passes = hot->c_count_passes; st.phases = hot->c_phases;
@@ -925,7 +925,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       for (int i = BK_WTID; i >= 0 && i < ng * 3 * BK_JOB_COPIES; i += BK_WTHREADS)
         reinterpret_cast<uint4*>(ctl->jobs[i / (ng * 3)])[i % (ng * 3)] = s4[i % (ng * 3)];
       CTRL_SYNC();
-      if (threadIdx.x == 0) { hot->n_jobs = ng; hot->cmd = BK_CMD_LL; hot->stage = BK_ST_WAIT_LL; }
+      if (threadIdx.x == 0) { hot->n_jobs = ng; hot->cmd = BK_CMD_LL; hot->stage_next = BK_ST_WAIT_LL; }
       CTRL_SYNC();
       return;
     }
@@ -978,7 +978,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     MARK(141);
     have_round = true;
     if (nj > 0) {
-      if (threadIdx.x == 0) { hot->cmd = BK_CMD_ROUND; hot->stage = BK_ST_WAIT_ROUND; }
+      if (threadIdx.x == 0) { hot->cmd = BK_CMD_ROUND; hot->stage_next = BK_ST_WAIT_ROUND; }
       return;   // (control_loop's barrier follows)
     }
     apply_pending_copy(P, c, hot, sh);   // no epoch to hide behind: the next round starts right away
@@ -1409,8 +1409,9 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
           if (d.x == sh.seen[c]) continue;
           if (lane == 0) fence_acq_rel_gpu();   // acquire (pairs with the control CTA's release fence); drops stale L1 lines
           __syncwarp();
-          sh.seen[c] = d.x;                                           // (all lanes store the same value)
-          if ((d.y & 0xFFu) == BK_CMD_DONE) { sh.fin[c] = 1; n_finished++; continue; }
+          if (lane == 0) { sh.seen[c] = d.x; if ((d.y & 0xFFu) == BK_CMD_DONE) sh.fin[c] = 1; }
+          __syncwarp();
+          if ((d.y & 0xFFu) == BK_CMD_DONE) { n_finished++; continue; }
           wk.chain = c; wk.cmd = (int)(d.y & 0xFFu); wk.njobs = (int)d.z; wk.total = (int)d.w;
           const unsigned ns = (unsigned)servers_of(P.C, c);
           if (wk.cmd == BK_CMD_SWEEP) {
@@ -1483,7 +1484,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
 
 // ---- control CTA of chain c: wait for the previous epoch, run the state machine, publish the next
 __device__ bool control_loop(const Params& P, int c, int tune, const float* sigma_in, int max_phases, CtlShared& sh) {
-  __shared__ int s_flag;
+  __shared__ int s_abort, s_fin;
   __shared__ ChainHot s_hot;
   ChainCtl* ctl = P.ctl + c;
   ChainHot* hot = &s_hot;
@@ -1518,15 +1519,16 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       }
       fence_acq_rel_gpu();
       if (!ab && ld_volatile_i32(P.abort_flag)) ab = 1;
-      s_flag = ab;
+      s_abort = ab;
       q1 = globaltimer_ns();
     }
     CTRL_SYNC();
-    if (s_flag) return false;
+    if (s_abort) return false;
     control_step(P, c, phase, tune, sigma_in, hot, sh);
     CTRL_SYNC();
     if (threadIdx.x == 0) {
       q2 = globaltimer_ns();
+      hot->stage = hot->stage_next;   // (every thread read the old stage before the barrier above)
       const int cmd = hot->cmd;
       int fin = 0;
       if (cmd == BK_CMD_DONE) {
@@ -1545,7 +1547,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
         fence_acq_rel_gpu();
         st_volatile_v4(&sy->desc, make_uint4(epoch, (unsigned)cmd, (unsigned)nj, (unsigned)total));
       }
-      s_flag = fin;
+      s_fin = fin;
       const unsigned long long q3 = globaltimer_ns();
       t_wait += q1 - q0; t_ctrl += q2 - q1; t_pub += q3 - q2;
       if (last_cmd == BK_CMD_SWEEP) t_wait_sweep += q1 - q0;
@@ -1563,7 +1565,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       }
     }
     CTRL_SYNC();
-    if (s_flag) return true;
+    if (s_fin) return true;
     if (hot->cmd == BK_CMD_ROUND) shadow_round(P, c, hot, sh);   // overlaps the epoch just published
   }
   if (threadIdx.x == 0) { atomicExch(P.abort_flag, 1); }

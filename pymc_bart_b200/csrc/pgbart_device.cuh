@@ -113,7 +113,8 @@ struct __align__(16) ChainHot {
   int32_t draw;      // steps so far (Philox counter word 0)  (persistent)
   int32_t wf_count;  // Welford count                         (persistent)
   float leaf_sd;     //                                       (persistent)
-  int32_t stage;
+  int32_t stage;       // state machine position, read by every control thread at the start of a phase
+  int32_t stage_next;  // written by thread 0 during the phase, moved into `stage` by control_loop
   int32_t tree_lo, tree_hi, cur_tree;
   int32_t round;
   int32_t buf;       // particle ping-pong index
