@@ -801,7 +801,9 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
   const int old_nn = P.forest_nn[(size_t)c * P.m + t];
   const int new_nn = W.h->n_nodes;
   for (int k = BK_WTID; k >= 0 && k < 256; k += BK_WTHREADS) {
-    ctl->old_vals[k] = (k < old_nn && ft[k].var < 0) ? ft[k].value : 0.0f;
+    const int ov = k < BK_MAX_NODES ? __ldcg(&ft[k].var) : 0;        // independent loads (slots beyond the tree are masked)
+    const float of = k < BK_MAX_NODES ? __ldcg(&ft[k].value) : 0.0f;
+    ctl->old_vals[k] = (k < old_nn && ov < 0) ? of : 0.0f;
     ctl->new_vals[k] = (k < new_nn && W.node(k).var < 0) ? W.node(k).value : 0.0f;
   }
   CTRL_SYNC();
@@ -1220,10 +1222,12 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
     sh.old_vals[k] = do_commit ? __ldcg(&ctl->old_vals[k]) : 0.0f;
     sh.new_vals[k] = do_commit ? __ldcg(&ctl->new_vals[k]) : 0.0f;
     float pv = 0.0f;
-    if (do_pro && k < 255) {
+    if (do_pro && k < 255) {   // three independent loads: one L2 round trip (slots beyond the tree hold stale nodes, masked by nn)
       const DNode* nd = P.forest + ((size_t)c * P.m + pro_tree) * BK_MAX_NODES + k;
-      int nn = __ldcg(P.forest_nn + (size_t)c * P.m + pro_tree);
-      if (k < nn) { int var = __ldcg(&nd->var); pv = var < 0 ? __ldcg(&nd->value) : 0.0f; }
+      const int nn = __ldcg(P.forest_nn + (size_t)c * P.m + pro_tree);
+      const int var = __ldcg(&nd->var);
+      const float val = __ldcg(&nd->value);
+      pv = (k < nn && var < 0) ? val : 0.0f;
     }
     sh.pro_vals[k] = pv;
   }
