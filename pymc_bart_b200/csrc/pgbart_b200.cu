@@ -382,40 +382,43 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
 }
 
 // Fixed-point weights of sh.lw[first..first+count) and systematic resampling into sh.anc[0..count) (bk_spec.h:
-// bk_weight_fix / bk_resample_*).  Runs in warp 0 (count <= 128: element i lives in lane i % 32, slot i / 32).
+// bk_weight_fix / bk_resample_*).  Runs in warps 1..4 (count <= 128: element i lives in warp 1 + i / 32, lane i % 32).
 // Everything is integer after the float exponential, so the warp-parallel scan gives the oracle's sequential sums
 // bit for bit.  Ends with a block barrier.
-// Runs in warp 1, not warp 0: lane 0 of warp 0 executes the chain's scalar sections alone and (non-aligned barriers)
-// can leave that warp split, and a split warp takes the WARPSYNC slow path on EVERY shuffle (~200 cycles each,
-// measured); warps 1..7 never diverge across a barrier, so their collectives stay on the fast path.
+// Never on warp 0: lane 0 of warp 0 executes the chain's scalar sections alone and (non-aligned barriers) can leave
+// that warp split, and a split warp takes the WARPSYNC slow path on EVERY shuffle (~200 cycles each, measured);
+// warps 1.. never diverge across a barrier, so their collectives stay on the fast path.
 __device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int o) {
   const unsigned lo = __shfl_up_sync(0xffffffffu, (unsigned)v, o), hi = __shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), o);
   return ((unsigned long long)hi << 32) | lo;
 }
 __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, uint32_t u32) {
-  if ((threadIdx.x >> 5) == 1) {
+  // warps 1..4, one 32-element slice each (count <= 128), meeting on their own named barrier
+  const int wq = (int)(threadIdx.x >> 5) - 1;
+  if (wq >= 0 && wq < 4) {
+#define R_SYNC() asm volatile("barrier.sync 13, 128;" ::: "memory")
+    __shared__ unsigned long long s_slice[4];
     const int lane = threadIdx.x & 31;
     CT0();
-    double mx = -1.7976931348623157e308;
+    double mx = -1.7976931348623157e308;   // every warp forms the same maximum
     for (int i = lane; i < count; i += 32) { double v = sh.lw[first + i]; mx = v > mx ? v : mx; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { double ov = __shfl_xor_sync(0xffffffffu, mx, o); mx = ov > mx ? ov : mx; }
     CT(0, __double2loint(mx));
-    unsigned long long run = 0ull;                       // sum of all earlier 32-element slices
-    for (int k0 = 0; k0 < count; k0 += 32) {
-      const int i = k0 + lane;
-      unsigned long long s = i < count ? bk_weight_fix(sh.lw[first + i], mx) : 0ull;
+    const int i = wq * 32 + lane;
+    unsigned long long s = i < count ? bk_weight_fix(sh.lw[first + i], mx) : 0ull;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const unsigned long long nb = shfl_up_u64(s, o); if (lane >= o) s += nb; }
-      s += run;
-      if (i < count) sh.cum_s[i] = s;
-      run = ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(s >> 32), 31) << 32) | __shfl_sync(0xffffffffu, (unsigned)s, 31);
-
-    }
-    __syncwarp();
-    CT(1, (int)run);
-    const unsigned long long s_last = run;               // = S[count - 1]
-    for (int i = lane; i < count; i += 32) {
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long nb = shfl_up_u64(s, o); if (lane >= o) s += nb; }
+    if (lane == 31) s_slice[wq] = s;
+    R_SYNC();
+    unsigned long long before = 0ull, s_last = 0ull;     // sum of the earlier slices; S[count - 1]
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const unsigned long long t = s_slice[k]; if (k < wq) before += t; s_last += t; }
+    s += before;
+    if (i < count) sh.cum_s[i] = s;
+    R_SYNC();
+    CT(1, (int)s_last);
+    if (i < count) {
       // first index whose running sum reaches the point (= the walk `while (point > c[idx]) idx++`)
       const bk_u128 point = bk_resample_point((uint32_t)i, u32, s_last);
       int lo = 0, hi = count - 1;
@@ -423,6 +426,7 @@ __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first
       sh.anc[i] = lo;
     }
     CT(4, sh.anc[lane < count ? lane : 0]);
+#undef R_SYNC
   }
   CTRL_SYNC();
 }
