@@ -816,16 +816,35 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
     for (int i = BK_WTID; i >= 0 && i < new_nn * 4; i += BK_WTHREADS) d4[i] = reinterpret_cast<const uint4*>(&W.node(i >> 2))[i & 3];
   }
   zero_acc0(P, c);
+  {
+    // split-variable usage of the new tree.  The cumulative prior is rebuilt from the counts BEFORE this tree's
+    // (oracle order); the running sums stay sequential in thread 0, the p divisions run in parallel.  The counts
+    // themselves are exact integer increments, so parallel atomics give the oracle's sequential result.
+    double* av = P.alpha_vec + (size_t)c * P.p;
+    const bool rebuild = hot->tune && hot->iter > P.m;
+    __shared__ double s_tot;
+    if (rebuild) {
+      if (P.p <= BK_CUM_SMEM) {
+        if (threadIdx.x == 0) {
+          double run = 0.0;
+          for (int v = 0; v < P.p; ++v) { run = BK_DADD(run, av[v]); sh.cum_prior[v] = run; }
+          s_tot = run;
+        }
+        CTRL_SYNC();
+        double* cum = P.cum + (size_t)c * P.p;
+        for (int v = BK_WTID; v >= 0 && v < P.p; v += BK_WTHREADS) cum[v] = BK_DDIV(sh.cum_prior[v], s_tot);
+      } else if (threadIdx.x == 0) {
+        rebuild_cum_dev(P, c);
+      }
+      CTRL_SYNC();   // the sums above read the counts before anybody bumps them
+    }
+    for (int k = BK_WTID; k >= 0 && k < new_nn; k += BK_WTHREADS) {
+      const int v = W.node(k).var;
+      if (v >= 0) { if (hot->tune) atomicAdd(&av[v], 1.0); else atomicAdd(P.vi + (size_t)c * P.p + v, 1); }
+    }
+  }
   if (threadIdx.x == 0) {
     P.forest_nn[(size_t)c * P.m + t] = new_nn;
-    double* av = P.alpha_vec + (size_t)c * P.p;
-    if (hot->tune) {
-      if (hot->iter > P.m) rebuild_cum_dev(P, c);
-      for (int k = 0; k < new_nn; ++k) { int v = W.node(k).var; if (v >= 0) av[v] = BK_DADD(av[v], 1.0); }
-    } else {
-      int32_t* vi = P.vi + (size_t)c * P.p;
-      for (int k = 0; k < new_nn; ++k) { int v = W.node(k).var; if (v >= 0) vi[v] += 1; }
-    }
     SweepJob sj; memset(&sj, 0, sizeof(sj));
     sj.do_commit = 1; sj.commit_tree = t; sj.new_row = W.h->row; sj.do_welford = hot->tune ? 1 : 0;
     sj.wf_count = hot->wf_count + (hot->tune ? 1 : 0);
