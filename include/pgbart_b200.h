@@ -83,16 +83,16 @@ typedef struct {
   int32_t grow_events;    /* successful particle growths (G of BASELINE.md) */
   int32_t grow_root;      /* ... of which at the root (no leaf-id read) */
   int32_t count_passes;   /* member-count-only passes */
-  int32_t phases;         /* grid-wide phases executed */
+  int32_t phases;         /* control phases (= epochs published + 1) */
   int32_t trace_len;      /* trace records written */
   int32_t error_flags;    /* 0 = clean */
   float leaf_sd;          /* running leaf sd after the step */
   int32_t iter;           /* tree updates since creation */
   int32_t us_control;     /* wall time (us) this chain's control CTA spent in control phases */
-  int32_t us_data;        /* ... in data phases (its own share of the streams) */
-  int32_t us_sync;        /* ... waiting at the two grid barriers per phase */
+  int32_t us_data;        /* ... waiting for the worker groups to finish its epochs */
+  int32_t us_sync;        /* ... publishing epochs (release fence + descriptor store) */
   int32_t us_total;       /* kernel wall time seen by the control CTA */
-  int32_t reserved[2];
+  int32_t reserved[2];    /* [0]: part of us_data spent on SWEEP epochs */
 } bk_step_stats;
 
 /* one record per (tree update, round, particle>=1) plus one per tree update (kind 2) */

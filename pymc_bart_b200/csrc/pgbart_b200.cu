@@ -119,7 +119,7 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 #define BK_BARRIER_TIMEOUT_CYCLES (8000000000LL)
 
 #ifdef BK_PROFILE_CTRL
-// worker-side latency sums (ns) per CTA: [0] publish->claimed, [1] ->jobs staged, [2] ->units done, [3] ->done added, [4] claims
+// worker-side latency sums (ns) per CTA (group 0): [0] publish->epoch seen, [2] ->units done, [3] ->done added, [4] epochs
 __device__ unsigned long long g_wdbg[256][16];
 // cycle stamp that waits for `dep` (a freshly loaded / computed register)
 // (the clock read is predicated on `dep`, so it cannot issue before the value has arrived)

@@ -23,13 +23,12 @@
 //                       // independent worker groups per worker CTA
 #define BK_GROUP_THREADS (BK_CTA_THREADS / BK_NGROUPS)
 #define BK_COMMIT_TILE (BK_GROUP_THREADS * 4)  // rows per group pass in the commit/prologue sweep
-#define BK_MAX_GROUP 16            // particles that share one register-resident (q_r, q_st) tile
 
 // leaf-id row references
 #define BK_ROW_VIRTUAL (-1)  // stump: every real row is in node 0
 #define BK_ROW_FOREST (-2)   // particle 0: the current tree's row in ids_tree
 
-// per-chain command for the next grid-wide data phase
+// per-chain command of an epoch (what the worker groups execute next)
 #define BK_CMD_IDLE 0
 #define BK_CMD_ROUND 1
 #define BK_CMD_SWEEP 2   // commit of tree A and/or prologue of tree B, fused
@@ -134,7 +133,7 @@ struct __align__(16) ChainCtl {
   SweepJob sweep;       // descriptor of the next SWEEP epoch (read by the workers)
   float old_vals[256];  // leaf values of the tree being replaced
   float new_vals[256];  // leaf values of the winning particle
-  Job jobs[BK_JOB_COPIES][BK_MAX_PARTICLES];   // identical copies: ~150 worker CTAs read the list at the same instant
+  Job jobs[BK_JOB_COPIES][BK_MAX_PARTICLES];   // the epoch's job list (optionally replicated; A/B: one copy is fastest)
 };
 
 // accumulator slots per particle (u64 each)
@@ -153,14 +152,15 @@ struct __align__(16) ChainCtl {
 #define BK_ACC0_WORDS (257 * BK_ACC0_STRIDE)
 
 // Per-chain dataflow synchronisation (own 128-byte line each).
-//   desc:   {epoch id, cmd | group << 8, n_jobs, total units}: ONE 16-byte store by the chain's control
-//           CTA (after a release fence), read by workers with one 16-byte load.
-//   ticket: (epoch << 32) | next unclaimed unit: release store by the control CTA after `desc`; workers
-//           claim units with an acquire fetch-add (dynamic balancing across chains).
-//   done:   units completed since the step began (workers: release add; control: polls, then fences).
+//   desc:   {epoch id, cmd, n_jobs, total units}: ONE aligned 16-byte store by the chain's control CTA after a release
+//           fence; the worker groups poll it with one 16-byte load (a single L2 round trip tells a group that an epoch
+//           started and what it is).
+//   done:   serving groups that have finished their share of the step's epochs (workers: release add; the control
+//           CTA polls, then fences).
+//   pad[1..2] hold the publication time stamp of the profiling build (-DBK_PROFILE_CTRL).
 struct __align__(128) ChainSync {
   uint4 desc;
-  unsigned long long ticket;
+  unsigned long long reserved0;   // (was the claim ticket of the dynamic scheduler)
   unsigned int done;
   unsigned int pad[25];
 };
