@@ -174,3 +174,17 @@ def test_edge_cases():
             vi, st = o.step(d < 5, 1.0)
             assert st.error_flags == 0
         assert np.all(np.isfinite(o.sum_trees()))
+
+
+def test_forest_invariants_hold_for_the_oracle():
+    """The size-independent properties the full-size GPU tests rely on (tests/test_gpu_fullsize.py), checked on the oracle."""
+    from helpers import check_forest_invariants
+
+    for lik in (0, 1):
+        X, y, _ = friedman(3000, 8, 31, kind="bernoulli" if lik else "normal")
+        s = make_settings(X, y, m=20, num_particles=16, seed=31, likelihood=lik)
+        o = OracleChain(s, X.T.copy(), y)
+        for d in range(40):
+            o.step(d < 20, 1.0)
+        nodes, nn = o.forest()
+        check_forest_invariants(nodes, nn, o.leaf_ids(), o.sum_trees(), 3000)
