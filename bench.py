@@ -29,7 +29,7 @@ CONFIGS = {
     "C1": (200, 5, 10, 20, 1, 1, 0, 1),
     "C2": (100_000, 10, 50, 40, 4, 2, 0, 1),
     "C3": (50_000, 20, 100, 40, 4, 3, 1, 1),
-    "C4": (50_000, 15, 50, 40, 1, 4, 0, 3),
+    "C4": (50_000, 15, 50, 40, 4, 4, 0, 3),
     "C5": (1_000_000, 50, 200, 60, 1, 5, 0, 1),   # 8 chains = one per GPU on the 8xB200 box
 }
 
@@ -311,6 +311,8 @@ def main():
                 "draws_timed": f"{n_tune} tuning + {steps - n_tune} post-tuning",
                 "l2": "256 MB fill between timed steps (L2 flushed)" if flush is not None else "no flush (working set stays in L2)",
                 "grow_events_per_tree_update": g_all / max(t_all, 1.0),
+                "tree_updates_per_s": t_all / (total_ms_max / 1e3),
+                "grow_events_per_s": g_all / (total_ms_max / 1e3),
                 "rounds_per_tree_update": rounds / max(tupd, 1),
                 "grid_phases_per_step": phases / steps,
             },
