@@ -177,7 +177,7 @@ def test_edge_cases():
 
 
 def test_forest_invariants_hold_for_the_oracle():
-    """The size-independent properties the full-size GPU tests rely on (tests/test_gpu_fullsize.py), checked on the oracle."""
+    """The size-independent properties the full-size GPU tests rely on (tests/test_gpu_z_fullsize.py), checked on the oracle."""
     from helpers import check_forest_invariants
 
     for lik in (0, 1):
