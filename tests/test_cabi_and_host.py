@@ -121,3 +121,77 @@ def test_device_sampler_refuses_to_run_without_cuda():
     X = np.zeros((10, 2)); Y = np.arange(10.0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         DeviceSampler(make_settings(X, Y, m=2, num_particles=3), X, Y)
+
+
+class _FakeCore:
+    """Stands in for core.DeviceSampler (no GPU): deterministic counters instead of a sampler, same surface."""
+
+    def __init__(self, settings, X, Y):
+        G = max(1, settings.n_groups)
+        self.N, self.p, self.m, self.G = settings.n_rows, settings.n_cols, settings.n_trees, G
+        self.C = settings.n_chains * G
+        self.calls = 0
+        self.h2d_bytes = 0
+
+    def enable_host_output(self, enable=True):
+        self.host_output = enable
+
+    def step(self, tune, sigma):
+        self.calls += 1
+        vi = np.zeros((self.C, self.p), dtype=np.int32)
+        if not tune:
+            vi[:, 0] = np.arange(self.C) + 1          # virtual chain vc used variable 0 (vc + 1) times
+        return vi, [None] * self.C
+
+    def sum_trees_host(self):
+        return np.arange(self.C * self.N, dtype=np.float32).reshape(self.C, self.N) + 1000 * self.calls
+
+    def forest(self, c):
+        nodes = np.zeros((self.m, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
+        nodes["value"][:, 0] = c
+        return nodes, np.ones(self.m, dtype=np.int32)
+
+    def trees(self, c, first, count):
+        nodes = np.zeros((count, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
+        nodes["value"][:, 0] = 100 * self.calls + c
+        return nodes, np.ones(count, dtype=np.int32)
+
+    def close(self):
+        pass
+
+
+def test_pgbart_step_protocol_with_a_fake_core(monkeypatch):
+    """Host logic of PGBART.astep without a GPU: value shapes for (chains, output groups), one inclusion string per
+    BART variable (groups summed), round-robin tree batches in the history, one all_trees entry per chain."""
+    import pymc_bart_b200.pgbart as pg
+    from pymc_bart_b200.utils import _decode_vi
+
+    monkeypatch.setattr(pg, "DeviceSampler", _FakeCore)
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(30, 3)); Y = rng.normal(size=(2, 30))
+    mu = BART("w", X, Y, m=20, shape=(2, 30), separate_trees=True)
+    step = pg.PGBART([mu], num_particles=4, chains=3, batch=(0.1, 0.25))     # 2 trees per tuning draw, 5 after
+    assert step.tune and step.core.host_output and type(mu.owner.op).n_outputs == 2
+    v, st = step.astep()
+    assert v.shape == (3, 2, 30) and len(st) == 3 and st[0] == {"variable_inclusion": "AAAA", "tune": True}
+    assert v[1, 1, 0] == 1000 + (1 * 2 + 1) * 30                           # chain-major, group-minor rows of the core
+    v2, _ = step.astep()
+    assert v[0, 0, 0] == 1000 and v2[0, 0, 0] == 2000                        # a fresh array every draw
+    step.stop_tuning()
+    for d in range(5):
+        v, st = step.astep()
+    assert [_decode_vi(s["variable_inclusion"], 3)[0] for s in st] == [1 + 2, 3 + 4, 5 + 6]   # groups of a chain summed
+    firsts = [b[0] for b in step._batches[0]]
+    assert firsts == [4, 9, 14, 19, 0]                                       # 2 tuning draws x 2 trees, then 5 per draw ...
+    assert [b[1].shape[0] for b in step._batches[0]] == [5, 5, 5, 1, 5]      # ... the batch that reaches m is cut there (B10)
+    step.publish_history(); step.publish_history()
+    op = mu.owner.op
+    assert len(op.all_trees) == 3                                            # one entry per chain (utils.py:117), published once
+    base, batches = op.all_trees[2]
+    assert len(base) == 2 and len(batches) == 2 and len(batches[1]) == 5    # per output group inside the chain's entry
+    assert base[1][0]["value"][0, 0] == 2 * 2 + 1                            # baseline of (chain 2, group 1) = virtual chain 5
+    with pytest.raises(ValueError):
+        pg.PGBART([mu, mu])
+    with pytest.raises(TypeError):
+        pg.PGBART([object()])
+    step.close()
