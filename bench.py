@@ -170,8 +170,10 @@ def main():
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        if args.impl == "reference" and args.steps > 12 and args.config != "C1":
-            args.steps, args.warmup = min(args.steps, 6), min(args.warmup, 1)   # bounded sample (minutes, not hours)
+        if args.config != "C1":   # bounded sample of the workload: about 10-30 s of CPU work (minutes, not hours)
+            N_, m_ = cfg[0], cfg[2]
+            cap = max(2, int(2e7 / (N_ * max(1, int(0.1 * m_)))))
+            args.steps, args.warmup = min(args.steps, cap), min(args.warmup, 1)
         run_reference(args, cfg)
         return
 
