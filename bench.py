@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py — PGBART draws/sec on synthetic Friedman data (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C1|C5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C1|C3|C4|C5] [--no-c5]
 
 One "step" = one PGBART step (astep) of every chain batched on a GPU = one draw per chain.
-At N=1 the workload is BASELINE.json configs[1] (C2: N=100k, p=10, m=50, 40 particles, 4 chains
-on one B200).  With --gpus N (launched by torchrun) every rank runs its own 4 chains (weak
-scaling: chains are independent, no data-path collective); the one NCCL all-gather of the run
-(posterior mean of each chain) is inside the timed region.
+The headline workload is BASELINE.json configs[1] (C2: N=100k, p=10, m=50, 40 particles, 4 chains on one B200).
+The same line carries a SECOND measured workload under ``config.c5``: BASELINE.json configs[4] (C5: N=1M, p=50,
+m=200, 60 particles, one chain per GPU = the "8 chains sharded across 8xB200" shard), the HBM-bound case, so that
+the driver's 1/2/4/8-GPU runs report both N=1e5 and N=1e6 (north_star).
+With --gpus N (launched by torchrun) every rank runs its own chains (weak scaling: chains are independent, no
+data-path collective); the run's single collective — one NCCL all-gather of the posterior draws, as
+pymc_bart_b200.sampling.gather_posterior does it — is inside the timed region.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -67,7 +70,8 @@ def algorithmic_bytes(N, grow_events, tree_updates, tune_updates, lik=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons; started before the warm-up (nvidia-smi needs ~0.5 s to produce its first
+    row), rows are stamped on arrival and only those inside [mark_begin, mark_end] count."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -76,10 +80,11 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.gpu = str(gpu_index)
+        self.windows = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", self.gpu], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -87,74 +92,268 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        sm, smax, reasons, n_all = [], [], set(), 0
+        for t, r in self.rows:
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                v_sm, v_max = float(r[1]), float(r[2])
             except Exception:
-                pass
+                continue
+            n_all += 1
+            if not any(a - 0.02 <= t <= b + 0.02 for a, b in self.windows):
+                continue
+            sm.append(v_sm); smax.append(v_max)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_whole_run": n_all}
 
 
-def run_reference(args, cfg):
-    """The reference's CPU path: oracle/ port (bartrs is not installable offline), one chain per host thread."""
+# ---------------------------------------------------------------------------------------------- reference arm (CPU)
+def oracle_sample(name, cfg, n_chains, steps, warm, threads):
+    """`steps` draws (half tuning, half post-tuning, like our arm) of `n_chains` oracle chains on `threads` host
+    threads (ctypes releases the GIL).  Returns (draws/s, seconds)."""
     from oracle.oracle_py import OracleChain
     from pymc_bart_b200.settings import make_settings
 
     N, p, m, P, chains, seed, lik, groups = cfg
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     X, y = friedman(N, p, seed, lik, groups)
-    n_chains = chains * max(1, args.gpus)
-    threads = min(os.cpu_count() or 1, n_chains * groups)
     s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1, likelihood=lik, n_groups=groups)
     Xc = np.ascontiguousarray(X.T)
     orcs = [OracleChain(s, Xc, y, chain=c, group=g) for c in range(n_chains) for g in range(groups)]
-    steps, warm = args.steps, args.warmup
-
-    def work(o, n, tune):
-        for _ in range(n):
-            o.step(tune, 1.0)
 
     def run_all(n, tune):
+        if n <= 0:
+            return
         sem = threading.Semaphore(threads)
         ths = []
         for o in orcs:
             def job(o=o):
                 with sem:
-                    work(o, n, tune)
+                    for _ in range(n):
+                        o.step(tune, 1.0)
             t = threading.Thread(target=job); t.start(); ths.append(t)
         for t in ths:
             t.join()
 
     run_all(warm, True)
     t0 = time.perf_counter()
-    run_all(steps // 2, True)            # same mix as our arm: half tuning, half post-tuning draws
-    run_all(steps - steps // 2, False)
+    run_all(steps - steps // 2, True)
+    run_all(steps // 2, False)
     dt = time.perf_counter() - t0
-    val = n_chains * steps / dt
+    return n_chains * steps / dt, dt, s.batch_tune
+
+
+def bounded_cpu_steps(cfg, steps, n_chains, threads):
+    """About 10-30 s of CPU work: one chain-draw of the oracle costs ~0.4 us x N x trees/draw x P/40 on the B200
+    hosts (C2: 0.2 s, C5: 12 s; about 2.5x that in the build container)."""
+    N, p, m, P = cfg[:4]
+    per_draw = 400e-9 * N * max(1, int(0.1 * m)) * P / 40.0 * (2.0 if cfg[6] else 1.0)
+    waves = max(1, -(-n_chains * cfg[7] // threads))
+    return int(max(2, min(steps, 20.0 / (per_draw * waves))))
+
+
+def run_reference(args, cfg):
+    """The reference's CPU path: oracle/ port (bartrs is not installable offline), one chain per host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, p, m, P, chains, seed, lik, groups = cfg
+    n_chains = chains * max(1, args.gpus)
+    threads = max(1, min(os.cpu_count() or 1, n_chains * groups))
+    steps, warm = args.steps, args.warmup
+    if args.config != "C1":
+        steps, warm = bounded_cpu_steps(cfg, steps, n_chains, threads), min(warm, 1)
+    val, dt, tpd = oracle_sample(args.config, cfg, n_chains, steps, warm, threads)
+    config = {"workload": workload_name(args.config, cfg, tpd),
+              "note": f"CPU restatement oracle/pgbart_oracle.c (bartrs unavailable offline), {n_chains} chains x {groups} output "
+                      f"groups on {threads} host threads (ctypes releases the GIL)"}
+    if args.config == "C2" and not args.no_c5:
+        c5 = CONFIGS["C5"]
+        n5 = c5[4] * max(1, args.gpus)
+        th5 = max(1, min(os.cpu_count() or 1, n5))
+        v5, dt5, tpd5 = oracle_sample("C5", c5, n5, 2, 0, th5)
+        config["c5"] = {"workload": workload_name("C5", c5, tpd5), "value": v5, "unit": "draws/s", "ms_per_step": 1e3 * dt5 / 2,
+                        "cpu_baseline": {"value": v5, "unit": "draws/s", "cores": th5, "kind": "port",
+                                         "sample": f"1 tuning + 1 post-tuning draw x {n5} chains, no warm-up"}}
     line = {
         "impl": "reference", "metric": "PGBART draws/sec", "value": val, "unit": "draws/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32+i64", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, cfg, s.batch_tune),
-                   "note": f"CPU restatement oracle/pgbart_oracle.c (bartrs unavailable offline), {n_chains} chains x {groups} output "
-                           f"groups on {threads} host threads (ctypes releases the GIL)"},
+        "dtype": "f32+i64", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": val, "unit": "draws/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps // 2} tuning + {steps - steps // 2} post-tuning draws x {n_chains} chains after {warm} warm-up"},
+                         "sample": f"{steps - steps // 2} tuning + {steps // 2} post-tuning draws x {n_chains} chains after {warm} warm-up"},
         "e2e": {"value": val, "unit": "draws/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm (B200)
+def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src, cpu_baseline=True):
+    """One workload on this rank's GPU: device-timed K steps (+ the all-gather of the draws when world > 1), then the
+    end-to-end leg through PGBART.astep with host buffers.  Returns the dict of measurements (rank 0: complete)."""
+    import torch
+    import torch.distributed as dist
+
+    from pymc_bart_b200.core import DeviceSampler
+    from pymc_bart_b200.settings import make_settings
+
+    cfg = CONFIGS[name]
+    N, p, m, P, chains, seed, lik, groups = cfg
+    X, y = friedman(N, p, seed, lik, groups)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains, chain_base=rank * chains, device=local,
+                      likelihood=lik, n_groups=groups)
+    dev = DeviceSampler(s, X, y)
+    stream = dev.stream()
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    n_tune = steps - steps // 2
+    n_post = steps - n_tune
+    nvc = chains * groups   # (chain, output group) pairs: one forest and one sum-of-trees row each
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the posterior draws stay on the device: ring [draw, chain x group, N]; gathered once at the end
+    draws_dev = torch.empty((max(n_post, 1), nvc, N), dtype=torch.float32, device="cuda")
+    gathered = None
+    if world > 1:
+        gathered = torch.empty((world * draws_dev.shape[0], *draws_dev.shape[1:]), dtype=torch.float32, device="cuda")
+    for i in range(warm):
+        dev.step(True, 1.0)
+    if world > 1:   # warm the communicator with the collective of the timed region (channel / NVLS setup is not the run's cost)
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(gathered, draws_dev)
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    grow = tupd = tune_upd = rounds = phases = 0
+    t_w0 = time.perf_counter()
+    for i in range(steps):
+        tune = i < n_tune
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(i & 0xFF)   # untimed: evicts the working set from the 126 MB L2
+        ev[i][0].record(stream)
+        dev.step_launch(tune, 1.0)
+        if not tune:
+            with torch.cuda.stream(stream):
+                draws_dev[i - n_tune].copy_(dev.sum_trees(), non_blocking=True)   # the draw is kept (inside the timed step)
+        ev[i][1].record(stream)
+        _, st = dev.step_wait()
+        for c in range(nvc):
+            grow += st[c].grow_events; tupd += st[c].tree_updates; rounds += st[c].rounds
+            tune_upd += st[c].tree_updates if tune else 0
+        phases += st[0].phases
+    t_gather0 = torch.cuda.Event(enable_timing=True); t_gather1 = torch.cuda.Event(enable_timing=True)
+    t_gather0.record(stream)
+    if world > 1:   # the run's single collective (sampling.gather_posterior): ordered after the steps on their stream
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(gathered, draws_dev)
+    t_gather1.record(stream)
+    torch.cuda.synchronize()
+    clocks.window(t_w0, time.perf_counter())
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    gather_ms = t_gather0.elapsed_time(t_gather1) if world > 1 else 0.0
+    total_ms = float(sum(step_ms)) + gather_ms
+    tm = torch.tensor([total_ms, gather_ms], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([float(grow), float(tupd), float(tune_upd)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    total_ms_max, gather_ms_max = [float(v) for v in tm.tolist()]
+    g_all, t_all, tu_all = [float(v) for v in agg.tolist()]
+    value = world * chains * steps / (total_ms_max / 1e3)
+    out = {"value": value, "unit": "draws/s", "ms_per_step": total_ms_max / steps, "steps": steps, "warmup": warm}
+    if args.profile_only:
+        dev.close()
+        return out
+
+    # ---------------- end to end through the public step API (host buffers, copies inside the timed region)
+    from pymc_bart_b200 import BART
+    from pymc_bart_b200.pgbart import PGBART
+
+    dev.close()
+    del dev, draws_dev, gathered
+    torch.cuda.synchronize()
+    e2e_steps = max(10, steps // 4)
+    t0 = time.perf_counter()
+    rv = BART("mu", X, y, m=m, shape=(groups, N) if groups > 1 else None, separate_trees=groups > 1)
+    stp = PGBART([rv], num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=True,
+                 likelihood="bernoulli" if lik else "normal")
+    t_build = time.perf_counter() - t0
+    for i in range(3):
+        stp.astep()
+    sync_all()
+    t_w0 = time.perf_counter()
+    for i in range(e2e_steps):
+        if i == e2e_steps // 2:
+            stp.stop_tuning()
+        val_host, stats = stp.astep()      # H2D sigma, step kernel, D2H sum-of-trees + VI counts + stats (+ tree history after tuning)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t_w0
+    clocks.window(t_w0, time.perf_counter())
+    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * chains * e2e_steps / float(e2e_t.item())
+    h2d = nvc * 4
+    d2h = nvc * N * 4 + nvc * p * 4 + nvc * 64 + 4 + int(getattr(stp, "history_bytes_per_step", 0))
+    h2d_once = stp.core.h2d_bytes
+    stp.close()
+    del stp
+    if rank != 0:
+        return out
+
+    ms_kernel = float(np.mean(step_ms))
+    bytes_per_launch = algorithmic_bytes(N, grow / steps, tupd / steps, tune_upd / steps, lik)
+    achieved = bytes_per_launch / (ms_kernel / 1e3) / 1e9
+    traffic = traffic_src = None
+    try:   # DRAM bytes per launch of the same command under `ncu --set full` (profiles/, committed)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name, {})
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    except Exception:
+        pass
+    out.update({
+        "workload": workload_name(name, cfg, s.batch_tune),
+        "draws_timed": f"{n_tune} tuning + {n_post} post-tuning",
+        "l2": "256 MB fill between timed steps (L2 flushed)" if flush is not None else "no flush (working set stays in L2)",
+        "grow_events_per_tree_update": g_all / max(t_all, 1.0),
+        "tree_updates_per_s": t_all / (total_ms_max / 1e3),
+        "grow_events_per_s": g_all / (total_ms_max / 1e3),
+        "rounds_per_tree_update": rounds / max(tupd, 1),
+        "grid_phases_per_step": phases / steps,
+        "gather_ms": gather_ms_max,
+        "gather_bytes_per_rank": int(n_post * nvc * N * 4) if world > 1 else 0,
+        "e2e": {"value": e2e_val, "unit": "draws/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build,
+                "history": "store_history=True: after tuning every step's rewritten trees are exported (op.all_trees protocol)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "frac_dram_traffic": (traffic / (ms_kernel / 1e3) / 1e9 / peak) if traffic else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "kernel": "pgbart_step_kernel", "kernel_ms": ms_kernel},
+    })
+    if cpu_baseline:
+        # ---------------- CPU baseline: the oracle on the host cores, bounded sample of the same workload
+        try:
+            ncpu = max(1, min((os.cpu_count() or 1) // groups, chains))   # chains sampled; each needs `groups` threads
+            nd = args.cpu_draws or bounded_cpu_steps(cfg, 40, ncpu, ncpu * groups)
+            v, cdt, _ = oracle_sample(name, cfg, ncpu, nd, 0, ncpu * groups)
+            out["cpu_baseline"] = {"value": v, "unit": "draws/s", "cores": ncpu * groups, "kind": "port",
+                                   "sample": f"{nd - nd // 2} tuning + {nd // 2} post-tuning draws x {ncpu} chains of {name} in {cdt:.1f} s, "
+                                             f"one chain per host thread (oracle/pgbart_oracle.c, gcc -O3; bartrs is not installable offline)"}
+        except Exception as e:  # noqa
+            out["cpu_baseline"] = {"value": None, "unit": "draws/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    return out
 
 
 def main():
@@ -165,25 +364,19 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-c5", action="store_true", help="skip the second workload (config.c5)")
+    ap.add_argument("--c5-steps", type=int, default=30)
     ap.add_argument("--cpu-draws", type=int, default=None, help="CPU baseline sample size (draws per chain)")
     ap.add_argument("--profile-only", action="store_true", help="device-timed leg only (for ncu runs)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        if args.config != "C1":   # bounded sample of the workload: about 10-30 s of CPU work (minutes, not hours)
-            N_, m_ = cfg[0], cfg[2]
-            cap = max(2, int(2e7 / (N_ * max(1, int(0.1 * m_)))))
-            args.steps, args.warmup = min(args.steps, cap), min(args.warmup, 1)
         run_reference(args, cfg)
         return
 
     import torch
     import torch.distributed as dist
 
-    from pymc_bart_b200.core import DeviceSampler
-    from pymc_bart_b200.settings import make_settings
-
-    N, p, m, P, chains, seed, lik, groups = cfg
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,162 +384,41 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     steps, warm = args.steps, max(3, args.warmup)
-    X, y = friedman(N, p, seed, lik, groups)
-    s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains, chain_base=rank * chains, device=local,
-                      likelihood=lik, n_groups=groups)
-    dev = DeviceSampler(s, X, y)
-    stream = dev.stream()
-    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    n_tune = steps // 2
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident throughput (value): K steps, CUDA events on the launch stream
-    for i in range(warm):
-        dev.step(True, 1.0)
-    sync_all()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     clocks = ClockSampler(local)
     clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    grow = tupd = tune_upd = rounds = phases = 0
-    nvc = chains * groups   # (chain, output group) pairs: one forest and one sum-of-trees row each
-    post_mean = torch.zeros((nvc, N), dtype=torch.float32, device="cuda")
-    for i in range(steps):
-        tune = i < n_tune
-        if flush is not None:
-            with torch.cuda.stream(stream):
-                flush.fill_(i & 0xFF)   # untimed: evicts the working set from the 126 MB L2
-        ev[i][0].record(stream)
-        dev.step_launch(tune, 1.0)
-        ev[i][1].record(stream)
-        _, st = dev.step_wait()
-        for c in range(nvc):
-            grow += st[c].grow_events; tupd += st[c].tree_updates; rounds += st[c].rounds
-            tune_upd += st[c].tree_updates if tune else 0
-        phases += st[0].phases
-        if not tune:
-            with torch.cuda.stream(stream):
-                post_mean += dev.sum_trees()
-    t_gather0 = torch.cuda.Event(enable_timing=True); t_gather1 = torch.cuda.Event(enable_timing=True)
-    t_gather0.record(stream)
-    if world > 1:  # the run's single collective: all-gather of the chains' posterior means
-        stream.synchronize()
-        gathered = [torch.empty_like(post_mean) for _ in range(world)]
-        dist.all_gather(gathered, post_mean)
-    t_gather1.record(stream)
-    torch.cuda.synchronize()
+    main_m = measure(args.config, steps, warm, args, rank, world, local, clocks, peak, peak_src)
+    c5_m = None
+    if args.config == "C2" and not args.no_c5 and not args.profile_only:
+        c5_m = measure("C5", max(25, args.c5_steps), 5, args, rank, world, local, clocks, peak, peak_src, cpu_baseline=False)
     clk = clocks.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms)) + (t_gather0.elapsed_time(t_gather1) if world > 1 else 0.0)
-    tm = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    agg = torch.tensor([float(grow), float(tupd), float(tune_upd)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    total_ms_max = float(tm.item())
-    g_all, t_all, tu_all = [float(v) for v in agg.tolist()]
-    value = world * chains * steps / (total_ms_max / 1e3)
-
-    if args.profile_only:
-        if rank == 0:
-            print(json.dumps({"profile_only": True, "value": value, "ms_per_step": total_ms_max / steps}), flush=True)
-        return
-    # ---------------- end to end through the public step API (host buffers, copies inside the timed region)
-    from pymc_bart_b200 import BART
-    from pymc_bart_b200.pgbart import PGBART
-
-    dev.close()
-    del dev
-    torch.cuda.synchronize()
-    e2e_steps = max(10, steps // 4)
-    t0 = time.perf_counter()
-    rv = BART("mu", X, y, m=m, shape=(groups, N) if groups > 1 else None, separate_trees=groups > 1)
-    stp = PGBART([rv], num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=False,
-                 likelihood="bernoulli" if lik else "normal")
-    t_build = time.perf_counter() - t0
-    for i in range(3):
-        stp.astep()
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        if i == e2e_steps // 2:
-            stp.stop_tuning()
-        val_host, stats = stp.astep()      # H2D sigma, step kernel, D2H sum-of-trees + VI counts + stats
-    torch.cuda.synchronize()
-    e2e_dt = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_val = world * chains * e2e_steps / float(e2e_t.item())
-    h2d = nvc * 4
-    d2h = nvc * N * 4 + nvc * p * 4 + nvc * 64 + 4
-    h2d_once = stp.core.h2d_bytes
-    stp.close()
-
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # roofline of the dominant (only) kernel: pgbart_step_kernel, one launch per step
-        ms_kernel = float(np.mean(step_ms))
-        bytes_per_launch = algorithmic_bytes(N, grow / steps, tupd / steps, tune_upd / steps, lik)
-        achieved = bytes_per_launch / (ms_kernel / 1e3) / 1e9
-        traffic = None
-        try:   # DRAM bytes per launch of the same command under `ncu --set full` (profiles/, committed)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.config, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        line = {
-            "metric": "PGBART draws/sec", "value": value, "unit": "draws/s", "n_gpus": world, "steps": steps, "warmup": warm,
-            "ms_per_step": total_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+i64", "data": "synthetic",
-            "config": {
-                "workload": workload_name(args.config, cfg, s.batch_tune),
-                "draws_timed": f"{n_tune} tuning + {steps - n_tune} post-tuning",
-                "l2": "256 MB fill between timed steps (L2 flushed)" if flush is not None else "no flush (working set stays in L2)",
-                "grow_events_per_tree_update": g_all / max(t_all, 1.0),
-                "tree_updates_per_s": t_all / (total_ms_max / 1e3),
-                "grow_events_per_s": g_all / (total_ms_max / 1e3),
-                "rounds_per_tree_update": rounds / max(tupd, 1),
-                "grid_phases_per_step": phases / steps,
-            },
-            "gpu_launches": steps,
-            "e2e": {"value": e2e_val, "unit": "draws/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel": "pgbart_step_kernel",
-                         "kernel_ms": ms_kernel},
-            "clocks": clk,
-        }
-        # ---------------- CPU baseline: the oracle on the host cores, bounded sample of the same workload
-        try:
-            from oracle.oracle_py import OracleChain
-
-            s1 = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1, likelihood=lik, n_groups=groups)
-            Xc = np.ascontiguousarray(X.T)
-            ncpu = max(1, min((os.cpu_count() or 1) // groups, chains))   # chains sampled; each needs `groups` threads
-            orcs = [OracleChain(s1, Xc, y, chain=c, group=g) for c in range(ncpu) for g in range(groups)]
-            nd = args.cpu_draws or (3 if N >= 100_000 else (20 if N >= 10_000 else 100))
-            t0 = time.perf_counter()
-            ths = [threading.Thread(target=lambda o=o: [o.step(True, 1.0) for _ in range(nd)]) for o in orcs]
-            [t.start() for t in ths]; [t.join() for t in ths]
-            cdt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": ncpu * nd / cdt, "unit": "draws/s", "cores": ncpu * groups, "kind": "port",
-                                    "sample": f"{nd} tuning draws x {ncpu} chains of {args.config}, one chain per host thread "
-                                              f"(oracle/pgbart_oracle.c; bartrs is not installable offline)"}
-        except Exception as e:  # noqa
-            line["cpu_baseline"] = {"value": None, "unit": "draws/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        if args.profile_only:
+            print(json.dumps({"profile_only": True, "value": main_m["value"], "ms_per_step": main_m["ms_per_step"]}), flush=True)
+        else:
+            config = {k: main_m[k] for k in ("workload", "draws_timed", "l2", "grow_events_per_tree_update", "tree_updates_per_s",
+                                             "grow_events_per_s", "rounds_per_tree_update", "grid_phases_per_step", "gather_ms",
+                                             "gather_bytes_per_rank")}
+            if c5_m is not None:
+                c5_m["n_gpus"] = world
+                c5_m["gpu_launches"] = c5_m["steps"]
+                config["c5"] = c5_m
+            line = {
+                "metric": "PGBART draws/sec", "value": main_m["value"], "unit": "draws/s", "n_gpus": world, "steps": steps, "warmup": warm,
+                "ms_per_step": main_m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32+i64", "data": "synthetic", "config": config,
+                "gpu_launches": steps, "e2e": main_m["e2e"], "roofline": main_m["roofline"], "clocks": clk,
+                "cpu_baseline": main_m.get("cpu_baseline"),
+            }
+            print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -40,7 +40,7 @@
  *   B9  final systematic resampling over all P + uniform pick; commit
  *   B10 batch of max(1,int(m*batch)) trees per step, round robin
  *
- * Build: see oracle/Makefile (gcc -O2 -march=x86-64-v3 -ffp-contract=off).
+ * Build: see oracle/Makefile (gcc -O3 -funroll-loops -march=x86-64-v3 -ffp-contract=off).
  */
 #include <math.h>
 #include <stdint.h>

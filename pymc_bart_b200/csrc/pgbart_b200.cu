@@ -1706,6 +1706,21 @@ static void set_err(const char* fmt, const char* a = "", const char* b = "") { s
     if (e_ != cudaSuccess) { set_err("CUDA error %s at %s", cudaGetErrorString(e_), #call); return BK_ERR_CUDA; } \
   } while (0)
 
+// Every entry point runs on the handle's device and puts the caller's current device back (the host is a torch
+// process whose current device must not change under its feet).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                                                                                              \
+  DeviceGuard guard_(dev);                                                                                          \
+  if (guard_.err != cudaSuccess) { set_err("CUDA error %s selecting the device", cudaGetErrorString(guard_.err)); return BK_ERR_CUDA; }
+
 struct bk_handle_s {
   bk_settings s;
   Params P;
@@ -1721,6 +1736,7 @@ struct bk_handle_s {
   int32_t* abort_pinned;
   float* st_pinned;       // [C][n_rows] host copy of the sum of trees (bk_set_host_output)
   int host_output;
+  int poisoned;           // a step timed out: trees / sum of trees may be half rewritten, the handle refuses further steps
   int32_t* marker_host;
   int marker_count;
 };
@@ -1779,6 +1795,9 @@ static int make_layout(const bk_settings* s, Layout* L) {
   return BK_OK;
 }
 
+static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, const float* X_dev, const float* y_dev,
+                       float* sum_trees_dev, void* workspace_dev);
+
 extern "C" {
 
 int bk_abi_version(void) { return BK_ABI_VERSION; }
@@ -1803,11 +1822,21 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   if (((uintptr_t)X_dev | (uintptr_t)y_dev | (uintptr_t)sum_trees_dev | (uintptr_t)workspace_dev) & 15) {
     set_err("device pointers must be 16-byte aligned"); return BK_ERR_ARG;
   }
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   bk_handle* h = new (std::nothrow) bk_handle();
   if (!h) { set_err("out of host memory"); return BK_ERR_ARG; }
   memset(h, 0, sizeof(*h));
   h->s = *s;
+  rc = create_body(h, s, L, X_dev, y_dev, sum_trees_dev, workspace_dev);
+  if (rc != BK_OK) { bk_destroy(h); return rc; }   // stream, pinned buffers and the handle go with it
+  *out = h;
+  return BK_OK;
+}
+
+}  // extern "C"
+
+static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, const float* X_dev, const float* y_dev,
+                       float* sum_trees_dev, void* workspace_dev) {
   char* w = (char*)workspace_dev;
   Params& P = h->P;
   P.N = s->n_rows; P.Npad = L.Npad; P.p = s->n_cols; P.m = s->n_trees; P.P = s->n_particles;
@@ -1879,25 +1908,29 @@ int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev, floa
   pgbart_init_cum_kernel<<<P.C, 32, 0, h->stream>>>(P);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
-  *out = h;
   return BK_OK;
 }
 
+extern "C" {
+
 void bk_destroy(bk_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->s.device);
+  DeviceGuard guard_(h->s.device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->vi_pinned) cudaFreeHost(h->vi_pinned);
   if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
   if (h->sigma_pinned) cudaFreeHost(h->sigma_pinned);
   if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
   if (h->st_pinned) cudaFreeHost(h->st_pinned);
+  if (h->P.marker) cudaFree(h->P.marker);
+  free(h->marker_host);
   delete h;
 }
 
 int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
-  CK(cudaSetDevice(h->s.device));
+  if (h->poisoned) { set_err("an earlier step timed out inside the kernel; the sampler state is undefined: create a new handle"); return BK_ERR_STATE; }
+  ON_DEVICE(h->s.device);
   Params& P = h->P;
   for (int c = 0; c < P.C; ++c) {
     float sg = sigma_host ? sigma_host[c] : 1.0f;
@@ -1906,6 +1939,7 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
   }
   CK(cudaMemcpyAsync(h->sigma_dev, h->sigma_pinned, (size_t)P.C * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(P.sync, 0, (size_t)P.C * sizeof(ChainSync), h->stream));
+  CK(cudaMemsetAsync(P.abort_flag, 0, sizeof(int32_t), h->stream));   // a timed-out step does not poison the next one
   int tune_i = tune ? 1 : 0;
   const float* sig = h->sigma_dev;
   int maxp = h->max_phases;
@@ -1926,7 +1960,7 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
 
 int bk_set_host_output(bk_handle* h, int enable) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
-  CK(cudaSetDevice(h->s.device));
+  ON_DEVICE(h->s.device);
   if (enable && !h->st_pinned) CK(cudaMallocHost(&h->st_pinned, (size_t)h->P.C * h->P.N * sizeof(float)));
   h->host_output = enable ? 1 : 0;
   return BK_OK;
@@ -1936,10 +1970,10 @@ const float* bk_sum_trees_host(bk_handle* h) { return (h && h->host_output) ? h-
 
 int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
-  CK(cudaSetDevice(h->s.device));
+  ON_DEVICE(h->s.device);
   Params& P = h->P;
   CK(cudaStreamSynchronize(h->stream));
-  if (*h->abort_pinned) { set_err("a dataflow wait timed out inside the step kernel"); return BK_ERR_TIMEOUT; }
+  if (*h->abort_pinned) { h->poisoned = 1; set_err("a dataflow wait timed out inside the step kernel"); return BK_ERR_TIMEOUT; }
   if (vi_counts_host) memcpy(vi_counts_host, h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t));
   if (stats_host) memcpy(stats_host, h->stats_pinned, (size_t)P.C * sizeof(bk_step_stats));
   for (int c = 0; c < P.C; ++c)
@@ -1994,7 +2028,7 @@ int32_t* bk_debug_markers(bk_handle* h, int* count) {
 
 int bk_read_trace(bk_handle* h, int chain, bk_trace_rec* out_host, int capacity) {
   if (!h || chain < 0 || chain >= h->P.C || !out_host) { set_err("bad argument"); return BK_ERR_ARG; }
-  if (cudaSetDevice(h->s.device) != cudaSuccess) return BK_ERR_CUDA;
+  ON_DEVICE(h->s.device);
   int n = h->stats_pinned[chain].trace_len;
   if (n > h->P.trace_cap) n = h->P.trace_cap;
   if (n > capacity) n = capacity;
@@ -2009,7 +2043,7 @@ int bk_export_trees(bk_handle* h, int chain, int first, int count, bk_node* node
     set_err("bad argument"); return BK_ERR_ARG;
   }
   if (count == 0) return BK_OK;
-  CK(cudaSetDevice(h->s.device));
+  ON_DEVICE(h->s.device);
   const Params& P = h->P;
   CK(cudaMemcpy(n_nodes_host, P.forest_nn + (size_t)chain * P.m + first, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost));
   DNode* tmp = (DNode*)malloc((size_t)BK_MAX_NODES * sizeof(DNode));
@@ -2030,7 +2064,7 @@ int bk_export_trees(bk_handle* h, int chain, int first, int count, bk_node* node
 
 int bk_export_forest(bk_handle* h, int chain, bk_node* nodes_host, int32_t* n_nodes_host) {
   if (!h || chain < 0 || chain >= h->P.C || !nodes_host || !n_nodes_host) { set_err("bad argument"); return BK_ERR_ARG; }
-  CK(cudaSetDevice(h->s.device));
+  ON_DEVICE(h->s.device);
   const Params& P = h->P;
   size_t cnt = (size_t)P.m * BK_MAX_NODES;
   DNode* tmp = (DNode*)malloc(cnt * sizeof(DNode));
@@ -2053,7 +2087,7 @@ int bk_export_forest(bk_handle* h, int chain, bk_node* nodes_host, int32_t* n_no
 
 int bk_export_leaf_ids(bk_handle* h, int chain, uint8_t* ids_host) {
   if (!h || chain < 0 || chain >= h->P.C || !ids_host) { set_err("bad argument"); return BK_ERR_ARG; }
-  CK(cudaSetDevice(h->s.device));
+  ON_DEVICE(h->s.device);
   const Params& P = h->P;
   CK(cudaMemcpy2D(ids_host, (size_t)P.N, P.ids_tree + (size_t)chain * P.m * P.Npad, (size_t)P.Npad, (size_t)P.N, (size_t)P.m,
                   cudaMemcpyDeviceToHost));
@@ -2065,7 +2099,7 @@ int bk_predict(int device, void* stream, const bk_node* forests_dev, const int32
                const int32_t* split_rules_dev, float* out_dev) {
   (void)n_nodes_dev;
   if (!forests_dev || !X_dev || !draw_idx_dev || !out_dev || n < 0 || n_idx < 0) { set_err("bad argument"); return BK_ERR_ARG; }
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   long long total = (long long)n * n_idx;
   if (total == 0) return BK_OK;
   int threads = 256;

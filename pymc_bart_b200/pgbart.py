@@ -32,7 +32,7 @@ class PGBART:
 
     def __init__(self, vars=None, num_particles=10, batch=(0.1, 0.1), model=None, *, likelihood="normal", sigma=1.0,
                  chains=1, chain_base=0, seed=0, device=0, depth_offset=0, store_history=True, trace_capacity=0,
-                 sigma_name=None, **kwargs):
+                 sigma_name=None, sigma_transform=None, **kwargs):
         if vars is None or len(vars) != 1:
             raise ValueError("PGBART takes exactly one BART variable: PGBART([rv], num_particles=...)")
         rv = vars[0]
@@ -63,6 +63,7 @@ class PGBART:
         self.tune = True
         self.sigma = sigma
         self.sigma_name = sigma_name
+        self.sigma_transform = sigma_transform   # e.g. np.exp when sigma_name is the log-transformed value variable
         self.store_history = bool(store_history)
         self.settings = make_settings(
             op.X, Yarr, m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
@@ -117,8 +118,12 @@ class PGBART:
 
     def step(self, point):
         """PyMC-style: reads the likelihood scale from the point when ``sigma_name`` is set."""
-        if self.sigma_name is not None and self.sigma_name in point:
-            self.sigma = point[self.sigma_name]
+        if self.sigma_name is not None:
+            if self.sigma_name not in point:   # a silently kept default would sample the wrong posterior
+                raise KeyError(f"sigma_name={self.sigma_name!r} is not in the point (keys: {sorted(point)}); PyMC points are keyed "
+                               "by value-variable names (e.g. 'sigma_log__'): pass sigma_transform= to map it back")
+            v = point[self.sigma_name]
+            self.sigma = self.sigma_transform(v) if self.sigma_transform is not None else v
         value, stats = self.astep(None)
         new_point = dict(point)
         new_point[self.vars[0].name] = value

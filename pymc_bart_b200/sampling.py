@@ -23,9 +23,11 @@ def gather_posterior(local, world: int):
 
     if world <= 1:
         return local
-    gathered = [torch.empty_like(local) for _ in range(world)]
-    dist.all_gather(gathered, local.contiguous())
-    return torch.cat(gathered, dim=0)
+    local = local.contiguous()
+    # one preallocated buffer (rank-major concatenation along dim 0), no list copy-outs
+    out = torch.empty((world * local.shape[0], *local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)
+    return out
 
 
 def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1), sigma=1.0, seed=0,

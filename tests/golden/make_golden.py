@@ -26,6 +26,36 @@ CASES = {
 }
 
 
+# Large / deep cases (the code paths only the big configs reach).  Arrays of N rows are stored as sha256
+# digests: (N, p, m, P, draws, seed, depth_offset, sigma)
+BIG_CASES = {
+    "big_n200k_p6_m4_P8": (200_000, 6, 4, 8, 6, 21, 0, 1.0),
+    "big_c5shape_n1m_p50_m2_P60": (1_000_000, 50, 2, 60, 3, 5, 0, 1.0),
+    "deep_n2000_p5_m4_P60": (2000, 5, 4, 60, 16, 23, 1, 0.05),
+}
+
+
+def _sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()
+
+
+def run_big_case(N, p, m, P, draws, seed, depth_offset, sigma):
+    X, y, _ = friedman(N, p, seed)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=depth_offset, trace_capacity=40000)
+    o = OracleChain(s, X.T.copy(), y)
+    traces, shas, vis = [], [], []
+    for d in range(draws):
+        vi, st = o.step(d < draws // 2, sigma)
+        traces.append(o.trace().copy())
+        shas.append(_sha(o.sum_trees()))
+        vis.append(vi.copy())
+    nodes, nn = o.forest()
+    return dict(trace=np.concatenate(traces), trace_len=np.array([len(t) for t in traces]), sum_trees_sha=np.array(shas),
+                vi=np.stack(vis), forest=nodes, forest_nn=nn, leaf_ids_sha=np.array(_sha(o.leaf_ids())), sigma=np.array(sigma))
+
+
 def run_case(N, p, m, P, draws, seed, depth_offset, lik=0):
     X, y, _ = friedman(N, p, seed, kind="bernoulli" if lik else "normal")
     s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=depth_offset, trace_capacity=20000, likelihood=lik)
@@ -49,4 +79,9 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         np.savez_compressed(os.path.join(out, name + ".npz"), cfg=np.array(cfg), **run_case(*cfg))
+        print("wrote", name)
+    for name, cfg in BIG_CASES.items():
+        if only and name not in only:
+            continue
+        np.savez_compressed(os.path.join(out, name + ".npz"), cfg=np.array(cfg[:7]), **run_big_case(*cfg))
         print("wrote", name)

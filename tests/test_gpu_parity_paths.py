@@ -1,0 +1,100 @@
+"""Oracle parity on the code paths only BASELINE.json's large configs reach ("What's weak" 1-2):
+
+* `select_split`'s two-level branch (more than 512 row tiles, N > 131 072) incl. a second pass of its inner loop
+  (more than 4096 tiles, N > 1 048 576) and the true C5 row count / particle count with the forest cut to two trees;
+* particles whose trees outgrow the shared-memory node store (`fastF` nodes per particle: 21 at P=60, 10 at P=128)
+  and spill into the global overflow array;
+* non-uniform `split_prior`, more than BK_CUM_SMEM=1024 columns, depth >= 64 (global depth-prior table) and the
+  255-node cap of one-byte leaf ids.
+
+Same bar as tests/test_gpu_parity.py: every trace record, the sum of trees, the forest, every leaf id, the inclusion
+counts and the running leaf sd are bit-identical to the CPU oracle.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_trace_equal, friedman
+from pymc_bart_b200.settings import make_settings
+from test_gpu_parity import run_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_level_member_search_n200k():
+    """782 row tiles: every grow below the root goes through select_split's `per > 4` branch."""
+    assert run_pair(200_000, 6, 4, 8, 6, seed=21)
+
+
+def test_two_level_member_search_second_inner_pass_n1100k():
+    """4297 tiles -> 34 four-tile groups per lane: the second-level scan needs two passes."""
+    assert run_pair(1_100_000, 3, 1, 6, 8, seed=22)
+
+
+def test_config5_shape_two_trees():
+    """configs[4] (N=1M, p=50, P=60) with the forest cut to m=2: the exact tile count, particle count and
+    shared-memory split (fastF=21) of the C5 bench line, three draws against the oracle."""
+    assert run_pair(1_000_000, 50, 2, 60, 3, seed=5)
+
+
+def test_p60_particles_overflow_the_shared_node_store():
+    """P=60 -> 21 nodes per particle in shared memory; sigma=0.05 with the historical depth prior grows trees of
+    up to ~45 nodes, so node reads/writes/copies cross into the global overflow array."""
+    assert run_pair(2000, 5, 4, 60, 16, seed=23, sigma=0.05, depth_offset=1, trace_capacity=40000)
+
+
+def test_p128_max_particles():
+    """The maximum particle count (fastF=10; four resampling slices; 256 pool rows)."""
+    assert run_pair(1500, 4, 3, 128, 10, seed=24, sigma=0.05, depth_offset=1, trace_capacity=60000)
+
+
+def test_non_uniform_split_prior():
+    assert run_pair(400, 6, 5, 12, 30, seed=26, split_prior=[5, 1, 0.5, 3, 0.1, 2])
+
+
+def test_more_columns_than_the_shared_prior_table():
+    """p=1100 > BK_CUM_SMEM: the cumulative prior and the split rules of columns >= 1024 come from global memory,
+    and the tuned prior rebuild takes the sequential branch."""
+    assert run_pair(300, 1100, 4, 10, 20, seed=25)
+
+
+def test_chain_like_trees_depth_over_64_and_node_cap():
+    """OneHot splits on all-distinct columns peel one row per split: depth reaches ~120 (> 64: global depth-prior
+    table) and trees hit the 255-node cap of one-byte leaf ids (grow attempts beyond it are rejected)."""
+    rng = np.random.default_rng(9)
+    N = 120
+    X = np.stack([rng.permutation(N).astype(np.float32), rng.permutation(N).astype(np.float32)], 1)
+    y = (X[:, 0] * 0.1 + rng.normal(0, 1, N)).astype(np.float32)
+    assert run_pair(N, 2, 3, 8, 40, seed=27, sigma=0.02, alpha=0.999, beta=0.001, X=X, y=y, split_rules=["OneHotSplit"] * 2)
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["big_n200k_p6_m4_P8", "big_c5shape_n1m_p50_m2_P60", "deep_n2000_p5_m4_P60"])
+def test_cuda_matches_committed_big_golden(name):
+    """CUDA vs committed digests (tests/golden/make_golden.py BIG_CASES): full trace, sha256 of the sum of trees per
+    draw and of the final leaf ids; no oracle involved."""
+    from pymc_bart_b200.core import DeviceSampler
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    N, p, m, P, draws, seed, off = [int(v) for v in g["cfg"][:7]]
+    sigma = float(g["sigma"])
+    X, y, _ = friedman(N, p, seed)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=off, trace_capacity=40000)
+    dev = DeviceSampler(s, X, y)
+    pos = 0
+    for d in range(draws):
+        vi, st = dev.step(d < draws // 2, sigma)
+        n = int(g["trace_len"][d])
+        assert_trace_equal(dev.trace(0), g["trace"][pos:pos + n], f"{name} draw {d}")
+        pos += n
+        assert _sha(dev.sum_trees().cpu().numpy()[0]) == str(g["sum_trees_sha"][d])
+        assert np.array_equal(vi[0], g["vi"][d])
+    nodes, nn = dev.forest(0)
+    assert np.array_equal(nn, g["forest_nn"]) and np.array_equal(nodes.view(np.uint8), g["forest"].view(np.uint8))
+    assert _sha(dev.leaf_ids(0)) == str(g["leaf_ids_sha"])
+    dev.close()

@@ -42,6 +42,30 @@ def test_oracle_matches_golden(name):
     assert np.array_equal(o.leaf_ids(), g["leaf_ids"])
 
 
+@pytest.mark.parametrize("name", ["big_n200k_p6_m4_P8", "big_c5shape_n1m_p50_m2_P60", "deep_n2000_p5_m4_P60"])
+def test_oracle_matches_big_golden(name):
+    """The digests of the large / deep cases (tests/golden/make_golden.py BIG_CASES) that pin the CUDA paths only
+    BASELINE.json's big configs reach."""
+    import hashlib
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()
+
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    N, p, m, P, draws, seed, off = [int(v) for v in g["cfg"][:7]]
+    X, y, _ = friedman(N, p, seed)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=off, trace_capacity=40000)
+    o = OracleChain(s, X.T.copy(), y)
+    pos = 0
+    for d in range(draws):
+        vi, st = o.step(d < draws // 2, float(g["sigma"]))
+        n = int(g["trace_len"][d])
+        assert_trace_equal(o.trace(), g["trace"][pos:pos + n], f"{name} draw {d}")
+        pos += n
+        assert sha(o.sum_trees()) == str(g["sum_trees_sha"][d])
+    assert sha(o.leaf_ids()) == str(g["leaf_ids_sha"])
+
+
 def _spec_probe():
     """Small C program over include/bk_spec.h: Philox KATs + max error of the math kernels vs libm."""
     src = r'''
