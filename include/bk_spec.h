@@ -309,12 +309,10 @@ typedef struct {
   int32_t n;      /* members                         */
   int64_t sst;    /* sum q(sum_trees)                */
   int64_t sr;     /* sum q(r), r = y - sum_trees_noi */
-  bk_u128 sr2;    /* sum q(r)^2                      */
 } bk_stats;
 
 BK_HD bk_stats bk_stats_sub(bk_stats a, bk_stats b) {
-  bk_stats r; r.n = a.n - b.n; r.sst = a.sst - b.sst; r.sr = a.sr - b.sr;
-  r.sr2 = bk_u128_sub(a.sr2, b.sr2); return r;
+  bk_stats r; r.n = a.n - b.n; r.sst = a.sst - b.sst; r.sr = a.sr - b.sr; return r;
 }
 
 /* leaf value: mean(sum_trees over members)/m + z*leaf_sd, 0 for an empty leaf
@@ -327,15 +325,23 @@ BK_HD float bk_leaf_value(int32_t n, int64_t sst, double inv_qm, double z, float
   return (float)v;
 }
 
-/* Gaussian: sum over members of (r - mu)^2 from (n, sum r, sum r^2) */
-BK_HD double bk_leaf_ssq(bk_stats s, float mu, double inv_qscale) {
+/* Gaussian: for a leaf with value mu, sum over members of (r - mu)^2 = R2_leaf - g with the leaf "gain"
+ *   g = mu * (2 * sum r - n * mu).
+ * Summed over the leaves of a tree the R2_leaf add up to the sum of squares of ALL rows, which does not depend on the
+ * tree: ssq(tree) = R2_total - sum over leaves of g.  A particle therefore carries only its gain sum (updated on a
+ * split as ((G - g_parent) + g_left) + g_right) and no per-leaf sum of squares exists anywhere on the path. */
+BK_HD double bk_leaf_gain(bk_stats s, float mu, double inv_qscale) {
   double r1 = BK_DMUL((double)s.sr, inv_qscale);
-  double r2 = BK_DMUL(BK_DMUL(bk_u128_to_double(s.sr2), inv_qscale), inv_qscale);
   double m = (double)mu;
-  double t = BK_DFMA(m, (double)s.n, BK_DMUL(-2.0, r1));
-  return BK_DFMA(m, t, r2);
+  double t = BK_DFMA(-m, (double)s.n, BK_DMUL(2.0, r1));
+  return BK_DMUL(m, t);
 }
-/* Gaussian log-likelihood of all N rows given the summed per-leaf ssq:
+/* sum of squares of all rows' residuals from the exact 128-bit integer sum of q(r)^2 */
+BK_HD double bk_total_r2(bk_u128 sr2, double inv_qscale) {
+  return BK_DMUL(BK_DMUL(bk_u128_to_double(sr2), inv_qscale), inv_qscale);
+}
+BK_HD double bk_ssq_from_gain(double r2_total, double gain) { return BK_DSUB(r2_total, gain); }
+/* Gaussian log-likelihood of all N rows given ssq = sum (r - mu_leaf)^2:
  * lw = -ssq * inv2s2 + c with the two per-step constants below */
 BK_HD double bk_normal_inv2s2(float sigma) {
   double s = (double)sigma;

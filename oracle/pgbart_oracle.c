@@ -33,7 +33,7 @@
  *       variable ~ split prior; split value = X[k-th member, var]
  *   B4  partition the node's rows (x <= s / x == s)
  *   B5  leaf value = mean(sum_trees over members)/m + z * leaf_sd
- *   B6  log-weight = Gaussian log-likelihood from per-leaf (n, sum r, sum r^2), or Bernoulli-logit
+ *   B6  log-weight = Gaussian log-likelihood from per-leaf (n, sum r) and the tree-independent total sum r^2, or Bernoulli-logit
  *       log-likelihood from a second pass over the rows of the two new leaves (fixed-point terms)
  *   B7  w = exp(lw - max) + 1e-12 in fixed point; exact integer running sums
  *   B8  systematic resampling of particles 1..P-1
@@ -64,7 +64,7 @@ typedef struct {
 typedef struct {
   int32_t n_nodes;
   int32_t q_head; /* expansion queue = nodes [q_head, n_nodes) in creation order */
-  double ssq;
+  double gain;    /* Gaussian: sum over leaves of bk_leaf_gain */
   int64_t llq;    /* Bernoulli: sum of the leaves' ll */
   double lw;
   o_node nodes[BK_MAX_NODES];
@@ -102,13 +102,14 @@ typedef struct bko_s {
   int32_t trace_len, trace_cap;
   uint64_t* w;   /* running sums of the fixed-point weights */
   int32_t* anc;
+  double r2_total;  /* Gaussian: sum of squares of all rows' residuals for the tree being updated */
   long long bytes_touched; /* rough algorithmic byte counter for the CPU baseline */
 } bko;
 
 static void part_alloc(o_particle* q, int N) { q->ids = (uint8_t*)malloc((size_t)N); }
 static void part_copy(o_particle* dst, const o_particle* src, int N) {
   uint8_t* keep = dst->ids;
-  dst->n_nodes = src->n_nodes; dst->q_head = src->q_head; dst->ssq = src->ssq; dst->llq = src->llq; dst->lw = src->lw;
+  dst->n_nodes = src->n_nodes; dst->q_head = src->q_head; dst->gain = src->gain; dst->llq = src->llq; dst->lw = src->lw;
   memcpy(dst->nodes, src->nodes, sizeof(o_node) * (size_t)src->n_nodes);
   dst->ids = keep;
   memcpy(dst->ids, src->ids, (size_t)N);
@@ -193,11 +194,11 @@ static bk_trace_rec* trace_slot(bko* o) {
 
 /* Gaussian log-likelihood of a whole particle from its per-leaf statistics,
  * leaves visited in node-index order */
-static double particle_ssq(const bko* o, const o_particle* q) {
-  double ssq = 0.0;
+static double particle_gain(const bko* o, const o_particle* q) {
+  double g = 0.0;
   for (int k = 0; k < q->n_nodes; ++k)
-    if (q->nodes[k].var < 0) ssq = BK_DADD(ssq, bk_leaf_ssq(q->nodes[k].st, q->nodes[k].value, o->inv_qscale));
-  return ssq;
+    if (q->nodes[k].var < 0) g = BK_DADD(g, bk_leaf_gain(q->nodes[k].st, q->nodes[k].value, o->inv_qscale));
+  return g;
 }
 
 /* Fixed-point weights W_i (bk_weight_fix), their exact integer running sums S_j, and systematic resampling:
@@ -266,14 +267,13 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
     q->ids[i] = (uint8_t)(left ? L : R);
     int64_t a = (int64_t)o->qr[i];
     t->n += 1; t->sst += (int64_t)o->qst[i]; t->sr += a;
-    t->sr2 = bk_u128_add(t->sr2, bk_u128_make(0, (uint64_t)(a * a)));
   }
   o->bytes_touched += (long long)N * 14;
   double zl = bk_normal(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_LEFT));
   double zr = bk_normal(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_RIGHT));
   float vl = bk_leaf_value(sl.n, sl.sst, o->inv_qm, zl, o->leaf_sd);
   float vr = bk_leaf_value(sr.n, sr.sst, o->inv_qm, zr, o->leaf_sd);
-  double c_parent = bk_leaf_ssq(nd->st, nd->value, o->inv_qscale);
+  double g_parent = bk_leaf_gain(nd->st, nd->value, o->inv_qscale);
   nd->var = v; nd->split = s; nd->left = L;
   o_node* nl = &q->nodes[L]; o_node* nr = &q->nodes[R];
   nl->var = -1; nl->split = 0.0f; nl->left = -1; nl->depth = depth + 1; nl->value = vl; nl->st = sl;
@@ -291,8 +291,8 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
     q->llq = q->llq - nd->ll + ll_l + ll_r;
     q->lw = bk_bern_loglik((double)q->llq);
   } else {
-    q->ssq = BK_DADD(BK_DADD(BK_DSUB(q->ssq, c_parent), bk_leaf_ssq(sl, vl, o->inv_qscale)), bk_leaf_ssq(sr, vr, o->inv_qscale));
-    q->lw = bk_normal_loglik(q->ssq, sigma, (double)N);
+    q->gain = BK_DADD(BK_DADD(BK_DSUB(q->gain, g_parent), bk_leaf_gain(sl, vl, o->inv_qscale)), bk_leaf_gain(sr, vr, o->inv_qscale));
+    q->lw = bk_normal_loglik(bk_ssq_from_gain(o->r2_total, q->gain), sigma, (double)N);
   }
   if (rec) { rec->var = v; rec->split = s; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
   return 1;
@@ -313,6 +313,7 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
     o_particle* old = &o->forest[t];
     /* B1: residual without tree t, fixed-point copies */
     bk_stats tot; memset(&tot, 0, sizeof(tot));
+    bk_u128 tot_sr2 = bk_u128_make(0, 0);
     for (int k = 0; k < old->n_nodes; ++k) { bk_stats z; memset(&z, 0, sizeof(z)); z.n = old->nodes[k].st.n; old->nodes[k].st = z; old->nodes[k].ll = 0; }
     int64_t tot_ll = 0;
     for (int i = 0; i < N; ++i) {
@@ -328,24 +329,22 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       int32_t a = bk_quant(r, o->qscale), b = bk_quant(o->st[i], o->qscale);
       o->qr[i] = a; o->qst[i] = b;
       bk_u128 sq = bk_u128_make(0, (uint64_t)((int64_t)a * (int64_t)a));
-      tot.n += 1; tot.sst += b; tot.sr += a; tot.sr2 = bk_u128_add(tot.sr2, sq);
-      if (old->ids[i] != BK_LIMBO) {
-        bk_stats* ls = &old->nodes[old->ids[i]].st;
-        ls->sr += a; ls->sr2 = bk_u128_add(ls->sr2, sq);
-      }
+      tot.n += 1; tot.sst += b; tot.sr += a; tot_sr2 = bk_u128_add(tot_sr2, sq);
+      if (old->ids[i] != BK_LIMBO) old->nodes[old->ids[i]].st.sr += a;
     }
     o->bytes_touched += (long long)N * 23;
+    o->r2_total = bk_total_r2(tot_sr2, o->inv_qscale);
     /* B2: particles */
     part_copy(&o->parts[0], old, N);
     o->parts[0].q_head = o->parts[0].n_nodes;
     if (bern) {
       int64_t llq = 0;
       for (int k = 0; k < old->n_nodes; ++k) if (old->nodes[k].var < 0) llq += old->nodes[k].ll;
-      o->parts[0].ssq = 0.0; o->parts[0].llq = llq; o->parts[0].lw = bk_bern_loglik((double)llq);
+      o->parts[0].gain = 0.0; o->parts[0].llq = llq; o->parts[0].lw = bk_bern_loglik((double)llq);
     } else {
-      o->parts[0].ssq = particle_ssq(o, &o->parts[0]);
+      o->parts[0].gain = particle_gain(o, &o->parts[0]);
       o->parts[0].llq = 0;
-      o->parts[0].lw = bk_normal_loglik(o->parts[0].ssq, sigma, (double)N);
+      o->parts[0].lw = bk_normal_loglik(bk_ssq_from_gain(o->r2_total, o->parts[0].gain), sigma, (double)N);
     }
     for (int q = 1; q < P; ++q) {
       o_particle* pq = &o->parts[q];
@@ -353,11 +352,11 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       pq->nodes[0].var = -1; pq->nodes[0].split = 0.0f; pq->nodes[0].left = -1; pq->nodes[0].depth = 0;
       pq->nodes[0].value = o->s.init_leaf; pq->nodes[0].st = tot; pq->nodes[0].ll = tot_ll;
       memset(pq->ids, 0, (size_t)N);
-      if (bern) { pq->ssq = 0.0; pq->llq = tot_ll; pq->lw = bk_bern_loglik((double)tot_ll); }
+      if (bern) { pq->gain = 0.0; pq->llq = tot_ll; pq->lw = bk_bern_loglik((double)tot_ll); }
       else {
         pq->llq = 0;
-        pq->ssq = bk_leaf_ssq(tot, o->s.init_leaf, o->inv_qscale);
-        pq->lw = bk_normal_loglik(pq->ssq, sigma, (double)N);
+        pq->gain = bk_leaf_gain(tot, o->s.init_leaf, o->inv_qscale);
+        pq->lw = bk_normal_loglik(bk_ssq_from_gain(o->r2_total, pq->gain), sigma, (double)N);
       }
     }
     /* B3-B8: grow rounds */

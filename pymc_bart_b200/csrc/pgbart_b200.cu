@@ -205,7 +205,7 @@ struct GroupShared {
   float old_vals[256];
   float new_vals[256];
   float pro_vals[256];
-  unsigned long long leaf_acc[256 * 3];
+  unsigned long long leaf_acc[256];      // per-leaf sum of the old tree's q(r) (Bernoulli: log-likelihood terms)
   unsigned long long tot_acc[8];
   Work work;
   unsigned seen[64];            // last epoch of each chain this group has executed
@@ -239,7 +239,7 @@ __device__ __forceinline__ int4 ld_ca_v4(const int4* p) {   // ordinary (weak, L
 // overflow to the global `parts` array.  All control-phase particle traffic is then ~30-cycle shared
 // memory instead of ~600-cycle L2 round trips.
 extern __shared__ __align__(16) unsigned char bk_dyn_smem[];
-struct PHdr { int32_t n_nodes, q_head, row, pad; double ssq, lw; };
+struct PHdr { int32_t n_nodes, q_head, row, pad; double gain, lw; };   // gain: Gaussian sum of bk_leaf_gain over the leaves; Bernoulli: integer log-likelihood sum
 static_assert(sizeof(PHdr) == 32, "PHdr layout");
 struct PRef {
   PHdr* h;
@@ -258,10 +258,10 @@ __device__ __forceinline__ PRef pref(const Params& P, int c, int buf, int q) {
   return r;
 }
 __device__ __forceinline__ bk_stats node_stats(const DNode& nd) {
-  bk_stats s; s.n = nd.n; s.sst = nd.sst; s.sr = nd.sr; s.sr2 = bk_u128_make(nd.sr2_hi, nd.sr2_lo); return s;
+  bk_stats s; s.n = nd.n; s.sst = nd.sst; s.sr = nd.sr; return s;
 }
 __device__ __forceinline__ void set_node_stats(DNode& nd, const bk_stats& s) {
-  nd.n = s.n; nd.sst = s.sst; nd.sr = s.sr; nd.sr2_hi = s.sr2.hi; nd.sr2_lo = s.sr2.lo;
+  nd.n = s.n; nd.sst = s.sst; nd.sr = s.sr;
 }
 __device__ __forceinline__ bk_trace_rec* trace_at(const Params& P, int c, int pos) {
   if (P.trace_cap <= 0 || pos < 0 || pos >= P.trace_cap) return nullptr;
@@ -456,8 +456,6 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     DNode nd = ft[k];
     nd.sst = 0;
     nd.sr = (int64_t)__ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 0);
-    bk_u128 s2 = bk_u128_from_split(__ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 2), __ldcg(a0 + (size_t)k * BK_ACC0_STRIDE + 1));
-    nd.sr2_hi = s2.hi; nd.sr2_lo = s2.lo;
     p0.node(k) = nd;
   }
   for (int r = BK_WTID; r >= 0 && r < P.R; r += BK_WTHREADS) sh.row_cnt_node[r] = -1;
@@ -465,13 +463,15 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
   CTRL_SYNC();
   const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
   if (threadIdx.x == 0) {
-    double ssq = 0.0;   // Bernoulli: integer sum of the leaves' quantised log-likelihood terms (exact in double)
+    double gain = 0.0;   // Bernoulli: integer sum of the leaves' quantised log-likelihood terms (exact in double)
     for (int k = 0; k < nn; ++k) {
       const DNode& nd = p0.node(k);
-      if (nd.var < 0) ssq = BK_DADD(ssq, bern ? (double)nd.sr : bk_leaf_ssq(node_stats(nd), nd.value, P.inv_qscale));
+      if (nd.var < 0) gain = BK_DADD(gain, bern ? (double)nd.sr : bk_leaf_gain(node_stats(nd), nd.value, P.inv_qscale));
     }
+    const double r2_total = bk_total_r2(bk_u128_from_split(__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 2), __ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 1)), P.inv_qscale);
+    hot->r2_total = r2_total;
     p0.h->n_nodes = nn; p0.h->q_head = nn; p0.h->row = BK_ROW_FOREST;
-    p0.h->ssq = ssq; p0.h->lw = bern ? bk_bern_loglik(ssq) : bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
+    p0.h->gain = gain; p0.h->lw = bern ? bk_bern_loglik(gain) : bk_normal_loglik_pre(bk_ssq_from_gain(r2_total, gain), hot->ll_inv2s2, hot->ll_c);
     hot->buf = 0; hot->round = 0; sh.live = 0;
   }
   const int q = BK_WTID;
@@ -479,16 +479,16 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     bk_stats tot;
     tot.n = P.N;
     tot.sr = (int64_t)__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 0);
-    tot.sr2 = bk_u128_from_split(__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 2), __ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 1));
+    const double r2_total = bk_total_r2(bk_u128_from_split(__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 2), __ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 1)), P.inv_qscale);
     tot.sst = (int64_t)__ldcg(a0 + (size_t)255 * BK_ACC0_STRIDE + 3);
     const PRef S = pref(P, c, 0, q);
     DNode nd;
-    nd.var = -1; nd.split = 0.0f; nd.left = -1; nd.depth = 0; nd.value = P.init_leaf; nd.pad = 0;
+    nd.var = -1; nd.split = 0.0f; nd.left = -1; nd.depth = 0; nd.value = P.init_leaf; nd.aux[0] = 0; nd.aux[1] = 0; nd.aux[2] = 0;
     set_node_stats(nd, tot);
     S.node(0) = nd;
     S.h->n_nodes = 1; S.h->q_head = 0; S.h->row = BK_ROW_VIRTUAL;
-    S.h->ssq = bern ? (double)tot.sr : bk_leaf_ssq(tot, P.init_leaf, P.inv_qscale);
-    S.h->lw = bern ? bk_bern_loglik(S.h->ssq) : bk_normal_loglik_pre(S.h->ssq, hot->ll_inv2s2, hot->ll_c);
+    S.h->gain = bern ? (double)tot.sr : bk_leaf_gain(tot, P.init_leaf, P.inv_qscale);
+    S.h->lw = bern ? bk_bern_loglik(S.h->gain) : bk_normal_loglik_pre(bk_ssq_from_gain(r2_total, S.h->gain), hot->ll_inv2s2, hot->ll_c);
   }
   CTRL_SYNC();
 }
@@ -708,9 +708,8 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     sl.n = (int32_t)__ldcg(acc + BK_ACC_N);
     sl.sst = (int64_t)__ldcg(acc + BK_ACC_SST);
     sl.sr = (int64_t)__ldcg(acc + BK_ACC_SR);
-    sl.sr2 = bk_u128_from_split(__ldcg(acc + BK_ACC_SR2HI), __ldcg(acc + BK_ACC_SR2LO));
 #pragma unroll
-    for (int e = 0; e < 5; ++e) acc[e] = 0ull;
+    for (int e = 0; e < 3; ++e) acc[e] = 0ull;
     DNode parent = S.node(jb.node);
     bk_stats sp = node_stats(parent);
     bk_stats sr = bk_stats_sub(sp, sl);
@@ -720,19 +719,19 @@ __device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     double zr = pre ? sh.pre_zr[q] : bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
     float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qm, zl, hot->leaf_sd);
     float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qm, zr, hot->leaf_sd);
-    double c_parent = bk_leaf_ssq(sp, parent.value, P.inv_qscale);
+    const double g_parent = bk_leaf_gain(sp, parent.value, P.inv_qscale);
     const int nn = S.h->n_nodes;
     parent.var = jb.var; parent.split = jb.split; parent.left = nn;
     S.node(jb.node) = parent;
-    DNode nl; nl.var = -1; nl.split = 0.0f; nl.left = -1; nl.depth = parent.depth + 1; nl.value = vl; nl.pad = 0;
+    DNode nl; nl.var = -1; nl.split = 0.0f; nl.left = -1; nl.depth = parent.depth + 1; nl.value = vl; nl.aux[0] = 0; nl.aux[1] = 0; nl.aux[2] = 0;
     set_node_stats(nl, sl);
     DNode nr = nl; nr.value = vr; set_node_stats(nr, sr);
     S.node(nn) = nl; S.node(nn + 1) = nr;
     S.h->n_nodes = nn + 2;
     if (!bern) {
-      double ssq = BK_DADD(BK_DADD(BK_DSUB(S.h->ssq, c_parent), bk_leaf_ssq(sl, vl, P.inv_qscale)), bk_leaf_ssq(sr, vr, P.inv_qscale));
-      S.h->ssq = ssq;
-      S.h->lw = bk_normal_loglik_pre(ssq, hot->ll_inv2s2, hot->ll_c);
+      const double gain = BK_DADD(BK_DADD(BK_DSUB(S.h->gain, g_parent), bk_leaf_gain(sl, vl, P.inv_qscale)), bk_leaf_gain(sr, vr, P.inv_qscale));
+      S.h->gain = gain;
+      S.h->lw = bk_normal_loglik_pre(bk_ssq_from_gain(hot->r2_total, gain), hot->ll_inv2s2, hot->ll_c);
     } else {   // turn the partition job into the LL job of the same particle (same list position)
       Job lj = jb;
       lj.kind = BK_JOB_LL; lj.src_row = jb.dst_row; lj.split = vl; lj.rule = __float_as_int(vr);
@@ -760,8 +759,8 @@ __device__ void finalize_ll(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
     const long long ll_parent = S.node(jb.node).sr;
     S.node(jb.left_id).sr = ll_l;
     S.node(jb.left_id + 1).sr = ll_r;
-    const double llq = BK_DADD(BK_DSUB(S.h->ssq, (double)ll_parent), (double)(ll_l + ll_r));   // integers: exact
-    S.h->ssq = llq;
+    const double llq = BK_DADD(BK_DSUB(S.h->gain, (double)ll_parent), (double)(ll_l + ll_r));   // integers: exact
+    S.h->gain = llq;
     S.h->lw = bk_bern_loglik(llq);
   }
   CTRL_SYNC();
@@ -1034,10 +1033,6 @@ __device__ __forceinline__ unsigned bytes_eq(unsigned w, unsigned pat4) {
 #define BK_LIMB_ST_HI 2
 #define BK_LIMB_SR_LO 3
 #define BK_LIMB_SR_HI 4
-#define BK_LIMB_C0 5
-#define BK_LIMB_C1 6
-#define BK_LIMB_C2 7
-#define BK_LIMB_C3 8
 #define BK_LIMB_LLL_LO 9
 #define BK_LIMB_LLL_HI 10
 #define BK_LIMB_LLR_LO 11
@@ -1051,8 +1046,6 @@ __device__ __forceinline__ unsigned long long take_stat(unsigned* L, int k) {
     case BK_ACC_N: lo = BK_LIMB_N; hi = -1; break;
     case BK_ACC_SST: lo = BK_LIMB_ST_LO; hi = BK_LIMB_ST_HI; break;
     case BK_ACC_SR: lo = BK_LIMB_SR_LO; hi = BK_LIMB_SR_HI; break;
-    case BK_ACC_SR2LO: lo = BK_LIMB_C0; hi = BK_LIMB_C1; sgn = false; break;
-    case BK_ACC_SR2HI: lo = BK_LIMB_C2; hi = BK_LIMB_C3; sgn = false; break;
     case BK_ACC_LLL: lo = BK_LIMB_LLL_LO; hi = BK_LIMB_LLL_HI; break;
     case BK_ACC_LLR: lo = BK_LIMB_LLR_LO; hi = BK_LIMB_LLR_HI; break;
     default: return 0ull;
@@ -1134,25 +1127,18 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       const unsigned n1 = (w1 & ~mem1) | (mem1 & ((lm1 & L4) | (~lm1 & R4)));
       __stcg(reinterpret_cast<uint2*>(const_cast<uint8_t*>(rows_c) + (size_t)dst_row * P.Npad), make_uint2(n0, n1));
       if (__any_sync(0xffffffffu, (lm0 | lm1) != 0u)) {
-        // masked per-lane sums: 4 rows fit 32 bits (|q| < 2^29); squares accumulate in 64 bits
+        // masked per-lane sums: 4 rows fit 32 bits (|q| < 2^29)
         int s_a = 0, s_b = 0, r_a = 0, r_b = 0;
-        unsigned long long r2 = 0ull;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int ma = (int)BK_ROWMASK(lm0, e), mb = (int)BK_ROWMASK(lm1, e);
           s_a += q_s[e] & ma; s_b += q_s[4 + e] & mb;
-          if (gauss) {
-            const int qa = q_r[e] & ma, qb = q_r[4 + e] & mb;
-            r_a += qa; r_b += qb;
-            r2 += (unsigned long long)((long long)qa * (long long)qa);
-            r2 += (unsigned long long)((long long)qb * (long long)qb);
-          }
+          if (gauss) { r_a += q_r[e] & ma; r_b += q_r[4 + e] & mb; }
         }
         const unsigned cl = (unsigned)(__popc(lm0) + __popc(lm1)) >> 3;
         const long long st = (long long)s_a + (long long)s_b, sr = (long long)r_a + (long long)r_b;
-        // REDUX partial sums = the limbs.  The member count shares a word with the top chunk of the squares.
-        const unsigned pk = __reduce_add_sync(0xffffffffu, (unsigned)(r2 >> 48) | (cl << 20));   // chunk < 2^13 per lane
-        unsigned v = pk >> 20;                                                                    // lane 0: BK_LIMB_N
+        // REDUX partial sums = the limbs
+        unsigned v = __reduce_add_sync(0xffffffffu, cl);                                          // lane 0: BK_LIMB_N
         const unsigned st_lo = __reduce_add_sync(0xffffffffu, (unsigned)st & 0xFFFFu);
         const int st_hi = __reduce_add_sync(0xffffffffu, (int)(st >> 16));
         v = lane == BK_LIMB_ST_LO ? st_lo : v;
@@ -1161,16 +1147,9 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
         if (gauss) {   // Gaussian sufficient statistics of the residual (Bernoulli: q_r holds noi bits)
           const unsigned sr_lo = __reduce_add_sync(0xffffffffu, (unsigned)sr & 0xFFFFu);
           const int sr_hi = __reduce_add_sync(0xffffffffu, (int)(sr >> 16));
-          const unsigned c0 = __reduce_add_sync(0xffffffffu, (unsigned)(r2 & 0xFFFFull));
-          const unsigned c1 = __reduce_add_sync(0xffffffffu, (unsigned)((r2 >> 16) & 0xFFFFull));
-          const unsigned c2 = __reduce_add_sync(0xffffffffu, (unsigned)((r2 >> 32) & 0xFFFFull));
           v = lane == BK_LIMB_SR_LO ? sr_lo : v;
           v = lane == BK_LIMB_SR_HI ? (unsigned)sr_hi : v;
-          v = lane == BK_LIMB_C0 ? c0 : v;
-          v = lane == BK_LIMB_C1 ? c1 : v;
-          v = lane == BK_LIMB_C2 ? c2 : v;
-          v = lane == BK_LIMB_C3 ? (pk & 0xFFFFFu) : v;
-          nl = 9;
+          nl = 5;
         }
         if (lane < nl) atomicAdd(sacc + ji * BK_LIMBS + lane, v);   // one shared-memory atomic instruction per job
       }
@@ -1254,7 +1233,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
     }
     sh.pro_vals[k] = pv;
   }
-  for (int k = tid; k < 256 * 3; k += BK_GROUP_THREADS) sh.leaf_acc[k] = 0ull;
+  for (int k = tid; k < 256; k += BK_GROUP_THREADS) sh.leaf_acc[k] = 0ull;
   if (tid < 8) sh.tot_acc[tid] = 0ull;
   GROUP_SYNC(g);
 
@@ -1350,18 +1329,11 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
       const unsigned key = ok ? pid : 0x100u;
       const unsigned grp = __match_any_sync(0xffffffffu, key);
       const int a = ok ? pro_q[e] : 0;
-      const unsigned long long sq = P.lik == BK_LIK_NORMAL ? (unsigned long long)((long long)a * (long long)a) : 0ull;
       const unsigned r_lo = __reduce_add_sync(grp, (unsigned)a & 0xFFFFu);
       const int r_hi = __reduce_add_sync(grp, a >> 16);
-      const unsigned c0 = __reduce_add_sync(grp, (unsigned)(sq & 0xFFFFull));
-      const unsigned c1 = __reduce_add_sync(grp, (unsigned)((sq >> 16) & 0xFFFFull));
-      const unsigned c2 = __reduce_add_sync(grp, (unsigned)((sq >> 32) & 0xFFFFull));
-      const unsigned c3 = __reduce_add_sync(grp, (unsigned)(sq >> 48));
       if (ok && (int)(tid & 31) == __ffs(grp) - 1) {
         const long long sr = (long long)r_hi * 65536ll + (long long)r_lo;
-        atomicAdd(&sh.leaf_acc[pid * 3 + 0], (unsigned long long)sr);
-        atomicAdd(&sh.leaf_acc[pid * 3 + 1], (unsigned long long)c0 + ((unsigned long long)c1 << 16));
-        atomicAdd(&sh.leaf_acc[pid * 3 + 2], (unsigned long long)c2 + ((unsigned long long)c3 << 16));
+        atomicAdd(&sh.leaf_acc[pid], (unsigned long long)sr);
       }
     }
   }
@@ -1380,9 +1352,9 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
   GROUP_SYNC(g);
   unsigned long long* a0 = P.acc0 + (size_t)c * BK_ACC0_WORDS;
   if (do_pro) {
-    for (int k = tid; k < 255 * 3; k += BK_GROUP_THREADS) {
+    for (int k = tid; k < 255; k += BK_GROUP_THREADS) {
       unsigned long long v = sh.leaf_acc[k];
-      if (v) red_add_u64(a0 + (size_t)(k / 3) * BK_ACC0_STRIDE + (k % 3), v);
+      if (v) red_add_u64(a0 + (size_t)k * BK_ACC0_STRIDE, v);
     }
     if (tid < 4) { unsigned long long v = sh.tot_acc[tid]; if (v) red_add_u64(a0 + (size_t)255 * BK_ACC0_STRIDE + tid, v); }
   }
@@ -1401,7 +1373,7 @@ __device__ __forceinline__ int servers_of(int C, int c) { return C >= BK_NGROUPS
 // chunk.  No claim atomics.  Every serving group reports each epoch exactly once (release add), so the control CTA
 // waits for `workers x servers_of(chain)` per epoch.
 __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
-  const int tid = threadIdx.x & (BK_GROUP_THREADS - 1), warp = tid >> 5;
+  const int tid = (int)threadIdx.x - g * BK_GROUP_THREADS, warp = tid >> 5;
   const int W = gridDim.x - P.C, w = blockIdx.x - P.C;
   const int c_first = P.C >= BK_NGROUPS ? g : g % P.C, c_step = P.C >= BK_NGROUPS ? BK_NGROUPS : P.C;
   const int my_rank = P.C >= BK_NGROUPS ? 0 : g / P.C;      // index of this group among the servers of its chain

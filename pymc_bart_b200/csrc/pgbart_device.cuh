@@ -58,9 +58,7 @@ struct __align__(16) DNode {
   int32_t n;
   int64_t sst;
   int64_t sr;
-  uint64_t sr2_hi;
-  uint64_t sr2_lo;
-  int64_t pad;
+  int64_t aux[3];   // reserved (multi-output leaf values)
 };
 static_assert(sizeof(DNode) == 64, "DNode must be 64 bytes");
 
@@ -69,7 +67,7 @@ struct __align__(16) DParticle {
   int32_t q_head;  // expansion queue = nodes [q_head, n_nodes)
   int32_t row;     // leaf-id row reference
   int32_t pad;
-  double ssq;
+  double gain;
   double lw;
   DNode nodes[BK_MAX_NODES];
 };
@@ -124,6 +122,7 @@ struct __align__(16) ChainHot {
   int32_t n_grow;    // partition jobs among them (listed first)
   int32_t c_tree_updates, c_rounds, c_grow, c_grow_root, c_count_passes, c_phases, c_err;
   double ll_inv2s2, ll_c;   // per-step constants of the Gaussian log-likelihood
+  double r2_total;          // Gaussian: sum of squares of all rows' residuals for the tree being updated (bk_total_r2)
   unsigned long long t_sub_last;
   unsigned long long t_sub[8];  // optional control sub-step timers (ns), -DBK_PROFILE_CTRL
 };
@@ -140,13 +139,11 @@ struct __align__(16) ChainCtl {
 #define BK_ACC_N 0
 #define BK_ACC_SST 1
 #define BK_ACC_SR 2
-#define BK_ACC_SR2LO 3
-#define BK_ACC_SR2HI 4
 #define BK_ACC_LLL 5    // Bernoulli: quantised log-likelihood of the new left / right leaf
 #define BK_ACC_LLR 6
 #define BK_ACC_STRIDE 8
 
-// acc0 layout per chain: [256][4]: leaf k -> (sr, sr2lo, sr2hi, n); entry 255 = totals
+// acc0 layout per chain: [256][4]: leaf k -> (sr, -, -, -); entry 255 = totals
 // (sr, sr2lo, sr2hi, sst); then [4]: (wf sd sum, -, -, -)
 #define BK_ACC0_STRIDE 4
 #define BK_ACC0_WORDS (257 * BK_ACC0_STRIDE)
