@@ -153,12 +153,8 @@ struct CtlShared {
   int s_j[BK_MAX_PARTICLES];
   int s_v[BK_MAX_PARTICLES];
   unsigned s_k[BK_MAX_PARTICLES];
-  int s_next[BK_MAX_PARTICLES];
   int s_row[BK_MAX_PARTICLES];
-  int s_nn[BK_MAX_PARTICLES];
-  int s_sparse[BK_MAX_PARTICLES];
   float s_split[BK_MAX_PARTICLES];
-  unsigned char row_used[2 * BK_MAX_PARTICLES];
   int row_cnt_node[2 * BK_MAX_PARTICLES];  // node whose per-tile counts a pool row holds (persists across phases)
   Job jobs[BK_MAX_PARTICLES];               // staged here, copied to global by the whole CTA
   unsigned long long cum_s[BK_MAX_PARTICLES];   // running sums of the fixed-point weights
@@ -172,7 +168,7 @@ struct CtlShared {
   uint32_t pre_ures;
   int pre_prop_tree, pre_prop_round;   // tag of pre_u1 / pre_v / pre_u3
   int pre_z_tree, pre_z_round;         // tag of pre_zl / pre_zr / pre_ures
-  // Deferred particle copy: after resampling, propose() reads every slot's state THROUGH src_slot (its ancestor in
+  // Deferred particle copy: after resampling, open_round() reads every slot's state THROUGH src_slot (its ancestor in
   // the current buffer) and only records the new queue head; the copy into the other buffer happens in the shadow
   // of the epoch it published (apply_pending_copy).
   int copy_pending;
@@ -184,6 +180,15 @@ struct CtlShared {
   int live;
   int win;
   unsigned pick;
+  // round path (open_round): job index of every slot, used-row bitmap, per-warp grower counts, count-job cursor,
+  // selection cursor, error bits, slices of the resampling scan
+  int s_jobidx[BK_MAX_PARTICLES];
+  unsigned used_rows[8];
+  int warp_grow[4];
+  int n_cnt_jobs;
+  int next_sel;
+  int err_bits;
+  unsigned long long r_slice[4];
 };
 
 // A worker CTA is split into BK_NGROUPS independent groups of BK_GROUP_THREADS threads.  Each group serves its own
@@ -431,6 +436,52 @@ __device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first
   CTRL_SYNC();
 }
 
+// Resampling by the particle threads themselves (round path).  Thread q = BK_WTID of warps 1..4 owns particle q; the
+// weight vector covers particles first..first+count-1 (element i = q - first).  Every warp forms the maximum of all log
+// weights from the particle headers (two 32-bit REDUX on an order-preserving key instead of ten 64-bit shuffles), the
+// fixed-point weights are scanned in particle order (warp scan + one slice exchange), and thread q searches the
+// ancestor of ITS OWN point, so the result stays in a register of the thread that pops the slot next: no block barrier
+// between resampling and the queue pops.  Same integers as normalise_and_resample / the oracle's sequential sums.
+// Must be called by all threads of warps 1..4 (two named barriers); returns the ancestor index in [0, count).
+__device__ __forceinline__ int resample_own(const Params& P, int c, int buf, CtlShared& sh, int first, int count, uint32_t u32) {
+#define R_SYNC() asm volatile("barrier.sync 13, 128;" ::: "memory")
+  const int q = BK_WTID, lane = threadIdx.x & 31, wq = q >> 5;
+  const int i = q - first;
+  const bool in = i >= 0 && i < count;
+  unsigned mh = 0u, ml = 0u;
+  {
+    unsigned long long best = 0ull;
+    for (int j = lane; j < count; j += 32) {
+      const unsigned long long b = bk_d2bits(pref(P, c, buf, first + j).h->lw);
+      const unsigned long long key = (b >> 63) ? ~b : (b | 0x8000000000000000ull);   // unsigned order = double order
+      best = key > best ? key : best;
+    }
+    mh = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
+    ml = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32) == mh ? (unsigned)best : 0u);
+  }
+  const unsigned long long mk = ((unsigned long long)mh << 32) | ml;
+  const double mx = bk_bits2d((mk >> 63) ? (mk & 0x7FFFFFFFFFFFFFFFull) : ~mk);
+  unsigned long long s = in ? bk_weight_fix(pref(P, c, buf, q).h->lw, mx) : 0ull;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long nb = shfl_up_u64(s, o); if (lane >= o) s += nb; }
+  if (lane == 31) sh.r_slice[wq] = s;
+  R_SYNC();
+  unsigned long long before = 0ull, s_last = 0ull;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const unsigned long long t = sh.r_slice[k]; if (k < wq) before += t; s_last += t; }
+  s += before;
+  if (in) sh.cum_s[i] = s;
+  R_SYNC();
+  int lo = 0;
+  if (in) {
+    const bk_u128 point = bk_resample_point((uint32_t)i, u32, s_last);
+    int hi = count - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (!bk_resample_le(point, sh.cum_s[mid], (uint32_t)count)) lo = mid + 1; else hi = mid; }
+  }
+#undef R_SYNC
+  return lo;
+}
+
 __device__ void zero_acc0(const Params& P, int c) {
   unsigned long long* a = P.acc0 + (size_t)c * BK_ACC0_WORDS;
   for (int i = BK_WTID; i >= 0 && i < BK_ACC0_WORDS; i += BK_WTHREADS) a[i] = 0ull;
@@ -508,7 +559,7 @@ __device__ __forceinline__ int draw_variable_dev(const Params& P, int c, const C
 __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot);
 
 // Executes a deferred particle copy (see CtlShared::copy_pending): buffer `buf` -> `buf ^ 1` through src_slot, then
-// the queue heads propose() recorded; flips the buffer.  All control threads.
+// the queue heads open_round() recorded; flips the buffer.  All control threads.
 __device__ void apply_pending_copy(const Params& P, int c, ChainHot* hot, CtlShared& sh) {
   if (!sh.copy_pending) return;     // (uniform: shared flag, read after a barrier)
   const int buf = hot->buf;
@@ -525,7 +576,7 @@ __device__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& s
   apply_pending_copy(P, c, hot, sh);
   const int q = BK_WTID;
   if (q >= 1 && q < P.P) {
-    // leaf-value normals of this round (used by finalize_grows when the epoch is done) for the slots that grow
+    // leaf-value normals of this round (used by finalize_own when the epoch is done) for the slots that grow
     if (sh.s_kind[q] == 1) {
       sh.pre_zl[q] = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
       sh.pre_zr[q] = bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
@@ -544,31 +595,117 @@ __device__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& s
   CTRL_SYNC();
 }
 
-// pops, grow decisions, split selection, job list.  Returns (uniformly) the job count.
-__device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
-  const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
-  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
+// n-th (0-based) zero bit of the used-row bitmap = n-th free pool row; -1 if there are fewer
+__device__ __forceinline__ int nth_free_row(const CtlShared& sh, int R, int n) {
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const int rows_here = R - 32 * w;
+    if (rows_here <= 0) break;
+    const unsigned valid = rows_here >= 32 ? 0xFFFFFFFFu : ((1u << rows_here) - 1u);
+    const unsigned freeb = ~sh.used_rows[w] & valid;
+    const int cfree = __popc(freeb);
+    if (n < cfree) return 32 * w + (int)__fns(freeb, 0, n + 1);
+    n -= cfree;
+  }
+  return -1;
+}
+
+// apply the statistics of the finished ROUND to slot q's particle if it grew (thread q = BK_WTID); no barrier inside
+__device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* hot, CtlShared& sh, int buf, int round, int t, int rbase) {
   const int q = BK_WTID;
-  __shared__ int s_njobs, s_err, s_next_sel;
-  __shared__ int s_free[2 * BK_MAX_PARTICLES];
-  __shared__ int s_warp_cnt[3][8];
-  if (q >= 0 && q < P.P) { sh.s_kind[q] = 0; sh.s_next[q] = -1; sh.s_j[q] = -1; }
-  if (threadIdx.x == 0) { s_err = 0; s_next_sel = 1; sh.live = 0; }
-  if (q >= 0 && q < P.R) sh.row_used[q] = 0;
-  if (q >= 1 && q < P.P) {
-    const bool deferred = sh.copy_pending != 0;
-    const PRef S = pref(P, c, buf, deferred ? sh.src_slot[q] : q);   // the slot's state-to-be = its ancestor's state
-    int nn = S.h->n_nodes, qh = S.h->q_head, row = S.h->row;
-    int kind = 0, j = -1, v = -1, next = -1;
-    unsigned k = 0;
+  if (q < 1 || q >= P.P) return;
+  const int ji = sh.s_jobidx[q];
+  if (ji < 0) return;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
+  const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
+  const Job jb = sh.jobs[ji];   // the job list staged by open_round() is still in shared memory
+  const PRef S = pref(P, c, buf, q);
+  unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
+  bk_stats sl;
+  sl.n = (int32_t)__ldcg(acc + BK_ACC_N);
+  sl.sst = (int64_t)__ldcg(acc + BK_ACC_SST);
+  sl.sr = (int64_t)__ldcg(acc + BK_ACC_SR);
+#pragma unroll
+  for (int e = 0; e < 3; ++e) acc[e] = 0ull;
+  DNode parent = S.node(jb.node);
+  const bk_stats sp = node_stats(parent);
+  bk_stats sr = bk_stats_sub(sp, sl);
+  if (bern) { sl.sr = 0; sr.sr = 0; }   // the children's log-likelihood sums arrive with the LL epoch
+  const bool pre = sh.pre_z_tree == t && sh.pre_z_round == round;
+  const double zl = pre ? sh.pre_zl[q] : bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
+  const double zr = pre ? sh.pre_zr[q] : bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
+  const float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qm, zl, hot->leaf_sd);
+  const float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qm, zr, hot->leaf_sd);
+  const double g_parent = bk_leaf_gain(sp, parent.value, P.inv_qscale);
+  const int nn = S.h->n_nodes;
+  const float split = sh.s_split[q];   // (the staged job carries the split value only in its global copy)
+  parent.var = jb.var; parent.split = split; parent.left = nn;
+  S.node(jb.node) = parent;
+  DNode nl; nl.var = -1; nl.split = 0.0f; nl.left = -1; nl.depth = parent.depth + 1; nl.value = vl; nl.aux[0] = 0; nl.aux[1] = 0; nl.aux[2] = 0;
+  set_node_stats(nl, sl);
+  DNode nr = nl; nr.value = vr; set_node_stats(nr, sr);
+  S.node(nn) = nl; S.node(nn + 1) = nr;
+  S.h->n_nodes = nn + 2;
+  if (!bern) {
+    const double gain = BK_DADD(BK_DADD(BK_DSUB(S.h->gain, g_parent), bk_leaf_gain(sl, vl, P.inv_qscale)), bk_leaf_gain(sr, vr, P.inv_qscale));
+    S.h->gain = gain;
+    S.h->lw = bk_normal_loglik_pre(bk_ssq_from_gain(hot->r2_total, gain), hot->ll_inv2s2, hot->ll_c);
+  } else {   // turn the partition job into the LL job of the same particle (same list position)
+    Job lj = jb;
+    lj.kind = BK_JOB_LL; lj.src_row = jb.dst_row; lj.split = vl; lj.rule = __float_as_int(vr);
+    sh.jobs[ji] = lj;
+  }
+  S.h->row = jb.dst_row;
+  atomicAdd(&hot->c_grow, 1);
+  if (jb.src_row == BK_ROW_VIRTUAL) atomicAdd(&hot->c_grow_root, 1);
+  bk_trace_rec* rec = trace_at(P, c, rbase + q - 1);
+  if (rec) { rec->var = jb.var; rec->split = split; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
+}
+
+// Bernoulli: the LL epoch summed the quantised log-likelihood terms of the rows of slot q's new leaf pair
+__device__ __forceinline__ void finalize_ll_own(const Params& P, int c, CtlShared& sh, int buf) {
+  const int q = BK_WTID;
+  if (q < 1 || q >= P.P) return;
+  const int ji = sh.s_jobidx[q];
+  if (ji < 0 || sh.jobs[ji].kind != BK_JOB_LL) return;
+  const Job jb = sh.jobs[ji];
+  const PRef S = pref(P, c, buf, q);
+  unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
+  const long long ll_l = (long long)__ldcg(acc + BK_ACC_LLL), ll_r = (long long)__ldcg(acc + BK_ACC_LLR);
+  acc[BK_ACC_LLL] = 0ull; acc[BK_ACC_LLR] = 0ull;
+  const long long ll_parent = S.node(jb.node).sr;
+  S.node(jb.left_id).sr = ll_l;
+  S.node(jb.left_id + 1).sr = ll_r;
+  const double llq = BK_DADD(BK_DSUB(S.h->gain, (double)ll_parent), (double)(ll_l + ll_r));   // integers: exact
+  S.h->gain = llq;
+  S.h->lw = bk_bern_loglik(llq);
+}
+
+// Opens round `round` of tree t: queue pops and grow decisions of every slot (through its ancestor `src` when a
+// resampling has just happened: the particle copy itself is deferred into the epoch's shadow), row allocation, job
+// list, split values (k-th member).  Called by every control thread; `src` is the calling particle thread's own
+// ancestor slot.  Two block barriers inside; returns (uniformly) the job count.  The caller's barrier orders the
+// global job list before thread 0 publishes the epoch.
+__device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh, const int buf, const int round,
+                          const int rbase, const bool deferred, const int src) {
+  const int t = hot->cur_tree;
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
+  const int q = BK_WTID, lane = threadIdx.x & 31, w = q >> 5;
+  const bool is_p = q >= 1 && q < P.P;
+  int kind = 0, j = -1, v = -1, next = -1, row = -3, nn = 0, sparse = 0;
+  unsigned k = 0;
+  if (is_p) {
+    const PRef S = pref(P, c, buf, deferred ? src : q);   // the slot's state-to-be = its ancestor's state
+    int qh = S.h->q_head;
+    nn = S.h->n_nodes; row = S.h->row;
     if (qh < nn) {
       j = qh; qh += 1;
       if (!deferred) S.h->q_head = qh;   // (deferred: several slots may share this ancestor; written after the copy)
       const int depth = S.node(j).depth;
       const int n = S.node(j).n;
-      double pl = depth < 64 ? sh.p_leaf[depth] : (depth < BK_MAX_DEPTH_TABLE ? P.p_leaf[depth] : 1.0);
+      const double pl = depth < 64 ? sh.p_leaf[depth] : (depth < BK_MAX_DEPTH_TABLE ? P.p_leaf[depth] : 1.0);
       const bool pre = sh.pre_prop_tree == t && sh.pre_prop_round == round;   // draws made in the shadow of the last epoch
-      double u1 = pre ? sh.pre_u1[q] : bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
+      const double u1 = pre ? sh.pre_u1[q] : bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_LEAF).v[0]);
       if (u1 > pl && nn + 2 <= BK_MAX_NODES) {
         v = pre ? sh.pre_v[q]
                 : draw_variable_dev(P, c, sh, bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAR).v[0]));
@@ -579,92 +716,63 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       }
       if (kind == 1) next = qh;            // a queued node, or one of the two children being made
       else { next = qh < nn ? qh : -1; if (next >= 0) kind = 2; }
+      sparse = ((long long)n * BK_SPARSE_DIV < (long long)P.N) ? 1 : 0;
     }
-    sh.s_sparse[q] = (j >= 0 && (long long)S.node(j).n * BK_SPARSE_DIV < (long long)P.N) ? 1 : 0;
+    sh.src_slot[q] = deferred ? src : q;
     sh.s_qh[q] = qh;
-    sh.s_kind[q] = kind; sh.s_j[q] = j; sh.s_v[q] = v; sh.s_k[q] = k; sh.s_next[q] = next; sh.s_row[q] = row; sh.s_nn[q] = nn;
-    bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + q - 1);
+    sh.s_kind[q] = kind; sh.s_j[q] = j; sh.s_v[q] = v; sh.s_k[q] = k; sh.s_row[q] = row;
+    sh.s_jobidx[q] = -1;
+    if (row >= 0) atomicOr(&sh.used_rows[row >> 5], 1u << (row & 31));
+    if (kind == 1 && row != BK_ROW_VIRTUAL && sh.row_cnt_node[row] != j) atomicOr(&sh.err_bits, 1);
+    bk_trace_rec* rec = trace_at(P, c, rbase + q - 1);
     if (rec) {
       bk_trace_rec r; memset(&r, 0, sizeof(r));
       r.kind = 1; r.tree = t; r.round = round; r.particle = q; r.node = j; r.var = -1; r.ancestor = -1;
       *rec = r;
     }
   }
+  if (q == 0) { sh.src_slot[0] = 0; sh.s_kind[0] = 0; sh.s_jobidx[0] = -1; }
+  unsigned bg = 0u;
+  if (w >= 0 && w < 4) {   // the particle warps (converged: every lane of warps 1..4 gets here)
+    bg = __ballot_sync(0xffffffffu, kind == 1);
+    if (lane == 0) sh.warp_grow[w] = __popc(bg);
+  }
   CTRL_SYNC();
   TSUB(4);
-  // Two teams work side by side.  Team J (threads 0..255) allocates rows and assembles the job list in shared memory
-  // (free rows = ranks of the unused pool rows; growers: rank among the growing slots -> dst row; count-only jobs are
-  // de-duplicated per source row with an exchange on row_cnt_node), synchronising on its own named barrier.  Every
-  // other warp — and team J's warps 1..7 once they are done — takes growing slots from a shared counter and finds
-  // their split value (k-th member).  The split values are patched into the jobs after the joint barrier.
-  // Warp 0 never runs a selection: it can be split (see normalise_and_resample) and would crawl through the shuffles.
-#define J_SYNC() asm volatile("barrier.sync 14, 256;" ::: "memory")
-  const int tx = BK_WTID, lane = threadIdx.x & 31, w = tx >> 5;   // team J = threads 32..287 (warps 1..8)
-  int is_grow = 0, is_cnt = 0, is_free = 0, rank_g = 0;
-  if (tx >= 0 && tx < 256) {   // ---- team J (R <= 256 and P <= 128: eight warps cover both index ranges)
-    if (tx >= 1 && tx < P.P) {
-      if (sh.s_row[tx] >= 0) sh.row_used[sh.s_row[tx]] = 1;
-      if (sh.s_kind[tx] == 1 && sh.s_row[tx] != BK_ROW_VIRTUAL && sh.row_cnt_node[sh.s_row[tx]] != sh.s_j[tx]) atomicOr(&s_err, 1);
-    }
-    J_SYNC();
-    if (tx >= 1 && tx < P.P) {
-      if (sh.s_kind[tx] == 1) is_grow = 1;
-      else if (sh.s_kind[tx] == 2 && sh.s_row[tx] >= 0) {
-        const int old = atomicExch(&sh.row_cnt_node[sh.s_row[tx]], sh.s_next[tx]);
-        is_cnt = old != sh.s_next[tx];
+  // ---- jobs (particle threads) beside the k-th member selections (every warp but the scalar warp 0)
+  int tot_g = 0;
+  if (w >= 0 && w < 4) {
+    int off_g = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const int cw = sh.warp_grow[i]; if (i < w) off_g += cw; tot_g += cw; }
+    if (kind == 1) {
+      const int rank_g = off_g + __popc(bg & ((1u << lane) - 1u));
+      const int dst = nth_free_row(sh, P.R, rank_g);
+      if (dst < 0) atomicOr(&sh.err_bits, 8);
+      Job jb;
+      jb.kind = BK_JOB_PARTITION; jb.slot = q; jb.src_row = row; jb.dst_row = dst < 0 ? 0 : dst;
+      jb.node = j; jb.var = v; jb.split = 0.0f; jb.left_id = nn;
+      jb.next_node = next; jb.rule = v < BK_CUM_SMEM ? (int)sh.rules[v] : P.rules[v]; jb.pad[0] = sparse; jb.pad[1] = 0;
+      if (dst >= 0) sh.row_cnt_node[dst] = next;
+      sh.jobs[rank_g] = jb;
+      sh.s_jobidx[q] = rank_g;
+    } else if (kind == 2 && row >= 0) {
+      // count-only: the members of the next queue node per tile, once per shared row (slots that share a row have the
+      // same queue)
+      const int old = atomicExch(&sh.row_cnt_node[row], next);
+      if (old != next) {
+        const int pos = tot_g + atomicAdd(&sh.n_cnt_jobs, 1);   // (order among count jobs is immaterial)
+        Job jb;
+        jb.kind = BK_JOB_COUNT; jb.slot = q; jb.src_row = row; jb.dst_row = row; jb.node = -1; jb.var = 0;
+        jb.split = 0.0f; jb.left_id = 0; jb.next_node = next; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
+        sh.jobs[pos] = jb;
       }
     }
-    if (tx < P.R) is_free = sh.row_used[tx] ? 0 : 1;
-    __syncwarp();
-    const unsigned bg = __ballot_sync(0xffffffffu, is_grow), bc = __ballot_sync(0xffffffffu, is_cnt),
-                   bf = __ballot_sync(0xffffffffu, is_free);
-    if (lane == 0) { s_warp_cnt[0][w] = __popc(bg); s_warp_cnt[1][w] = __popc(bc); s_warp_cnt[2][w] = __popc(bf); }
-    const unsigned below = (1u << lane) - 1u;
-    const int in_f = __popc(bf & below), in_g = __popc(bg & below), in_c = __popc(bc & below);
-    J_SYNC();
-    int off_g = 0, off_c = 0, off_f = 0, tot_g = 0;
-    for (int k = 0; k < 8; ++k) {
-      if (k < w) { off_g += s_warp_cnt[0][k]; off_c += s_warp_cnt[1][k]; off_f += s_warp_cnt[2][k]; }
-      tot_g += s_warp_cnt[0][k];
-    }
-    const int rank_f = off_f + in_f, rank_c = off_c + in_c;
-    rank_g = off_g + in_g;
-    if (is_free) s_free[rank_f] = tx;
-    J_SYNC();
-    if (is_grow) {
-      Job jb;
-      jb.kind = BK_JOB_PARTITION; jb.slot = tx; jb.src_row = sh.s_row[tx]; jb.dst_row = s_free[rank_g];
-      jb.node = sh.s_j[tx]; jb.var = sh.s_v[tx]; jb.split = 0.0f; jb.left_id = sh.s_nn[tx];
-      jb.next_node = sh.s_next[tx]; jb.rule = sh.s_v[tx] < BK_CUM_SMEM ? (int)sh.rules[sh.s_v[tx]] : P.rules[sh.s_v[tx]]; jb.pad[0] = sh.s_sparse[tx]; jb.pad[1] = 0;
-      sh.row_cnt_node[jb.dst_row] = jb.next_node;
-      sh.jobs[rank_g] = jb;
-    } else if (is_cnt) {
-      Job jb;
-      jb.kind = BK_JOB_COUNT; jb.slot = tx; jb.src_row = sh.s_row[tx]; jb.dst_row = sh.s_row[tx]; jb.node = -1; jb.var = 0;
-      jb.split = 0.0f; jb.left_id = 0; jb.next_node = sh.s_next[tx]; jb.rule = 0; jb.pad[0] = 0; jb.pad[1] = 0;
-      sh.jobs[tot_g + rank_c] = jb;
-    }
-    if (tx == 0) {
-      int tot_c = 0, tot_f = 0;
-      for (int k = 0; k < 8; ++k) { tot_c += s_warp_cnt[1][k]; tot_f += s_warp_cnt[2][k]; }
-      const int nj = tot_g + tot_c;
-      hot->n_jobs = nj; hot->n_grow = tot_g;
-      if (tot_c) hot->c_count_passes += tot_c;
-      if (tot_g > tot_f) hot->c_err |= 8;
-      s_njobs = nj;
-    }
-    J_SYNC();
-    {  // publish the job list (48-byte descriptors; the split values of the growers follow below)
-      const int nj = s_njobs;
-      const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
-      for (int i = tx; i < nj * 3 * BK_JOB_COPIES; i += 256)
-        reinterpret_cast<uint4*>(ctl->jobs[i / (nj * 3)])[i % (nj * 3)] = s4[i % (nj * 3)];
-    }
   }
-  if (threadIdx.x >= 32) {   // ---- split values: warps 1.. take growing slots from the shared counter
+  if (threadIdx.x >= 32) {   // split values: warps 1.. take growing slots from the shared cursor
     for (;;) {
       int sl = 0;
-      if (lane == 0) sl = atomicAdd(&s_next_sel, 1);
+      if (lane == 0) sl = atomicAdd(&sh.next_sel, 1);
       sl = __shfl_sync(0xffffffffu, sl, 0);
       if (sl >= P.P) break;
       if (sh.s_kind[sl] != 1) continue;
@@ -674,96 +782,28 @@ __device__ int propose(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, Ctl
       } else {
         int err = 0;
         sv = select_split(P, c, sh.s_row[sl], sh.s_j[sl], sh.s_k[sl], sh.s_v[sl], &err);
-        if (lane == 0 && err) atomicOr(&s_err, err);
+        if (lane == 0 && err) atomicOr(&sh.err_bits, err);
       }
       if (lane == 0) sh.s_split[sl] = sv;
     }
   }
   CTRL_SYNC();
-  if (is_grow) {
-    const float sv = sh.s_split[tx];
-    sh.jobs[rank_g].split = sv;
-    for (int k = 0; k < BK_JOB_COPIES; ++k) ctl->jobs[k][rank_g].split = sv;
-  }
-  if (threadIdx.x == 0 && s_err) hot->c_err |= s_err;
   TSUB(5);
-#undef J_SYNC
+  // ---- the list goes to global memory with the split values patched in (48-byte descriptors, 16-byte pieces)
+  tot_g = sh.warp_grow[0] + sh.warp_grow[1] + sh.warp_grow[2] + sh.warp_grow[3];
+  const int nj = tot_g + sh.n_cnt_jobs;
+  for (int i = q; i >= 0 && i < nj * 3; i += BK_WTHREADS) {
+    uint4 piece = reinterpret_cast<const uint4*>(sh.jobs)[i];
+    if (i % 3 == 1 && i / 3 < tot_g) piece.z = __float_as_uint(sh.s_split[sh.jobs[i / 3].slot]);
+    reinterpret_cast<uint4*>(ctl->jobs[0])[i] = piece;
+  }
+  if (threadIdx.x == 0) {
+    hot->n_jobs = nj; hot->n_grow = tot_g;
+    hot->c_count_passes += sh.n_cnt_jobs;
+    if (sh.err_bits) hot->c_err |= sh.err_bits;
+  }
   TSUB(6);
-  return s_njobs;   // (the caller's barrier orders the patched list before thread 0 publishes the epoch)
-}
-
-// apply the statistics of the finished ROUND to the particles that grew
-__device__ void finalize_grows(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
-  const int buf = hot->buf, round = hot->round, t = hot->cur_tree;
-  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
-  const int nj = hot->n_jobs;
-  const int ji = (int)threadIdx.x - 32;   // job threads start at warp 1: warp 0 is the scalar warp and may run split
-  const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
-  if (ji >= 0 && ji < nj && sh.jobs[ji].kind == BK_JOB_PARTITION) {   // the job list staged by propose() is still in shared memory
-    const Job jb = sh.jobs[ji];
-    const int q = jb.slot;
-    const PRef S = pref(P, c, buf, q);
-    unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
-    bk_stats sl;
-    sl.n = (int32_t)__ldcg(acc + BK_ACC_N);
-    sl.sst = (int64_t)__ldcg(acc + BK_ACC_SST);
-    sl.sr = (int64_t)__ldcg(acc + BK_ACC_SR);
-#pragma unroll
-    for (int e = 0; e < 3; ++e) acc[e] = 0ull;
-    DNode parent = S.node(jb.node);
-    bk_stats sp = node_stats(parent);
-    bk_stats sr = bk_stats_sub(sp, sl);
-    if (bern) { sl.sr = 0; sr.sr = 0; }   // the children's log-likelihood sums arrive with the LL epoch
-    const bool pre = sh.pre_z_tree == t && sh.pre_z_round == round;
-    double zl = pre ? sh.pre_zl[q] : bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
-    double zr = pre ? sh.pre_zr[q] : bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
-    float vl = bk_leaf_value(sl.n, sl.sst, P.inv_qm, zl, hot->leaf_sd);
-    float vr = bk_leaf_value(sr.n, sr.sst, P.inv_qm, zr, hot->leaf_sd);
-    const double g_parent = bk_leaf_gain(sp, parent.value, P.inv_qscale);
-    const int nn = S.h->n_nodes;
-    parent.var = jb.var; parent.split = jb.split; parent.left = nn;
-    S.node(jb.node) = parent;
-    DNode nl; nl.var = -1; nl.split = 0.0f; nl.left = -1; nl.depth = parent.depth + 1; nl.value = vl; nl.aux[0] = 0; nl.aux[1] = 0; nl.aux[2] = 0;
-    set_node_stats(nl, sl);
-    DNode nr = nl; nr.value = vr; set_node_stats(nr, sr);
-    S.node(nn) = nl; S.node(nn + 1) = nr;
-    S.h->n_nodes = nn + 2;
-    if (!bern) {
-      const double gain = BK_DADD(BK_DADD(BK_DSUB(S.h->gain, g_parent), bk_leaf_gain(sl, vl, P.inv_qscale)), bk_leaf_gain(sr, vr, P.inv_qscale));
-      S.h->gain = gain;
-      S.h->lw = bk_normal_loglik_pre(bk_ssq_from_gain(hot->r2_total, gain), hot->ll_inv2s2, hot->ll_c);
-    } else {   // turn the partition job into the LL job of the same particle (same list position)
-      Job lj = jb;
-      lj.kind = BK_JOB_LL; lj.src_row = jb.dst_row; lj.split = vl; lj.rule = __float_as_int(vr);
-      sh.jobs[ji] = lj;
-    }
-    S.h->row = jb.dst_row;
-    atomicAdd(&hot->c_grow, 1);
-    if (jb.src_row == BK_ROW_VIRTUAL) atomicAdd(&hot->c_grow_root, 1);
-    bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base + q - 1);
-    if (rec) { rec->var = jb.var; rec->split = jb.split; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
-  }
-  CTRL_SYNC();
-}
-
-// Bernoulli: the LL epoch summed the quantised log-likelihood terms of the rows of every new leaf pair
-__device__ void finalize_ll(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
-  const int buf = hot->buf;
-  const int ji = (int)threadIdx.x - 32;
-  if (ji >= 0 && ji < hot->n_jobs && sh.jobs[ji].kind == BK_JOB_LL) {
-    const Job jb = sh.jobs[ji];
-    const PRef S = pref(P, c, buf, jb.slot);
-    unsigned long long* acc = P.accL + ((size_t)c * P.P + jb.slot) * BK_ACC_STRIDE;
-    const long long ll_l = (long long)__ldcg(acc + BK_ACC_LLL), ll_r = (long long)__ldcg(acc + BK_ACC_LLR);
-    acc[BK_ACC_LLL] = 0ull; acc[BK_ACC_LLR] = 0ull;
-    const long long ll_parent = S.node(jb.node).sr;
-    S.node(jb.left_id).sr = ll_l;
-    S.node(jb.left_id + 1).sr = ll_r;
-    const double llq = BK_DADD(BK_DSUB(S.h->gain, (double)ll_parent), (double)(ll_l + ll_r));   // integers: exact
-    S.h->gain = llq;
-    S.h->lw = bk_bern_loglik(llq);
-  }
-  CTRL_SYNC();
+  return nj;
 }
 
 __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot /* smem, [P] */) {
@@ -898,7 +938,8 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     return;
   }
 
-  bool have_round = false;
+  // `closing` = a round of the current tree has just completed (its epoch is done); false right after init_particles
+  bool closing = false;
   if (stage == BK_ST_WAIT_SWEEP) {
     __shared__ int s_more;
     if (threadIdx.x == 0) {
@@ -939,73 +980,75 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     MARK(111);
   } else if (stage == BK_ST_WAIT_ROUND) {
     MARK(120);
-    finalize_grows(P, c, ctl, hot, sh);
+    finalize_own(P, c, hot, sh, hot->buf, hot->round, hot->cur_tree, hot->trace_round_base);
     TSUB(0);
     MARK(121);
     if (P.lik == BK_LIK_BERNOULLI_LOGIT && hot->n_grow > 0) {
       // leaf values are known now: publish the LL jobs (the first n_grow list entries) and wait for their sums
+      CTRL_SYNC();
       const int ng = hot->n_grow;
       const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
-      for (int i = BK_WTID; i >= 0 && i < ng * 3 * BK_JOB_COPIES; i += BK_WTHREADS)
-        reinterpret_cast<uint4*>(ctl->jobs[i / (ng * 3)])[i % (ng * 3)] = s4[i % (ng * 3)];
-      CTRL_SYNC();
+      for (int i = BK_WTID; i >= 0 && i < ng * 3; i += BK_WTHREADS) reinterpret_cast<uint4*>(ctl->jobs[0])[i] = s4[i];
       if (threadIdx.x == 0) { hot->n_jobs = ng; hot->cmd = BK_CMD_LL; hot->stage_next = BK_ST_WAIT_LL; }
       CTRL_SYNC();
       return;
     }
-    have_round = true;
+    closing = true;
   } else {  // BK_ST_WAIT_LL
-    finalize_ll(P, c, ctl, hot, sh);
+    finalize_ll_own(P, c, sh, hot->buf);
     TSUB(0);
-    have_round = true;
+    closing = true;
   }
 
   for (;;) {
-    if (have_round) {
-      // the round hot->round is complete: log weights, liveness, resampling
-      const int buf = hot->buf;
-      const int rbase = hot->trace_round_base;   // (thread 0 moves it on only after the barrier below)
-      if (BK_WTID >= 1 && BK_WTID < P.P) {   // sh.live was cleared by propose() / init_particles()
-        const PRef S = pref(P, c, buf, BK_WTID);
-        sh.lw[BK_WTID] = S.h->lw;
-        if (S.h->q_head < S.h->n_nodes) sh.live = 1;
-        bk_trace_rec* rec = trace_at(P, c, rbase + BK_WTID - 1);
-        if (rec) rec->log_w = S.h->lw;
-      }
-      CTRL_SYNC();
-      const int live = sh.live;
+    // Every thread works on values it read BEFORE the barrier below; thread 0 moves the shared scalars on after it.
+    const int buf = hot->buf, t = hot->cur_tree;
+    const int round_done = hot->round, rbase = hot->trace_round_base;
+    const int q = BK_WTID;
+    const bool is_p = q >= 1 && q < P.P;
+    if (closing && is_p) {   // the round `round_done` is complete: log weights and liveness (own particle, finalized above)
+      const PRef S = pref(P, c, buf, q);
+      if (S.h->q_head < S.h->n_nodes) sh.live = 1;
+      bk_trace_rec* rec = trace_at(P, c, rbase + q - 1);
+      if (rec) rec->log_w = S.h->lw;
+    }
+    if (q >= 0 && q < 8) sh.used_rows[q] = 0u;
+    if (q == 0) { sh.n_cnt_jobs = 0; sh.next_sel = 1; sh.err_bits = 0; }
+    CTRL_SYNC();
+    const int live = sh.live;
+    int round = 0, rb = rbase, src = q;
+    bool deferred = false;
+    if (closing) {
       if (threadIdx.x == 0) { hot->c_rounds += 1; hot->trace_round_base = rbase + (P.P - 1); }
       MARK(130 + live);
       TSUB(1);
       if (!live) { CTRL_SYNC(); finish_tree(P, c, ctl, hot, sh); TSUB(7); MARK(139); return; }
-      const uint32_t u = (sh.pre_z_tree == hot->cur_tree && sh.pre_z_round == hot->round)
-                             ? sh.pre_ures
-                             : bk_rng(P.seed, P.chain_base + (uint32_t)(c / P.G), (uint32_t)hot->draw, (uint32_t)(c % P.G),
-                                      (uint32_t)hot->cur_tree, (uint32_t)hot->round, 0, BK_U_RESAMPLE).v[0];
-      MARK(132);
-      normalise_and_resample(P, sh, 1, P.P - 1, u);
-      TSUB(2);
-      MARK(133);
-      // anc[i] indexes particles 1..P-1; convert to slot -> source slot
-      if (BK_WTID >= 0 && BK_WTID < P.P) {
-        int s = BK_WTID;
-        sh.src_slot[s] = s == 0 ? 0 : sh.anc[s - 1] + 1;
-        if (s >= 1) { bk_trace_rec* rec = trace_at(P, c, rbase + s - 1); if (rec) rec->ancestor = sh.src_slot[s]; }
+      round = round_done + 1; rb = rbase + (P.P - 1); deferred = true;
+      if (q >= 0 && q < 128) {   // warps 1..4: the particle threads resample for themselves
+        const uint32_t u = (sh.pre_z_tree == t && sh.pre_z_round == round_done)
+                               ? sh.pre_ures
+                               : bk_rng(P.seed, P.chain_base + (uint32_t)(c / P.G), (uint32_t)hot->draw, (uint32_t)(c % P.G),
+                                        (uint32_t)t, (uint32_t)round_done, 0, BK_U_RESAMPLE).v[0];
+        const int anc = resample_own(P, c, buf, sh, 1, P.P - 1, u);
+        src = is_p ? anc + 1 : 0;
+        if (is_p) { bk_trace_rec* rec = trace_at(P, c, rbase + q - 1); if (rec) rec->ancestor = src; }   // (record of the round just closed)
       }
-      if (threadIdx.x == 0) { sh.copy_pending = 1; hot->round += 1; }   // the copy itself runs in the epoch's shadow
-      CTRL_SYNC();
-      TSUB(3);
-      (void)buf;
+      TSUB(2);
     }
     MARK(140);
-    int nj = propose(P, c, ctl, hot, sh);
+    const int nj = open_round(P, c, ctl, hot, sh, buf, round, rb, deferred, src);
     MARK(141);
-    have_round = true;
+    if (threadIdx.x == 0) {   // (every thread took its copies of these before the barriers inside open_round)
+      hot->round = round; sh.live = 0;
+      if (deferred) sh.copy_pending = 1;
+    }
     if (nj > 0) {
       if (threadIdx.x == 0) { hot->cmd = BK_CMD_ROUND; hot->stage_next = BK_ST_WAIT_ROUND; }
       return;   // (control_loop's barrier follows)
     }
+    CTRL_SYNC();
     apply_pending_copy(P, c, hot, sh);   // no epoch to hide behind: the next round starts right away
+    closing = true;
   }
 }
 

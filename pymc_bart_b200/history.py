@@ -1,0 +1,180 @@
+"""Forest history: the ``(baseline_forest, batches)`` format published in ``op.all_trees`` and its device store.
+
+Reference: bartrs' native ``PosteriorSampler`` as the shell uses it — ``from_history(batches, baseline_forest, m,
+n_outputs)`` (pymc_bart/utils.py:124-127), ``n_draws`` / ``n_outputs`` (:63,83,91), ``sample_posterior(X, draw_indices,
+excluded)`` (:67,69,103) — and ``_MultiChainSampler`` (:74-107).  "Better tree storage" (CHANGELOG.md:23): a chain's
+history is its initial forest plus, per draw, only the trees that draw rewrote.
+
+Formats (plain numpy, picklable through the ``multiprocessing.Manager`` proxy of pymc_bart/bart.py:134-135):
+
+* ``baseline_forest = (nodes, n_nodes)``: ``n_nodes`` int32 ``[G*m]`` (output group major), ``nodes`` the trees' nodes
+  back to back (NODE_DTYPE, 24 bytes each, ``n_nodes`` of them per tree);
+* one batch per post-tuning draw: ``(first, n_nodes, nodes)`` with ``n_nodes`` int32 ``[G, T]`` for the trees
+  ``first .. first+T-1`` of every output group, nodes back to back in that order.
+
+Device store (``DeviceForests``): every tree version once, plus a table ``[forest][tree] -> version``; a draw costs
+``m`` ints (C5: 800 bytes instead of a 1.2 MB dense forest).  Forest rows are ordered (chain, draw, group): the
+global draw index of the multi-chain sampler addresses the table directly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+
+
+def compact_forest(nodes: np.ndarray, n_nodes: np.ndarray):
+    """Dense ``[k][255]`` nodes + counts -> (flat nodes, counts)."""
+    n_nodes = np.ascontiguousarray(n_nodes, dtype=np.int32).reshape(-1)
+    nodes = np.asarray(nodes, dtype=_cabi.NODE_DTYPE).reshape(n_nodes.size, -1)
+    flat = np.concatenate([nodes[t, : n_nodes[t]] for t in range(n_nodes.size)]) if n_nodes.size else np.zeros(0, _cabi.NODE_DTYPE)
+    return np.ascontiguousarray(flat), n_nodes
+
+
+class ChainHistory:
+    """Host description of one chain's history: tree versions and the per-draw version table."""
+
+    def __init__(self, batches, baseline_forest, m: int, n_outputs: int):
+        base_nodes, base_nn = baseline_forest
+        G = int(n_outputs)
+        base_nn = np.ascontiguousarray(base_nn, dtype=np.int32).reshape(-1)
+        if base_nn.size != G * m:
+            raise ValueError("baseline forest does not hold n_outputs * m trees")
+        batches = list(batches)
+        self.m, self.G, self.n_draws = int(m), G, len(batches)
+        nn_parts = [base_nn] + [np.ascontiguousarray(b[1], dtype=np.int32).reshape(-1) for b in batches]
+        node_parts = [np.asarray(base_nodes, dtype=_cabi.NODE_DTYPE)] + [np.asarray(b[2], dtype=_cabi.NODE_DTYPE) for b in batches]
+        self.ver_nn = np.concatenate(nn_parts)
+        self.nodes = np.concatenate(node_parts) if node_parts else np.zeros(0, _cabi.NODE_DTYPE)
+        if int(self.ver_nn.sum()) != self.nodes.size:
+            raise ValueError("history node counts do not add up")
+        # version table: forest row (draw, group) -> version of every tree
+        tbl = np.empty((self.n_draws, G, m), dtype=np.int32)
+        cur = np.arange(G * m, dtype=np.int32).reshape(G, m)
+        nxt = G * m
+        for d, b in enumerate(batches):
+            first, nn = int(b[0]), np.asarray(b[1])
+            T = nn.reshape(G, -1).shape[1]
+            cur[:, first:first + T] = nxt + np.arange(G * T, dtype=np.int32).reshape(G, T)
+            nxt += G * T
+            tbl[d] = cur
+        self.ver_tbl = tbl.reshape(self.n_draws * G, m)
+
+    def forest_sizes(self) -> np.ndarray:
+        return self.ver_nn[self.ver_tbl].sum(axis=1) if self.ver_tbl.size else np.zeros(0, np.int64)
+
+    def dense_forests(self) -> np.ndarray:
+        """[n_draws*G][m][255] dense nodes (test helper for the oracle's dense predictor; O(draws*m*255) memory)."""
+        off = np.concatenate([[0], np.cumsum(self.ver_nn)])
+        out = np.zeros((self.ver_tbl.shape[0], self.m, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
+        for f in range(self.ver_tbl.shape[0]):
+            for t in range(self.m):
+                v = self.ver_tbl[f, t]
+                out[f, t, : self.ver_nn[v]] = self.nodes[off[v]: off[v + 1]]
+        return out
+
+
+class DeviceForests:
+    """All chains of an op on the device: nodes, version offsets, version table; one launch per prediction call."""
+
+    def __init__(self, chains: list, split_rules=None, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("posterior prediction needs a CUDA device (no CPU fallback)")
+        if not chains:
+            raise ValueError("No posterior draws available yet: run pm.sample() first.")
+        self.lib = _cabi.load()
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.m, self.G = chains[0].m, chains[0].G
+        nodes, nn, tbl, voff = [], [], [], 0
+        for ch in chains:
+            if ch.m != self.m or ch.G != self.G:
+                raise ValueError("chains disagree on m / n_outputs")
+            nodes.append(ch.nodes); nn.append(ch.ver_nn); tbl.append(ch.ver_tbl + voff)
+            voff += ch.ver_nn.size
+        ver_nn = np.concatenate(nn)
+        ver_off = np.zeros(ver_nn.size + 1, dtype=np.int64)
+        np.cumsum(ver_nn, out=ver_off[1:])
+        if ver_off[-1] >= 2**31:
+            raise ValueError("forest history exceeds 2^31 nodes")
+        ver_tbl = np.ascontiguousarray(np.concatenate(tbl), dtype=np.int32)
+        self.n_draws_per_chain = [ch.n_draws for ch in chains]
+        self.n_draws = int(sum(self.n_draws_per_chain))
+        self.max_forest_nodes = int(ver_nn[ver_tbl].sum(axis=1).max()) if ver_tbl.size else 0
+        self.history_bytes = int(ver_off[-1]) * _cabi.NODE_DTYPE.itemsize + ver_tbl.nbytes + ver_off.size * 4
+        with torch.cuda.device(self.device):
+            self.nodes_dev = torch.from_numpy(np.concatenate(nodes).view(np.uint8).reshape(-1).copy()).to(self.device)
+            self.ver_off_dev = torch.from_numpy(ver_off.astype(np.int32)).to(self.device)
+            self.ver_tbl_dev = torch.from_numpy(ver_tbl).to(self.device)
+            self.rules_dev = None
+            if split_rules is not None:
+                self.rules_dev = torch.from_numpy(np.ascontiguousarray(split_rules, dtype=np.int32)).to(self.device)
+            self.err_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def upload(self, X):
+        """Row-major float32 copy of X on the device (upload once, predict many times)."""
+        torch = self.torch
+        if isinstance(X, torch.Tensor):
+            return X
+        Xh = np.ascontiguousarray(np.asarray(X, dtype=np.float32))
+        if Xh.ndim != 2:
+            raise ValueError("X must be two-dimensional")
+        return torch.from_numpy(Xh).to(self.device)
+
+    def predict(self, X, draw_indices, masks=None):
+        """Sum of trees of the forests of the global draws ``draw_indices`` at the rows of X.
+
+        masks: None or uint8 ``[n_masks][p]`` (1 = excluded variable).  Returns a device tensor
+        ``[n_masks or 1][len(draw_indices)][G][n]`` float32."""
+        torch = self.torch
+        Xd = self.upload(X)
+        n, p = int(Xd.shape[0]), int(Xd.shape[1])
+        di = np.asarray(draw_indices, dtype=np.int64).reshape(-1)
+        if di.size and (di.min() < 0 or di.max() >= self.n_draws):
+            raise IndexError("draw index out of range")
+        sel = (di[:, None] * self.G + np.arange(self.G)[None, :]).reshape(-1).astype(np.int32)
+        n_masks = 0 if masks is None else int(np.asarray(masks).shape[0])
+        with torch.cuda.device(self.device):
+            sel_dev = torch.from_numpy(sel).to(self.device)
+            masks_dev = None
+            if n_masks:
+                mk = np.ascontiguousarray(masks, dtype=np.uint8)
+                if mk.shape != (n_masks, p):
+                    raise ValueError("masks must have shape [n_masks][p]")
+                masks_dev = torch.from_numpy(mk).to(self.device)
+            self.err_dev.zero_()
+            stream = torch.cuda.current_stream(self.device)
+            outs = []
+            for s0 in range(0, sel.size, 32768):   # (grid limit: 65535 forests per launch)
+                s1 = min(sel.size, s0 + 32768)
+                out_s = torch.empty((max(n_masks, 1), s1 - s0, n), dtype=torch.float32, device=self.device)
+                rc = self.lib.bk_predict_history(
+                    self.device.index, C.c_void_p(stream.cuda_stream), self.nodes_dev.data_ptr(), self.ver_off_dev.data_ptr(),
+                    self.ver_tbl_dev.data_ptr(), self.m, self.max_forest_nodes, Xd.data_ptr(), n, p,
+                    sel_dev.data_ptr() + 4 * s0, s1 - s0, None if masks_dev is None else masks_dev.data_ptr(), n_masks,
+                    None if self.rules_dev is None else self.rules_dev.data_ptr(), out_s.data_ptr(), self.err_dev.data_ptr())
+                _cabi.check(rc, "bk_predict_history")
+                outs.append(out_s)
+            out = outs[0] if len(outs) == 1 else (torch.cat(outs, dim=1) if outs else
+                                                  torch.empty((max(n_masks, 1), 0, n), dtype=torch.float32, device=self.device))
+            if int(self.err_dev.item()) != 0:
+                raise RuntimeError("posterior prediction: device-side consistency flag set (malformed forest history)")
+        return out.reshape(max(n_masks, 1), di.size, self.G, n)
+
+    def pearson_r2(self, a, b):
+        """Squared Pearson correlation per (subset, sample): a ``[S][len]``, b ``[K][S][len]`` device tensors
+        (pymc_bart/utils.py:1339-1346) -> numpy ``[K][S]`` float64."""
+        torch = self.torch
+        a = a.contiguous(); b = b.contiguous()
+        S, ln = int(a.shape[0]), int(a[0].numel())
+        K = int(b.shape[0])
+        with torch.cuda.device(self.device):
+            out = torch.empty((K, S), dtype=torch.float64, device=self.device)
+            stream = torch.cuda.current_stream(self.device)
+            _cabi.check(self.lib.bk_pearson_r2(self.device.index, C.c_void_p(stream.cuda_stream), a.data_ptr(), b.data_ptr(), ln, S, K,
+                                               out.data_ptr()), "bk_pearson_r2")
+            return out.cpu().numpy()
