@@ -76,15 +76,18 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=20):
         self.rows = []
         self.proc = None
         self.gpu = str(gpu_index)
         self.windows = []
+        self.period_ms = int(period_ms)
 
     def start(self):
+        if self.period_ms <= 0:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms),
                                           "-i", self.gpu], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -236,6 +239,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     sync_all()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     grow = tupd = tune_upd = rounds = phases = 0
+    us_total = us_control = us_data = 0
     t_w0 = time.perf_counter()
     for i in range(steps):
         tune = i < n_tune
@@ -253,6 +257,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
             grow += st[c].grow_events; tupd += st[c].tree_updates; rounds += st[c].rounds
             tune_upd += st[c].tree_updates if tune else 0
         phases += st[0].phases
+        us_total += max(st[c].us_total for c in range(nvc)); us_control += st[0].us_control; us_data += st[0].us_data
     t_gather0 = torch.cuda.Event(enable_timing=True); t_gather1 = torch.cuda.Event(enable_timing=True)
     t_gather0.record(stream)
     if world > 1:   # the run's single collective (sampling.gather_posterior): ordered after the steps on their stream
@@ -272,7 +277,8 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     total_ms_max, gather_ms_max = [float(v) for v in tm.tolist()]
     g_all, t_all, tu_all = [float(v) for v in agg.tolist()]
     value = world * chains * steps / (total_ms_max / 1e3)
-    out = {"value": value, "unit": "draws/s", "ms_per_step": total_ms_max / steps, "steps": steps, "warmup": warm}
+    out = {"value": value, "unit": "draws/s", "ms_per_step": total_ms_max / steps, "steps": steps, "warmup": warm,
+           "in_kernel_us": {"step": us_total / steps, "control_chain0": us_control / steps, "data_wait_chain0": us_data / steps}}
     if args.profile_only:
         dev.close()
         return out
@@ -368,6 +374,7 @@ def main():
     ap.add_argument("--c5-steps", type=int, default=30)
     ap.add_argument("--cpu-draws", type=int, default=None, help="CPU baseline sample size (draws per chain)")
     ap.add_argument("--profile-only", action="store_true", help="device-timed leg only (for ncu runs)")
+    ap.add_argument("--clock-ms", type=int, default=20, help="nvidia-smi sampling period in ms (0 = no clock sampling)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -391,7 +398,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, args.clock_ms)
     clocks.start()
     main_m = measure(args.config, steps, warm, args, rank, world, local, clocks, peak, peak_src)
     c5_m = None
@@ -400,10 +407,11 @@ def main():
     clk = clocks.stop()
     if rank == 0:
         if args.profile_only:
-            print(json.dumps({"profile_only": True, "value": main_m["value"], "ms_per_step": main_m["ms_per_step"]}), flush=True)
+            print(json.dumps({"profile_only": True, "value": main_m["value"], "ms_per_step": main_m["ms_per_step"],
+                              "in_kernel_us": main_m["in_kernel_us"]}), flush=True)
         else:
             config = {k: main_m[k] for k in ("workload", "draws_timed", "l2", "grow_events_per_tree_update", "tree_updates_per_s",
-                                             "grow_events_per_s", "rounds_per_tree_update", "grid_phases_per_step", "gather_ms",
+                                             "grow_events_per_s", "rounds_per_tree_update", "grid_phases_per_step", "in_kernel_us", "gather_ms",
                                              "gather_bytes_per_rank")}
             if c5_m is not None:
                 c5_m["n_gpus"] = world

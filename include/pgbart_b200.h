@@ -20,8 +20,11 @@
  *                                shell encodes with _encode_vi (pymc_bart/utils.py:1387-1398)
  *   bk_export_forest          <- the (baseline_forest, batches) history published in
  *                                op.all_trees (pymc_bart/utils.py:117,124-127)
- *   bk_predict                <- PosteriorSampler.sample_posterior(X, draw_indices,
- *                                excluded) (pymc_bart/utils.py:60-71,93-107)
+ *   bk_set_history/bk_history_batch <- the per-draw batches of that history, appended while sampling
+ *                                (pymc_bart/bart.py:133-146)
+ *   bk_predict_history        <- PosteriorSampler.from_history(...).sample_posterior(X, draw_indices,
+ *                                excluded) (pymc_bart/utils.py:60-71,93-107,124-127)
+ *   bk_pearson_r2             <- pearsonr2 of compute_variable_importance (pymc_bart/utils.py:1339-1346)
  *
  * Conventions: plain pointers and sizes only; 0 = success, negative = error
  * (message via bk_last_error); nothing throws across the boundary.  Device
@@ -38,7 +41,7 @@
 extern "C" {
 #endif
 
-#define BK_ABI_VERSION 1
+#define BK_ABI_VERSION 2
 
 #define BK_OK 0
 #define BK_ERR_ARG (-1)
@@ -151,9 +154,10 @@ void bk_destroy(bk_handle* h);
 int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_host,
             bk_step_stats* stats_host);
 
-/* Asynchronous form: bk_step_launch enqueues the H2D of sigma, the step kernel and the D2H of
- * the per-step outputs on the handle's stream and returns; bk_step_wait blocks until they are
- * done and copies them out (same outputs as bk_step).  bk_stream returns the handle's
+/* Asynchronous form: bk_step_launch enqueues the step kernel and the D2H of the per-step outputs
+ * on the handle's stream and returns; bk_step_wait blocks until the OLDEST step in flight is done
+ * and copies its outputs out (same outputs as bk_step).  Up to two steps may be in flight (launch,
+ * launch, wait, launch, wait, ...): the host prepares step k+1 while step k runs.  bk_stream returns the handle's
  * cudaStream_t (as void*) so the host can record events on it or order its own copies after it. */
 int bk_step_launch(bk_handle* h, int tune, const float* sigma_host);
 int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host);
@@ -178,15 +182,35 @@ int bk_export_trees(bk_handle* h, int chain, int first, int count, bk_node* node
 /* leaf assignment of every training row in every tree: ids_host [n_trees][n_rows] uint8 */
 int bk_export_leaf_ids(bk_handle* h, int chain, uint8_t* ids_host);
 
-/* Posterior prediction (row N1).  forests_dev: [n_draws][n_trees][255] bk_node,
- * n_nodes_dev: [n_draws][n_trees]; X_dev: [n][n_cols] float32 ROW-major new data;
- * draw_idx_dev: [n_idx]; excluded_mask_dev: [n_cols] uint8 or NULL;
- * split_rules_dev: [n_cols] BK_RULE_* or NULL (all continuous);
- * out_dev: [n_idx][n] float32.  Runs on `stream` (cudaStream_t as void*). */
-int bk_predict(int device, void* stream, const bk_node* forests_dev, const int32_t* n_nodes_dev,
-               int n_trees, const float* X_dev, int n, int n_cols, const int32_t* draw_idx_dev,
-               int n_idx, const uint8_t* excluded_mask_dev, const int32_t* split_rules_dev,
-               float* out_dev);
+/* Tree history (the `(baseline_forest, batches)` entries of op.all_trees, pymc_bart/utils.py:117,124-127; bart.py:133-146).
+ * With bk_set_history(h, 1) every post-tuning step also copies the trees it rewrote into pinned host memory behind
+ * the kernel (asynchronous, the step does not stall).  bk_history_batch hands out the batch of the last step waited
+ * for: *first_tree, n_nodes_host [n_chains*n_groups][T] and the trees' nodes compacted back to back in the same order
+ * (capacity n_chains*n_groups*T*255), *total_nodes of them.  Returns T, 0 for a tuning step / history off, < 0 on error. */
+int bk_set_history(bk_handle* h, int enable);
+int bk_history_batch(bk_handle* h, int32_t* first_tree, int32_t* n_nodes_host, bk_node* nodes_host, int64_t* total_nodes);
+
+/* Posterior prediction from the forest history (row N1): what bartrs' PosteriorSampler.sample_posterior(X, draw_indices,
+ * excluded) does for the shell (pymc_bart/utils.py:60-71,93-107), for all chains of an op in ONE launch.
+ * nodes_dev: every stored tree version, compacted; ver_off_dev [n_versions + 1]: first node of a version;
+ * ver_tbl_dev [n_forests][n_trees]: version of every tree of a forest (forest = chain, draw, output group);
+ * max_forest_nodes: largest node total of a forest (sizes the shared-memory staging); X_dev [n][n_cols] float32
+ * ROW-major new data; sel_dev: forest rows to evaluate, [n_sel] (shared by all masks) or, with sel_per_mask,
+ * [n_masks][n_sel]; excluded_masks_dev [n_masks][n_cols] uint8 (1 = variable excluded: weighted descent by the
+ * children's training counts) or NULL with n_masks = 0; split_rules_dev [n_cols] BK_RULE_* or NULL;
+ * out_dev [max(n_masks,1)][n_sel][n] float32; err_dev: int32 device flag the caller cleared (non-zero afterwards =
+ * malformed history).  Runs on `stream` (cudaStream_t as void*). */
+int bk_predict_history(int device, void* stream, const bk_node* nodes_dev, const int32_t* ver_off_dev,
+                       const int32_t* ver_tbl_dev, int n_trees, int max_forest_nodes, const float* X_dev, int n,
+                       int n_cols, const int32_t* sel_dev, int n_sel, int sel_per_mask,
+                       const uint8_t* excluded_masks_dev, int n_masks, const int32_t* split_rules_dev,
+                       float* out_dev, int32_t* err_dev);
+
+/* Squared Pearson correlation of the variable-importance search (row N4; pymc_bart/utils.py:1339-1346 `pearsonr2`,
+ * called per posterior sample at :1003-1005 and :1038-1040).  a_dev [n_samples][len] (full model),
+ * b_dev [n_subsets][n_samples][len]; out_dev [n_subsets][n_samples] float64. */
+int bk_pearson_r2(int device, void* stream, const float* a_dev, const float* b_dev, int len, int n_samples,
+                  int n_subsets, double* out_dev);
 
 #ifdef __cplusplus
 }

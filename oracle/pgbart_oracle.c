@@ -471,7 +471,7 @@ float bko_leaf_sd(const bko* o) { return o->leaf_sd; }
  */
 static double predict_tree(const bk_node* nodes, const float* x, const uint8_t* excl, const int32_t* rules) {
   /* explicit stack of (node, weight); the right child is pushed first so the left is visited first */
-  int sn[48]; double sw[48]; int sp = 1;
+  int sn[130]; double sw[130]; int sp = 1;   /* depth + 2 <= 130 entries for trees of at most 255 nodes: cannot overflow */
   sn[0] = 0; sw[0] = 1.0;
   double tv = 0.0;
   while (sp > 0) {
@@ -482,7 +482,7 @@ static double predict_tree(const bk_node* nodes, const float* x, const uint8_t* 
     int l = nd->left, r = nd->left + 1;
     if (excl && excl[nd->var]) {
       double tot = (double)nodes[l].n + (double)nodes[r].n;
-      if (!(tot > 0.0) || sp + 2 > 48) continue;
+      if (!(tot > 0.0) || sp + 2 > 130) continue;
       double wl = BK_DDIV((double)nodes[l].n, tot);
       double wr = BK_DSUB(1.0, wl);
       sn[sp] = r; sw[sp] = BK_DMUL(w, wr); ++sp;

@@ -7,8 +7,15 @@ matplotlib analytics of pymc_bart/utils.py are out of scope (SURVEY.md §2 C6-C7
 from .bart import BART, BARTRV  # noqa: F401
 from .utils import PosteriorSampler, _decode_vi, _encode_vi, _get_posterior_sampler, _sample_posterior  # noqa: F401
 
-__version__ = "0.1.0"
-__all__ = ["BART", "PGBART", "PosteriorSampler", "sample"]
+try:   # what `import bartrs` does for the reference (pymc_bart/__init__.py:15-18): register PGBART with PyMC when it is there
+    import pymc as _pm  # noqa: F401
+except ImportError:
+    _pm = None
+if _pm is not None:
+    from . import pymc_adapter  # noqa: F401  (appends the step class to pm.STEP_METHODS)
+
+__version__ = "0.2.0"
+__all__ = ["BART", "PGBART", "PosteriorSampler", "sample", "compute_variable_importance", "get_variable_inclusion"]
 
 
 def __getattr__(name):  # PGBART / sample import torch lazily
@@ -20,4 +27,8 @@ def __getattr__(name):  # PGBART / sample import torch lazily
         from .sampling import sample
 
         return sample
+    if name in ("compute_variable_importance", "get_variable_inclusion", "vi_to_kulprit"):
+        from . import importance
+
+        return getattr(importance, name)
     raise AttributeError(name)

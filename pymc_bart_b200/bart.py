@@ -16,6 +16,35 @@ import numpy as np
 
 __all__ = ["BART", "BARTRV", "preprocess_xy"]
 
+_manager = None
+
+
+def _history_manager():
+    """One ``multiprocessing.Manager`` server for the process, started on first use.  The reference starts one per BART
+    variable (pymc_bart/bart.py:133-135); the lists it serves are what crosses PyMC's per-chain worker processes."""
+    global _manager
+    if _manager is None:
+        import multiprocessing
+
+        # "spawn": the server must not be forked from a process that already runs CUDA / BLAS threads
+        _manager = multiprocessing.get_context("spawn").Manager()
+    return _manager
+
+
+def sibling_list(all_trees):
+    """A new list of the same kind as `all_trees`: a fresh shared list on the SAME manager server when `all_trees` is
+    a Manager proxy (also from a worker process, which only holds the unpickled proxy), else a plain list.  The step
+    uses it for a chain's `batches`, so that every draw ships only its own trees through the proxy."""
+    from multiprocessing.managers import BaseProxy, SyncManager
+
+    if not isinstance(all_trees, BaseProxy):
+        return []
+    mgr = getattr(all_trees, "_manager", None)
+    if mgr is None:
+        mgr = SyncManager(address=all_trees._token.address, authkey=all_trees._authkey)
+        mgr.connect()
+    return mgr.list()
+
 
 def preprocess_xy(X, Y):
     """pandas / polars / array -> float64 numpy (pymc_bart/bart.py:193-212)."""
@@ -74,19 +103,24 @@ class BARTVariable:
 
 
 def BART(name, X, Y, m=50, alpha=0.95, beta=2.0, response="constant", split_rules=None, split_prior=None,
-         shape=None, separate_trees=False, **kwargs):
+         shape=None, separate_trees=False, shared_history=True, **kwargs):
     """Same signature as ``pmb.BART`` (pymc_bart/bart.py:115-127) plus ``separate_trees``
-    (dropped from the reference at this commit; BASELINE.json config 4 asks for it)."""
+    (dropped from the reference at this commit; BASELINE.json config 4 asks for it).
+
+    ``shared_history=True`` (the reference's behaviour, bart.py:133-135) makes ``op.all_trees`` a
+    ``multiprocessing.Manager().list()`` proxy, so that step objects running in worker processes publish their tree
+    history to the parent; ``False`` keeps a plain list (single process, no manager server)."""
     if response in ("linear", "mix"):
         warnings.warn("Options linear and mix are experimental and still not well tested\nUse with caution.")
     Xn, Yn = preprocess_xy(X, Y)
     sp = np.array([]) if split_prior is None else np.asarray(split_prior)
+    mgr = _history_manager() if shared_history else None
     op_type = type(
         f"BART_{name}",
         (BARTRV,),
         {
             "name": "BART",
-            "all_trees": [],          # reference: multiprocessing.Manager().list() (bart.py:134-135)
+            "all_trees": mgr.list() if mgr is not None else [],   # bart.py:134-135
             "inplace": False,
             "initval": Yn.mean(),
             "X": Xn,

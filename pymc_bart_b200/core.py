@@ -58,7 +58,7 @@ class DeviceSampler:
         self._stats = (_cabi.BkStepStats * Cn)()
         self._sigma = np.ones(Cn, dtype=np.float32)
         self._host_out = None
-        self._host_view = None
+        self._host_enabled = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -94,6 +94,32 @@ class DeviceSampler:
         """torch view of the sampler's CUDA stream (for events and ordered copies)."""
         return self.torch.cuda.ExternalStream(int(self.lib.bk_stream(self.h)), device=self.device)
 
+    # ---- tree history (pymc_bart/utils.py:117-127) -------------------------------------------------------------------
+    def enable_history(self, enable: bool = True):
+        """Post-tuning steps also copy the trees they rewrote to pinned host memory behind the kernel."""
+        _cabi.check(self.lib.bk_set_history(self.h, int(bool(enable))), "bk_set_history")
+        T = max(self.settings.batch_tune, self.settings.batch_post)
+        self._hist_nn = np.zeros((self.C, T), dtype=np.int32)
+        self._hist_nodes = np.zeros(self.C * T * _cabi.BK_MAX_NODES, dtype=_cabi.NODE_DTYPE)
+        self.history_bytes_per_step = self.C * self.settings.batch_post * (_cabi.BK_MAX_NODES * 64 + 4)
+
+    def history_batch(self):
+        """Trees rewritten by the last step waited for: (first, n_nodes [C][T], nodes back to back) or None."""
+        first, total = C.c_int32(), C.c_int64()
+        T = self.lib.bk_history_batch(self.h, C.byref(first), self._hist_nn.ctypes.data, self._hist_nodes.ctypes.data, C.byref(total))
+        if T < 0:
+            _cabi.check(T, "bk_history_batch")
+        if T == 0:
+            return None
+        nn = self._hist_nn.reshape(-1)[: self.C * T].reshape(self.C, T).copy()
+        return int(first.value), nn, self._hist_nodes[: int(total.value)].copy()
+
+    def baseline(self):
+        """Current forest of every (chain, group), compacted: list of (nodes, n_nodes) per virtual chain."""
+        from .history import compact_forest
+
+        return [compact_forest(*self.forest(c)) for c in range(self.C)]
+
     def trees(self, chain: int, first: int, count: int):
         nodes = np.zeros((count, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
         nn = np.zeros(count, dtype=np.int32)
@@ -107,16 +133,13 @@ class DeviceSampler:
     def enable_host_output(self, enable: bool = True):
         """Every step also copies the sum of trees to pinned host memory behind the kernel (the value handed to PyMC)."""
         _cabi.check(self.lib.bk_set_host_output(self.h, int(bool(enable))), "bk_set_host_output")
-        self._host_view = None
-        if enable:
-            ptr = self.lib.bk_sum_trees_host(self.h)
-            self._host_view = np.ctypeslib.as_array(ptr, shape=(self.C, self.N))
+        self._host_enabled = bool(enable)
 
     def sum_trees_host(self) -> np.ndarray:
         """Host view [C, N] of the sum of trees after the last step: the library's pinned buffer when host output is
         enabled (no extra copy), otherwise a blocking D2H copy."""
-        if getattr(self, "_host_view", None) is not None:
-            return self._host_view
+        if getattr(self, "_host_enabled", False):   # (two pinned buffers alternate: ask for the last step's every time)
+            return np.ctypeslib.as_array(self.lib.bk_sum_trees_host(self.h), shape=(self.C, self.N))
         torch = self.torch
         if self._host_out is None:
             self._host_out = torch.empty((self.C, self.N), dtype=torch.float32).pin_memory()

@@ -133,7 +133,14 @@ __shared__ unsigned long long s_cdbg[32];
 #define CT(i, dep) do { if (threadIdx.x == 32) { const long long n_ = UTICK(dep); s_cdbg[i] += (unsigned long long)(n_ - ct_last_); ct_last_ = n_; } } while (0)
 #define WDBG(i, t0)                                                              \
   do { if (threadIdx.x == 0) g_wdbg[blockIdx.x][i] += globaltimer_ns() - (t0); } while (0)
+// running cycle stamps of thread 32 (lane 0 of the first particle warp) across the round path: CTS(i, dep) adds the
+// cycles since the previous stamp to slot i once `dep` is available
+__shared__ long long s_ct_last;
+#define CTS(i, dep) do { if (threadIdx.x == 32) { const long long n_ = UTICK(dep); s_cdbg[i] += (unsigned long long)(n_ - s_ct_last); s_ct_last = n_; } } while (0)
+#define CTN(i) do { if (threadIdx.x == 32) s_cdbg[i] += 1ull; } while (0)
 #else
+#define CTS(i, dep) do { } while (0)
+#define CTN(i) do { } while (0)
 #define WDBG(i, t0) do { } while (0)
 #define UTICK(dep) 0ll
 #define UACC(i, v) do { } while (0)
@@ -146,6 +153,11 @@ __shared__ unsigned long long s_cdbg[32];
 #define BK_SPARSE_DIV 8
 #endif
 #define BK_CUM_SMEM 1024
+// per-launch arguments passed by value (no H2D copy, no memset on the step's stream)
+struct StepArgs {
+  float sigma[64];       // likelihood scale of every (chain, group)
+  unsigned epoch_base;   // epoch ids of this launch start above it
+};
 struct CtlShared {
   double lw[BK_MAX_PARTICLES];
   int anc[BK_MAX_PARTICLES];
@@ -189,6 +201,11 @@ struct CtlShared {
   int next_sel;
   int err_bits;
   unsigned long long r_slice[4];
+  int warp_grow_root[4];
+  // last value read from every accumulator word of accL: the workers only ever ADD (RED), the control CTA takes
+  // differences (exact in wrapping 64-bit arithmetic), so no accumulator is ever zeroed by a store that would have
+  // to be ordered before the next epoch's adds
+  unsigned long long acc_prev[BK_MAX_PARTICLES][BK_ACC_STRIDE];
 };
 
 // A worker CTA is split into BK_NGROUPS independent groups of BK_GROUP_THREADS threads.  Each group serves its own
@@ -273,25 +290,19 @@ __device__ __forceinline__ bk_trace_rec* trace_at(const Params& P, int c, int po
   return P.trace + (size_t)c * P.trace_cap + pos;
 }
 
-// k-th member (ascending row index) of `node` in pool row `row`; executed by one warp.
-// Two-level search over the per-tile member counts the workers left in rowcnt: every lane sums a contiguous chunk of
-// tiles (128-bit loads), one warp scan finds the chunk, a second scan over that chunk's 4-tile groups finds the tile —
-// about a dozen shuffles and three dependent L2 round trips whatever N is.
 __device__ __forceinline__ unsigned warp_incl_scan_u32(unsigned v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const unsigned nb = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += nb; }
   return v;
 }
-__device__ float select_split(const Params& P, int c, int row, int node, unsigned k, int var, int* err) {
-  const int lane = threadIdx.x & 31;
-  const uint4* cnt4 = reinterpret_cast<const uint4*>(P.rowcnt + ((size_t)c * P.R + row) * P.cnt_stride);
-  const int n4 = P.cnt_stride >> 2;                 // 4-tile groups in the row (padding tiles count 0)
-  const int per = (n4 + 31) >> 5;                   // groups per lane
-  unsigned off = k;
-  int tile = -1;
+// position of the k-th unit in an array of counts: returns the entry index and leaves the remaining offset in `off`
+// (-1 when the counts hold fewer than off + 1 units).  n4 = entries / 4 (the arrays are padded to 16 bytes with zeros).
+__device__ __forceinline__ int find_in_counts(const uint4* __restrict__ cnt4, int n4, unsigned& off, int lane) {
+  const int per = (n4 + 31) >> 5;                   // 4-entry groups per lane
+  int idx = -1;
   if (per <= 4) {
-    // small N: a lane keeps its (at most 16) tile counts in registers, so the lane that owns the k-th member walks
-    // them itself — one L2 round trip for the whole search
+    // a lane keeps its (at most 16) counts in registers, so the lane that owns the k-th unit walks them itself —
+    // one L2 round trip for the whole search
     uint4 v[4];
     unsigned sum = 0u;
 #pragma unroll
@@ -315,7 +326,7 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
           if (!found) { if (o2 < cs[e]) { found = true; t = u * 4 + e; } else o2 -= cs[e]; }
         }
       }
-      tile = __shfl_sync(0xffffffffu, src * per * 4 + t, src);
+      idx = __shfl_sync(0xffffffffu, src * per * 4 + t, src);
       off = __shfl_sync(0xffffffffu, o2, src);
     }
   } else {
@@ -336,7 +347,7 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
       const int src = __ffs(b) - 1;
       off -= __shfl_sync(0xffffffffu, excl, src);
       // second level: the `per` groups of lane src's chunk, 32 at a time
-      for (int j0 = 0; j0 < per && tile < 0; j0 += 32) {
+      for (int j0 = 0; j0 < per && idx < 0; j0 += 32) {
         const int i4 = src * per + j0 + lane;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (j0 + lane < per && i4 < n4) v = __ldcg(cnt4 + i4);
@@ -348,7 +359,7 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
           unsigned o2 = off - ex2;          // valid in lane l2
           int t = 0;
           if (o2 >= v.x) { o2 -= v.x; t = 1; if (o2 >= v.y) { o2 -= v.y; t = 2; if (o2 >= v.z) { o2 -= v.z; t = 3; } } }
-          tile = __shfl_sync(0xffffffffu, (src * per + j0 + l2) * 4 + t, l2);
+          idx = __shfl_sync(0xffffffffu, (src * per + j0 + l2) * 4 + t, l2);
           off = __shfl_sync(0xffffffffu, o2, l2);
         } else {
           off -= __shfl_sync(0xffffffffu, in2, 31);
@@ -356,34 +367,60 @@ __device__ float select_split(const Params& P, int c, int row, int node, unsigne
       }
     }
   }
+  return idx;
+}
+
+// k-th member (ascending row index) of `node` in pool row `row`; executed by one warp.  Search over the member counts
+// the workers left behind: [large N only: one count per bucket of 32 tiles, then the bucket's 32 tile counts] or the
+// per-tile counts directly; then the tile's leaf ids AND the tile of the split column are requested together, so the
+// split value is there when the member's position is known: two dependent L2 round trips at N = 100k, three at N = 1M.
+__device__ float select_split(const Params& P, int c, int row, int node, unsigned k, int var, int* err) {
+  const int lane = threadIdx.x & 31;
+  CTS(20, 0);   // (time between the end of the job assembly / previous selection and this one: cursor traffic)
+  const unsigned* cnt = P.rowcnt + ((size_t)c * P.R + row) * P.cnt_stride;
+  unsigned off = k;
+  int tile = -1;
+  if (P.nb > 0) {
+    const int bucket = find_in_counts(reinterpret_cast<const uint4*>(P.coarse + ((size_t)c * P.R + row) * P.nb_stride), P.nb_stride >> 2, off, lane);
+    if (bucket >= 0) {
+      const int t = bucket * BK_COARSE_TILES + lane;
+      const unsigned v = t < P.ntiles ? __ldcg(cnt + t) : 0u;
+      const unsigned incl = warp_incl_scan_u32(v, lane), excl = incl - v;
+      const unsigned b = __ballot_sync(0xffffffffu, off >= excl && off < incl);
+      if (b != 0u) {
+        const int src = __ffs(b) - 1;
+        tile = bucket * BK_COARSE_TILES + src;
+        off -= __shfl_sync(0xffffffffu, excl, src);
+      }
+    }
+  } else {
+    tile = find_in_counts(reinterpret_cast<const uint4*>(cnt), P.cnt_stride >> 2, off, lane);
+  }
   if (tile < 0) { if (lane == 0) *err |= 2; return 0.0f; }
-  const uint8_t* rp = P.rows + ((size_t)c * P.R + row) * P.Npad + (size_t)tile * BK_WARP_TILE + lane * BK_ROWS_PER_LANE;
-  unsigned long long ids = __ldcg(reinterpret_cast<const unsigned long long*>(rp));
+  CTS(26, tile);
+  const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
+  const unsigned long long ids = __ldcg(reinterpret_cast<const unsigned long long*>(P.rows + ((size_t)c * P.R + row) * P.Npad + base));
+  const float4* xp = reinterpret_cast<const float4*>(P.X + (size_t)var * P.Npad + base);
+  const float4 x0 = __ldg(xp), x1 = __ldg(xp + 1);       // (speculative: 1 KB per selection buys a whole round trip)
   unsigned mm = 0;
 #pragma unroll
   for (int e = 0; e < 8; ++e) mm |= (((unsigned)(ids >> (8 * e)) & 255u) == (unsigned)node) ? (1u << e) : 0u;
-  unsigned v = __popc(mm), incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned nb = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += nb;
-  }
-  unsigned excl = incl - v;
-  bool here = (off >= excl) && (off < incl);
-  unsigned b = __ballot_sync(0xffffffffu, here);
+  const unsigned v = __popc(mm);
+  CTS(27, v);
+  const unsigned incl = warp_incl_scan_u32(v, lane), excl = incl - v;
+  const unsigned b = __ballot_sync(0xffffffffu, off >= excl && off < incl);
   if (b == 0) { if (lane == 0) *err |= 4; return 0.0f; }
-  int src = __ffs(b) - 1;
-  int pos = -1;
+  const int src = __ffs(b) - 1;
+  float val = 0.0f;
   if (lane == src) {
-    unsigned want = off - excl, seen = 0;
+    const int pos = (int)__fns(mm, 0, (int)(off - excl) + 1);   // position of the (off - excl)-th member among the lane's 8 rows
+    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (mm & (1u << e)) { if (seen == want && pos < 0) pos = e; seen++; }
-    }
+    for (int e = 0; e < 8; ++e) if (e == pos) val = xs[e];
   }
-  pos = __shfl_sync(0xffffffffu, pos, src);
-  size_t i = (size_t)tile * BK_WARP_TILE + (size_t)src * BK_ROWS_PER_LANE + (size_t)pos;
-  return __ldg(P.X + (size_t)var * P.Npad + i);
+  val = __shfl_sync(0xffffffffu, val, src);
+  CTS(28, __float_as_int(val));
+  return val;
 }
 
 // Fixed-point weights of sh.lw[first..first+count) and systematic resampling into sh.anc[0..count) (bk_spec.h:
@@ -622,11 +659,14 @@ __device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* h
   const PRef S = pref(P, c, buf, q);
   unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
   bk_stats sl;
-  sl.n = (int32_t)__ldcg(acc + BK_ACC_N);
-  sl.sst = (int64_t)__ldcg(acc + BK_ACC_SST);
-  sl.sr = (int64_t)__ldcg(acc + BK_ACC_SR);
-#pragma unroll
-  for (int e = 0; e < 3; ++e) acc[e] = 0ull;
+  {
+    const unsigned long long a_n = __ldcg(acc + BK_ACC_N), a_st = __ldcg(acc + BK_ACC_SST), a_sr = __ldcg(acc + BK_ACC_SR);
+    unsigned long long* prev = sh.acc_prev[q];
+    sl.n = (int32_t)(a_n - prev[BK_ACC_N]);
+    sl.sst = (int64_t)(a_st - prev[BK_ACC_SST]);
+    sl.sr = (int64_t)(a_sr - prev[BK_ACC_SR]);
+    prev[BK_ACC_N] = a_n; prev[BK_ACC_SST] = a_st; prev[BK_ACC_SR] = a_sr;
+  }
   DNode parent = S.node(jb.node);
   const bk_stats sp = node_stats(parent);
   bk_stats sr = bk_stats_sub(sp, sl);
@@ -656,8 +696,6 @@ __device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* h
     sh.jobs[ji] = lj;
   }
   S.h->row = jb.dst_row;
-  atomicAdd(&hot->c_grow, 1);
-  if (jb.src_row == BK_ROW_VIRTUAL) atomicAdd(&hot->c_grow_root, 1);
   bk_trace_rec* rec = trace_at(P, c, rbase + q - 1);
   if (rec) { rec->var = jb.var; rec->split = split; rec->n_left = sl.n; rec->n_right = sr.n; rec->val_left = vl; rec->val_right = vr; }
 }
@@ -671,8 +709,9 @@ __device__ __forceinline__ void finalize_ll_own(const Params& P, int c, CtlShare
   const Job jb = sh.jobs[ji];
   const PRef S = pref(P, c, buf, q);
   unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
-  const long long ll_l = (long long)__ldcg(acc + BK_ACC_LLL), ll_r = (long long)__ldcg(acc + BK_ACC_LLR);
-  acc[BK_ACC_LLL] = 0ull; acc[BK_ACC_LLR] = 0ull;
+  const unsigned long long a_l = __ldcg(acc + BK_ACC_LLL), a_r = __ldcg(acc + BK_ACC_LLR);
+  const long long ll_l = (long long)(a_l - sh.acc_prev[q][BK_ACC_LLL]), ll_r = (long long)(a_r - sh.acc_prev[q][BK_ACC_LLR]);
+  sh.acc_prev[q][BK_ACC_LLL] = a_l; sh.acc_prev[q][BK_ACC_LLR] = a_r;
   const long long ll_parent = S.node(jb.node).sr;
   S.node(jb.left_id).sr = ll_l;
   S.node(jb.left_id + 1).sr = ll_r;
@@ -735,9 +774,11 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
   unsigned bg = 0u;
   if (w >= 0 && w < 4) {   // the particle warps (converged: every lane of warps 1..4 gets here)
     bg = __ballot_sync(0xffffffffu, kind == 1);
-    if (lane == 0) sh.warp_grow[w] = __popc(bg);
+    const unsigned bv = __ballot_sync(0xffffffffu, kind == 1 && row == BK_ROW_VIRTUAL);
+    if (lane == 0) { sh.warp_grow[w] = __popc(bg); sh.warp_grow_root[w] = __popc(bv); }
   }
   CTRL_SYNC();
+  CTS(19, 0);
   TSUB(4);
   // ---- jobs (particle threads) beside the k-th member selections (every warp but the scalar warp 0)
   int tot_g = 0;
@@ -769,6 +810,7 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
       }
     }
   }
+  CTS(20, 0);
   if (threadIdx.x >= 32) {   // split values: warps 1.. take growing slots from the shared cursor
     for (;;) {
       int sl = 0;
@@ -783,11 +825,14 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
         int err = 0;
         sv = select_split(P, c, sh.s_row[sl], sh.s_j[sl], sh.s_k[sl], sh.s_v[sl], &err);
         if (lane == 0 && err) atomicOr(&sh.err_bits, err);
+        CTN(29);
       }
       if (lane == 0) sh.s_split[sl] = sv;
     }
   }
+  CTS(21, 0);
   CTRL_SYNC();
+  CTS(22, 0);
   TSUB(5);
   // ---- the list goes to global memory with the split values patched in (48-byte descriptors, 16-byte pieces)
   tot_g = sh.warp_grow[0] + sh.warp_grow[1] + sh.warp_grow[2] + sh.warp_grow[3];
@@ -797,8 +842,20 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
     if (i % 3 == 1 && i / 3 < tot_g) piece.z = __float_as_uint(sh.s_split[sh.jobs[i / 3].slot]);
     reinterpret_cast<uint4*>(ctl->jobs[0])[i] = piece;
   }
+  if (P.nb > 0 && threadIdx.x >= 32) {
+    // large N: the bucket counts of every row that gets new member counts this epoch start from zero (the workers add)
+    const int wj = (int)(threadIdx.x >> 5) - 1, nw = (BK_CTRL_THREADS >> 5) - 1;
+    for (int ji = wj; ji < nj; ji += nw) {
+      const Job& jb = sh.jobs[ji];
+      if (jb.next_node < 0) continue;
+      unsigned* cz = P.coarse + ((size_t)c * P.R + (jb.kind == BK_JOB_PARTITION ? jb.dst_row : jb.src_row)) * P.nb_stride;
+      for (int i = lane; i < P.nb_stride; i += 32) cz[i] = 0u;
+    }
+  }
   if (threadIdx.x == 0) {
     hot->n_jobs = nj; hot->n_grow = tot_g;
+    hot->c_grow += tot_g;   // (a partition job always grows its particle)
+    hot->c_grow_root += sh.warp_grow_root[0] + sh.warp_grow_root[1] + sh.warp_grow_root[2] + sh.warp_grow_root[3];
     hot->c_count_passes += sh.n_cnt_jobs;
     if (sh.err_bits) hot->c_err |= sh.err_bits;
   }
@@ -902,12 +959,12 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
   CTRL_SYNC();
 }
 
-__device__ void control_step(const Params& P, int c, int phase, int tune, const float* sigma_in, ChainHot* hot, CtlShared& sh) {
+__device__ void control_step(const Params& P, int c, int phase, int tune, const StepArgs& A, ChainHot* hot, CtlShared& sh) {
   const int first_phase = phase == 0;
   ChainCtl* ctl = P.ctl + c;
   if (first_phase) {
     if (threadIdx.x == 0) {
-      hot->stage = BK_ST_START; hot->stage_next = BK_ST_START; hot->tune = tune; hot->sigma = sigma_in[c];
+      hot->stage = BK_ST_START; hot->stage_next = BK_ST_START; hot->tune = tune; hot->sigma = A.sigma[c];
       hot->ll_inv2s2 = bk_normal_inv2s2(hot->sigma); hot->ll_c = bk_normal_const(hot->sigma, (double)P.N);
     }
     CTRL_SYNC();
@@ -1015,6 +1072,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     if (q >= 0 && q < 8) sh.used_rows[q] = 0u;
     if (q == 0) { sh.n_cnt_jobs = 0; sh.next_sel = 1; sh.err_bits = 0; }
     CTRL_SYNC();
+    CTS(17, 0);
     const int live = sh.live;
     int round = 0, rb = rbase, src = q;
     bool deferred = false;
@@ -1032,6 +1090,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
         const int anc = resample_own(P, c, buf, sh, 1, P.P - 1, u);
         src = is_p ? anc + 1 : 0;
         if (is_p) { bk_trace_rec* rec = trace_at(P, c, rbase + q - 1); if (rec) rec->ancestor = src; }   // (record of the round just closed)
+        CTS(18, src);
       }
       TSUB(2);
     }
@@ -1199,12 +1258,18 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       if (next_node >= 0) {
         const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(n0, next4)) + __popc(bytes_eq_msb(n1, next4)));
         const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0) cnt_c[(size_t)dst_row * P.cnt_stride] = tot;
+        if (lane == 0) {
+          cnt_c[(size_t)dst_row * P.cnt_stride] = tot;
+          if (P.nb > 0 && tot) atomicAdd(P.coarse + ((size_t)c * P.R + dst_row) * P.nb_stride + (tile / BK_COARSE_TILES), tot);
+        }
       }
     } else {  // BK_JOB_COUNT
       const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(w0, next4)) + __popc(bytes_eq_msb(w1, next4)));
       const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
-      if (lane == 0) cnt_c[(size_t)src_row * P.cnt_stride] = tot;
+      if (lane == 0) {
+        cnt_c[(size_t)src_row * P.cnt_stride] = tot;
+        if (P.nb > 0 && tot) atomicAdd(P.coarse + ((size_t)c * P.R + src_row) * P.nb_stride + (tile / BK_COARSE_TILES), tot);
+      }
     }
   }
 }
@@ -1415,7 +1480,33 @@ __device__ __forceinline__ int servers_of(int C, int c) { return C >= BK_NGROUPS
 // residual tiles through L1), the chain's groups in that CTA split the range, and each warp takes a contiguous
 // chunk.  No claim atomics.  Every serving group reports each epoch exactly once (release add), so the control CTA
 // waits for `workers x servers_of(chain)` per epoch.
-__device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
+// Cold start: while the control CTAs run their first phase, every worker thread asks the L2 for a slice of what the
+// step is going to touch (the covariates, the responses, each chain's sum of trees, the leaf-id rows of the trees of
+// this batch, the running-sd arrays while tuning).  A step then meets DRAM latency once, in parallel, instead of once
+// per first touch inside the latency-bound rounds (bench.py flushes the L2 between steps: 0.24 ms of a 0.91 ms C2 step
+// were cold misses).  When the working set is still resident the prefetches are L2 hits and cost nothing.
+__device__ __forceinline__ void prefetch_l2_range(const void* base, size_t bytes, size_t first, size_t stride) {
+  const char* b = reinterpret_cast<const char*>(base);
+  for (size_t o = first * 128; o < bytes; o += stride * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+}
+__device__ void cold_start_prefetch(const Params& P, const int tune) {
+  const size_t W = gridDim.x - P.C, first = (size_t)(blockIdx.x - P.C) * BK_CTA_THREADS + threadIdx.x, stride = W * BK_CTA_THREADS;
+  const size_t col = (size_t)P.Npad * 4;
+  if ((size_t)P.p * col <= ((size_t)48 << 20)) prefetch_l2_range(P.X, (size_t)P.p * col, first, stride);   // (larger X does not fit the L2 anyway)
+  prefetch_l2_range(P.y, (size_t)P.G * col, first, stride);
+  for (int c = 0; c < P.C; ++c) {
+    prefetch_l2_range(P.st + (size_t)c * P.Npad, col, first, stride);
+    if (tune) {
+      prefetch_l2_range(P.wf_mean + (size_t)c * P.Npad, col, first, stride);
+      prefetch_l2_range(P.wf_m2 + (size_t)c * P.Npad, col, first, stride);
+    }
+    const int lo = P.ctl[c].hot.lower, T = tune ? P.batch_tune : P.batch_post;   // (the control CTA writes `hot` back only when the step is done)
+    const int hi = lo + T < P.m ? lo + T : P.m;
+    prefetch_l2_range(P.ids_tree + ((size_t)c * P.m + lo) * P.Npad, (size_t)(hi - lo) * P.Npad, first, stride);
+  }
+}
+
+__device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const unsigned epoch_base) {
   const int tid = (int)threadIdx.x - g * BK_GROUP_THREADS, warp = tid >> 5;
   const int W = gridDim.x - P.C, w = blockIdx.x - P.C;
   const int c_first = P.C >= BK_NGROUPS ? g : g % P.C, c_step = P.C >= BK_NGROUPS ? BK_NGROUPS : P.C;
@@ -1423,7 +1514,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
   int n_mine = 0;
   for (int c = c_first; c < P.C; c += c_step) n_mine++;
   if (P.C < BK_NGROUPS) n_mine = 1;
-  if (tid < 64) { sh.fin[tid] = 0; sh.seen[tid] = 0u; }
+  if (tid < 64) { sh.fin[tid] = 0; sh.seen[tid] = epoch_base; }
   for (int i = tid; i < BK_MAX_PARTICLES * BK_LIMBS; i += BK_GROUP_THREADS) sh.acc[i] = 0u;
   GROUP_SYNC(g);
   int next = 0, n_finished = 0;
@@ -1448,7 +1539,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
           // the descriptor {epoch, cmd, jobs, units} is ONE aligned 16-byte word, stored and loaded whole: a single
           // L2 round trip tells the group that an epoch started and what it is
           const uint4 d = ld_volatile_v4(&sy->desc);
-          if (d.x == sh.seen[c]) continue;
+          if ((int)(d.x - sh.seen[c]) <= 0) continue;   // (a descriptor left by an earlier launch is older than epoch_base)
           // acquire (pairs with the control CTA's release fence); also drops stale L1 lines, which is what lets the
           // residual tiles be read through L1.  A/B (profiles/): dropping it and reading everything with ld.cg is 3.8 %
           // faster on C2 and works on this hardware, but leaves the epoch hand-over without a formal acquire — kept.
@@ -1528,7 +1619,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g) {
 }
 
 // ---- control CTA of chain c: wait for the previous epoch, run the state machine, publish the next
-__device__ bool control_loop(const Params& P, int c, int tune, const float* sigma_in, int max_phases, CtlShared& sh) {
+__device__ bool control_loop(const Params& P, int c, int tune, const StepArgs& A, int max_phases, CtlShared& sh) {
   __shared__ int s_abort, s_fin;
   __shared__ ChainHot s_hot;
   ChainCtl* ctl = P.ctl + c;
@@ -1538,12 +1629,16 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
   // read-only tables of the round path: the control CTA's L1 is dropped by every acquire fence, so a global table
   // costs an L2 round trip per phase
   if (threadIdx.x < 64) sh.p_leaf[threadIdx.x] = P.p_leaf[threadIdx.x];
+  for (int i = threadIdx.x; i < P.P * BK_ACC_STRIDE; i += BK_CTRL_THREADS)
+    sh.acc_prev[i / BK_ACC_STRIDE][i % BK_ACC_STRIDE] = __ldcg(P.accL + (size_t)c * P.P * BK_ACC_STRIDE + i);
   for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += BK_CTRL_THREADS) sh.rules[v] = (signed char)P.rules[v];
 #ifdef BK_PROFILE_CTRL
   if (threadIdx.x < 32) s_cdbg[threadIdx.x] = 0ull;
 #endif
   CTRL_SYNC();
-  unsigned issued = 0, epoch = 0;
+  // epoch ids and the done counter run on across launches (no per-launch memset of the sync lines): this launch's epochs are
+  // A.epoch_base + 1, + 2, ...; the workers' share of an epoch is counted from the value `done` had when the launch began
+  unsigned issued = ld_relaxed_u32(&sy->done), epoch = A.epoch_base;
   const int n_workers = (gridDim.x - P.C) * servers_of(P.C, c);   // serving groups: each reports every epoch once
   const int sweep_tiles = (P.Npad + BK_COMMIT_TILE - 1) / BK_COMMIT_TILE;
   unsigned long long t_wait = 0, t_ctrl = 0, t_pub = 0, t_begin = 0, t_wait_sweep = 0;
@@ -1556,7 +1651,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       int ab = 0;
       long long t0 = clock64();
       unsigned spins = 0;
-      while (ld_relaxed_u32(&sy->done) < issued) {
+      while ((int)(ld_relaxed_u32(&sy->done) - issued) < 0) {
         if ((++spins & 63u) == 0) {
           if (ld_volatile_i32(P.abort_flag)) { ab = 1; break; }
           if (clock64() - t0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); ab = 1; break; }
@@ -1569,8 +1664,10 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
     }
     CTRL_SYNC();
     if (s_abort) return false;
-    control_step(P, c, phase, tune, sigma_in, hot, sh);
+    CTS(16, 0);
+    control_step(P, c, phase, tune, A, hot, sh);
     CTRL_SYNC();
+    CTS(23, 0);
     if (threadIdx.x == 0) {
       q2 = globaltimer_ns();
       hot->stage = hot->stage_next;   // (every thread read the old stage before the barrier above)
@@ -1610,8 +1707,10 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
       }
     }
     CTRL_SYNC();
+    CTS(24, 0);
     if (s_fin) return true;
     if (hot->cmd == BK_CMD_ROUND) shadow_round(P, c, hot, sh);   // overlaps the epoch just published
+    CTS(25, 0);
   }
   if (threadIdx.x == 0) { atomicExch(P.abort_flag, 1); }
   return false;
@@ -1619,14 +1718,17 @@ __device__ bool control_loop(const Params& P, int c, int tune, const float* sigm
 
 // ------------------------------------------------------------------ the step kernel
 __global__ void __launch_bounds__(BK_CTA_THREADS, 1)
-pgbart_step_kernel(const Params P, const int tune, const float* __restrict__ sigma_in, const int max_phases) {
+pgbart_step_kernel(const Params P, const int tune, const StepArgs A, const int max_phases) {
   if ((int)blockIdx.x < P.C) {
     __shared__ KernelShared sh;
-    if (threadIdx.x < BK_CTRL_THREADS) control_loop(P, blockIdx.x, tune, sigma_in, max_phases, sh.ctl);
+    if (threadIdx.x < BK_CTRL_THREADS) control_loop(P, blockIdx.x, tune, A, max_phases, sh.ctl);
     return;
   }
   const int g = threadIdx.x / BK_GROUP_THREADS;
-  worker_loop(P, reinterpret_cast<GroupShared*>(bk_dyn_smem)[g], g);
+#ifndef BK_NO_COLD_PREFETCH
+  cold_start_prefetch(P, tune);
+#endif
+  worker_loop(P, reinterpret_cast<GroupShared*>(bk_dyn_smem)[g], g, A.epoch_base);
 }
 
 // ------------------------------------------------------------------ init kernel
@@ -1644,6 +1746,7 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
     P.ids_tree[i] = r < (size_t)P.N ? 0 : BK_LIMBO;
   }
   for (size_t i = tid; i < (size_t)P.C * P.R * P.cnt_stride; i += nth) P.rowcnt[i] = 0u;
+  for (size_t i = tid; i < (size_t)P.C * P.R * P.nb_stride; i += nth) P.coarse[i] = 0u;
   for (size_t i = tid; i < (size_t)P.C * P.P * BK_ACC_STRIDE; i += nth) P.accL[i] = 0ull;
   for (size_t i = tid; i < (size_t)P.C * BK_ACC0_WORDS; i += nth) P.acc0[i] = 0ull;
   for (size_t i = tid; i < (size_t)P.C * P.m; i += nth) {
@@ -1666,50 +1769,6 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
 __global__ void pgbart_init_cum_kernel(const Params P) {
   int c = blockIdx.x;
   if (threadIdx.x == 0 && c < P.C) rebuild_cum_dev(P, c);
-}
-
-// ------------------------------------------------------------------ prediction kernel (row N1)
-// one thread per (draw, row); iterative weighted descent with a small explicit stack
-__global__ void pgbart_predict_kernel(const bk_node* __restrict__ forests, int n_trees, const float* __restrict__ X,
-                                      int n, int n_cols, const int32_t* __restrict__ draw_idx, int n_idx,
-                                      const uint8_t* __restrict__ excl, const int32_t* __restrict__ rules,
-                                      float* __restrict__ out) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)n_idx * n) return;
-  const int d = (int)(gid / n), i = (int)(gid % n);
-  const bk_node* f = forests + (size_t)draw_idx[d] * n_trees * BK_MAX_NODES;
-  const float* x = X + (size_t)i * n_cols;
-  double acc = 0.0;
-  for (int t = 0; t < n_trees; ++t) {
-    const bk_node* nodes = f + (size_t)t * BK_MAX_NODES;
-    // explicit post-order evaluation: value(node) = wl*value(l) + wr*value(r) only at excluded splits.
-    // Stack entries: (node, weight) — equivalent to the recursion because the map is linear.
-    int sn[48]; double sw[48]; int sp = 0;
-    sn[0] = 0; sw[0] = 1.0; sp = 1;
-    double tv = 0.0;
-    // NOTE: summation order differs from a recursive formulation only when >1 excluded split is met;
-    // the oracle uses the same stack discipline (left pushed last, popped first).
-    while (sp > 0) {
-      --sp; int k = sn[sp]; double w = sw[sp];
-      const bk_node nd = nodes[k];
-      if (nd.var < 0) { tv = BK_DFMA(w, (double)nd.value, tv); continue; }
-      const int l = nd.left, r = nd.left + 1;
-      if (excl && excl[nd.var]) {
-        double tot = (double)nodes[l].n + (double)nodes[r].n;
-        if (!(tot > 0.0) || sp + 2 > 48) continue;
-        double wl = BK_DDIV((double)nodes[l].n, tot);
-        double wr = BK_DSUB(1.0, wl);
-        sn[sp] = r; sw[sp] = BK_DMUL(w, wr); ++sp;
-        sn[sp] = l; sw[sp] = BK_DMUL(w, wl); ++sp;
-      } else {
-        float xv = x[nd.var];
-        bool left = (rules && rules[nd.var] == BK_RULE_ONEHOT) ? (xv == nd.split) : (xv <= nd.split);
-        sn[sp] = left ? l : r; sw[sp] = w; ++sp;
-      }
-    }
-    acc = BK_DADD(acc, tv);
-  }
-  out[(size_t)d * n + i] = (float)acc;
 }
 
 // ==================================================================== host side / C ABI
@@ -1743,13 +1802,25 @@ struct bk_handle_s {
   int grid;
   int max_phases;
   size_t dyn_smem;
-  float* sigma_dev;
   double* split_prior_dev;
+  char* workspace;
   int32_t* vi_pinned;
   bk_step_stats* stats_pinned;
-  float* sigma_pinned;
+  // Two steps may be in flight (bk_step_launch twice, then bk_step_wait): every per-step host buffer exists twice and
+  // slot k & 1 belongs to launch k; the *_pinned pointers above / below follow the last step waited for
+  unsigned char* out_slot[2];  // pinned block [vi | stats | abort flag] of a launch: ONE D2H copy per step
+  float* st_slot[2];           // pinned [C][n_rows] sum of trees (bk_set_host_output)
+  DNode* hist_nodes_slot[2];   // pinned [C][Tmax][255] raw nodes of the trees a post-tuning step rewrote (bk_set_history)
+  int32_t* hist_nn_slot[2];    // pinned [C][Tmax]
+  int hist_first[2], hist_count[2];
+  cudaEvent_t done_ev[2];
+  long long n_launched, n_waited;
+  int last_slot;
+  int history;                 // capture the rewritten trees of post-tuning steps
+  int host_lower;              // host mirror of the chains' `lower` (first tree of the next batch)
+  size_t out_off_dev, out_bytes, out_stats_off, out_abort_off;
+  StepArgs args;
   int32_t* abort_pinned;
-  float* st_pinned;       // [C][n_rows] host copy of the sum of trees (bk_set_host_output)
   int host_output;
   int poisoned;           // a step timed out: trees / sum of trees may be half rewritten, the handle refuses further steps
   int32_t* marker_host;
@@ -1759,9 +1830,9 @@ struct bk_handle_s {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-  size_t qr, qst, ids_tree, rows, rowcnt, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, alpha_vec, cum,
-      p_leaf, rules, vi, stats, trace, sync, abort_flag, sigma, split_prior, total;
-  int Npad, ntiles, R;
+  size_t qr, qst, ids_tree, rows, rowcnt, coarse, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, alpha_vec, cum,
+      p_leaf, rules, vi, stats, trace, sync, abort_flag, split_prior, total;
+  int Npad, ntiles, R, nb;
 };
 
 static int make_layout(const bk_settings* s, Layout* L) {
@@ -1786,6 +1857,8 @@ static int make_layout(const bk_settings* s, Layout* L) {
   CARVE(ids_tree, C * m * Npad);
   CARVE(rows, C * R * Npad);
   CARVE(rowcnt, C * R * (size_t)((L->ntiles + 3) & ~3) * 4);   // rows padded to 16 bytes for 128-bit loads
+  L->nb = L->ntiles > BK_COARSE_MIN_TILES ? (L->ntiles + BK_COARSE_TILES - 1) / BK_COARSE_TILES : 0;   // bucket counts only where the tile counts no longer fit one load per lane
+  CARVE(coarse, C * R * (size_t)((L->nb + 3) & ~3) * 4);
   CARVE(wf_mean, C * Npad * 4);
   CARVE(wf_m2, C * Npad * 4);
   CARVE(parts, C * 2 * P * sizeof(DParticle));
@@ -1798,12 +1871,11 @@ static int make_layout(const bk_settings* s, Layout* L) {
   CARVE(cum, C * p * 8);
   CARVE(p_leaf, 256 * 8);
   CARVE(rules, p * 4);
-  CARVE(vi, C * p * 4);
+  CARVE(vi, C * p * 4);                         // vi | stats | abort_flag stay adjacent: one D2H copy per step
   CARVE(stats, C * sizeof(bk_step_stats));
+  CARVE(abort_flag, 256);
   CARVE(trace, C * (size_t)(s->trace_capacity > 0 ? s->trace_capacity : 0) * sizeof(bk_trace_rec));
   CARVE(sync, C * sizeof(ChainSync));
-  CARVE(abort_flag, 256);
-  CARVE(sigma, C * 4);
   CARVE(split_prior, p * 8);
 #undef CARVE
   L->total = o;
@@ -1816,6 +1888,7 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
 extern "C" {
 
 int bk_abi_version(void) { return BK_ABI_VERSION; }
+void bk_set_error_message(const char* msg) { set_err("%s", msg); }   // (used by the prediction translation unit)
 int bk_padded_rows(int n_rows) { return n_rows < 1 ? 0 : (int)align_up((size_t)n_rows, BK_WARP_TILE); }
 const char* bk_last_error(void) { return g_err; }
 
@@ -1865,13 +1938,14 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   P.X = X_dev; P.y = y_dev; P.st = sum_trees_dev;
   P.qr = (int32_t*)(w + L.qr); P.qst = (int32_t*)(w + L.qst); P.ids_tree = (uint8_t*)(w + L.ids_tree);
   P.rows = (uint8_t*)(w + L.rows); P.rowcnt = (uint32_t*)(w + L.rowcnt);
+  P.coarse = (uint32_t*)(w + L.coarse); P.nb = L.nb; P.nb_stride = (L.nb + 3) & ~3;
   P.wf_mean = (float*)(w + L.wf_mean); P.wf_m2 = (float*)(w + L.wf_m2);
   P.parts = (DParticle*)(w + L.parts); P.forest = (DNode*)(w + L.forest); P.forest_nn = (int32_t*)(w + L.forest_nn);
   P.ctl = (ChainCtl*)(w + L.ctl); P.accL = (unsigned long long*)(w + L.accL); P.acc0 = (unsigned long long*)(w + L.acc0);
   P.alpha_vec = (double*)(w + L.alpha_vec); P.cum = (double*)(w + L.cum); P.p_leaf = (double*)(w + L.p_leaf);
   P.rules = (int32_t*)(w + L.rules); P.vi = (int32_t*)(w + L.vi); P.stats = (bk_step_stats*)(w + L.stats);
   P.trace = (bk_trace_rec*)(w + L.trace); P.sync = (ChainSync*)(w + L.sync); P.abort_flag = (int32_t*)(w + L.abort_flag);
-  h->sigma_dev = (float*)(w + L.sigma); h->split_prior_dev = (double*)(w + L.split_prior);
+  h->split_prior_dev = (double*)(w + L.split_prior);
 
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaMemcpyAsync(P.p_leaf, s->p_leaf, 256 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1884,10 +1958,19 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
     free(rules_h);
     CK(e);
   }
-  CK(cudaMallocHost(&h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t)));
-  CK(cudaMallocHost(&h->stats_pinned, (size_t)P.C * sizeof(bk_step_stats)));
-  CK(cudaMallocHost(&h->sigma_pinned, (size_t)P.C * sizeof(float)));
-  CK(cudaMallocHost(&h->abort_pinned, sizeof(int32_t)));
+  // vi, stats and the abort flag are adjacent in the workspace: one D2H copy brings all three back
+  h->out_off_dev = L.vi; h->out_stats_off = L.stats - L.vi; h->out_abort_off = L.abort_flag - L.vi;
+  h->out_bytes = h->out_abort_off + sizeof(int32_t);
+  for (int k = 0; k < 2; ++k) {
+    CK(cudaMallocHost(&h->out_slot[k], h->out_bytes));
+    memset(h->out_slot[k], 0, h->out_bytes);
+    CK(cudaEventCreateWithFlags(&h->done_ev[k], cudaEventDisableTiming));
+  }
+  h->vi_pinned = (int32_t*)h->out_slot[0];
+  h->stats_pinned = (bk_step_stats*)(h->out_slot[0] + h->out_stats_off);
+  h->abort_pinned = (int32_t*)(h->out_slot[0] + h->out_abort_off);
+  h->workspace = (char*)workspace_dev;
+  memset(&h->args, 0, sizeof(h->args));
 
   int dev = s->device, n_sm = 0, coop = 0, occ = 0;
   CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -1932,11 +2015,13 @@ void bk_destroy(bk_handle* h) {
   if (!h) return;
   DeviceGuard guard_(h->s.device);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
-  if (h->vi_pinned) cudaFreeHost(h->vi_pinned);
-  if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
-  if (h->sigma_pinned) cudaFreeHost(h->sigma_pinned);
-  if (h->abort_pinned) cudaFreeHost(h->abort_pinned);
-  if (h->st_pinned) cudaFreeHost(h->st_pinned);
+  for (int k = 0; k < 2; ++k) {
+    if (h->out_slot[k]) cudaFreeHost(h->out_slot[k]);
+    if (h->st_slot[k]) cudaFreeHost(h->st_slot[k]);
+    if (h->hist_nodes_slot[k]) cudaFreeHost(h->hist_nodes_slot[k]);
+    if (h->hist_nn_slot[k]) cudaFreeHost(h->hist_nn_slot[k]);
+    if (h->done_ev[k]) cudaEventDestroy(h->done_ev[k]);
+  }
   if (h->P.marker) cudaFree(h->P.marker);
   free(h->marker_host);
   delete h;
@@ -1945,49 +2030,112 @@ void bk_destroy(bk_handle* h) {
 int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
   if (h->poisoned) { set_err("an earlier step timed out inside the kernel; the sampler state is undefined: create a new handle"); return BK_ERR_STATE; }
+  if (h->n_launched - h->n_waited >= 2) { set_err("two steps are already in flight: call bk_step_wait first"); return BK_ERR_STATE; }
   ON_DEVICE(h->s.device);
   Params& P = h->P;
   for (int c = 0; c < P.C; ++c) {
     float sg = sigma_host ? sigma_host[c] : 1.0f;
     if (!(sg > 0.0f)) { set_err("sigma must be positive"); return BK_ERR_ARG; }
-    h->sigma_pinned[c] = sg;
+    h->args.sigma[c] = sg;
   }
-  CK(cudaMemcpyAsync(h->sigma_dev, h->sigma_pinned, (size_t)P.C * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(P.sync, 0, (size_t)P.C * sizeof(ChainSync), h->stream));
-  CK(cudaMemsetAsync(P.abort_flag, 0, sizeof(int32_t), h->stream));   // a timed-out step does not poison the next one
   int tune_i = tune ? 1 : 0;
-  const float* sig = h->sigma_dev;
   int maxp = h->max_phases;
   {
     const char* dbg = getenv("BK_DEBUG");
     P.debug = dbg ? atoi(dbg) : 0;
   }
-  void* args[] = {(void*)&P, (void*)&tune_i, (void*)&sig, (void*)&maxp};
+  const int slot = (int)(h->n_launched & 1);
+  const int lo = h->host_lower, T = tune ? P.batch_tune : P.batch_post, hi = lo + T < P.m ? lo + T : P.m;
+  // ONE kernel and ONE small D2H copy per step: the likelihood scales travel as kernel arguments, the epoch ids and
+  // done counters of the dataflow run on across launches (no memset), the per-step outputs are adjacent
+  void* args[] = {(void*)&P, (void*)&tune_i, (void*)&h->args, (void*)&maxp};
   CK(cudaLaunchCooperativeKernel((const void*)pgbart_step_kernel, dim3(h->grid), dim3(BK_CTA_THREADS), args, h->dyn_smem, h->stream));
-  CK(cudaMemcpyAsync(h->vi_pinned, P.vi, (size_t)P.C * P.p * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(h->stats_pinned, P.stats, (size_t)P.C * sizeof(bk_step_stats), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(h->abort_pinned, P.abort_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  h->args.epoch_base += 1u << 20;   // (max_phases = 2^20 epochs per launch at most)
+  CK(cudaMemcpyAsync(h->out_slot[slot], h->workspace + h->out_off_dev, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
   if (h->host_output)   // the value handed back to PyMC: strided device rows -> dense pinned host rows, behind the kernel
-    CK(cudaMemcpy2DAsync(h->st_pinned, (size_t)P.N * sizeof(float), P.st, (size_t)P.Npad * sizeof(float), (size_t)P.N * sizeof(float),
+    CK(cudaMemcpy2DAsync(h->st_slot[slot], (size_t)P.N * sizeof(float), P.st, (size_t)P.Npad * sizeof(float), (size_t)P.N * sizeof(float),
                          (size_t)P.C, cudaMemcpyDeviceToHost, h->stream));
+  h->hist_count[slot] = 0;
+  if (h->history && !tune) {
+    // the trees this step rewrote (op.all_trees batches, pymc_bart/utils.py:117-127): two strided copies behind the
+    // kernel, no stall; bk_history_batch compacts them on the host
+    const int Tmax = P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post;
+    CK(cudaMemcpy2DAsync(h->hist_nn_slot[slot], (size_t)Tmax * sizeof(int32_t), P.forest_nn + lo, (size_t)P.m * sizeof(int32_t),
+                         (size_t)(hi - lo) * sizeof(int32_t), (size_t)P.C, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpy2DAsync(h->hist_nodes_slot[slot], (size_t)Tmax * BK_MAX_NODES * sizeof(DNode), P.forest + (size_t)lo * BK_MAX_NODES,
+                         (size_t)P.m * BK_MAX_NODES * sizeof(DNode), (size_t)(hi - lo) * BK_MAX_NODES * sizeof(DNode), (size_t)P.C,
+                         cudaMemcpyDeviceToHost, h->stream));
+    h->hist_first[slot] = lo; h->hist_count[slot] = hi - lo;
+  }
+  CK(cudaEventRecord(h->done_ev[slot], h->stream));
+  h->host_lower = hi < P.m ? hi : 0;
+  h->n_launched += 1;
   return BK_OK;
 }
 
 int bk_set_host_output(bk_handle* h, int enable) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
   ON_DEVICE(h->s.device);
-  if (enable && !h->st_pinned) CK(cudaMallocHost(&h->st_pinned, (size_t)h->P.C * h->P.N * sizeof(float)));
+  if (h->n_launched != h->n_waited) { set_err("steps in flight"); return BK_ERR_STATE; }
+  for (int k = 0; k < 2 && enable; ++k)
+    if (!h->st_slot[k]) CK(cudaMallocHost(&h->st_slot[k], (size_t)h->P.C * h->P.N * sizeof(float)));
   h->host_output = enable ? 1 : 0;
   return BK_OK;
 }
 
-const float* bk_sum_trees_host(bk_handle* h) { return (h && h->host_output) ? h->st_pinned : nullptr; }
+const float* bk_sum_trees_host(bk_handle* h) { return (h && h->host_output) ? h->st_slot[h->last_slot] : nullptr; }
+
+int bk_set_history(bk_handle* h, int enable) {
+  if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
+  ON_DEVICE(h->s.device);
+  if (h->n_launched != h->n_waited) { set_err("steps in flight"); return BK_ERR_STATE; }
+  const Params& P = h->P;
+  const size_t Tmax = (size_t)(P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post);
+  for (int k = 0; k < 2 && enable; ++k) {
+    if (!h->hist_nodes_slot[k]) CK(cudaMallocHost(&h->hist_nodes_slot[k], (size_t)P.C * Tmax * BK_MAX_NODES * sizeof(DNode)));
+    if (!h->hist_nn_slot[k]) CK(cudaMallocHost(&h->hist_nn_slot[k], (size_t)P.C * Tmax * sizeof(int32_t)));
+  }
+  h->history = enable ? 1 : 0;
+  return BK_OK;
+}
+
+int bk_history_batch(bk_handle* h, int32_t* first_tree, int32_t* n_nodes_host, bk_node* nodes_host, int64_t* total_nodes) {
+  if (!h || !first_tree || !n_nodes_host || !nodes_host || !total_nodes) { set_err("bad argument"); return BK_ERR_ARG; }
+  const Params& P = h->P;
+  const int slot = h->last_slot, T = h->hist_count[slot];
+  *first_tree = h->hist_first[slot]; *total_nodes = 0;
+  if (!h->history || T <= 0) return 0;
+  const size_t Tmax = (size_t)(P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post);
+  int64_t tot = 0;
+  for (int c = 0; c < P.C; ++c)
+    for (int t = 0; t < T; ++t) {
+      const int nn = h->hist_nn_slot[slot][(size_t)c * Tmax + t];
+      if (nn < 1 || nn > BK_MAX_NODES) { set_err("history batch holds a malformed tree"); return BK_ERR_STATE; }
+      n_nodes_host[(size_t)c * T + t] = nn;
+      const DNode* src = h->hist_nodes_slot[slot] + ((size_t)c * Tmax + t) * BK_MAX_NODES;
+      for (int k = 0; k < nn; ++k) {
+        bk_node* d = &nodes_host[tot + k];
+        d->var = src[k].var; d->split = src[k].split; d->left = src[k].left; d->value = src[k].var < 0 ? src[k].value : 0.0f;
+        d->n = src[k].n; d->depth = src[k].depth;
+      }
+      tot += nn;
+    }
+  *total_nodes = tot;
+  return T;
+}
 
 int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
+  if (h->n_waited >= h->n_launched) { set_err("no step in flight"); return BK_ERR_STATE; }
   ON_DEVICE(h->s.device);
   Params& P = h->P;
-  CK(cudaStreamSynchronize(h->stream));
+  const int slot = (int)(h->n_waited & 1);
+  CK(cudaEventSynchronize(h->done_ev[slot]));
+  h->n_waited += 1;
+  h->last_slot = slot;
+  h->vi_pinned = (int32_t*)h->out_slot[slot];
+  h->stats_pinned = (bk_step_stats*)(h->out_slot[slot] + h->out_stats_off);
+  h->abort_pinned = (int32_t*)(h->out_slot[slot] + h->out_abort_off);
   if (*h->abort_pinned) { h->poisoned = 1; set_err("a dataflow wait timed out inside the step kernel"); return BK_ERR_TIMEOUT; }
   if (vi_counts_host) memcpy(vi_counts_host, h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t));
   if (stats_host) memcpy(stats_host, h->stats_pinned, (size_t)P.C * sizeof(bk_step_stats));
@@ -2043,6 +2191,7 @@ int32_t* bk_debug_markers(bk_handle* h, int* count) {
 
 int bk_read_trace(bk_handle* h, int chain, bk_trace_rec* out_host, int capacity) {
   if (!h || chain < 0 || chain >= h->P.C || !out_host) { set_err("bad argument"); return BK_ERR_ARG; }
+  if (h->n_launched != h->n_waited) { set_err("bk_read_trace: a step is in flight (the trace is the last step's)"); return BK_ERR_STATE; }
   ON_DEVICE(h->s.device);
   int n = h->stats_pinned[chain].trace_len;
   if (n > h->P.trace_cap) n = h->P.trace_cap;
@@ -2059,6 +2208,7 @@ int bk_export_trees(bk_handle* h, int chain, int first, int count, bk_node* node
   }
   if (count == 0) return BK_OK;
   ON_DEVICE(h->s.device);
+  CK(cudaStreamSynchronize(h->stream));   // (steps still in flight settle first)
   const Params& P = h->P;
   CK(cudaMemcpy(n_nodes_host, P.forest_nn + (size_t)chain * P.m + first, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost));
   DNode* tmp = (DNode*)malloc((size_t)BK_MAX_NODES * sizeof(DNode));
@@ -2080,6 +2230,7 @@ int bk_export_trees(bk_handle* h, int chain, int first, int count, bk_node* node
 int bk_export_forest(bk_handle* h, int chain, bk_node* nodes_host, int32_t* n_nodes_host) {
   if (!h || chain < 0 || chain >= h->P.C || !nodes_host || !n_nodes_host) { set_err("bad argument"); return BK_ERR_ARG; }
   ON_DEVICE(h->s.device);
+  CK(cudaStreamSynchronize(h->stream));
   const Params& P = h->P;
   size_t cnt = (size_t)P.m * BK_MAX_NODES;
   DNode* tmp = (DNode*)malloc(cnt * sizeof(DNode));
@@ -2103,25 +2254,10 @@ int bk_export_forest(bk_handle* h, int chain, bk_node* nodes_host, int32_t* n_no
 int bk_export_leaf_ids(bk_handle* h, int chain, uint8_t* ids_host) {
   if (!h || chain < 0 || chain >= h->P.C || !ids_host) { set_err("bad argument"); return BK_ERR_ARG; }
   ON_DEVICE(h->s.device);
+  CK(cudaStreamSynchronize(h->stream));
   const Params& P = h->P;
   CK(cudaMemcpy2D(ids_host, (size_t)P.N, P.ids_tree + (size_t)chain * P.m * P.Npad, (size_t)P.Npad, (size_t)P.N, (size_t)P.m,
                   cudaMemcpyDeviceToHost));
-  return BK_OK;
-}
-
-int bk_predict(int device, void* stream, const bk_node* forests_dev, const int32_t* n_nodes_dev, int n_trees, const float* X_dev,
-               int n, int n_cols, const int32_t* draw_idx_dev, int n_idx, const uint8_t* excluded_mask_dev,
-               const int32_t* split_rules_dev, float* out_dev) {
-  (void)n_nodes_dev;
-  if (!forests_dev || !X_dev || !draw_idx_dev || !out_dev || n < 0 || n_idx < 0) { set_err("bad argument"); return BK_ERR_ARG; }
-  ON_DEVICE(device);
-  long long total = (long long)n * n_idx;
-  if (total == 0) return BK_OK;
-  int threads = 256;
-  long long blocks = (total + threads - 1) / threads;
-  pgbart_predict_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(forests_dev, n_trees, X_dev, n, n_cols, draw_idx_dev,
-                                                                               n_idx, excluded_mask_dev, split_rules_dev, out_dev);
-  CK(cudaGetLastError());
   return BK_OK;
 }
 

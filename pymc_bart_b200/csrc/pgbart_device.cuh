@@ -14,6 +14,8 @@
 #define BK_MAX_PARTICLES 128
 #define BK_WARP_TILE 256           // rows per warp pass: 32 lanes x 8 rows
 #define BK_ROWS_PER_LANE 8
+#define BK_COARSE_TILES 32          // tiles per bucket of the coarse member counts (k-th member search at large N)
+#define BK_COARSE_MIN_TILES 512    // more tiles than this: the per-tile counts no longer fit 16 per lane, use buckets
 #ifndef BK_CTA_THREADS
 #define BK_CTA_THREADS 1024
 #endif
@@ -181,6 +183,8 @@ struct Params {
   uint8_t* ids_tree;   // [C][m][Npad]
   uint8_t* rows;       // [C][R][Npad]
   uint32_t* rowcnt;    // [C][R][cnt_stride]
+  uint32_t* coarse;    // [C][R][nb_stride]: members of the row's counted node per bucket of BK_COARSE_TILES tiles (nb > 0 only)
+  int32_t nb, nb_stride;
   float* wf_mean;      // [C][Npad]
   float* wf_m2;        // [C][Npad]
   DParticle* parts;    // [C][2][P]

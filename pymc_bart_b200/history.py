@@ -66,7 +66,7 @@ class ChainHistory:
         return self.ver_nn[self.ver_tbl].sum(axis=1) if self.ver_tbl.size else np.zeros(0, np.int64)
 
     def dense_forests(self) -> np.ndarray:
-        """[n_draws*G][m][255] dense nodes (test helper for the oracle's dense predictor; O(draws*m*255) memory)."""
+        """[n_draws*G][m][255] dense nodes (a test helper: the CPU checker predicts from dense forests; O(draws*m*255) memory)."""
         off = np.concatenate([[0], np.cumsum(self.ver_nn)])
         out = np.zeros((self.ver_tbl.shape[0], self.m, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
         for f in range(self.ver_tbl.shape[0]):
@@ -125,19 +125,28 @@ class DeviceForests:
             raise ValueError("X must be two-dimensional")
         return torch.from_numpy(Xh).to(self.device)
 
-    def predict(self, X, draw_indices, masks=None):
+    def predict(self, X, draw_indices, masks=None, per_mask=False):
         """Sum of trees of the forests of the global draws ``draw_indices`` at the rows of X.
 
-        masks: None or uint8 ``[n_masks][p]`` (1 = excluded variable).  Returns a device tensor
-        ``[n_masks or 1][len(draw_indices)][G][n]`` float32."""
+        masks: None or uint8 ``[n_masks][p]`` (1 = excluded variable); per_mask: ``draw_indices`` is ``[n_masks][S]``,
+        one set of draws per mask.  Returns a device tensor ``[n_masks or 1][S][G][n]`` float32."""
         torch = self.torch
         Xd = self.upload(X)
         n, p = int(Xd.shape[0]), int(Xd.shape[1])
-        di = np.asarray(draw_indices, dtype=np.int64).reshape(-1)
+        n_masks = 0 if masks is None else int(np.asarray(masks).shape[0])
+        di = np.asarray(draw_indices, dtype=np.int64)
+        if per_mask:
+            if di.ndim != 2 or di.shape[0] != n_masks:
+                raise ValueError("per_mask needs draw indices of shape [n_masks][S]")
+        else:
+            di = di.reshape(1, -1)
         if di.size and (di.min() < 0 or di.max() >= self.n_draws):
             raise IndexError("draw index out of range")
-        sel = (di[:, None] * self.G + np.arange(self.G)[None, :]).reshape(-1).astype(np.int32)
-        n_masks = 0 if masks is None else int(np.asarray(masks).shape[0])
+        S = di.shape[1]
+        # forest rows: (draw, group) -> draw * G + group, per mask when the draws differ per mask
+        sel2 = (di[:, :, None] * self.G + np.arange(self.G)[None, None, :]).reshape(di.shape[0], S * self.G).astype(np.int32)
+        sel = sel2.reshape(-1)
+        n_sel = S * self.G
         with torch.cuda.device(self.device):
             sel_dev = torch.from_numpy(sel).to(self.device)
             masks_dev = None
@@ -148,22 +157,19 @@ class DeviceForests:
                 masks_dev = torch.from_numpy(mk).to(self.device)
             self.err_dev.zero_()
             stream = torch.cuda.current_stream(self.device)
-            outs = []
-            for s0 in range(0, sel.size, 32768):   # (grid limit: 65535 forests per launch)
-                s1 = min(sel.size, s0 + 32768)
-                out_s = torch.empty((max(n_masks, 1), s1 - s0, n), dtype=torch.float32, device=self.device)
+            if n_sel > 65535:
+                raise ValueError("at most 65535 (draw, output) forests per prediction call")
+            out = torch.empty((max(n_masks, 1), n_sel, n), dtype=torch.float32, device=self.device)
+            if n_sel and n:
                 rc = self.lib.bk_predict_history(
                     self.device.index, C.c_void_p(stream.cuda_stream), self.nodes_dev.data_ptr(), self.ver_off_dev.data_ptr(),
                     self.ver_tbl_dev.data_ptr(), self.m, self.max_forest_nodes, Xd.data_ptr(), n, p,
-                    sel_dev.data_ptr() + 4 * s0, s1 - s0, None if masks_dev is None else masks_dev.data_ptr(), n_masks,
-                    None if self.rules_dev is None else self.rules_dev.data_ptr(), out_s.data_ptr(), self.err_dev.data_ptr())
+                    sel_dev.data_ptr(), n_sel, int(bool(per_mask)), None if masks_dev is None else masks_dev.data_ptr(), n_masks,
+                    None if self.rules_dev is None else self.rules_dev.data_ptr(), out.data_ptr(), self.err_dev.data_ptr())
                 _cabi.check(rc, "bk_predict_history")
-                outs.append(out_s)
-            out = outs[0] if len(outs) == 1 else (torch.cat(outs, dim=1) if outs else
-                                                  torch.empty((max(n_masks, 1), 0, n), dtype=torch.float32, device=self.device))
             if int(self.err_dev.item()) != 0:
                 raise RuntimeError("posterior prediction: device-side consistency flag set (malformed forest history)")
-        return out.reshape(max(n_masks, 1), di.size, self.G, n)
+        return out.reshape(max(n_masks, 1), S, self.G, n)
 
     def pearson_r2(self, a, b):
         """Squared Pearson correlation per (subset, sample): a ``[S][len]``, b ``[K][S][len]`` device tensors

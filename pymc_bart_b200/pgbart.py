@@ -2,15 +2,22 @@
 constructed as ``PGBART([rv], num_particles=...)`` at tests/test_bart.py:231-232 and
 driven by ``pm.sample`` one ``step(point)`` per draw).
 
-State lives on the GPU (pymc_bart_b200.core.DeviceSampler); this class keeps the
-step protocol: ``astep`` returns the new value of the BART variable (the sum of
-trees) and the per-draw stats ``{"variable_inclusion": <base64 varint>, "tune": bool}``
-(pymc_bart/utils.py:1387-1398, consumers :778-790), ``stop_tuning()`` ends
-adaptation, and after tuning every step's rewritten trees are appended to the
-op's history so that ``op.all_trees`` ends up with ONE ``(baseline_forest,
-batches)`` entry per chain (pymc_bart/utils.py:117,124-127) and ``op.n_outputs`` is set
-(utils.py:125).  Extension: ``chains=C`` batches C independent chains in one
-launch (the reference runs one step object per chain/process).
+State lives on the GPU (pymc_bart_b200.core.DeviceSampler); this class keeps the step protocol:
+
+* ``astep`` returns the new value of the BART variable (the sum of trees) and the per-draw stats
+  ``{"variable_inclusion": <base64 varint>, "tune": bool}`` (pymc_bart/utils.py:1387-1398, consumers :778-790);
+* ``stop_tuning()`` ends adaptation.  From the first post-tuning draw on, the chain has ONE entry
+  ``(baseline_forest, batches)`` in ``op.all_trees`` (pymc_bart/utils.py:117,124-127) and every draw appends the trees it
+  rewrote to that entry's ``batches`` — a nested ``Manager().list()`` proxy when ``op.all_trees`` is one
+  (pymc_bart/bart.py:133-146), so a worker process ships ~T trees per draw and the parent can predict at any time;
+  ``op.n_outputs`` is set on the op class (utils.py:125);
+* the object pickles WITHOUT device state (PyMC pickles the step into one worker process per chain when
+  ``cores > 1``): the CUDA context, the device buffers and the native handle are created on first use in whichever
+  process runs the chain, on ``device = chain % n_gpus`` unless a device is given;
+* when ``tune`` goes back to True after post-tuning draws (PyMC re-using one step object for the next chain,
+  ``cores=1``), the sampler starts a fresh chain with the next chain index.
+
+Extension: ``chains=C`` batches C independent chains in one launch (the reference runs one step object per chain).
 """
 from __future__ import annotations
 
@@ -31,7 +38,7 @@ class PGBART:
     stats_dtypes_shapes = {"variable_inclusion": (object, []), "tune": (bool, [])}
 
     def __init__(self, vars=None, num_particles=10, batch=(0.1, 0.1), model=None, *, likelihood="normal", sigma=1.0,
-                 chains=1, chain_base=0, seed=0, device=0, depth_offset=0, store_history=True, trace_capacity=0,
+                 chains=1, chain_base=0, seed=0, device=None, depth_offset=0, store_history=True, trace_capacity=0,
                  sigma_name=None, sigma_transform=None, **kwargs):
         if vars is None or len(vars) != 1:
             raise ValueError("PGBART takes exactly one BART variable: PGBART([rv], num_particles=...)")
@@ -60,27 +67,67 @@ class PGBART:
         self.num_particles = int(num_particles)
         self.batch = tuple(batch)
         self.chains = int(chains)
+        self.chain_base = int(chain_base)
+        self.seed = seed
+        self.device = device
         self.tune = True
         self.sigma = sigma
         self.sigma_name = sigma_name
         self.sigma_transform = sigma_transform   # e.g. np.exp when sigma_name is the log-transformed value variable
         self.store_history = bool(store_history)
-        self.settings = make_settings(
-            op.X, Yarr, m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
-            num_particles=num_particles, batch=batch, n_chains=chains, seed=seed, chain_base=chain_base,
-            likelihood=LIKELIHOODS[likelihood], depth_offset=depth_offset, device=device, trace_capacity=trace_capacity,
-            n_groups=groups,
-        )
-        self.core = DeviceSampler(self.settings, op.X, Yarr)
-        self.core.enable_host_output(True)   # astep returns a host array every draw (the trace stores it)
-        self.n_rows, self.n_cols, self.m = self.core.N, self.core.p, self.core.m
-        self._lower = 0
-        self._baseline = None   # per chain: (nodes [m,255], n_nodes [m])
-        self._batches = [[] for _ in range(self.chains * self.groups)]
-        self._published = False
+        self._Y = Yarr
+        self._settings_kw = dict(
+            m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
+            num_particles=num_particles, batch=batch, n_chains=chains, seed=seed, likelihood=LIKELIHOODS[likelihood],
+            depth_offset=depth_offset, trace_capacity=trace_capacity, n_groups=groups)
+        self.settings = make_settings(op.X, Yarr, chain_base=self.chain_base, device=0 if device is None else device,
+                                      **self._settings_kw)
+        self.n_rows, self.n_cols, self.m = self.settings.n_rows, self.settings.n_cols, self.settings.n_trees
+        self.core = None                # device state: created lazily, never pickled
+        self._reset_chain_state()
         self.last_stats = None
+        self.history_bytes_per_step = 0
         # read back through the CLASS by BARTRV.rng_fn -> _get_posterior_sampler(cls) (bart.py:65, utils.py:125)
         (op if isinstance(op, type) else type(op)).n_outputs = groups
+
+    # ---- device state ---------------------------------------------------------
+    def _reset_chain_state(self):
+        self._lower = 0
+        self._post_draws = 0
+        self._batches = None        # per chain: the `batches` list published in op.all_trees
+
+    def _pick_device(self):
+        if self.device is not None:
+            return int(self.device)
+        import torch
+
+        n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+        return (self.chain_base // max(1, self.chains)) % n if n else 0
+
+    def _ensure_core(self):
+        if self.core is None:
+            dev = self._pick_device()
+            self.settings = make_settings(self.op.X, self._Y, chain_base=self.chain_base, device=dev, **self._settings_kw)
+            self.core = DeviceSampler(self.settings, self.op.X, self._Y)
+            self.core.enable_host_output(True)   # astep returns a host array every draw (the trace stores it)
+            if self.store_history:
+                self.core.enable_history(True)
+                self.history_bytes_per_step = getattr(self.core, "history_bytes_per_step", 0)
+        return self.core
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["core"] = None            # no CUDA context / native handle crosses a process boundary
+        state["_batches"] = None
+        state["last_stats"] = None
+        return state
+
+    def next_chain(self):
+        """Start a fresh chain on this step object (PyMC with cores=1 runs the chains one after the other)."""
+        self.close()
+        self.chain_base += self.chains
+        self._reset_chain_state()
+        self.tune = True
 
     # ---- step-method protocol -------------------------------------------------
     @staticmethod
@@ -91,22 +138,44 @@ class PGBART:
     def stop_tuning(self):
         self.tune = False
 
+    def _new_batches(self):
+        """A list of the same kind as op.all_trees: a nested Manager proxy when the history crosses processes."""
+        from .bart import sibling_list
+
+        return sibling_list(self.op.all_trees)
+
+    def _chain_slice(self, per_vc, c):
+        """(chain c's output groups) of a per-(chain, group) list of (nodes, n_nodes) -> one (nodes, n_nodes [G*m])."""
+        parts = per_vc[c * self.groups:(c + 1) * self.groups]
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
     def astep(self, _q=None):
         tune = bool(self.tune)
+        if tune and self._post_draws > 0:     # tuning again after posterior draws: the next chain starts
+            self.next_chain()
+        core = self._ensure_core()
         T = self.settings.batch_tune if tune else self.settings.batch_post
         lo = self._lower
         hi = min(lo + T, self.m)
-        nvc = self.chains * self.groups          # "virtual chains": chain-major, group-minor
-        if not tune and self.store_history and self._baseline is None:
-            self._baseline = [self.core.forest(c) for c in range(nvc)]
-        vi, stats = self.core.step(tune, self.sigma)
+        if not tune and self.store_history and self._batches is None:
+            # first posterior draw: publish the chain's entry (baseline = the forest tuning ended with); every
+            # later draw appends its rewritten trees to the entry's `batches`
+            base = core.baseline()
+            self._batches = [self._new_batches() for _ in range(self.chains)]
+            for c in range(self.chains):
+                self.op.all_trees.append((self._chain_slice(base, c), self._batches[c]))
+        vi, stats = core.step(tune, self.sigma)
         self.last_stats = stats
         self._lower = hi if hi < self.m else 0
-        value = self.core.sum_trees_host()
-        if not tune and self.store_history:
-            for c in range(nvc):
-                nodes, nn = self.core.trees(c, lo, hi - lo)
-                self._batches[c].append((lo, nodes, nn))
+        value = core.sum_trees_host()
+        if not tune:
+            self._post_draws += 1
+            if self.store_history:
+                first, nn, nodes = core.history_batch()
+                off = np.concatenate([[0], np.cumsum(nn.sum(axis=1))])
+                G = self.groups
+                for c in range(self.chains):
+                    self._batches[c].append((first, nn[c * G:(c + 1) * G].copy(), nodes[off[c * G]: off[(c + 1) * G]].copy()))
         vic = vi.reshape(self.chains, self.groups, -1).sum(axis=1)       # one inclusion vector per BART variable
         out_stats = [{"variable_inclusion": _encode_vi(vic[c].tolist()), "tune": tune} for c in range(self.chains)]
         value = value.reshape(self.chains, self.groups, -1)
@@ -129,19 +198,11 @@ class PGBART:
         new_point[self.vars[0].name] = value
         return new_point, stats
 
-    # ---- history (pymc_bart/utils.py:117-127) -----------------------------------
     def publish_history(self):
-        """Append one (baseline_forest, batches) entry per chain to op.all_trees."""
-        if self._published or self._baseline is None:
-            return
-        for c in range(self.chains):
-            if self.groups == 1:
-                self.op.all_trees.append((self._baseline[c], list(self._batches[c])))
-            else:   # one (baseline, batches) pair per output group inside the chain's entry
-                g0 = c * self.groups
-                self.op.all_trees.append(([self._baseline[g0 + g] for g in range(self.groups)],
-                                          [list(self._batches[g0 + g]) for g in range(self.groups)]))
-        self._published = True
+        """Kept for callers of the round-1 API: the history is published while sampling (see astep)."""
+        return None
 
     def close(self):
-        self.core.close()
+        if self.core is not None:
+            self.core.close()
+            self.core = None

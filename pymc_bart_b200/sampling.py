@@ -54,7 +54,7 @@ def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1)
             step.stop_tuning()
         if sigma_fn is not None:
             step.sigma = sigma_fn(d, step)
-        value, stats = step.astep()
+        value, stats = step.astep()      # (after tuning every draw appends its trees to the chains' op.all_trees entries)
         if d >= tune:
             v = value if chains > 1 else value[None]
             s = stats if chains > 1 else [stats[0]]
@@ -62,7 +62,6 @@ def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1)
                 post[:, d - tune] = v
             for c in range(chains):
                 vi[c][d - tune] = s[c]["variable_inclusion"]
-    step.publish_history()
     out = {"step": step, "variable_inclusion": vi, "posterior": post, "rank": rank, "world": world}
     if distributed and world > 1 and keep_draws:
         # the single collective of the run: all-gather of the posterior draws over NVLink

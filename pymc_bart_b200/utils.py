@@ -1,18 +1,19 @@
 """Posterior-prediction glue and the variable-inclusion codec.
 
-Mirrors pymc_bart/utils.py:26-130 (``_sample_posterior``, ``_MultiChainSampler``,
-``_get_posterior_sampler``) and :1368-1398 (``_decode_vi`` / ``_encode_vi``); the native
-``PosteriorSampler`` the reference gets from bartrs (pymc_bart/pymc_bart.py:2) is
-implemented here on top of the CUDA kernel behind ``bk_predict``.
+Same names and call contracts as pymc_bart/utils.py:26-130 (``_sample_posterior``, ``_MultiChainSampler``,
+``_get_posterior_sampler``) and :1368-1398 (``_decode_vi`` / ``_encode_vi``), so that ``BARTRV.rng_fn`` and the
+analytics call them unchanged; what sits behind them is different.  The reference keeps one native
+``PosteriorSampler`` per chain (bartrs, pymc_bart/pymc_bart.py:2) and routes every requested draw to its chain in a
+Python loop.  Here ALL chains of an op live in one device store of tree versions (``history.DeviceForests``): a global
+draw index addresses the version table directly, so a prediction call is one upload of X and one kernel launch.
 """
 from __future__ import annotations
 
 import base64
-import ctypes as C
 
 import numpy as np
 
-from . import _cabi
+from .history import ChainHistory, DeviceForests
 
 
 def _decode_vi(s: str, length: int) -> list[int]:
@@ -45,180 +46,125 @@ def _encode_vi(vec) -> str:
     return base64.b64encode(bytes(buf)).decode("ascii")
 
 
+def _rule_codes(split_rules):
+    if split_rules is None:
+        return None
+    from .settings import SPLIT_RULE_CODES
+
+    return np.array([SPLIT_RULE_CODES[r if (r is None or isinstance(r, str)) else type(r).__name__] for r in split_rules], dtype=np.int32)
+
+
 class PosteriorSampler:
-    """Device-resident forest history of one chain + batched prediction.
+    """One chain's forest history (the object bartrs hands the shell: pymc_bart/utils.py:60-71,91,124-127).
 
-    Same surface as the native class the reference shell calls
-    (pymc_bart/utils.py:60-71,91,124-127): ``from_history``, ``n_draws``, ``n_outputs``,
-    ``sample_posterior(X, draw_indices, excluded) -> (n_idx, n_outputs, n)``.
-    """
+    ``from_history(batches, baseline_forest, m, n_outputs)``, ``n_draws``, ``n_outputs`` and
+    ``sample_posterior(X, draw_indices, excluded) -> (n_idx, n_outputs, n)``.  The chain is described on the host
+    (``history.ChainHistory``: tree versions + a draw -> version table); a device store is built on first use, or once
+    for all chains by ``_MultiChainSampler``."""
 
-    def __init__(self, forests: np.ndarray, n_outputs: int = 1, split_rules=None, device: int = 0):
-        import torch
-
-        if not torch.cuda.is_available():
-            raise RuntimeError("PosteriorSampler needs a CUDA device (no CPU fallback)")
-        self.lib = _cabi.load()
-        self.torch = torch
-        self.device = torch.device("cuda", device)
-        forests = np.ascontiguousarray(forests, dtype=_cabi.NODE_DTYPE)
-        self._n_draws, self.m = forests.shape[0], forests.shape[1]
-        self._n_outputs = int(n_outputs)
-        self.forests_dev = torch.from_numpy(forests.view(np.uint8).reshape(-1)).to(self.device)
-        self.rules_dev = None
-        if split_rules is not None:
-            self.rules_dev = torch.from_numpy(np.ascontiguousarray(split_rules, dtype=np.int32)).to(self.device)
-
-    @staticmethod
-    def rebuild_forests(batches, baseline_forest, m) -> np.ndarray:
-        """Initial forest + per-draw deltas -> [n_draws][m][255] nodes (pure numpy)."""
-        base_nodes, _ = baseline_forest
-        cur = np.array(base_nodes, dtype=_cabi.NODE_DTYPE, copy=True)
-        if cur.shape[0] != m:
-            raise ValueError("baseline forest does not hold m trees")
-        forests = np.zeros((len(batches), m, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
-        for d, (first, nodes, _nn) in enumerate(batches):
-            cur[first:first + nodes.shape[0]] = nodes
-            forests[d] = cur
-        return forests
+    def __init__(self, history: ChainHistory, split_rules=None, device: int = 0):
+        self.history = history
+        self.split_rules = split_rules
+        self.device = device
+        self._store = None
 
     @classmethod
     def from_history(cls, batches, baseline_forest, m, n_outputs, split_rules=None, device: int = 0):
-        """Rebuild per-draw forests from the initial forest plus per-draw deltas
-        (pymc_bart/utils.py:124-127; CHANGELOG.md:23 "Better tree storage").  With n_outputs > 1
-        (separate trees) `baseline_forest` and `batches` are lists with one entry per output group."""
-        if n_outputs > 1:
-            return _MultiOutputSampler([cls(cls.rebuild_forests(batches[g], baseline_forest[g], m), n_outputs=1,
-                                            split_rules=split_rules, device=device) for g in range(n_outputs)])
-        return cls(cls.rebuild_forests(batches, baseline_forest, m), n_outputs=n_outputs, split_rules=split_rules, device=device)
+        return cls(ChainHistory(batches, baseline_forest, m, n_outputs), split_rules=split_rules, device=device)
 
     @property
     def n_draws(self) -> int:
-        return int(self._n_draws)
+        return self.history.n_draws
 
     @property
     def n_outputs(self) -> int:
-        return self._n_outputs
+        return self.history.G
 
     def sample_posterior(self, X, draw_indices, excluded=None) -> np.ndarray:
-        torch = self.torch
-        X = np.ascontiguousarray(np.asarray(X, dtype=np.float32))
-        n, p = X.shape
-        di = np.ascontiguousarray(np.asarray(draw_indices, dtype=np.int32))
-        if di.size and (di.min() < 0 or di.max() >= self._n_draws):
-            raise IndexError("draw index out of range")
-        with torch.cuda.device(self.device):
-            Xd = torch.from_numpy(X).to(self.device)
-            dd = torch.from_numpy(di).to(self.device)
-            out = torch.empty((di.size, n), dtype=torch.float32, device=self.device)
-            ex_ptr = None
-            if excluded is not None and len(excluded):
-                mask = np.zeros(p, dtype=np.uint8)
-                mask[np.asarray(list(excluded), dtype=np.int64)] = 1
-                ex = torch.from_numpy(mask).to(self.device)
-                ex_ptr = ex.data_ptr()
-            stream = torch.cuda.current_stream(self.device)
-            rc = self.lib.bk_predict(self.device.index, C.c_void_p(stream.cuda_stream), self.forests_dev.data_ptr(), None, self.m,
-                                     Xd.data_ptr(), n, p, dd.data_ptr(), int(di.size), ex_ptr,
-                                     None if self.rules_dev is None else self.rules_dev.data_ptr(), out.data_ptr())
-            _cabi.check(rc, "bk_predict")
-            res = out.cpu().numpy()
-        return res.reshape(di.size, 1, n).astype(np.float64)
-
-
-class _MultiOutputSampler:
-    """k single-output samplers (separate trees) presented as one sampler with n_outputs = k."""
-
-    def __init__(self, parts):
-        self.parts = parts
-
-    @property
-    def n_draws(self):
-        return self.parts[0].n_draws
-
-    @property
-    def n_outputs(self):
-        return len(self.parts)
-
-    def sample_posterior(self, X, draw_indices, excluded=None):
-        return np.concatenate([p.sample_posterior(X, draw_indices, excluded) for p in self.parts], axis=1)
-
-
-def _sample_posterior(sampler, X, rng, size=None, excluded=None):
-    """pymc_bart/utils.py:26-71."""
-    if size is None:
-        size_iter = ()
-    elif isinstance(size, int):
-        size_iter = [size]
-    else:
-        size_iter = size
-    flat = 1
-    for s in size_iter:
-        flat *= s
-    X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
-    excl = list(excluded) if excluded is not None else None
-    first = sampler[0] if isinstance(sampler, list) else sampler
-    draw_indices = rng.integers(0, first.n_draws, size=flat).tolist()
-    if isinstance(sampler, list):
-        pred = np.concatenate([s.sample_posterior(X, draw_indices, excl) for s in sampler], axis=1)
-    else:
-        pred = sampler.sample_posterior(X, draw_indices, excl)
-    return pred.transpose((0, 2, 1)).reshape((*size_iter, -1, pred.shape[1]))
+        if self._store is None:
+            self._store = _MultiChainSampler([self])
+        return self._store.sample_posterior(X, draw_indices, excluded)
 
 
 class _MultiChainSampler:
-    """Routes each requested draw to the sampler of the chain it came from (pymc_bart/utils.py:74-107)."""
+    """All chains of an op behind one sampler (pymc_bart/utils.py:74-107): draws are numbered chain after chain.
+
+    The reference looks the chain of every draw up and loops over the chains; here the chains' histories are
+    concatenated into one device store whose forest rows are in that same global order, so the lookup disappears."""
 
     def __init__(self, chain_samplers: list):
         if not chain_samplers:
             raise ValueError("No posterior draws available yet: run pm.sample() first.")
-        self._chain_samplers = chain_samplers
-        self._offsets = np.cumsum([0] + [s.n_draws for s in chain_samplers])
+        first = chain_samplers[0]
+        self._forests = DeviceForests([s.history for s in chain_samplers], split_rules=first.split_rules, device=first.device)
+        self.n_chains = len(chain_samplers)
 
     @property
     def n_draws(self) -> int:
-        return int(self._offsets[-1])
+        return self._forests.n_draws
 
     @property
     def n_outputs(self) -> int:
-        return self._chain_samplers[0].n_outputs
+        return self._forests.G
 
-    def sample_posterior(self, X, draw_indices, excluded):
-        draw_indices = np.asarray(draw_indices)
-        chain_of_draw = np.searchsorted(self._offsets, draw_indices, side="right") - 1
-        out = None
-        for chain_idx, sampler in enumerate(self._chain_samplers):
-            mask = chain_of_draw == chain_idx
-            if not np.any(mask):
-                continue
-            local = (draw_indices[mask] - self._offsets[chain_idx]).tolist()
-            preds = sampler.sample_posterior(X, local, excluded)
-            if out is None:
-                out = np.empty((len(draw_indices), *preds.shape[1:]), dtype=preds.dtype)
-            out[mask] = preds
-        return out
+    def upload(self, X):
+        """Device copy of X for repeated calls (the importance search predicts dozens of times on the same rows)."""
+        return self._forests.upload(X)
+
+    @staticmethod
+    def _mask(excluded, p):
+        if excluded is None or len(excluded) == 0:
+            return None
+        mk = np.zeros((1, p), dtype=np.uint8)
+        mk[0, np.asarray(list(excluded), dtype=np.int64)] = 1
+        return mk
+
+    def sample_posterior(self, X, draw_indices, excluded=None) -> np.ndarray:
+        Xd = self.upload(X)
+        out = self._forests.predict(Xd, np.asarray(draw_indices), self._mask(excluded, int(Xd.shape[1])))
+        return out[0].cpu().numpy().astype(np.float64)        # (n_idx, n_outputs, n)
+
+    def predict_subsets(self, X, draws_per_subset, masks):
+        """ONE launch for K exclusion masks, each with its own draw indices: device tensor [K][S][n_outputs][n]."""
+        return self._forests.predict(self.upload(X), np.asarray(draws_per_subset), np.asarray(masks, dtype=np.uint8), per_mask=True)
+
+    def pearson_r2(self, a, b):
+        return self._forests.pearson_r2(a, b)
+
+
+def _sample_posterior(sampler, X, rng, size=None, excluded=None):
+    """Random posterior draws of the sum of trees at the rows of X (pymc_bart/utils.py:26-71): `size` draws are picked
+    with ``rng.integers(0, n_draws)``; the result has shape ``(*size, n_rows, n_outputs)`` (``(n_rows, n_outputs)``
+    for ``size=None``).  A list of samplers (several BART variables) is stacked along the output axis."""
+    dims = () if size is None else ((int(size),) if np.isscalar(size) else tuple(int(v) for v in size))
+    samplers = list(sampler) if isinstance(sampler, (list, tuple)) else [sampler]
+    picks = rng.integers(0, samplers[0].n_draws, size=int(np.prod(dims)) if dims else 1)
+    blocks = [s.sample_posterior(X, picks, None if excluded is None else list(excluded)) for s in samplers]
+    pred = blocks[0] if len(blocks) == 1 else np.concatenate(blocks, axis=1)          # (n_picks, n_outputs, n_rows)
+    return np.moveaxis(pred, 1, 2).reshape(*dims, pred.shape[2], pred.shape[1])
 
 
 _posterior_sampler_cache: dict = {}
 
 
-def _get_posterior_sampler(op) -> _MultiChainSampler:
-    """pymc_bart/utils.py:113-130."""
-    n_chains = len(op.all_trees)
-    cached = _posterior_sampler_cache.get(id(op))
-    if cached is not None and cached[0] == n_chains:
-        return cached[1]
-    from .settings import SPLIT_RULE_CODES
+def _history_signature(op):
+    """(chains, draws per chain): the history of a running sampler grows, the cached device store must follow."""
+    return tuple(len(entry[1]) for entry in op.all_trees)
 
-    rules = None
-    if getattr(op, "split_rules", None) is not None:
-        rules = np.array([SPLIT_RULE_CODES[r if (r is None or isinstance(r, str)) else type(r).__name__] for r in op.split_rules], dtype=np.int32)
-    chain_samplers = [
-        PosteriorSampler.from_history(batches, baseline_forest, op.m, op.n_outputs, split_rules=rules)
-        for baseline_forest, batches in op.all_trees
-    ]
-    sampler = _MultiChainSampler(chain_samplers)
-    _posterior_sampler_cache[id(op)] = (n_chains, sampler)
+
+def _get_posterior_sampler(op) -> _MultiChainSampler:
+    """The op's multi-chain sampler, rebuilt when chains or draws were added (pymc_bart/utils.py:110-130 caches on the
+    chain count alone because bartrs publishes a chain's history in one piece)."""
+    sig = _history_signature(op)
+    cached = _posterior_sampler_cache.get(id(op))
+    if cached is not None and cached[0] == sig and cached[2] is op:
+        return cached[1]
+    rules = _rule_codes(getattr(op, "split_rules", None))
+    chains = [PosteriorSampler.from_history(list(batches), baseline_forest, op.m, op.n_outputs, split_rules=rules,
+                                            device=getattr(op, "device", 0))
+              for baseline_forest, batches in op.all_trees]
+    sampler = _MultiChainSampler(chains)
+    _posterior_sampler_cache[id(op)] = (sig, sampler, op)
     return sampler
 
 

@@ -4,5 +4,5 @@
 set -e
 cd "$(dirname "$0")/.."
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -DBK_PROFILE_CTRL \
-  -Iinclude -Ipymc_bart_b200/csrc -shared -o pymc_bart_b200/libpgbart_b200.so pymc_bart_b200/csrc/pgbart_b200.cu 2>/dev/null
+  -Iinclude -Ipymc_bart_b200/csrc -shared -o pymc_bart_b200/libpgbart_b200.so pymc_bart_b200/csrc/pgbart_b200.cu pymc_bart_b200/csrc/pgbart_predict.cu 2>/dev/null
 python tests/gpu_profile_phases.py "$@"

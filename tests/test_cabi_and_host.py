@@ -9,7 +9,6 @@ import pytest
 
 from pymc_bart_b200 import BART, _cabi
 from pymc_bart_b200.settings import choose_qshift, depth_prior_table, make_settings
-from pymc_bart_b200.utils import PosteriorSampler
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -91,17 +90,36 @@ def test_bart_op_mirror_attributes():
     assert isinstance(mu2.owner.op.X, np.ndarray)
 
 
-def test_history_rebuild_is_baseline_plus_deltas():
+def _leaf_tree(value):
+    nd = np.zeros(1, dtype=_cabi.NODE_DTYPE)
+    nd["var"] = -1; nd["value"] = value
+    return nd
+
+
+def test_history_is_baseline_plus_deltas():
+    """ChainHistory: every tree version once, a (draw, group) -> version table; a draw costs m ints."""
+    from pymc_bart_b200.history import ChainHistory, compact_forest
+
     m = 4
-    base = np.zeros((m, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
-    base["var"] = -1
-    base["value"][:, 0] = np.arange(m)
-    b1 = np.zeros((2, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE); b1["value"][:, 0] = [10, 11]
-    b2 = np.zeros((1, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE); b2["value"][:, 0] = [30]
-    f = PosteriorSampler.rebuild_forests([(0, b1, None), (3, b2, None)], (base, None), m)
-    assert f.shape == (2, m, _cabi.BK_MAX_NODES)
-    assert f["value"][0, :, 0].tolist() == [10, 11, 2, 3]
-    assert f["value"][1, :, 0].tolist() == [10, 11, 2, 30]
+    base = (np.concatenate([_leaf_tree(t) for t in range(m)]), np.ones(m, dtype=np.int32))
+    b1 = (0, np.ones((1, 2), dtype=np.int32), np.concatenate([_leaf_tree(10), _leaf_tree(11)]))     # rewrites trees 0, 1
+    b2 = (3, np.ones((1, 1), dtype=np.int32), _leaf_tree(30))                                        # rewrites tree 3
+    h = ChainHistory([b1, b2], base, m, 1)
+    assert h.n_draws == 2 and h.ver_tbl.tolist() == [[4, 5, 2, 3], [4, 5, 2, 6]]
+    d = h.dense_forests()
+    assert d.shape == (2, m, _cabi.BK_MAX_NODES)
+    assert d["value"][0, :, 0].tolist() == [10, 11, 2, 3] and d["value"][1, :, 0].tolist() == [10, 11, 2, 30]
+    assert h.forest_sizes().tolist() == [4, 4]
+    # two output groups: group-major baseline, batches carry [G][T] counts
+    base2 = (np.concatenate([_leaf_tree(t) for t in range(2 * m)]), np.ones(2 * m, dtype=np.int32))
+    b = (1, np.ones((2, 1), dtype=np.int32), np.concatenate([_leaf_tree(100), _leaf_tree(200)]))
+    h2 = ChainHistory([b], base2, m, 2)
+    assert h2.ver_tbl.tolist() == [[0, 8, 2, 3], [4, 9, 6, 7]]
+    with pytest.raises(ValueError):
+        ChainHistory([], (base[0], np.ones(3, dtype=np.int32)), m, 1)
+    dense = np.zeros((2, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE); dense["value"][:, 0] = [7, 8]; dense["value"][1, 1] = 9
+    flat, nn = compact_forest(dense, np.array([1, 2]))
+    assert flat["value"].tolist() == [7, 8, 9] and nn.tolist() == [1, 2]
 
 
 def test_product_never_imports_the_oracle():
@@ -126,18 +144,32 @@ def test_device_sampler_refuses_to_run_without_cuda():
 class _FakeCore:
     """Stands in for core.DeviceSampler (no GPU): deterministic counters instead of a sampler, same surface."""
 
+    instances = []
+
     def __init__(self, settings, X, Y):
         G = max(1, settings.n_groups)
+        self.settings = settings
         self.N, self.p, self.m, self.G = settings.n_rows, settings.n_cols, settings.n_trees, G
         self.C = settings.n_chains * G
         self.calls = 0
         self.h2d_bytes = 0
+        self.lower = 0
+        self.closed = False
+        self.chain_base = settings.chain_base
+        _FakeCore.instances.append(self)
 
     def enable_host_output(self, enable=True):
         self.host_output = enable
 
+    def enable_history(self, enable=True):
+        self.history = enable
+
     def step(self, tune, sigma):
         self.calls += 1
+        self.last_sigma = sigma
+        T = self.settings.batch_tune if tune else self.settings.batch_post
+        self.last = (self.lower, min(self.lower + T, self.m), tune)
+        self.lower = self.last[1] if self.last[1] < self.m else 0
         vi = np.zeros((self.C, self.p), dtype=np.int32)
         if not tune:
             vi[:, 0] = np.arange(self.C) + 1          # virtual chain vc used variable 0 (vc + 1) times
@@ -146,50 +178,80 @@ class _FakeCore:
     def sum_trees_host(self):
         return np.arange(self.C * self.N, dtype=np.float32).reshape(self.C, self.N) + 1000 * self.calls
 
-    def forest(self, c):
-        nodes = np.zeros((self.m, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
-        nodes["value"][:, 0] = c
-        return nodes, np.ones(self.m, dtype=np.int32)
+    def baseline(self):
+        out = []
+        for c in range(self.C):
+            nodes = np.zeros(self.m, dtype=_cabi.NODE_DTYPE); nodes["var"] = -1; nodes["value"] = c
+            out.append((nodes, np.ones(self.m, dtype=np.int32)))
+        return out
 
-    def trees(self, c, first, count):
-        nodes = np.zeros((count, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
-        nodes["value"][:, 0] = 100 * self.calls + c
-        return nodes, np.ones(count, dtype=np.int32)
+    def history_batch(self):
+        lo, hi, tune = self.last
+        if tune:
+            return None
+        T = hi - lo
+        nodes = np.zeros(self.C * T, dtype=_cabi.NODE_DTYPE); nodes["var"] = -1
+        nodes["value"] = 100 * self.calls + np.repeat(np.arange(self.C), T)
+        return lo, np.ones((self.C, T), dtype=np.int32), nodes
 
     def close(self):
-        pass
+        self.closed = True
 
 
 def test_pgbart_step_protocol_with_a_fake_core(monkeypatch):
     """Host logic of PGBART.astep without a GPU: value shapes for (chains, output groups), one inclusion string per
-    BART variable (groups summed), round-robin tree batches in the history, one all_trees entry per chain."""
+    BART variable (groups summed), round-robin tree batches, ONE all_trees entry per chain that grows by one batch per
+    posterior draw, pickling without device state, a fresh chain when tuning starts again."""
+    import cloudpickle
+    import pickle
+
     import pymc_bart_b200.pgbart as pg
+    from pymc_bart_b200.history import ChainHistory
     from pymc_bart_b200.utils import _decode_vi
 
     monkeypatch.setattr(pg, "DeviceSampler", _FakeCore)
+    _FakeCore.instances.clear()
     rng = np.random.default_rng(0)
     X = rng.normal(size=(30, 3)); Y = rng.normal(size=(2, 30))
     mu = BART("w", X, Y, m=20, shape=(2, 30), separate_trees=True)
     step = pg.PGBART([mu], num_particles=4, chains=3, batch=(0.1, 0.25))     # 2 trees per tuning draw, 5 after
-    assert step.tune and step.core.host_output and type(mu.owner.op).n_outputs == 2
+    assert step.tune and step.core is None and type(mu.owner.op).n_outputs == 2      # no device state before the first step
     v, st = step.astep()
+    assert step.core.host_output and step.core.history
     assert v.shape == (3, 2, 30) and len(st) == 3 and st[0] == {"variable_inclusion": "AAAA", "tune": True}
     assert v[1, 1, 0] == 1000 + (1 * 2 + 1) * 30                           # chain-major, group-minor rows of the core
     v2, _ = step.astep()
     assert v[0, 0, 0] == 1000 and v2[0, 0, 0] == 2000                        # a fresh array every draw
+    op = mu.owner.op
+    assert len(op.all_trees) == 0                                            # nothing is published while tuning
     step.stop_tuning()
     for d in range(5):
         v, st = step.astep()
+        assert len(op.all_trees) == 3 and len(op.all_trees[0][1]) == d + 1   # one entry per chain (utils.py:117), one batch per draw
     assert [_decode_vi(s["variable_inclusion"], 3)[0] for s in st] == [1 + 2, 3 + 4, 5 + 6]   # groups of a chain summed
-    firsts = [b[0] for b in step._batches[0]]
-    assert firsts == [4, 9, 14, 19, 0]                                       # 2 tuning draws x 2 trees, then 5 per draw ...
-    assert [b[1].shape[0] for b in step._batches[0]] == [5, 5, 5, 1, 5]      # ... the batch that reaches m is cut there (B10)
-    step.publish_history(); step.publish_history()
-    op = mu.owner.op
-    assert len(op.all_trees) == 3                                            # one entry per chain (utils.py:117), published once
     base, batches = op.all_trees[2]
-    assert len(base) == 2 and len(batches) == 2 and len(batches[1]) == 5    # per output group inside the chain's entry
-    assert base[1][0]["value"][0, 0] == 2 * 2 + 1                            # baseline of (chain 2, group 1) = virtual chain 5
+    batches = list(batches)
+    assert [b[0] for b in batches] == [4, 9, 14, 19, 0]                      # 2 tuning draws x 2 trees, then 5 per draw ...
+    assert [b[1].shape for b in batches] == [(2, 5), (2, 5), (2, 5), (2, 1), (2, 5)]   # ... the batch that reaches m is cut there (B10)
+    assert base[1].shape == (2 * 20,) and base[0]["value"][0] == 4 and base[0]["value"][20] == 5   # (chain 2, groups 0 and 1) = virtual chains 4, 5
+    assert batches[0][2]["value"].tolist() == [304] * 5 + [305] * 5
+    h = ChainHistory(batches, base, 20, 2)                                   # the published entry is a valid history
+    assert h.n_draws == 5 and h.ver_tbl.shape == (10, 20)
+    # pickling: no device state crosses a process boundary (PyMC pickles the step into its worker processes)
+    clone = pickle.loads(cloudpickle.dumps(step))
+    assert clone.core is None and clone._batches is None and clone.chains == 3 and clone.op.m == 20
+    # PyMC re-using the step object for the next chain (cores=1): tune goes back to True
+    first_core = step.core
+    step.tune = True
+    step.astep()
+    assert first_core.closed and step.core is not first_core and step.core.chain_base == 3 and step.chain_base == 3
+    step.stop_tuning(); step.astep()
+    assert len(op.all_trees) == 6                                            # the new chains' entries follow the old ones
+    with pytest.raises(KeyError):
+        pg.PGBART([mu], sigma_name="sigma").step({"sigma_log__": 0.0})       # a scale that is not in the point must not be ignored
+    s2 = pg.PGBART([BART("z", X, Y[0], m=5)], sigma_name="sigma_log__", sigma_transform=np.exp)
+    s2.step({"sigma_log__": np.log(2.5)})
+    assert s2.core.last_sigma == pytest.approx(2.5)
     with pytest.raises(ValueError):
         pg.PGBART([mu, mu])
     with pytest.raises(TypeError):

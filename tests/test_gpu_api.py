@@ -41,16 +41,18 @@ def test_step_protocol_and_vi_dominance():
         tot += vi
     frac = tot / tot.sum()
     assert frac[0] > frac[1:].sum()
-    step.publish_history()
     op = mu.owner.op
     assert len(op.all_trees) == 1 and op.n_outputs == 1          # one (baseline, batches) entry per chain (utils.py:117)
     baseline, batches = op.all_trees[0]
-    assert len(batches) == 200 and baseline[0].shape == (10, _cabi.BK_MAX_NODES)
+    assert len(batches) == 200 and baseline[1].shape == (10,) and baseline[0].shape == (int(baseline[1].sum()),)
+    first, nn, nodes = batches[0]
+    assert first == 0 and nn.shape == (1, 1) and nodes.shape == (int(nn.sum()),) and nodes.dtype == _cabi.NODE_DTYPE
     step.close()
 
 
 def test_posterior_sampler_matches_in_sample_draws_and_oracle_predict():
     from oracle import oracle_py
+    from pymc_bart_b200.history import ChainHistory
     from pymc_bart_b200.utils import PosteriorSampler, _get_posterior_sampler, _sample_posterior
 
     X, Y, _ = friedman(400, 6, 17)
@@ -60,21 +62,32 @@ def test_posterior_sampler_matches_in_sample_draws_and_oracle_predict():
     sampler = _get_posterior_sampler(op)
     assert sampler.n_draws == 50 and sampler.n_outputs == 1
     post = out["posterior"]                       # (chains, draws, N) values the sampler itself produced
+    idx = [0, 7, 24]
+    ex = [1, 3]
+    mask = np.zeros(6, np.uint8); mask[ex] = 1
     for chain in range(2):
         baseline, batches = op.all_trees[chain]
-        forests = PosteriorSampler.rebuild_forests(batches, baseline, op.m)
-        ps = PosteriorSampler(forests)
-        idx = [0, 7, 24]
+        ps = PosteriorSampler.from_history(list(batches), baseline, op.m, 1)      # one chain on its own (utils.py:124-127)
+        assert ps.n_draws == 25 and ps.n_outputs == 1
         pred = ps.sample_posterior(X, idx, None)                       # (3, 1, N)
         assert pred.shape == (3, 1, 400)
         np.testing.assert_allclose(pred[:, 0, :], post[chain, idx, :], atol=3e-4, rtol=0)
-        ref = oracle_py.predict(forests, X.astype(np.float32), idx)
+        dense = ChainHistory(list(batches), baseline, op.m, 1).dense_forests()     # the CPU restatement predicts from dense forests
+        ref = oracle_py.predict(dense, X.astype(np.float32), idx)
         assert np.array_equal(pred[:, 0, :].astype(np.float32), ref)   # kernel vs oracle restatement, bit for bit
-        ex = [1, 3]
-        mask = np.zeros(6, np.uint8); mask[ex] = 1
         pe = ps.sample_posterior(X[:50], idx, ex)
-        re = oracle_py.predict(forests, X[:50].astype(np.float32), idx, excluded_mask=mask)
+        re = oracle_py.predict(dense, X[:50].astype(np.float32), idx, excluded_mask=mask)
         assert np.array_equal(pe[:, 0, :].astype(np.float32), re)
+        # the multi-chain store numbers the draws chain after chain: same numbers through the global index
+        glob = sampler.sample_posterior(X[:50], [25 * chain + i for i in idx], ex)
+        assert np.array_equal(glob, pe)
+    # one launch for several exclusion masks, each with its own draws (row N4)
+    masks = np.zeros((3, 6), np.uint8); masks[1, ex] = 1; masks[2, [0]] = 1
+    draws = np.array([[0, 30], [7, 49], [24, 25]])
+    multi = sampler.predict_subsets(X[:64], draws, masks).cpu().numpy()
+    for k in range(3):
+        one = sampler.sample_posterior(X[:64], draws[k], np.nonzero(masks[k])[0].tolist() or None)
+        assert np.array_equal(multi[k].astype(np.float64), one)
     # tests/test_utils.py:24-32 — prediction self-consistency and shapes
     pa = _sample_posterior(sampler, X=X, rng=np.random.default_rng(3), size=2)
     pf = _sample_posterior(sampler, X=X[:10], rng=np.random.default_rng(3))
@@ -83,6 +96,119 @@ def test_posterior_sampler_matches_in_sample_draws_and_oracle_predict():
     # rng_fn on new data after sampling (tests/test_bart.py:84-104 shapes)
     assert type(op).rng_fn(rng=np.random.default_rng(0), X=X[:3]).shape == (3,)
     out["step"].close()
+
+
+def test_variable_importance_search_on_device():
+    """Row N4 (pymc_bart/utils.py:868-1090): every level of the search is one prediction launch over all candidate
+    subsets + one fused correlation launch; the numbers equal the reference's sequential formulation (one
+    sample_posterior call per subset, pearsonr2 per sample) for the same random_seed."""
+    import pymc_bart_b200 as pmb
+    from pymc_bart_b200.importance import compute_variable_importance, generate_sequences, get_variable_inclusion
+    from pymc_bart_b200.utils import _get_posterior_sampler, _sample_posterior, get_variable_inclusion_counts
+
+    rng = np.random.default_rng(11)
+    X = rng.uniform(0, 1, (300, 5))
+    Y = 6 * X[:, 2] + 3 * X[:, 0] + rng.normal(0, 0.3, 300)
+    mu = pmb.BART("mu", X, Y, m=20)
+    out = pmb.sample(mu, tune=150, draws=60, chains=2, num_particles=10, seed=11, sigma=0.3)
+    stats = [{"variable_inclusion": s} for ch in out["variable_inclusion"] for s in ch]
+    op = mu.owner.op
+    sampler = _get_posterior_sampler(op)
+
+    def pearsonr2(A, B):            # pymc_bart/utils.py:1339-1346
+        am, bm = A.ravel() - A.mean(), B.ravel() - B.mean()
+        return (am @ bm) ** 2 / (np.sum(am ** 2) * np.sum(bm ** 2))
+
+    # --- "VI": subsets by increasing inclusion, evaluated sequentially like the reference
+    res = compute_variable_importance(stats, mu, X, method="VI", samples=12, random_seed=5)
+    r = np.random.default_rng(5)
+    p_all = _sample_posterior(sampler, X, r, size=12)
+    idxs = np.argsort(get_variable_inclusion_counts(stats, 5))
+    subsets = [list(idxs[:-i]) for i in range(1, 5)] + [None]
+    for k, sub in enumerate(subsets):
+        p_sub = _sample_posterior(sampler, X, r, size=12, excluded=sub)
+        r2 = np.array([pearsonr2(p_all[j], p_sub[j]) for j in range(12)])
+        assert res["r2_mean"][k] == pytest.approx(r2.mean(), rel=1e-5)
+        np.testing.assert_allclose(res["preds"][k], p_sub.squeeze(), rtol=0, atol=0)
+    assert res["indices"].tolist() == idxs[::-1].tolist() and res["preds_all"].shape == (12, 300)
+    assert set(res["indices"][:2].tolist()) == {0, 2}                        # the two informative columns rank first
+    assert res["r2_mean"][-1] > 0.9 and res["r2_mean"][0] < res["r2_mean"][-1]   # the full set reproduces itself
+    assert res["labels"][0] == str(res["indices"][0]) and res["labels"][1].startswith("+ ")
+    # --- "backward": one launch per level, first-maximum choice
+    resb = compute_variable_importance(None, mu, X, method="backward", samples=8, random_seed=6)
+    r = np.random.default_rng(6)
+    p_all = _sample_posterior(sampler, X, r, size=8)
+    least = []
+    for i_var in range(5):
+        best, best_mean = None, -np.inf
+        for sub in generate_sequences(5, i_var, least):
+            p_sub = _sample_posterior(sampler, X, r, size=8, excluded=sub)
+            mean = np.mean([pearsonr2(p_all[j], p_sub[j]) for j in range(8)])
+            if mean > best_mean:
+                best, best_mean = sub, mean
+        assert resb["r2_mean"][::-1][i_var] == pytest.approx(best_mean, rel=1e-5)
+        least += [v for v in best if v not in least]
+    assert resb["indices"].tolist() == least[::-1] and set(resb["indices"][:2].tolist()) == {0, 2}
+    resbv = compute_variable_importance(stats, mu, X, method="backward_VI", fixed=2, samples=6, random_seed=7)
+    assert sorted(resbv["indices"].tolist()) == [0, 1, 2, 3, 4] and resbv["r2_mean"].shape == (5,)
+    vi_norm, labels = get_variable_inclusion(stats, X)
+    assert vi_norm.sum() == pytest.approx(1.0) and labels[0] in ("0", "2")
+    with pytest.raises(ValueError):
+        compute_variable_importance(stats, mu, X, method="forward")
+    out["step"].close()
+
+
+def _spawned_chain(payload, chain, q):
+    """Worker process of test_history_crosses_processes: unpickles the step (no device state inside), runs one chain."""
+    import pickle
+
+    step = pickle.loads(payload)
+    step.chain_base = chain
+    vals = []
+    for d in range(14):
+        if d == 8:
+            step.stop_tuning()
+        v, _ = step.astep()
+        if d >= 8:
+            vals.append(v.copy())
+    q.put((chain, np.stack(vals), step.core.device.index))
+    step.close()
+
+
+def test_history_crosses_processes():
+    """pymc_bart/bart.py:133-146: op.all_trees is a Manager proxy because PyMC runs every chain in its own process with
+    a pickled copy of the step.  Two spawned workers sample one chain each; the parent predicts from what they
+    published and gets the values the workers saw."""
+    import multiprocessing as mp
+
+    import cloudpickle
+
+    import pymc_bart_b200 as pmb
+    from pymc_bart_b200.utils import _get_posterior_sampler
+
+    X, Y, _ = friedman(300, 4, 21)
+    mu = pmb.BART("mu", X, Y, m=8)
+    step = pmb.PGBART([mu], num_particles=6, seed=21)
+    payload = cloudpickle.dumps(step)              # what PyMC ships to a worker; the parent never created a device sampler
+    assert step.core is None
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_spawned_chain, args=(payload, c, q)) for c in range(2)]
+    [p.start() for p in procs]
+    got = dict()
+    for _ in range(2):
+        chain, vals, dev = q.get(timeout=300)
+        got[chain] = vals
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    op = mu.owner.op
+    assert len(op.all_trees) == 2 and sorted(len(b) for _, b in op.all_trees) == [6, 6]
+    sampler = _get_posterior_sampler(op)
+    assert sampler.n_draws == 12
+    pred = sampler.sample_posterior(X, list(range(12)), None)[:, 0, :]      # entries are in arrival order: match by value
+    for chain in range(2):
+        hit = [k for k in range(2) if np.allclose(pred[6 * k: 6 * k + 6], got[chain], atol=3e-4, rtol=0)]
+        assert len(hit) == 1, chain
 
 
 def test_fit_quality_friedman():
@@ -108,6 +234,12 @@ def test_unsupported_options_raise_not_fallback():
         pmb.PGBART([pmb.BART("b", Xn, Y, m=3)])
     with pytest.raises(NotImplementedError):
         pmb.PGBART([pmb.BART("c", X, Y, m=3)], likelihood="poisson")
+    with pytest.raises(ValueError, match="No posterior draws"):
+        from pymc_bart_b200.utils import _get_posterior_sampler
+
+        op = pmb.BART("d", X, Y, m=3).owner.op
+        type(op).n_outputs = 1
+        _get_posterior_sampler(op)
 
 
 def test_multi_output_api_shapes_and_prediction():

@@ -1,7 +1,7 @@
 """Oracle parity on the code paths only BASELINE.json's large configs reach ("What's weak" 1-2):
 
-* `select_split`'s two-level branch (more than 512 row tiles, N > 131 072) incl. a second pass of its inner loop
-  (more than 4096 tiles, N > 1 048 576) and the true C5 row count / particle count with the forest cut to two trees;
+* `select_split` above 512 row tiles (N > 131 072: bucket counts, then tile counts), above 16 384 tiles (N > 4.2M:
+  two-level search over the bucket counts) and at the true C5 row count / particle count with the forest cut to two trees;
 * particles whose trees outgrow the shared-memory node store (`fastF` nodes per particle: 21 at P=60, 10 at P=128)
   and spill into the global overflow array;
 * non-uniform `split_prior`, more than BK_CUM_SMEM=1024 columns, depth >= 64 (global depth-prior table) and the
@@ -24,13 +24,19 @@ pytestmark = pytest.mark.gpu
 
 
 def test_two_level_member_search_n200k():
-    """782 row tiles: every grow below the root goes through select_split's `per > 4` branch."""
+    """782 row tiles: every grow below the root goes through the bucket-count level of select_split."""
     assert run_pair(200_000, 6, 4, 8, 6, seed=21)
 
 
-def test_two_level_member_search_second_inner_pass_n1100k():
-    """4297 tiles -> 34 four-tile groups per lane: the second-level scan needs two passes."""
+def test_bucket_counts_n1100k():
+    """4297 tiles -> 135 buckets of 32 tiles: bucket level in registers, then the bucket's tile counts."""
     assert run_pair(1_100_000, 3, 1, 6, 8, seed=22)
+
+
+def test_bucket_counts_two_level_n4300k():
+    """16797 tiles -> 525 buckets: more than 16 bucket counts per lane, so the bucket level itself takes the two-level
+    branch of find_in_counts (reached only above N = 4.2M rows)."""
+    assert run_pair(4_300_000, 2, 1, 4, 6, seed=28)
 
 
 def test_config5_shape_two_trees():
