@@ -227,7 +227,8 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
         torch.cuda.synchronize()
 
     # the posterior draws stay on the device: ring [draw, chain x group, N]; gathered once at the end
-    draws_dev = torch.empty((max(n_post, 1), nvc, N), dtype=torch.float32, device="cuda")
+    # (rows keep the sampler's padding so that a draw is ONE contiguous device-to-device copy)
+    draws_dev = torch.empty((max(n_post, 1), nvc, dev.ld), dtype=torch.float32, device="cuda")
     gathered = None
     if world > 1:
         gathered = torch.empty((world * draws_dev.shape[0], *draws_dev.shape[1:]), dtype=torch.float32, device="cuda")
@@ -240,6 +241,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     grow = tupd = tune_upd = rounds = phases = 0
     us_total = us_control = us_data = 0
+    us_by_phase = {True: 0.0, False: 0.0}
     t_w0 = time.perf_counter()
     for i in range(steps):
         tune = i < n_tune
@@ -250,7 +252,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
         dev.step_launch(tune, 1.0)
         if not tune:
             with torch.cuda.stream(stream):
-                draws_dev[i - n_tune].copy_(dev.sum_trees(), non_blocking=True)   # the draw is kept (inside the timed step)
+                draws_dev[i - n_tune].copy_(dev.sum_trees_dev, non_blocking=True)   # the draw is kept (inside the timed step)
         ev[i][1].record(stream)
         _, st = dev.step_wait()
         for c in range(nvc):
@@ -258,6 +260,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
             tune_upd += st[c].tree_updates if tune else 0
         phases += st[0].phases
         us_total += max(st[c].us_total for c in range(nvc)); us_control += st[0].us_control; us_data += st[0].us_data
+        us_by_phase[tune] += max(st[c].us_total for c in range(nvc))
     t_gather0 = torch.cuda.Event(enable_timing=True); t_gather1 = torch.cuda.Event(enable_timing=True)
     t_gather0.record(stream)
     if world > 1:   # the run's single collective (sampling.gather_posterior): ordered after the steps on their stream
@@ -278,7 +281,10 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     g_all, t_all, tu_all = [float(v) for v in agg.tolist()]
     value = world * chains * steps / (total_ms_max / 1e3)
     out = {"value": value, "unit": "draws/s", "ms_per_step": total_ms_max / steps, "steps": steps, "warmup": warm,
-           "in_kernel_us": {"step": us_total / steps, "control_chain0": us_control / steps, "data_wait_chain0": us_data / steps}}
+           "in_kernel_us": {"step": us_total / steps, "control_chain0": us_control / steps, "data_wait_chain0": us_data / steps,
+                            "step_tuning": us_by_phase[True] / max(n_tune, 1), "step_post": us_by_phase[False] / max(n_post, 1),
+                            "event_tuning": 1e3 * float(np.mean(step_ms[:n_tune])) if n_tune else None,
+                            "event_post": 1e3 * float(np.mean(step_ms[n_tune:])) if n_post else None}}
     if args.profile_only:
         dev.close()
         return out
@@ -303,7 +309,8 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     for i in range(e2e_steps):
         if i == e2e_steps // 2:
             stp.stop_tuning()
-        val_host, stats = stp.astep()      # H2D sigma, step kernel, D2H sum-of-trees + VI counts + stats (+ tree history after tuning)
+        val_host, stats = stp.astep()      # step kernel, D2H sum-of-trees + VI counts + stats (+ the rewritten trees after tuning)
+    stp.flush_history()                    # every batch has reached op.all_trees (the Manager proxy of pymc_bart/bart.py:134)
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t_w0
     clocks.window(t_w0, time.perf_counter())
@@ -338,7 +345,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
         "rounds_per_tree_update": rounds / max(tupd, 1),
         "grid_phases_per_step": phases / steps,
         "gather_ms": gather_ms_max,
-        "gather_bytes_per_rank": int(n_post * nvc * N * 4) if world > 1 else 0,
+        "gather_bytes_per_rank": int(n_post * nvc * N * 4) if world > 1 else 0,   # (+0.1 % row padding on the wire)
         "e2e": {"value": e2e_val, "unit": "draws/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build,
                 "history": "store_history=True: after tuning every step's rewritten trees are exported (op.all_trees protocol)"},

@@ -84,6 +84,8 @@ class PGBART:
                                       **self._settings_kw)
         self.n_rows, self.n_cols, self.m = self.settings.n_rows, self.settings.n_cols, self.settings.n_trees
         self.core = None                # device state: created lazily, never pickled
+        self._pub_thread = None
+        self._pub_queue = None
         self._reset_chain_state()
         self.last_stats = None
         self.history_bytes_per_step = 0
@@ -120,6 +122,8 @@ class PGBART:
         state["core"] = None            # no CUDA context / native handle crosses a process boundary
         state["_batches"] = None
         state["last_stats"] = None
+        state["_pub_thread"] = None
+        state["_pub_queue"] = None
         return state
 
     def next_chain(self):
@@ -137,6 +141,49 @@ class PGBART:
 
     def stop_tuning(self):
         self.tune = False
+
+    # ---- history publication ---------------------------------------------------
+    # Appending to a Manager proxy is an IPC round trip (~0.1 ms per chain and draw): a writer thread does it, so the
+    # step does not wait for the parent process.  Appends keep their order (one queue, one thread); flush_history()
+    # waits until everything queued so far is in op.all_trees (close() and sample() call it).
+    def _publish(self, target, item):
+        from multiprocessing.managers import BaseProxy
+
+        if not isinstance(target, BaseProxy):
+            target.append(item)
+            return
+        if self._pub_thread is None:
+            import queue
+            import threading
+
+            self._pub_queue = queue.Queue()
+
+            def drain(q=self._pub_queue):
+                while True:
+                    job = q.get()
+                    try:
+                        if job is not None:
+                            job[0].append(job[1])
+                    finally:
+                        q.task_done()
+                    if job is None:
+                        return
+
+            self._pub_thread = threading.Thread(target=drain, name="pgbart-history", daemon=False)
+            self._pub_thread.start()
+        self._pub_queue.put((target, item))
+
+    def flush_history(self):
+        """Block until every batch queued so far has reached op.all_trees."""
+        if self._pub_thread is not None:
+            self._pub_queue.join()
+
+    def _stop_publisher(self):
+        if self._pub_thread is not None:
+            self._pub_queue.put(None)
+            self._pub_thread.join()
+            self._pub_thread = None
+            self._pub_queue = None
 
     def _new_batches(self):
         """A list of the same kind as op.all_trees: a nested Manager proxy when the history crosses processes."""
@@ -163,7 +210,7 @@ class PGBART:
             base = core.baseline()
             self._batches = [self._new_batches() for _ in range(self.chains)]
             for c in range(self.chains):
-                self.op.all_trees.append((self._chain_slice(base, c), self._batches[c]))
+                self._publish(self.op.all_trees, (self._chain_slice(base, c), self._batches[c]))
         vi, stats = core.step(tune, self.sigma)
         self.last_stats = stats
         self._lower = hi if hi < self.m else 0
@@ -175,7 +222,7 @@ class PGBART:
                 off = np.concatenate([[0], np.cumsum(nn.sum(axis=1))])
                 G = self.groups
                 for c in range(self.chains):
-                    self._batches[c].append((first, nn[c * G:(c + 1) * G].copy(), nodes[off[c * G]: off[(c + 1) * G]].copy()))
+                    self._publish(self._batches[c], (first, nn[c * G:(c + 1) * G].copy(), nodes[off[c * G]: off[(c + 1) * G]].copy()))
         vic = vi.reshape(self.chains, self.groups, -1).sum(axis=1)       # one inclusion vector per BART variable
         out_stats = [{"variable_inclusion": _encode_vi(vic[c].tolist()), "tune": tune} for c in range(self.chains)]
         value = value.reshape(self.chains, self.groups, -1)
@@ -203,6 +250,13 @@ class PGBART:
         return None
 
     def close(self):
+        self._stop_publisher()
         if self.core is not None:
             self.core.close()
             self.core = None
+
+    def __del__(self):
+        try:
+            self._stop_publisher()
+        except Exception:
+            pass

@@ -62,6 +62,7 @@ def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1)
                 post[:, d - tune] = v
             for c in range(chains):
                 vi[c][d - tune] = s[c]["variable_inclusion"]
+    step.flush_history()
     out = {"step": step, "variable_inclusion": vi, "posterior": post, "rank": rank, "world": world}
     if distributed and world > 1 and keep_draws:
         # the single collective of the run: all-gather of the posterior draws over NVLink

@@ -227,6 +227,7 @@ def test_pgbart_step_protocol_with_a_fake_core(monkeypatch):
     step.stop_tuning()
     for d in range(5):
         v, st = step.astep()
+        step.flush_history()                                                 # (Manager appends run on a writer thread)
         assert len(op.all_trees) == 3 and len(op.all_trees[0][1]) == d + 1   # one entry per chain (utils.py:117), one batch per draw
     assert [_decode_vi(s["variable_inclusion"], 3)[0] for s in st] == [1 + 2, 3 + 4, 5 + 6]   # groups of a chain summed
     base, batches = op.all_trees[2]
@@ -245,7 +246,7 @@ def test_pgbart_step_protocol_with_a_fake_core(monkeypatch):
     step.tune = True
     step.astep()
     assert first_core.closed and step.core is not first_core and step.core.chain_base == 3 and step.chain_base == 3
-    step.stop_tuning(); step.astep()
+    step.stop_tuning(); step.astep(); step.flush_history()
     assert len(op.all_trees) == 6                                            # the new chains' entries follow the old ones
     with pytest.raises(KeyError):
         pg.PGBART([mu], sigma_name="sigma").step({"sigma_log__": 0.0})       # a scale that is not in the point must not be ignored

@@ -100,6 +100,7 @@ def test_registration_and_two_chains_through_one_step_object(fake_pymc, monkeypa
             point, stats = step.step(point)
             assert point["mu"].shape == (40,) and stats[0]["tune"] == (d < 3)
             assert step._core.core.last_sigma == pytest.approx(0.7)   # backward-transformed value of the point, not log(sigma)
+        step._core.flush_history()
         assert len(op.all_trees) == chain + 1 and len(op.all_trees[chain][1]) == 3    # published while sampling, one entry per chain
     assert [c.chain_base for c in _FakeCore.instances[-2:]] == [0, 1]                   # the second chain has its own Philox stream
     with pytest.raises(KeyError):
