@@ -74,6 +74,8 @@
 #define BK_QBITS 29           /* |q| <= 2^29-1 so 16 squared terms fit in u64 */
 #define BK_QMAX ((int32_t)((1 << BK_QBITS) - 1))
 #define BK_MAX_DEPTH_TABLE 256
+#define BK_SPLIT_TRIES 4      /* candidate members per split-value draw (the 4 words of one Philox block); a candidate
+                                 whose covariate is missing (NaN) is skipped, 4 misses leave the node a leaf         */
 
 /* RNG purposes */
 #define BK_U_LEAF 0u      /* grow-or-stay-leaf test of the popped node */

@@ -244,24 +244,36 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
   int v = draw_variable(o, u2);
   int n = nd->st.n;
   if (n < 2) return 0;                            /* fewer than two candidate split values */
-  uint32_t k = bk_index(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAL).v[0], (uint32_t)n);
+  /* Split value = covariate of a uniformly drawn member with a value (members with a missing
+   * covariate are not candidates).  bk_spec.h BK_SPLIT_TRIES: the four words of ONE Philox block give up to four
+   * candidate members k_t = floor(x_t * n / 2^32) among ALL members of the node (ascending row index); the first one
+   * whose covariate is not NaN supplies the value (rejection sampling: uniform over the members that have one); four
+   * misses in a row leave the node a leaf.  Without missing values the first word decides, as before. */
+  const bk_u32x4 wv = bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAL);
   const float* xc = o->X + (size_t)v * (size_t)N;
-  /* k-th member of node j in ascending row index */
   float s = 0.0f;
-  {
-    uint32_t seen = 0; int found = 0;
+  int have = 0;
+  for (int t = 0; t < BK_SPLIT_TRIES && !have; ++t) {
+    uint32_t k = bk_index(wv.v[t], (uint32_t)n), seen = 0;
     for (int i = 0; i < N; ++i) {
-      if (q->ids[i] == (uint8_t)j) { if (seen == k) { s = xc[i]; found = 1; break; } seen++; }
+      if (q->ids[i] == (uint8_t)j) { if (seen == k) { s = xc[i]; break; } seen++; }
     }
-    if (!found) return 0; /* cannot happen: n counts the members */
+    have = !(s != s);
   }
+  if (!have) return 0;
   int L = q->n_nodes, R = q->n_nodes + 1;
   bk_stats sl, sr;
   memset(&sl, 0, sizeof(sl)); memset(&sr, 0, sizeof(sr));
+  int64_t ll_dropped = 0;   /* Bernoulli: terms of the rows dropped here, at the value 0 they now carry */
   const int onehot = o->rules[v] == BK_RULE_ONEHOT;
   for (int i = 0; i < N; ++i) {
     if (q->ids[i] != (uint8_t)j) continue;
     float x = xc[i];
+    if (x != x) {   /* missing covariate: the row leaves the tree (limbo, predicts 0) and counts for neither child */
+      q->ids[i] = BK_LIMBO;
+      if (o->s.likelihood == BK_LIK_BERNOULLI_LOGIT) ll_dropped += (int64_t)bk_bern_q(o->y[i], o->noi[i], 0.0f);
+      continue;
+    }
     int left = onehot ? (x == s) : (x <= s);
     bk_stats* t = left ? &sl : &sr;
     q->ids[i] = (uint8_t)(left ? L : R);
@@ -288,7 +300,7 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
     }
     o->bytes_touched += (long long)N * 9;
     nl->ll = ll_l; nr->ll = ll_r;
-    q->llq = q->llq - nd->ll + ll_l + ll_r;
+    q->llq = q->llq - nd->ll + ll_l + ll_r + ll_dropped;
     q->lw = bk_bern_loglik((double)q->llq);
   } else {
     q->gain = BK_DADD(BK_DADD(BK_DSUB(q->gain, g_parent), bk_leaf_gain(sl, vl, o->inv_qscale)), bk_leaf_gain(sr, vr, o->inv_qscale));
@@ -315,7 +327,7 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
     bk_stats tot; memset(&tot, 0, sizeof(tot));
     bk_u128 tot_sr2 = bk_u128_make(0, 0);
     for (int k = 0; k < old->n_nodes; ++k) { bk_stats z; memset(&z, 0, sizeof(z)); z.n = old->nodes[k].st.n; old->nodes[k].st = z; old->nodes[k].ll = 0; }
-    int64_t tot_ll = 0;
+    int64_t tot_ll = 0, limbo_ll = 0;
     for (int i = 0; i < N; ++i) {
       float oldp = old->ids[i] == BK_LIMBO ? 0.0f : old->nodes[old->ids[i]].value;
       float noi = BK_FSUB(o->st[i], oldp);
@@ -323,6 +335,7 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       o->noi[i] = noi;
       if (bern) {   /* per-row terms of the old tree's leaf and of the root-only stump */
         if (old->ids[i] != BK_LIMBO) old->nodes[old->ids[i]].ll += (int64_t)bk_bern_q(o->y[i], noi, oldp);
+        else limbo_ll += (int64_t)bk_bern_q(o->y[i], noi, 0.0f);   /* rows the old tree dropped predict 0 */
         tot_ll += (int64_t)bk_bern_q(o->y[i], noi, o->s.init_leaf);
         r = 0.0f;   /* the Gaussian residual statistics are not used */
       }
@@ -338,7 +351,7 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
     part_copy(&o->parts[0], old, N);
     o->parts[0].q_head = o->parts[0].n_nodes;
     if (bern) {
-      int64_t llq = 0;
+      int64_t llq = limbo_ll;
       for (int k = 0; k < old->n_nodes; ++k) if (old->nodes[k].var < 0) llq += old->nodes[k].ll;
       o->parts[0].gain = 0.0; o->parts[0].llq = llq; o->parts[0].lw = bk_bern_loglik((double)llq);
     } else {

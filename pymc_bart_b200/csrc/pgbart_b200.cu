@@ -149,6 +149,12 @@ __shared__ long long s_ct_last;
 #endif
 
 // a node with fewer than N / BK_SPARSE_DIV members loads the split column only in lanes that hold members
+// -DBK_NO_MISSING compiles the missing-covariate paths out (A/B of their cost on data without NaNs; tests/gpu_variants.sh)
+#ifdef BK_NO_MISSING
+#define BK_MISSING_ENABLED 0
+#else
+#define BK_MISSING_ENABLED 1
+#endif
 #ifndef BK_SPARSE_DIV
 #define BK_SPARSE_DIV 8
 #endif
@@ -202,6 +208,8 @@ struct CtlShared {
   int err_bits;
   unsigned long long r_slice[4];
   int warp_grow_root[4];
+  int n_nan_fail, n_fail_root;   // slots whose split value could not be drawn (only members with a missing covariate)
+  Params params_copy;            // for the out-of-line retry path (a reference to the kernel parameter would force a per-thread stack copy)
   // last value read from every accumulator word of accL: the workers only ever ADD (RED), the control CTA takes
   // differences (exact in wrapping 64-bit arithmetic), so no accumulator is ever zeroed by a store that would have
   // to be ordered before the next epoch's adds
@@ -551,7 +559,9 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
   CTRL_SYNC();
   const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
   if (threadIdx.x == 0) {
-    double gain = 0.0;   // Bernoulli: integer sum of the leaves' quantised log-likelihood terms (exact in double)
+    // Bernoulli: integer sum of the leaves' quantised log-likelihood terms (exact in double), plus the terms of the rows
+    // the tree dropped for a missing covariate (they predict 0)
+    double gain = bern ? (double)(long long)__ldcg(a0 + (size_t)256 * BK_ACC0_STRIDE + 1) : 0.0;
     for (int k = 0; k < nn; ++k) {
       const DNode& nd = p0.node(k);
       if (nd.var < 0) gain = BK_DADD(gain, bern ? (double)nd.sr : bk_leaf_gain(node_stats(nd), nd.value, P.inv_qscale));
@@ -670,6 +680,15 @@ __device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* h
   DNode parent = S.node(jb.node);
   const bk_stats sp = node_stats(parent);
   bk_stats sr = bk_stats_sub(sp, sl);
+  if (BK_MISSING_ENABLED && jb.pad[1]) {   // the split column has missing values: the rows dropped from the node count for neither child
+    const unsigned long long a_n = __ldcg(acc + BK_ACC_ND), a_st = __ldcg(acc + BK_ACC_SSTD), a_sr = __ldcg(acc + BK_ACC_SRD);
+    unsigned long long* prev = sh.acc_prev[q];
+    bk_stats sd;
+    sd.n = (int32_t)(a_n - prev[BK_ACC_ND]); sd.sst = (int64_t)(a_st - prev[BK_ACC_SSTD]); sd.sr = (int64_t)(a_sr - prev[BK_ACC_SRD]);
+    prev[BK_ACC_ND] = a_n; prev[BK_ACC_SSTD] = a_st; prev[BK_ACC_SRD] = a_sr;
+    if (bern) { S.h->gain = BK_DADD(S.h->gain, (double)sd.sr); sd.sr = 0; }   // their log-likelihood terms at the value 0 they now carry
+    sr = bk_stats_sub(sr, sd);
+  }
   if (bern) { sl.sr = 0; sr.sr = 0; }   // the children's log-likelihood sums arrive with the LL epoch
   const bool pre = sh.pre_z_tree == t && sh.pre_z_round == round;
   const double zl = pre ? sh.pre_zl[q] : bk_normal(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
@@ -718,6 +737,29 @@ __device__ __forceinline__ void finalize_ll_own(const Params& P, int c, CtlShare
   const double llq = BK_DADD(BK_DSUB(S.h->gain, (double)ll_parent), (double)(ll_l + ll_r));   // integers: exact
   S.h->gain = llq;
   S.h->lw = bk_bern_loglik(llq);
+}
+
+// bk_spec.h BK_SPLIT_TRIES: candidates 1..3 of a split-value draw whose first candidate member has no value in the split
+// column (NaN).  Out of line: columns without missing values never get here, and the round path keeps its registers.
+__device__ __noinline__ float retry_split_value(const Params& P, int c, CtlShared& sh, int buf, int sl, uint32_t S0, uint32_t C0,
+                                                uint32_t D0, uint32_t G0, int t, int round) {
+  const int lane = threadIdx.x & 31;
+  const PRef S = pref(P, c, buf, sh.src_slot[sl]);
+  const bk_u32x4 wv = bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)sl, BK_U_VAL);
+  const uint32_t n = (uint32_t)S.node(sh.s_j[sl]).n;
+  float sv = bk_bits2f(0x7FC00000u);
+  for (int tr = 1; tr < BK_SPLIT_TRIES; ++tr) {
+    const unsigned kk = bk_index(wv.v[tr], n);
+    if (sh.s_row[sl] == BK_ROW_VIRTUAL) {
+      sv = __ldg(P.X + (size_t)sh.s_v[sl] * P.Npad + kk);
+    } else {
+      int err = 0;
+      sv = select_split(P, c, sh.s_row[sl], sh.s_j[sl], kk, sh.s_v[sl], &err);
+      if (lane == 0 && err) atomicOr(&sh.err_bits, err);
+    }
+    if (!(sv != sv)) break;
+  }
+  return sv;
 }
 
 // Opens round `round` of tree t: queue pops and grow decisions of every slot (through its ancestor `src` when a
@@ -793,7 +835,7 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
       Job jb;
       jb.kind = BK_JOB_PARTITION; jb.slot = q; jb.src_row = row; jb.dst_row = dst < 0 ? 0 : dst;
       jb.node = j; jb.var = v; jb.split = 0.0f; jb.left_id = nn;
-      jb.next_node = next; jb.rule = v < BK_CUM_SMEM ? (int)sh.rules[v] : P.rules[v]; jb.pad[0] = sparse; jb.pad[1] = 0;
+      jb.next_node = next; jb.rule = v < BK_CUM_SMEM ? (int)sh.rules[v] : P.rules[v]; jb.pad[0] = sparse; jb.pad[1] = P.col_nan[v];
       if (dst >= 0) sh.row_cnt_node[dst] = next;
       sh.jobs[rank_g] = jb;
       sh.s_jobidx[q] = rank_g;
@@ -827,13 +869,31 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
         if (lane == 0 && err) atomicOr(&sh.err_bits, err);
         CTN(29);
       }
-      if (lane == 0) sh.s_split[sl] = sv;
+      if (BK_MISSING_ENABLED && sv != sv) sv = retry_split_value(sh.params_copy, c, sh, buf, sl, S0, C0, D0, G0, t, round);   // the candidate's covariate is missing
+      if (lane == 0) { sh.s_split[sl] = sv; if (sv != sv) atomicAdd(&sh.n_nan_fail, 1); }
     }
   }
   CTS(21, 0);
   CTRL_SYNC();
   CTS(22, 0);
   TSUB(5);
+  if (BK_MISSING_ENABLED && sh.n_nan_fail) {
+    // Some slot found only members with a missing covariate (BK_SPLIT_TRIES misses): its node stays a leaf.  The
+    // partition job becomes the count-only job the slot would have got (or nothing), and finalize skips the slot.
+    if (is_p && kind == 1 && sh.s_split[q] != sh.s_split[q]) {
+      const int ji = sh.s_jobidx[q];
+      const int next2 = sh.s_qh[q] < nn ? sh.s_qh[q] : -1;
+      Job jb = sh.jobs[ji];
+      jb.kind = BK_JOB_NOP; jb.next_node = -1;
+      if (row >= 0 && next2 >= 0 && atomicExch(&sh.row_cnt_node[row], next2) != next2) {
+        jb.kind = BK_JOB_COUNT; jb.src_row = row; jb.dst_row = row; jb.next_node = next2;
+      }
+      sh.jobs[ji] = jb;
+      sh.s_jobidx[q] = -1; sh.s_kind[q] = 0;
+      if (row == BK_ROW_VIRTUAL) atomicAdd(&sh.n_fail_root, 1);
+    }
+    CTRL_SYNC();
+  }
   // ---- the list goes to global memory with the split values patched in (48-byte descriptors, 16-byte pieces)
   tot_g = sh.warp_grow[0] + sh.warp_grow[1] + sh.warp_grow[2] + sh.warp_grow[3];
   const int nj = tot_g + sh.n_cnt_jobs;
@@ -854,8 +914,8 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
   }
   if (threadIdx.x == 0) {
     hot->n_jobs = nj; hot->n_grow = tot_g;
-    hot->c_grow += tot_g;   // (a partition job always grows its particle)
-    hot->c_grow_root += sh.warp_grow_root[0] + sh.warp_grow_root[1] + sh.warp_grow_root[2] + sh.warp_grow_root[3];
+    hot->c_grow += tot_g - sh.n_nan_fail;   // (a partition job grows its particle unless its split value was cancelled)
+    hot->c_grow_root += sh.warp_grow_root[0] + sh.warp_grow_root[1] + sh.warp_grow_root[2] + sh.warp_grow_root[3] - sh.n_fail_root;
     hot->c_count_passes += sh.n_cnt_jobs;
     if (sh.err_bits) hot->c_err |= sh.err_bits;
   }
@@ -1070,7 +1130,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       if (rec) rec->log_w = S.h->lw;
     }
     if (q >= 0 && q < 8) sh.used_rows[q] = 0u;
-    if (q == 0) { sh.n_cnt_jobs = 0; sh.next_sel = 1; sh.err_bits = 0; }
+    if (q == 0) { sh.n_cnt_jobs = 0; sh.next_sel = 1; sh.err_bits = 0; sh.n_nan_fail = 0; sh.n_fail_root = 0; }
     CTRL_SYNC();
     CTS(17, 0);
     const int live = sh.live;
@@ -1135,6 +1195,11 @@ __device__ __forceinline__ unsigned bytes_eq(unsigned w, unsigned pat4) {
 #define BK_LIMB_ST_HI 2
 #define BK_LIMB_SR_LO 3
 #define BK_LIMB_SR_HI 4
+#define BK_LIMB_ND 5        // rows dropped from the node by a missing covariate: count, sum q(sum_trees), sum q(r)
+#define BK_LIMB_STD_LO 6
+#define BK_LIMB_STD_HI 7
+#define BK_LIMB_SRD_LO 8
+#define BK_LIMB_SRD_HI 13
 #define BK_LIMB_LLL_LO 9
 #define BK_LIMB_LLL_HI 10
 #define BK_LIMB_LLR_LO 11
@@ -1148,6 +1213,9 @@ __device__ __forceinline__ unsigned long long take_stat(unsigned* L, int k) {
     case BK_ACC_N: lo = BK_LIMB_N; hi = -1; break;
     case BK_ACC_SST: lo = BK_LIMB_ST_LO; hi = BK_LIMB_ST_HI; break;
     case BK_ACC_SR: lo = BK_LIMB_SR_LO; hi = BK_LIMB_SR_HI; break;
+    case BK_ACC_ND: lo = BK_LIMB_ND; hi = -1; break;
+    case BK_ACC_SSTD: lo = BK_LIMB_STD_LO; hi = BK_LIMB_STD_HI; break;
+    case BK_ACC_SRD: lo = BK_LIMB_SRD_LO; hi = BK_LIMB_SRD_HI; break;
     case BK_ACC_LLL: lo = BK_LIMB_LLL_LO; hi = BK_LIMB_LLL_HI; break;
     case BK_ACC_LLR: lo = BK_LIMB_LLR_LO; hi = BK_LIMB_LLR_HI; break;
     default: return 0ull;
@@ -1163,6 +1231,9 @@ __device__ __forceinline__ unsigned long long take_stat(unsigned* L, int k) {
 // byte e (0..3) of a 0x00/0xFF byte mask widened to a 32-bit mask
 #define BK_ROWMASK(m, e) __byte_perm((m), 0u, 0x1111u * (e))
 
+// MISSING: X holds NaNs somewhere (Params::has_nan).  A separate instantiation so that the path without missing values
+// keeps its register allocation (the extra masks and sums cost the C5 step 12 % when compiled into one body).
+template <bool MISSING>
 __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
                                            unsigned* __restrict__ sacc) {
   const int lane = threadIdx.x & 31;
@@ -1196,6 +1267,7 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     const int kind = j0.x, src_row = j0.z, dst_row = j0.w;
     const int node = j1.x, var = j1.y; const float split = __int_as_float(j1.z); const int left_id = j1.w;
     const int next_node = j2.x, rule = j2.y, sparse = j2.z;
+    const bool has_nan = MISSING && j2.w != 0;
     unsigned w0 = vw0, w1 = vw1;
     if (src_row != BK_ROW_VIRTUAL) {
       const uint2 v = __ldcg(reinterpret_cast<const uint2*>(rows_c + (size_t)src_row * P.Npad));
@@ -1208,9 +1280,10 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       unsigned lb0 = 0u, lb1 = 0u;
       // dense nodes: the column load is issued together with the leaf-id load (one L2/HBM round trip
       // per job); sparse nodes (few members) keep it dependent on the ids to save the bytes
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
       if (!sparse || (mem0 | mem1)) {
         const float4* xp = reinterpret_cast<const float4*>(x_b + (size_t)var * P.Npad);
-        const float4 x0 = __ldg(xp), x1 = __ldg(xp + 1);
+        x0 = __ldg(xp); x1 = __ldg(xp + 1);
         if (rule == BK_RULE_ONEHOT) {
           if (x0.x == split) lb0 |= 0x000000FFu; if (x0.y == split) lb0 |= 0x0000FF00u;
           if (x0.z == split) lb0 |= 0x00FF0000u; if (x0.w == split) lb0 |= 0xFF000000u;
@@ -1225,8 +1298,53 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       }
       const unsigned lm0 = lb0 & mem0, lm1 = lb1 & mem1;           // 0xFF where the row goes to the left child
       const unsigned L4 = (unsigned)left_id * 0x01010101u, R4 = L4 + 0x01010101u;
-      const unsigned n0 = (w0 & ~mem0) | (mem0 & ((lm0 & L4) | (~lm0 & R4)));
-      const unsigned n1 = (w1 & ~mem1) | (mem1 & ((lm1 & L4) | (~lm1 & R4)));
+      unsigned n0 = (w0 & ~mem0) | (mem0 & ((lm0 & L4) | (~lm0 & R4)));
+      unsigned n1 = (w1 & ~mem1) | (mem1 & ((lm1 & L4) | (~lm1 & R4)));
+      if (has_nan) {
+        // Missing covariates: a member whose x is NaN leaves the tree (leaf id BK_LIMBO, predicts 0)
+        // and counts for neither child; its statistics go to the job's "dropped" accumulators so that the right
+        // child is parent - left - dropped.  (NaN compares false, so such a row never went left above.)
+        unsigned d0 = 0u, d1 = 0u;
+        if (!sparse || (mem0 | mem1)) {
+          if (x0.x != x0.x) d0 |= 0x000000FFu; if (x0.y != x0.y) d0 |= 0x0000FF00u;
+          if (x0.z != x0.z) d0 |= 0x00FF0000u; if (x0.w != x0.w) d0 |= 0xFF000000u;
+          if (x1.x != x1.x) d1 |= 0x000000FFu; if (x1.y != x1.y) d1 |= 0x0000FF00u;
+          if (x1.z != x1.z) d1 |= 0x00FF0000u; if (x1.w != x1.w) d1 |= 0xFF000000u;
+        }
+        d0 &= mem0; d1 &= mem1;
+        n0 |= d0; n1 |= d1;                                          // 0xFF = BK_LIMBO
+        if (__any_sync(0xffffffffu, (d0 | d1) != 0u)) {
+          int s_a = 0, r_a = 0;
+          long long ll = 0;
+          if (gauss) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int ma = (int)BK_ROWMASK(d0, e), mb = (int)BK_ROWMASK(d1, e);
+              s_a += (q_s[e] & ma) + (q_s[4 + e] & mb); r_a += (q_r[e] & ma) + (q_r[4 + e] & mb);
+            }
+          } else {   // Bernoulli: q_r holds noi; the dropped rows' terms at the value 0 (rare path: y is read here)
+            const float4* yp = reinterpret_cast<const float4*>(P.y + (size_t)(c % P.G) * P.Npad + base);
+            const float4 y0 = __ldg(yp), y1 = __ldg(yp + 1);
+            const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              s_a += (q_s[e] & (int)BK_ROWMASK(d0, e)) + (q_s[4 + e] & (int)BK_ROWMASK(d1, e));
+              if (BK_ROWMASK(d0, e)) ll += (long long)bk_bern_q(yy[e], __int_as_float(q_r[e]), 0.0f);
+              if (BK_ROWMASK(d1, e)) ll += (long long)bk_bern_q(yy[4 + e], __int_as_float(q_r[4 + e]), 0.0f);
+            }
+          }
+          // (|q| < 2^29 and at most 8 rows per lane: the per-lane sums fit 32 bits; Bernoulli terms < 2^29 each as well)
+          const long long st = (long long)s_a, sr = gauss ? (long long)r_a : ll;
+          const unsigned cd = (unsigned)(__popc(d0) + __popc(d1)) >> 3;
+          unsigned v = __reduce_add_sync(0xffffffffu, cd);
+          const unsigned st_lo = __reduce_add_sync(0xffffffffu, (unsigned)st & 0xFFFFu);
+          const int st_hi = __reduce_add_sync(0xffffffffu, (int)(st >> 16));
+          const unsigned sr_lo = __reduce_add_sync(0xffffffffu, (unsigned)sr & 0xFFFFu);
+          const int sr_hi = __reduce_add_sync(0xffffffffu, (int)(sr >> 16));
+          v = lane == 1 ? st_lo : v; v = lane == 2 ? (unsigned)st_hi : v; v = lane == 3 ? sr_lo : v; v = lane == 4 ? (unsigned)sr_hi : v;
+          if (lane < 5) atomicAdd(sacc + ji * BK_LIMBS + (lane < 4 ? BK_LIMB_ND + lane : BK_LIMB_SRD_HI), v);
+        }
+      }
       __stcg(reinterpret_cast<uint2*>(const_cast<uint8_t*>(rows_c) + (size_t)dst_row * P.Npad), make_uint2(n0, n1));
       if (__any_sync(0xffffffffu, (lm0 | lm1) != 0u)) {
         // masked per-lane sums: 4 rows fit 32 bits (|q| < 2^29)
@@ -1263,7 +1381,7 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
           if (P.nb > 0 && tot) atomicAdd(P.coarse + ((size_t)c * P.R + dst_row) * P.nb_stride + (tile / BK_COARSE_TILES), tot);
         }
       }
-    } else {  // BK_JOB_COUNT
+    } else if (kind == BK_JOB_COUNT) {
       const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(w0, next4)) + __popc(bytes_eq_msb(w1, next4)));
       const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
       if (lane == 0) {
@@ -1295,6 +1413,7 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
   for (int ji = job_lo; ji < job_hi; ++ji) {
     const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
     const int4 j0 = jp[0], j1 = jp[1], j2 = jp[2];
+    if (j0.x != BK_JOB_LL) continue;   // (a cancelled partition job keeps its list position)
     const int src_row = j0.z;
     const float vl = __int_as_float(j1.z), vr = __int_as_float(j2.y);
     const unsigned left_id = (unsigned)j1.w;
@@ -1346,7 +1465,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
   GROUP_SYNC(g);
 
   const size_t base = (size_t)ctile * BK_COMMIT_TILE + (size_t)tid * 4;
-  long long t_sst = 0, t_sr = 0, t_sd = 0;
+  long long t_sst = 0, t_sr = 0, t_sd = 0, t_limbo = 0;
   unsigned long long t_r2 = 0;
   unsigned pro_pid4 = 0xFFFFFFFFu;
   int pro_valid = 0;
@@ -1419,6 +1538,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
           qrv[e] = real ? __float_as_int(noi) : 0;
           pro_q[e] = real ? bk_bern_q(yv[e], noi, oldp) : 0;
           if (real) { t_sst += b; t_sr += bk_bern_q(yv[e], noi, P.init_leaf); }
+          if (BK_MISSING_ENABLED && real && pid == BK_LIMBO) t_limbo += pro_q[e];   // rows the old tree dropped (missing covariate) predict 0: oldp = 0
         }
       }
       pro_pid4 = pid4; pro_valid = 1;
@@ -1452,9 +1572,11 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
     unsigned long long v2 = warp_sum_u64(t_r2 >> 32);
     unsigned long long v3 = warp_sum_u64((unsigned long long)t_sst);
     unsigned long long v4 = warp_sum_u64((unsigned long long)t_sd);
+    unsigned long long v5 = (BK_MISSING_ENABLED && P.has_nan) ? warp_sum_u64((unsigned long long)t_limbo) : 0ull;
     if ((tid & 31) == 0) {
       atomicAdd(&sh.tot_acc[0], v0); atomicAdd(&sh.tot_acc[1], v1); atomicAdd(&sh.tot_acc[2], v2);
       atomicAdd(&sh.tot_acc[3], v3); atomicAdd(&sh.tot_acc[4], v4);
+      if (v5) atomicAdd(&sh.tot_acc[5], v5);
     }
   }
   GROUP_SYNC(g);
@@ -1465,6 +1587,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
       if (v) red_add_u64(a0 + (size_t)k * BK_ACC0_STRIDE, v);
     }
     if (tid < 4) { unsigned long long v = sh.tot_acc[tid]; if (v) red_add_u64(a0 + (size_t)255 * BK_ACC0_STRIDE + tid, v); }
+    if (tid == 4) { unsigned long long v = sh.tot_acc[5]; if (v) red_add_u64(a0 + (size_t)256 * BK_ACC0_STRIDE + 1, v); }   // Bernoulli terms of the limbo rows
   }
   if (do_commit && do_wf && tid == 0) { unsigned long long v = sh.tot_acc[4]; if (v) red_add_u64(a0 + (size_t)256 * BK_ACC0_STRIDE, v); }
   GROUP_SYNC(g);
@@ -1596,7 +1719,10 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
       while (lo < hi) {     // one call per tile segment of this warp's range
         const unsigned tile = lo / (unsigned)wk.njobs, j0 = lo - tile * (unsigned)wk.njobs;
         const unsigned seg = (unsigned)wk.njobs - j0 < hi - lo ? (unsigned)wk.njobs - j0 : hi - lo;
-        if (wk.cmd == BK_CMD_ROUND) round_unit(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
+        if (wk.cmd == BK_CMD_ROUND) {
+          if (BK_MISSING_ENABLED && P.has_nan) round_unit<true>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
+          else round_unit<false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
+        }
         else ll_unit(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
         lo += seg;
       }
@@ -1629,6 +1755,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const StepArgs& A
   // read-only tables of the round path: the control CTA's L1 is dropped by every acquire fence, so a global table
   // costs an L2 round trip per phase
   if (threadIdx.x < 64) sh.p_leaf[threadIdx.x] = P.p_leaf[threadIdx.x];
+  if (threadIdx.x == 0) sh.params_copy = P;
   for (int i = threadIdx.x; i < P.P * BK_ACC_STRIDE; i += BK_CTRL_THREADS)
     sh.acc_prev[i / BK_ACC_STRIDE][i % BK_ACC_STRIDE] = __ldcg(P.accL + (size_t)c * P.P * BK_ACC_STRIDE + i);
   for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += BK_CTRL_THREADS) sh.rules[v] = (signed char)P.rules[v];
@@ -1766,6 +1893,13 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
   if (tid == 0) *P.abort_flag = 0;
   for (size_t i = tid; i < (size_t)P.C * (sizeof(ChainSync) / 4); i += nth) reinterpret_cast<unsigned int*>(P.sync)[i] = 0u;
 }
+__global__ void pgbart_nan_scan_kernel(const Params P) {   // one block per column
+  const float* x = P.X + (size_t)blockIdx.x * P.Npad;
+  int any = 0;
+  for (int i = threadIdx.x; i < P.N; i += blockDim.x) any |= (x[i] != x[i]) ? 1 : 0;
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) P.col_nan[blockIdx.x] = any ? 1 : 0;
+}
 __global__ void pgbart_init_cum_kernel(const Params P) {
   int c = blockIdx.x;
   if (threadIdx.x == 0 && c < P.C) rebuild_cum_dev(P, c);
@@ -1831,7 +1965,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   size_t qr, qst, ids_tree, rows, rowcnt, coarse, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, alpha_vec, cum,
-      p_leaf, rules, vi, stats, trace, sync, abort_flag, split_prior, total;
+      p_leaf, rules, col_nan, vi, stats, trace, sync, abort_flag, split_prior, total;
   int Npad, ntiles, R, nb;
 };
 
@@ -1871,6 +2005,7 @@ static int make_layout(const bk_settings* s, Layout* L) {
   CARVE(cum, C * p * 8);
   CARVE(p_leaf, 256 * 8);
   CARVE(rules, p * 4);
+  CARVE(col_nan, p * 4);
   CARVE(vi, C * p * 4);                         // vi | stats | abort_flag stay adjacent: one D2H copy per step
   CARVE(stats, C * sizeof(bk_step_stats));
   CARVE(abort_flag, 256);
@@ -1943,7 +2078,7 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   P.parts = (DParticle*)(w + L.parts); P.forest = (DNode*)(w + L.forest); P.forest_nn = (int32_t*)(w + L.forest_nn);
   P.ctl = (ChainCtl*)(w + L.ctl); P.accL = (unsigned long long*)(w + L.accL); P.acc0 = (unsigned long long*)(w + L.acc0);
   P.alpha_vec = (double*)(w + L.alpha_vec); P.cum = (double*)(w + L.cum); P.p_leaf = (double*)(w + L.p_leaf);
-  P.rules = (int32_t*)(w + L.rules); P.vi = (int32_t*)(w + L.vi); P.stats = (bk_step_stats*)(w + L.stats);
+  P.rules = (int32_t*)(w + L.rules); P.col_nan = (int32_t*)(w + L.col_nan); P.vi = (int32_t*)(w + L.vi); P.stats = (bk_step_stats*)(w + L.stats);
   P.trace = (bk_trace_rec*)(w + L.trace); P.sync = (ChainSync*)(w + L.sync); P.abort_flag = (int32_t*)(w + L.abort_flag);
   h->split_prior_dev = (double*)(w + L.split_prior);
 
@@ -2002,6 +2137,18 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   }
   h->max_phases = 1 << 20;
 
+  {
+    // which columns hold missing values (NaN): one block per column; the answer also sizes the code paths (P.has_nan)
+    pgbart_nan_scan_kernel<<<P.p, 256, 0, h->stream>>>(P);
+    int32_t* flags = (int32_t*)malloc((size_t)P.p * sizeof(int32_t));
+    if (!flags) { set_err("out of host memory"); return BK_ERR_ARG; }
+    cudaError_t e = cudaMemcpyAsync(flags, P.col_nan, (size_t)P.p * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    P.has_nan = 0;
+    for (int v = 0; v < P.p && e == cudaSuccess; ++v) P.has_nan |= flags[v] ? 1 : 0;
+    free(flags);
+    CK(e);
+  }
   pgbart_init_kernel<<<n_sm * 2, 512, 0, h->stream>>>(P, s->init_sum, s->leaf_sd_init, h->split_prior_dev);
   pgbart_init_cum_kernel<<<P.C, 32, 0, h->stream>>>(P);
   CK(cudaGetLastError());

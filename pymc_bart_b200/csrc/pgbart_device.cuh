@@ -49,6 +49,7 @@
 #endif
 #define BK_JOB_PARTITION 1
 #define BK_JOB_COUNT 2
+#define BK_JOB_NOP 0  // a partition job whose split value could not be drawn (only members with a missing covariate)
 #define BK_JOB_LL 3   // src_row = the particle's new row, left_id, split = left leaf value, rule = bits of the right leaf value
 
 struct __align__(16) DNode {
@@ -141,12 +142,15 @@ struct __align__(16) ChainCtl {
 #define BK_ACC_N 0
 #define BK_ACC_SST 1
 #define BK_ACC_SR 2
+#define BK_ACC_ND 3     // rows dropped from the split node by a missing covariate: count, sum q(sum_trees), sum q(r) / log-lik terms
+#define BK_ACC_SSTD 4
+#define BK_ACC_SRD 7
 #define BK_ACC_LLL 5    // Bernoulli: quantised log-likelihood of the new left / right leaf
 #define BK_ACC_LLR 6
 #define BK_ACC_STRIDE 8
 
 // acc0 layout per chain: [256][4]: leaf k -> (sr, -, -, -); entry 255 = totals
-// (sr, sr2lo, sr2hi, sst); then [4]: (wf sd sum, -, -, -)
+// (sr, sr2lo, sr2hi, sst); then [4]: (wf sd sum, Bernoulli terms of the rows in limbo, -, -)
 #define BK_ACC0_STRIDE 4
 #define BK_ACC0_WORDS (257 * BK_ACC0_STRIDE)
 
@@ -171,6 +175,7 @@ struct Params {
   int32_t cnt_stride;                      // ntiles rounded up to a multiple of 4 (row stride of rowcnt)
   int32_t fastF, fast_stride;   // nodes per particle kept in the control CTA's shared memory; bytes per particle there
   int32_t lik, trace_cap, batch_tune, batch_post;
+  int32_t has_nan;   // some column of X holds missing values
   float qscale, init_leaf;
   double inv_qscale;
   double inv_qm;     // 2^-qshift / m (leaf mean scale)
@@ -197,6 +202,7 @@ struct Params {
   double* cum;         // [C][p]
   double* p_leaf;      // [256]
   int32_t* rules;      // [p]
+  int32_t* col_nan;    // [p] 1 = the column holds missing values (NaN)
   int32_t* vi;         // [C][p]
   bk_step_stats* stats;  // [C]
   bk_trace_rec* trace;   // [C][trace_cap]

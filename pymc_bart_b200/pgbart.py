@@ -48,8 +48,6 @@ class PGBART:
             raise TypeError("PGBART can only sample BART variables")
         if op.response != "constant":
             raise NotImplementedError(f"response={op.response!r} has no device implementation (constant leaves only)")
-        if np.isnan(np.asarray(op.X)).any():
-            raise NotImplementedError("NaN covariates have no device implementation yet")
         if likelihood not in LIKELIHOODS:
             raise NotImplementedError(f"likelihood {likelihood!r} has no device implementation")
         # multi-output: BART(shape=(k, n), separate_trees=True) = k output groups, each with its own forest and

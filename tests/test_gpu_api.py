@@ -224,6 +224,26 @@ def test_fit_quality_friedman():
     out["step"].close()
 
 
+def test_missing_data_through_the_api():
+    """tests/test_bart.py:67-81: NaNs in X[10:20, 0]; the sampler runs, the fit stays finite and follows the signal, and
+    rows whose split covariate is missing are predicted from the other trees only."""
+    import pymc_bart_b200 as pmb
+    from pymc_bart_b200.utils import _get_posterior_sampler
+
+    rng = np.random.default_rng(0)
+    X = rng.normal(0, 1, size=(2, 50)).T.copy()
+    Y = rng.normal(0, 1, size=50) + 2 * X[:, 1]
+    X[10:20, 0] = np.nan
+    mu = pmb.BART("mu", X, Y, m=10)
+    out = pmb.sample(mu, tune=100, draws=100, chains=1, num_particles=10, seed=1, sigma=1.0)
+    post = out["posterior"]
+    assert post.shape == (1, 100, 50) and np.all(np.isfinite(post))
+    assert np.corrcoef(post.mean(axis=(0, 1)), Y)[0, 1] > 0.6
+    pred = _get_posterior_sampler(mu.owner.op).sample_posterior(X, [0, 50, 99], None)      # NaN compares false: such rows go right
+    assert pred.shape == (3, 1, 50) and np.all(np.isfinite(pred))
+    out["step"].close()
+
+
 def test_unsupported_options_raise_not_fallback():
     import pymc_bart_b200 as pmb
 
@@ -232,9 +252,6 @@ def test_unsupported_options_raise_not_fallback():
         mu = pmb.BART("mu", X, Y, m=3, response="linear")
     with pytest.raises(NotImplementedError):
         pmb.PGBART([mu])
-    Xn = X.copy(); Xn[3, 0] = np.nan
-    with pytest.raises(NotImplementedError):
-        pmb.PGBART([pmb.BART("b", Xn, Y, m=3)])
     with pytest.raises(NotImplementedError):
         pmb.PGBART([pmb.BART("c", X, Y, m=3)], likelihood="poisson")
     with pytest.raises(ValueError, match="No posterior draws"):

@@ -104,3 +104,39 @@ def test_cuda_matches_committed_big_golden(name):
     assert np.array_equal(nn, g["forest_nn"]) and np.array_equal(nodes.view(np.uint8), g["forest"].view(np.uint8))
     assert _sha(dev.leaf_ids(0)) == str(g["leaf_ids_sha"])
     dev.close()
+
+
+def _with_missing(N, p, seed, kind="normal", all_nan_col=None):
+    X, y, _ = friedman(N, p, seed, kind=kind)
+    rng = np.random.default_rng(seed + 1000)
+    X = X.copy()
+    X[N // 6: N // 3, 0] = np.nan                              # a block of rows without column 0 (tests/test_bart.py:67-81)
+    X[rng.uniform(size=N) < 0.1, 2] = np.nan                   # 10 % scattered in column 2
+    if all_nan_col is not None:
+        X[:, all_nan_col] = np.nan                             # every candidate is missing: the split is cancelled
+    return X, y
+
+
+def test_missing_covariates_gaussian():
+    """NaN covariates (reference smoke test tests/test_bart.py:67-81): candidates with a missing
+    value are skipped (up to BK_SPLIT_TRIES draws), rows with a missing split covariate leave the tree (leaf id 255,
+    predict 0) and count for neither child."""
+    X, y = _with_missing(600, 4, 31)
+    assert run_pair(600, 4, 6, 10, 40, seed=31, X=X, y=y)
+    assert run_pair(600, 4, 6, 10, 20, seed=32, X=X, y=y, chains=2, depth_offset=1, sigma=0.3)
+
+
+def test_missing_covariates_cancelled_splits_and_bernoulli():
+    """A column that is missing everywhere: every draw of it exhausts its tries and the grow is cancelled (the
+    partition job turns into the count-only job / nothing).  Bernoulli: the dropped rows' log-likelihood terms."""
+    X, y = _with_missing(500, 5, 33, all_nan_col=1)
+    assert run_pair(500, 5, 5, 12, 30, seed=33, X=X, y=y, depth_offset=1)
+    Xb, yb = _with_missing(700, 6, 34, kind="bernoulli")
+    assert run_pair(700, 6, 6, 10, 30, seed=34, X=Xb, y=yb, likelihood=1)
+    Xc, yc = _with_missing(400, 5, 35, kind="bernoulli", all_nan_col=3)
+    assert run_pair(400, 5, 4, 8, 24, seed=35, X=Xc, y=yc, likelihood=1, depth_offset=1)
+
+
+def test_missing_covariates_large_n_bucket_counts():
+    X, y = _with_missing(150_000, 4, 36)
+    assert run_pair(150_000, 4, 2, 8, 6, seed=36, X=X, y=y, depth_offset=1)

@@ -66,6 +66,32 @@ def test_oracle_matches_big_golden(name):
     assert sha(o.leaf_ids()) == str(g["leaf_ids_sha"])
 
 
+def test_oracle_missing_covariates():
+    """SURVEY.md App. A.4 in the restatement: NaN candidates are skipped, rows with a missing split covariate go to
+    limbo (id 255) and count for neither child, a column that is missing everywhere is never split on."""
+    X, y, _ = friedman(400, 5, 41)
+    X = X.copy()
+    X[50:150, 0] = np.nan
+    X[:, 3] = np.nan
+    s = make_settings(X, y, m=6, num_particles=10, seed=41, depth_offset=1)
+    o = OracleChain(s, X.T.copy(), y)
+    for d in range(40):
+        o.step(d < 20, 1.0)
+    nodes, nn = o.forest()
+    ids = o.leaf_ids()
+    used = np.unique(np.concatenate([nodes[t]["var"][: nn[t]] for t in range(6)]))
+    assert 3 not in used and 0 in used and np.all(np.isfinite(o.sum_trees()))
+    for t in range(6):
+        nd = nodes[t][: nn[t]]
+        limbo = ids[t] == 255
+        assert np.all(np.isnan(X[limbo, 0]))                                   # only rows without the split covariate are dropped
+        split = np.nonzero(nd["var"] >= 0)[0]
+        kids = nd["n"][nd["left"][split]] + nd["n"][nd["left"][split] + 1]
+        assert np.all(kids <= nd["n"][split]) and nd["n"][0] == 400
+        leaf = nd["var"] < 0
+        assert np.array_equal(np.bincount(ids[t][~limbo], minlength=nn[t])[leaf], nd["n"][leaf])
+
+
 def _spec_probe():
     """Small C program over include/bk_spec.h: Philox KATs + max error of the math kernels vs libm."""
     src = r'''
