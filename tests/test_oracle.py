@@ -69,8 +69,9 @@ def test_oracle_matches_big_golden(name):
 def test_oracle_missing_covariates():
     """SURVEY.md App. A.4 in the restatement: NaN candidates are skipped, rows with a missing split covariate go to
     limbo (id 255) and count for neither child, a column that is missing everywhere is never split on."""
-    X, y, _ = friedman(400, 5, 41)
+    X, _, _ = friedman(400, 5, 41)
     X = X.copy()
+    y = (6 * X[:, 0] + np.random.default_rng(41).normal(0, 0.5, 400)).astype(np.float32)   # column 0 carries the signal
     X[50:150, 0] = np.nan
     X[:, 3] = np.nan
     s = make_settings(X, y, m=6, num_particles=10, seed=41, depth_offset=1)
@@ -81,6 +82,7 @@ def test_oracle_missing_covariates():
     ids = o.leaf_ids()
     used = np.unique(np.concatenate([nodes[t]["var"][: nn[t]] for t in range(6)]))
     assert 3 not in used and 0 in used and np.all(np.isfinite(o.sum_trees()))
+    assert (ids == 255).sum() > 0
     for t in range(6):
         nd = nodes[t][: nn[t]]
         limbo = ids[t] == 255
