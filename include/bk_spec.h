@@ -90,6 +90,11 @@
 /* likelihood families */
 #define BK_LIK_NORMAL 0
 #define BK_LIK_BERNOULLI_LOGIT 1
+/* shared-tree multi-output families (every leaf carries one value per output; the reference's tested multi-output
+ * models, tests/test_bart.py:107-123 and :140-164) */
+#define BK_LIK_NORMAL_HETERO 2   /* y ~ Normal(f[0], |f[1]|),    BART(shape=(2, n)) */
+#define BK_LIK_CATEGORICAL 3     /* y ~ Categorical(softmax(f)), BART(shape=(k, n)), y in {0..k-1} */
+#define BK_MAX_OUTPUTS 7         /* leaf values per leaf (one 64-byte device node holds 7 floats) */
 
 /* --------------------------------------------------------- Philox4x32-10 */
 typedef struct { uint32_t v[4]; } bk_u32x4;
@@ -407,6 +412,55 @@ BK_HD int32_t bk_bern_q(float y, float noi, float value) {
 }
 /* log-likelihood of a particle from the integer sum of its leaves' terms (exact: |llq| < 2^53) */
 BK_HD double bk_bern_loglik(double llq) { return BK_DMUL(llq, 9.5367431640625e-07); }
+
+/* natural log of a positive normal float (float kernel, fixed order; |error| ~ 1e-7 relative) */
+BK_HD uint32_t bk_f2bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+BK_HD float bk_logf(float x) {
+  const uint32_t b = bk_f2bits(x);
+  int32_t e = (int32_t)((b >> 23) & 0xFFu) - 127;
+  float m = bk_bits2f((b & 0x007FFFFFu) | 0x3F800000u);
+  if (m > 1.4142135f) { m = BK_FMUL(m, 0.5f); e += 1; }
+  const float f = BK_FSUB(m, 1.0f);
+  const float s = BK_FDIV(f, BK_FADD(2.0f, f));
+  const float z = BK_FMUL(s, s);
+  float p = 0.1111111111111111f;
+  p = BK_FFMA(p, z, 0.14285714285714285f);
+  p = BK_FFMA(p, z, 0.2f);
+  p = BK_FFMA(p, z, 0.3333333333333333f);
+  p = BK_FFMA(p, z, 1.0f);
+  const float lm = BK_FMUL(BK_FMUL(2.0f, s), p);
+  const float ef = (float)e;
+  return BK_FFMA(ef, 0.693145751953125f, BK_FFMA(ef, 1.4286068203094173e-06f, lm));
+}
+
+/* Per-row log-likelihood term of the shared-tree multi-output families at the linear predictors f[0..K-1]
+ * (the weight is the full-model data log-likelihood).  Float kernels in a fixed order; the caller
+ * quantises with bk_lik_q and sums integers, exactly like the Bernoulli path. */
+BK_HD float bk_lik_term(int lik, int K, float y, const float* f) {
+  if (lik == BK_LIK_NORMAL_HETERO) {       /* -1/2 ((y - f0)/|f1|)^2 - log|f1| - 1/2 log(2 pi) */
+    float a = f[1] < 0.0f ? -f[1] : f[1];
+    a = a < 1e-20f ? 1e-20f : a;
+    const float z = BK_FDIV(BK_FSUB(y, f[0]), a);
+    return BK_FSUB(BK_FSUB(BK_FMUL(-0.5f, BK_FMUL(z, z)), bk_logf(a)), 0.9189385332046727f);
+  }
+  /* BK_LIK_CATEGORICAL: f[y] - logsumexp(f) */
+  float mx = f[0];
+  for (int j = 1; j < K; ++j) mx = f[j] > mx ? f[j] : mx;
+  float sum = 0.0f;
+  for (int j = 0; j < K; ++j) sum = BK_FADD(sum, bk_exp_neg_f(BK_FSUB(mx, f[j])));
+  int yi = (int)y;
+  yi = yi < 0 ? 0 : (yi >= K ? K - 1 : yi);
+  float fy = f[0];
+  for (int j = 1; j < K; ++j) fy = j == yi ? f[j] : fy;
+  return BK_FSUB(BK_FSUB(fy, mx), bk_logf(sum));
+}
+BK_HD int32_t bk_lik_q(int lik, int K, float y, const float* f) { return bk_quant(bk_lik_term(lik, K, y, f), 1048576.0f); }
 
 /* Particle weights and systematic resampling in FIXED POINT (w = exp(lw - max) + 1e-12,
  * normalise, inverse-CDF walk over the points (u + i)/L).

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define BK_ABI_VERSION 2
+#define BK_ABI_VERSION 3
 
 #define BK_OK 0
 #define BK_ERR_ARG (-1)
@@ -74,6 +74,9 @@ typedef struct {
   int32_t device;        /* CUDA device ordinal */
   int32_t trace_capacity;/* trace records per chain per step (0 = off) */
   int32_t n_groups;      /* output groups with separate trees (BART(shape=(k,n), separate_trees=True)); 0/1 = single output */
+  int32_t n_outputs;     /* leaf values per leaf with SHARED trees (BART(shape=(k,n)), tests/test_bart.py:107-123,140-164);
+                            0/1 = single output; needs likelihood BK_LIK_NORMAL_HETERO / BK_LIK_CATEGORICAL, n_groups <= 1 */
+  int32_t reserved0;
   const double* p_leaf;        /* [256] P(node at depth d stays a leaf) (bart.py:107-109) */
   const double* split_prior;   /* [n_cols] positive weights (bart.py:139,155) */
   const int32_t* split_rules;  /* [n_cols] BK_RULE_* (bart.py:156), NULL = all continuous */
@@ -139,7 +142,7 @@ int bk_padded_rows(int n_rows);
 
 /* X: [n_cols][ld] float32 (column-major copy of op.X, bart.py:209-210; padding
  * rows may hold anything); y: [n_groups][ld] float32 (padding 0); sum_trees:
- * [n_chains][n_groups][ld] float32 (written by every step: the value handed back to PyMC); workspace:
+ * [n_chains][max(n_groups, n_outputs)][ld] float32 (written by every step: the value handed back to PyMC); workspace:
  * bk_query_bytes bytes.  All four are device pointers that stay owned by the caller. */
 int bk_create(const bk_settings* s, const float* X_dev, const float* y_dev,
               float* sum_trees_dev, void* workspace_dev, bk_handle** out);
@@ -189,6 +192,11 @@ int bk_export_leaf_ids(bk_handle* h, int chain, uint8_t* ids_host);
  * (capacity n_chains*n_groups*T*255), *total_nodes of them.  Returns T, 0 for a tuning step / history off, < 0 on error. */
 int bk_set_history(bk_handle* h, int enable);
 int bk_history_batch(bk_handle* h, int32_t* first_tree, int32_t* n_nodes_host, bk_node* nodes_host, int64_t* total_nodes);
+/* Shared-tree multi-output (n_outputs > 1; BART(shape=(k, n)), tests/test_bart.py:107-123,140-164): every leaf carries one
+ * value per output.  bk_history_values: the values of the last batch's nodes, [total_nodes][n_outputs] in the order of
+ * bk_history_batch; bk_export_leaf_values: the current forest's, [n_trees][255][n_outputs] (0 for split nodes). */
+int bk_history_values(bk_handle* h, float* values_host);
+int bk_export_leaf_values(bk_handle* h, int chain, float* values_host);
 
 /* Posterior prediction from the forest history (row N1): what bartrs' PosteriorSampler.sample_posterior(X, draw_indices,
  * excluded) does for the shell (pymc_bart/utils.py:60-71,93-107), for all chains of an op in ONE launch.
@@ -198,13 +206,14 @@ int bk_history_batch(bk_handle* h, int32_t* first_tree, int32_t* n_nodes_host, b
  * ROW-major new data; sel_dev: forest rows to evaluate, [n_sel] (shared by all masks) or, with sel_per_mask,
  * [n_masks][n_sel]; excluded_masks_dev [n_masks][n_cols] uint8 (1 = variable excluded: weighted descent by the
  * children's training counts) or NULL with n_masks = 0; split_rules_dev [n_cols] BK_RULE_* or NULL;
- * out_dev [max(n_masks,1)][n_sel][n] float32; err_dev: int32 device flag the caller cleared (non-zero afterwards =
- * malformed history).  Runs on `stream` (cudaStream_t as void*). */
+ * leaf_values_dev: NULL, or for shared-tree multi-output the values of every node, [total nodes][n_values] (then one
+ * tree walk yields n_values outputs); out_dev [max(n_masks,1)][n_sel][max(n_values,1)][n] float32; err_dev: int32
+ * device flag the caller cleared (non-zero afterwards = malformed history).  Runs on `stream` (cudaStream_t as void*). */
 int bk_predict_history(int device, void* stream, const bk_node* nodes_dev, const int32_t* ver_off_dev,
                        const int32_t* ver_tbl_dev, int n_trees, int max_forest_nodes, const float* X_dev, int n,
                        int n_cols, const int32_t* sel_dev, int n_sel, int sel_per_mask,
                        const uint8_t* excluded_masks_dev, int n_masks, const int32_t* split_rules_dev,
-                       float* out_dev, int32_t* err_dev);
+                       const float* leaf_values_dev, int n_values, float* out_dev, int32_t* err_dev);
 
 /* Squared Pearson correlation of the variable-importance search (row N4; pymc_bart/utils.py:1339-1346 `pearsonr2`,
  * called per posterior sample at :1003-1005 and :1038-1040).  a_dev [n_samples][len] (full model),

@@ -46,6 +46,7 @@ def load():
     lib.bko_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.bko_export_forest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bko_export_leaf_ids.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bko_export_leaf_values.argtypes = [C.c_void_p, C.c_void_p]
     lib.bko_bytes_touched.argtypes = [C.c_void_p]
     lib.bko_bytes_touched.restype = C.c_longlong
     lib.bko_leaf_sd.argtypes = [C.c_void_p]
@@ -72,6 +73,7 @@ class OracleChain:
             raise RuntimeError(f"bko_create failed: {rc}")
         self.h = h
         self.N, self.p, self.m = settings.n_rows, settings.n_cols, settings.n_trees
+        self.K = max(1, int(getattr(settings, "n_outputs", 1)))
 
     def close(self):
         if getattr(self, "h", None):
@@ -93,8 +95,15 @@ class OracleChain:
         return vi, st
 
     def sum_trees(self) -> np.ndarray:
-        out = np.empty(self.N, dtype=np.float32)
+        """[N], or [K][N] for shared-tree multi-output."""
+        out = np.empty(self.N if self.K == 1 else (self.K, self.N), dtype=np.float32)
         self.lib.bko_sum_trees(self.h, out.ctypes.data)
+        return out
+
+    def leaf_values(self) -> np.ndarray:
+        """[m][255][K] leaf values of every output (0 for split nodes / unused slots)."""
+        out = np.zeros((self.m, _cabi.BK_MAX_NODES, self.K), dtype=np.float32)
+        self.lib.bko_export_leaf_values(self.h, out.ctypes.data)
         return out
 
     def trace(self) -> np.ndarray:

@@ -57,8 +57,9 @@ typedef struct {
   int32_t left;  /* right = left + 1 */
   int32_t depth;
   float value;
+  float vals[BK_MAX_OUTPUTS]; /* shared-tree multi-output: one value per output (vals[0] == value) */
   bk_stats st;
-  int64_t ll;    /* Bernoulli: sum over member rows of the quantised log-likelihood terms at `value` */
+  int64_t ll;    /* Bernoulli / multi-output: sum over member rows of the quantised log-likelihood terms at the leaf's value(s) */
 } o_node;
 
 typedef struct {
@@ -104,6 +105,14 @@ typedef struct bko_s {
   int32_t* anc;
   double r2_total;  /* Gaussian: sum of squares of all rows' residuals for the tree being updated */
   long long bytes_touched; /* rough algorithmic byte counter for the CPU baseline */
+  /* shared-tree multi-output (K = n_outputs > 1): per-output copies of the row arrays and of the running leaf sd */
+  int K;
+  float* stk;      /* [K][N] sum of trees */
+  float* noik;     /* [K][N] */
+  int32_t* qstk;   /* [K][N] */
+  float* wf_meank; /* [K][N] */
+  float* wf_m2k;   /* [K][N] */
+  float leaf_sdk[BK_MAX_OUTPUTS];
 } bko;
 
 static void part_alloc(o_particle* q, int N) { q->ids = (uint8_t*)malloc((size_t)N); }
@@ -166,6 +175,19 @@ int bko_create(const bk_settings* s, const float* X, const float* y, int chain_l
   o->tmp = (o_particle*)calloc((size_t)o->P, sizeof(o_particle));
   for (int q = 0; q < o->P; ++q) { part_alloc(&o->parts[q], N); part_alloc(&o->tmp[q], N); }
   o->leaf_sd = s->leaf_sd_init;
+  o->K = s->n_outputs > 1 ? s->n_outputs : 1;
+  if (o->K > 1) {
+    if (o->K > BK_MAX_OUTPUTS || s->n_groups > 1) return BK_ERR_UNSUPPORTED;
+    const size_t KN = (size_t)o->K * (size_t)N;
+    o->stk = (float*)malloc(sizeof(float) * KN);
+    o->noik = (float*)malloc(sizeof(float) * KN);
+    o->qstk = (int32_t*)malloc(sizeof(int32_t) * KN);
+    o->wf_meank = (float*)calloc(KN, sizeof(float));
+    o->wf_m2k = (float*)calloc(KN, sizeof(float));
+    for (size_t i = 0; i < KN; ++i) o->stk[i] = s->init_sum;
+    for (int j = 0; j < o->K; ++j) o->leaf_sdk[j] = s->leaf_sd_init;
+    for (int t = 0; t < o->m; ++t) for (int j = 0; j < o->K; ++j) o->forest[t].nodes[0].vals[j] = s->init_leaf;
+  }
   o->trace_cap = s->trace_capacity;
   if (o->trace_cap > 0) o->trace = (bk_trace_rec*)calloc((size_t)o->trace_cap, sizeof(bk_trace_rec));
   o->w = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)o->P);
@@ -182,6 +204,7 @@ void bko_destroy(bko* o) {
   free(o->alpha_vec); free(o->cum); free(o->rules);
   free(o->st); free(o->noi); free(o->qr); free(o->qst); free(o->wf_mean); free(o->wf_m2);
   free(o->trace); free(o->w); free(o->anc);
+  free(o->stk); free(o->noik); free(o->qstk); free(o->wf_meank); free(o->wf_m2k);
   free(o);
 }
 
@@ -310,7 +333,10 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
   return 1;
 }
 
+static int bko_step_multi(bko* o, int tune, int32_t* vi_counts, bk_step_stats* stats);
+
 int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* stats) {
+  if (o->K > 1) return bko_step_multi(o, tune, vi_counts, stats);
   const int bern = o->s.likelihood == BK_LIK_BERNOULLI_LOGIT;
   if (!bern && o->s.likelihood != BK_LIK_NORMAL) return BK_ERR_UNSUPPORTED;
   const int N = o->N, P = o->P, m = o->m;
@@ -444,7 +470,224 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
   return BK_OK;
 }
 
-int bko_sum_trees(const bko* o, float* out) { memcpy(out, o->st, sizeof(float) * (size_t)o->N); return BK_OK; }
+/* ------------------------------------------------------------------------
+ * Shared-tree multi-output step (BART(shape=(k, n)) without separate trees: the reference's tested multi-output mode,
+ * tests/test_bart.py:107-123 heteroscedastic Normal, :140-164 Categorical-softmax).  Every leaf carries K values;
+ * the particle weight is the full-model log-likelihood of the (K, N) value, which has no
+ * sufficient statistic: like the Bernoulli path, the rows of the two new leaves are revisited once the leaf values
+ * are known and contribute quantised per-row terms (bk_lik_q); sums are exact integers.
+ *   leaf value of output j: mean(sum_trees[j] over members)/m + z_j * leaf_sd[j], z_j = normal of the Philox block
+ *   whose `group` word is j; running leaf sd per output.
+ */
+static int64_t multi_row_term(const bko* o, int i, const float* leaf_vals) {
+  float f[BK_MAX_OUTPUTS];
+  for (int j = 0; j < o->K; ++j) f[j] = BK_FADD(o->noik[(size_t)j * (size_t)o->N + (size_t)i], leaf_vals[j]);
+  return (int64_t)bk_lik_q(o->s.likelihood, o->K, o->y[i], f);
+}
+
+static int grow_multi(bko* o, int tree, int round, int pi, bk_trace_rec* rec) {
+  o_particle* q = &o->parts[pi];
+  const int N = o->N, K = o->K;
+  if (rec) { rec->node = -1; rec->var = -1; }
+  if (q->q_head >= q->n_nodes) return 0;
+  int j = q->q_head++;
+  if (rec) rec->node = j;
+  o_node* nd = &q->nodes[j];
+  uint32_t S = o->s.seed, C = o->s.chain_base + (uint32_t)o->chain, D = (uint32_t)o->draw;
+  int depth = nd->depth;
+  double pl = depth < BK_MAX_DEPTH_TABLE ? o->p_leaf[depth] : 1.0;
+  double u1 = bk_u01(bk_rng(S, C, D, 0u, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_LEAF).v[0]);
+  if (!(u1 > pl)) return 0;
+  if (q->n_nodes + 2 > BK_MAX_NODES) return 0;
+  double u2 = bk_u01(bk_rng(S, C, D, 0u, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAR).v[0]);
+  int v = draw_variable(o, u2);
+  int n = nd->st.n;
+  if (n < 2) return 0;
+  uint32_t k = bk_index(bk_rng(S, C, D, 0u, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_U_VAL).v[0], (uint32_t)n);
+  const float* xc = o->X + (size_t)v * (size_t)N;
+  float s = 0.0f;
+  {
+    uint32_t seen = 0;
+    for (int i = 0; i < N; ++i) if (q->ids[i] == (uint8_t)j) { if (seen == k) { s = xc[i]; break; } seen++; }
+  }
+  int L = q->n_nodes, R = q->n_nodes + 1;
+  int32_t n_l = 0, n_r = 0;
+  int64_t sst_l[BK_MAX_OUTPUTS], sst_r[BK_MAX_OUTPUTS];
+  for (int jj = 0; jj < K; ++jj) { sst_l[jj] = 0; sst_r[jj] = 0; }
+  const int onehot = o->rules[v] == BK_RULE_ONEHOT;
+  for (int i = 0; i < N; ++i) {
+    if (q->ids[i] != (uint8_t)j) continue;
+    float x = xc[i];
+    int left = onehot ? (x == s) : (x <= s);
+    q->ids[i] = (uint8_t)(left ? L : R);
+    if (left) n_l += 1; else n_r += 1;
+    for (int jj = 0; jj < K; ++jj) {
+      int64_t b = (int64_t)o->qstk[(size_t)jj * (size_t)N + (size_t)i];
+      if (left) sst_l[jj] += b; else sst_r[jj] += b;
+    }
+  }
+  nd->var = v; nd->split = s; nd->left = L;
+  o_node* nl = &q->nodes[L]; o_node* nr = &q->nodes[R];
+  memset(nl, 0, sizeof(*nl)); memset(nr, 0, sizeof(*nr));
+  nl->var = -1; nl->left = -1; nl->depth = depth + 1; nl->st.n = n_l;
+  nr->var = -1; nr->left = -1; nr->depth = depth + 1; nr->st.n = n_r;
+  for (int jj = 0; jj < K; ++jj) {
+    double zl = bk_normal(bk_rng(S, C, D, (uint32_t)jj, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_LEFT));
+    double zr = bk_normal(bk_rng(S, C, D, (uint32_t)jj, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_RIGHT));
+    nl->vals[jj] = bk_leaf_value(n_l, sst_l[jj], o->inv_qm, zl, o->leaf_sdk[jj]);
+    nr->vals[jj] = bk_leaf_value(n_r, sst_r[jj], o->inv_qm, zr, o->leaf_sdk[jj]);
+  }
+  nl->value = nl->vals[0]; nr->value = nr->vals[0];
+  nl->st.sst = sst_l[0]; nr->st.sst = sst_r[0];
+  q->n_nodes += 2;
+  int64_t ll_l = 0, ll_r = 0;
+  for (int i = 0; i < N; ++i) {
+    if (q->ids[i] == (uint8_t)L) ll_l += multi_row_term(o, i, nl->vals);
+    else if (q->ids[i] == (uint8_t)R) ll_r += multi_row_term(o, i, nr->vals);
+  }
+  nl->ll = ll_l; nr->ll = ll_r;
+  q->llq = q->llq - nd->ll + ll_l + ll_r;
+  q->lw = bk_bern_loglik((double)q->llq);
+  o->bytes_touched += (long long)N * (6 + 4 * K) + (long long)N * (5 + 4 * K);
+  if (rec) { rec->var = v; rec->split = s; rec->n_left = n_l; rec->n_right = n_r; rec->val_left = nl->vals[0]; rec->val_right = nr->vals[0]; }
+  return 1;
+}
+
+static int bko_step_multi(bko* o, int tune, int32_t* vi_counts, bk_step_stats* stats) {
+  const int lik = o->s.likelihood;
+  if (lik != BK_LIK_NORMAL_HETERO && lik != BK_LIK_CATEGORICAL) return BK_ERR_UNSUPPORTED;
+  const int N = o->N, P = o->P, m = o->m, K = o->K;
+  bk_step_stats loc; memset(&loc, 0, sizeof(loc));
+  o->trace_len = 0;
+  if (vi_counts) memset(vi_counts, 0, sizeof(int32_t) * (size_t)o->p);
+  int T = tune ? o->s.batch_tune : o->s.batch_post;
+  int upper = o->lower + T < m ? o->lower + T : m;
+  uint32_t S = o->s.seed, C = o->s.chain_base + (uint32_t)o->chain, D = (uint32_t)o->draw;
+  float init_vals[BK_MAX_OUTPUTS];
+  for (int j = 0; j < K; ++j) init_vals[j] = o->s.init_leaf;
+  for (int t = o->lower; t < upper; ++t) {
+    o->iter += 1;
+    o_particle* old = &o->forest[t];
+    /* B1: linear predictors without tree t, fixed-point copies of the sums of trees, per-leaf terms of the old tree */
+    for (int k = 0; k < old->n_nodes; ++k) old->nodes[k].ll = 0;
+    int64_t tot_ll = 0, tot_sst0 = 0;
+    for (int i = 0; i < N; ++i) {
+      const o_node* on = &old->nodes[old->ids[i]];
+      for (int j = 0; j < K; ++j) {
+        const size_t ix = (size_t)j * (size_t)N + (size_t)i;
+        o->noik[ix] = BK_FSUB(o->stk[ix], on->vals[j]);
+        o->qstk[ix] = bk_quant(o->stk[ix], o->qscale);
+      }
+      tot_sst0 += (int64_t)o->qstk[i];
+      old->nodes[old->ids[i]].ll += multi_row_term(o, i, on->vals);
+      tot_ll += multi_row_term(o, i, init_vals);
+    }
+    /* B2: particles */
+    part_copy(&o->parts[0], old, N);
+    o->parts[0].q_head = o->parts[0].n_nodes;
+    {
+      int64_t llq = 0;
+      for (int k = 0; k < old->n_nodes; ++k) if (old->nodes[k].var < 0) llq += old->nodes[k].ll;
+      o->parts[0].gain = 0.0; o->parts[0].llq = llq; o->parts[0].lw = bk_bern_loglik((double)llq);
+    }
+    for (int q = 1; q < P; ++q) {
+      o_particle* pq = &o->parts[q];
+      pq->n_nodes = 1; pq->q_head = 0;
+      memset(&pq->nodes[0], 0, sizeof(o_node));
+      pq->nodes[0].var = -1; pq->nodes[0].left = -1;
+      pq->nodes[0].value = o->s.init_leaf;
+      for (int j = 0; j < K; ++j) pq->nodes[0].vals[j] = o->s.init_leaf;
+      pq->nodes[0].st.n = N; pq->nodes[0].st.sst = tot_sst0; pq->nodes[0].ll = tot_ll;
+      memset(pq->ids, 0, (size_t)N);
+      pq->gain = 0.0; pq->llq = tot_ll; pq->lw = bk_bern_loglik((double)tot_ll);
+    }
+    /* B3-B8: grow rounds */
+    int round = 0;
+    for (;; ++round) {
+      int tr0 = o->trace_len;
+      for (int q = 1; q < P; ++q) {
+        bk_trace_rec* rec = trace_slot(o);
+        if (rec) { rec->kind = 1; rec->tree = t; rec->round = round; rec->particle = q; rec->ancestor = -1; }
+        int was_root = o->parts[q].q_head == 0;
+        if (grow_multi(o, t, round, q, rec)) { loc.grow_events++; if (was_root) loc.grow_root++; }
+        if (rec) rec->log_w = o->parts[q].lw;
+      }
+      loc.rounds++;
+      int live = 0;
+      for (int q = 1; q < P; ++q) if (o->parts[q].q_head < o->parts[q].n_nodes) live = 1;
+      if (!live) break;
+      weight_sums(o->parts, 1, P - 1, o->w);
+      uint32_t u = bk_rng(S, C, D, 0u, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0];
+      systematic(o->w, P - 1, u, o->anc);
+      for (int q = 1; q < P; ++q) part_copy(&o->tmp[q], &o->parts[o->anc[q - 1] + 1], N);
+      for (int q = 1; q < P; ++q) {
+        o_particle sw = o->parts[q]; o->parts[q] = o->tmp[q]; o->tmp[q] = sw;
+        if (o->trace && tr0 + q - 1 < o->trace_cap) o->trace[tr0 + q - 1].ancestor = o->anc[q - 1] + 1;
+      }
+    }
+    /* B9: final selection and commit, per output */
+    weight_sums(o->parts, 0, P, o->w);
+    uint32_t uf = bk_rng(S, C, D, 0u, (uint32_t)t, 0xFFFFu, 0, BK_U_FINAL).v[0];
+    systematic(o->w, P, uf, o->anc);
+    uint32_t pick = bk_index(bk_rng(S, C, D, 0u, (uint32_t)t, 0xFFFFu, 0, BK_U_PICK).v[0], (uint32_t)P);
+    int win = o->anc[pick];
+    o_particle* nw = &o->parts[win];
+    if (tune) o->wf_count += 1;
+    for (int j = 0; j < K; ++j) {
+      int64_t sd_sum = 0;
+      for (int i = 0; i < N; ++i) {
+        const size_t ix = (size_t)j * (size_t)N + (size_t)i;
+        float newp = nw->nodes[nw->ids[i]].vals[j];
+        o->stk[ix] = BK_FADD(o->noik[ix], newp);
+        if (tune) {
+          float cnt = (float)o->wf_count;
+          float delta = BK_FSUB(newp, o->wf_meank[ix]);
+          float mean = BK_FADD(o->wf_meank[ix], BK_FDIV(delta, cnt));
+          float delta2 = BK_FSUB(newp, mean);
+          float m2 = BK_FFMA(delta, delta2, o->wf_m2k[ix]);
+          o->wf_meank[ix] = mean; o->wf_m2k[ix] = m2;
+          sd_sum += (int64_t)bk_quant(BK_FSQRT(BK_FDIV(m2, cnt)), o->qscale);
+        }
+      }
+      if (tune && o->iter > 2) o->leaf_sdk[j] = (float)BK_DDIV(BK_DMUL((double)sd_sum, o->inv_qscale), (double)N);
+    }
+    o->leaf_sd = o->leaf_sdk[0];
+    if (tune) {
+      if (o->iter > m) rebuild_cum(o);
+      for (int k = 0; k < nw->n_nodes; ++k) if (nw->nodes[k].var >= 0) o->alpha_vec[nw->nodes[k].var] = BK_DADD(o->alpha_vec[nw->nodes[k].var], 1.0);
+    } else if (vi_counts) {
+      for (int k = 0; k < nw->n_nodes; ++k) if (nw->nodes[k].var >= 0) vi_counts[nw->nodes[k].var] += 1;
+    }
+    bk_trace_rec* rec = trace_slot(o);
+    if (rec) { rec->kind = 2; rec->tree = t; rec->round = round; rec->particle = win; rec->node = nw->n_nodes; rec->var = -1; rec->ancestor = (int32_t)pick; rec->log_w = nw->lw; rec->aux = (double)o->leaf_sdk[K - 1]; }
+    part_copy(old, nw, N);
+    old->q_head = old->n_nodes;
+    loc.tree_updates++;
+  }
+  o->lower = upper < m ? upper : 0;
+  o->draw += 1;
+  loc.trace_len = o->trace_len; loc.leaf_sd = o->leaf_sdk[0]; loc.iter = o->iter;
+  if (o->trace && o->trace_len > o->trace_cap) loc.error_flags |= 1;
+  if (stats) *stats = loc;
+  return BK_OK;
+}
+
+/* out: [K][N] for shared-tree multi-output, [N] otherwise */
+int bko_sum_trees(const bko* o, float* out) {
+  if (o->K > 1) memcpy(out, o->stk, sizeof(float) * (size_t)o->K * (size_t)o->N);
+  else memcpy(out, o->st, sizeof(float) * (size_t)o->N);
+  return BK_OK;
+}
+
+/* leaf values of every output: vals [n_trees][255][K] (shared-tree multi-output) */
+int bko_export_leaf_values(const bko* o, float* vals) {
+  for (int t = 0; t < o->m; ++t)
+    for (int k = 0; k < BK_MAX_NODES; ++k)
+      for (int j = 0; j < o->K; ++j)
+        vals[((size_t)t * BK_MAX_NODES + k) * (size_t)o->K + j] =
+            (k < o->forest[t].n_nodes && o->forest[t].nodes[k].var < 0) ? (o->K > 1 ? o->forest[t].nodes[k].vals[j] : o->forest[t].nodes[k].value) : 0.0f;
+  return BK_OK;
+}
 
 int bko_read_trace(const bko* o, bk_trace_rec* out, int capacity) {
   int n = o->trace_len < o->trace_cap ? o->trace_len : o->trace_cap;

@@ -12,10 +12,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpgbart_b200.so")
 
-BK_ABI_VERSION = 2
+BK_ABI_VERSION = 3
 BK_MAX_NODES = 255
 BK_LIK_NORMAL = 0
 BK_LIK_BERNOULLI_LOGIT = 1
+BK_LIK_NORMAL_HETERO = 2
+BK_LIK_CATEGORICAL = 3
+BK_MAX_OUTPUTS = 7
 BK_RULE_CONTINUOUS = 0
 BK_RULE_ONEHOT = 1
 
@@ -40,6 +43,8 @@ class BkSettings(C.Structure):
         ("device", C.c_int32),
         ("trace_capacity", C.c_int32),
         ("n_groups", C.c_int32),
+        ("n_outputs", C.c_int32),
+        ("reserved0", C.c_int32),
         ("p_leaf", C.POINTER(C.c_double)),
         ("split_prior", C.POINTER(C.c_double)),
         ("split_rules", C.POINTER(C.c_int32)),
@@ -116,7 +121,7 @@ assert NODE_DTYPE.itemsize == C.sizeof(BkNode) == 24
 EXPORTS = (
     "bk_abi_version", "bk_last_error", "bk_padded_rows", "bk_query_bytes", "bk_create", "bk_destroy",
     "bk_step", "bk_step_launch", "bk_step_wait", "bk_stream", "bk_set_host_output", "bk_sum_trees_host", "bk_export_trees", "bk_read_trace", "bk_export_forest", "bk_export_leaf_ids",
-    "bk_set_history", "bk_history_batch", "bk_predict_history", "bk_pearson_r2",
+    "bk_set_history", "bk_history_batch", "bk_history_values", "bk_export_leaf_values", "bk_predict_history", "bk_pearson_r2",
 )
 
 _lib = None
@@ -155,8 +160,11 @@ def load():
     lib.bk_export_leaf_ids.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.bk_set_history.argtypes = [C.c_void_p, C.c_int]
     lib.bk_history_batch.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    lib.bk_history_values.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bk_export_leaf_values.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.bk_predict_history.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                       C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+                                       C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p]
     lib.bk_pearson_r2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     if lib.bk_abi_version() != BK_ABI_VERSION:
         raise RuntimeError("libpgbart_b200.so ABI version mismatch; rebuild")

@@ -25,8 +25,10 @@ class DeviceSampler:
         self.settings = settings
         self.device = torch.device("cuda", settings.device)
         G = max(1, settings.n_groups)
+        K = max(1, getattr(settings, "n_outputs", 1))                          # leaf values per leaf (shared trees)
         N, p, Cn = settings.n_rows, settings.n_cols, settings.n_chains * G   # Cn: chains x output groups
-        self.N, self.p, self.m, self.C, self.G = N, p, settings.n_trees, Cn, G
+        self.N, self.p, self.m, self.C, self.G, self.K = N, p, settings.n_trees, Cn, G, K
+        self.rows = Cn * K                                                     # rows of the sum-of-trees matrix
         self.ld = int(self.lib.bk_padded_rows(N))
         # host staging in pinned memory, column-major fp32 (bart.py:209-210 hands over f64 row-major)
         Xh = torch.zeros((p, self.ld), dtype=torch.float32).pin_memory()
@@ -40,7 +42,7 @@ class DeviceSampler:
         with torch.cuda.device(self.device):
             self.X_dev = Xh.to(self.device, non_blocking=True)
             self.y_dev = yh.to(self.device, non_blocking=True)
-            self.sum_trees_dev = torch.empty((Cn, self.ld), dtype=torch.float32, device=self.device)
+            self.sum_trees_dev = torch.empty((Cn * K, self.ld), dtype=torch.float32, device=self.device)
             self._cs = settings.to_c()
             nbytes = C.c_size_t()
             _cabi.check(self.lib.bk_query_bytes(C.byref(self._cs), C.byref(nbytes)), "bk_query_bytes")
@@ -101,10 +103,12 @@ class DeviceSampler:
         T = max(self.settings.batch_tune, self.settings.batch_post)
         self._hist_nn = np.zeros((self.C, T), dtype=np.int32)
         self._hist_nodes = np.zeros(self.C * T * _cabi.BK_MAX_NODES, dtype=_cabi.NODE_DTYPE)
+        self._hist_vals = np.zeros((self.C * T * _cabi.BK_MAX_NODES, self.K), dtype=np.float32) if self.K > 1 else None
         self.history_bytes_per_step = self.C * self.settings.batch_post * (_cabi.BK_MAX_NODES * 64 + 4)
 
     def history_batch(self):
-        """Trees rewritten by the last step waited for: (first, n_nodes [C][T], nodes back to back) or None."""
+        """Trees rewritten by the last step waited for: (first, n_nodes [C][T], nodes back to back[, leaf values
+        [nodes][K] for shared-tree multi-output]) or None."""
         first, total = C.c_int32(), C.c_int64()
         T = self.lib.bk_history_batch(self.h, C.byref(first), self._hist_nn.ctypes.data, self._hist_nodes.ctypes.data, C.byref(total))
         if T < 0:
@@ -112,13 +116,33 @@ class DeviceSampler:
         if T == 0:
             return None
         nn = self._hist_nn.reshape(-1)[: self.C * T].reshape(self.C, T).copy()
+        if self.K > 1:
+            rc = self.lib.bk_history_values(self.h, self._hist_vals.ctypes.data)
+            if rc < 0:
+                _cabi.check(rc, "bk_history_values")
+            return int(first.value), nn, self._hist_nodes[: int(total.value)].copy(), self._hist_vals[: int(total.value)].copy()
         return int(first.value), nn, self._hist_nodes[: int(total.value)].copy()
 
     def baseline(self):
         """Current forest of every (chain, group), compacted: list of (nodes, n_nodes) per virtual chain."""
         from .history import compact_forest
 
-        return [compact_forest(*self.forest(c)) for c in range(self.C)]
+        out = []
+        for c in range(self.C):
+            nodes, nn = self.forest(c)
+            flat, nn = compact_forest(nodes, nn)
+            if self.K > 1:      # shared-tree multi-output: the nodes' K leaf values travel beside them
+                vals = self.leaf_values(c)
+                out.append((flat, nn, np.concatenate([vals[t, : nn[t]] for t in range(self.m)])))
+            else:
+                out.append((flat, nn))
+        return out
+
+    def leaf_values(self, chain: int = 0) -> np.ndarray:
+        """[m][255][K] leaf values of every output of a chain's current forest."""
+        vals = np.zeros((self.m, _cabi.BK_MAX_NODES, self.K), dtype=np.float32)
+        _cabi.check(self.lib.bk_export_leaf_values(self.h, int(chain), vals.ctypes.data), "bk_export_leaf_values")
+        return vals
 
     def trees(self, chain: int, first: int, count: int):
         nodes = np.zeros((count, _cabi.BK_MAX_NODES), dtype=_cabi.NODE_DTYPE)
@@ -127,7 +151,7 @@ class DeviceSampler:
         return nodes, nn
 
     def sum_trees(self):
-        """torch view [C, N] of the current sum of trees (device)."""
+        """torch view [C*K, N] of the current sum of trees (device); rows are (chain, group or output)."""
         return self.sum_trees_dev[:, : self.N]
 
     def enable_host_output(self, enable: bool = True):
@@ -139,10 +163,10 @@ class DeviceSampler:
         """Host view [C, N] of the sum of trees after the last step: the library's pinned buffer when host output is
         enabled (no extra copy), otherwise a blocking D2H copy."""
         if getattr(self, "_host_enabled", False):   # (two pinned buffers alternate: ask for the last step's every time)
-            return np.ctypeslib.as_array(self.lib.bk_sum_trees_host(self.h), shape=(self.C, self.N))
+            return np.ctypeslib.as_array(self.lib.bk_sum_trees_host(self.h), shape=(self.rows, self.N))
         torch = self.torch
         if self._host_out is None:
-            self._host_out = torch.empty((self.C, self.N), dtype=torch.float32).pin_memory()
+            self._host_out = torch.empty((self.rows, self.N), dtype=torch.float32).pin_memory()
         self._host_out.copy_(self.sum_trees_dev[:, : self.N], non_blocking=False)
         return self._host_out.numpy()
 

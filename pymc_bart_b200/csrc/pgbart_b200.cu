@@ -208,6 +208,7 @@ struct CtlShared {
   int err_bits;
   unsigned long long r_slice[4];
   int warp_grow_root[4];
+  float job_vals[BK_MAX_PARTICLES][2][BK_MAX_OUTPUTS];   // shared-tree multi-output: leaf values of the LL jobs (staged, copied to global)
   int n_nan_fail, n_fail_root;   // slots whose split value could not be drawn (only members with a missing covariate)
   Params params_copy;            // for the out-of-line retry path (a reference to the kernel parameter would force a per-thread stack copy)
   // last value read from every accumulator word of accL: the workers only ever ADD (RED), the control CTA takes
@@ -237,6 +238,13 @@ struct GroupShared {
   float pro_vals[256];
   unsigned long long leaf_acc[256];      // per-leaf sum of the old tree's q(r) (Bernoulli: log-likelihood terms)
   unsigned long long tot_acc[8];
+  unsigned long long sd_acc[8];          // K > 1: running-sd sums per output of a SWEEP
+  // shared-tree multi-output scratch, one use per epoch kind (ROUND / LL / SWEEP): zeroed / staged at the start of each
+  union {
+    unsigned acck[BK_MAX_PARTICLES][BK_MAX_OUTPUTS][4];      // ROUND: (lo, hi) limbs of sum q(sum_trees[j]) for the left / right child
+    float job_vals[BK_MAX_PARTICLES][2][BK_MAX_OUTPUTS];     // LL: leaf values of the two new leaves of every job
+    float pro_vals_k[BK_MAX_OUTPUTS][256];                   // SWEEP: leaf values of the tree the prologue removes
+  } u;
   Work work;
   unsigned seen[64];            // last epoch of each chain this group has executed
   unsigned char fin[64];
@@ -260,6 +268,12 @@ __device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
 __device__ __forceinline__ int4 ld_ca_v4(const int4* p) {   // ordinary (weak, L1-cached) 16-byte load, never the .nc path
   int4 v;
   asm volatile("ld.global.ca.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ int ld_ca_s32(const int* p) {   // ordinary (weak, L1-cached) 4-byte load, never the .nc path
+  int v;
+  asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -557,7 +571,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
   for (int r = BK_WTID; r >= 0 && r < P.R; r += BK_WTHREADS) sh.row_cnt_node[r] = -1;
   for (int v = BK_WTID; v >= 0 && v < P.p && v < BK_CUM_SMEM; v += BK_WTHREADS) sh.cum_prior[v] = P.cum[(size_t)c * P.p + v];
   CTRL_SYNC();
-  const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
+  const bool bern = P.lik != BK_LIK_NORMAL;   // every family without a sufficient statistic: weights come from the LL epoch
   if (threadIdx.x == 0) {
     // Bernoulli: integer sum of the leaves' quantised log-likelihood terms (exact in double), plus the terms of the rows
     // the tree dropped for a missing covariate (they predict 0)
@@ -582,6 +596,7 @@ __device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* 
     const PRef S = pref(P, c, 0, q);
     DNode nd;
     nd.var = -1; nd.split = 0.0f; nd.left = -1; nd.depth = 0; nd.value = P.init_leaf; nd.aux[0] = 0; nd.aux[1] = 0; nd.aux[2] = 0;
+    for (int j = 1; j < P.K; ++j) set_node_val(nd, j, P.init_leaf);
     set_node_stats(nd, tot);
     S.node(0) = nd;
     S.h->n_nodes = 1; S.h->q_head = 0; S.h->row = BK_ROW_VIRTUAL;
@@ -657,6 +672,42 @@ __device__ __forceinline__ int nth_free_row(const CtlShared& sh, int R, int n) {
   return -1;
 }
 
+// Shared-tree multi-output: K leaf values per child from the per-output sums of both children (accK, zeroed here: the
+// release fence of the next publication orders the stores before the workers' next adds), K normals per child from the
+// Philox blocks whose `group` word is the output index; the values also go to the LL job of the slot.
+__device__ __noinline__ void finalize_multi(const Params& P, int c, ChainHot* hot, CtlShared& sh, const PRef& S, const Job& jb, int ji, int q,
+                                            DNode& parent, int n_left, int round, int t, int rbase) {
+  const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)hot->draw;
+  const int nn = S.h->n_nodes, n_right = parent.n - n_left;
+  const float split = sh.s_split[q];
+  parent.var = jb.var; parent.split = split; parent.left = nn;
+  S.node(jb.node) = parent;
+  DNode nl; memset(&nl, 0, sizeof(nl));
+  nl.var = -1; nl.left = -1; nl.depth = parent.depth + 1;
+  DNode nr = nl;
+  nl.n = n_left; nr.n = n_right;
+  unsigned long long* ak = P.accK + ((size_t)c * P.P + q) * P.K * 2;
+  for (int j = 0; j < P.K; ++j) {
+    const long long sst_l = (long long)__ldcg(ak + 2 * j), sst_r = (long long)__ldcg(ak + 2 * j + 1);
+    ak[2 * j] = 0ull; ak[2 * j + 1] = 0ull;
+    const double zl = bk_normal(bk_rng(S0, C0, D0, (uint32_t)j, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_LEFT));
+    const double zr = bk_normal(bk_rng(S0, C0, D0, (uint32_t)j, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_Z_RIGHT));
+    const float vl = bk_leaf_value(n_left, sst_l, P.inv_qm, zl, hot->leaf_sdk[j]);
+    const float vr = bk_leaf_value(n_right, sst_r, P.inv_qm, zr, hot->leaf_sdk[j]);
+    set_node_val(nl, j, vl); set_node_val(nr, j, vr);
+    sh.job_vals[ji][0][j] = vl; sh.job_vals[ji][1][j] = vr;
+    if (j == 0) { nl.sst = sst_l; nr.sst = sst_r; }
+  }
+  S.node(nn) = nl; S.node(nn + 1) = nr;
+  S.h->n_nodes = nn + 2;
+  Job lj = jb;   // the partition job becomes the LL job of the same particle (same list position)
+  lj.kind = BK_JOB_LL; lj.src_row = jb.dst_row;
+  sh.jobs[ji] = lj;
+  S.h->row = jb.dst_row;
+  bk_trace_rec* rec = trace_at(P, c, rbase + q - 1);
+  if (rec) { rec->var = jb.var; rec->split = split; rec->n_left = n_left; rec->n_right = n_right; rec->val_left = nl.value; rec->val_right = nr.value; }
+}
+
 // apply the statistics of the finished ROUND to slot q's particle if it grew (thread q = BK_WTID); no barrier inside
 __device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* hot, CtlShared& sh, int buf, int round, int t, int rbase) {
   const int q = BK_WTID;
@@ -664,7 +715,7 @@ __device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* h
   const int ji = sh.s_jobidx[q];
   if (ji < 0) return;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
-  const bool bern = P.lik == BK_LIK_BERNOULLI_LOGIT;
+  const bool bern = P.lik != BK_LIK_NORMAL;   // every family without a sufficient statistic: weights come from the LL epoch
   const Job jb = sh.jobs[ji];   // the job list staged by open_round() is still in shared memory
   const PRef S = pref(P, c, buf, q);
   unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
@@ -678,6 +729,7 @@ __device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* h
     prev[BK_ACC_N] = a_n; prev[BK_ACC_SST] = a_st; prev[BK_ACC_SR] = a_sr;
   }
   DNode parent = S.node(jb.node);
+  if (P.K > 1) { finalize_multi(sh.params_copy, c, hot, sh, S, jb, ji, q, parent, sl.n, round, t, rbase); return; }
   const bk_stats sp = node_stats(parent);
   bk_stats sr = bk_stats_sub(sp, sl);
   if (BK_MISSING_ENABLED && jb.pad[1]) {   // the split column has missing values: the rows dropped from the node count for neither child
@@ -965,6 +1017,13 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
     const float of = k < BK_MAX_NODES ? __ldcg(&ft[k].value) : 0.0f;
     ctl->old_vals[k] = (k < old_nn && ov < 0) ? of : 0.0f;
     ctl->new_vals[k] = (k < new_nn && W.node(k).var < 0) ? W.node(k).value : 0.0f;
+    if (P.K > 1) {
+      for (int j = 0; j < P.K; ++j) {
+        const float ofj = (k < BK_MAX_NODES && j > 0) ? __ldcg(reinterpret_cast<const float*>(ft[k].aux) + (j - 1)) : of;
+        ctl->old_vals_k[j][k] = (k < old_nn && ov < 0) ? ofj : 0.0f;
+        ctl->new_vals_k[j][k] = (k < new_nn && W.node(k).var < 0) ? node_val(W.node(k), j) : 0.0f;
+      }
+    }
   }
   CTRL_SYNC();
   {
@@ -1065,13 +1124,22 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
         if (hot->tune) {
           hot->wf_count = sj.wf_count;
           if (hot->iter > 2) {
-            long long sd_sum = (long long)__ldcg(P.acc0 + (size_t)c * BK_ACC0_WORDS + (size_t)256 * BK_ACC0_STRIDE);
-            hot->leaf_sd = (float)BK_DDIV(BK_DMUL((double)sd_sum, P.inv_qscale), (double)P.N);
+            if (P.K > 1) {
+              for (int j = 0; j < P.K; ++j) {
+                const long long sd_j = (long long)__ldcg(P.acc_sd + (size_t)c * 8 + j);
+                hot->leaf_sdk[j] = (float)BK_DDIV(BK_DMUL((double)sd_j, P.inv_qscale), (double)P.N);
+              }
+              hot->leaf_sd = hot->leaf_sdk[0];
+            } else {
+              long long sd_sum = (long long)__ldcg(P.acc0 + (size_t)c * BK_ACC0_WORDS + (size_t)256 * BK_ACC0_STRIDE);
+              hot->leaf_sd = (float)BK_DDIV(BK_DMUL((double)sd_sum, P.inv_qscale), (double)P.N);
+            }
           }
+          if (P.K > 1) for (int j = 0; j < 8; ++j) P.acc_sd[(size_t)c * 8 + j] = 0ull;   // (ordered before the next SWEEP by the publication's release fence)
         }
         hot->c_tree_updates += 1;
         bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base);
-        if (rec) rec->aux = (double)hot->leaf_sd;
+        if (rec) rec->aux = (double)(P.K > 1 ? hot->leaf_sdk[P.K - 1] : hot->leaf_sd);
         hot->trace_round_base += 1;
       }
       if (sj.do_prologue) {
@@ -1100,12 +1168,14 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     finalize_own(P, c, hot, sh, hot->buf, hot->round, hot->cur_tree, hot->trace_round_base);
     TSUB(0);
     MARK(121);
-    if (P.lik == BK_LIK_BERNOULLI_LOGIT && hot->n_grow > 0) {
+    if (P.lik != BK_LIK_NORMAL && hot->n_grow > 0) {
       // leaf values are known now: publish the LL jobs (the first n_grow list entries) and wait for their sums
       CTRL_SYNC();
       const int ng = hot->n_grow;
       const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
       for (int i = BK_WTID; i >= 0 && i < ng * 3; i += BK_WTHREADS) reinterpret_cast<uint4*>(ctl->jobs[0])[i] = s4[i];
+      if (P.K > 1)
+        for (int i = BK_WTID; i >= 0 && i < ng * 2 * BK_MAX_OUTPUTS; i += BK_WTHREADS) (&ctl->job_vals[0][0][0])[i] = (&sh.job_vals[0][0][0])[i];
       if (threadIdx.x == 0) { hot->n_jobs = ng; hot->cmd = BK_CMD_LL; hot->stage_next = BK_ST_WAIT_LL; }
       CTRL_SYNC();
       return;
@@ -1233,14 +1303,20 @@ __device__ __forceinline__ unsigned long long take_stat(unsigned* L, int k) {
 
 // MISSING: X holds NaNs somewhere (Params::has_nan).  A separate instantiation so that the path without missing values
 // keeps its register allocation (the extra masks and sums cost the C5 step 12 % when compiled into one body).
-template <bool MISSING>
+// MULTI: shared-tree multi-output (Params::K > 1): per job the sums of q(sum_trees[j]) of BOTH children for every
+// output j go to `acck` (no parent statistics are kept per output); no Gaussian residual statistics (the weight comes
+// from the LL epoch).
+template <bool MISSING, bool MULTI>
 __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
-                                           unsigned* __restrict__ sacc) {
+                                           unsigned* __restrict__ sacc, unsigned (*__restrict__ acck)[BK_MAX_OUTPUTS][4]) {
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
-  const bool gauss = P.lik == BK_LIK_NORMAL;
+  const bool gauss = !MULTI && P.lik == BK_LIK_NORMAL;
   int q_r[8], q_s[8];
-  {
+  if (MULTI) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { q_r[e] = 0; q_s[e] = 0; }
+  } else {
     const int4* a = reinterpret_cast<const int4*>(P.qr + (size_t)c * P.Npad + base);
     const int4* b = reinterpret_cast<const int4*>(P.qst + (size_t)c * P.Npad + base);
     // L1-cached on purpose: the warps of this CTA share a few tiles (fresh after the epoch's acquire fence)
@@ -1346,7 +1422,31 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
         }
       }
       __stcg(reinterpret_cast<uint2*>(const_cast<uint8_t*>(rows_c) + (size_t)dst_row * P.Npad), make_uint2(n0, n1));
-      if (__any_sync(0xffffffffu, (lm0 | lm1) != 0u)) {
+      if (MULTI) {
+        if (__any_sync(0xffffffffu, (mem0 | mem1) != 0u)) {
+          const unsigned rm0 = mem0 & ~lm0, rm1 = mem1 & ~lm1;     // rows of the right child
+          const unsigned cl = (unsigned)(__popc(lm0) + __popc(lm1)) >> 3;
+          const unsigned nl_tot = __reduce_add_sync(0xffffffffu, cl);
+          if (lane == 0 && nl_tot) atomicAdd(sacc + ji * BK_LIMBS + BK_LIMB_N, nl_tot);
+          for (int j = 0; j < P.K; ++j) {
+            const int4* b = reinterpret_cast<const int4*>(P.qst + ((size_t)c * P.K + j) * P.Npad + base);
+            const int4 b0 = ld_ca_v4(b), b1 = ld_ca_v4(b + 1);
+            const int qs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            int sl_a = 0, sr_a = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              sl_a += (qs[e] & (int)BK_ROWMASK(lm0, e)) + (qs[4 + e] & (int)BK_ROWMASK(lm1, e));
+              sr_a += (qs[e] & (int)BK_ROWMASK(rm0, e)) + (qs[4 + e] & (int)BK_ROWMASK(rm1, e));
+            }
+            // (8 rows of |q| < 2^29 fit a 32-bit lane sum; limbs as in the single-output path)
+            const unsigned l_lo = __reduce_add_sync(0xffffffffu, (unsigned)sl_a & 0xFFFFu), r_lo = __reduce_add_sync(0xffffffffu, (unsigned)sr_a & 0xFFFFu);
+            const int l_hi = __reduce_add_sync(0xffffffffu, sl_a >> 16), r_hi = __reduce_add_sync(0xffffffffu, sr_a >> 16);
+            unsigned v = l_lo;
+            v = lane == 1 ? (unsigned)l_hi : v; v = lane == 2 ? r_lo : v; v = lane == 3 ? (unsigned)r_hi : v;
+            if (lane < 4) atomicAdd(&acck[ji][j][lane], v);
+          }
+        }
+      } else if (__any_sync(0xffffffffu, (lm0 | lm1) != 0u)) {
         // masked per-lane sums: 4 rows fit 32 bits (|q| < 2^29)
         int s_a = 0, s_b = 0, r_a = 0, r_b = 0;
 #pragma unroll
@@ -1427,6 +1527,50 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
       else if (id == left_id + 1u) { s_r += (long long)bk_bern_q(yv[e], noi[e], vr); any = true; }
     }
     if (__any_sync(0xffffffffu, any)) {   // |s| <= 8 * 2^29 per lane: (hi, lo) limbs as in round_unit
+      const unsigned l_lo = __reduce_add_sync(0xffffffffu, (unsigned)s_l & 0xFFFFu), r_lo = __reduce_add_sync(0xffffffffu, (unsigned)s_r & 0xFFFFu);
+      const int l_hi = __reduce_add_sync(0xffffffffu, (int)(s_l >> 16)), r_hi = __reduce_add_sync(0xffffffffu, (int)(s_r >> 16));
+      unsigned v = l_lo;
+      v = lane == 1 ? (unsigned)l_hi : v;
+      v = lane == 2 ? r_lo : v;
+      v = lane == 3 ? (unsigned)r_hi : v;
+      if (lane < 4) atomicAdd(sacc + ji * BK_LIMBS + BK_LIMB_LLL_LO + lane, v);
+    }
+  }
+}
+
+// Shared-tree multi-output: the rows of the two new leaves contribute bk_lik_q(y, noi[.] + leaf values[.]); the K
+// linear predictors without the tree are read per job (L1 hits after the first job of the tile), y stays in registers.
+__device__ __forceinline__ void ll_unit_multi(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
+                                              unsigned* __restrict__ sacc, const float (*__restrict__ jvals)[2][BK_MAX_OUTPUTS]) {
+  const int lane = threadIdx.x & 31;
+  const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
+  float yv[8];
+  {
+    const float4* b = reinterpret_cast<const float4*>(P.y + base);
+    const float4 b0 = __ldg(b), b1 = __ldg(b + 1);
+    yv[0] = b0.x; yv[1] = b0.y; yv[2] = b0.z; yv[3] = b0.w; yv[4] = b1.x; yv[5] = b1.y; yv[6] = b1.z; yv[7] = b1.w;
+  }
+  for (int ji = job_lo; ji < job_hi; ++ji) {
+    const int4* jp = reinterpret_cast<const int4*>(&sjobs[ji]);
+    const int4 j0 = jp[0], j1 = jp[1];
+    if (j0.x != BK_JOB_LL) continue;
+    const int src_row = j0.z;
+    const unsigned left_id = (unsigned)j1.w;
+    const unsigned long long ids = __ldcg(reinterpret_cast<const unsigned long long*>(P.rows + ((size_t)c * P.R + src_row) * P.Npad + base));
+    long long s_l = 0, s_r = 0;
+    bool any = false;
+    for (int e = 0; e < 8; ++e) {
+      const unsigned id = (unsigned)(ids >> (8 * e)) & 255u;
+      const int side = id == left_id ? 0 : (id == left_id + 1u ? 1 : -1);
+      if (side < 0) continue;
+      float f[BK_MAX_OUTPUTS];
+      for (int j = 0; j < P.K; ++j)
+        f[j] = BK_FADD(__int_as_float(ld_ca_s32(P.qr + ((size_t)c * P.K + j) * P.Npad + base + e)), jvals[ji][side][j]);
+      const long long q = (long long)bk_lik_q(P.lik, P.K, yv[e], f);
+      if (side == 0) s_l += q; else s_r += q;
+      any = true;
+    }
+    if (__any_sync(0xffffffffu, any)) {
       const unsigned l_lo = __reduce_add_sync(0xffffffffu, (unsigned)s_l & 0xFFFFu), r_lo = __reduce_add_sync(0xffffffffu, (unsigned)s_r & 0xFFFFu);
       const int l_hi = __reduce_add_sync(0xffffffffu, (int)(s_l >> 16)), r_hi = __reduce_add_sync(0xffffffffu, (int)(s_r >> 16));
       unsigned v = l_lo;
@@ -1593,6 +1737,160 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
   GROUP_SYNC(g);
 }
 
+// Shared-tree multi-output SWEEP (Params::K > 1): same fusion as sweep_unit — commit of tree A and prologue of tree
+// B — looped over the K outputs (the leaf-value tables of one output at a time in shared memory), then ONE pass of
+// per-row log-likelihood terms with all K linear predictors: the old tree's leaf of the row (per-leaf sums, particle 0)
+// and the root-only stump (total).
+__device__ void sweep_unit_multi(const Params& P, int c, int ctile, GroupShared& sh, const int g, const int tid) {
+  const ChainCtl* ctl = P.ctl + c;
+  const int4 s0 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep));
+  const int4 s1 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep) + 1);
+  const int do_commit = s0.x, commit_tree = s0.y, new_row = s0.z, do_wf = s0.w;
+  const int do_pro = s1.x, pro_tree = s1.y, wf_count = s1.z;
+  const int K = P.K;
+  for (int idx = tid; idx < K * 256; idx += BK_GROUP_THREADS) {
+    const int j = idx >> 8, k = idx & 255;
+    float pv = 0.0f;
+    if (do_pro && k < 255) {
+      const DNode* nd = P.forest + ((size_t)c * P.m + pro_tree) * BK_MAX_NODES + k;
+      const int nn = __ldcg(P.forest_nn + (size_t)c * P.m + pro_tree);
+      const int var = __ldcg(&nd->var);
+      const float val = j == 0 ? __ldcg(&nd->value) : __ldcg(reinterpret_cast<const float*>(nd->aux) + (j - 1));
+      pv = (k < nn && var < 0) ? val : 0.0f;
+    }
+    sh.u.pro_vals_k[j][k] = pv;
+  }
+  for (int k = tid; k < 256; k += BK_GROUP_THREADS) sh.leaf_acc[k] = 0ull;
+  if (tid < 8) { sh.tot_acc[tid] = 0ull; sh.sd_acc[tid] = 0ull; }
+  GROUP_SYNC(g);
+
+  const size_t base = (size_t)ctile * BK_COMMIT_TILE + (size_t)tid * 4;
+  const bool in = base < (size_t)P.Npad;
+  unsigned oid4 = 0u, nid4 = 0u, pid4 = 0xFFFFFFFFu;
+  if (in && do_commit) {
+    uint8_t* idp = P.ids_tree + ((size_t)c * P.m + commit_tree) * P.Npad + base;
+    oid4 = __ldcg(reinterpret_cast<const unsigned*>(idp));
+    if (new_row == BK_ROW_FOREST) nid4 = oid4;
+    else if (new_row == BK_ROW_VIRTUAL) {
+      nid4 = 0u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (base + e >= (size_t)P.N) nid4 |= 0xFFu << (8 * e);
+    } else nid4 = __ldcg(reinterpret_cast<const unsigned*>(P.rows + ((size_t)c * P.R + new_row) * P.Npad + base));
+  }
+  if (in && do_pro) pid4 = __ldcg(reinterpret_cast<const unsigned*>(P.ids_tree + ((size_t)c * P.m + pro_tree) * P.Npad + base));
+  float noi_k[BK_MAX_OUTPUTS][4];
+  long long t_sst0 = 0;
+  for (int j = 0; j < K; ++j) {
+    // this output's tables of the committed tree
+    for (int k = tid; k < 256; k += BK_GROUP_THREADS) {
+      sh.old_vals[k] = do_commit ? __ldcg(&ctl->old_vals_k[j][k]) : 0.0f;
+      sh.new_vals[k] = do_commit ? __ldcg(&ctl->new_vals_k[j][k]) : 0.0f;
+    }
+    GROUP_SYNC(g);
+    long long t_sd = 0;
+    if (in) {
+      float* stp = P.st + ((size_t)c * K + j) * P.Npad + base;
+      const float4 st4 = __ldcg(reinterpret_cast<const float4*>(stp));
+      float stv[4] = {st4.x, st4.y, st4.z, st4.w};
+      if (do_commit) {
+        float4 mean4 = make_float4(0.f, 0.f, 0.f, 0.f), m24 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* mp = P.wf_mean + ((size_t)c * K + j) * P.Npad + base;
+        float* m2p = P.wf_m2 + ((size_t)c * K + j) * P.Npad + base;
+        if (do_wf) { mean4 = __ldcg(reinterpret_cast<const float4*>(mp)); m24 = __ldcg(reinterpret_cast<const float4*>(m2p)); }
+        float mean[4] = {mean4.x, mean4.y, mean4.z, mean4.w}, m2[4] = {m24.x, m24.y, m24.z, m24.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned oid = (oid4 >> (8 * e)) & 255u, nid = (nid4 >> (8 * e)) & 255u;
+          const float oldp = sh.old_vals[oid], newp = sh.new_vals[nid];
+          const float noi = BK_FSUB(stv[e], oldp);
+          stv[e] = BK_FADD(noi, newp);
+          if (do_wf && base + e < (size_t)P.N) {
+            const float cntf = (float)wf_count;
+            const float delta = BK_FSUB(newp, mean[e]);
+            const float mn = BK_FADD(mean[e], BK_FDIV(delta, cntf));
+            const float delta2 = BK_FSUB(newp, mn);
+            const float mm2 = BK_FFMA(delta, delta2, m2[e]);
+            mean[e] = mn; m2[e] = mm2;
+            t_sd += (long long)bk_quant(BK_FSQRT(BK_FDIV(mm2, cntf)), P.qscale);
+          }
+        }
+        __stcg(reinterpret_cast<float4*>(stp), make_float4(stv[0], stv[1], stv[2], stv[3]));
+        if (do_wf) {
+          __stcg(reinterpret_cast<float4*>(mp), make_float4(mean[0], mean[1], mean[2], mean[3]));
+          __stcg(reinterpret_cast<float4*>(m2p), make_float4(m2[0], m2[1], m2[2], m2[3]));
+        }
+      }
+      if (do_pro) {
+        int qrv[4], qsv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const unsigned pid = (pid4 >> (8 * e)) & 255u;
+          const float noi = BK_FSUB(stv[e], sh.u.pro_vals_k[j][pid]);
+          const bool real = base + e < (size_t)P.N;
+          noi_k[j][e] = noi;
+          qrv[e] = real ? __float_as_int(noi) : 0;
+          qsv[e] = real ? bk_quant(stv[e], P.qscale) : 0;
+          if (j == 0 && real) t_sst0 += qsv[e];
+        }
+        __stcg(reinterpret_cast<int4*>(P.qr + ((size_t)c * K + j) * P.Npad + base), make_int4(qrv[0], qrv[1], qrv[2], qrv[3]));
+        __stcg(reinterpret_cast<int4*>(P.qst + ((size_t)c * K + j) * P.Npad + base), make_int4(qsv[0], qsv[1], qsv[2], qsv[3]));
+      }
+    }
+    if (do_commit && do_wf) {
+      const unsigned long long v = warp_sum_u64((unsigned long long)t_sd);
+      if ((tid & 31) == 0 && v) atomicAdd(&sh.sd_acc[j], v);
+    }
+    GROUP_SYNC(g);   // (the tables are overwritten for the next output)
+  }
+  if (in && do_commit && new_row != BK_ROW_FOREST)
+    __stcg(reinterpret_cast<unsigned*>(P.ids_tree + ((size_t)c * P.m + commit_tree) * P.Npad + base), nid4);
+  // per-row log-likelihood terms with all K outputs
+  long long t_sr = 0;
+  int pro_q[4] = {0, 0, 0, 0};
+  if (in && do_pro) {
+    const float4 y4 = __ldg(reinterpret_cast<const float4*>(P.y + base));
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    for (int e = 0; e < 4; ++e) {
+      if (base + e >= (size_t)P.N) continue;
+      const unsigned pid = (pid4 >> (8 * e)) & 255u;
+      float f_old[BK_MAX_OUTPUTS], f_init[BK_MAX_OUTPUTS];
+      for (int j = 0; j < K; ++j) {
+        f_old[j] = BK_FADD(noi_k[j][e], sh.u.pro_vals_k[j][pid]);
+        f_init[j] = BK_FADD(noi_k[j][e], P.init_leaf);
+      }
+      pro_q[e] = bk_lik_q(P.lik, K, yv[e], f_old);
+      t_sr += (long long)bk_lik_q(P.lik, K, yv[e], f_init);
+    }
+  }
+  if (do_pro) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned pid = (pid4 >> (8 * e)) & 255u;
+      const bool ok = in && pid != BK_LIMBO && base + e < (size_t)P.N;
+      const unsigned key = ok ? pid : 0x100u;
+      const unsigned grp = __match_any_sync(0xffffffffu, key);
+      const int a = ok ? pro_q[e] : 0;
+      const unsigned r_lo = __reduce_add_sync(grp, (unsigned)a & 0xFFFFu);
+      const int r_hi = __reduce_add_sync(grp, a >> 16);
+      if (ok && (int)(tid & 31) == __ffs(grp) - 1) atomicAdd(&sh.leaf_acc[pid], (unsigned long long)((long long)r_hi * 65536ll + (long long)r_lo));
+    }
+    const unsigned long long v0 = warp_sum_u64((unsigned long long)t_sr), v3 = warp_sum_u64((unsigned long long)t_sst0);
+    if ((tid & 31) == 0) { atomicAdd(&sh.tot_acc[0], v0); atomicAdd(&sh.tot_acc[3], v3); }
+  }
+  GROUP_SYNC(g);
+  unsigned long long* a0 = P.acc0 + (size_t)c * BK_ACC0_WORDS;
+  if (do_pro) {
+    for (int k = tid; k < 255; k += BK_GROUP_THREADS) {
+      const unsigned long long v = sh.leaf_acc[k];
+      if (v) red_add_u64(a0 + (size_t)k * BK_ACC0_STRIDE, v);
+    }
+    if (tid == 0) { unsigned long long v = sh.tot_acc[0]; if (v) red_add_u64(a0 + (size_t)255 * BK_ACC0_STRIDE + 0, v); }
+    if (tid == 1) { unsigned long long v = sh.tot_acc[3]; if (v) red_add_u64(a0 + (size_t)255 * BK_ACC0_STRIDE + 3, v); }
+  }
+  if (do_commit && do_wf && tid < K) { const unsigned long long v = sh.sd_acc[tid]; if (v) red_add_u64(P.acc_sd + (size_t)c * 8 + tid, v); }
+  GROUP_SYNC(g);
+}
+
 // ------------------------------------------------------------------ dataflow scheduling
 // Which groups serve chain c: with C >= BK_NGROUPS chains, group g serves the chains c = g (mod BK_NGROUPS); with
 // fewer chains, group g serves chain g mod C, so chain c has servers_of(c) groups per worker CTA.
@@ -1709,6 +2007,16 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
         const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[wk.chain].jobs[(w * BK_NGROUPS + g) % BK_JOB_COPIES]);   // readers spread over the copies
         uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
         for (int i = tid; i < wk.njobs * 3; i += BK_GROUP_THREADS) d4[i] = __ldcg(g4 + i);
+        if (P.K > 1) {   // shared-tree multi-output: per-output accumulators (ROUND) / the jobs' leaf values (LL)
+          if (wk.cmd == BK_CMD_ROUND) {
+            unsigned* z = &sh.u.acck[0][0][0];
+            for (int i = tid; i < wk.njobs * BK_MAX_OUTPUTS * 4; i += BK_GROUP_THREADS) z[i] = 0u;
+          } else {
+            const float* gv = &P.ctl[wk.chain].job_vals[0][0][0];
+            float* dv = &sh.u.job_vals[0][0][0];
+            for (int i = tid; i < wk.njobs * 2 * BK_MAX_OUTPUTS; i += BK_GROUP_THREADS) dv[i] = __ldcg(gv + i);
+          }
+        }
       }
       GROUP_SYNC(g);
       const Job* jobs = sh.jobs;
@@ -1720,9 +2028,11 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
         const unsigned tile = lo / (unsigned)wk.njobs, j0 = lo - tile * (unsigned)wk.njobs;
         const unsigned seg = (unsigned)wk.njobs - j0 < hi - lo ? (unsigned)wk.njobs - j0 : hi - lo;
         if (wk.cmd == BK_CMD_ROUND) {
-          if (BK_MISSING_ENABLED && P.has_nan) round_unit<true>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
-          else round_unit<false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
+          if (P.K > 1) round_unit<false, true>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.acck);
+          else if (BK_MISSING_ENABLED && P.has_nan) round_unit<true, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr);
+          else round_unit<false, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr);
         }
+        else if (P.K > 1) ll_unit_multi(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.job_vals);
         else ll_unit(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
         lo += seg;
       }
@@ -1733,8 +2043,19 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
         const unsigned long long v = take_stat(sh.acc + ji * BK_LIMBS, k);
         if (v) red_add_u64(P.accL + ((size_t)wk.chain * P.P + jobs[ji].slot) * BK_ACC_STRIDE + k, v);
       }
+      if (P.K > 1 && wk.cmd == BK_CMD_ROUND) {   // per-output sums of both children: (lo, hi) limbs -> one global atomic each
+        for (int i = tid; i < wk.njobs * P.K * 2; i += BK_GROUP_THREADS) {
+          const int ji = i / (P.K * 2), j = (i / 2) % P.K, side = i & 1;
+          const unsigned lo = sh.u.acck[ji][j][2 * side], hi = sh.u.acck[ji][j][2 * side + 1];
+          const long long v = (long long)(int)hi * 65536ll + (long long)lo;
+          if (v) red_add_u64(P.accK + (((size_t)wk.chain * P.P + jobs[ji].slot) * P.K + j) * 2 + side, (unsigned long long)v);
+        }
+      }
     } else {  // BK_CMD_SWEEP: group-wide row tiles, round robin over all serving groups
-      for (unsigned u = wk.lo; u < (unsigned)wk.total; u += wk.hi) sweep_unit(P, wk.chain, (int)u, sh, g, tid);
+      for (unsigned u = wk.lo; u < (unsigned)wk.total; u += wk.hi) {
+        if (P.K > 1) sweep_unit_multi(P, wk.chain, (int)u, sh, g, tid);
+        else sweep_unit(P, wk.chain, (int)u, sh, g, tid);
+      }
     }
     GROUP_SYNC(g);   // every warp's stores are ordered before the release below
     if (wk.cmd == BK_CMD_ROUND && g == 0) WDBG(2, t_pub);
@@ -1863,11 +2184,13 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
                                    const double* __restrict__ split_prior) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nth = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = tid; i < (size_t)P.C * P.Npad; i += nth) {
+  for (size_t i = tid; i < (size_t)P.C * P.K * P.Npad; i += nth) {
     size_t r = i % P.Npad;
     P.st[i] = r < (size_t)P.N ? init_sum : 0.0f;
     P.wf_mean[i] = 0.0f; P.wf_m2[i] = 0.0f; P.qr[i] = 0; P.qst[i] = 0;
   }
+  for (size_t i = tid; i < (size_t)P.C * P.P * P.K * 2; i += nth) P.accK[i] = 0ull;
+  for (size_t i = tid; i < (size_t)P.C * 8; i += nth) P.acc_sd[i] = 0ull;
   for (size_t i = tid; i < (size_t)P.C * P.m * P.Npad; i += nth) {
     size_t r = i % P.Npad;
     P.ids_tree[i] = r < (size_t)P.N ? 0 : BK_LIMBO;
@@ -1880,13 +2203,15 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
     P.forest_nn[i] = 1;
     DNode nd; memset(&nd, 0, sizeof(nd));
     nd.var = -1; nd.left = -1; nd.value = P.init_leaf; nd.n = P.N;
+    for (int j = 1; j < P.K; ++j) set_node_val(nd, j, P.init_leaf);
     P.forest[i * BK_MAX_NODES] = nd;
   }
   for (size_t i = tid; i < (size_t)P.C * P.p; i += nth) { P.alpha_vec[i] = split_prior[i % P.p]; P.vi[i] = 0; }
   for (size_t c = tid; c < (size_t)P.C; c += nth) {
     ChainCtl* ctl = P.ctl + c;
     ctl->hot.tune = 1; ctl->hot.sigma = 1.0f; ctl->hot.iter = 0; ctl->hot.lower = 0; ctl->hot.draw = 0; ctl->hot.wf_count = 0;
-    ctl->hot.leaf_sd = leaf_sd_init; ctl->hot.stage = BK_ST_DONE; ctl->hot.cmd = BK_CMD_DONE; ctl->hot.n_jobs = 0;
+    ctl->hot.leaf_sd = leaf_sd_init; ctl->hot.stage = BK_ST_DONE;
+    for (int j = 0; j < BK_MAX_OUTPUTS; ++j) ctl->hot.leaf_sdk[j] = leaf_sd_init; ctl->hot.cmd = BK_CMD_DONE; ctl->hot.n_jobs = 0;
     ctl->hot.c_err = 0; ctl->hot.trace_round_base = 0;
     memset(&P.stats[c], 0, sizeof(bk_step_stats));
   }
@@ -1964,7 +2289,7 @@ struct bk_handle_s {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-  size_t qr, qst, ids_tree, rows, rowcnt, coarse, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, alpha_vec, cum,
+  size_t qr, qst, ids_tree, rows, rowcnt, coarse, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, accK, acc_sd, alpha_vec, cum,
       p_leaf, rules, col_nan, vi, stats, trace, sync, abort_flag, split_prior, total;
   int Npad, ntiles, R, nb;
 };
@@ -1977,30 +2302,37 @@ static int make_layout(const bk_settings* s, Layout* L) {
   if (s->n_groups > 0xFFFF) { set_err("n_groups must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
   if (s->n_trees > 65535) { set_err("n_trees must fit the 16-bit Philox counter field"); return BK_ERR_ARG; }
   if (s->n_rows > (1 << 25)) { set_err("n_rows above 2^25 would overflow the 32-bit partial-sum limbs of a worker group"); return BK_ERR_ARG; }
-  if (s->likelihood != BK_LIK_NORMAL && s->likelihood != BK_LIK_BERNOULLI_LOGIT) { set_err("likelihood not implemented on the device (no CPU fallback)"); return BK_ERR_UNSUPPORTED; }
+  if (s->n_outputs > 1) {
+    if (s->n_outputs > BK_MAX_OUTPUTS || s->n_groups > 1) { set_err("at most 7 shared-tree outputs, and not together with separate trees"); return BK_ERR_UNSUPPORTED; }
+    if (s->likelihood != BK_LIK_NORMAL_HETERO && s->likelihood != BK_LIK_CATEGORICAL) { set_err("shared-tree multi-output needs the heteroscedastic Normal or the Categorical likelihood"); return BK_ERR_UNSUPPORTED; }
+    if (s->likelihood == BK_LIK_NORMAL_HETERO && s->n_outputs != 2) { set_err("the heteroscedastic Normal likelihood takes two outputs"); return BK_ERR_ARG; }
+  } else if (s->likelihood != BK_LIK_NORMAL && s->likelihood != BK_LIK_BERNOULLI_LOGIT) { set_err("likelihood not implemented on the device (no CPU fallback)"); return BK_ERR_UNSUPPORTED; }
   if (!s->p_leaf || !s->split_prior) { set_err("p_leaf and split_prior are required"); return BK_ERR_ARG; }
   const size_t C = (size_t)s->n_chains * (s->n_groups > 1 ? s->n_groups : 1), P = s->n_particles, m = s->n_trees, p = s->n_cols;
+  const size_t K = s->n_outputs > 1 ? (size_t)s->n_outputs : 1;
   L->Npad = (int)align_up((size_t)s->n_rows, BK_WARP_TILE);
   L->ntiles = L->Npad / BK_WARP_TILE;
   L->R = 2 * s->n_particles;
   const size_t Npad = L->Npad, R = L->R;
   size_t o = 0;
 #define CARVE(name, bytes) L->name = o; o = align_up(o + (bytes), 256)
-  CARVE(qr, C * Npad * 4);
-  CARVE(qst, C * Npad * 4);
+  CARVE(qr, C * K * Npad * 4);
+  CARVE(qst, C * K * Npad * 4);
   CARVE(ids_tree, C * m * Npad);
   CARVE(rows, C * R * Npad);
   CARVE(rowcnt, C * R * (size_t)((L->ntiles + 3) & ~3) * 4);   // rows padded to 16 bytes for 128-bit loads
   L->nb = L->ntiles > BK_COARSE_MIN_TILES ? (L->ntiles + BK_COARSE_TILES - 1) / BK_COARSE_TILES : 0;   // bucket counts only where the tile counts no longer fit one load per lane
   CARVE(coarse, C * R * (size_t)((L->nb + 3) & ~3) * 4);
-  CARVE(wf_mean, C * Npad * 4);
-  CARVE(wf_m2, C * Npad * 4);
+  CARVE(wf_mean, C * K * Npad * 4);
+  CARVE(wf_m2, C * K * Npad * 4);
   CARVE(parts, C * 2 * P * sizeof(DParticle));
   CARVE(forest, C * m * BK_MAX_NODES * sizeof(DNode));
   CARVE(forest_nn, C * m * 4);
   CARVE(ctl, C * sizeof(ChainCtl));
   CARVE(accL, C * P * BK_ACC_STRIDE * 8);
   CARVE(acc0, C * BK_ACC0_WORDS * 8);
+  CARVE(accK, C * P * K * 2 * 8);
+  CARVE(acc_sd, C * 8 * 8);
   CARVE(alpha_vec, C * p * 8);
   CARVE(cum, C * p * 8);
   CARVE(p_leaf, 256 * 8);
@@ -2065,6 +2397,7 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   P.N = s->n_rows; P.Npad = L.Npad; P.p = s->n_cols; P.m = s->n_trees; P.P = s->n_particles;
   P.C = s->n_chains * (s->n_groups > 1 ? s->n_groups : 1);
   P.G = s->n_groups > 1 ? s->n_groups : 1;
+  P.K = s->n_outputs > 1 ? s->n_outputs : 1;
   P.R = L.R; P.ntiles = L.ntiles; P.cnt_stride = (L.ntiles + 3) & ~3; P.lik = s->likelihood; P.trace_cap = s->trace_capacity > 0 ? s->trace_capacity : 0;
   P.batch_tune = s->batch_tune < 1 ? 1 : s->batch_tune; P.batch_post = s->batch_post < 1 ? 1 : s->batch_post;
   P.qscale = ldexpf(1.0f, s->qshift); P.inv_qscale = ldexp(1.0, -s->qshift); P.init_leaf = s->init_leaf;
@@ -2077,6 +2410,7 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   P.wf_mean = (float*)(w + L.wf_mean); P.wf_m2 = (float*)(w + L.wf_m2);
   P.parts = (DParticle*)(w + L.parts); P.forest = (DNode*)(w + L.forest); P.forest_nn = (int32_t*)(w + L.forest_nn);
   P.ctl = (ChainCtl*)(w + L.ctl); P.accL = (unsigned long long*)(w + L.accL); P.acc0 = (unsigned long long*)(w + L.acc0);
+  P.accK = (unsigned long long*)(w + L.accK); P.acc_sd = (unsigned long long*)(w + L.acc_sd);
   P.alpha_vec = (double*)(w + L.alpha_vec); P.cum = (double*)(w + L.cum); P.p_leaf = (double*)(w + L.p_leaf);
   P.rules = (int32_t*)(w + L.rules); P.col_nan = (int32_t*)(w + L.col_nan); P.vi = (int32_t*)(w + L.vi); P.stats = (bk_step_stats*)(w + L.stats);
   P.trace = (bk_trace_rec*)(w + L.trace); P.sync = (ChainSync*)(w + L.sync); P.abort_flag = (int32_t*)(w + L.abort_flag);
@@ -2201,7 +2535,7 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
   CK(cudaMemcpyAsync(h->out_slot[slot], h->workspace + h->out_off_dev, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
   if (h->host_output)   // the value handed back to PyMC: strided device rows -> dense pinned host rows, behind the kernel
     CK(cudaMemcpy2DAsync(h->st_slot[slot], (size_t)P.N * sizeof(float), P.st, (size_t)P.Npad * sizeof(float), (size_t)P.N * sizeof(float),
-                         (size_t)P.C, cudaMemcpyDeviceToHost, h->stream));
+                         (size_t)P.C * P.K, cudaMemcpyDeviceToHost, h->stream));
   h->hist_count[slot] = 0;
   if (h->history && !tune) {
     // the trees this step rewrote (op.all_trees batches, pymc_bart/utils.py:117-127): two strided copies behind the
@@ -2225,7 +2559,7 @@ int bk_set_host_output(bk_handle* h, int enable) {
   ON_DEVICE(h->s.device);
   if (h->n_launched != h->n_waited) { set_err("steps in flight"); return BK_ERR_STATE; }
   for (int k = 0; k < 2 && enable; ++k)
-    if (!h->st_slot[k]) CK(cudaMallocHost(&h->st_slot[k], (size_t)h->P.C * h->P.N * sizeof(float)));
+    if (!h->st_slot[k]) CK(cudaMallocHost(&h->st_slot[k], (size_t)h->P.C * h->P.K * h->P.N * sizeof(float)));
   h->host_output = enable ? 1 : 0;
   return BK_OK;
 }
@@ -2269,6 +2603,47 @@ int bk_history_batch(bk_handle* h, int32_t* first_tree, int32_t* n_nodes_host, b
     }
   *total_nodes = tot;
   return T;
+}
+
+/* leaf values of every output of the last history batch, [total_nodes][n_outputs] in the batch's node order */
+int bk_history_values(bk_handle* h, float* values_host) {
+  if (!h || !values_host) { set_err("bad argument"); return BK_ERR_ARG; }
+  const Params& P = h->P;
+  const int slot = h->last_slot, T = h->hist_count[slot];
+  if (!h->history || T <= 0) return 0;
+  const size_t Tmax = (size_t)(P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post);
+  size_t tot = 0;
+  for (int c = 0; c < P.C; ++c)
+    for (int t = 0; t < T; ++t) {
+      const int nn = h->hist_nn_slot[slot][(size_t)c * Tmax + t];
+      const DNode* src = h->hist_nodes_slot[slot] + ((size_t)c * Tmax + t) * BK_MAX_NODES;
+      for (int k = 0; k < nn; ++k, ++tot)
+        for (int j = 0; j < P.K; ++j) values_host[tot * P.K + j] = src[k].var < 0 ? node_val(src[k], j) : 0.0f;
+    }
+  return T;
+}
+
+/* leaf values of every output of a chain's current forest: values_host [n_trees][255][n_outputs] */
+int bk_export_leaf_values(bk_handle* h, int chain, float* values_host) {
+  if (!h || chain < 0 || chain >= h->P.C || !values_host) { set_err("bad argument"); return BK_ERR_ARG; }
+  ON_DEVICE(h->s.device);
+  CK(cudaStreamSynchronize(h->stream));
+  const Params& P = h->P;
+  const size_t cnt = (size_t)P.m * BK_MAX_NODES;
+  DNode* tmp = (DNode*)malloc(cnt * sizeof(DNode));
+  int32_t* nn = (int32_t*)malloc((size_t)P.m * sizeof(int32_t));
+  if (!tmp || !nn) { free(tmp); free(nn); set_err("out of host memory"); return BK_ERR_ARG; }
+  cudaError_t e = cudaMemcpy(tmp, P.forest + (size_t)chain * cnt, cnt * sizeof(DNode), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(nn, P.forest_nn + (size_t)chain * P.m, (size_t)P.m * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(tmp); free(nn); set_err("CUDA error %s in bk_export_leaf_values", cudaGetErrorString(e)); return BK_ERR_CUDA; }
+  for (int t = 0; t < P.m; ++t)
+    for (int k = 0; k < BK_MAX_NODES; ++k)
+      for (int j = 0; j < P.K; ++j) {
+        const DNode& nd = tmp[(size_t)t * BK_MAX_NODES + k];
+        values_host[((size_t)t * BK_MAX_NODES + k) * P.K + j] = (k < nn[t] && nd.var < 0) ? node_val(nd, j) : 0.0f;
+      }
+  free(tmp); free(nn);
+  return BK_OK;
 }
 
 int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host) {

@@ -61,8 +61,11 @@ struct __align__(16) DNode {
   int32_t n;
   int64_t sst;
   int64_t sr;
-  int64_t aux[3];   // reserved (multi-output leaf values)
+  int64_t aux[3];   // shared-tree multi-output: leaf values of outputs 1..6 as floats (output 0 is `value`)
 };
+static_assert(BK_MAX_OUTPUTS <= 7, "a device node holds 1 + 6 leaf values");
+__host__ __device__ __forceinline__ float node_val(const DNode& nd, int j) { return j == 0 ? nd.value : reinterpret_cast<const float*>(nd.aux)[j - 1]; }
+__host__ __device__ __forceinline__ void set_node_val(DNode& nd, int j, float v) { if (j == 0) nd.value = v; else reinterpret_cast<float*>(nd.aux)[j - 1] = v; }
 static_assert(sizeof(DNode) == 64, "DNode must be 64 bytes");
 
 struct __align__(16) DParticle {
@@ -113,6 +116,8 @@ struct __align__(16) ChainHot {
   int32_t draw;      // steps so far (Philox counter word 0)  (persistent)
   int32_t wf_count;  // Welford count                         (persistent)
   float leaf_sd;     //                                       (persistent)
+  float leaf_sdk[BK_MAX_OUTPUTS];   // shared-tree multi-output: running leaf sd per output (persistent; [0] mirrors leaf_sd)
+  int32_t pad_sdk;
   int32_t stage;       // state machine position, read by every control thread at the start of a phase
   int32_t stage_next;  // written by thread 0 during the phase, moved into `stage` by control_loop
   int32_t tree_lo, tree_hi, cur_tree;
@@ -135,6 +140,10 @@ struct __align__(16) ChainCtl {
   SweepJob sweep;       // descriptor of the next SWEEP epoch (read by the workers)
   float old_vals[256];  // leaf values of the tree being replaced
   float new_vals[256];  // leaf values of the winning particle
+  // shared-tree multi-output (K > 1): the same two tables per output, and the leaf values of the LL jobs
+  float old_vals_k[BK_MAX_OUTPUTS][256];
+  float new_vals_k[BK_MAX_OUTPUTS][256];
+  float job_vals[BK_MAX_PARTICLES][2][BK_MAX_OUTPUTS];   // [job][left/right][output]
   Job jobs[BK_JOB_COPIES][BK_MAX_PARTICLES];   // the epoch's job list (optionally replicated; A/B: one copy is fastest)
 };
 
@@ -172,6 +181,7 @@ static_assert(sizeof(ChainSync) == 128, "ChainSync layout");
 struct Params {
   int32_t N, Npad, p, m, P, C, R, ntiles;   // C = chains * groups ("virtual chains": one forest + one sum-of-trees row each)
   int32_t G;                               // output groups per chain (separate trees); y has G rows
+  int32_t K;                               // leaf values per leaf (shared-tree multi-output); per-row arrays marked [C][K] then hold K rows per chain
   int32_t cnt_stride;                      // ntiles rounded up to a multiple of 4 (row stride of rowcnt)
   int32_t fastF, fast_stride;   // nodes per particle kept in the control CTA's shared memory; bytes per particle there
   int32_t lik, trace_cap, batch_tune, batch_post;
@@ -182,22 +192,24 @@ struct Params {
   uint32_t seed, chain_base;
   const float* X;   // [p][Npad]
   const float* y;   // [Npad]
-  float* st;        // [C][Npad] sum of trees
-  int32_t* qr;      // [C][Npad]
-  int32_t* qst;     // [C][Npad]
+  float* st;        // [C][K][Npad] sum of trees
+  int32_t* qr;      // [C][K][Npad]  (Gaussian: q(r); other likelihoods: bits of the linear predictor without the tree)
+  int32_t* qst;     // [C][K][Npad]
   uint8_t* ids_tree;   // [C][m][Npad]
   uint8_t* rows;       // [C][R][Npad]
   uint32_t* rowcnt;    // [C][R][cnt_stride]
   uint32_t* coarse;    // [C][R][nb_stride]: members of the row's counted node per bucket of BK_COARSE_TILES tiles (nb > 0 only)
   int32_t nb, nb_stride;
-  float* wf_mean;      // [C][Npad]
-  float* wf_m2;        // [C][Npad]
+  float* wf_mean;      // [C][K][Npad]
+  float* wf_m2;        // [C][K][Npad]
   DParticle* parts;    // [C][2][P]
   DNode* forest;       // [C][m][255]
   int32_t* forest_nn;  // [C][m]
   ChainCtl* ctl;       // [C]
   unsigned long long* accL;  // [C][P][BK_ACC_STRIDE]
   unsigned long long* acc0;  // [C][BK_ACC0_WORDS]
+  unsigned long long* accK;  // [C][P][K][2]: sum q(sum_trees[j]) of the new left / right child (K > 1; zeroed by the reader)
+  unsigned long long* acc_sd;  // [C][8]: running-sd sums per output (K > 1)
   double* alpha_vec;   // [C][p]
   double* cum;         // [C][p]
   double* p_leaf;      // [256]

@@ -27,8 +27,8 @@ extern "C" {
 
 int bk_predict_history(int device, void* stream, const bk_node* nodes_dev, const int32_t* ver_off_dev, const int32_t* ver_tbl_dev,
                        int n_trees, int max_forest_nodes, const float* X_dev, int n, int n_cols, const int32_t* sel_dev, int n_sel,
-                       int sel_per_mask, const uint8_t* excluded_masks_dev, int n_masks, const int32_t* split_rules_dev, float* out_dev,
-                       int32_t* err_dev) {
+                       int sel_per_mask, const uint8_t* excluded_masks_dev, int n_masks, const int32_t* split_rules_dev,
+                       const float* leaf_values_dev, int n_values, float* out_dev, int32_t* err_dev) {
   if (!nodes_dev || !ver_off_dev || !ver_tbl_dev || !X_dev || !sel_dev || !out_dev || !err_dev || n < 0 || n_sel < 0 || n_trees < 1 ||
       n_cols < 1 || n_masks < 0 || (n_masks > 0 && !excluded_masks_dev)) {
     bk_set_error_message("bk_predict_history: bad argument");
@@ -42,6 +42,8 @@ int bk_predict_history(int device, void* stream, const bk_node* nodes_dev, const
   A.nodes = nodes_dev; A.ver_off = ver_off_dev; A.ver_tbl = ver_tbl_dev; A.m = n_trees; A.X = X_dev; A.n = n; A.p = n_cols;
   A.sel = sel_dev; A.n_sel = n_sel; A.sel_stride = (sel_per_mask && n_masks > 0) ? n_sel : 0; A.excl = excluded_masks_dev; A.n_masks = n_masks; A.rules = split_rules_dev; A.out = out_dev;
   A.err = err_dev;
+  A.vals = leaf_values_dev; A.K = leaf_values_dev ? n_values : 1;
+  if (leaf_values_dev && (n_values < 1 || n_values > BK_MAX_OUTPUTS)) { bk_set_error_message("bk_predict_history: n_values out of range"); return BK_ERR_ARG; }
   int cap = max_forest_nodes < 0 ? 0 : max_forest_nodes;
   if (cap > BKP_SMEM_NODES) cap = BKP_SMEM_NODES;
   A.smem_nodes = cap;

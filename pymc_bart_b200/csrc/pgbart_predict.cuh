@@ -44,19 +44,27 @@ struct PredictArgs {
   const uint8_t* excl;  // [n_masks][p] or nullptr
   int n_masks;
   const int32_t* rules;  // [p] or nullptr
-  float* out;            // [n_masks][n_sel][n]
+  const float* vals;     // nullptr, or shared-tree multi-output: leaf values of every node [total][K]
+  int K;                 // outputs per forest (1 without vals)
+  float* out;            // [n_masks][n_sel][K][n]
   int smem_nodes;        // nodes of shared memory available for staging (host: min(largest forest, BKP_SMEM_NODES))
   int32_t* err;          // device flag: 1 = stack overflow (cannot happen for trees of <= 255 nodes), 2 = bad version id
 };
 
+// acc[j] += value_j of the tree at x (K = 1: the node's own value; K > 1: vals[(node0 + k) * K + j])
 template <bool EXCL>
-__device__ __forceinline__ double bkp_tree_value(const bk_node* __restrict__ nodes, const float* __restrict__ x,
-                                                 const uint8_t* __restrict__ excl, const int32_t* __restrict__ rules, int32_t* err) {
+__device__ __forceinline__ void bkp_tree_value(const bk_node* __restrict__ nodes, const float* __restrict__ x,
+                                               const uint8_t* __restrict__ excl, const int32_t* __restrict__ rules, int32_t* err,
+                                               const float* __restrict__ vals, int K, int node0, double* __restrict__ acc) {
   if (!EXCL) {
     int k = 0;
     for (;;) {
       const bk_node nd = nodes[k];
-      if (nd.var < 0) return (double)nd.value;
+      if (nd.var < 0) {
+        if (!vals) acc[0] = BK_DADD(acc[0], (double)nd.value);
+        else for (int j = 0; j < K; ++j) acc[j] = BK_DADD(acc[j], (double)vals[(size_t)(node0 + k) * K + j]);
+        return;
+      }
       const float xv = x[nd.var];
       const bool left = (rules && rules[nd.var] == BK_RULE_ONEHOT) ? (xv == nd.split) : (xv <= nd.split);
       k = left ? nd.left : nd.left + 1;
@@ -68,13 +76,18 @@ __device__ __forceinline__ double bkp_tree_value(const bk_node* __restrict__ nod
     double sw[BKP_STACK];
     int sp = 1;
     sn[0] = 0; sw[0] = 1.0;
-    double tv = 0.0;
+    double tv[BK_MAX_OUTPUTS];
+    for (int j = 0; j < K; ++j) tv[j] = 0.0;
     while (sp > 0) {
       --sp;
       const int k = sn[sp];
       const double w = sw[sp];
       const bk_node nd = nodes[k];
-      if (nd.var < 0) { tv = BK_DFMA(w, (double)nd.value, tv); continue; }
+      if (nd.var < 0) {
+        if (!vals) tv[0] = BK_DFMA(w, (double)nd.value, tv[0]);
+        else for (int j = 0; j < K; ++j) tv[j] = BK_DFMA(w, (double)vals[(size_t)(node0 + k) * K + j], tv[j]);
+        continue;
+      }
       const int l = nd.left, r = nd.left + 1;
       if (excl[nd.var]) {
         const double tot = (double)nodes[l].n + (double)nodes[r].n;
@@ -90,7 +103,7 @@ __device__ __forceinline__ double bkp_tree_value(const bk_node* __restrict__ nod
         sn[sp] = left ? l : r; sw[sp] = w; ++sp;
       }
     }
-    return tv;
+    for (int j = 0; j < K; ++j) acc[j] = BK_DADD(acc[j], tv[j]);
   }
 }
 
@@ -142,18 +155,21 @@ __global__ void __launch_bounds__(BKP_THREADS) pgbart_predict_hist_kernel(const 
     }
   }
 
-  const size_t out_base = ((size_t)blockIdx.z * A.n_sel + blockIdx.y) * (size_t)A.n;
+  const int K = A.vals ? A.K : 1;
+  const size_t out_base = ((size_t)blockIdx.z * A.n_sel + blockIdx.y) * (size_t)K * (size_t)A.n;
 #pragma unroll 1
   for (int r = 0; r < BKP_ROWS_PER_THREAD; ++r) {
     const long long i = (long long)blockIdx.x * BKP_TILE + (long long)r * BKP_THREADS + tid;
     if (i >= A.n) break;
     const float* x = A.X + (size_t)i * A.p;
-    double acc = 0.0;
+    double acc[BK_MAX_OUTPUTS];
+    for (int j = 0; j < K; ++j) acc[j] = 0.0;
     for (int t = 0; t < A.m; ++t) {
-      const bk_node* nodes = staged ? s_nodes + s_off[t] : A.nodes + A.ver_off[vrow[t]];
-      acc = BK_DADD(acc, bkp_tree_value<EXCL>(nodes, x, excl, A.rules, A.err));
+      const int node0 = A.ver_off[vrow[t]];
+      const bk_node* nodes = staged ? s_nodes + s_off[t] : A.nodes + node0;
+      bkp_tree_value<EXCL>(nodes, x, excl, A.rules, A.err, A.vals, K, node0, acc);
     }
-    A.out[out_base + (size_t)i] = (float)acc;
+    for (int j = 0; j < K; ++j) A.out[out_base + (size_t)j * A.n + (size_t)i] = (float)acc[j];
   }
 }
 

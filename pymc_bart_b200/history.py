@@ -10,7 +10,9 @@ Formats (plain numpy, picklable through the ``multiprocessing.Manager`` proxy of
 * ``baseline_forest = (nodes, n_nodes)``: ``n_nodes`` int32 ``[G*m]`` (output group major), ``nodes`` the trees' nodes
   back to back (NODE_DTYPE, 24 bytes each, ``n_nodes`` of them per tree);
 * one batch per post-tuning draw: ``(first, n_nodes, nodes)`` with ``n_nodes`` int32 ``[G, T]`` for the trees
-  ``first .. first+T-1`` of every output group, nodes back to back in that order.
+  ``first .. first+T-1`` of every output group, nodes back to back in that order;
+* shared-tree multi-output (every leaf carries K values): both tuples end with one more array, the nodes' leaf
+  values ``[n_nodes_total][K]`` float32 (G = 1 then; the K outputs come from one tree walk).
 
 Device store (``DeviceForests``): every tree version once, plus a table ``[forest][tree] -> version``; a draw costs
 ``m`` ints (C5: 800 bytes instead of a 1.2 MB dense forest).  Forest rows are ordered (chain, draw, group): the
@@ -37,8 +39,12 @@ class ChainHistory:
     """Host description of one chain's history: tree versions and the per-draw version table."""
 
     def __init__(self, batches, baseline_forest, m: int, n_outputs: int):
-        base_nodes, base_nn = baseline_forest
-        G = int(n_outputs)
+        base_nodes, base_nn = baseline_forest[0], baseline_forest[1]
+        base_vals = baseline_forest[2] if len(baseline_forest) > 2 else None
+        self.K = 1 if base_vals is None else int(np.asarray(base_vals).shape[1])    # shared-tree outputs per leaf
+        G = 1 if self.K > 1 else int(n_outputs)
+        if self.K > 1 and self.K != int(n_outputs):
+            raise ValueError("baseline leaf values do not hold n_outputs columns")
         base_nn = np.ascontiguousarray(base_nn, dtype=np.int32).reshape(-1)
         if base_nn.size != G * m:
             raise ValueError("baseline forest does not hold n_outputs * m trees")
@@ -50,6 +56,12 @@ class ChainHistory:
         self.nodes = np.concatenate(node_parts) if node_parts else np.zeros(0, _cabi.NODE_DTYPE)
         if int(self.ver_nn.sum()) != self.nodes.size:
             raise ValueError("history node counts do not add up")
+        self.vals = None
+        if self.K > 1:
+            self.vals = np.ascontiguousarray(np.concatenate([np.asarray(base_vals, dtype=np.float32)] +
+                                                            [np.asarray(b[3], dtype=np.float32) for b in batches]))
+            if self.vals.shape != (self.nodes.size, self.K):
+                raise ValueError("history leaf values do not match the nodes")
         # version table: forest row (draw, group) -> version of every tree
         tbl = np.empty((self.n_draws, G, m), dtype=np.int32)
         cur = np.arange(G * m, dtype=np.int32).reshape(G, m)
@@ -89,12 +101,14 @@ class DeviceForests:
         self.lib = _cabi.load()
         self.torch = torch
         self.device = torch.device("cuda", device)
-        self.m, self.G = chains[0].m, chains[0].G
-        nodes, nn, tbl, voff = [], [], [], 0
+        self.m, self.G, self.K = chains[0].m, chains[0].G, chains[0].K
+        nodes, nn, tbl, vals, voff = [], [], [], [], 0
         for ch in chains:
-            if ch.m != self.m or ch.G != self.G:
+            if ch.m != self.m or ch.G != self.G or ch.K != self.K:
                 raise ValueError("chains disagree on m / n_outputs")
             nodes.append(ch.nodes); nn.append(ch.ver_nn); tbl.append(ch.ver_tbl + voff)
+            if self.K > 1:
+                vals.append(ch.vals)
             voff += ch.ver_nn.size
         ver_nn = np.concatenate(nn)
         ver_off = np.zeros(ver_nn.size + 1, dtype=np.int64)
@@ -110,6 +124,7 @@ class DeviceForests:
             self.nodes_dev = torch.from_numpy(np.concatenate(nodes).view(np.uint8).reshape(-1).copy()).to(self.device)
             self.ver_off_dev = torch.from_numpy(ver_off.astype(np.int32)).to(self.device)
             self.ver_tbl_dev = torch.from_numpy(ver_tbl).to(self.device)
+            self.vals_dev = torch.from_numpy(np.ascontiguousarray(np.concatenate(vals))).to(self.device) if self.K > 1 else None
             self.rules_dev = None
             if split_rules is not None:
                 self.rules_dev = torch.from_numpy(np.ascontiguousarray(split_rules, dtype=np.int32)).to(self.device)
@@ -129,7 +144,8 @@ class DeviceForests:
         """Sum of trees of the forests of the global draws ``draw_indices`` at the rows of X.
 
         masks: None or uint8 ``[n_masks][p]`` (1 = excluded variable); per_mask: ``draw_indices`` is ``[n_masks][S]``,
-        one set of draws per mask.  Returns a device tensor ``[n_masks or 1][S][G][n]`` float32."""
+        one set of draws per mask.  Returns a device tensor ``[n_masks or 1][S][n_outputs][n]`` float32 (n_outputs =
+        separate-tree groups, or the K values of shared-tree leaves)."""
         torch = self.torch
         Xd = self.upload(X)
         n, p = int(Xd.shape[0]), int(Xd.shape[1])
@@ -159,17 +175,18 @@ class DeviceForests:
             stream = torch.cuda.current_stream(self.device)
             if n_sel > 65535:
                 raise ValueError("at most 65535 (draw, output) forests per prediction call")
-            out = torch.empty((max(n_masks, 1), n_sel, n), dtype=torch.float32, device=self.device)
+            out = torch.empty((max(n_masks, 1), n_sel, self.K, n), dtype=torch.float32, device=self.device)
             if n_sel and n:
                 rc = self.lib.bk_predict_history(
                     self.device.index, C.c_void_p(stream.cuda_stream), self.nodes_dev.data_ptr(), self.ver_off_dev.data_ptr(),
                     self.ver_tbl_dev.data_ptr(), self.m, self.max_forest_nodes, Xd.data_ptr(), n, p,
                     sel_dev.data_ptr(), n_sel, int(bool(per_mask)), None if masks_dev is None else masks_dev.data_ptr(), n_masks,
-                    None if self.rules_dev is None else self.rules_dev.data_ptr(), out.data_ptr(), self.err_dev.data_ptr())
+                    None if self.rules_dev is None else self.rules_dev.data_ptr(),
+                    None if self.vals_dev is None else self.vals_dev.data_ptr(), self.K, out.data_ptr(), self.err_dev.data_ptr())
                 _cabi.check(rc, "bk_predict_history")
             if int(self.err_dev.item()) != 0:
                 raise RuntimeError("posterior prediction: device-side consistency flag set (malformed forest history)")
-        return out.reshape(max(n_masks, 1), S, self.G, n)
+        return out.reshape(max(n_masks, 1), S, self.G * self.K, n)
 
     def pearson_r2(self, a, b):
         """Squared Pearson correlation per (subset, sample): a ``[S][len]``, b ``[K][S][len]`` device tensors

@@ -28,7 +28,12 @@ from .core import DeviceSampler
 from .settings import make_settings
 from .utils import _encode_vi
 
-LIKELIHOODS = {"normal": _cabi.BK_LIK_NORMAL, "bernoulli": _cabi.BK_LIK_BERNOULLI_LOGIT}
+# Closed likelihood families of the device path.  The two multi-output ones are the models the reference's own tests
+# build on shared trees: y ~ Normal(w[0], |w[1]|) with w = BART(shape=(2, n)) (tests/test_bart.py:107-123) and
+# y ~ Categorical(softmax(mu, axis=0)) with mu = BART(shape=(k, n)) (tests/test_bart.py:140-164).
+LIKELIHOODS = {"normal": _cabi.BK_LIK_NORMAL, "bernoulli": _cabi.BK_LIK_BERNOULLI_LOGIT,
+               "normal_hetero": _cabi.BK_LIK_NORMAL_HETERO, "categorical": _cabi.BK_LIK_CATEGORICAL}
+SHARED_TREE_LIKELIHOODS = ("normal_hetero", "categorical")
 
 
 class PGBART:
@@ -50,16 +55,27 @@ class PGBART:
             raise NotImplementedError(f"response={op.response!r} has no device implementation (constant leaves only)")
         if likelihood not in LIKELIHOODS:
             raise NotImplementedError(f"likelihood {likelihood!r} has no device implementation")
-        # multi-output: BART(shape=(k, n), separate_trees=True) = k output groups, each with its own forest and
-        # its own response row (independent likelihood per output); shared-tree multi-output has no device form
+        # multi-output, BART(shape=(k, n)):
+        #  * separate_trees=True -> k output groups, each with its own forest and its own response row (independent
+        #    likelihood per output; BASELINE.json config 4);
+        #  * otherwise SHARED trees (the reference's mode at this commit, tests/test_bart.py:107-123,140-164): one
+        #    forest, k values per leaf, the weight is the likelihood of the whole (k, n) value -> needs one of the
+        #    multi-output families
         shape = tuple(getattr(rv, "shape", (np.asarray(op.X).shape[0],)))
-        groups = int(shape[0]) if len(shape) == 2 else 1
-        if groups > 1 and not getattr(op, "separate_trees", False):
-            raise NotImplementedError("multi-output BART needs separate_trees=True on the device (shared trees are not implemented)")
+        k_out = int(shape[0]) if len(shape) == 2 else 1
+        separate = bool(getattr(op, "separate_trees", False))
+        groups = k_out if separate else 1
+        outputs = 1 if separate else k_out
+        if outputs > 1 and likelihood not in SHARED_TREE_LIKELIHOODS:
+            raise NotImplementedError("shared-tree multi-output BART needs likelihood='normal_hetero' (shape=(2, n)) or "
+                                      "'categorical' (shape=(k, n)); pass separate_trees=True for independent outputs")
+        if outputs == 1 and likelihood in SHARED_TREE_LIKELIHOODS:
+            raise ValueError(f"likelihood={likelihood!r} needs a multi-output BART variable with shared trees (shape=(k, n))")
         Yarr = np.asarray(op.Y, dtype=np.float64)
         if groups > 1 and Yarr.ndim == 1:
             Yarr = np.broadcast_to(Yarr, (groups, Yarr.shape[0]))
         self.groups = groups
+        self.outputs = outputs
         self.op = op
         self.vars = [rv]
         self.num_particles = int(num_particles)
@@ -77,7 +93,7 @@ class PGBART:
         self._settings_kw = dict(
             m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
             num_particles=num_particles, batch=batch, n_chains=chains, seed=seed, likelihood=LIKELIHOODS[likelihood],
-            depth_offset=depth_offset, trace_capacity=trace_capacity, n_groups=groups)
+            depth_offset=depth_offset, trace_capacity=trace_capacity, n_groups=groups, n_outputs=outputs)
         self.settings = make_settings(op.X, Yarr, chain_base=self.chain_base, device=0 if device is None else device,
                                       **self._settings_kw)
         self.n_rows, self.n_cols, self.m = self.settings.n_rows, self.settings.n_cols, self.settings.n_trees
@@ -88,7 +104,7 @@ class PGBART:
         self.last_stats = None
         self.history_bytes_per_step = 0
         # read back through the CLASS by BARTRV.rng_fn -> _get_posterior_sampler(cls) (bart.py:65, utils.py:125)
-        (op if isinstance(op, type) else type(op)).n_outputs = groups
+        (op if isinstance(op, type) else type(op)).n_outputs = k_out
 
     # ---- device state ---------------------------------------------------------
     def _reset_chain_state(self):
@@ -190,9 +206,9 @@ class PGBART:
         return sibling_list(self.op.all_trees)
 
     def _chain_slice(self, per_vc, c):
-        """(chain c's output groups) of a per-(chain, group) list of (nodes, n_nodes) -> one (nodes, n_nodes [G*m])."""
+        """(chain c's output groups) of a per-(chain, group) list of (nodes, n_nodes[, leaf values]) -> one entry."""
         parts = per_vc[c * self.groups:(c + 1) * self.groups]
-        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(len(parts[0])))
 
     def astep(self, _q=None):
         tune = bool(self.tune)
@@ -216,15 +232,16 @@ class PGBART:
         if not tune:
             self._post_draws += 1
             if self.store_history:
-                first, nn, nodes = core.history_batch()
+                first, nn, *arrays = core.history_batch()      # nodes[, leaf values of every output]
                 off = np.concatenate([[0], np.cumsum(nn.sum(axis=1))])
                 G = self.groups
                 for c in range(self.chains):
-                    self._publish(self._batches[c], (first, nn[c * G:(c + 1) * G].copy(), nodes[off[c * G]: off[(c + 1) * G]].copy()))
+                    self._publish(self._batches[c], (first, nn[c * G:(c + 1) * G].copy(),
+                                                     *(a[off[c * G]: off[(c + 1) * G]].copy() for a in arrays)))
         vic = vi.reshape(self.chains, self.groups, -1).sum(axis=1)       # one inclusion vector per BART variable
         out_stats = [{"variable_inclusion": _encode_vi(vic[c].tolist()), "tune": tune} for c in range(self.chains)]
-        value = value.reshape(self.chains, self.groups, -1)
-        if self.groups == 1:
+        value = value.reshape(self.chains, self.groups * self.outputs, -1)    # (chain, output, row)
+        if self.groups * self.outputs == 1:
             value = value[:, 0]
         if self.chains == 1:
             return value[0].copy(), [out_stats[0]]

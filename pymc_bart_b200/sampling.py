@@ -46,7 +46,8 @@ def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1)
     step = PGBART([rv], num_particles=num_particles, batch=batch, likelihood=likelihood, sigma=sigma, chains=chains,
                   chain_base=chain_base_for_rank(rank, chains), seed=seed, device=device, **step_kwargs)
     N = step.n_rows
-    vshape = (N,) if step.groups == 1 else (step.groups, N)
+    k_out = step.groups * step.outputs
+    vshape = (N,) if k_out == 1 else (k_out, N)
     post = np.empty((chains, draws, *vshape), dtype=np.float32) if keep_draws else None
     vi = [[None] * draws for _ in range(chains)]
     for d in range(tune + draws):

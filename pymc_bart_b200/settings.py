@@ -68,6 +68,7 @@ class SamplerSettings:
     device: int
     trace_capacity: int
     n_groups: int
+    n_outputs: int
     p_leaf: np.ndarray
     split_prior: np.ndarray
     split_rules: np.ndarray
@@ -77,7 +78,7 @@ class SamplerSettings:
         s = _cabi.BkSettings()
         s.abi_version = _cabi.BK_ABI_VERSION
         for name in ("n_rows", "n_cols", "n_trees", "n_particles", "n_chains", "likelihood", "qshift", "batch_tune",
-                     "batch_post", "seed", "chain_base", "device", "trace_capacity", "n_groups"):
+                     "batch_post", "seed", "chain_base", "device", "trace_capacity", "n_groups", "n_outputs"):
             setattr(s, name, int(getattr(self, name)))
         s.init_sum = float(self.init_sum)
         s.init_leaf = float(self.init_leaf)
@@ -109,6 +110,7 @@ def make_settings(
     device: int = 0,
     trace_capacity: int = 0,
     n_groups: int = 1,
+    n_outputs: int = 1,
 ) -> SamplerSettings:
     X = np.asarray(X)
     Y = np.asarray(Y, dtype=np.float64)
@@ -138,7 +140,21 @@ def make_settings(
         leaf_sd = 3.0 / math.sqrt(m)
     else:
         leaf_sd = float(Y.std()) / math.sqrt(m)
-    if int(likelihood) == _cabi.BK_LIK_BERNOULLI_LOGIT:
+    if int(n_outputs) > 1:
+        if int(likelihood) not in (_cabi.BK_LIK_NORMAL_HETERO, _cabi.BK_LIK_CATEGORICAL):
+            raise NotImplementedError("shared-tree multi-output BART needs likelihood 'normal_hetero' or 'categorical' on the device")
+        if int(n_outputs) > _cabi.BK_MAX_OUTPUTS or int(n_groups) > 1:
+            raise NotImplementedError(f"at most {_cabi.BK_MAX_OUTPUTS} shared-tree outputs, and not together with separate trees")
+        if int(likelihood) == _cabi.BK_LIK_NORMAL_HETERO and int(n_outputs) != 2:
+            raise ValueError("the heteroscedastic Normal likelihood takes shape=(2, n): mean and scale")
+        if int(likelihood) == _cabi.BK_LIK_CATEGORICAL and not np.all((Y == np.floor(Y)) & (Y >= 0) & (Y < int(n_outputs))):
+            raise ValueError("the Categorical likelihood needs integer labels 0..k-1")
+        if np.isnan(np.asarray(X, dtype=np.float64)).any():
+            raise NotImplementedError("missing covariates are not supported together with shared-tree multi-output")
+        qshift = choose_qshift(max(16.0, float(np.abs(Y).max()), abs(ymean)))   # linear predictors: fixed-point range of at least +-64
+    elif int(likelihood) in (_cabi.BK_LIK_NORMAL_HETERO, _cabi.BK_LIK_CATEGORICAL):
+        raise ValueError("likelihoods 'normal_hetero' / 'categorical' need a multi-output BART variable (shape=(k, n))")
+    elif int(likelihood) == _cabi.BK_LIK_BERNOULLI_LOGIT:
         if not np.all((Y == 0.0) | (Y == 1.0)):
             raise ValueError("the Bernoulli likelihood needs a 0/1 response")
         qshift = choose_qshift(16.0)    # the sum of trees is a logit: fixed-point range +-64
@@ -153,6 +169,6 @@ def make_settings(
         likelihood=int(likelihood), qshift=qshift,
         batch_tune=bt, batch_post=bp, seed=int(seed) & 0xFFFFFFFF, chain_base=int(chain_base),
         init_sum=float(init_sum), init_leaf=float(init_leaf), leaf_sd_init=float(np.float32(leaf_sd)),
-        device=int(device), trace_capacity=int(trace_capacity), n_groups=max(1, int(n_groups)),
+        device=int(device), trace_capacity=int(trace_capacity), n_groups=max(1, int(n_groups)), n_outputs=max(1, int(n_outputs)),
         p_leaf=depth_prior_table(alpha, beta, depth_offset), split_prior=sp, split_rules=rules,
     )

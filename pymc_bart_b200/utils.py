@@ -78,7 +78,7 @@ class PosteriorSampler:
 
     @property
     def n_outputs(self) -> int:
-        return self.history.G
+        return self.history.G * self.history.K
 
     def sample_posterior(self, X, draw_indices, excluded=None) -> np.ndarray:
         if self._store is None:
@@ -105,7 +105,7 @@ class _MultiChainSampler:
 
     @property
     def n_outputs(self) -> int:
-        return self._forests.G
+        return self._forests.G * self._forests.K
 
     def upload(self, X):
         """Device copy of X for repeated calls (the importance search predicts dozens of times on the same rows)."""

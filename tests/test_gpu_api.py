@@ -280,8 +280,6 @@ def test_multi_output_api_shapes_and_prediction():
     # outputs 0 and 1 were fitted to y and -y: their posterior means must be strongly anti-correlated
     m0, m1 = out["posterior"][0, :, 0].mean(0), out["posterior"][0, :, 1].mean(0)
     assert np.corrcoef(m0, m1)[0, 1] < -0.25 and np.corrcoef(m0, y)[0, 1] > 0.4 and np.corrcoef(m1, -y)[0, 1] > 0.4
-    with pytest.raises(NotImplementedError):
-        pmb.PGBART([pmb.BART("s", X, y, m=3, shape=(2, 300))])       # shared-tree multi-output
     out["step"].close()
 
 
