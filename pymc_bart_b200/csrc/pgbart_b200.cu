@@ -86,6 +86,8 @@
 #endif
 
 
+// Every device function that takes `const Params& P` is forced inline: the structure is a kernel parameter (constant
+// bank); a real call would make each thread copy its 350 bytes to the stack and read them back from local memory.
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -150,11 +152,18 @@ __shared__ long long s_ct_last;
 
 // a node with fewer than N / BK_SPARSE_DIV members loads the split column only in lanes that hold members
 // -DBK_NO_MISSING compiles the missing-covariate paths out (A/B of their cost on data without NaNs; tests/gpu_variants.sh)
-#ifdef BK_NO_MISSING
-#define BK_MISSING_ENABLED 0
-#else
-#define BK_MISSING_ENABLED 1
-#endif
+// The step kernel exists in three MODES, chosen once per CTA at kernel entry and carried as a template argument, so that
+// the plain path never executes, fetches or allocates registers for the other two (compiled into one body, the
+// multi-output and missing-value code cost the plain C2 / C5 steps 8 %: twice the code for the instruction cache, and
+// calls in the hot loops):
+//   BK_MODE_PLAIN    single output per forest, no NaN in X
+//   BK_MODE_MISSING  X holds NaNs (Params::has_nan)
+//   BK_MODE_MULTI    shared-tree multi-output (Params::K > 1)
+#define BK_MODE_PLAIN 0
+#define BK_MODE_MISSING 1
+#define BK_MODE_MULTI 2
+#define BK_IS_MULTI(P) (MODE == BK_MODE_MULTI)
+#define BK_MISSING_ENABLED (MODE == BK_MODE_MISSING)
 #ifndef BK_SPARSE_DIV
 #define BK_SPARSE_DIV 8
 #endif
@@ -210,7 +219,6 @@ struct CtlShared {
   int warp_grow_root[4];
   float job_vals[BK_MAX_PARTICLES][2][BK_MAX_OUTPUTS];   // shared-tree multi-output: leaf values of the LL jobs (staged, copied to global)
   int n_nan_fail, n_fail_root;   // slots whose split value could not be drawn (only members with a missing covariate)
-  Params params_copy;            // for the out-of-line retry path (a reference to the kernel parameter would force a per-thread stack copy)
   // last value read from every accumulator word of accL: the workers only ever ADD (RED), the control CTA takes
   // differences (exact in wrapping 64-bit arithmetic), so no accumulator is ever zeroed by a store that would have
   // to be ordered before the next epoch's adds
@@ -396,7 +404,7 @@ __device__ __forceinline__ int find_in_counts(const uint4* __restrict__ cnt4, in
 // the workers left behind: [large N only: one count per bucket of 32 tiles, then the bucket's 32 tile counts] or the
 // per-tile counts directly; then the tile's leaf ids AND the tile of the split column are requested together, so the
 // split value is there when the member's position is known: two dependent L2 round trips at N = 100k, three at N = 1M.
-__device__ float select_split(const Params& P, int c, int row, int node, unsigned k, int var, int* err) {
+__device__ __forceinline__ float select_split(const Params& P, int c, int row, int node, unsigned k, int var, int* err) {
   const int lane = threadIdx.x & 31;
   CTS(20, 0);   // (time between the end of the job assembly / previous selection and this one: cursor traffic)
   const unsigned* cnt = P.rowcnt + ((size_t)c * P.R + row) * P.cnt_stride;
@@ -456,7 +464,7 @@ __device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, 
   const unsigned lo = __shfl_up_sync(0xffffffffu, (unsigned)v, o), hi = __shfl_up_sync(0xffffffffu, (unsigned)(v >> 32), o);
   return ((unsigned long long)hi << 32) | lo;
 }
-__device__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, uint32_t u32) {
+__device__ __forceinline__ void normalise_and_resample(const Params& P, CtlShared& sh, int first, int count, uint32_t u32) {
   // warps 1..4, one 32-element slice each (count <= 128), meeting on their own named barrier
   const int wq = (int)(threadIdx.x >> 5) - 1;
   if (wq >= 0 && wq < 4) {
@@ -541,12 +549,12 @@ __device__ __forceinline__ int resample_own(const Params& P, int c, int buf, Ctl
   return lo;
 }
 
-__device__ void zero_acc0(const Params& P, int c) {
+__device__ __forceinline__ void zero_acc0(const Params& P, int c) {
   unsigned long long* a = P.acc0 + (size_t)c * BK_ACC0_WORDS;
   for (int i = BK_WTID; i >= 0 && i < BK_ACC0_WORDS; i += BK_WTHREADS) a[i] = 0ull;
 }
 
-__device__ void rebuild_cum_dev(const Params& P, int c) {  // thread 0 only
+__device__ __forceinline__ void rebuild_cum_dev(const Params& P, int c) {  // thread 0 only
   double* av = P.alpha_vec + (size_t)c * P.p;
   double* cum = P.cum + (size_t)c * P.p;
   double tot = 0.0;
@@ -556,7 +564,7 @@ __device__ void rebuild_cum_dev(const Params& P, int c) {  // thread 0 only
 }
 
 // ------------------------------------------------------------------ control phase
-__device__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
+__device__ __forceinline__ void init_particles(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int t = hot->cur_tree;
   const unsigned long long* a0 = P.acc0 + (size_t)c * BK_ACC0_WORDS;
   const DNode* ft = P.forest + ((size_t)c * P.m + t) * BK_MAX_NODES;
@@ -618,11 +626,11 @@ __device__ __forceinline__ int draw_variable_dev(const Params& P, int c, const C
   return lo;
 }
 
-__device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot);
+__device__ __forceinline__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot);
 
 // Executes a deferred particle copy (see CtlShared::copy_pending): buffer `buf` -> `buf ^ 1` through src_slot, then
 // the queue heads open_round() recorded; flips the buffer.  All control threads.
-__device__ void apply_pending_copy(const Params& P, int c, ChainHot* hot, CtlShared& sh) {
+__device__ __forceinline__ void apply_pending_copy(const Params& P, int c, ChainHot* hot, CtlShared& sh) {
   if (!sh.copy_pending) return;     // (uniform: shared flag, read after a barrier)
   const int buf = hot->buf;
   copy_particles(P, c, buf, sh.src_slot);
@@ -632,7 +640,7 @@ __device__ void apply_pending_copy(const Params& P, int c, ChainHot* hot, CtlSha
 }
 
 // Runs right after a ROUND epoch has been published (all control threads), overlapping the workers.
-__device__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& sh) {
+__device__ __forceinline__ void shadow_round(const Params& P, int c, ChainHot* hot, CtlShared& sh) {
   const int round = hot->round, t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   apply_pending_copy(P, c, hot, sh);
@@ -675,9 +683,19 @@ __device__ __forceinline__ int nth_free_row(const CtlShared& sh, int R, int n) {
 // Shared-tree multi-output: K leaf values per child from the per-output sums of both children (accK, zeroed here: the
 // release fence of the next publication orders the stores before the workers' next adds), K normals per child from the
 // Philox blocks whose `group` word is the output index; the values also go to the LL job of the slot.
-__device__ __noinline__ void finalize_multi(const Params& P, int c, ChainHot* hot, CtlShared& sh, const PRef& S, const Job& jb, int ji, int q,
-                                            DNode& parent, int n_left, int round, int t, int rbase) {
+__device__ __forceinline__ void finalize_multi(const Params& P, int c, ChainHot* hot, CtlShared& sh, int buf, int q, int ji, int round, int t,
+                                            int rbase) {
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)c, D0 = (uint32_t)hot->draw;
+  const Job jb = sh.jobs[ji];
+  const PRef S = pref(P, c, buf, q);
+  int n_left;
+  {
+    unsigned long long* acc = P.accL + ((size_t)c * P.P + q) * BK_ACC_STRIDE;
+    const unsigned long long a_n = __ldcg(acc + BK_ACC_N);
+    n_left = (int)(a_n - sh.acc_prev[q][BK_ACC_N]);
+    sh.acc_prev[q][BK_ACC_N] = a_n;
+  }
+  DNode parent = S.node(jb.node);
   const int nn = S.h->n_nodes, n_right = parent.n - n_left;
   const float split = sh.s_split[q];
   parent.var = jb.var; parent.split = split; parent.left = nn;
@@ -709,12 +727,14 @@ __device__ __noinline__ void finalize_multi(const Params& P, int c, ChainHot* ho
 }
 
 // apply the statistics of the finished ROUND to slot q's particle if it grew (thread q = BK_WTID); no barrier inside
+template <int MODE>
 __device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* hot, CtlShared& sh, int buf, int round, int t, int rbase) {
   const int q = BK_WTID;
   if (q < 1 || q >= P.P) return;
   const int ji = sh.s_jobidx[q];
   if (ji < 0) return;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
+  if (BK_IS_MULTI(P)) { finalize_multi(P, c, hot, sh, buf, q, ji, round, t, rbase); return; }
   const bool bern = P.lik != BK_LIK_NORMAL;   // every family without a sufficient statistic: weights come from the LL epoch
   const Job jb = sh.jobs[ji];   // the job list staged by open_round() is still in shared memory
   const PRef S = pref(P, c, buf, q);
@@ -729,7 +749,6 @@ __device__ __forceinline__ void finalize_own(const Params& P, int c, ChainHot* h
     prev[BK_ACC_N] = a_n; prev[BK_ACC_SST] = a_st; prev[BK_ACC_SR] = a_sr;
   }
   DNode parent = S.node(jb.node);
-  if (P.K > 1) { finalize_multi(sh.params_copy, c, hot, sh, S, jb, ji, q, parent, sl.n, round, t, rbase); return; }
   const bk_stats sp = node_stats(parent);
   bk_stats sr = bk_stats_sub(sp, sl);
   if (BK_MISSING_ENABLED && jb.pad[1]) {   // the split column has missing values: the rows dropped from the node count for neither child
@@ -792,8 +811,8 @@ __device__ __forceinline__ void finalize_ll_own(const Params& P, int c, CtlShare
 }
 
 // bk_spec.h BK_SPLIT_TRIES: candidates 1..3 of a split-value draw whose first candidate member has no value in the split
-// column (NaN).  Out of line: columns without missing values never get here, and the round path keeps its registers.
-__device__ __noinline__ float retry_split_value(const Params& P, int c, CtlShared& sh, int buf, int sl, uint32_t S0, uint32_t C0,
+// column (NaN).  Only the BK_MODE_MISSING instantiation of the round path contains it.
+__device__ __forceinline__ float retry_split_value(const Params& P, int c, CtlShared& sh, int buf, int sl, uint32_t S0, uint32_t C0,
                                                 uint32_t D0, uint32_t G0, int t, int round) {
   const int lane = threadIdx.x & 31;
   const PRef S = pref(P, c, buf, sh.src_slot[sl]);
@@ -819,7 +838,8 @@ __device__ __noinline__ float retry_split_value(const Params& P, int c, CtlShare
 // list, split values (k-th member).  Called by every control thread; `src` is the calling particle thread's own
 // ancestor slot.  Two block barriers inside; returns (uniformly) the job count.  The caller's barrier orders the
 // global job list before thread 0 publishes the epoch.
-__device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh, const int buf, const int round,
+template <int MODE>
+__device__ __forceinline__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh, const int buf, const int round,
                           const int rbase, const bool deferred, const int src) {
   const int t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
@@ -921,7 +941,7 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
         if (lane == 0 && err) atomicOr(&sh.err_bits, err);
         CTN(29);
       }
-      if (BK_MISSING_ENABLED && sv != sv) sv = retry_split_value(sh.params_copy, c, sh, buf, sl, S0, C0, D0, G0, t, round);   // the candidate's covariate is missing
+      if (BK_MISSING_ENABLED && sv != sv) sv = retry_split_value(P, c, sh, buf, sl, S0, C0, D0, G0, t, round);   // the candidate's covariate is missing
       if (lane == 0) { sh.s_split[sl] = sv; if (sv != sv) atomicAdd(&sh.n_nan_fail, 1); }
     }
   }
@@ -975,7 +995,7 @@ __device__ int open_round(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, 
   return nj;
 }
 
-__device__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot /* smem, [P] */) {
+__device__ __forceinline__ void copy_particles(const Params& P, int c, int buf, const int* anc_of_slot /* smem, [P] */) {
   const int warp = (int)(threadIdx.x >> 5) - 1, nwarps = (BK_CTRL_THREADS >> 5) - 1, lane = threadIdx.x & 31;   // warps 1..15
   for (int s = warp; s >= 0 && s < P.P; s += nwarps) {
     const PRef src = pref(P, c, buf, anc_of_slot[s]);
@@ -995,7 +1015,8 @@ __device__ void copy_particles(const Params& P, int c, int buf, const int* anc_o
   CTRL_SYNC();
 }
 
-__device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
+template <int MODE>
+__device__ __forceinline__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot, CtlShared& sh) {
   const int buf = hot->buf, t = hot->cur_tree;
   const uint32_t S0 = P.seed, C0 = P.chain_base + (uint32_t)(c / P.G), G0 = (uint32_t)(c % P.G), D0 = (uint32_t)hot->draw;
   if (BK_WTID >= 0 && BK_WTID < P.P) sh.lw[BK_WTID] = pref(P, c, buf, BK_WTID).h->lw;
@@ -1017,7 +1038,7 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
     const float of = k < BK_MAX_NODES ? __ldcg(&ft[k].value) : 0.0f;
     ctl->old_vals[k] = (k < old_nn && ov < 0) ? of : 0.0f;
     ctl->new_vals[k] = (k < new_nn && W.node(k).var < 0) ? W.node(k).value : 0.0f;
-    if (P.K > 1) {
+    if (BK_IS_MULTI(P)) {
       for (int j = 0; j < P.K; ++j) {
         const float ofj = (k < BK_MAX_NODES && j > 0) ? __ldcg(reinterpret_cast<const float*>(ft[k].aux) + (j - 1)) : of;
         ctl->old_vals_k[j][k] = (k < old_nn && ov < 0) ? ofj : 0.0f;
@@ -1078,7 +1099,8 @@ __device__ void finish_tree(const Params& P, int c, ChainCtl* ctl, ChainHot* hot
   CTRL_SYNC();
 }
 
-__device__ void control_step(const Params& P, int c, int phase, int tune, const StepArgs& A, ChainHot* hot, CtlShared& sh) {
+template <int MODE>
+__device__ __forceinline__ void control_step(const Params& P, int c, int phase, int tune, const StepArgs& A, ChainHot* hot, CtlShared& sh) {
   const int first_phase = phase == 0;
   ChainCtl* ctl = P.ctl + c;
   if (first_phase) {
@@ -1124,7 +1146,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
         if (hot->tune) {
           hot->wf_count = sj.wf_count;
           if (hot->iter > 2) {
-            if (P.K > 1) {
+            if (BK_IS_MULTI(P)) {
               for (int j = 0; j < P.K; ++j) {
                 const long long sd_j = (long long)__ldcg(P.acc_sd + (size_t)c * 8 + j);
                 hot->leaf_sdk[j] = (float)BK_DDIV(BK_DMUL((double)sd_j, P.inv_qscale), (double)P.N);
@@ -1135,11 +1157,11 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
               hot->leaf_sd = (float)BK_DDIV(BK_DMUL((double)sd_sum, P.inv_qscale), (double)P.N);
             }
           }
-          if (P.K > 1) for (int j = 0; j < 8; ++j) P.acc_sd[(size_t)c * 8 + j] = 0ull;   // (ordered before the next SWEEP by the publication's release fence)
+          if (BK_IS_MULTI(P)) for (int j = 0; j < 8; ++j) P.acc_sd[(size_t)c * 8 + j] = 0ull;   // (ordered before the next SWEEP by the publication's release fence)
         }
         hot->c_tree_updates += 1;
         bk_trace_rec* rec = trace_at(P, c, hot->trace_round_base);
-        if (rec) rec->aux = (double)(P.K > 1 ? hot->leaf_sdk[P.K - 1] : hot->leaf_sd);
+        if (rec) rec->aux = (double)(BK_IS_MULTI(P) ? hot->leaf_sdk[P.K - 1] : hot->leaf_sd);
         hot->trace_round_base += 1;
       }
       if (sj.do_prologue) {
@@ -1165,7 +1187,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
     MARK(111);
   } else if (stage == BK_ST_WAIT_ROUND) {
     MARK(120);
-    finalize_own(P, c, hot, sh, hot->buf, hot->round, hot->cur_tree, hot->trace_round_base);
+    finalize_own<MODE>(P, c, hot, sh, hot->buf, hot->round, hot->cur_tree, hot->trace_round_base);
     TSUB(0);
     MARK(121);
     if (P.lik != BK_LIK_NORMAL && hot->n_grow > 0) {
@@ -1174,7 +1196,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       const int ng = hot->n_grow;
       const uint4* s4 = reinterpret_cast<const uint4*>(sh.jobs);
       for (int i = BK_WTID; i >= 0 && i < ng * 3; i += BK_WTHREADS) reinterpret_cast<uint4*>(ctl->jobs[0])[i] = s4[i];
-      if (P.K > 1)
+      if (BK_IS_MULTI(P))
         for (int i = BK_WTID; i >= 0 && i < ng * 2 * BK_MAX_OUTPUTS; i += BK_WTHREADS) (&ctl->job_vals[0][0][0])[i] = (&sh.job_vals[0][0][0])[i];
       if (threadIdx.x == 0) { hot->n_jobs = ng; hot->cmd = BK_CMD_LL; hot->stage_next = BK_ST_WAIT_LL; }
       CTRL_SYNC();
@@ -1210,7 +1232,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       if (threadIdx.x == 0) { hot->c_rounds += 1; hot->trace_round_base = rbase + (P.P - 1); }
       MARK(130 + live);
       TSUB(1);
-      if (!live) { CTRL_SYNC(); finish_tree(P, c, ctl, hot, sh); TSUB(7); MARK(139); return; }
+      if (!live) { CTRL_SYNC(); finish_tree<MODE>(P, c, ctl, hot, sh); TSUB(7); MARK(139); return; }
       round = round_done + 1; rb = rbase + (P.P - 1); deferred = true;
       if (q >= 0 && q < 128) {   // warps 1..4: the particle threads resample for themselves
         const uint32_t u = (sh.pre_z_tree == t && sh.pre_z_round == round_done)
@@ -1225,7 +1247,7 @@ __device__ void control_step(const Params& P, int c, int phase, int tune, const 
       TSUB(2);
     }
     MARK(140);
-    const int nj = open_round(P, c, ctl, hot, sh, buf, round, rb, deferred, src);
+    const int nj = open_round<MODE>(P, c, ctl, hot, sh, buf, round, rb, deferred, src);
     MARK(141);
     if (threadIdx.x == 0) {   // (every thread took its copies of these before the barriers inside open_round)
       hot->round = round; sh.live = 0;
@@ -1584,7 +1606,8 @@ __device__ __forceinline__ void ll_unit_multi(const Params& P, int c, int tile, 
 
 // ------------------------------------------------------------------ data phase: SWEEP
 // Group-wide: BK_GROUP_THREADS threads x 4 rows.  Fuses commit of tree A with prologue of tree B.
-__device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, const int g, const int tid) {
+template <int MODE>
+__device__ __forceinline__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, const int g, const int tid) {
   const ChainCtl* ctl = P.ctl + c;
   const int4 s0 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep));
   const int4 s1 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep) + 1);
@@ -1716,7 +1739,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
     unsigned long long v2 = warp_sum_u64(t_r2 >> 32);
     unsigned long long v3 = warp_sum_u64((unsigned long long)t_sst);
     unsigned long long v4 = warp_sum_u64((unsigned long long)t_sd);
-    unsigned long long v5 = (BK_MISSING_ENABLED && P.has_nan) ? warp_sum_u64((unsigned long long)t_limbo) : 0ull;
+    unsigned long long v5 = BK_MISSING_ENABLED ? warp_sum_u64((unsigned long long)t_limbo) : 0ull;
     if ((tid & 31) == 0) {
       atomicAdd(&sh.tot_acc[0], v0); atomicAdd(&sh.tot_acc[1], v1); atomicAdd(&sh.tot_acc[2], v2);
       atomicAdd(&sh.tot_acc[3], v3); atomicAdd(&sh.tot_acc[4], v4);
@@ -1741,7 +1764,7 @@ __device__ void sweep_unit(const Params& P, int c, int ctile, GroupShared& sh, c
 // B — looped over the K outputs (the leaf-value tables of one output at a time in shared memory), then ONE pass of
 // per-row log-likelihood terms with all K linear predictors: the old tree's leaf of the row (per-leaf sums, particle 0)
 // and the root-only stump (total).
-__device__ void sweep_unit_multi(const Params& P, int c, int ctile, GroupShared& sh, const int g, const int tid) {
+__device__ __forceinline__ void sweep_unit_multi(const Params& P, int c, int ctile, GroupShared& sh, const int g, const int tid) {
   const ChainCtl* ctl = P.ctl + c;
   const int4 s0 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep));
   const int4 s1 = __ldcg(reinterpret_cast<const int4*>(&ctl->sweep) + 1);
@@ -1910,7 +1933,7 @@ __device__ __forceinline__ void prefetch_l2_range(const void* base, size_t bytes
   const char* b = reinterpret_cast<const char*>(base);
   for (size_t o = first * 128; o < bytes; o += stride * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
 }
-__device__ void cold_start_prefetch(const Params& P, const int tune) {
+__device__ __forceinline__ void cold_start_prefetch(const Params& P, const int tune) {
   const size_t W = gridDim.x - P.C, first = (size_t)(blockIdx.x - P.C) * BK_CTA_THREADS + threadIdx.x, stride = W * BK_CTA_THREADS;
   const size_t col = (size_t)P.Npad * 4;
   if ((size_t)P.p * col <= ((size_t)48 << 20)) prefetch_l2_range(P.X, (size_t)P.p * col, first, stride);   // (larger X does not fit the L2 anyway)
@@ -1927,7 +1950,8 @@ __device__ void cold_start_prefetch(const Params& P, const int tune) {
   }
 }
 
-__device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const unsigned epoch_base) {
+template <int MODE>
+__device__ __forceinline__ void worker_loop(const Params& P, GroupShared& sh, const int g, const unsigned epoch_base) {
   const int tid = (int)threadIdx.x - g * BK_GROUP_THREADS, warp = tid >> 5;
   const int W = gridDim.x - P.C, w = blockIdx.x - P.C;
   const int c_first = P.C >= BK_NGROUPS ? g : g % P.C, c_step = P.C >= BK_NGROUPS ? BK_NGROUPS : P.C;
@@ -2007,7 +2031,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
         const uint4* g4 = reinterpret_cast<const uint4*>(P.ctl[wk.chain].jobs[(w * BK_NGROUPS + g) % BK_JOB_COPIES]);   // readers spread over the copies
         uint4* d4 = reinterpret_cast<uint4*>(sh.jobs);
         for (int i = tid; i < wk.njobs * 3; i += BK_GROUP_THREADS) d4[i] = __ldcg(g4 + i);
-        if (P.K > 1) {   // shared-tree multi-output: per-output accumulators (ROUND) / the jobs' leaf values (LL)
+        if (BK_IS_MULTI(P)) {   // shared-tree multi-output: per-output accumulators (ROUND) / the jobs' leaf values (LL)
           if (wk.cmd == BK_CMD_ROUND) {
             unsigned* z = &sh.u.acck[0][0][0];
             for (int i = tid; i < wk.njobs * BK_MAX_OUTPUTS * 4; i += BK_GROUP_THREADS) z[i] = 0u;
@@ -2028,11 +2052,11 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
         const unsigned tile = lo / (unsigned)wk.njobs, j0 = lo - tile * (unsigned)wk.njobs;
         const unsigned seg = (unsigned)wk.njobs - j0 < hi - lo ? (unsigned)wk.njobs - j0 : hi - lo;
         if (wk.cmd == BK_CMD_ROUND) {
-          if (P.K > 1) round_unit<false, true>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.acck);
-          else if (BK_MISSING_ENABLED && P.has_nan) round_unit<true, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr);
+          if (BK_IS_MULTI(P)) round_unit<false, true>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.acck);
+          else if (BK_MISSING_ENABLED) round_unit<true, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr);
           else round_unit<false, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr);
         }
-        else if (P.K > 1) ll_unit_multi(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.job_vals);
+        else if (BK_IS_MULTI(P)) ll_unit_multi(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.job_vals);
         else ll_unit(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
         lo += seg;
       }
@@ -2043,7 +2067,7 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
         const unsigned long long v = take_stat(sh.acc + ji * BK_LIMBS, k);
         if (v) red_add_u64(P.accL + ((size_t)wk.chain * P.P + jobs[ji].slot) * BK_ACC_STRIDE + k, v);
       }
-      if (P.K > 1 && wk.cmd == BK_CMD_ROUND) {   // per-output sums of both children: (lo, hi) limbs -> one global atomic each
+      if (BK_IS_MULTI(P) && wk.cmd == BK_CMD_ROUND) {   // per-output sums of both children: (lo, hi) limbs -> one global atomic each
         for (int i = tid; i < wk.njobs * P.K * 2; i += BK_GROUP_THREADS) {
           const int ji = i / (P.K * 2), j = (i / 2) % P.K, side = i & 1;
           const unsigned lo = sh.u.acck[ji][j][2 * side], hi = sh.u.acck[ji][j][2 * side + 1];
@@ -2053,8 +2077,8 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
       }
     } else {  // BK_CMD_SWEEP: group-wide row tiles, round robin over all serving groups
       for (unsigned u = wk.lo; u < (unsigned)wk.total; u += wk.hi) {
-        if (P.K > 1) sweep_unit_multi(P, wk.chain, (int)u, sh, g, tid);
-        else sweep_unit(P, wk.chain, (int)u, sh, g, tid);
+        if (BK_IS_MULTI(P)) sweep_unit_multi(P, wk.chain, (int)u, sh, g, tid);
+        else sweep_unit<MODE>(P, wk.chain, (int)u, sh, g, tid);
       }
     }
     GROUP_SYNC(g);   // every warp's stores are ordered before the release below
@@ -2066,7 +2090,8 @@ __device__ void worker_loop(const Params& P, GroupShared& sh, const int g, const
 }
 
 // ---- control CTA of chain c: wait for the previous epoch, run the state machine, publish the next
-__device__ bool control_loop(const Params& P, int c, int tune, const StepArgs& A, int max_phases, CtlShared& sh) {
+template <int MODE>
+__device__ __forceinline__ bool control_loop(const Params& P, int c, int tune, const StepArgs& A, int max_phases, CtlShared& sh) {
   __shared__ int s_abort, s_fin;
   __shared__ ChainHot s_hot;
   ChainCtl* ctl = P.ctl + c;
@@ -2076,7 +2101,6 @@ __device__ bool control_loop(const Params& P, int c, int tune, const StepArgs& A
   // read-only tables of the round path: the control CTA's L1 is dropped by every acquire fence, so a global table
   // costs an L2 round trip per phase
   if (threadIdx.x < 64) sh.p_leaf[threadIdx.x] = P.p_leaf[threadIdx.x];
-  if (threadIdx.x == 0) sh.params_copy = P;
   for (int i = threadIdx.x; i < P.P * BK_ACC_STRIDE; i += BK_CTRL_THREADS)
     sh.acc_prev[i / BK_ACC_STRIDE][i % BK_ACC_STRIDE] = __ldcg(P.accL + (size_t)c * P.P * BK_ACC_STRIDE + i);
   for (int v = threadIdx.x; v < P.p && v < BK_CUM_SMEM; v += BK_CTRL_THREADS) sh.rules[v] = (signed char)P.rules[v];
@@ -2113,7 +2137,7 @@ __device__ bool control_loop(const Params& P, int c, int tune, const StepArgs& A
     CTRL_SYNC();
     if (s_abort) return false;
     CTS(16, 0);
-    control_step(P, c, phase, tune, A, hot, sh);
+    control_step<MODE>(P, c, phase, tune, A, hot, sh);
     CTRL_SYNC();
     CTS(23, 0);
     if (threadIdx.x == 0) {
@@ -2167,16 +2191,24 @@ __device__ bool control_loop(const Params& P, int c, int tune, const StepArgs& A
 // ------------------------------------------------------------------ the step kernel
 __global__ void __launch_bounds__(BK_CTA_THREADS, 1)
 pgbart_step_kernel(const Params P, const int tune, const StepArgs A, const int max_phases) {
+  const int mode = P.K > 1 ? BK_MODE_MULTI : (P.has_nan ? BK_MODE_MISSING : BK_MODE_PLAIN);   // (uniform over the grid)
   if ((int)blockIdx.x < P.C) {
     __shared__ KernelShared sh;
-    if (threadIdx.x < BK_CTRL_THREADS) control_loop(P, blockIdx.x, tune, A, max_phases, sh.ctl);
+    if (threadIdx.x < BK_CTRL_THREADS) {
+      if (mode == BK_MODE_PLAIN) control_loop<BK_MODE_PLAIN>(P, blockIdx.x, tune, A, max_phases, sh.ctl);
+      else if (mode == BK_MODE_MISSING) control_loop<BK_MODE_MISSING>(P, blockIdx.x, tune, A, max_phases, sh.ctl);
+      else control_loop<BK_MODE_MULTI>(P, blockIdx.x, tune, A, max_phases, sh.ctl);
+    }
     return;
   }
   const int g = threadIdx.x / BK_GROUP_THREADS;
 #ifndef BK_NO_COLD_PREFETCH
   cold_start_prefetch(P, tune);
 #endif
-  worker_loop(P, reinterpret_cast<GroupShared*>(bk_dyn_smem)[g], g, A.epoch_base);
+  GroupShared& gs = reinterpret_cast<GroupShared*>(bk_dyn_smem)[g];
+  if (mode == BK_MODE_PLAIN) worker_loop<BK_MODE_PLAIN>(P, gs, g, A.epoch_base);
+  else if (mode == BK_MODE_MISSING) worker_loop<BK_MODE_MISSING>(P, gs, g, A.epoch_base);
+  else worker_loop<BK_MODE_MULTI>(P, gs, g, A.epoch_base);
 }
 
 // ------------------------------------------------------------------ init kernel
