@@ -321,6 +321,32 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     h2d = nvc * 4
     d2h = nvc * N * 4 + nvc * p * 4 + nvc * 64 + 4 + int(getattr(stp, "history_bytes_per_step", 0))
     h2d_once = stp.core.h2d_bytes
+    # ---------------- posterior prediction from the history the e2e leg just published (row N1): all chains, one launch
+    predict = None
+    try:
+        from pymc_bart_b200.utils import _get_posterior_sampler
+
+        sampler = _get_posterior_sampler(rv.owner.op)
+        n_d = min(sampler.n_draws, 64)
+        picks = np.arange(n_d) * (sampler.n_draws // n_d)
+        Xd = sampler.upload(X)
+        sampler._forests.predict(Xd, picks)                       # warm-up (module load, first launch)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        p0.record()
+        for _ in range(reps):
+            pred = sampler._forests.predict(Xd, picks)
+        p1.record()
+        torch.cuda.synchronize()
+        ms = p0.elapsed_time(p1) / reps
+        predict = {"value": N * m * n_d * sampler.n_outputs / (ms / 1e3), "unit": "row-tree walks/s", "ms_per_call": ms,
+                   "rows": N, "trees": m, "draws": int(n_d), "outputs": int(sampler.n_outputs), "chains_in_store": int(sampler.n_chains),
+                   "history_bytes_on_device": int(sampler._forests.history_bytes),
+                   "note": "one bk_predict_history launch over all chains' draws, X resident, output [draws][outputs][rows] float32 on the device"}
+        del pred, Xd, sampler
+    except Exception as e:  # noqa
+        predict = {"value": None, "note": f"failed: {e}"}
     stp.close()
     del stp
     if rank != 0:
@@ -349,6 +375,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
         "e2e": {"value": e2e_val, "unit": "draws/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build,
                 "history": "store_history=True: after tuning every step's rewritten trees are exported (op.all_trees protocol)"},
+        "predict": predict,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "frac_dram_traffic": (traffic / (ms_kernel / 1e3) / 1e9 / peak) if traffic else None,
@@ -419,7 +446,7 @@ def main():
         else:
             config = {k: main_m[k] for k in ("workload", "draws_timed", "l2", "grow_events_per_tree_update", "tree_updates_per_s",
                                              "grow_events_per_s", "rounds_per_tree_update", "grid_phases_per_step", "in_kernel_us", "gather_ms",
-                                             "gather_bytes_per_rank")}
+                                             "gather_bytes_per_rank", "predict")}
             if c5_m is not None:
                 c5_m["n_gpus"] = world
                 c5_m["gpu_launches"] = c5_m["steps"]
