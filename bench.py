@@ -238,29 +238,38 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
         with torch.cuda.stream(stream):
             dist.all_gather_into_tensor(gathered, draws_dev)
     sync_all()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    # K steps in launches of `spl` steps (bk_run_launch: the chains of a launch do not wait for each other between steps and
+    # no launch gap separates them; sigma is fixed in this benchmark).  A launch never mixes tuning and
+    # posterior steps; the posterior steps' draws are written into the ring by each step's last commit.
+    spl = max(1, min(int(args.steps_per_launch), dev.MAX_STEPS_PER_LAUNCH))
+    plan = []
+    i = 0
+    while i < steps:
+        tune = i < n_tune
+        n = min(spl, (n_tune if tune else steps) - i)
+        plan.append((i, n, tune))
+        i += n
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in plan]
     grow = tupd = tune_upd = rounds = phases = 0
     us_total = us_control = us_data = 0
     us_by_phase = {True: 0.0, False: 0.0}
     t_w0 = time.perf_counter()
-    for i in range(steps):
-        tune = i < n_tune
+    for li, (i0, n, tune) in enumerate(plan):
         if flush is not None:
             with torch.cuda.stream(stream):
-                flush.fill_(i & 0xFF)   # untimed: evicts the working set from the 126 MB L2
-        ev[i][0].record(stream)
-        dev.step_launch(tune, 1.0)
-        if not tune:
-            with torch.cuda.stream(stream):
-                draws_dev[i - n_tune].copy_(dev.sum_trees_dev, non_blocking=True)   # the draw is kept (inside the timed step)
-        ev[i][1].record(stream)
-        _, st = dev.step_wait()
-        for c in range(nvc):
-            grow += st[c].grow_events; tupd += st[c].tree_updates; rounds += st[c].rounds
-            tune_upd += st[c].tree_updates if tune else 0
-        phases += st[0].phases
-        us_total += max(st[c].us_total for c in range(nvc)); us_control += st[0].us_control; us_data += st[0].us_data
-        us_by_phase[tune] += max(st[c].us_total for c in range(nvc))
+                flush.fill_(li & 0xFF)   # untimed: evicts the working set from the 126 MB L2
+        ev[li][0].record(stream)
+        dev.run_launch(n, tune, 1.0, draws_out=None if tune else draws_dev[i0 - n_tune: i0 - n_tune + n])
+        ev[li][1].record(stream)
+        _, sts = dev.run_wait()
+        for st in sts:
+            for c in range(nvc):
+                grow += st[c].grow_events; tupd += st[c].tree_updates; rounds += st[c].rounds
+                tune_upd += st[c].tree_updates if tune else 0
+            phases += st[0].phases
+        last = sts[-1]           # (the launch-wide in-kernel timers travel with the last step's record)
+        us_total += max(last[c].us_total for c in range(nvc)); us_control += last[0].us_control; us_data += last[0].us_data
+        us_by_phase[tune] += max(last[c].us_total for c in range(nvc))
     t_gather0 = torch.cuda.Event(enable_timing=True); t_gather1 = torch.cuda.Event(enable_timing=True)
     t_gather0.record(stream)
     if world > 1:   # the run's single collective (sampling.gather_posterior): ordered after the steps on their stream
@@ -269,9 +278,10 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     t_gather1.record(stream)
     torch.cuda.synchronize()
     clocks.window(t_w0, time.perf_counter())
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    launch_ms = [a.elapsed_time(b) for a, b in ev]
+    step_ms = [ms / n for ms, (_, n, _) in zip(launch_ms, plan) for _ in range(n)]      # per step, for the tuning / posterior split
     gather_ms = t_gather0.elapsed_time(t_gather1) if world > 1 else 0.0
-    total_ms = float(sum(step_ms)) + gather_ms
+    total_ms = float(sum(launch_ms)) + gather_ms
     tm = torch.tensor([total_ms, gather_ms], dtype=torch.float64, device="cuda")
     agg = torch.tensor([float(grow), float(tupd), float(tune_upd)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -281,6 +291,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     g_all, t_all, tu_all = [float(v) for v in agg.tolist()]
     value = world * chains * steps / (total_ms_max / 1e3)
     out = {"value": value, "unit": "draws/s", "ms_per_step": total_ms_max / steps, "steps": steps, "warmup": warm,
+           "steps_per_launch": spl, "launches": len(plan),
            "in_kernel_us": {"step": us_total / steps, "control_chain0": us_control / steps, "data_wait_chain0": us_data / steps,
                             "step_tuning": us_by_phase[True] / max(n_tune, 1), "step_post": us_by_phase[False] / max(n_post, 1),
                             "event_tuning": 1e3 * float(np.mean(step_ms[:n_tune])) if n_tune else None,
@@ -409,6 +420,7 @@ def main():
     ap.add_argument("--cpu-draws", type=int, default=None, help="CPU baseline sample size (draws per chain)")
     ap.add_argument("--profile-only", action="store_true", help="device-timed leg only (for ncu runs)")
     ap.add_argument("--clock-ms", type=int, default=20, help="nvidia-smi sampling period in ms (0 = no clock sampling)")
+    ap.add_argument("--steps-per-launch", type=int, default=16, help="steps of every chain per kernel launch in the device-timed leg (1..16)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -442,20 +454,21 @@ def main():
     if rank == 0:
         if args.profile_only:
             print(json.dumps({"profile_only": True, "value": main_m["value"], "ms_per_step": main_m["ms_per_step"],
-                              "in_kernel_us": main_m["in_kernel_us"]}), flush=True)
+                              "steps_per_launch": main_m["steps_per_launch"], "in_kernel_us": main_m["in_kernel_us"]}), flush=True)
         else:
             config = {k: main_m[k] for k in ("workload", "draws_timed", "l2", "grow_events_per_tree_update", "tree_updates_per_s",
-                                             "grow_events_per_s", "rounds_per_tree_update", "grid_phases_per_step", "in_kernel_us", "gather_ms",
+                                             "grow_events_per_s", "rounds_per_tree_update", "grid_phases_per_step", "in_kernel_us",
+                                             "steps_per_launch", "launches", "gather_ms",
                                              "gather_bytes_per_rank", "predict")}
             if c5_m is not None:
                 c5_m["n_gpus"] = world
-                c5_m["gpu_launches"] = c5_m["steps"]
+                c5_m["gpu_launches"] = c5_m["launches"]
                 config["c5"] = c5_m
             line = {
                 "metric": "PGBART draws/sec", "value": main_m["value"], "unit": "draws/s", "n_gpus": world, "steps": steps, "warmup": warm,
                 "ms_per_step": main_m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32+i64", "data": "synthetic", "config": config,
-                "gpu_launches": steps, "e2e": main_m["e2e"], "roofline": main_m["roofline"], "clocks": clk,
+                "gpu_launches": main_m["launches"], "e2e": main_m["e2e"], "roofline": main_m["roofline"], "clocks": clk,
                 "cpu_baseline": main_m.get("cpu_baseline"),
             }
             print(json.dumps(line), flush=True)

@@ -164,6 +164,16 @@ int bk_step(bk_handle* h, int tune, const float* sigma_host, int32_t* vi_counts_
  * cudaStream_t (as void*) so the host can record events on it or order its own copies after it. */
 int bk_step_launch(bk_handle* h, int tune, const float* sigma_host);
 int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host);
+
+/* Several steps in ONE launch (1 <= n_steps <= 16) for drivers whose likelihood parameters do not change between steps
+ * (the reference's `pm.sample` with a fixed scale; not usable when another step method updates sigma between draws):
+ * every chain runs its n_steps back to back inside the persistent kernel, so chains do not wait for each other at step
+ * boundaries and no launch gap separates the steps.  draws_dev: NULL, or device memory [n_steps][n_chains*max(n_groups,
+ * n_outputs)][ld] float32 that receives the sum of trees after every step (the posterior draws stay on the device).
+ * bk_run_wait returns the steps' outputs in order: vi_counts_host [n_steps][..][n_cols], stats_host [n_steps][..].
+ * Tree-history capture (bk_set_history) and the trace need one step per launch.  bk_step_launch/wait = n_steps 1. */
+int bk_run_launch(bk_handle* h, int n_steps, int tune, const float* sigma_host, float* draws_dev);
+int bk_run_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host);
 void* bk_stream(bk_handle* h);
 
 /* Host copy of the value (tests/test_bart.py:121-123,197: the step returns the new value of the BART variable as a

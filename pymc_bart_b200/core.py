@@ -92,6 +92,29 @@ class DeviceSampler:
         _cabi.check(self.lib.bk_step_wait(self.h, self._vi.ctypes.data, C.cast(self._stats, C.c_void_p)), "bk_step_wait")
         return self._vi, self._stats
 
+    # ---- several steps per launch (fixed likelihood parameters between them) -----------------------------------------
+    MAX_STEPS_PER_LAUNCH = 16
+
+    def run_launch(self, n_steps: int, tune: bool, sigma=1.0, draws_out=None):
+        """Enqueue n_steps steps of every chain as ONE launch.  draws_out: None or a float32 CUDA tensor
+        [n_steps, C*K, ld] that receives the sum of trees after every step."""
+        self._sigma[...] = np.asarray(sigma, dtype=np.float32)
+        ptr = None
+        if draws_out is not None:
+            if tuple(draws_out.shape) != (int(n_steps), self.rows, self.ld) or draws_out.dtype != self.torch.float32 or not draws_out.is_contiguous():
+                raise ValueError(f"draws_out must be a contiguous float32 tensor of shape ({n_steps}, {self.rows}, {self.ld})")
+            ptr = draws_out.data_ptr()
+        _cabi.check(self.lib.bk_run_launch(self.h, int(n_steps), int(bool(tune)), self._sigma.ctypes.data, ptr), "bk_run_launch")
+        self._run_n = int(n_steps)
+
+    def run_wait(self):
+        """(vi counts [n_steps][C][p] int32, stats [n_steps][C]) of the oldest launch in flight."""
+        n = self._run_n
+        vi = np.zeros((n, self.C, self.p), dtype=np.int32)
+        stats = (_cabi.BkStepStats * (n * self.C))()
+        _cabi.check(self.lib.bk_run_wait(self.h, vi.ctypes.data, C.cast(stats, C.c_void_p)), "bk_run_wait")
+        return vi, [stats[i * self.C:(i + 1) * self.C] for i in range(n)]
+
     def stream(self):
         """torch view of the sampler's CUDA stream (for events and ordered copies)."""
         return self.torch.cuda.ExternalStream(int(self.lib.bk_stream(self.h)), device=self.device)

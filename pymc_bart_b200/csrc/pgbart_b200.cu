@@ -172,7 +172,14 @@ __shared__ long long s_ct_last;
 struct StepArgs {
   float sigma[64];       // likelihood scale of every (chain, group)
   unsigned epoch_base;   // epoch ids of this launch start above it
+  int n_steps;           // steps of every chain in this launch (chains do not wait for each other between steps)
 };
+__device__ __forceinline__ bk_step_stats* step_stats(const Params& P, int step, int c) {
+  return reinterpret_cast<bk_step_stats*>(reinterpret_cast<char*>(P.stats) + (size_t)step * P.rec_stride) + c;
+}
+__device__ __forceinline__ int32_t* step_vi(const Params& P, int step, int c) {
+  return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(P.vi) + (size_t)step * P.rec_stride) + (size_t)c * P.p;
+}
 struct CtlShared {
   double lw[BK_MAX_PARTICLES];
   int anc[BK_MAX_PARTICLES];
@@ -1076,7 +1083,7 @@ __device__ __forceinline__ void finish_tree(const Params& P, int c, ChainCtl* ct
     }
     for (int k = BK_WTID; k >= 0 && k < new_nn; k += BK_WTHREADS) {
       const int v = W.node(k).var;
-      if (v >= 0) { if (hot->tune) atomicAdd(&av[v], 1.0); else atomicAdd(P.vi + (size_t)c * P.p + v, 1); }
+      if (v >= 0) { if (hot->tune) atomicAdd(&av[v], 1.0); else atomicAdd(step_vi(P, hot->step_in_launch, c) + v, 1); }
     }
   }
   if (threadIdx.x == 0) {
@@ -1085,6 +1092,7 @@ __device__ __forceinline__ void finish_tree(const Params& P, int c, ChainCtl* ct
     sj.do_commit = 1; sj.commit_tree = t; sj.new_row = W.h->row; sj.do_welford = hot->tune ? 1 : 0;
     sj.wf_count = hot->wf_count + (hot->tune ? 1 : 0);
     sj.do_prologue = (t + 1 < hot->tree_hi) ? 1 : 0; sj.prologue_tree = t + 1;
+    sj.draw_slot = (P.draws_out && !sj.do_prologue) ? hot->step_in_launch + 1 : 0;   // the step's last commit also keeps the draw
     ctl->sweep = sj;
     hot->cmd = BK_CMD_SWEEP; hot->stage_next = BK_ST_WAIT_SWEEP;
     // kind-2 trace record is completed after the sweep (leaf_sd); stash its fields now
@@ -1105,7 +1113,7 @@ __device__ __forceinline__ void control_step(const Params& P, int c, int phase, 
   ChainCtl* ctl = P.ctl + c;
   if (first_phase) {
     if (threadIdx.x == 0) {
-      hot->stage = BK_ST_START; hot->stage_next = BK_ST_START; hot->tune = tune; hot->sigma = A.sigma[c];
+      hot->stage = BK_ST_START; hot->stage_next = BK_ST_START; hot->tune = tune; hot->sigma = A.sigma[c]; hot->step_in_launch = 0;
       hot->ll_inv2s2 = bk_normal_inv2s2(hot->sigma); hot->ll_c = bk_normal_const(hot->sigma, (double)P.N);
     }
     CTRL_SYNC();
@@ -1118,8 +1126,11 @@ __device__ __forceinline__ void control_step(const Params& P, int c, int phase, 
   if (stage == BK_ST_DONE) return;
   if (threadIdx.x == 0) hot->c_phases += 1;
 
-  if (stage == BK_ST_START) {
-    for (int v = BK_WTID; v >= 0 && v < P.p; v += BK_WTHREADS) P.vi[(size_t)c * P.p + v] = 0;
+  // first phase of a step (of the launch, or right after the previous step's last commit): clear the step's counters,
+  // pick the tree batch, publish the prologue of its first tree
+  auto begin_step = [&]() {
+    int32_t* vis = step_vi(P, hot->step_in_launch, c);
+    for (int v = BK_WTID; v >= 0 && v < P.p; v += BK_WTHREADS) vis[v] = 0;
     zero_acc0(P, c);
     if (threadIdx.x == 0) {
       int T = hot->tune ? P.batch_tune : P.batch_post;
@@ -1133,8 +1144,8 @@ __device__ __forceinline__ void control_step(const Params& P, int c, int phase, 
       ctl->sweep = sj; hot->cmd = BK_CMD_SWEEP; hot->stage_next = BK_ST_WAIT_SWEEP;
     }
     CTRL_SYNC();
-    return;
-  }
+  };
+  if (stage == BK_ST_START) { begin_step(); return; }
 
   // `closing` = a round of the current tree has just completed (its epoch is done); false right after init_particles
   bool closing = false;
@@ -1167,20 +1178,22 @@ __device__ __forceinline__ void control_step(const Params& P, int c, int phase, 
       if (sj.do_prologue) {
         hot->iter += 1; hot->cur_tree = sj.prologue_tree; s_more = 1;
       } else {
-        s_more = 0;
         hot->lower = hot->tree_hi < P.m ? hot->tree_hi : 0;
         hot->draw += 1;
-        hot->cmd = BK_CMD_DONE; hot->stage_next = BK_ST_DONE;
+        s_more = (hot->step_in_launch + 1 < A.n_steps) ? 2 : 0;     // 2: this chain's next step starts right away
+        if (!s_more) { hot->cmd = BK_CMD_DONE; hot->stage_next = BK_ST_DONE; }
         bk_step_stats st; memset(&st, 0, sizeof(st));
         st.tree_updates = hot->c_tree_updates; st.rounds = hot->c_rounds; st.grow_events = hot->c_grow;
         st.grow_root = hot->c_grow_root; st.count_passes = hot->c_count_passes; st.phases = hot->c_phases;
         st.trace_len = hot->trace_round_base; st.error_flags = hot->c_err | (hot->trace_round_base > P.trace_cap && P.trace_cap > 0 ? 1 : 0);
         st.leaf_sd = hot->leaf_sd; st.iter = hot->iter;
-        P.stats[c] = st;
+        *step_stats(P, hot->step_in_launch, c) = st;
+        if (s_more) hot->step_in_launch += 1;
       }
     }
     CTRL_SYNC();
     if (!s_more) return;
+    if (s_more == 2) { begin_step(); return; }
     MARK(110);
     init_particles(P, c, ctl, hot, sh);
     TSUB(7);
@@ -1674,6 +1687,8 @@ __device__ __forceinline__ void sweep_unit(const Params& P, int c, int ctile, Gr
         }
       }
       __stcg(reinterpret_cast<float4*>(stp), make_float4(stv[0], stv[1], stv[2], stv[3]));
+      if (s1.w > 0)   // the step's last commit: keep the draw (bk_run_launch's draws_out)
+        __stcs(reinterpret_cast<float4*>(P.draws_out + ((size_t)(s1.w - 1) * P.C + c) * P.Npad + base), make_float4(stv[0], stv[1], stv[2], stv[3]));
       if (new_row != BK_ROW_FOREST) __stcg(reinterpret_cast<unsigned*>(idp), nid4);
       if (do_wf) {
         __stcg(reinterpret_cast<float4*>(mp), make_float4(mean[0], mean[1], mean[2], mean[3]));
@@ -1838,6 +1853,8 @@ __device__ __forceinline__ void sweep_unit_multi(const Params& P, int c, int cti
           }
         }
         __stcg(reinterpret_cast<float4*>(stp), make_float4(stv[0], stv[1], stv[2], stv[3]));
+        if (s1.w > 0)
+          __stcs(reinterpret_cast<float4*>(P.draws_out + (((size_t)(s1.w - 1) * P.C + c) * K + j) * P.Npad + base), make_float4(stv[0], stv[1], stv[2], stv[3]));
         if (do_wf) {
           __stcg(reinterpret_cast<float4*>(mp), make_float4(mean[0], mean[1], mean[2], mean[3]));
           __stcg(reinterpret_cast<float4*>(m2p), make_float4(m2[0], m2[1], m2[2], m2[3]));
@@ -2171,7 +2188,7 @@ __device__ __forceinline__ bool control_loop(const Params& P, int c, int tune, c
 #ifdef BK_PROFILE_CTRL
         if (c == 0) for (int i = 0; i < 32; ++i) g_cdbg[i] += s_cdbg[i];
 #endif
-        bk_step_stats* st = P.stats + c;
+        bk_step_stats* st = step_stats(P, A.n_steps - 1, c);   // (launch-wide timers go with the last step's record)
         st->us_control = (int32_t)(t_ctrl / 1000ull); st->us_data = (int32_t)(t_wait / 1000ull);
         st->us_sync = (int32_t)(t_pub / 1000ull); st->us_total = (int32_t)((q3 - t_begin) / 1000ull);
         st->reserved[0] = (int32_t)(t_wait_sweep / 1000ull);   // part of us_data spent waiting for SWEEP epochs
@@ -2238,14 +2255,14 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
     for (int j = 1; j < P.K; ++j) set_node_val(nd, j, P.init_leaf);
     P.forest[i * BK_MAX_NODES] = nd;
   }
-  for (size_t i = tid; i < (size_t)P.C * P.p; i += nth) { P.alpha_vec[i] = split_prior[i % P.p]; P.vi[i] = 0; }
+  for (size_t i = tid; i < (size_t)P.C * P.p; i += nth) P.alpha_vec[i] = split_prior[i % P.p];
+  for (size_t i = tid; i < (size_t)BK_MAX_STEPS_PER_LAUNCH * P.rec_stride / 4; i += nth) reinterpret_cast<int32_t*>(P.stats)[i] = 0;
   for (size_t c = tid; c < (size_t)P.C; c += nth) {
     ChainCtl* ctl = P.ctl + c;
     ctl->hot.tune = 1; ctl->hot.sigma = 1.0f; ctl->hot.iter = 0; ctl->hot.lower = 0; ctl->hot.draw = 0; ctl->hot.wf_count = 0;
     ctl->hot.leaf_sd = leaf_sd_init; ctl->hot.stage = BK_ST_DONE;
     for (int j = 0; j < BK_MAX_OUTPUTS; ++j) ctl->hot.leaf_sdk[j] = leaf_sd_init; ctl->hot.cmd = BK_CMD_DONE; ctl->hot.n_jobs = 0;
     ctl->hot.c_err = 0; ctl->hot.trace_round_base = 0;
-    memset(&P.stats[c], 0, sizeof(bk_step_stats));
   }
   if (tid == 0) *P.abort_flag = 0;
   for (size_t i = tid; i < (size_t)P.C * (sizeof(ChainSync) / 4); i += nth) reinterpret_cast<unsigned int*>(P.sync)[i] = 0u;
@@ -2309,7 +2326,8 @@ struct bk_handle_s {
   int last_slot;
   int history;                 // capture the rewritten trees of post-tuning steps
   int host_lower;              // host mirror of the chains' `lower` (first tree of the next batch)
-  size_t out_off_dev, out_bytes, out_stats_off, out_abort_off;
+  size_t out_off_dev, out_bytes, out_stats_off, out_abort_off, rec_stride;
+  int steps_in_slot[2];        // steps of the launch that owns the slot
   StepArgs args;
   int32_t* abort_pinned;
   int host_output;
@@ -2322,8 +2340,9 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   size_t qr, qst, ids_tree, rows, rowcnt, coarse, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, accK, acc_sd, alpha_vec, cum,
-      p_leaf, rules, col_nan, vi, stats, trace, sync, abort_flag, split_prior, total;
+      p_leaf, rules, col_nan, stats, trace, sync, abort_flag, split_prior, total;
   int Npad, ntiles, R, nb;
+  size_t rec_stride;
 };
 
 static int make_layout(const bk_settings* s, Layout* L) {
@@ -2370,9 +2389,11 @@ static int make_layout(const bk_settings* s, Layout* L) {
   CARVE(p_leaf, 256 * 8);
   CARVE(rules, p * 4);
   CARVE(col_nan, p * 4);
-  CARVE(vi, C * p * 4);                         // vi | stats | abort_flag stay adjacent: one D2H copy per step
-  CARVE(stats, C * sizeof(bk_step_stats));
+  // abort flag | step records [stats [C] | vi [C][p]] x BK_MAX_STEPS_PER_LAUNCH: ONE D2H copy per launch brings the flag and the
+  // records of the steps that ran
   CARVE(abort_flag, 256);
+  L->rec_stride = align_up(C * sizeof(bk_step_stats) + C * p * 4, 16);
+  CARVE(stats, (size_t)BK_MAX_STEPS_PER_LAUNCH * L->rec_stride);
   CARVE(trace, C * (size_t)(s->trace_capacity > 0 ? s->trace_capacity : 0) * sizeof(bk_trace_rec));
   CARVE(sync, C * sizeof(ChainSync));
   CARVE(split_prior, p * 8);
@@ -2444,7 +2465,8 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   P.ctl = (ChainCtl*)(w + L.ctl); P.accL = (unsigned long long*)(w + L.accL); P.acc0 = (unsigned long long*)(w + L.acc0);
   P.accK = (unsigned long long*)(w + L.accK); P.acc_sd = (unsigned long long*)(w + L.acc_sd);
   P.alpha_vec = (double*)(w + L.alpha_vec); P.cum = (double*)(w + L.cum); P.p_leaf = (double*)(w + L.p_leaf);
-  P.rules = (int32_t*)(w + L.rules); P.col_nan = (int32_t*)(w + L.col_nan); P.vi = (int32_t*)(w + L.vi); P.stats = (bk_step_stats*)(w + L.stats);
+  P.rules = (int32_t*)(w + L.rules); P.col_nan = (int32_t*)(w + L.col_nan); P.stats = (bk_step_stats*)(w + L.stats);
+  P.vi = (int32_t*)(w + L.stats + (size_t)P.C * sizeof(bk_step_stats)); P.rec_stride = (int32_t)L.rec_stride; P.draws_out = nullptr;
   P.trace = (bk_trace_rec*)(w + L.trace); P.sync = (ChainSync*)(w + L.sync); P.abort_flag = (int32_t*)(w + L.abort_flag);
   h->split_prior_dev = (double*)(w + L.split_prior);
 
@@ -2460,15 +2482,16 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
     CK(e);
   }
   // vi, stats and the abort flag are adjacent in the workspace: one D2H copy brings all three back
-  h->out_off_dev = L.vi; h->out_stats_off = L.stats - L.vi; h->out_abort_off = L.abort_flag - L.vi;
-  h->out_bytes = h->out_abort_off + sizeof(int32_t);
+  h->out_off_dev = L.abort_flag; h->out_stats_off = L.stats - L.abort_flag; h->out_abort_off = 0;
+  h->out_bytes = h->out_stats_off + (size_t)BK_MAX_STEPS_PER_LAUNCH * L.rec_stride;
+  h->rec_stride = L.rec_stride;
   for (int k = 0; k < 2; ++k) {
     CK(cudaMallocHost(&h->out_slot[k], h->out_bytes));
     memset(h->out_slot[k], 0, h->out_bytes);
     CK(cudaEventCreateWithFlags(&h->done_ev[k], cudaEventDisableTiming));
   }
-  h->vi_pinned = (int32_t*)h->out_slot[0];
   h->stats_pinned = (bk_step_stats*)(h->out_slot[0] + h->out_stats_off);
+  h->vi_pinned = (int32_t*)(h->out_slot[0] + h->out_stats_off + (size_t)P.C * sizeof(bk_step_stats));
   h->abort_pinned = (int32_t*)(h->out_slot[0] + h->out_abort_off);
   h->workspace = (char*)workspace_dev;
   memset(&h->args, 0, sizeof(h->args));
@@ -2540,8 +2563,12 @@ void bk_destroy(bk_handle* h) {
   delete h;
 }
 
-int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
+int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) { return bk_run_launch(h, 1, tune, sigma_host, nullptr); }
+
+int bk_run_launch(bk_handle* h, int n_steps, int tune, const float* sigma_host, float* draws_dev) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
+  if (n_steps < 1 || n_steps > BK_MAX_STEPS_PER_LAUNCH) { set_err("n_steps must be in [1, 16]"); return BK_ERR_ARG; }
+  if (n_steps > 1 && (h->history || h->s.trace_capacity > 0)) { set_err("tree history / trace capture need one step per launch"); return BK_ERR_STATE; }
   if (h->poisoned) { set_err("an earlier step timed out inside the kernel; the sampler state is undefined: create a new handle"); return BK_ERR_STATE; }
   if (h->n_launched - h->n_waited >= 2) { set_err("two steps are already in flight: call bk_step_wait first"); return BK_ERR_STATE; }
   ON_DEVICE(h->s.device);
@@ -2559,12 +2586,15 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
   }
   const int slot = (int)(h->n_launched & 1);
   const int lo = h->host_lower, T = tune ? P.batch_tune : P.batch_post, hi = lo + T < P.m ? lo + T : P.m;
+  h->args.n_steps = n_steps;
+  P.draws_out = draws_dev;
+  h->steps_in_slot[slot] = n_steps;
   // ONE kernel and ONE small D2H copy per step: the likelihood scales travel as kernel arguments, the epoch ids and
   // done counters of the dataflow run on across launches (no memset), the per-step outputs are adjacent
   void* args[] = {(void*)&P, (void*)&tune_i, (void*)&h->args, (void*)&maxp};
   CK(cudaLaunchCooperativeKernel((const void*)pgbart_step_kernel, dim3(h->grid), dim3(BK_CTA_THREADS), args, h->dyn_smem, h->stream));
   h->args.epoch_base += 1u << 20;   // (max_phases = 2^20 epochs per launch at most)
-  CK(cudaMemcpyAsync(h->out_slot[slot], h->workspace + h->out_off_dev, h->out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->out_slot[slot], h->workspace + h->out_off_dev, h->out_stats_off + (size_t)n_steps * h->rec_stride, cudaMemcpyDeviceToHost, h->stream));
   if (h->host_output)   // the value handed back to PyMC: strided device rows -> dense pinned host rows, behind the kernel
     CK(cudaMemcpy2DAsync(h->st_slot[slot], (size_t)P.N * sizeof(float), P.st, (size_t)P.Npad * sizeof(float), (size_t)P.N * sizeof(float),
                          (size_t)P.C * P.K, cudaMemcpyDeviceToHost, h->stream));
@@ -2581,7 +2611,11 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) {
     h->hist_first[slot] = lo; h->hist_count[slot] = hi - lo;
   }
   CK(cudaEventRecord(h->done_ev[slot], h->stream));
-  h->host_lower = hi < P.m ? hi : 0;
+  {
+    int l = lo;
+    for (int sidx = 0; sidx < n_steps; ++sidx) { const int hh = l + T < P.m ? l + T : P.m; l = hh < P.m ? hh : 0; }
+    h->host_lower = l;
+  }
   h->n_launched += 1;
   return BK_OK;
 }
@@ -2678,7 +2712,9 @@ int bk_export_leaf_values(bk_handle* h, int chain, float* values_host) {
   return BK_OK;
 }
 
-int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host) {
+int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host) { return bk_run_wait(h, vi_counts_host, stats_host); }
+
+int bk_run_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
   if (h->n_waited >= h->n_launched) { set_err("no step in flight"); return BK_ERR_STATE; }
   ON_DEVICE(h->s.device);
@@ -2687,17 +2723,21 @@ int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_hos
   CK(cudaEventSynchronize(h->done_ev[slot]));
   h->n_waited += 1;
   h->last_slot = slot;
-  h->vi_pinned = (int32_t*)h->out_slot[slot];
-  h->stats_pinned = (bk_step_stats*)(h->out_slot[slot] + h->out_stats_off);
+  const int n_steps = h->steps_in_slot[slot];
   h->abort_pinned = (int32_t*)(h->out_slot[slot] + h->out_abort_off);
   if (*h->abort_pinned) { h->poisoned = 1; set_err("a dataflow wait timed out inside the step kernel"); return BK_ERR_TIMEOUT; }
-  if (vi_counts_host) memcpy(vi_counts_host, h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t));
-  if (stats_host) memcpy(stats_host, h->stats_pinned, (size_t)P.C * sizeof(bk_step_stats));
-  for (int c = 0; c < P.C; ++c)
-    if (h->stats_pinned[c].error_flags & ~1) {
-      char buf[64]; snprintf(buf, sizeof(buf), "chain %d flags 0x%x", c, h->stats_pinned[c].error_flags);
-      set_err("device-side consistency check failed: %s", buf); return BK_ERR_STATE;
-    }
+  for (int sidx = 0; sidx < n_steps; ++sidx) {   // records of the launch's steps, in order: [n_steps][C] stats, [n_steps][C][p] counts
+    unsigned char* rec = h->out_slot[slot] + h->out_stats_off + (size_t)sidx * h->rec_stride;
+    h->stats_pinned = (bk_step_stats*)rec;                                      // (the last step's stay current for the trace readers)
+    h->vi_pinned = (int32_t*)(rec + (size_t)P.C * sizeof(bk_step_stats));
+    if (vi_counts_host) memcpy(vi_counts_host + (size_t)sidx * P.C * P.p, h->vi_pinned, (size_t)P.C * P.p * sizeof(int32_t));
+    if (stats_host) memcpy(stats_host + (size_t)sidx * P.C, h->stats_pinned, (size_t)P.C * sizeof(bk_step_stats));
+    for (int c = 0; c < P.C; ++c)
+      if (h->stats_pinned[c].error_flags & ~1) {
+        char buf[64]; snprintf(buf, sizeof(buf), "chain %d flags 0x%x", c, h->stats_pinned[c].error_flags);
+        set_err("device-side consistency check failed: %s", buf); return BK_ERR_STATE;
+      }
+  }
   return BK_OK;
 }
 

@@ -49,6 +49,7 @@
 #endif
 #define BK_JOB_PARTITION 1
 #define BK_JOB_COUNT 2
+#define BK_MAX_STEPS_PER_LAUNCH 16
 #define BK_JOB_NOP 0  // a partition job whose split value could not be drawn (only members with a missing covariate)
 #define BK_JOB_LL 3   // src_row = the particle's new row, left_id, split = left leaf value, rule = bits of the right leaf value
 
@@ -102,7 +103,7 @@ struct __align__(16) SweepJob {
   int32_t do_prologue;
   int32_t prologue_tree;
   int32_t wf_count;
-  int32_t pad;
+  int32_t draw_slot;    // 1 + step index whose final sum of trees this commit also writes to Params::draws_out (0: none)
 };
 
 // Scalar state of a chain.  The persistent part lives in global memory between steps; during a
@@ -114,6 +115,8 @@ struct __align__(16) ChainHot {
   int32_t iter;      // tree updates so far                  (persistent)
   int32_t lower;     // first tree of the next batch          (persistent)
   int32_t draw;      // steps so far (Philox counter word 0)  (persistent)
+  int32_t step_in_launch;   // step index inside the current launch
+  int32_t pad_step;
   int32_t wf_count;  // Welford count                         (persistent)
   float leaf_sd;     //                                       (persistent)
   float leaf_sdk[BK_MAX_OUTPUTS];   // shared-tree multi-output: running leaf sd per output (persistent; [0] mirrors leaf_sd)
@@ -215,8 +218,12 @@ struct Params {
   double* p_leaf;      // [256]
   int32_t* rules;      // [p]
   int32_t* col_nan;    // [p] 1 = the column holds missing values (NaN)
-  int32_t* vi;         // [C][p]
-  bk_step_stats* stats;  // [C]
+  // Per-step outputs live in RECORDS [stats [C] | vi [C][p]], rec_stride bytes apart, one per step of a launch
+  // (bk_run_launch runs up to BK_MAX_STEPS_PER_LAUNCH steps per launch); `vi` / `stats` point into record 0.
+  int32_t* vi;         // [C][p] of record 0
+  bk_step_stats* stats;  // [C] of record 0
+  int32_t rec_stride;
+  float* draws_out;    // per launch: [n_steps][C*K][Npad] the sum of trees after every step, or nullptr
   bk_trace_rec* trace;   // [C][trace_cap]
   ChainSync* sync;   // [C]
   int32_t* abort_flag;

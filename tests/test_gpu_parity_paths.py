@@ -140,3 +140,37 @@ def test_missing_covariates_cancelled_splits_and_bernoulli():
 def test_missing_covariates_large_n_bucket_counts():
     X, y = _with_missing(150_000, 4, 36)
     assert run_pair(150_000, 4, 2, 8, 6, seed=36, X=X, y=y, depth_offset=1)
+
+
+def test_several_steps_per_launch_equal_single_steps():
+    """bk_run_launch: n steps of every chain inside ONE persistent launch (chains do not wait for each other at step
+    boundaries) give bit for bit what n single-step launches give: per-step inclusion counts and stats, the draw written
+    by every step's last commit, and the final forest."""
+    import torch
+
+    from pymc_bart_b200.core import DeviceSampler
+
+    X, y, _ = friedman(3000, 6, 61)
+    s = make_settings(X, y, m=12, num_particles=10, seed=61, n_chains=3)        # 1 tree per step: the batch wraps around m
+    a, b = DeviceSampler(s, X, y), DeviceSampler(s, X, y)
+    for tune, n in ((True, 5), (True, 16), (False, 7), (False, 1)):
+        draws = torch.zeros((n, b.rows, b.ld), dtype=torch.float32, device="cuda")
+        b.run_launch(n, tune, 0.7, draws_out=draws)
+        vi_b, st_b = b.run_wait()
+        torch.cuda.synchronize()
+        for k in range(n):
+            vi_a, st_a = a.step(tune, 0.7)
+            assert np.array_equal(vi_a, vi_b[k])
+            for c in range(3):
+                assert (st_a[c].grow_events, st_a[c].rounds, st_a[c].tree_updates, st_a[c].iter) == \
+                       (st_b[k][c].grow_events, st_b[k][c].rounds, st_b[k][c].tree_updates, st_b[k][c].iter)
+                assert np.float32(st_a[c].leaf_sd).view(np.uint32) == np.float32(st_b[k][c].leaf_sd).view(np.uint32)
+                assert st_b[k][c].error_flags == 0
+            assert torch.equal(draws[k], a.sum_trees_dev)
+    for c in range(3):
+        na, nna = a.forest(c); nb, nnb = b.forest(c)
+        assert np.array_equal(nna, nnb) and np.array_equal(na.view(np.uint8), nb.view(np.uint8))
+        assert np.array_equal(a.leaf_ids(c), b.leaf_ids(c))
+    with pytest.raises(RuntimeError):
+        b.run_launch(17, True, 1.0)
+    a.close(); b.close()
