@@ -1360,9 +1360,13 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     q_s[0] = b0.x; q_s[1] = b0.y; q_s[2] = b0.z; q_s[3] = b0.w; q_s[4] = b1.x; q_s[5] = b1.y; q_s[6] = b1.z; q_s[7] = b1.w;
   }
   // per-unit address bases (the per-job part is one multiply-add)
-  const uint8_t* rows_c = P.rows + (size_t)c * P.R * P.Npad + base;
+  // Addresses as base pointer + (unsigned 32 x 32 -> 64) products: one IMAD.WIDE.U32 each.  With signed `int * size_t` the
+  // compiler spent ~70 of the ~250 instructions of a (tile, job) unit on 64-bit address arithmetic (sign extensions, two
+  // 64-bit multiplies per address), recomputed per job because the 64-register cap leaves no room to keep them.
+  const unsigned uNpad = (unsigned)P.Npad, uCnt = (unsigned)P.cnt_stride, uCR = (unsigned)c * (unsigned)P.R;
+  const uint8_t* rows_c = P.rows + (unsigned long long)uCR * uNpad + base;
   const float* x_b = P.X + base;
-  unsigned* cnt_c = P.rowcnt + (size_t)c * P.R * P.cnt_stride + tile;
+  unsigned* cnt_c = P.rowcnt + (unsigned long long)uCR * uCnt + (unsigned)tile;
   // leaf ids of a stump: 0 for real rows, 0xFF (limbo) for the padding rows of the last tile
   unsigned vw0 = 0u, vw1 = 0u;
   if (base + 8 > (size_t)P.N) {
@@ -1381,7 +1385,7 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     const bool has_nan = MISSING && j2.w != 0;
     unsigned w0 = vw0, w1 = vw1;
     if (src_row != BK_ROW_VIRTUAL) {
-      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(rows_c + (size_t)src_row * P.Npad));
+      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(rows_c + (unsigned long long)(unsigned)src_row * uNpad));
       w0 = v.x; w1 = v.y;
     }
     const unsigned next4 = (unsigned)next_node * 0x01010101u;
@@ -1393,7 +1397,7 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       // per job); sparse nodes (few members) keep it dependent on the ids to save the bytes
       float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
       if (!sparse || (mem0 | mem1)) {
-        const float4* xp = reinterpret_cast<const float4*>(x_b + (size_t)var * P.Npad);
+        const float4* xp = reinterpret_cast<const float4*>(x_b + (unsigned long long)(unsigned)var * uNpad);
         x0 = __ldg(xp); x1 = __ldg(xp + 1);
         if (rule == BK_RULE_ONEHOT) {
           if (x0.x == split) lb0 |= 0x000000FFu; if (x0.y == split) lb0 |= 0x0000FF00u;
@@ -1456,7 +1460,7 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
           if (lane < 5) atomicAdd(sacc + ji * BK_LIMBS + (lane < 4 ? BK_LIMB_ND + lane : BK_LIMB_SRD_HI), v);
         }
       }
-      __stcg(reinterpret_cast<uint2*>(const_cast<uint8_t*>(rows_c) + (size_t)dst_row * P.Npad), make_uint2(n0, n1));
+      __stcg(reinterpret_cast<uint2*>(const_cast<uint8_t*>(rows_c) + (unsigned long long)(unsigned)dst_row * uNpad), make_uint2(n0, n1));
       if (MULTI) {
         if (__any_sync(0xffffffffu, (mem0 | mem1) != 0u)) {
           const unsigned rm0 = mem0 & ~lm0, rm1 = mem1 & ~lm1;     // rows of the right child
@@ -1512,16 +1516,16 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
         const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(n0, next4)) + __popc(bytes_eq_msb(n1, next4)));
         const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) {
-          cnt_c[(size_t)dst_row * P.cnt_stride] = tot;
-          if (P.nb > 0 && tot) atomicAdd(P.coarse + ((size_t)c * P.R + dst_row) * P.nb_stride + (tile / BK_COARSE_TILES), tot);
+          cnt_c[(unsigned long long)(unsigned)dst_row * uCnt] = tot;
+          if (P.nb > 0 && tot) atomicAdd(P.coarse + (unsigned long long)(uCR + (unsigned)dst_row) * (unsigned)P.nb_stride + ((unsigned)tile / BK_COARSE_TILES), tot);
         }
       }
     } else if (kind == BK_JOB_COUNT) {
       const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(w0, next4)) + __popc(bytes_eq_msb(w1, next4)));
       const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
       if (lane == 0) {
-        cnt_c[(size_t)src_row * P.cnt_stride] = tot;
-        if (P.nb > 0 && tot) atomicAdd(P.coarse + ((size_t)c * P.R + src_row) * P.nb_stride + (tile / BK_COARSE_TILES), tot);
+        cnt_c[(unsigned long long)(unsigned)src_row * uCnt] = tot;
+        if (P.nb > 0 && tot) atomicAdd(P.coarse + (unsigned long long)(uCR + (unsigned)src_row) * (unsigned)P.nb_stride + ((unsigned)tile / BK_COARSE_TILES), tot);
       }
     }
   }
@@ -1552,7 +1556,7 @@ __device__ __forceinline__ void ll_unit(const Params& P, int c, int tile, int jo
     const int src_row = j0.z;
     const float vl = __int_as_float(j1.z), vr = __int_as_float(j2.y);
     const unsigned left_id = (unsigned)j1.w;
-    const unsigned long long ids = __ldcg(reinterpret_cast<const unsigned long long*>(P.rows + ((size_t)c * P.R + src_row) * P.Npad + base));
+    const unsigned long long ids = __ldcg(reinterpret_cast<const unsigned long long*>(P.rows + (unsigned long long)((unsigned)c * (unsigned)P.R + (unsigned)src_row) * (unsigned)P.Npad + base));
     long long s_l = 0, s_r = 0;
     bool any = false;
 #pragma unroll
