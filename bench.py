@@ -307,11 +307,15 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     dev.close()
     del dev, draws_dev, gathered
     torch.cuda.synchronize()
-    e2e_steps = max(10, steps // 4)
+    e2e_steps = max(10, steps // 4) if args.lookahead <= 1 else max(64, steps // 2)
     t0 = time.perf_counter()
     rv = BART("mu", X, y, m=m, shape=(groups, N) if groups > 1 else None, separate_trees=groups > 1)
+    # sigma is fixed in this benchmark, so the posterior draws may be served from launches of several steps
+    # (PGBART(lookahead=n): the next launch runs while the caller consumes the previous one); every astep() still returns the
+    # draw as a host array with its stats and publishes its batch of rewritten trees.  `e2e.one_launch_per_call` below is the
+    # same loop with lookahead=1 (what a model whose scale is updated by another step method between draws gets).
     stp = PGBART([rv], num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=True,
-                 likelihood="bernoulli" if lik else "normal")
+                 likelihood="bernoulli" if lik else "normal", lookahead=args.lookahead)
     t_build = time.perf_counter() - t0
     for i in range(3):
         stp.astep()
@@ -322,8 +326,8 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
             stp.stop_tuning()
         val_host, stats = stp.astep()      # step kernel, D2H sum-of-trees + VI counts + stats (+ the rewritten trees after tuning)
     stp.flush_history()                    # every batch has reached op.all_trees (the Manager proxy of pymc_bart/bart.py:134)
+    e2e_dt = time.perf_counter() - t_w0    # all K draws, stats and tree batches are on the host (a launch that ran ahead is not waited for)
     torch.cuda.synchronize()
-    e2e_dt = time.perf_counter() - t_w0
     clocks.window(t_w0, time.perf_counter())
     e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -332,6 +336,29 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     h2d = nvc * 4
     d2h = nvc * N * 4 + nvc * p * 4 + nvc * 64 + 4 + int(getattr(stp, "history_bytes_per_step", 0))
     h2d_once = stp.core.h2d_bytes
+    e2e_single = None
+    if args.lookahead > 1:       # the same loop, one launch per astep() call
+        stp.close()
+        rv1 = BART("mu1", X, y, m=m, shape=(groups, N) if groups > 1 else None, separate_trees=groups > 1)
+        stp1 = PGBART([rv1], num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=True,
+                      likelihood="bernoulli" if lik else "normal", lookahead=1)
+        n1 = max(10, e2e_steps // 2)
+        for i in range(3):
+            stp1.astep()
+        sync_all()
+        t1 = time.perf_counter()
+        for i in range(n1):
+            if i == n1 // 2:
+                stp1.stop_tuning()
+            stp1.astep()
+        stp1.flush_history()
+        torch.cuda.synchronize()
+        dt1 = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt1, op=dist.ReduceOp.MAX)
+        e2e_single = {"value": world * chains * n1 / float(dt1.item()), "unit": "draws/s", "steps": n1}
+        stp1.close()
+        del stp1
     # ---------------- posterior prediction from the history the e2e leg just published (row N1): all chains, one launch
     predict = None
     try:
@@ -384,7 +411,8 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
         "gather_ms": gather_ms_max,
         "gather_bytes_per_rank": int(n_post * nvc * N * 4) if world > 1 else 0,   # (+0.1 % row padding on the wire)
         "e2e": {"value": e2e_val, "unit": "draws/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build,
+                "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build, "lookahead": int(args.lookahead),
+                "one_launch_per_call": e2e_single,
                 "history": "store_history=True: after tuning every step's rewritten trees are exported (op.all_trees protocol)"},
         "predict": predict,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -420,6 +448,7 @@ def main():
     ap.add_argument("--cpu-draws", type=int, default=None, help="CPU baseline sample size (draws per chain)")
     ap.add_argument("--profile-only", action="store_true", help="device-timed leg only (for ncu runs)")
     ap.add_argument("--clock-ms", type=int, default=20, help="nvidia-smi sampling period in ms (0 = no clock sampling)")
+    ap.add_argument("--lookahead", type=int, default=16, help="PGBART(lookahead=) of the e2e leg (1 = one launch per astep call)")
     ap.add_argument("--steps-per-launch", type=int, default=16, help="steps of every chain per kernel launch in the device-timed leg (1..16)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -171,7 +171,8 @@ int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_hos
  * boundaries and no launch gap separates the steps.  draws_dev: NULL, or device memory [n_steps][n_chains*max(n_groups,
  * n_outputs)][ld] float32 that receives the sum of trees after every step (the posterior draws stay on the device).
  * bk_run_wait returns the steps' outputs in order: vi_counts_host [n_steps][..][n_cols], stats_host [n_steps][..].
- * Tree-history capture (bk_set_history) and the trace need one step per launch.  bk_step_launch/wait = n_steps 1. */
+ * With the tree history on (bk_set_history) the steps of a launch must not rewrite a tree twice (n_steps * trees per
+ * step <= n_trees); the trace needs one step per launch.  bk_step_launch/wait = n_steps 1. */
 int bk_run_launch(bk_handle* h, int n_steps, int tune, const float* sigma_host, float* draws_dev);
 int bk_run_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host);
 void* bk_stream(bk_handle* h);
@@ -207,6 +208,9 @@ int bk_history_batch(bk_handle* h, int32_t* first_tree, int32_t* n_nodes_host, b
  * bk_history_batch; bk_export_leaf_values: the current forest's, [n_trees][255][n_outputs] (0 for split nodes). */
 int bk_history_values(bk_handle* h, float* values_host);
 int bk_export_leaf_values(bk_handle* h, int chain, float* values_host);
+/* The same for step `step` of a launch of several steps (bk_run_launch); the plain forms are step 0. */
+int bk_history_batch_at(bk_handle* h, int step, int32_t* first_tree, int32_t* n_nodes_host, bk_node* nodes_host, int64_t* total_nodes);
+int bk_history_values_at(bk_handle* h, int step, float* values_host);
 
 /* Posterior prediction from the forest history (row N1): what bartrs' PosteriorSampler.sample_posterior(X, draw_indices,
  * excluded) does for the shell (pymc_bart/utils.py:60-71,93-107), for all chains of an op in ONE launch.

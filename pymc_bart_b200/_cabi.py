@@ -121,7 +121,7 @@ assert NODE_DTYPE.itemsize == C.sizeof(BkNode) == 24
 EXPORTS = (
     "bk_abi_version", "bk_last_error", "bk_padded_rows", "bk_query_bytes", "bk_create", "bk_destroy",
     "bk_step", "bk_step_launch", "bk_step_wait", "bk_run_launch", "bk_run_wait", "bk_stream", "bk_set_host_output", "bk_sum_trees_host", "bk_export_trees", "bk_read_trace", "bk_export_forest", "bk_export_leaf_ids",
-    "bk_set_history", "bk_history_batch", "bk_history_values", "bk_export_leaf_values", "bk_predict_history", "bk_pearson_r2",
+    "bk_set_history", "bk_history_batch", "bk_history_values", "bk_history_batch_at", "bk_history_values_at", "bk_export_leaf_values", "bk_predict_history", "bk_pearson_r2",
 )
 
 _lib = None
@@ -163,6 +163,8 @@ def load():
     lib.bk_set_history.argtypes = [C.c_void_p, C.c_int]
     lib.bk_history_batch.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     lib.bk_history_values.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bk_history_batch_at.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    lib.bk_history_values_at.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.bk_export_leaf_values.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.bk_predict_history.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                        C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

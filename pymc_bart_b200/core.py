@@ -129,18 +129,19 @@ class DeviceSampler:
         self._hist_vals = np.zeros((self.C * T * _cabi.BK_MAX_NODES, self.K), dtype=np.float32) if self.K > 1 else None
         self.history_bytes_per_step = self.C * self.settings.batch_post * (_cabi.BK_MAX_NODES * 64 + 4)
 
-    def history_batch(self):
-        """Trees rewritten by the last step waited for: (first, n_nodes [C][T], nodes back to back[, leaf values
-        [nodes][K] for shared-tree multi-output]) or None."""
+    def history_batch(self, step: int = 0):
+        """Trees rewritten by step `step` of the last launch waited for: (first, n_nodes [C][T], nodes back to back[,
+        leaf values [nodes][K] for shared-tree multi-output]) or None."""
         first, total = C.c_int32(), C.c_int64()
-        T = self.lib.bk_history_batch(self.h, C.byref(first), self._hist_nn.ctypes.data, self._hist_nodes.ctypes.data, C.byref(total))
+        T = self.lib.bk_history_batch_at(self.h, int(step), C.byref(first), self._hist_nn.ctypes.data, self._hist_nodes.ctypes.data,
+                                         C.byref(total))
         if T < 0:
-            _cabi.check(T, "bk_history_batch")
+            _cabi.check(T, "bk_history_batch_at")
         if T == 0:
             return None
         nn = self._hist_nn.reshape(-1)[: self.C * T].reshape(self.C, T).copy()
         if self.K > 1:
-            rc = self.lib.bk_history_values(self.h, self._hist_vals.ctypes.data)
+            rc = self.lib.bk_history_values_at(self.h, int(step), self._hist_vals.ctypes.data)
             if rc < 0:
                 _cabi.check(rc, "bk_history_values")
             return int(first.value), nn, self._hist_nodes[: int(total.value)].copy(), self._hist_vals[: int(total.value)].copy()

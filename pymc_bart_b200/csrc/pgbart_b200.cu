@@ -2322,9 +2322,10 @@ struct bk_handle_s {
   // slot k & 1 belongs to launch k; the *_pinned pointers above / below follow the last step waited for
   unsigned char* out_slot[2];  // pinned block [vi | stats | abort flag] of a launch: ONE D2H copy per step
   float* st_slot[2];           // pinned [C][n_rows] sum of trees (bk_set_host_output)
-  DNode* hist_nodes_slot[2];   // pinned [C][Tmax][255] raw nodes of the trees a post-tuning step rewrote (bk_set_history)
-  int32_t* hist_nn_slot[2];    // pinned [C][Tmax]
-  int hist_first[2], hist_count[2];
+  DNode* hist_nodes_slot[2];   // pinned [steps][C][Tmax][255] raw nodes of the trees the post-tuning steps rewrote (bk_set_history)
+  int32_t* hist_nn_slot[2];    // pinned [steps][C][Tmax]
+  int hist_cap[2];             // steps the slot's buffers hold
+  int hist_first[2][BK_MAX_STEPS_PER_LAUNCH], hist_count[2][BK_MAX_STEPS_PER_LAUNCH];
   cudaEvent_t done_ev[2];
   long long n_launched, n_waited;
   int last_slot;
@@ -2572,7 +2573,10 @@ int bk_step_launch(bk_handle* h, int tune, const float* sigma_host) { return bk_
 int bk_run_launch(bk_handle* h, int n_steps, int tune, const float* sigma_host, float* draws_dev) {
   if (!h) { set_err("NULL handle"); return BK_ERR_ARG; }
   if (n_steps < 1 || n_steps > BK_MAX_STEPS_PER_LAUNCH) { set_err("n_steps must be in [1, 16]"); return BK_ERR_ARG; }
-  if (n_steps > 1 && (h->history || h->s.trace_capacity > 0)) { set_err("tree history / trace capture need one step per launch"); return BK_ERR_STATE; }
+  if (n_steps > 1 && h->s.trace_capacity > 0) { set_err("the trace needs one step per launch"); return BK_ERR_STATE; }
+  if (n_steps > 1 && h->history && !tune && (long long)n_steps * h->P.batch_post > h->P.m) {
+    set_err("with the tree history on, the steps of one launch must not rewrite a tree twice (n_steps * trees per step <= n_trees)"); return BK_ERR_ARG;
+  }
   if (h->poisoned) { set_err("an earlier step timed out inside the kernel; the sampler state is undefined: create a new handle"); return BK_ERR_STATE; }
   if (h->n_launched - h->n_waited >= 2) { set_err("two steps are already in flight: call bk_step_wait first"); return BK_ERR_STATE; }
   ON_DEVICE(h->s.device);
@@ -2602,17 +2606,31 @@ int bk_run_launch(bk_handle* h, int n_steps, int tune, const float* sigma_host, 
   if (h->host_output)   // the value handed back to PyMC: strided device rows -> dense pinned host rows, behind the kernel
     CK(cudaMemcpy2DAsync(h->st_slot[slot], (size_t)P.N * sizeof(float), P.st, (size_t)P.Npad * sizeof(float), (size_t)P.N * sizeof(float),
                          (size_t)P.C * P.K, cudaMemcpyDeviceToHost, h->stream));
-  h->hist_count[slot] = 0;
+  for (int sidx = 0; sidx < BK_MAX_STEPS_PER_LAUNCH; ++sidx) h->hist_count[slot][sidx] = 0;
   if (h->history && !tune) {
-    // the trees this step rewrote (op.all_trees batches, pymc_bart/utils.py:117-127): two strided copies behind the
-    // kernel, no stall; bk_history_batch compacts them on the host
-    const int Tmax = P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post;
-    CK(cudaMemcpy2DAsync(h->hist_nn_slot[slot], (size_t)Tmax * sizeof(int32_t), P.forest_nn + lo, (size_t)P.m * sizeof(int32_t),
-                         (size_t)(hi - lo) * sizeof(int32_t), (size_t)P.C, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpy2DAsync(h->hist_nodes_slot[slot], (size_t)Tmax * BK_MAX_NODES * sizeof(DNode), P.forest + (size_t)lo * BK_MAX_NODES,
-                         (size_t)P.m * BK_MAX_NODES * sizeof(DNode), (size_t)(hi - lo) * BK_MAX_NODES * sizeof(DNode), (size_t)P.C,
-                         cudaMemcpyDeviceToHost, h->stream));
-    h->hist_first[slot] = lo; h->hist_count[slot] = hi - lo;
+    // the trees every step of the launch rewrote (op.all_trees batches, pymc_bart/utils.py:117-127): two strided copies per
+    // step behind the kernel, no stall (a tree is rewritten at most once per launch, so its nodes are still the step's
+    // when the launch ends); bk_history_batch_at compacts them on the host
+    const size_t Tmax = (size_t)(P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post);
+    if (h->hist_cap[slot] < n_steps) {   // (the slot is idle: its previous launch has been waited for)
+      if (h->hist_nodes_slot[slot]) cudaFreeHost(h->hist_nodes_slot[slot]);
+      if (h->hist_nn_slot[slot]) cudaFreeHost(h->hist_nn_slot[slot]);
+      h->hist_nodes_slot[slot] = nullptr; h->hist_nn_slot[slot] = nullptr; h->hist_cap[slot] = 0;
+      CK(cudaMallocHost(&h->hist_nodes_slot[slot], (size_t)n_steps * P.C * Tmax * BK_MAX_NODES * sizeof(DNode)));
+      CK(cudaMallocHost(&h->hist_nn_slot[slot], (size_t)n_steps * P.C * Tmax * sizeof(int32_t)));
+      h->hist_cap[slot] = n_steps;
+    }
+    int l = lo;
+    for (int sidx = 0; sidx < n_steps; ++sidx) {
+      const int hh = l + T < P.m ? l + T : P.m;
+      CK(cudaMemcpy2DAsync(h->hist_nn_slot[slot] + (size_t)sidx * P.C * Tmax, Tmax * sizeof(int32_t), P.forest_nn + l, (size_t)P.m * sizeof(int32_t),
+                           (size_t)(hh - l) * sizeof(int32_t), (size_t)P.C, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpy2DAsync(h->hist_nodes_slot[slot] + (size_t)sidx * P.C * Tmax * BK_MAX_NODES, Tmax * BK_MAX_NODES * sizeof(DNode),
+                           P.forest + (size_t)l * BK_MAX_NODES, (size_t)P.m * BK_MAX_NODES * sizeof(DNode),
+                           (size_t)(hh - l) * BK_MAX_NODES * sizeof(DNode), (size_t)P.C, cudaMemcpyDeviceToHost, h->stream));
+      h->hist_first[slot][sidx] = l; h->hist_count[slot][sidx] = hh - l;
+      l = hh < P.m ? hh : 0;
+    }
   }
   CK(cudaEventRecord(h->done_ev[slot], h->stream));
   {
@@ -2643,27 +2661,36 @@ int bk_set_history(bk_handle* h, int enable) {
   const Params& P = h->P;
   const size_t Tmax = (size_t)(P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post);
   for (int k = 0; k < 2 && enable; ++k) {
-    if (!h->hist_nodes_slot[k]) CK(cudaMallocHost(&h->hist_nodes_slot[k], (size_t)P.C * Tmax * BK_MAX_NODES * sizeof(DNode)));
-    if (!h->hist_nn_slot[k]) CK(cudaMallocHost(&h->hist_nn_slot[k], (size_t)P.C * Tmax * sizeof(int32_t)));
+    if (!h->hist_nodes_slot[k]) {
+      CK(cudaMallocHost(&h->hist_nodes_slot[k], (size_t)P.C * Tmax * BK_MAX_NODES * sizeof(DNode)));
+      CK(cudaMallocHost(&h->hist_nn_slot[k], (size_t)P.C * Tmax * sizeof(int32_t)));
+      h->hist_cap[k] = 1;
+    }
   }
   h->history = enable ? 1 : 0;
   return BK_OK;
 }
 
 int bk_history_batch(bk_handle* h, int32_t* first_tree, int32_t* n_nodes_host, bk_node* nodes_host, int64_t* total_nodes) {
-  if (!h || !first_tree || !n_nodes_host || !nodes_host || !total_nodes) { set_err("bad argument"); return BK_ERR_ARG; }
+  return bk_history_batch_at(h, 0, first_tree, n_nodes_host, nodes_host, total_nodes);
+}
+int bk_history_values(bk_handle* h, float* values_host) { return bk_history_values_at(h, 0, values_host); }
+
+int bk_history_batch_at(bk_handle* h, int step, int32_t* first_tree, int32_t* n_nodes_host, bk_node* nodes_host, int64_t* total_nodes) {
+  if (!h || !first_tree || !n_nodes_host || !nodes_host || !total_nodes || step < 0 || step >= BK_MAX_STEPS_PER_LAUNCH) { set_err("bad argument"); return BK_ERR_ARG; }
   const Params& P = h->P;
-  const int slot = h->last_slot, T = h->hist_count[slot];
-  *first_tree = h->hist_first[slot]; *total_nodes = 0;
+  const int slot = h->last_slot, T = h->hist_count[slot][step];
+  *first_tree = h->hist_first[slot][step]; *total_nodes = 0;
   if (!h->history || T <= 0) return 0;
   const size_t Tmax = (size_t)(P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post);
+  const size_t sbase = (size_t)step * P.C * Tmax;
   int64_t tot = 0;
   for (int c = 0; c < P.C; ++c)
     for (int t = 0; t < T; ++t) {
-      const int nn = h->hist_nn_slot[slot][(size_t)c * Tmax + t];
+      const int nn = h->hist_nn_slot[slot][sbase + (size_t)c * Tmax + t];
       if (nn < 1 || nn > BK_MAX_NODES) { set_err("history batch holds a malformed tree"); return BK_ERR_STATE; }
       n_nodes_host[(size_t)c * T + t] = nn;
-      const DNode* src = h->hist_nodes_slot[slot] + ((size_t)c * Tmax + t) * BK_MAX_NODES;
+      const DNode* src = h->hist_nodes_slot[slot] + (sbase + (size_t)c * Tmax + t) * BK_MAX_NODES;
       for (int k = 0; k < nn; ++k) {
         bk_node* d = &nodes_host[tot + k];
         d->var = src[k].var; d->split = src[k].split; d->left = src[k].left; d->value = src[k].var < 0 ? src[k].value : 0.0f;
@@ -2676,17 +2703,18 @@ int bk_history_batch(bk_handle* h, int32_t* first_tree, int32_t* n_nodes_host, b
 }
 
 /* leaf values of every output of the last history batch, [total_nodes][n_outputs] in the batch's node order */
-int bk_history_values(bk_handle* h, float* values_host) {
-  if (!h || !values_host) { set_err("bad argument"); return BK_ERR_ARG; }
+int bk_history_values_at(bk_handle* h, int step, float* values_host) {
+  if (!h || !values_host || step < 0 || step >= BK_MAX_STEPS_PER_LAUNCH) { set_err("bad argument"); return BK_ERR_ARG; }
   const Params& P = h->P;
-  const int slot = h->last_slot, T = h->hist_count[slot];
+  const int slot = h->last_slot, T = h->hist_count[slot][step];
   if (!h->history || T <= 0) return 0;
   const size_t Tmax = (size_t)(P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post);
+  const size_t sbase = (size_t)step * P.C * Tmax;
   size_t tot = 0;
   for (int c = 0; c < P.C; ++c)
     for (int t = 0; t < T; ++t) {
-      const int nn = h->hist_nn_slot[slot][(size_t)c * Tmax + t];
-      const DNode* src = h->hist_nodes_slot[slot] + ((size_t)c * Tmax + t) * BK_MAX_NODES;
+      const int nn = h->hist_nn_slot[slot][sbase + (size_t)c * Tmax + t];
+      const DNode* src = h->hist_nodes_slot[slot] + (sbase + (size_t)c * Tmax + t) * BK_MAX_NODES;
       for (int k = 0; k < nn; ++k, ++tot)
         for (int j = 0; j < P.K; ++j) values_host[tot * P.K + j] = src[k].var < 0 ? node_val(src[k], j) : 0.0f;
     }

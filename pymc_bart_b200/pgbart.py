@@ -17,7 +17,12 @@ State lives on the GPU (pymc_bart_b200.core.DeviceSampler); this class keeps the
 * when ``tune`` goes back to True after post-tuning draws (PyMC re-using one step object for the next chain,
   ``cores=1``), the sampler starts a fresh chain with the next chain index.
 
-Extension: ``chains=C`` batches C independent chains in one launch (the reference runs one step object per chain).
+Extensions: ``chains=C`` batches C independent chains in one launch (the reference runs one step object per chain).
+``lookahead=n`` (posterior phase only, and only when the likelihood parameters are FIXED — no ``sigma_name``, nobody
+assigns ``step.sigma`` between draws): ``astep`` is served from launches of ``n`` steps (``bk_run_launch``); the next launch
+runs on the GPU while the caller consumes the draws of the previous one, each draw still arrives as a host array with its
+stats and its batch of rewritten trees.  With another step method updating the scale between draws (the reference's
+``sigma ~ HalfNormal`` models) keep ``lookahead=1``: a step needs the scale of the current point.
 """
 from __future__ import annotations
 
@@ -44,7 +49,7 @@ class PGBART:
 
     def __init__(self, vars=None, num_particles=10, batch=(0.1, 0.1), model=None, *, likelihood="normal", sigma=1.0,
                  chains=1, chain_base=0, seed=0, device=None, depth_offset=0, store_history=True, trace_capacity=0,
-                 sigma_name=None, sigma_transform=None, **kwargs):
+                 sigma_name=None, sigma_transform=None, lookahead=1, **kwargs):
         if vars is None or len(vars) != 1:
             raise ValueError("PGBART takes exactly one BART variable: PGBART([rv], num_particles=...)")
         rv = vars[0]
@@ -89,6 +94,7 @@ class PGBART:
         self.sigma_name = sigma_name
         self.sigma_transform = sigma_transform   # e.g. np.exp when sigma_name is the log-transformed value variable
         self.store_history = bool(store_history)
+        self.lookahead = int(lookahead)
         self._Y = Yarr
         self._settings_kw = dict(
             m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
@@ -111,6 +117,9 @@ class PGBART:
         self._lower = 0
         self._post_draws = 0
         self._batches = None        # per chain: the `batches` list published in op.all_trees
+        self._served = []           # lookahead: draws of the last collected launch not handed out yet
+        self._inflight = None       # lookahead: the launch running on the GPU
+        self._ring = None
 
     def _pick_device(self):
         if self.device is not None:
@@ -138,6 +147,9 @@ class PGBART:
         state["last_stats"] = None
         state["_pub_thread"] = None
         state["_pub_queue"] = None
+        state["_served"] = []
+        state["_inflight"] = None
+        state["_ring"] = None
         return state
 
     def next_chain(self):
@@ -210,21 +222,81 @@ class PGBART:
         parts = per_vc[c * self.groups:(c + 1) * self.groups]
         return tuple(np.concatenate([p[i] for p in parts]) for i in range(len(parts[0])))
 
+    # ---- lookahead: posterior draws served from launches of several steps -----------------------------------------------
+    def _publish_first_entry(self, core):
+        """First posterior draw: publish the chain's entry (baseline = the forest tuning ended with); every later draw
+        appends its rewritten trees to the entry's `batches`."""
+        base = core.baseline()
+        self._batches = [self._new_batches() for _ in range(self.chains)]
+        for c in range(self.chains):
+            self._publish(self.op.all_trees, (self._chain_slice(base, c), self._batches[c]))
+
+    def _publish_batch(self, batch):
+        first, nn, *arrays = batch      # nodes[, leaf values of every output]
+        off = np.concatenate([[0], np.cumsum(nn.sum(axis=1))])
+        G = self.groups
+        for c in range(self.chains):
+            self._publish(self._batches[c], (first, nn[c * G:(c + 1) * G].copy(), *(a[off[c * G]: off[(c + 1) * G]].copy() for a in arrays)))
+
+    def _launch_ahead(self, core):
+        torch = core.torch
+        n = max(1, min(self.lookahead, core.MAX_STEPS_PER_LAUNCH, self.m // max(1, self.settings.batch_post)))
+        if self._ring is None or self._ring["n"] != n:
+            with torch.cuda.device(core.device):
+                self._ring = {"n": n, "slot": 0,
+                              "dev": [torch.empty((n, core.rows, core.ld), dtype=torch.float32, device=core.device) for _ in range(2)],
+                              "host": [torch.empty((n, core.rows, core.ld), dtype=torch.float32).pin_memory() for _ in range(2)],
+                              "ev": [torch.cuda.Event() for _ in range(2)]}
+        r = self._ring
+        k = r["slot"]
+        core.run_launch(n, False, self.sigma, draws_out=r["dev"][k])
+        with torch.cuda.stream(core.stream()):                  # the draws follow the kernel to pinned host memory
+            r["host"][k].copy_(r["dev"][k], non_blocking=True)
+            r["ev"][k].record()
+        self._inflight = {"slot": k, "n": n, "sigma": np.array(self.sigma, dtype=np.float64, copy=True)}
+        r["slot"] = k ^ 1
+
+    def _collect_ahead(self, core):
+        fl, self._inflight = self._inflight, None
+        vi, stats = core.run_wait()
+        self._ring["ev"][fl["slot"]].synchronize()
+        host = self._ring["host"][fl["slot"]].numpy()[:, :, : self.n_rows]
+        hist = [core.history_batch(k) for k in range(fl["n"])] if self.store_history else [None] * fl["n"]
+        self._served = [(host[k], vi[k], stats[k], hist[k], fl["sigma"]) for k in range(fl["n"])]
+
+    def _astep_ahead(self, core):
+        if not self._served:
+            if self._inflight is None:
+                self._launch_ahead(core)
+            self._collect_ahead(core)
+            self._launch_ahead(core)          # runs while the caller consumes what was just collected
+        value, vi, stats, hist, sigma = self._served.pop(0)
+        if not np.array_equal(np.asarray(self.sigma, dtype=np.float64), sigma):
+            raise RuntimeError("lookahead > 1 needs fixed likelihood parameters: step.sigma changed while draws computed with the "
+                               "old value were waiting (use lookahead=1 when another step method updates the scale)")
+        self.last_stats = stats
+        if hist is not None:
+            self._publish_batch(hist)
+        return value, vi
+
     def astep(self, _q=None):
         tune = bool(self.tune)
         if tune and self._post_draws > 0:     # tuning again after posterior draws: the next chain starts
             self.next_chain()
         core = self._ensure_core()
+        if not tune and self.lookahead > 1 and self.sigma_name is None:
+            if self.store_history and self._batches is None:
+                self._publish_first_entry(core)
+            value, vi = self._astep_ahead(core)
+            self._post_draws += 1
+            return self._pack(value, vi, tune)
+        if self._served or self._inflight is not None:
+            raise RuntimeError("draws computed ahead are pending: lookahead cannot be switched off in the middle of a chain")
         T = self.settings.batch_tune if tune else self.settings.batch_post
         lo = self._lower
         hi = min(lo + T, self.m)
         if not tune and self.store_history and self._batches is None:
-            # first posterior draw: publish the chain's entry (baseline = the forest tuning ended with); every
-            # later draw appends its rewritten trees to the entry's `batches`
-            base = core.baseline()
-            self._batches = [self._new_batches() for _ in range(self.chains)]
-            for c in range(self.chains):
-                self._publish(self.op.all_trees, (self._chain_slice(base, c), self._batches[c]))
+            self._publish_first_entry(core)
         vi, stats = core.step(tune, self.sigma)
         self.last_stats = stats
         self._lower = hi if hi < self.m else 0
@@ -232,12 +304,11 @@ class PGBART:
         if not tune:
             self._post_draws += 1
             if self.store_history:
-                first, nn, *arrays = core.history_batch()      # nodes[, leaf values of every output]
-                off = np.concatenate([[0], np.cumsum(nn.sum(axis=1))])
-                G = self.groups
-                for c in range(self.chains):
-                    self._publish(self._batches[c], (first, nn[c * G:(c + 1) * G].copy(),
-                                                     *(a[off[c * G]: off[(c + 1) * G]].copy() for a in arrays)))
+                self._publish_batch(core.history_batch())
+        return self._pack(value, vi, tune)
+
+    def _pack(self, value, vi, tune):
+        """(value, stats) in the shapes the step protocol hands back."""
         vic = vi.reshape(self.chains, self.groups, -1).sum(axis=1)       # one inclusion vector per BART variable
         out_stats = [{"variable_inclusion": _encode_vi(vic[c].tolist()), "tune": tune} for c in range(self.chains)]
         value = value.reshape(self.chains, self.groups * self.outputs, -1)    # (chain, output, row)
@@ -265,6 +336,14 @@ class PGBART:
         return None
 
     def close(self):
+        if self._inflight is not None and self.core is not None:      # let the launch that ran ahead settle
+            try:
+                self.core.run_wait()
+            except Exception:
+                pass
+        self._inflight = None
+        self._served = []
+        self._ring = None
         self._stop_publisher()
         if self.core is not None:
             self.core.close()

@@ -224,6 +224,39 @@ def test_fit_quality_friedman():
     out["step"].close()
 
 
+def test_lookahead_serves_the_same_draws():
+    """PGBART(lookahead=n): after tuning, astep is served from launches of n steps (the next launch runs while the
+    caller consumes the previous one).  Same draws, same stats, same published history as one step per call."""
+    import pymc_bart_b200 as pmb
+
+    X, Y, _ = friedman(700, 5, 71)
+    runs = []
+    for la in (1, 6):
+        mu = pmb.BART(f"mu{la}", X, Y, m=20, shared_history=False)
+        step = pmb.PGBART([mu], num_particles=8, chains=2, seed=71, sigma=0.8, lookahead=la)
+        vals, vis = [], []
+        for d in range(10 + 17):                      # 17 posterior draws: launches of 6, 6, 6 (one runs ahead)
+            if d == 10:
+                step.stop_tuning()
+            v, st = step.astep()
+            if d >= 10:
+                vals.append(v.copy()); vis.append([s["variable_inclusion"] for s in st])
+        step.flush_history()
+        runs.append((np.stack(vals), vis, [(b, list(bt)) for b, bt in mu.owner.op.all_trees]))
+        if la > 1:
+            step.sigma = 0.9
+            with pytest.raises(RuntimeError, match="fixed likelihood parameters"):
+                step.astep()                          # a draw computed with the old scale is waiting
+        step.close()
+    (v1, s1, h1), (v6, s6, h6) = runs
+    assert np.array_equal(v1, v6) and s1 == s6
+    assert len(h1) == len(h6) == 2
+    for (b1, bt1), (b6, bt6) in zip(h1, h6):
+        assert all(np.array_equal(x, y) for x, y in zip(b1, b6)) and len(bt1) == len(bt6) == 17
+        for x, y in zip(bt1, bt6):
+            assert x[0] == y[0] and all(np.array_equal(p, q) for p, q in zip(x[1:], y[1:]))
+
+
 def test_missing_data_through_the_api():
     """tests/test_bart.py:67-81: NaNs in X[10:20, 0]; the sampler runs, the fit stays finite and follows the signal, and
     rows whose split covariate is missing are predicted from the other trees only."""
