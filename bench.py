@@ -307,24 +307,37 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     dev.close()
     del dev, draws_dev, gathered
     torch.cuda.synchronize()
-    e2e_steps = max(10, steps // 4) if args.lookahead <= 1 else max(64, steps // 2)
+    e2e_steps = max(10, steps // 4) if args.lookahead <= 1 else max(64, steps)
     t0 = time.perf_counter()
     rv = BART("mu", X, y, m=m, shape=(groups, N) if groups > 1 else None, separate_trees=groups > 1)
     # sigma is fixed in this benchmark, so the posterior draws may be served from launches of several steps
     # (PGBART(lookahead=n): the next launch runs while the caller consumes the previous one); every astep() still returns the
     # draw as a host array with its stats and publishes its batch of rewritten trees.  `e2e.one_launch_per_call` below is the
     # same loop with lookahead=1 (what a model whose scale is updated by another step method between draws gets).
-    stp = PGBART([rv], num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=True,
-                 likelihood="bernoulli" if lik else "normal", lookahead=args.lookahead)
+    step_kw = dict(num_particles=P, chains=chains, chain_base=rank * chains, seed=seed, device=local, store_history=True,
+                   likelihood="bernoulli" if lik else "normal", lookahead=args.lookahead)
+    td = e2e_steps // 2 if (args.lookahead > 1 and args.tune_ahead) else None
+    stp = PGBART([rv], tune_draws=td, **step_kw).prepare()      # device state, X/Y upload, pinned buffers
     t_build = time.perf_counter() - t0
-    for i in range(3):
-        stp.astep()
+    # warm-up on a second step object (first launch of the process, allocator, writer thread), so that the timed region
+    # starts with nothing computed ahead: every one of its K steps runs inside it
+    warm_rv = BART("mu_warm", X, y, m=m, shape=(groups, N) if groups > 1 else None, separate_trees=groups > 1)
+    warm_stp = PGBART([warm_rv], tune_draws=2 if td is not None else None, **step_kw)
+    for i in range(4):
+        if i == 2:
+            warm_stp.stop_tuning()
+        warm_stp.astep()
+    warm_stp.close()
+    del warm_stp, warm_rv
     sync_all()
     t_w0 = time.perf_counter()
+    call_ms = []
     for i in range(e2e_steps):
         if i == e2e_steps // 2:
             stp.stop_tuning()
+        tc = time.perf_counter()
         val_host, stats = stp.astep()      # step kernel, D2H sum-of-trees + VI counts + stats (+ the rewritten trees after tuning)
+        call_ms.append((time.perf_counter() - tc) * 1e3)
     stp.flush_history()                    # every batch has reached op.all_trees (the Manager proxy of pymc_bart/bart.py:134)
     e2e_dt = time.perf_counter() - t_w0    # all K draws, stats and tree batches are on the host (a launch that ran ahead is not waited for)
     torch.cuda.synchronize()
@@ -336,6 +349,10 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     h2d = nvc * 4
     d2h = nvc * N * 4 + nvc * p * 4 + nvc * 64 + 4 + int(getattr(stp, "history_bytes_per_step", 0))
     h2d_once = stp.core.h2d_bytes
+    post_ms = call_ms[e2e_steps // 2:]
+    call_summary = {"tuning_median": float(np.median(call_ms[: e2e_steps // 2])), "post_first": float(post_ms[0]),
+                    "post_median": float(np.median(post_ms)), "post_max_after_first": float(max(post_ms[1:])),
+                    "post_sum": float(sum(post_ms)), "note": "wall ms per astep() call on this rank"}
     e2e_single = None
     if args.lookahead > 1:       # the same loop, one launch per astep() call
         stp.close()
@@ -411,7 +428,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
         "gather_ms": gather_ms_max,
         "gather_bytes_per_rank": int(n_post * nvc * N * 4) if world > 1 else 0,   # (+0.1 % row padding on the wire)
         "e2e": {"value": e2e_val, "unit": "draws/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build, "lookahead": int(args.lookahead),
+                "steps": e2e_steps, "call_ms": call_summary, "h2d_bytes_once_XY": h2d_once, "build_seconds": t_build, "lookahead": int(args.lookahead), "tune_draws_given": bool(args.lookahead > 1 and args.tune_ahead),
                 "one_launch_per_call": e2e_single,
                 "history": "store_history=True: after tuning every step's rewritten trees are exported (op.all_trees protocol)"},
         "predict": predict,
@@ -448,6 +465,8 @@ def main():
     ap.add_argument("--cpu-draws", type=int, default=None, help="CPU baseline sample size (draws per chain)")
     ap.add_argument("--profile-only", action="store_true", help="device-timed leg only (for ncu runs)")
     ap.add_argument("--clock-ms", type=int, default=20, help="nvidia-smi sampling period in ms (0 = no clock sampling)")
+    ap.add_argument("--tune-ahead", type=int, default=1, help="e2e leg: tell the step where tuning ends (PGBART(tune_draws=)), so tuning "
+                    "steps are served ahead too (0 = the PyMC protocol: one launch per tuning call)")
     ap.add_argument("--lookahead", type=int, default=16, help="PGBART(lookahead=) of the e2e leg (1 = one launch per astep call)")
     ap.add_argument("--steps-per-launch", type=int, default=16, help="steps of every chain per kernel launch in the device-timed leg (1..16)")
     args = ap.parse_args()

@@ -197,8 +197,9 @@ int bk_export_trees(bk_handle* h, int chain, int first, int count, bk_node* node
 int bk_export_leaf_ids(bk_handle* h, int chain, uint8_t* ids_host);
 
 /* Tree history (the `(baseline_forest, batches)` entries of op.all_trees, pymc_bart/utils.py:117,124-127; bart.py:133-146).
- * With bk_set_history(h, 1) every post-tuning step also copies the trees it rewrote into pinned host memory behind
- * the kernel (asynchronous, the step does not stall).  bk_history_batch hands out the batch of the last step waited
+ * With bk_set_history(h, n >= 1) every post-tuning step also copies the trees it rewrote into pinned host memory behind
+ * the kernel (asynchronous, the step does not stall); n = the steps per launch the pinned buffers are sized for up
+ * front (1 for bk_step_launch; a larger bk_run_launch grows them when it comes).  0 switches the history off.  bk_history_batch hands out the batch of the last step waited
  * for: *first_tree, n_nodes_host [n_chains*n_groups][T] and the trees' nodes compacted back to back in the same order
  * (capacity n_chains*n_groups*T*255), *total_nodes of them.  Returns T, 0 for a tuning step / history off, < 0 on error. */
 int bk_set_history(bk_handle* h, int enable);

@@ -61,6 +61,7 @@ class DeviceSampler:
         self._sigma = np.ones(Cn, dtype=np.float32)
         self._host_out = None
         self._host_enabled = False
+        self._run_n = []        # steps of the launches in flight (run_launch/run_wait), oldest first
 
     def close(self):
         if getattr(self, "h", None):
@@ -105,11 +106,13 @@ class DeviceSampler:
                 raise ValueError(f"draws_out must be a contiguous float32 tensor of shape ({n_steps}, {self.rows}, {self.ld})")
             ptr = draws_out.data_ptr()
         _cabi.check(self.lib.bk_run_launch(self.h, int(n_steps), int(bool(tune)), self._sigma.ctypes.data, ptr), "bk_run_launch")
-        self._run_n = int(n_steps)
+        self._run_n.append(int(n_steps))      # (up to two launches are in flight: the waits come in launch order)
 
     def run_wait(self):
         """(vi counts [n_steps][C][p] int32, stats [n_steps][C]) of the oldest launch in flight."""
-        n = self._run_n
+        if not self._run_n:
+            raise RuntimeError("run_wait without a launch in flight")
+        n = self._run_n.pop(0)
         vi = np.zeros((n, self.C, self.p), dtype=np.int32)
         stats = (_cabi.BkStepStats * (n * self.C))()
         _cabi.check(self.lib.bk_run_wait(self.h, vi.ctypes.data, C.cast(stats, C.c_void_p)), "bk_run_wait")
@@ -120,9 +123,10 @@ class DeviceSampler:
         return self.torch.cuda.ExternalStream(int(self.lib.bk_stream(self.h)), device=self.device)
 
     # ---- tree history (pymc_bart/utils.py:117-127) -------------------------------------------------------------------
-    def enable_history(self, enable: bool = True):
-        """Post-tuning steps also copy the trees they rewrote to pinned host memory behind the kernel."""
-        _cabi.check(self.lib.bk_set_history(self.h, int(bool(enable))), "bk_set_history")
+    def enable_history(self, enable: bool = True, steps_per_launch: int = 1):
+        """Post-tuning steps also copy the trees they rewrote to pinned host memory behind the kernel (buffers sized
+        for launches of `steps_per_launch` steps)."""
+        _cabi.check(self.lib.bk_set_history(self.h, max(1, int(steps_per_launch)) if enable else 0), "bk_set_history")
         T = max(self.settings.batch_tune, self.settings.batch_post)
         self._hist_nn = np.zeros((self.C, T), dtype=np.int32)
         self._hist_nodes = np.zeros(self.C * T * _cabi.BK_MAX_NODES, dtype=_cabi.NODE_DTYPE)

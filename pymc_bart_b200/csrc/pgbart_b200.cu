@@ -2660,11 +2660,15 @@ int bk_set_history(bk_handle* h, int enable) {
   if (h->n_launched != h->n_waited) { set_err("steps in flight"); return BK_ERR_STATE; }
   const Params& P = h->P;
   const size_t Tmax = (size_t)(P.batch_tune > P.batch_post ? P.batch_tune : P.batch_post);
-  for (int k = 0; k < 2 && enable; ++k) {
-    if (!h->hist_nodes_slot[k]) {
-      CK(cudaMallocHost(&h->hist_nodes_slot[k], (size_t)P.C * Tmax * BK_MAX_NODES * sizeof(DNode)));
-      CK(cudaMallocHost(&h->hist_nn_slot[k], (size_t)P.C * Tmax * sizeof(int32_t)));
-      h->hist_cap[k] = 1;
+  if (enable > BK_MAX_STEPS_PER_LAUNCH) enable = BK_MAX_STEPS_PER_LAUNCH;
+  for (int k = 0; k < 2 && enable > 0; ++k) {   // enable = the steps per launch the pinned buffers are sized for (they grow on demand)
+    if (h->hist_cap[k] < enable) {
+      if (h->hist_nodes_slot[k]) cudaFreeHost(h->hist_nodes_slot[k]);
+      if (h->hist_nn_slot[k]) cudaFreeHost(h->hist_nn_slot[k]);
+      h->hist_nodes_slot[k] = nullptr; h->hist_nn_slot[k] = nullptr; h->hist_cap[k] = 0;
+      CK(cudaMallocHost(&h->hist_nodes_slot[k], (size_t)enable * P.C * Tmax * BK_MAX_NODES * sizeof(DNode)));
+      CK(cudaMallocHost(&h->hist_nn_slot[k], (size_t)enable * P.C * Tmax * sizeof(int32_t)));
+      h->hist_cap[k] = enable;
     }
   }
   h->history = enable ? 1 : 0;

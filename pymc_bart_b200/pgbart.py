@@ -22,7 +22,10 @@ Extensions: ``chains=C`` batches C independent chains in one launch (the referen
 assigns ``step.sigma`` between draws): ``astep`` is served from launches of ``n`` steps (``bk_run_launch``); the next launch
 runs on the GPU while the caller consumes the draws of the previous one, each draw still arrives as a host array with its
 stats and its batch of rewritten trees.  With another step method updating the scale between draws (the reference's
-``sigma ~ HalfNormal`` models) keep ``lookahead=1``: a step needs the scale of the current point.
+``sigma ~ HalfNormal`` models) keep ``lookahead=1``: a step needs the scale of the current point.  A step method is not
+told how long tuning lasts (PyMC calls ``stop_tuning()`` when it is over), so tuning steps are one launch per call unless
+the caller says it: with ``tune_draws=k`` the first k calls (made with ``tune=True``) are served ahead as well, and the
+launches change to posterior steps exactly there; a call whose ``tune`` flag disagrees with that count raises.
 """
 from __future__ import annotations
 
@@ -49,7 +52,7 @@ class PGBART:
 
     def __init__(self, vars=None, num_particles=10, batch=(0.1, 0.1), model=None, *, likelihood="normal", sigma=1.0,
                  chains=1, chain_base=0, seed=0, device=None, depth_offset=0, store_history=True, trace_capacity=0,
-                 sigma_name=None, sigma_transform=None, lookahead=1, **kwargs):
+                 sigma_name=None, sigma_transform=None, lookahead=1, tune_draws=None, **kwargs):
         if vars is None or len(vars) != 1:
             raise ValueError("PGBART takes exactly one BART variable: PGBART([rv], num_particles=...)")
         rv = vars[0]
@@ -95,6 +98,7 @@ class PGBART:
         self.sigma_transform = sigma_transform   # e.g. np.exp when sigma_name is the log-transformed value variable
         self.store_history = bool(store_history)
         self.lookahead = int(lookahead)
+        self.tune_draws = None if tune_draws is None else int(tune_draws)
         self._Y = Yarr
         self._settings_kw = dict(
             m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
@@ -118,8 +122,9 @@ class PGBART:
         self._post_draws = 0
         self._batches = None        # per chain: the `batches` list published in op.all_trees
         self._served = []           # lookahead: draws of the last collected launch not handed out yet
-        self._inflight = None       # lookahead: the launch running on the GPU
+        self._inflight = []         # lookahead: the launches queued on the GPU, oldest first (at most two)
         self._ring = None
+        self._tune_launched = 0     # tuning steps launched ahead (tune_draws given)
 
     def _pick_device(self):
         if self.device is not None:
@@ -135,10 +140,40 @@ class PGBART:
             self.settings = make_settings(self.op.X, self._Y, chain_base=self.chain_base, device=dev, **self._settings_kw)
             self.core = DeviceSampler(self.settings, self.op.X, self._Y)
             self.core.enable_host_output(True)   # astep returns a host array every draw (the trace stores it)
+            ahead = self.core.MAX_STEPS_PER_LAUNCH if self._serves_ahead(True) else (
+                self._steps_ahead(self.core) if self._serves_ahead(False) else 1)
+            ahead = min(ahead, max(1, self.lookahead))
             if self.store_history:
-                self.core.enable_history(True)
+                self.core.enable_history(True, steps_per_launch=ahead)
                 self.history_bytes_per_step = getattr(self.core, "history_bytes_per_step", 0)
+            if ahead > 1:
+                self._make_ring(self.core, ahead)     # (pinning host memory takes ~1 ms per MB: part of the set-up, not of a draw)
         return self.core
+
+    def prepare(self):
+        """Create the device state now (X/Y upload, workspace, pinned buffers) instead of at the first astep()."""
+        self._ensure_core()
+        return self
+
+    def _serves_ahead(self, tune):
+        """Are calls of this phase served from launches of several steps?"""
+        if self.lookahead <= 1 or self.sigma_name is not None:
+            return False
+        return (self.tune_draws is not None and self.tune_draws > 0) if tune else True
+
+    def _steps_ahead(self, core):
+        """Steps of a posterior launch: the history needs every tree rewritten at most once per launch."""
+        return max(1, min(self.lookahead, core.MAX_STEPS_PER_LAUNCH, self.m // max(1, self.settings.batch_post)))
+
+    def _make_ring(self, core, n):
+        torch = core.torch
+        with torch.cuda.device(core.device):
+            self._ring = {"n": n, "slot": 0,
+                          # three slots: two launches queued on the GPU + the one whose draws are being handed out
+                          "dev": [torch.empty((n, core.rows, core.ld), dtype=torch.float32, device=core.device) for _ in range(3)],
+                          "host": [torch.empty((n, core.rows, core.ld), dtype=torch.float32).pin_memory() for _ in range(3)],
+                          "ev": [torch.cuda.Event() for _ in range(3)], "kernel_done": [torch.cuda.Event() for _ in range(3)],
+                          "copy_stream": torch.cuda.Stream(device=core.device)}
 
     def __getstate__(self):
         state = dict(self.__dict__)
@@ -148,7 +183,7 @@ class PGBART:
         state["_pub_thread"] = None
         state["_pub_queue"] = None
         state["_served"] = []
-        state["_inflight"] = None
+        state["_inflight"] = []
         state["_ring"] = None
         return state
 
@@ -240,37 +275,47 @@ class PGBART:
 
     def _launch_ahead(self, core):
         torch = core.torch
-        n = max(1, min(self.lookahead, core.MAX_STEPS_PER_LAUNCH, self.m // max(1, self.settings.batch_post)))
-        if self._ring is None or self._ring["n"] != n:
-            with torch.cuda.device(core.device):
-                self._ring = {"n": n, "slot": 0,
-                              "dev": [torch.empty((n, core.rows, core.ld), dtype=torch.float32, device=core.device) for _ in range(2)],
-                              "host": [torch.empty((n, core.rows, core.ld), dtype=torch.float32).pin_memory() for _ in range(2)],
-                              "ev": [torch.cuda.Event() for _ in range(2)]}
+        left = 0 if self.tune_draws is None else self.tune_draws - self._tune_launched
+        tune = left > 0                     # (without tune_draws only posterior steps come here)
+        n = min(left, core.MAX_STEPS_PER_LAUNCH, max(1, self.lookahead)) if tune else self._steps_ahead(core)
+        if self._ring is None or self._ring["n"] < n:
+            self._make_ring(core, n)
+        if not tune and self.store_history and self._batches is None:
+            self._publish_first_entry(core)   # the forest tuning ended with (nothing is in flight at this point)
         r = self._ring
         k = r["slot"]
-        core.run_launch(n, False, self.sigma, draws_out=r["dev"][k])
-        with torch.cuda.stream(core.stream()):                  # the draws follow the kernel to pinned host memory
-            r["host"][k].copy_(r["dev"][k], non_blocking=True)
+        core.run_launch(n, tune, self.sigma, draws_out=r["dev"][k][:n])
+        # the draws follow the kernel to pinned host memory on a second stream: the next launch does not wait for 4*n*rows*N
+        # bytes to cross PCIe (the ring slot is not written again before this copy has been waited for)
+        r["kernel_done"][k].record(core.stream())
+        with torch.cuda.stream(r["copy_stream"]):
+            r["copy_stream"].wait_event(r["kernel_done"][k])
+            r["host"][k][:n].copy_(r["dev"][k][:n], non_blocking=True)
             r["ev"][k].record()
-        self._inflight = {"slot": k, "n": n, "sigma": np.array(self.sigma, dtype=np.float64, copy=True)}
-        r["slot"] = k ^ 1
+        if tune:
+            self._tune_launched += n
+        self._inflight.append({"slot": k, "n": n, "tune": tune, "sigma": np.array(self.sigma, dtype=np.float64, copy=True)})
+        r["slot"] = (k + 1) % 3
 
     def _collect_ahead(self, core):
-        fl, self._inflight = self._inflight, None
+        fl = self._inflight.pop(0)
         vi, stats = core.run_wait()
         self._ring["ev"][fl["slot"]].synchronize()
         host = self._ring["host"][fl["slot"]].numpy()[:, :, : self.n_rows]
-        hist = [core.history_batch(k) for k in range(fl["n"])] if self.store_history else [None] * fl["n"]
-        self._served = [(host[k], vi[k], stats[k], hist[k], fl["sigma"]) for k in range(fl["n"])]
+        keep = self.store_history and not fl["tune"]
+        hist = [core.history_batch(k) for k in range(fl["n"])] if keep else [None] * fl["n"]
+        self._served = [(host[k], vi[k], stats[k], hist[k], fl["sigma"], fl["tune"]) for k in range(fl["n"])]
 
-    def _astep_ahead(self, core):
+    def _astep_ahead(self, core, tune):
         if not self._served:
-            if self._inflight is None:
+            while len(self._inflight) < 2:    # two launches queued: the GPU goes from one to the next without the host
                 self._launch_ahead(core)
-            self._collect_ahead(core)
-            self._launch_ahead(core)          # runs while the caller consumes what was just collected
-        value, vi, stats, hist, sigma = self._served.pop(0)
+            self._collect_ahead(core)         # (waits for the older one)
+            self._launch_ahead(core)          # queued behind the one that is running now
+        value, vi, stats, hist, sigma, was_tune = self._served.pop(0)
+        if was_tune != tune:
+            raise RuntimeError(f"tune_draws={self.tune_draws} does not match the calls: a step computed with tune={was_tune} "
+                               f"was asked for with tune={tune} (stop_tuning() must come after exactly tune_draws calls)")
         if not np.array_equal(np.asarray(self.sigma, dtype=np.float64), sigma):
             raise RuntimeError("lookahead > 1 needs fixed likelihood parameters: step.sigma changed while draws computed with the "
                                "old value were waiting (use lookahead=1 when another step method updates the scale)")
@@ -284,13 +329,11 @@ class PGBART:
         if tune and self._post_draws > 0:     # tuning again after posterior draws: the next chain starts
             self.next_chain()
         core = self._ensure_core()
-        if not tune and self.lookahead > 1 and self.sigma_name is None:
-            if self.store_history and self._batches is None:
-                self._publish_first_entry(core)
-            value, vi = self._astep_ahead(core)
-            self._post_draws += 1
+        if self._serves_ahead(tune):
+            value, vi = self._astep_ahead(core, tune)
+            self._post_draws += 0 if tune else 1
             return self._pack(value, vi, tune)
-        if self._served or self._inflight is not None:
+        if self._served or self._inflight:
             raise RuntimeError("draws computed ahead are pending: lookahead cannot be switched off in the middle of a chain")
         T = self.settings.batch_tune if tune else self.settings.batch_post
         lo = self._lower
@@ -336,12 +379,13 @@ class PGBART:
         return None
 
     def close(self):
-        if self._inflight is not None and self.core is not None:      # let the launch that ran ahead settle
+        while self._inflight and self.core is not None:      # let the launches that ran ahead settle
+            self._inflight.pop(0)
             try:
                 self.core.run_wait()
             except Exception:
-                pass
-        self._inflight = None
+                break
+        self._inflight = []
         self._served = []
         self._ring = None
         self._stop_publisher()

@@ -43,8 +43,9 @@ def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1)
     rank = dist.get_rank() if distributed else 0
     world = dist.get_world_size() if distributed else 1
     device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-    if sigma_fn is None:          # fixed likelihood parameters: posterior draws may be served from launches of several steps
-        step_kwargs.setdefault("lookahead", 16)
+    if sigma_fn is None:          # fixed likelihood parameters: draws may be served from launches of several steps,
+        step_kwargs.setdefault("lookahead", 16)      # tuning included, because this driver knows where tuning ends
+        step_kwargs.setdefault("tune_draws", tune)
     step = PGBART([rv], num_particles=num_particles, batch=batch, likelihood=likelihood, sigma=sigma, chains=chains,
                   chain_base=chain_base_for_rank(rank, chains), seed=seed, device=device, **step_kwargs)
     N = step.n_rows

@@ -161,7 +161,7 @@ class _FakeCore:
     def enable_host_output(self, enable=True):
         self.host_output = enable
 
-    def enable_history(self, enable=True):
+    def enable_history(self, enable=True, steps_per_launch=1):
         self.history = enable
 
     def step(self, tune, sigma):

@@ -231,9 +231,9 @@ def test_lookahead_serves_the_same_draws():
 
     X, Y, _ = friedman(700, 5, 71)
     runs = []
-    for la in (1, 6):
-        mu = pmb.BART(f"mu{la}", X, Y, m=20, shared_history=False)
-        step = pmb.PGBART([mu], num_particles=8, chains=2, seed=71, sigma=0.8, lookahead=la)
+    for la, td in ((1, None), (6, None), (6, 10)):   # (6, 10): the 10 tuning calls are served ahead as well
+        mu = pmb.BART(f"mu{la}{td}", X, Y, m=20, shared_history=False)
+        step = pmb.PGBART([mu], num_particles=8, chains=2, seed=71, sigma=0.8, lookahead=la, tune_draws=td)
         vals, vis = [], []
         for d in range(10 + 17):                      # 17 posterior draws: launches of 6, 6, 6 (one runs ahead)
             if d == 10:
@@ -248,13 +248,23 @@ def test_lookahead_serves_the_same_draws():
             with pytest.raises(RuntimeError, match="fixed likelihood parameters"):
                 step.astep()                          # a draw computed with the old scale is waiting
         step.close()
-    (v1, s1, h1), (v6, s6, h6) = runs
-    assert np.array_equal(v1, v6) and s1 == s6
-    assert len(h1) == len(h6) == 2
-    for (b1, bt1), (b6, bt6) in zip(h1, h6):
-        assert all(np.array_equal(x, y) for x, y in zip(b1, b6)) and len(bt1) == len(bt6) == 17
-        for x, y in zip(bt1, bt6):
-            assert x[0] == y[0] and all(np.array_equal(p, q) for p, q in zip(x[1:], y[1:]))
+    v1, s1, h1 = runs[0]
+    for v6, s6, h6 in runs[1:]:
+        assert np.array_equal(v1, v6) and s1 == s6
+        assert len(h1) == len(h6) == 2
+        for (b1, bt1), (b6, bt6) in zip(h1, h6):
+            assert all(np.array_equal(x, y) for x, y in zip(b1, b6)) and len(bt1) == len(bt6) == 17
+            for x, y in zip(bt1, bt6):
+                assert x[0] == y[0] and all(np.array_equal(p, q) for p, q in zip(x[1:], y[1:]))
+    # a stop_tuning() that does not come after exactly tune_draws calls is an error, not a wrong chain
+    mu = pmb.BART("mu_td", X, Y, m=20, shared_history=False)
+    step = pmb.PGBART([mu], num_particles=8, chains=2, seed=71, sigma=0.8, lookahead=6, tune_draws=10)
+    for _ in range(4):
+        step.astep()
+    step.stop_tuning()
+    with pytest.raises(RuntimeError, match="tune_draws=10 does not match"):
+        step.astep()
+    step.close()
 
 
 def test_missing_data_through_the_api():
