@@ -407,13 +407,20 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     if rank != 0:
         return out
 
-    ms_kernel = float(np.mean(step_ms))
-    bytes_per_launch = algorithmic_bytes(N, grow / steps, tupd / steps, tune_upd / steps, lik)
+    # per LAUNCH of pgbart_step_kernel (a launch = `spl` steps of every chain): mean launch duration from the CUDA events on
+    # the launch stream, algorithmic bytes of the steps it ran
+    steps_per_launch_mean = steps / len(plan)
+    ms_kernel = float(np.mean(launch_ms))
+    bytes_per_launch = algorithmic_bytes(N, grow / steps, tupd / steps, tune_upd / steps, lik) * steps_per_launch_mean
     achieved = bytes_per_launch / (ms_kernel / 1e3) / 1e9
     traffic = traffic_src = None
     try:   # DRAM bytes per launch of the same command under `ncu --set full` (profiles/, committed)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name, {})
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        cap_spl = float(tj.get("steps_per_launch", 1))
+        if traffic is not None and abs(cap_spl - steps_per_launch_mean) > 1e-9:   # captured at another launch size: per step x steps
+            traffic = traffic / cap_spl * steps_per_launch_mean
+            traffic_src = f"{traffic_src}; captured at {cap_spl:g} steps per launch, scaled to {steps_per_launch_mean:g}"
     except Exception:
         pass
     out.update({
@@ -436,7 +443,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "frac_dram_traffic": (traffic / (ms_kernel / 1e3) / 1e9 / peak) if traffic else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                     "kernel": "pgbart_step_kernel", "kernel_ms": ms_kernel},
+                     "kernel": "pgbart_step_kernel", "kernel_ms": ms_kernel, "steps_per_launch": steps_per_launch_mean},
     })
     if cpu_baseline:
         # ---------------- CPU baseline: the oracle on the host cores, bounded sample of the same workload
