@@ -75,7 +75,8 @@ class PGBART(ArrayStepShared):
             raise ValueError("likelihood='normal' needs sigma= (the scale random variable, a point key, or a number)")
         value_vars = [model.rvs_to_values[v] for v in vars]
         fixed, key, back = _resolve_sigma(model, sigma)
-        core_kw = {k: kwargs.pop(k) for k in ("seed", "device", "depth_offset", "chain_base", "store_history") if k in kwargs}
+        core_kw = {k: kwargs.pop(k) for k in ("seed", "device", "depth_offset", "chain_base", "store_history", "lookahead", "tune_draws")
+                   if k in kwargs}     # (lookahead / tune_draws: draws served ahead, fixed likelihood parameters only — see pgbart.py)
         self._core = _CorePGBART(vars, num_particles=num_particles, batch=batch, likelihood=likelihood,
                                  sigma=1.0 if fixed is None else fixed, sigma_name=key, sigma_transform=back, **core_kw)
         self.tune = True
