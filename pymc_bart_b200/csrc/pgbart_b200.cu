@@ -271,6 +271,16 @@ struct __align__(16) KernelShared {   // static shared memory of a control CTA (
 };
 
 // ------------------------------------------------------------------ dataflow sync helpers
+__device__ __forceinline__ uint4 ld_acquire_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
   uint4 v;
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -2004,12 +2014,20 @@ __device__ __forceinline__ void worker_loop(const Params& P, GroupShared& sh, co
           ChainSync* sy = P.sync + c;
           // the descriptor {epoch, cmd, jobs, units} is ONE aligned 16-byte word, stored and loaded whole: a single
           // L2 round trip tells the group that an epoch started and what it is
+          // The poll IS the acquire (ld.acquire.gpu = LDG.STRONG.GPU + CCTL.IVALL, no MEMBAR): it pairs with the control
+          // CTA's release fence before the descriptor store, and it drops stale L1 lines, which is what lets the residual
+          // tiles be read through L1.  The other threads of the group are ordered behind it by the group barrier.
+          // -DBK_POLL_FENCE: the earlier form, a volatile poll + fence.acq_rel once the epoch is seen (A/B in
+          // profiles/r2_ab_acquire_poll.txt: the acquire polls are +4.8 % on C2, +1.4 % on C5).
+#ifndef BK_POLL_FENCE
+          const uint4 d = ld_acquire_v4(&sy->desc);
+#else
           const uint4 d = ld_volatile_v4(&sy->desc);
+#endif
           if ((int)(d.x - sh.seen[c]) <= 0) continue;   // (a descriptor left by an earlier launch is older than epoch_base)
-          // acquire (pairs with the control CTA's release fence); also drops stale L1 lines, which is what lets the
-          // residual tiles be read through L1.  A/B (profiles/): dropping it and reading everything with ld.cg is 3.8 %
-          // faster on C2 and works on this hardware, but leaves the epoch hand-over without a formal acquire — kept.
+#ifdef BK_POLL_FENCE
           if (lane == 0) fence_acq_rel_gpu();
+#endif
           __syncwarp();
           if (lane == 0) { sh.seen[c] = d.x; if ((d.y & 0xFFu) == BK_CMD_DONE) sh.fin[c] = 1; }
           __syncwarp();
@@ -2144,13 +2162,20 @@ __device__ __forceinline__ bool control_loop(const Params& P, int c, int tune, c
       int ab = 0;
       long long t0 = clock64();
       unsigned spins = 0;
+      // acquire poll of the done counter (pairs with the serving groups' red.release); -DBK_POLL_FENCE: relaxed poll + fence
+#ifndef BK_POLL_FENCE
+      while ((int)(ld_acquire_u32(&sy->done) - issued) < 0) {
+#else
       while ((int)(ld_relaxed_u32(&sy->done) - issued) < 0) {
+#endif
         if ((++spins & 63u) == 0) {
           if (ld_volatile_i32(P.abort_flag)) { ab = 1; break; }
           if (clock64() - t0 > BK_BARRIER_TIMEOUT_CYCLES) { atomicExch(P.abort_flag, 1); ab = 1; break; }
         }
       }
+#ifdef BK_POLL_FENCE
       fence_acq_rel_gpu();
+#endif
       if (!ab && ld_volatile_i32(P.abort_flag)) ab = 1;
       s_abort = ab;
       q1 = globaltimer_ns();
