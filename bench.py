@@ -228,15 +228,37 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
 
     # the posterior draws stay on the device: ring [draw, chain x group, N]; gathered once at the end
     # (rows keep the sampler's padding so that a draw is ONE contiguous device-to-device copy)
-    draws_dev = torch.empty((max(n_post, 1), nvc, dev.ld), dtype=torch.float32, device="cuda")
-    gathered = None
+    # N > 1: the run's one collective, the all-gather of the posterior draws (sampling.gather_posterior), is FUSED into the
+    # step kernel: the buffer is a symmetric allocation mapped into every peer, the commit sweep that keeps a draw stores it
+    # into block `rank` of all of them over NVLink (bk_set_draw_peers); what remains after the last launch is a barrier.
+    # --nccl-gather (or symmetric memory unavailable): one NCCL all_gather_into_tensor after the steps instead.
+    n_keep = max(n_post, 1)
+    gathered = peer_hdl = None
+    gather_kind = "none (1 GPU)"
     if world > 1:
-        gathered = torch.empty((world * draws_dev.shape[0], *draws_dev.shape[1:]), dtype=torch.float32, device="cuda")
+        from pymc_bart_b200.sampling import peer_draw_buffer
+
+        why = "--nccl-gather"
+        if not args.nccl_gather:
+            gathered, peer_hdl, peer_ptrs, why = peer_draw_buffer(n_keep, (nvc, dev.ld), rank, world)
+        if gathered is not None:
+            draws_dev = gathered[rank * n_keep:(rank + 1) * n_keep]
+            dev.set_draw_peers(peer_ptrs, gathered.data_ptr())
+            gather_kind = "P2P stores from the step kernel's commit sweep into every peer's buffer (NVLink), then a barrier"
+        else:
+            gather_kind = f"NCCL all_gather_into_tensor after the steps ({why})"
+    if gathered is None:
+        draws_dev = torch.empty((n_keep, nvc, dev.ld), dtype=torch.float32, device="cuda")
+        if world > 1:
+            gathered = torch.empty((world * n_keep, nvc, dev.ld), dtype=torch.float32, device="cuda")
     for i in range(warm):
         dev.step(True, 1.0)
-    if world > 1:   # warm the communicator with the collective of the timed region (channel / NVLS setup is not the run's cost)
+    if world > 1:   # warm the collective of the timed region (channel / NVLS / signal-pad setup is not the run's cost)
         with torch.cuda.stream(stream):
-            dist.all_gather_into_tensor(gathered, draws_dev)
+            if peer_hdl is not None:
+                peer_hdl.barrier(channel=0)
+            else:
+                dist.all_gather_into_tensor(gathered, draws_dev)
     sync_all()
     # K steps in launches of `spl` steps (bk_run_launch: the chains of a launch do not wait for each other between steps and
     # no launch gap separates them; sigma is fixed in this benchmark).  A launch never mixes tuning and
@@ -272,11 +294,23 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
         us_by_phase[tune] += max(last[c].us_total for c in range(nvc))
     t_gather0 = torch.cuda.Event(enable_timing=True); t_gather1 = torch.cuda.Event(enable_timing=True)
     t_gather0.record(stream)
-    if world > 1:   # the run's single collective (sampling.gather_posterior): ordered after the steps on their stream
+    if world > 1:   # the run's single collective: ordered after the steps on their stream
         with torch.cuda.stream(stream):
-            dist.all_gather_into_tensor(gathered, draws_dev)
+            if peer_hdl is not None:
+                peer_hdl.barrier(channel=0)      # every rank's launches are complete: every block of every buffer is there
+            else:
+                dist.all_gather_into_tensor(gathered, draws_dev)
     t_gather1.record(stream)
     torch.cuda.synchronize()
+    gather_check = None
+    if world > 1 and peer_hdl is not None:   # untimed: the fused gather against NCCL's
+        ref = torch.empty_like(gathered)
+        dist.all_gather_into_tensor(ref, draws_dev.contiguous())
+        torch.cuda.synchronize()
+        same = torch.tensor([1 if torch.equal(ref, gathered) else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        gather_check = "equal to nccl all_gather_into_tensor on every rank" if int(same.item()) else "MISMATCH against nccl all_gather_into_tensor"
+        del ref
     clocks.window(t_w0, time.perf_counter())
     launch_ms = [a.elapsed_time(b) for a, b in ev]
     step_ms = [ms / n for ms, (_, n, _) in zip(launch_ms, plan) for _ in range(n)]      # per step, for the tuning / posterior split
@@ -291,7 +325,7 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     g_all, t_all, tu_all = [float(v) for v in agg.tolist()]
     value = world * chains * steps / (total_ms_max / 1e3)
     out = {"value": value, "unit": "draws/s", "ms_per_step": total_ms_max / steps, "steps": steps, "warmup": warm,
-           "steps_per_launch": spl, "launches": len(plan),
+           "steps_per_launch": spl, "launches": len(plan), "gather": gather_kind, "gather_check": gather_check,
            "in_kernel_us": {"step": us_total / steps, "control_chain0": us_control / steps, "data_wait_chain0": us_data / steps,
                             "step_tuning": us_by_phase[True] / max(n_tune, 1), "step_post": us_by_phase[False] / max(n_post, 1),
                             "event_tuning": 1e3 * float(np.mean(step_ms[:n_tune])) if n_tune else None,
@@ -474,6 +508,8 @@ def main():
     ap.add_argument("--clock-ms", type=int, default=20, help="nvidia-smi sampling period in ms (0 = no clock sampling)")
     ap.add_argument("--tune-ahead", type=int, default=1, help="e2e leg: tell the step where tuning ends (PGBART(tune_draws=)), so tuning "
                     "steps are served ahead too (0 = the PyMC protocol: one launch per tuning call)")
+    ap.add_argument("--nccl-gather", action="store_true", help="N > 1: gather the draws with one NCCL all_gather after the steps "
+                    "instead of the P2P stores fused into the step kernel")
     ap.add_argument("--lookahead", type=int, default=16, help="PGBART(lookahead=) of the e2e leg (1 = one launch per astep call)")
     ap.add_argument("--steps-per-launch", type=int, default=16, help="steps of every chain per kernel launch in the device-timed leg (1..16)")
     args = ap.parse_args()
@@ -513,7 +549,7 @@ def main():
         else:
             config = {k: main_m[k] for k in ("workload", "draws_timed", "l2", "grow_events_per_tree_update", "tree_updates_per_s",
                                              "grow_events_per_s", "rounds_per_tree_update", "grid_phases_per_step", "in_kernel_us",
-                                             "steps_per_launch", "launches", "gather_ms",
+                                             "steps_per_launch", "launches", "gather", "gather_check", "gather_ms",
                                              "gather_bytes_per_rank", "predict")}
             if c5_m is not None:
                 c5_m["n_gpus"] = world

@@ -175,6 +175,13 @@ int bk_step_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_hos
  * step <= n_trees); the trace needs one step per launch.  bk_step_launch/wait = n_steps 1. */
 int bk_run_launch(bk_handle* h, int n_steps, int tune, const float* sigma_host, float* draws_dev);
 int bk_run_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host);
+/* Multi-GPU runs (chains are independent replicas, one process per GPU): the run's one collective is the
+ * all-gather of the posterior draws.  With peers set, the commit sweep that writes a draw into draws_dev also stores it
+ * into the same place of every peer's buffer (P2P stores over NVLink): local_base is this GPU's buffer, peer_bases[i]
+ * this process's mapping of peer i's buffer of the same layout (e.g. torch symmetric memory), draws_dev of
+ * bk_run_launch points into local_base.  After the last launch a barrier across the ranks is all that is left of the
+ * gather.  n_peers = 0 switches it off.  At most 7 peers. */
+int bk_set_draw_peers(bk_handle* h, int n_peers, const void* const* peer_bases, const void* local_base);
 void* bk_stream(bk_handle* h);
 
 /* Host copy of the value (tests/test_bart.py:121-123,197: the step returns the new value of the BART variable as a

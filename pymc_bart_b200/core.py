@@ -118,6 +118,13 @@ class DeviceSampler:
         _cabi.check(self.lib.bk_run_wait(self.h, vi.ctypes.data, C.cast(stats, C.c_void_p)), "bk_run_wait")
         return vi, [stats[i * self.C:(i + 1) * self.C] for i in range(n)]
 
+    def set_draw_peers(self, peer_ptrs, local_ptr):
+        """The draws a launch writes into `draws_out` (a view into the buffer at `local_ptr`) also go to the same place of
+        the peers' buffers (device pointers as mapped in this process), by P2P stores from the commit sweep."""
+        n = len(peer_ptrs)
+        arr = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        _cabi.check(self.lib.bk_set_draw_peers(self.h, n, C.cast(arr, C.c_void_p), C.c_void_p(int(local_ptr))), "bk_set_draw_peers")
+
     def stream(self):
         """torch view of the sampler's CUDA stream (for events and ordered copies)."""
         return self.torch.cuda.ExternalStream(int(self.lib.bk_stream(self.h)), device=self.device)

@@ -1701,8 +1701,12 @@ __device__ __forceinline__ void sweep_unit(const Params& P, int c, int ctile, Gr
         }
       }
       __stcg(reinterpret_cast<float4*>(stp), make_float4(stv[0], stv[1], stv[2], stv[3]));
-      if (s1.w > 0)   // the step's last commit: keep the draw (bk_run_launch's draws_out)
-        __stcs(reinterpret_cast<float4*>(P.draws_out + ((size_t)(s1.w - 1) * P.C + c) * P.Npad + base), make_float4(stv[0], stv[1], stv[2], stv[3]));
+      if (s1.w > 0) {   // the step's last commit: keep the draw (bk_run_launch's draws_out), here and on the peer GPUs
+        float* dp = P.draws_out + ((size_t)(s1.w - 1) * P.C + c) * P.Npad + base;
+        __stcs(reinterpret_cast<float4*>(dp), make_float4(stv[0], stv[1], stv[2], stv[3]));
+        for (int pe = 0; pe < P.n_draw_peers; ++pe)   // P2P stores over NVLink: the all-gather of the draws, fused
+          __stcs(reinterpret_cast<float4*>(reinterpret_cast<char*>(dp) + P.draw_peer_delta[pe]), make_float4(stv[0], stv[1], stv[2], stv[3]));
+      }
       if (new_row != BK_ROW_FOREST) __stcg(reinterpret_cast<unsigned*>(idp), nid4);
       if (do_wf) {
         __stcg(reinterpret_cast<float4*>(mp), make_float4(mean[0], mean[1], mean[2], mean[3]));
@@ -1867,8 +1871,12 @@ __device__ __forceinline__ void sweep_unit_multi(const Params& P, int c, int cti
           }
         }
         __stcg(reinterpret_cast<float4*>(stp), make_float4(stv[0], stv[1], stv[2], stv[3]));
-        if (s1.w > 0)
-          __stcs(reinterpret_cast<float4*>(P.draws_out + (((size_t)(s1.w - 1) * P.C + c) * K + j) * P.Npad + base), make_float4(stv[0], stv[1], stv[2], stv[3]));
+        if (s1.w > 0) {
+          float* dp = P.draws_out + (((size_t)(s1.w - 1) * P.C + c) * K + j) * P.Npad + base;
+          __stcs(reinterpret_cast<float4*>(dp), make_float4(stv[0], stv[1], stv[2], stv[3]));
+          for (int pe = 0; pe < P.n_draw_peers; ++pe)
+            __stcs(reinterpret_cast<float4*>(reinterpret_cast<char*>(dp) + P.draw_peer_delta[pe]), make_float4(stv[0], stv[1], stv[2], stv[3]));
+        }
         if (do_wf) {
           __stcg(reinterpret_cast<float4*>(mp), make_float4(mean[0], mean[1], mean[2], mean[3]));
           __stcg(reinterpret_cast<float4*>(m2p), make_float4(m2[0], m2[1], m2[2], m2[3]));
@@ -2496,7 +2504,7 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   P.accK = (unsigned long long*)(w + L.accK); P.acc_sd = (unsigned long long*)(w + L.acc_sd);
   P.alpha_vec = (double*)(w + L.alpha_vec); P.cum = (double*)(w + L.cum); P.p_leaf = (double*)(w + L.p_leaf);
   P.rules = (int32_t*)(w + L.rules); P.col_nan = (int32_t*)(w + L.col_nan); P.stats = (bk_step_stats*)(w + L.stats);
-  P.vi = (int32_t*)(w + L.stats + (size_t)P.C * sizeof(bk_step_stats)); P.rec_stride = (int32_t)L.rec_stride; P.draws_out = nullptr;
+  P.vi = (int32_t*)(w + L.stats + (size_t)P.C * sizeof(bk_step_stats)); P.rec_stride = (int32_t)L.rec_stride; P.draws_out = nullptr; P.n_draw_peers = 0;
   P.trace = (bk_trace_rec*)(w + L.trace); P.sync = (ChainSync*)(w + L.sync); P.abort_flag = (int32_t*)(w + L.abort_flag);
   h->split_prior_dev = (double*)(w + L.split_prior);
 
@@ -2664,6 +2672,17 @@ int bk_run_launch(bk_handle* h, int n_steps, int tune, const float* sigma_host, 
     h->host_lower = l;
   }
   h->n_launched += 1;
+  return BK_OK;
+}
+
+int bk_set_draw_peers(bk_handle* h, int n_peers, const void* const* peer_bases, const void* local_base) {
+  if (!h || n_peers < 0 || n_peers > BK_MAX_DRAW_PEERS || (n_peers > 0 && (!peer_bases || !local_base))) { set_err("bad argument"); return BK_ERR_ARG; }
+  if (h->n_launched != h->n_waited) { set_err("steps in flight"); return BK_ERR_STATE; }
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peer_bases[i]) { set_err("NULL peer buffer"); return BK_ERR_ARG; }
+    h->P.draw_peer_delta[i] = (long long)((const char*)peer_bases[i] - (const char*)local_base);
+  }
+  h->P.n_draw_peers = n_peers;
   return BK_OK;
 }
 

@@ -44,6 +44,7 @@
 #define BK_ST_DONE 3
 #define BK_ST_WAIT_LL 4
 
+#define BK_MAX_DRAW_PEERS 7   // the other GPUs of one NVSwitch domain of 8
 #ifndef BK_JOB_COPIES
 #define BK_JOB_COPIES 1
 #endif
@@ -224,6 +225,10 @@ struct Params {
   bk_step_stats* stats;  // [C] of record 0
   int32_t rec_stride;
   float* draws_out;    // per launch: [n_steps][C*K][Npad] the sum of trees after every step, or nullptr
+  // Draws also stored into the same place of peer GPUs' buffers (bk_set_draw_peers): byte distance from this GPU's
+  // buffer to each peer's mapping of its own.  The posterior all-gather of a multi-GPU run happens inside the commit sweep.
+  int32_t n_draw_peers;
+  long long draw_peer_delta[BK_MAX_DRAW_PEERS];
   bk_trace_rec* trace;   // [C][trace_cap]
   ChainSync* sync;   // [C]
   int32_t* abort_flag;

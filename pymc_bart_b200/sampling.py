@@ -30,6 +30,38 @@ def gather_posterior(local, world: int):
     return out
 
 
+def peer_draw_buffer(rows_per_rank: int, row_shape, rank: int, world: int):
+    """Buffer for the all-gather of device-resident draws FUSED into the step kernel (bk_set_draw_peers): a symmetric
+    allocation [world * rows_per_rank, *row_shape] float32 on every rank, mapped into every peer (torch symmetric memory:
+    CUDA VMM handles exchanged through the process group's store).  Rank r points bk_run_launch's draws_out into its block
+    r; the commit sweep stores each draw there and into the same place of the 7 or fewer peers over NVLink, so after the last
+    launch a barrier is all that is left of the collective.
+    Returns (buffer, handle, peer_ptrs, why): buffer None (and `why` set) when symmetric memory is unavailable — every
+    rank takes the same branch (the outcome is agreed with an all-reduce); the caller then uses gather_posterior."""
+    import torch
+    import torch.distributed as dist
+
+    buf = hdl = None
+    ptrs, why = [], ""
+    try:
+        if world - 1 > 7:
+            raise RuntimeError("more than 7 peers")
+        import torch.distributed._symmetric_memory as symm
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        buf = symm.empty((world * int(rows_per_rank), *row_shape), dtype=torch.float32, device=dev)
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        ptrs = [int(hdl.buffer_ptrs[r]) for r in range(world) if r != rank]
+    except Exception as e:  # noqa: BLE001 - any failure means "use NCCL"
+        why = f"{type(e).__name__}: {e}"[:200]
+        buf = hdl = None
+    ok = torch.tensor([1 if buf is not None else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        return None, None, [], why or "symmetric memory failed on another rank"
+    return buf, hdl, ptrs, ""
+
+
 def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1), sigma=1.0, seed=0,
            likelihood="normal", sigma_fn=None, keep_draws=True, **step_kwargs):
     """Returns a dict: posterior (chains_total, draws, N) float32 [if keep_draws],
