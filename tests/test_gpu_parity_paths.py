@@ -174,3 +174,38 @@ def test_several_steps_per_launch_equal_single_steps():
     with pytest.raises(RuntimeError):
         b.run_launch(17, True, 1.0)
     a.close(); b.close()
+
+
+def test_draws_also_stored_into_peer_buffers():
+    """bk_set_draw_peers: the commit sweep that keeps a draw also stores it into the same place of every peer buffer
+    (multi-GPU runs map the other ranks' buffers here; the test uses two more buffers on the same GPU as the peers).
+    bench.py checks the real thing against NCCL's all-gather at N > 1 (`config.gather_check`)."""
+    import torch
+
+    from pymc_bart_b200.core import DeviceSampler
+
+    X, y, _ = friedman(2500, 5, 62)
+    s = make_settings(X, y, m=10, num_particles=8, seed=62, n_chains=2)
+    d = DeviceSampler(s, X, y)
+    n_keep, world, rank = 6, 3, 1
+    bufs = [torch.zeros((world * n_keep, d.rows, d.ld), dtype=torch.float32, device="cuda") for _ in range(world)]
+    d.set_draw_peers([bufs[0].data_ptr(), bufs[2].data_ptr()], bufs[rank].data_ptr())
+    mine = bufs[rank][rank * n_keep:(rank + 1) * n_keep]
+    d.run_launch(4, True, 1.0)                       # tuning steps keep no draw
+    d.run_wait()
+    d.run_launch(n_keep, False, 1.0, draws_out=mine)
+    d.run_wait()
+    torch.cuda.synchronize()
+    assert torch.equal(mine[-1], d.sum_trees_dev) and float(mine.abs().sum()) > 0
+    for b in bufs:
+        assert torch.equal(b[rank * n_keep:(rank + 1) * n_keep], mine)
+        assert float(b[:rank * n_keep].abs().sum()) == 0 and float(b[(rank + 1) * n_keep:].abs().sum()) == 0
+    d.set_draw_peers([], 0)                          # off again: only the local buffer is written
+    before = bufs[0].clone()
+    d.run_launch(2, False, 1.0, draws_out=mine[:2])
+    d.run_wait()
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[0], before) and torch.equal(mine[1], d.sum_trees_dev)
+    with pytest.raises(RuntimeError):
+        d.set_draw_peers([1] * 8, bufs[rank].data_ptr())
+    d.close()
