@@ -87,6 +87,12 @@
 #define BK_U_FINAL 6u     /* final systematic resampling               */
 #define BK_U_PICK 7u      /* final position pick                       */
 
+/* SubsetSplit (docs/api_reference.rst:16 `SubsetSplitRule`): categorical covariates hold integer
+ * category codes 0..BK_SUBSET_MAX_CATS-1 (the host maps arbitrary category values to codes); the split "value" of a node
+ * is the SET of categories that go left, carried as the float whose integer value is the set's bit mask (< 2^24: exact). */
+#define BK_SUBSET_MAX_CATS 24
+#define BK_MAX_SUBSET_COLS 8  /* columns with the subset rule per model (per-row presence masks are kept for each) */
+
 /* likelihood families */
 #define BK_LIK_NORMAL 0
 #define BK_LIK_BERNOULLI_LOGIT 1
@@ -139,6 +145,38 @@ BK_HD bk_u32x4 bk_rng(uint32_t seed, uint32_t chain, uint32_t draw, uint32_t gro
 BK_HD double bk_u01(uint32_t x) { return BK_DMUL((double)x, 2.3283064365386963e-10); }
 /* floor(x * n / 2^32): uniform index in [0, n) without any rounding */
 BK_HD uint32_t bk_index(uint32_t x, uint32_t n) { return bk_mulhi32(x, n); }
+
+/* ------------------------------------------------------------ SubsetSplit */
+/* category code of a covariate value: the integers 0..23; anything else (NaN included) has no category (-1) */
+BK_HD int bk_subset_code(float x) {
+  if (!(x >= 0.0f && x < (float)BK_SUBSET_MAX_CATS)) return -1;
+  const int c = (int)x;
+  return ((float)c == x) ? c : -1;
+}
+/* does a row with covariate x go left at a subset split whose node carries `split`? */
+BK_HD int bk_subset_left(float x, float split) {
+  const int c = bk_subset_code(x);
+  return c >= 0 && ((((uint32_t)split) >> c) & 1u);
+}
+/* The set drawn for a node whose members show the categories `present` (bit c = some member with a value has category
+ * c): a uniformly drawn NON-EMPTY subset of the present categories without the largest one — every split of the
+ * present categories into two non-empty groups is drawn with the same probability and the right child is never empty
+ * (the historical rule: `unique(values)[:-1]`, redrawn until non-empty).  pick = 1 + floor(r * n_sub / 2^32) indexes
+ * the n_sub = 2^(u-1) - 1 non-empty subsets of the u - 1 candidates; bit i of pick decides the i-th smallest
+ * candidate.  Returns 0 (no split: the node stays a leaf) when fewer than two categories are present. */
+BK_HD uint32_t bk_subset_draw(uint32_t present, uint32_t r) {
+  present &= (1u << BK_SUBSET_MAX_CATS) - 1u;
+  int u = 0, top = -1;
+  for (int c = 0; c < BK_SUBSET_MAX_CATS; ++c) if ((present >> c) & 1u) { u += 1; top = c; }
+  if (u < 2) return 0u;
+  const uint32_t cand = present & ~(1u << top);
+  const uint32_t n_sub = (1u << (u - 1)) - 1u;
+  uint32_t pick = bk_index(r, n_sub) + 1u;
+  uint32_t out = 0u;
+  for (int c = 0; c < BK_SUBSET_MAX_CATS; ++c)
+    if ((cand >> c) & 1u) { if (pick & 1u) out |= 1u << c; pick >>= 1; }
+  return out;
+}
 
 /* ------------------------------------------------------- bit-level helpers */
 BK_HD uint64_t bk_d2bits(double d) {

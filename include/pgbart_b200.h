@@ -52,6 +52,8 @@ extern "C" {
 
 #define BK_RULE_CONTINUOUS 0 /* "ContinuousSplit": x <= s  (tests/test_bart.py:143) */
 #define BK_RULE_ONEHOT 1     /* "OneHotSplit":     x == s  (tests/test_bart.py:144) */
+#define BK_RULE_SUBSET 2     /* "SubsetSplit":     category(x) in S (docs/api_reference.rst:16, pymc_bart/bart.py:103); the column holds
+                                integer category codes 0..23, S travels as the float (mask of S) — bk_spec.h bk_subset_* */
 
 typedef struct bk_handle_s bk_handle;
 

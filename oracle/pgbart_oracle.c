@@ -15,7 +15,7 @@
  *   - inputs read from the op ............ pymc_bart/bart.py:141-158
  *   - depth prior alpha*(1+d)^-beta ...... pymc_bart/bart.py:107-109 (table passed in)
  *   - initial value Y.mean() ............. pymc_bart/bart.py:148
- *   - split rules "ContinuousSplit"/"OneHotSplit" tests/test_bart.py:143-145
+ *   - split rules "ContinuousSplit"/"OneHotSplit" tests/test_bart.py:143-145; "SubsetSplit" docs/api_reference.rst:16
  *   - variable_inclusion counts .......... pymc_bart/utils.py:1387-1398, tests/test_bart.py:59-64
  *   - VI dominance / prediction self-consistency: tests/test_bart.py:44-64, tests/test_utils.py:24-32
  * The only exact fixture the reference has for this path — the varint/base64 codec
@@ -31,7 +31,7 @@
  *   B2  particle 0 = old tree (never grows); 1..P-1 = stumps
  *   B3  pop one node per particle and round: stay leaf w.p. p_leaf[depth];
  *       variable ~ split prior; split value = X[k-th member, var]
- *   B4  partition the node's rows (x <= s / x == s)
+ *   B4  partition the node's rows (x <= s / x == s / category(x) in S)
  *   B5  leaf value = mean(sum_trees over members)/m + z * leaf_sd
  *   B6  log-weight = Gaussian log-likelihood from per-leaf (n, sum r) and the tree-independent total sum r^2, or Bernoulli-logit
  *       log-likelihood from a second pass over the rows of the two new leaves (fixed-point terms)
@@ -178,6 +178,7 @@ int bko_create(const bk_settings* s, const float* X, const float* y, int chain_l
   o->K = s->n_outputs > 1 ? s->n_outputs : 1;
   if (o->K > 1) {
     if (o->K > BK_MAX_OUTPUTS || s->n_groups > 1) return BK_ERR_UNSUPPORTED;
+    for (int v = 0; v < o->p; ++v) if (o->rules[v] == BK_RULE_SUBSET) return BK_ERR_UNSUPPORTED;   /* (device: the same) */
     const size_t KN = (size_t)o->K * (size_t)N;
     o->stk = (float*)malloc(sizeof(float) * KN);
     o->noik = (float*)malloc(sizeof(float) * KN);
@@ -276,7 +277,22 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
   const float* xc = o->X + (size_t)v * (size_t)N;
   float s = 0.0f;
   int have = 0;
-  for (int t = 0; t < BK_SPLIT_TRIES && !have; ++t) {
+  const int subset = o->rules[v] == BK_RULE_SUBSET;
+  if (subset) {
+    /* SubsetSplit (bk_spec.h bk_subset_draw): the categories present among the node's members
+     * that have a value, then a uniformly drawn non-empty subset of them without the largest; fewer than two
+     * categories present: no split.  The set travels as the float whose integer value is its bit mask. */
+    uint32_t present = 0u;
+    for (int i = 0; i < N; ++i) {
+      if (q->ids[i] != (uint8_t)j) continue;
+      const int code = bk_subset_code(xc[i]);
+      if (code >= 0) present |= 1u << code;
+    }
+    const uint32_t mask = bk_subset_draw(present, wv.v[0]);
+    s = (float)mask;
+    have = mask != 0u;
+  }
+  for (int t = 0; t < BK_SPLIT_TRIES && !have && !subset; ++t) {
     uint32_t k = bk_index(wv.v[t], (uint32_t)n), seen = 0;
     for (int i = 0; i < N; ++i) {
       if (q->ids[i] == (uint8_t)j) { if (seen == k) { s = xc[i]; break; } seen++; }
@@ -297,7 +313,7 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
       if (o->s.likelihood == BK_LIK_BERNOULLI_LOGIT) ll_dropped += (int64_t)bk_bern_q(o->y[i], o->noi[i], 0.0f);
       continue;
     }
-    int left = onehot ? (x == s) : (x <= s);
+    int left = subset ? bk_subset_left(x, s) : (onehot ? (x == s) : (x <= s));
     bk_stats* t = left ? &sl : &sr;
     q->ids[i] = (uint8_t)(left ? L : R);
     int64_t a = (int64_t)o->qr[i];
@@ -745,7 +761,8 @@ static double predict_tree(const bk_node* nodes, const float* x, const uint8_t* 
       sn[sp] = l; sw[sp] = BK_DMUL(w, wl); ++sp;
     } else {
       float xv = x[nd->var];
-      int left = (rules && rules[nd->var] == BK_RULE_ONEHOT) ? (xv == nd->split) : (xv <= nd->split);
+      const int rule = rules ? rules[nd->var] : BK_RULE_CONTINUOUS;
+      int left = rule == BK_RULE_SUBSET ? bk_subset_left(xv, nd->split) : (rule == BK_RULE_ONEHOT ? (xv == nd->split) : (xv <= nd->split));
       sn[sp] = left ? l : r; sw[sp] = w; ++sp;
     }
   }

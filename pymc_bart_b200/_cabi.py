@@ -21,6 +21,9 @@ BK_LIK_CATEGORICAL = 3
 BK_MAX_OUTPUTS = 7
 BK_RULE_CONTINUOUS = 0
 BK_RULE_ONEHOT = 1
+BK_RULE_SUBSET = 2
+BK_SUBSET_MAX_CATS = 24     # category codes 0..23 (bk_spec.h)
+BK_MAX_SUBSET_COLS = 8
 
 
 class BkSettings(C.Structure):

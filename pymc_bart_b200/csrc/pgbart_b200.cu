@@ -157,7 +157,7 @@ __shared__ long long s_ct_last;
 // multi-output and missing-value code cost the plain C2 / C5 steps 8 %: twice the code for the instruction cache, and
 // calls in the hot loops):
 //   BK_MODE_PLAIN    single output per forest, no NaN in X
-//   BK_MODE_MISSING  X holds NaNs (Params::has_nan)
+//   BK_MODE_MISSING  X holds NaNs (Params::has_nan) and / or some column uses the SubsetSplit rule (Params::n_subset)
 //   BK_MODE_MULTI    shared-tree multi-output (Params::K > 1)
 #define BK_MODE_PLAIN 0
 #define BK_MODE_MISSING 1
@@ -880,7 +880,10 @@ __device__ __forceinline__ int open_round(const Params& P, int c, ChainCtl* ctl,
         v = pre ? sh.pre_v[q]
                 : draw_variable_dev(P, c, sh, bk_u01(bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAR).v[0]));
         if (n >= 2) {
-          k = bk_index(pre ? sh.pre_u3[q] : bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAL).v[0], (uint32_t)n);
+          const uint32_t u3 = pre ? sh.pre_u3[q] : bk_rng(S0, C0, D0, G0, (uint32_t)t, (uint32_t)round, (uint32_t)q, BK_U_VAL).v[0];
+          // SubsetSplit columns draw a set of categories from the raw uniform (bk_subset_draw), not a member index
+          const bool sub = BK_MISSING_ENABLED && (v < BK_CUM_SMEM ? (int)sh.rules[v] : P.rules[v]) == BK_RULE_SUBSET;
+          k = sub ? u3 : bk_index(u3, (uint32_t)n);
           kind = 1;
         }
       }
@@ -950,15 +953,27 @@ __device__ __forceinline__ int open_round(const Params& P, int c, ChainCtl* ctl,
       if (sl >= P.P) break;
       if (sh.s_kind[sl] != 1) continue;
       float sv;
-      if (sh.s_row[sl] == BK_ROW_VIRTUAL) {
-        sv = __ldg(P.X + (size_t)sh.s_v[sl] * P.Npad + sh.s_k[sl]);
+      const int vv = sh.s_v[sl];
+      if (BK_MISSING_ENABLED && (vv < BK_CUM_SMEM ? (int)sh.rules[vv] : P.rules[vv]) == BK_RULE_SUBSET) {
+        // SubsetSplit: the categories present among the node's members were left by the workers beside the member
+        // counts (a stump's root: the whole column's); the set is drawn from them.  Fewer than two present: no split
+        // (NaN = the cancelled-split marker of the missing-value path; a set's float is an integer < 2^24).
+        const int rw = sh.s_row[sl];
+        const unsigned present = rw == BK_ROW_VIRTUAL ? __ldg(P.col_cats + vv)
+                                                      : __ldcg(P.present + ((size_t)c * P.R + rw) * BK_MAX_SUBSET_COLS + __ldg(P.subset_idx + vv));
+        const unsigned set = bk_subset_draw(present, sh.s_k[sl]);
+        sv = set ? (float)set : bk_bits2f(0x7FC00000u);
       } else {
-        int err = 0;
-        sv = select_split(P, c, sh.s_row[sl], sh.s_j[sl], sh.s_k[sl], sh.s_v[sl], &err);
-        if (lane == 0 && err) atomicOr(&sh.err_bits, err);
-        CTN(29);
+        if (sh.s_row[sl] == BK_ROW_VIRTUAL) {
+          sv = __ldg(P.X + (size_t)vv * P.Npad + sh.s_k[sl]);
+        } else {
+          int err = 0;
+          sv = select_split(P, c, sh.s_row[sl], sh.s_j[sl], sh.s_k[sl], vv, &err);
+          if (lane == 0 && err) atomicOr(&sh.err_bits, err);
+          CTN(29);
+        }
+        if (BK_MISSING_ENABLED && sv != sv) sv = retry_split_value(P, c, sh, buf, sl, S0, C0, D0, G0, t, round);   // the candidate's covariate is missing
       }
-      if (BK_MISSING_ENABLED && sv != sv) sv = retry_split_value(P, c, sh, buf, sl, S0, C0, D0, G0, t, round);   // the candidate's covariate is missing
       if (lane == 0) { sh.s_split[sl] = sv; if (sv != sv) atomicAdd(&sh.n_nan_fail, 1); }
     }
   }
@@ -991,14 +1006,20 @@ __device__ __forceinline__ int open_round(const Params& P, int c, ChainCtl* ctl,
     if (i % 3 == 1 && i / 3 < tot_g) piece.z = __float_as_uint(sh.s_split[sh.jobs[i / 3].slot]);
     reinterpret_cast<uint4*>(ctl->jobs[0])[i] = piece;
   }
-  if (P.nb > 0 && threadIdx.x >= 32) {
-    // large N: the bucket counts of every row that gets new member counts this epoch start from zero (the workers add)
+  const bool zero_present = BK_MISSING_ENABLED && P.n_subset > 0;
+  if ((P.nb > 0 || zero_present) && threadIdx.x >= 32) {
+    // large N: the bucket counts of every row that gets new member counts this epoch start from zero (the workers add);
+    // SubsetSplit: so do the row's category presence masks (the workers OR)
     const int wj = (int)(threadIdx.x >> 5) - 1, nw = (BK_CTRL_THREADS >> 5) - 1;
     for (int ji = wj; ji < nj; ji += nw) {
       const Job& jb = sh.jobs[ji];
       if (jb.next_node < 0) continue;
-      unsigned* cz = P.coarse + ((size_t)c * P.R + (jb.kind == BK_JOB_PARTITION ? jb.dst_row : jb.src_row)) * P.nb_stride;
-      for (int i = lane; i < P.nb_stride; i += 32) cz[i] = 0u;
+      const size_t rr = (size_t)c * P.R + (jb.kind == BK_JOB_PARTITION ? jb.dst_row : jb.src_row);
+      if (P.nb > 0) {
+        unsigned* cz = P.coarse + rr * P.nb_stride;
+        for (int i = lane; i < P.nb_stride; i += 32) cz[i] = 0u;
+      }
+      if (zero_present && lane < BK_MAX_SUBSET_COLS) P.present[rr * BK_MAX_SUBSET_COLS + lane] = 0u;
     }
   }
   if (threadIdx.x == 0) {
@@ -1351,6 +1372,34 @@ __device__ __forceinline__ unsigned long long take_stat(unsigned* L, int k) {
 // MULTI: shared-tree multi-output (Params::K > 1): per job the sums of q(sum_trees[j]) of BOTH children for every
 // output j go to `acck` (no parent statistics are kept per output); no Gaussian residual statistics (the weight comes
 // from the LL epoch).
+// SubsetSplit (feature instantiation only).  subset_left: bk_subset_left with the node's set already decoded.
+__device__ __forceinline__ bool subset_left(float x, unsigned set) {
+  const int cd = bk_subset_code(x);
+  return cd >= 0 && ((set >> cd) & 1u);
+}
+// The categories present among the members of a row's counted node (m0 / m1: 0x80 in the bytes of the member rows of
+// this lane), for every subset column: OR over the tile, one global atomic per (tile, column) that found any.  The
+// control CTA zeroed the row's masks before it published the epoch and reads them when it pops that node.
+__device__ __forceinline__ void note_present(const Params& P, unsigned uCR, int row, unsigned m0, unsigned m1, const float* x_b, unsigned uNpad,
+                                             int lane) {
+  const bool anym = (m0 | m1) != 0u;
+  for (int sc = 0; sc < P.n_subset; ++sc) {
+    unsigned bits = 0u;
+    if (anym) {
+      const float4* xp = reinterpret_cast<const float4*>(x_b + (unsigned long long)(unsigned)__ldg(P.subset_cols + sc) * uNpad);
+      const float4 a = __ldg(xp), b = __ldg(xp + 1);
+      const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (m0 & (0x80u << (8 * e))) { const int cd = bk_subset_code(xs[e]); if (cd >= 0) bits |= 1u << cd; }
+        if (m1 & (0x80u << (8 * e))) { const int cd = bk_subset_code(xs[4 + e]); if (cd >= 0) bits |= 1u << cd; }
+      }
+    }
+    bits = __reduce_or_sync(0xffffffffu, bits);
+    if (lane == 0 && bits) atomicOr(P.present + (unsigned long long)(uCR + (unsigned)row) * BK_MAX_SUBSET_COLS + sc, bits);
+  }
+}
+
 template <bool MISSING, bool MULTI>
 __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
                                            unsigned* __restrict__ sacc, unsigned (*__restrict__ acck)[BK_MAX_OUTPUTS][4]) {
@@ -1409,7 +1458,13 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       if (!sparse || (mem0 | mem1)) {
         const float4* xp = reinterpret_cast<const float4*>(x_b + (unsigned long long)(unsigned)var * uNpad);
         x0 = __ldg(xp); x1 = __ldg(xp + 1);
-        if (rule == BK_RULE_ONEHOT) {
+        if (MISSING && rule == BK_RULE_SUBSET) {   // the node's set of left-going categories travels as the float of its bit mask
+          const unsigned set = (unsigned)split;
+          if (subset_left(x0.x, set)) lb0 |= 0x000000FFu; if (subset_left(x0.y, set)) lb0 |= 0x0000FF00u;
+          if (subset_left(x0.z, set)) lb0 |= 0x00FF0000u; if (subset_left(x0.w, set)) lb0 |= 0xFF000000u;
+          if (subset_left(x1.x, set)) lb1 |= 0x000000FFu; if (subset_left(x1.y, set)) lb1 |= 0x0000FF00u;
+          if (subset_left(x1.z, set)) lb1 |= 0x00FF0000u; if (subset_left(x1.w, set)) lb1 |= 0xFF000000u;
+        } else if (rule == BK_RULE_ONEHOT) {
           if (x0.x == split) lb0 |= 0x000000FFu; if (x0.y == split) lb0 |= 0x0000FF00u;
           if (x0.z == split) lb0 |= 0x00FF0000u; if (x0.w == split) lb0 |= 0xFF000000u;
           if (x1.x == split) lb1 |= 0x000000FFu; if (x1.y == split) lb1 |= 0x0000FF00u;
@@ -1523,20 +1578,24 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
         if (lane < nl) atomicAdd(sacc + ji * BK_LIMBS + lane, v);   // one shared-memory atomic instruction per job
       }
       if (next_node >= 0) {
-        const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(n0, next4)) + __popc(bytes_eq_msb(n1, next4)));
+        const unsigned nm0 = bytes_eq_msb(n0, next4), nm1 = bytes_eq_msb(n1, next4);
+        const unsigned cnt = (unsigned)(__popc(nm0) + __popc(nm1));
         const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) {
           cnt_c[(unsigned long long)(unsigned)dst_row * uCnt] = tot;
           if (P.nb > 0 && tot) atomicAdd(P.coarse + (unsigned long long)(uCR + (unsigned)dst_row) * (unsigned)P.nb_stride + ((unsigned)tile / BK_COARSE_TILES), tot);
         }
+        if (MISSING && P.n_subset > 0 && tot) note_present(P, uCR, dst_row, nm0, nm1, x_b, uNpad, lane);
       }
     } else if (kind == BK_JOB_COUNT) {
-      const unsigned cnt = (unsigned)(__popc(bytes_eq_msb(w0, next4)) + __popc(bytes_eq_msb(w1, next4)));
+      const unsigned nm0 = bytes_eq_msb(w0, next4), nm1 = bytes_eq_msb(w1, next4);
+      const unsigned cnt = (unsigned)(__popc(nm0) + __popc(nm1));
       const unsigned tot = __reduce_add_sync(0xffffffffu, cnt);
       if (lane == 0) {
         cnt_c[(unsigned long long)(unsigned)src_row * uCnt] = tot;
         if (P.nb > 0 && tot) atomicAdd(P.coarse + (unsigned long long)(uCR + (unsigned)src_row) * (unsigned)P.nb_stride + ((unsigned)tile / BK_COARSE_TILES), tot);
       }
+      if (MISSING && P.n_subset > 0 && tot) note_present(P, uCR, src_row, nm0, nm1, x_b, uNpad, lane);
     }
   }
 }
@@ -2245,7 +2304,7 @@ __device__ __forceinline__ bool control_loop(const Params& P, int c, int tune, c
 // ------------------------------------------------------------------ the step kernel
 __global__ void __launch_bounds__(BK_CTA_THREADS, 1)
 pgbart_step_kernel(const Params P, const int tune, const StepArgs A, const int max_phases) {
-  const int mode = P.K > 1 ? BK_MODE_MULTI : (P.has_nan ? BK_MODE_MISSING : BK_MODE_PLAIN);   // (uniform over the grid)
+  const int mode = P.K > 1 ? BK_MODE_MULTI : ((P.has_nan || P.n_subset > 0) ? BK_MODE_MISSING : BK_MODE_PLAIN);   // (uniform over the grid)
   if ((int)blockIdx.x < P.C) {
     __shared__ KernelShared sh;
     if (threadIdx.x < BK_CTRL_THREADS) {
@@ -2283,6 +2342,7 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
   }
   for (size_t i = tid; i < (size_t)P.C * P.R * P.cnt_stride; i += nth) P.rowcnt[i] = 0u;
   for (size_t i = tid; i < (size_t)P.C * P.R * P.nb_stride; i += nth) P.coarse[i] = 0u;
+  for (size_t i = tid; i < (size_t)P.C * P.R * BK_MAX_SUBSET_COLS; i += nth) P.present[i] = 0u;
   for (size_t i = tid; i < (size_t)P.C * P.P * BK_ACC_STRIDE; i += nth) P.accL[i] = 0ull;
   for (size_t i = tid; i < (size_t)P.C * BK_ACC0_WORDS; i += nth) P.acc0[i] = 0ull;
   for (size_t i = tid; i < (size_t)P.C * P.m; i += nth) {
@@ -2304,12 +2364,26 @@ __global__ void pgbart_init_kernel(const Params P, const float init_sum, const f
   if (tid == 0) *P.abort_flag = 0;
   for (size_t i = tid; i < (size_t)P.C * (sizeof(ChainSync) / 4); i += nth) reinterpret_cast<unsigned int*>(P.sync)[i] = 0u;
 }
-__global__ void pgbart_nan_scan_kernel(const Params P) {   // one block per column
+// One block per column: does it hold missing values (bit 0 of col_nan)?  SubsetSplit columns: the categories present in the
+// column (col_cats) and whether every value is a category code (bit 1 of col_nan = some value is not).
+__global__ void pgbart_nan_scan_kernel(const Params P) {
   const float* x = P.X + (size_t)blockIdx.x * P.Npad;
-  int any = 0;
-  for (int i = threadIdx.x; i < P.N; i += blockDim.x) any |= (x[i] != x[i]) ? 1 : 0;
+  const bool subset = P.rules[blockIdx.x] == BK_RULE_SUBSET;
+  __shared__ unsigned s_cats;
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) { s_cats = 0u; s_bad = 0; }
+  __syncthreads();
+  int any = 0, bad = 0;
+  unsigned cats = 0u;
+  for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
+    const float xv = x[i];
+    if (xv != xv) any = 1;
+    else if (subset) { const int cd = bk_subset_code(xv); if (cd < 0) bad = 1; else cats |= 1u << cd; }
+  }
+  if (cats) atomicOr(&s_cats, cats);
+  if (bad) s_bad = 1;
   any = __syncthreads_or(any);
-  if (threadIdx.x == 0) P.col_nan[blockIdx.x] = any ? 1 : 0;
+  if (threadIdx.x == 0) { P.col_nan[blockIdx.x] = (any ? 1 : 0) | (s_bad ? 2 : 0); P.col_cats[blockIdx.x] = s_cats; }
 }
 __global__ void pgbart_init_cum_kernel(const Params P) {
   int c = blockIdx.x;
@@ -2378,7 +2452,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   size_t qr, qst, ids_tree, rows, rowcnt, coarse, wf_mean, wf_m2, parts, forest, forest_nn, ctl, accL, acc0, accK, acc_sd, alpha_vec, cum,
-      p_leaf, rules, col_nan, stats, trace, sync, abort_flag, split_prior, total;
+      p_leaf, rules, col_nan, subset_cols, subset_idx, col_cats, present, stats, trace, sync, abort_flag, split_prior, total;
   int Npad, ntiles, R, nb;
   size_t rec_stride;
 };
@@ -2397,6 +2471,15 @@ static int make_layout(const bk_settings* s, Layout* L) {
     if (s->likelihood == BK_LIK_NORMAL_HETERO && s->n_outputs != 2) { set_err("the heteroscedastic Normal likelihood takes two outputs"); return BK_ERR_ARG; }
   } else if (s->likelihood != BK_LIK_NORMAL && s->likelihood != BK_LIK_BERNOULLI_LOGIT) { set_err("likelihood not implemented on the device (no CPU fallback)"); return BK_ERR_UNSUPPORTED; }
   if (!s->p_leaf || !s->split_prior) { set_err("p_leaf and split_prior are required"); return BK_ERR_ARG; }
+  if (s->split_rules) {
+    int n_sub = 0;
+    for (int v = 0; v < s->n_cols; ++v) {
+      if (s->split_rules[v] < BK_RULE_CONTINUOUS || s->split_rules[v] > BK_RULE_SUBSET) { set_err("unknown split rule code"); return BK_ERR_ARG; }
+      n_sub += s->split_rules[v] == BK_RULE_SUBSET ? 1 : 0;
+    }
+    if (n_sub > BK_MAX_SUBSET_COLS) { set_err("at most 8 columns may use the SubsetSplit rule"); return BK_ERR_UNSUPPORTED; }
+    if (n_sub > 0 && s->n_outputs > 1) { set_err("SubsetSplit is not available together with shared-tree multi-output"); return BK_ERR_UNSUPPORTED; }
+  }
   const size_t C = (size_t)s->n_chains * (s->n_groups > 1 ? s->n_groups : 1), P = s->n_particles, m = s->n_trees, p = s->n_cols;
   const size_t K = s->n_outputs > 1 ? (size_t)s->n_outputs : 1;
   L->Npad = (int)align_up((size_t)s->n_rows, BK_WARP_TILE);
@@ -2427,6 +2510,10 @@ static int make_layout(const bk_settings* s, Layout* L) {
   CARVE(p_leaf, 256 * 8);
   CARVE(rules, p * 4);
   CARVE(col_nan, p * 4);
+  CARVE(subset_cols, BK_MAX_SUBSET_COLS * 4);
+  CARVE(subset_idx, p * 4);
+  CARVE(col_cats, p * 4);
+  CARVE(present, C * R * BK_MAX_SUBSET_COLS * 4);
   // abort flag | step records [stats [C] | vi [C][p]] x BK_MAX_STEPS_PER_LAUNCH: ONE D2H copy per launch brings the flag and the
   // records of the steps that ran
   CARVE(abort_flag, 256);
@@ -2504,6 +2591,8 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   P.accK = (unsigned long long*)(w + L.accK); P.acc_sd = (unsigned long long*)(w + L.acc_sd);
   P.alpha_vec = (double*)(w + L.alpha_vec); P.cum = (double*)(w + L.cum); P.p_leaf = (double*)(w + L.p_leaf);
   P.rules = (int32_t*)(w + L.rules); P.col_nan = (int32_t*)(w + L.col_nan); P.stats = (bk_step_stats*)(w + L.stats);
+  P.subset_cols = (int32_t*)(w + L.subset_cols); P.subset_idx = (int32_t*)(w + L.subset_idx);
+  P.col_cats = (uint32_t*)(w + L.col_cats); P.present = (uint32_t*)(w + L.present); P.n_subset = 0;
   P.vi = (int32_t*)(w + L.stats + (size_t)P.C * sizeof(bk_step_stats)); P.rec_stride = (int32_t)L.rec_stride; P.draws_out = nullptr; P.n_draw_peers = 0;
   P.trace = (bk_trace_rec*)(w + L.trace); P.sync = (ChainSync*)(w + L.sync); P.abort_flag = (int32_t*)(w + L.abort_flag);
   h->split_prior_dev = (double*)(w + L.split_prior);
@@ -2513,10 +2602,20 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
   CK(cudaMemcpyAsync(h->split_prior_dev, s->split_prior, (size_t)P.p * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   {
     int32_t* rules_h = (int32_t*)calloc((size_t)P.p, sizeof(int32_t));
+    int32_t* sidx_h = (int32_t*)malloc((size_t)P.p * sizeof(int32_t));
+    if (!rules_h || !sidx_h) { free(rules_h); free(sidx_h); set_err("out of host memory"); return BK_ERR_ARG; }
     if (s->split_rules) memcpy(rules_h, s->split_rules, (size_t)P.p * sizeof(int32_t));
+    int32_t scols_h[BK_MAX_SUBSET_COLS];
+    for (int i = 0; i < BK_MAX_SUBSET_COLS; ++i) scols_h[i] = 0;
+    for (int v = 0; v < P.p; ++v) {
+      sidx_h[v] = -1;
+      if (rules_h[v] == BK_RULE_SUBSET && P.n_subset < BK_MAX_SUBSET_COLS) { sidx_h[v] = P.n_subset; scols_h[P.n_subset++] = v; }
+    }
     cudaError_t e = cudaMemcpyAsync(P.rules, rules_h, (size_t)P.p * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(P.subset_idx, sidx_h, (size_t)P.p * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(P.subset_cols, scols_h, sizeof(scols_h), cudaMemcpyHostToDevice, h->stream);
     cudaStreamSynchronize(h->stream);
-    free(rules_h);
+    free(rules_h); free(sidx_h);
     CK(e);
   }
   // vi, stats and the abort flag are adjacent in the workspace: one D2H copy brings all three back
@@ -2572,9 +2671,11 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
     cudaError_t e = cudaMemcpyAsync(flags, P.col_nan, (size_t)P.p * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     P.has_nan = 0;
-    for (int v = 0; v < P.p && e == cudaSuccess; ++v) P.has_nan |= flags[v] ? 1 : 0;
+    int bad_codes = 0;
+    for (int v = 0; v < P.p && e == cudaSuccess; ++v) { P.has_nan |= (flags[v] & 1) ? 1 : 0; bad_codes |= (flags[v] & 2) ? 1 : 0; }
     free(flags);
     CK(e);
+    if (bad_codes) { set_err("a SubsetSplit column holds values that are not category codes (integers 0..23)"); return BK_ERR_ARG; }
   }
   pgbart_init_kernel<<<n_sm * 2, 512, 0, h->stream>>>(P, s->init_sum, s->leaf_sd_init, h->split_prior_dev);
   pgbart_init_cum_kernel<<<P.C, 32, 0, h->stream>>>(P);

@@ -219,6 +219,13 @@ struct Params {
   double* p_leaf;      // [256]
   int32_t* rules;      // [p]
   int32_t* col_nan;    // [p] 1 = the column holds missing values (NaN)
+  // SubsetSplit columns (bk_spec.h bk_subset_*; served by the same instantiation as the missing values)
+  int32_t n_subset;          // columns with the subset rule
+  int32_t* subset_cols;      // [BK_MAX_SUBSET_COLS] their column indices
+  int32_t* subset_idx;       // [p] index of a column among them, -1 otherwise
+  uint32_t* col_cats;        // [p] categories present in the whole column (the presence mask of a root node)
+  uint32_t* present;         // [C][R][BK_MAX_SUBSET_COLS] categories present among the members of the node the row's
+                             // per-tile counts belong to (the particle's next queue node), per subset column
   // Per-step outputs live in RECORDS [stats [C] | vi [C][p]], rec_stride bytes apart, one per step of a launch
   // (bk_run_launch runs up to BK_MAX_STEPS_PER_LAUNCH steps per launch); `vi` / `stats` point into record 0.
   int32_t* vi;         // [C][p] of record 0

@@ -66,7 +66,8 @@ __device__ __forceinline__ void bkp_tree_value(const bk_node* __restrict__ nodes
         return;
       }
       const float xv = x[nd.var];
-      const bool left = (rules && rules[nd.var] == BK_RULE_ONEHOT) ? (xv == nd.split) : (xv <= nd.split);
+      const int rule = rules ? rules[nd.var] : BK_RULE_CONTINUOUS;
+      const bool left = rule == BK_RULE_SUBSET ? (bk_subset_left(xv, nd.split) != 0) : (rule == BK_RULE_ONEHOT ? (xv == nd.split) : (xv <= nd.split));
       k = left ? nd.left : nd.left + 1;
     }
   } else {
@@ -99,7 +100,8 @@ __device__ __forceinline__ void bkp_tree_value(const bk_node* __restrict__ nodes
         sn[sp] = l; sw[sp] = BK_DMUL(w, wl); ++sp;
       } else {
         const float xv = x[nd.var];
-        const bool left = (rules && rules[nd.var] == BK_RULE_ONEHOT) ? (xv == nd.split) : (xv <= nd.split);
+        const int rule = rules ? rules[nd.var] : BK_RULE_CONTINUOUS;
+        const bool left = rule == BK_RULE_SUBSET ? (bk_subset_left(xv, nd.split) != 0) : (rule == BK_RULE_ONEHOT ? (xv == nd.split) : (xv <= nd.split));
         sn[sp] = left ? l : r; sw[sp] = w; ++sp;
       }
     }

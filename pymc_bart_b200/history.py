@@ -91,8 +91,10 @@ class ChainHistory:
 class DeviceForests:
     """All chains of an op on the device: nodes, version offsets, version table; one launch per prediction call."""
 
-    def __init__(self, chains: list, split_rules=None, device: int = 0):
+    def __init__(self, chains: list, split_rules=None, device: int = 0, subset_tables=None):
         import torch
+
+        self.subset_tables = subset_tables or {}   # SubsetSplit columns: value -> category code tables of the training data
 
         if not torch.cuda.is_available():
             raise RuntimeError("posterior prediction needs a CUDA device (no CPU fallback)")
@@ -135,6 +137,10 @@ class DeviceForests:
         torch = self.torch
         if isinstance(X, torch.Tensor):
             return X
+        if self.subset_tables:
+            from .settings import encode_subset_columns
+
+            X = encode_subset_columns(np.asarray(X), self.subset_tables)
         Xh = np.ascontiguousarray(np.asarray(X, dtype=np.float32))
         if Xh.ndim != 2:
             raise ValueError("X must be two-dimensional")

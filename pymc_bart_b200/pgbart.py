@@ -33,7 +33,7 @@ import numpy as np
 
 from . import _cabi
 from .core import DeviceSampler
-from .settings import make_settings
+from .settings import encode_subset_columns, make_settings, subset_category_tables
 from .utils import _encode_vi
 
 # Closed likelihood families of the device path.  The two multi-output ones are the models the reference's own tests
@@ -106,6 +106,10 @@ class PGBART:
             depth_offset=depth_offset, trace_capacity=trace_capacity, n_groups=groups, n_outputs=outputs)
         self.settings = make_settings(op.X, Yarr, chain_base=self.chain_base, device=0 if device is None else device,
                                       **self._settings_kw)
+        # SubsetSplit columns (docs/api_reference.rst:16): the device works on category codes; the tables that map a
+        # column's values to codes stay with the op, so that prediction on new data encodes it the same way
+        self.subset_tables = subset_category_tables(np.asarray(op.X), self.settings.split_rules)
+        (op if isinstance(op, type) else type(op)).subset_tables = self.subset_tables
         self.n_rows, self.n_cols, self.m = self.settings.n_rows, self.settings.n_cols, self.settings.n_trees
         self.core = None                # device state: created lazily, never pickled
         self._pub_thread = None
@@ -138,7 +142,7 @@ class PGBART:
         if self.core is None:
             dev = self._pick_device()
             self.settings = make_settings(self.op.X, self._Y, chain_base=self.chain_base, device=dev, **self._settings_kw)
-            self.core = DeviceSampler(self.settings, self.op.X, self._Y)
+            self.core = DeviceSampler(self.settings, encode_subset_columns(np.asarray(self.op.X), self.subset_tables), self._Y)
             self.core.enable_host_output(True)   # astep returns a host array every draw (the trace stores it)
             ahead = self.core.MAX_STEPS_PER_LAUNCH if self._serves_ahead(True) else (
                 self._steps_ahead(self.core) if self._serves_ahead(False) else 1)

@@ -19,7 +19,44 @@ SPLIT_RULE_CODES = {
     "ContinuousSplitRule": _cabi.BK_RULE_CONTINUOUS,
     "OneHotSplit": _cabi.BK_RULE_ONEHOT,           # tests/test_bart.py:144
     "OneHotSplitRule": _cabi.BK_RULE_ONEHOT,
+    "SubsetSplit": _cabi.BK_RULE_SUBSET,           # docs/api_reference.rst:16, pymc_bart/bart.py:103
+    "SubsetSplitRule": _cabi.BK_RULE_SUBSET,
 }
+
+
+def subset_category_tables(X: np.ndarray, rules: np.ndarray):
+    """Category tables of the SubsetSplit columns: {column: sorted unique non-missing values}.  The device works on
+    integer category CODES (the position of a value in its column's table, at most 24 of them: the set of categories
+    that go left travels as a 24-bit mask); the reference's rule takes arbitrary values (`np.isin(x, subset)`)."""
+    tables = {}
+    cols = np.nonzero(np.asarray(rules) == _cabi.BK_RULE_SUBSET)[0]
+    if cols.size > _cabi.BK_MAX_SUBSET_COLS:
+        raise NotImplementedError(f"at most {_cabi.BK_MAX_SUBSET_COLS} columns may use SubsetSplit")
+    for v in cols:
+        col = np.asarray(X[:, v], dtype=np.float64)
+        cats = np.unique(col[~np.isnan(col)])
+        if cats.size > _cabi.BK_SUBSET_MAX_CATS:
+            raise NotImplementedError(f"SubsetSplit column {int(v)} holds {cats.size} categories; the device handles up to "
+                                      f"{_cabi.BK_SUBSET_MAX_CATS}")
+        tables[int(v)] = cats
+    return tables
+
+
+def encode_subset_columns(X: np.ndarray, tables: dict) -> np.ndarray:
+    """X with every SubsetSplit column replaced by its category codes (float; NaN stays NaN; a value that is not in the
+    column's table — possible only in new data — gets the code 31, which belongs to no set and therefore goes right,
+    like `np.isin` of an unseen value)."""
+    if not tables:
+        return X
+    X = np.array(X, dtype=np.float64, copy=True)
+    for v, cats in tables.items():
+        col = X[:, v]
+        nan = np.isnan(col)
+        pos = np.searchsorted(cats, col)
+        pos_c = np.clip(pos, 0, max(0, cats.size - 1))
+        known = (~nan) & (cats.size > 0) & (cats[pos_c] == col)
+        X[:, v] = np.where(nan, np.nan, np.where(known, pos_c.astype(np.float64), 31.0))
+    return X
 
 
 def depth_prior_table(alpha: float, beta: float, depth_offset: int = 0) -> np.ndarray:
@@ -151,6 +188,8 @@ def make_settings(
             raise ValueError("the Categorical likelihood needs integer labels 0..k-1")
         if np.isnan(np.asarray(X, dtype=np.float64)).any():
             raise NotImplementedError("missing covariates are not supported together with shared-tree multi-output")
+        if np.any(rules == _cabi.BK_RULE_SUBSET):
+            raise NotImplementedError("SubsetSplit is not supported together with shared-tree multi-output")
         qshift = choose_qshift(max(16.0, float(np.abs(Y).max()), abs(ymean)))   # linear predictors: fixed-point range of at least +-64
     elif int(likelihood) in (_cabi.BK_LIK_NORMAL_HETERO, _cabi.BK_LIK_CATEGORICAL):
         raise ValueError("likelihoods 'normal_hetero' / 'categorical' need a multi-output BART variable (shape=(k, n))")

@@ -62,15 +62,17 @@ class PosteriorSampler:
     (``history.ChainHistory``: tree versions + a draw -> version table); a device store is built on first use, or once
     for all chains by ``_MultiChainSampler``."""
 
-    def __init__(self, history: ChainHistory, split_rules=None, device: int = 0):
+    def __init__(self, history: ChainHistory, split_rules=None, device: int = 0, subset_tables=None):
         self.history = history
         self.split_rules = split_rules
         self.device = device
+        self.subset_tables = subset_tables
         self._store = None
 
     @classmethod
-    def from_history(cls, batches, baseline_forest, m, n_outputs, split_rules=None, device: int = 0):
-        return cls(ChainHistory(batches, baseline_forest, m, n_outputs), split_rules=split_rules, device=device)
+    def from_history(cls, batches, baseline_forest, m, n_outputs, split_rules=None, device: int = 0, subset_tables=None):
+        return cls(ChainHistory(batches, baseline_forest, m, n_outputs), split_rules=split_rules, device=device,
+                   subset_tables=subset_tables)
 
     @property
     def n_draws(self) -> int:
@@ -96,7 +98,8 @@ class _MultiChainSampler:
         if not chain_samplers:
             raise ValueError("No posterior draws available yet: run pm.sample() first.")
         first = chain_samplers[0]
-        self._forests = DeviceForests([s.history for s in chain_samplers], split_rules=first.split_rules, device=first.device)
+        self._forests = DeviceForests([s.history for s in chain_samplers], split_rules=first.split_rules, device=first.device,
+                                      subset_tables=getattr(first, "subset_tables", None))
         self.n_chains = len(chain_samplers)
 
     @property
@@ -161,7 +164,7 @@ def _get_posterior_sampler(op) -> _MultiChainSampler:
         return cached[1]
     rules = _rule_codes(getattr(op, "split_rules", None))
     chains = [PosteriorSampler.from_history(list(batches), baseline_forest, op.m, op.n_outputs, split_rules=rules,
-                                            device=getattr(op, "device", 0))
+                                            device=getattr(op, "device", 0), subset_tables=getattr(op, "subset_tables", None))
               for baseline_forest, batches in op.all_trees]
     sampler = _MultiChainSampler(chains)
     _posterior_sampler_cache[id(op)] = (sig, sampler, op)

@@ -66,9 +66,9 @@ def test_settings_from_op_attributes():
     assert sb.leaf_sd_init == pytest.approx(1.0)           # 3/sqrt(m) for 0/1 data
     assert choose_qshift(30.0) == 22
     with pytest.raises(NotImplementedError):
-        make_settings(X, Y, split_rules=["SubsetSplit"] * 3)
-    r = make_settings(X, Y, split_rules=["ContinuousSplit", "OneHotSplit", "ContinuousSplit"]).split_rules
-    assert r.tolist() == [0, 1, 0]                          # tests/test_bart.py:143-145
+        make_settings(X, Y, split_rules=["NoSuchRule"] * 3)
+    r = make_settings(X, Y, split_rules=["ContinuousSplit", "OneHotSplit", "SubsetSplit"]).split_rules
+    assert r.tolist() == [0, 1, 2]                          # tests/test_bart.py:143-145; docs/api_reference.rst:16
     with pytest.raises(ValueError):
         make_settings(X, Y, alpha=1.5)
 
