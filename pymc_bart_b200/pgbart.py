@@ -17,6 +17,12 @@ State lives on the GPU (pymc_bart_b200.core.DeviceSampler); this class keeps the
 * when ``tune`` goes back to True after post-tuning draws (PyMC re-using one step object for the next chain,
   ``cores=1``), the sampler starts a fresh chain with the next chain index.
 
+Several BART variables in one model (tests/test_bart.py:167-241, ``pm.Normal("y", mu1 + mu2, sigma, observed=Y)``): one step
+object per variable, as in the reference; ``observed=`` is the likelihood's data and ``offset_names=`` the point entries
+that make up the rest of the location (the other BART variables), so that each step weighs its particles with
+``Normal(observed - offset | value, sigma)`` at the current point — what the reference's compiled ``datalogp`` does with
+the other variables as shared inputs.  Normal likelihood only.
+
 Extensions: ``chains=C`` batches C independent chains in one launch (the reference runs one step object per chain).
 ``lookahead=n`` (posterior phase only, and only when the likelihood parameters are FIXED — no ``sigma_name``, nobody
 assigns ``step.sigma`` between draws): ``astep`` is served from launches of ``n`` steps (``bk_run_launch``); the next launch
@@ -52,7 +58,8 @@ class PGBART:
 
     def __init__(self, vars=None, num_particles=10, batch=(0.1, 0.1), model=None, *, likelihood="normal", sigma=1.0,
                  chains=1, chain_base=0, seed=0, device=None, depth_offset=0, store_history=True, trace_capacity=0,
-                 sigma_name=None, sigma_transform=None, lookahead=1, tune_draws=None, **kwargs):
+                 sigma_name=None, sigma_transform=None, lookahead=1, tune_draws=None, observed=None, offset_names=None,
+                 **kwargs):
         if vars is None or len(vars) != 1:
             raise ValueError("PGBART takes exactly one BART variable: PGBART([rv], num_particles=...)")
         rv = vars[0]
@@ -82,6 +89,24 @@ class PGBART:
         Yarr = np.asarray(op.Y, dtype=np.float64)
         if groups > 1 and Yarr.ndim == 1:
             Yarr = np.broadcast_to(Yarr, (groups, Yarr.shape[0]))
+        # Several BART variables in one model (tests/test_bart.py:167-241: pm.Normal("y", mu1 + mu2, sigma, observed=Y)): the
+        # likelihood of this variable's step is Normal(observed - offset | value, sigma), offset = the other terms of the
+        # location at the current point.  `observed` is the likelihood's data (default: the Y handed to BART, which the
+        # reference uses for the initial value and the leaf scale only); `offset_names` are the point entries added up into
+        # the offset by step(point); set_offset() does the same for a caller that drives astep() itself.
+        self.offset_names = list(offset_names) if offset_names else None
+        self._observed = None if observed is None else np.asarray(observed, dtype=np.float64)
+        self._offset_dirty = False
+        if self._observed is not None or self.offset_names:
+            if likelihood != "normal":
+                raise NotImplementedError("observed= / offset_names= (this variable as one term of the location) are implemented for "
+                                          "likelihood='normal' only")
+            if self._observed is None:
+                self._observed = np.asarray(op.Y, dtype=np.float64)
+            if self._observed.shape != Yarr.shape:
+                self._observed = np.broadcast_to(self._observed, Yarr.shape)
+            if lookahead and int(lookahead) > 1 and self.offset_names:
+                raise ValueError("offset_names needs lookahead=1: the offset changes with every point")
         self.groups = groups
         self.outputs = outputs
         self.op = op
@@ -103,7 +128,8 @@ class PGBART:
         self._settings_kw = dict(
             m=op.m, alpha=op.alpha, beta=op.beta, split_prior=op.split_prior, split_rules=op.split_rules,
             num_particles=num_particles, batch=batch, n_chains=chains, seed=seed, likelihood=LIKELIHOODS[likelihood],
-            depth_offset=depth_offset, trace_capacity=trace_capacity, n_groups=groups, n_outputs=outputs)
+            depth_offset=depth_offset, trace_capacity=trace_capacity, n_groups=groups, n_outputs=outputs,
+            value_range=0.0 if self._observed is None else float(np.abs(self._observed).max()))
         self.settings = make_settings(op.X, Yarr, chain_base=self.chain_base, device=0 if device is None else device,
                                       **self._settings_kw)
         # SubsetSplit columns (docs/api_reference.rst:16): the device works on category codes; the tables that map a
@@ -112,6 +138,7 @@ class PGBART:
         (op if isinstance(op, type) else type(op)).subset_tables = self.subset_tables
         self.n_rows, self.n_cols, self.m = self.settings.n_rows, self.settings.n_cols, self.settings.n_trees
         self.core = None                # device state: created lazily, never pickled
+        self._offset = None
         self._pub_thread = None
         self._pub_queue = None
         self._reset_chain_state()
@@ -143,6 +170,8 @@ class PGBART:
             dev = self._pick_device()
             self.settings = make_settings(self.op.X, self._Y, chain_base=self.chain_base, device=dev, **self._settings_kw)
             self.core = DeviceSampler(self.settings, encode_subset_columns(np.asarray(self.op.X), self.subset_tables), self._Y)
+            if self._observed is not None:
+                self.set_offset(self._offset if getattr(self, "_offset", None) is not None else 0.0)
             self.core.enable_host_output(True)   # astep returns a host array every draw (the trace stores it)
             ahead = self.core.MAX_STEPS_PER_LAUNCH if self._serves_ahead(True) else (
                 self._steps_ahead(self.core) if self._serves_ahead(False) else 1)
@@ -153,6 +182,17 @@ class PGBART:
             if ahead > 1:
                 self._make_ring(self.core, ahead)     # (pinning host memory takes ~1 ms per MB: part of the set-up, not of a draw)
         return self.core
+
+    def set_offset(self, offset):
+        """The other terms of the likelihood's location at the current point (array [n] / [groups][n] or a number): the next
+        steps see the response `observed - offset`."""
+        if self._observed is None:
+            raise RuntimeError("set_offset needs observed= (or offset_names=) at construction")
+        self._offset = np.broadcast_to(np.asarray(offset, dtype=np.float64), self._observed.shape)
+        if self.core is not None:
+            if self._served or self._inflight:
+                raise RuntimeError("the offset cannot change while draws computed ahead are pending (use lookahead=1)")
+            self.core.set_response(self._observed - self._offset)
 
     def prepare(self):
         """Create the device state now (X/Y upload, workspace, pinned buffers) instead of at the first astep()."""
@@ -190,6 +230,10 @@ class PGBART:
         state["_inflight"] = []
         state["_ring"] = None
         return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.__dict__.setdefault("_offset", None)
 
     def next_chain(self):
         """Start a fresh chain on this step object (PyMC with cores=1 runs the chains one after the other)."""
@@ -373,6 +417,11 @@ class PGBART:
                                "by value-variable names (e.g. 'sigma_log__'): pass sigma_transform= to map it back")
             v = point[self.sigma_name]
             self.sigma = self.sigma_transform(v) if self.sigma_transform is not None else v
+        if self.offset_names:
+            missing = [n for n in self.offset_names if n not in point]
+            if missing:
+                raise KeyError(f"offset_names {missing} are not in the point (keys: {sorted(point)})")
+            self.set_offset(sum(np.asarray(point[n], dtype=np.float64) for n in self.offset_names))
         value, stats = self.astep(None)
         new_point = dict(point)
         new_point[self.vars[0].name] = value

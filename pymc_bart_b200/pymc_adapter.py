@@ -64,7 +64,8 @@ class PGBART(ArrayStepShared):
     generates_stats = True
     stats_dtypes_shapes = {"variable_inclusion": (object, []), "tune": (bool, [])}
 
-    def __init__(self, vars=None, num_particles=10, batch=(0.1, 0.1), model=None, likelihood=None, sigma=None, **kwargs):
+    def __init__(self, vars=None, num_particles=10, batch=(0.1, 0.1), model=None, likelihood=None, sigma=None, observed=None,
+                 offset=None, **kwargs):
         model = pm.modelcontext(model)
         if vars is None:
             vars = [v for v in model.free_RVs if getattr(getattr(getattr(v, "owner", None), "op", None), "name", None) == "BART"]
@@ -77,8 +78,14 @@ class PGBART(ArrayStepShared):
         fixed, key, back = _resolve_sigma(model, sigma)
         core_kw = {k: kwargs.pop(k) for k in ("seed", "device", "depth_offset", "chain_base", "store_history", "lookahead", "tune_draws")
                    if k in kwargs}     # (lookahead / tune_draws: draws served ahead, fixed likelihood parameters only — see pgbart.py)
+        # several BART variables in one likelihood (tests/test_bart.py:167-241): observed= the data, offset= the OTHER random
+        # variables of the location (their current values are read from the point before every step)
+        offset_names = None
+        if offset is not None:
+            offset_names = [o if isinstance(o, str) else model.rvs_to_values[o].name for o in (offset if isinstance(offset, (list, tuple)) else [offset])]
         self._core = _CorePGBART(vars, num_particles=num_particles, batch=batch, likelihood=likelihood,
-                                 sigma=1.0 if fixed is None else fixed, sigma_name=key, sigma_transform=back, **core_kw)
+                                 sigma=1.0 if fixed is None else fixed, sigma_name=key, sigma_transform=back,
+                                 observed=observed, offset_names=offset_names, **core_kw)
         self.tune = True
         super().__init__(value_vars, [], **kwargs)
 
@@ -89,6 +96,11 @@ class PGBART(ArrayStepShared):
                 raise KeyError(f"the likelihood scale {core.sigma_name!r} is not in the point (keys: {sorted(point)})")
             v = point[core.sigma_name]
             core.sigma = core.sigma_transform(v) if core.sigma_transform is not None else float(v)
+        if core.offset_names:
+            missing = [n for n in core.offset_names if n not in point]
+            if missing:
+                raise KeyError(f"offset variables {missing} are not in the point (keys: {sorted(point)})")
+            core.set_offset(sum(np.asarray(point[n], dtype=np.float64) for n in core.offset_names))
         return super().step(point)
 
     def astep(self, _):

@@ -148,6 +148,7 @@ def make_settings(
     trace_capacity: int = 0,
     n_groups: int = 1,
     n_outputs: int = 1,
+    value_range: float = 0.0,
 ) -> SamplerSettings:
     X = np.asarray(X)
     Y = np.asarray(Y, dtype=np.float64)
@@ -198,7 +199,8 @@ def make_settings(
             raise ValueError("the Bernoulli likelihood needs a 0/1 response")
         qshift = choose_qshift(16.0)    # the sum of trees is a logit: fixed-point range +-64
     else:
-        qshift = choose_qshift(max(float(np.abs(Y).max()), abs(ymean)))
+        # (value_range: largest magnitude of the likelihood's data when it is not the Y handed to BART — observed= of the step)
+        qshift = choose_qshift(max(float(np.abs(Y).max()), abs(ymean), float(value_range)))
     bt = max(1, int(m * batch[0]))
     bp = max(1, int(m * batch[1]))
     init_sum = np.float32(ymean)

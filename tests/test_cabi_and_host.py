@@ -194,8 +194,44 @@ class _FakeCore:
         nodes["value"] = 100 * self.calls + np.repeat(np.arange(self.C), T)
         return lo, np.ones((self.C, T), dtype=np.int32), nodes
 
+    def set_response(self, Y):
+        self.response = np.atleast_2d(np.array(Y, dtype=np.float64, copy=True))
+
     def close(self):
         self.closed = True
+
+
+def test_two_bart_variables_see_each_other_as_offsets(monkeypatch):
+    """tests/test_bart.py:167-241 (two BART variables in one Normal likelihood) on the host side: each step is handed
+    `observed - the other variable's current value` before it runs, from the point (step(point)) or by set_offset."""
+    import pymc_bart_b200.pgbart as pg
+
+    monkeypatch.setattr(pg, "DeviceSampler", _FakeCore)
+    _FakeCore.instances.clear()
+    rng = np.random.default_rng(1)
+    X1 = rng.normal(size=(30, 2)); X2 = rng.normal(size=(30, 3)); Yobs = rng.normal(size=30) * 7
+    mu1 = BART("mu1", X1, X1[:, 0], m=5); mu2 = BART("mu2", X2, X2[:, 1], m=5)
+    s1 = pg.PGBART([mu1], num_particles=5, observed=Yobs, offset_names=["mu2"])
+    s2 = pg.PGBART([mu2], num_particles=5, observed=Yobs, offset_names=["mu1"])
+    assert mu1.owner.op.all_trees is not mu2.owner.op.all_trees
+    point = {"mu1": np.full(30, X1[:, 0].mean()), "mu2": np.full(30, X2[:, 1].mean())}
+    point, st1 = s1.step(point)
+    np.testing.assert_allclose(s1.core.response[0], Yobs - X2[:, 1].mean())     # the response of step 1 = observed - mu2
+    point, st2 = s2.step(point)
+    np.testing.assert_allclose(s2.core.response[0], Yobs - point["mu1"])         # step 2 already sees the new mu1
+    assert point["mu1"].shape == (30,) and point["mu2"].shape == (30,) and st1[0]["tune"] and st2[0]["tune"]
+    # the fixed-point range covers the likelihood's data, not only the Y handed to BART
+    assert 2.0 ** s1.settings.qshift * 4 * np.abs(Yobs).max() <= 2 ** 29
+    s1.set_offset(np.ones(30)); np.testing.assert_allclose(s1.core.response[0], Yobs - 1.0)
+    with pytest.raises(KeyError):
+        s1.step({"mu1": point["mu1"]})
+    with pytest.raises(ValueError):
+        pg.PGBART([mu1], observed=Yobs, offset_names=["mu2"], lookahead=8)
+    with pytest.raises(NotImplementedError):
+        pg.PGBART([BART("b", X1, (Yobs > 0).astype(float), m=5)], likelihood="bernoulli", offset_names=["mu2"])
+    with pytest.raises(RuntimeError):
+        pg.PGBART([mu1]).set_offset(0.0)
+    s1.close(); s2.close()
 
 
 def test_pgbart_step_protocol_with_a_fake_core(monkeypatch):
