@@ -186,6 +186,14 @@ int bk_run_wait(bk_handle* h, int32_t* vi_counts_host, bk_step_stats* stats_host
 int bk_set_draw_peers(bk_handle* h, int n_peers, const void* const* peer_bases, const void* local_base);
 void* bk_stream(bk_handle* h);
 
+/* Several BART variables in one likelihood (tests/test_bart.py:167-241, `pm.Normal("y", mu1 + mu2, sigma, observed=Y)`): the
+ * step of one variable sees the response `observed - the other terms of the location` at the current point, which the
+ * reference gets by re-evaluating its compiled datalogp with the other variables as shared inputs.  bk_set_response
+ * replaces the response rows (y_host [n_groups][n_rows] float32, any host memory; staged through pinned memory, copied
+ * on the handle's stream before the next launch; no step may be in flight).  The kernels read y afresh in every step.
+ * Normal likelihood: the response is the data; other families would need the offset inside the linear predictor. */
+int bk_set_response(bk_handle* h, const float* y_host);
+
 /* Host copy of the value (tests/test_bart.py:121-123,197: the step returns the new value of the BART variable as a
  * host array).  With bk_set_host_output(h, 1) every step also copies the sum of trees into a pinned host buffer
  * [n_chains*n_groups][n_rows] behind the kernel on the handle's stream; bk_sum_trees_host returns that buffer (valid

@@ -123,7 +123,7 @@ assert NODE_DTYPE.itemsize == C.sizeof(BkNode) == 24
 # every symbol include/pgbart_b200.h declares
 EXPORTS = (
     "bk_abi_version", "bk_last_error", "bk_padded_rows", "bk_query_bytes", "bk_create", "bk_destroy",
-    "bk_step", "bk_step_launch", "bk_step_wait", "bk_run_launch", "bk_run_wait", "bk_set_draw_peers", "bk_stream", "bk_set_host_output", "bk_sum_trees_host", "bk_export_trees", "bk_read_trace", "bk_export_forest", "bk_export_leaf_ids",
+    "bk_step", "bk_step_launch", "bk_step_wait", "bk_run_launch", "bk_run_wait", "bk_set_draw_peers", "bk_stream", "bk_set_response", "bk_set_host_output", "bk_sum_trees_host", "bk_export_trees", "bk_read_trace", "bk_export_forest", "bk_export_leaf_ids",
     "bk_set_history", "bk_history_batch", "bk_history_values", "bk_history_batch_at", "bk_history_values_at", "bk_export_leaf_values", "bk_predict_history", "bk_pearson_r2",
 )
 
@@ -157,6 +157,7 @@ def load():
     lib.bk_stream.argtypes = [C.c_void_p]
     lib.bk_stream.restype = C.c_void_p
     lib.bk_set_draw_peers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.bk_set_response.argtypes = [C.c_void_p, C.c_void_p]
     lib.bk_set_host_output.argtypes = [C.c_void_p, C.c_int]
     lib.bk_sum_trees_host.argtypes = [C.c_void_p]
     lib.bk_sum_trees_host.restype = C.POINTER(C.c_float)

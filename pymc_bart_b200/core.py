@@ -66,19 +66,14 @@ class DeviceSampler:
     def set_response(self, Y):
         """Replace the response the steps see (rows [G][N]) — for models in which this BART variable is one term of the
         likelihood's location (several BART variables in one model, tests/test_bart.py:167-241: the step of one
-        variable sees `observed - the other terms` at the current point).  One small H2D copy from pinned memory on the
-        sampler's stream, ordered before the next launch; the kernels read `y` afresh in every step."""
-        torch = self.torch
-        Y2 = np.atleast_2d(np.asarray(Y, dtype=np.float32))
+        variable sees `observed - the other terms` at the current point).  One small H2D copy from the library's pinned
+        staging buffer on the sampler's stream, ordered before the next launch; the kernels read `y` afresh in every step."""
+        Y2 = np.ascontiguousarray(np.atleast_2d(np.asarray(Y, dtype=np.float32)))
         if Y2.shape != (self.G, self.N):
             raise ValueError(f"the response must have shape ({self.G}, {self.N})")
         if self._run_n:
             raise RuntimeError("set_response with launches in flight")
-        if getattr(self, "_y_stage", None) is None:
-            self._y_stage = torch.zeros((self.G, self.N), dtype=torch.float32).pin_memory()
-        self._y_stage.copy_(torch.from_numpy(np.ascontiguousarray(Y2)))
-        with torch.cuda.stream(self.stream()):
-            self.y_dev[:, : self.N].copy_(self._y_stage, non_blocking=True)
+        _cabi.check(self.lib.bk_set_response(self.h, Y2.ctypes.data), "bk_set_response")
 
     def close(self):
         if getattr(self, "h", None):

@@ -2446,6 +2446,7 @@ struct bk_handle_s {
   int poisoned;           // a step timed out: trees / sum of trees may be half rewritten, the handle refuses further steps
   int32_t* marker_host;
   int marker_count;
+  float* y_stage;         // pinned [G][n_rows] staging of bk_set_response
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -2698,6 +2699,7 @@ void bk_destroy(bk_handle* h) {
     if (h->done_ev[k]) cudaEventDestroy(h->done_ev[k]);
   }
   if (h->P.marker) cudaFree(h->P.marker);
+  if (h->y_stage) cudaFreeHost(h->y_stage);
   free(h->marker_host);
   delete h;
 }
@@ -2784,6 +2786,19 @@ int bk_set_draw_peers(bk_handle* h, int n_peers, const void* const* peer_bases, 
     h->P.draw_peer_delta[i] = (long long)((const char*)peer_bases[i] - (const char*)local_base);
   }
   h->P.n_draw_peers = n_peers;
+  return BK_OK;
+}
+
+int bk_set_response(bk_handle* h, const float* y_host) {
+  if (!h || !y_host) { set_err("bad argument"); return BK_ERR_ARG; }
+  if (h->n_launched != h->n_waited) { set_err("steps in flight"); return BK_ERR_STATE; }
+  ON_DEVICE(h->s.device);
+  const Params& P = h->P;
+  const size_t row = (size_t)P.N * sizeof(float);
+  if (!h->y_stage) CK(cudaMallocHost(&h->y_stage, (size_t)P.G * row));
+  else CK(cudaStreamSynchronize(h->stream));   // (an earlier copy out of the staging buffer has completed)
+  memcpy(h->y_stage, y_host, (size_t)P.G * row);
+  CK(cudaMemcpy2DAsync(const_cast<float*>(P.y), (size_t)P.Npad * sizeof(float), h->y_stage, row, row, (size_t)P.G, cudaMemcpyHostToDevice, h->stream));
   return BK_OK;
 }
 
