@@ -108,3 +108,30 @@ def test_registration_and_two_chains_through_one_step_object(fake_pymc, monkeypa
     fixed = ad.PGBART([mu], model=model, likelihood="normal", sigma=2.0)
     fixed.step({"mu": np.zeros(40)})
     assert fixed._core.core.last_sigma == 2.0
+
+
+def test_two_bart_variables_through_the_adapter(fake_pymc, monkeypatch):
+    """tests/test_bart.py:211-241 (`step=[PGBART([mu1], ...), PGBART([mu2], ...)]`, `pm.Normal("y", mu1 + mu2, sigma,
+    observed=Y)`): each step is told the data and the other term of the location as random variables; before it runs it
+    reads the other variable's current value from the point."""
+    import pymc_bart_b200 as pmb
+    import pymc_bart_b200.pgbart as pg
+
+    monkeypatch.setattr(pg, "DeviceSampler", _FakeCore)
+    import pymc_bart_b200.pymc_adapter as ad
+
+    rng = np.random.default_rng(2)
+    X1 = rng.normal(size=(30, 2)); X2 = rng.normal(size=(30, 2)); Y = rng.normal(size=30)
+    mu1 = pmb.BART("mu1", X1, X1[:, 0], m=3); mu2 = pmb.BART("mu2", X2, X2[:, 1], m=3)
+    model = types.SimpleNamespace(free_RVs=[mu1, mu2], rvs_to_values={mu1: _Var("mu1"), mu2: _Var("mu2")}, rvs_to_transforms={})
+    s1 = ad.PGBART([mu1], model=model, likelihood="normal", sigma=1.0, num_particles=5, observed=Y, offset=[mu2])
+    s2 = ad.PGBART([mu2], model=model, likelihood="normal", sigma=1.0, num_particles=5, observed=Y, offset=mu1)
+    assert s1._core.offset_names == ["mu2"] and s2._core.offset_names == ["mu1"]
+    point = {"mu1": np.zeros(30), "mu2": np.ones(30)}
+    point, _ = s1.step(point)
+    np.testing.assert_allclose(s1._core.core.response[0], Y - 1.0)
+    point, _ = s2.step(point)
+    np.testing.assert_allclose(s2._core.core.response[0], Y - point["mu1"])
+    assert mu1.owner.op.all_trees is not mu2.owner.op.all_trees
+    with pytest.raises(KeyError):
+        s1.step({"mu1": np.zeros(30)})
