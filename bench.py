@@ -6,8 +6,11 @@
 One "step" = one PGBART step (astep) of every chain batched on a GPU = one draw per chain.
 The headline workload is BASELINE.json configs[1] (C2: N=100k, p=10, m=50, 40 particles, 4 chains on one B200).
 The same line carries a SECOND measured workload under ``config.c5``: BASELINE.json configs[4] (C5: N=1M, p=50,
-m=200, 60 particles, one chain per GPU = the "8 chains sharded across 8xB200" shard), the HBM-bound case, so that
-the driver's 1/2/4/8-GPU runs report both N=1e5 and N=1e6 (north_star).
+m=200, 60 particles, 8 chains), the large case, so that the driver's 1/2/4/8-GPU runs report both N=1e5 and N=1e6
+(north_star).  Like C2's four chains, the eight chains of C5 are batched on every GPU (weak scaling: 8 chains per GPU at
+every N): one chain's control phases run while the workers stream the other chains' epochs, which a single chain per GPU
+cannot do (1 -> 8 chains per GPU: 197 -> 337 draws/s on one B200).  ``config.c5.one_chain_per_gpu`` keeps the
+device-timed figure of the "8 chains sharded one per GPU" reading beside it.
 With --gpus N (launched by torchrun) every rank runs its own chains (weak scaling: chains are independent, no
 data-path collective); the run's single collective — one NCCL all-gather of the posterior draws, as
 pymc_bart_b200.sampling.gather_posterior does it — is inside the timed region.
@@ -33,7 +36,7 @@ CONFIGS = {
     "C2": (100_000, 10, 50, 40, 4, 2, 0, 1),
     "C3": (50_000, 20, 100, 40, 4, 3, 1, 1),
     "C4": (50_000, 15, 50, 40, 4, 4, 0, 3),
-    "C5": (1_000_000, 50, 200, 60, 1, 5, 0, 1),   # 8 chains = one per GPU on the 8xB200 box
+    "C5": (1_000_000, 50, 200, 60, 8, 5, 0, 1),   # BASELINE's 8 chains, batched on every GPU (see the module docstring)
 }
 
 
@@ -181,8 +184,10 @@ def run_reference(args, cfg):
                       f"groups on {threads} host threads (ctypes releases the GIL)"}
     if args.config == "C2" and not args.no_c5:
         c5 = CONFIGS["C5"]
-        n5 = c5[4] * max(1, args.gpus)
-        th5 = max(1, min(os.cpu_count() or 1, n5))
+        # bounded sample: one chain per host thread, at most 16 of the workload's chains (a C5 draw takes the oracle ~10 s and a
+        # chain ~350 MB of host memory)
+        n5 = max(1, min(c5[4] * max(1, args.gpus), os.cpu_count() or 1, 16))
+        th5 = n5
         v5, dt5, tpd5 = oracle_sample("C5", c5, n5, 2, 0, th5)
         config["c5"] = {"workload": workload_name("C5", c5, tpd5), "value": v5, "unit": "draws/s", "ms_per_step": 1e3 * dt5 / 2,
                         "cpu_baseline": {"value": v5, "unit": "draws/s", "cores": th5, "kind": "port",
@@ -199,7 +204,7 @@ def run_reference(args, cfg):
 
 
 # ---------------------------------------------------------------------------------------------- our arm (B200)
-def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src, cpu_baseline=True):
+def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src, cpu_baseline=True, chains_override=0):
     """One workload on this rank's GPU: device-timed K steps (+ the all-gather of the draws when world > 1), then the
     end-to-end leg through PGBART.astep with host buffers.  Returns the dict of measurements (rank 0: complete)."""
     import torch
@@ -209,6 +214,8 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     from pymc_bart_b200.settings import make_settings
 
     cfg = CONFIGS[name]
+    if chains_override:
+        cfg = cfg[:4] + (int(chains_override),) + cfg[5:]
     N, p, m, P, chains, seed, lik, groups = cfg
     X, y = friedman(N, p, seed, lik, groups)
     s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=chains, chain_base=rank * chains, device=local,
@@ -451,6 +458,8 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
     try:   # DRAM bytes per launch of the same command under `ncu --set full` (profiles/, committed)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name, {})
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        if int(tj.get("chains_per_gpu", chains)) != chains:   # captured with another number of chains per GPU: not this workload's traffic
+            traffic, traffic_src = None, f"no capture at {chains} chains per GPU ({traffic_src})"
         cap_spl = float(tj.get("steps_per_launch", 1))
         if traffic is not None and abs(cap_spl - steps_per_launch_mean) > 1e-9:   # captured at another launch size: per step x steps
             traffic = traffic / cap_spl * steps_per_launch_mean
@@ -500,6 +509,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="C2")
+    ap.add_argument("--chains", type=int, default=0, help="override the chains per GPU of --config (experiments; 0 = the config's own)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-c5", action="store_true", help="skip the second workload (config.c5)")
     ap.add_argument("--c5-steps", type=int, default=30)
@@ -513,6 +523,8 @@ def main():
     ap.add_argument("--lookahead", type=int, default=16, help="PGBART(lookahead=) of the e2e leg (1 = one launch per astep call)")
     ap.add_argument("--steps-per-launch", type=int, default=16, help="steps of every chain per kernel launch in the device-timed leg (1..16)")
     args = ap.parse_args()
+    if args.chains > 0:
+        c = list(CONFIGS[args.config]); c[4] = int(args.chains); CONFIGS[args.config] = tuple(c)
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         run_reference(args, cfg)
@@ -541,6 +553,12 @@ def main():
     c5_m = None
     if args.config == "C2" and not args.no_c5 and not args.profile_only:
         c5_m = measure("C5", max(25, args.c5_steps), 5, args, rank, world, local, clocks, peak, peak_src, cpu_baseline=False)
+        # the "8 chains sharded one per GPU" reading of the same config, device-timed only
+        one_args = argparse.Namespace(**vars(args)); one_args.profile_only = True
+        c5_one = measure("C5", max(25, args.c5_steps), 5, one_args, rank, world, local, clocks, peak, peak_src, cpu_baseline=False,
+                         chains_override=1)
+        if rank == 0:
+            c5_m["one_chain_per_gpu"] = {k: c5_one[k] for k in ("value", "unit", "ms_per_step", "steps", "steps_per_launch", "in_kernel_us")}
     clk = clocks.stop()
     if rank == 0:
         if args.profile_only:

@@ -1372,6 +1372,51 @@ __device__ __forceinline__ unsigned long long take_stat(unsigned* L, int k) {
 // MULTI: shared-tree multi-output (Params::K > 1): per job the sums of q(sum_trees[j]) of BOTH children for every
 // output j go to `acck` (no parent statistics are kept per output); no Gaussian residual statistics (the weight comes
 // from the LL epoch).
+// ------------------------------------------------------------------ staged loads of the ROUND epoch (cp.async)
+// A (tile, job) unit is a dependent chain: leaf ids + column tile (an L2 / HBM round trip), then ~250 instructions of
+// routing and sums.  With 32 resident warps per SM at 64 registers each, the loads of job j+1 cannot live in registers
+// beside the work of job j (tried: the spills cost more than the latency), so they go to SHARED memory instead: while a
+// warp works on job j, the leaf ids and the column tile of job j+1 are in flight as asynchronous copies
+// (cp.async = LDGSTS) into a slot the same lane reads back itself — every lane copies and consumes its own 40 bytes,
+// so no cross-lane synchronisation is needed, only cp.async.wait_group.  Two slots per lane (ping-pong): the slot being
+// refilled was consumed a whole job earlier.  Per warp 2 x 1280 B, per group of 8 warps 20 KB.  Worker CTAs have that
+// memory idle: groups 0-1 use the static area that holds the control state in control CTAs, groups 2-3 the tail of the
+// dynamic area.  Leaf ids are copied with .ca (8-byte copies exist only in that form): like the residual tiles they are
+// read through an L1 that the epoch's acquire poll has just invalidated, and a row read in an epoch is never written
+// in it; the column tile bypasses L1 (.cg).
+// MEASURED, NOT ENABLED: compiled only with -DBK_STAGE.  Bit-identical results (40 parity tests), but no gain on a B200:
+// C2 6283 -> 6136 draws/s (-2.3 %), C5 at 8 chains per GPU 341 -> 344 (+0.9 %) (profiles/r2_ab_stage_cpasync.txt).  With
+// 8 warps per scheduler issuing ~52 % of the cycles, one job's 250 instructions already take longer than the load
+// latency they would hide; the units are bound by their instruction count, not by the round trip.
+#define BK_STAGE_SLOT_BYTES 1280                                  // [32 lanes x 16 B x0][32 x 16 B x1][32 x 8 B ids]
+#define BK_STAGE_WARP_BYTES (2 * BK_STAGE_SLOT_BYTES)
+#define BK_STAGE_GROUP_BYTES ((BK_GROUP_THREADS / 32) * BK_STAGE_WARP_BYTES)
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// start the copies of one job's inputs into `slot` (this lane's part): leaf ids unless the source is a stump, the
+// column tile for a partition of a dense node (sparse nodes load it only in lanes that hold members, after the ids)
+__device__ __forceinline__ void stage_issue(unsigned char* slot, const Job* __restrict__ jb, const uint8_t* rows_c, const float* x_b,
+                                            unsigned uNpad, int lane) {
+  const int4* jp = reinterpret_cast<const int4*>(jb);
+  const int4 j0 = jp[0];
+  const int kind = j0.x, src_row = j0.z;
+  if (kind == BK_JOB_PARTITION || kind == BK_JOB_COUNT) {
+    if (src_row != BK_ROW_VIRTUAL) cp_async_8(slot + 1024 + lane * 8, rows_c + (unsigned long long)(unsigned)src_row * uNpad);
+    if (kind == BK_JOB_PARTITION && jp[2].z == 0) {
+      const float* xp = x_b + (unsigned long long)(unsigned)jp[1].y * uNpad;
+      cp_async_16(slot + lane * 16, xp);
+      cp_async_16(slot + 512 + lane * 16, xp + 4);
+    }
+  }
+  cp_async_commit();
+}
+
 // SubsetSplit (feature instantiation only).  subset_left: bk_subset_left with the node's set already decoded.
 __device__ __forceinline__ bool subset_left(float x, unsigned set) {
   const int cd = bk_subset_code(x);
@@ -1402,10 +1447,19 @@ __device__ __forceinline__ void note_present(const Params& P, unsigned uCR, int 
 
 template <bool MISSING, bool MULTI>
 __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int job_lo, int job_hi, const Job* __restrict__ sjobs,
-                                           unsigned* __restrict__ sacc, unsigned (*__restrict__ acck)[BK_MAX_OUTPUTS][4]) {
+                                           unsigned* __restrict__ sacc, unsigned (*__restrict__ acck)[BK_MAX_OUTPUTS][4],
+                                           unsigned char* __restrict__ stage) {
   const int lane = threadIdx.x & 31;
   const size_t base = (size_t)tile * BK_WARP_TILE + (size_t)lane * BK_ROWS_PER_LANE;
   const bool gauss = !MULTI && P.lik == BK_LIK_NORMAL;
+#ifdef BK_STAGE
+  // the first job's inputs start before the residual tiles are asked for (one round trip for both)
+  {
+    const unsigned uNp = (unsigned)P.Npad;
+    stage_issue(stage, &sjobs[job_lo], P.rows + (unsigned long long)((unsigned)c * (unsigned)P.R) * uNp + base, P.X + base, uNp, lane);
+  }
+  int cur = 0;
+#endif
   int q_r[8], q_s[8];
   if (MULTI) {
 #pragma unroll
@@ -1443,10 +1497,30 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
     const int next_node = j2.x, rule = j2.y, sparse = j2.z;
     const bool has_nan = MISSING && j2.w != 0;
     unsigned w0 = vw0, w1 = vw1;
+#ifdef BK_STAGE
+    // this job's inputs were copied into the current slot while the previous job was worked on; the next job's go
+    // into the other slot now
+    float4 xs0 = make_float4(0.f, 0.f, 0.f, 0.f), xs1 = xs0;
+    {
+      cp_async_wait_all();
+      const unsigned char* sl = stage + cur * BK_STAGE_SLOT_BYTES;
+      if ((kind == BK_JOB_PARTITION || kind == BK_JOB_COUNT) && src_row != BK_ROW_VIRTUAL) {
+        const uint2 v = *reinterpret_cast<const uint2*>(sl + 1024 + lane * 8);
+        w0 = v.x; w1 = v.y;
+      }
+      if (kind == BK_JOB_PARTITION && !sparse) {
+        xs0 = *reinterpret_cast<const float4*>(sl + lane * 16);
+        xs1 = *reinterpret_cast<const float4*>(sl + 512 + lane * 16);
+      }
+      cur ^= 1;
+      if (ji + 1 < job_hi) stage_issue(stage + cur * BK_STAGE_SLOT_BYTES, &sjobs[ji + 1], rows_c, x_b, uNpad, lane);
+    }
+#else
     if (src_row != BK_ROW_VIRTUAL) {
       const uint2 v = __ldcg(reinterpret_cast<const uint2*>(rows_c + (unsigned long long)(unsigned)src_row * uNpad));
       w0 = v.x; w1 = v.y;
     }
+#endif
     const unsigned next4 = (unsigned)next_node * 0x01010101u;
     if (kind == BK_JOB_PARTITION) {
       const unsigned node4 = (unsigned)node * 0x01010101u;
@@ -1456,8 +1530,14 @@ __device__ __forceinline__ void round_unit(const Params& P, int c, int tile, int
       // per job); sparse nodes (few members) keep it dependent on the ids to save the bytes
       float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
       if (!sparse || (mem0 | mem1)) {
-        const float4* xp = reinterpret_cast<const float4*>(x_b + (unsigned long long)(unsigned)var * uNpad);
-        x0 = __ldg(xp); x1 = __ldg(xp + 1);
+#ifdef BK_STAGE
+        if (!sparse) { x0 = xs0; x1 = xs1; }
+        else
+#endif
+        {
+          const float4* xp = reinterpret_cast<const float4*>(x_b + (unsigned long long)(unsigned)var * uNpad);
+          x0 = __ldg(xp); x1 = __ldg(xp + 1);
+        }
         if (MISSING && rule == BK_RULE_SUBSET) {   // the node's set of left-going categories travels as the float of its bit mask
           const unsigned set = (unsigned)split;
           if (subset_left(x0.x, set)) lb0 |= 0x000000FFu; if (subset_left(x0.y, set)) lb0 |= 0x0000FF00u;
@@ -2049,8 +2129,9 @@ __device__ __forceinline__ void cold_start_prefetch(const Params& P, const int t
 }
 
 template <int MODE>
-__device__ __forceinline__ void worker_loop(const Params& P, GroupShared& sh, const int g, const unsigned epoch_base) {
+__device__ __forceinline__ void worker_loop(const Params& P, GroupShared& sh, const int g, const unsigned epoch_base, unsigned char* stage_group) {
   const int tid = (int)threadIdx.x - g * BK_GROUP_THREADS, warp = tid >> 5;
+  unsigned char* const stage = stage_group + warp * BK_STAGE_WARP_BYTES;   // this warp's two staging slots (see stage_issue)
   const int W = gridDim.x - P.C, w = blockIdx.x - P.C;
   const int c_first = P.C >= BK_NGROUPS ? g : g % P.C, c_step = P.C >= BK_NGROUPS ? BK_NGROUPS : P.C;
   const int my_rank = P.C >= BK_NGROUPS ? 0 : g / P.C;      // index of this group among the servers of its chain
@@ -2158,9 +2239,9 @@ __device__ __forceinline__ void worker_loop(const Params& P, GroupShared& sh, co
         const unsigned tile = lo / (unsigned)wk.njobs, j0 = lo - tile * (unsigned)wk.njobs;
         const unsigned seg = (unsigned)wk.njobs - j0 < hi - lo ? (unsigned)wk.njobs - j0 : hi - lo;
         if (wk.cmd == BK_CMD_ROUND) {
-          if (BK_IS_MULTI(P)) round_unit<false, true>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.acck);
-          else if (BK_MISSING_ENABLED) round_unit<true, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr);
-          else round_unit<false, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr);
+          if (BK_IS_MULTI(P)) round_unit<false, true>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.acck, stage);
+          else if (BK_MISSING_ENABLED) round_unit<true, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr, stage);
+          else round_unit<false, false>(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, nullptr, stage);
         }
         else if (BK_IS_MULTI(P)) ll_unit_multi(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc, sh.u.job_vals);
         else ll_unit(P, wk.chain, (int)tile, (int)j0, (int)(j0 + seg), jobs, sh.acc);
@@ -2305,8 +2386,8 @@ __device__ __forceinline__ bool control_loop(const Params& P, int c, int tune, c
 __global__ void __launch_bounds__(BK_CTA_THREADS, 1)
 pgbart_step_kernel(const Params P, const int tune, const StepArgs A, const int max_phases) {
   const int mode = P.K > 1 ? BK_MODE_MULTI : ((P.has_nan || P.n_subset > 0) ? BK_MODE_MISSING : BK_MODE_PLAIN);   // (uniform over the grid)
+  __shared__ KernelShared sh;   // control CTAs: the chain's control state; worker CTAs: staging slots of groups 0-1
   if ((int)blockIdx.x < P.C) {
-    __shared__ KernelShared sh;
     if (threadIdx.x < BK_CTRL_THREADS) {
       if (mode == BK_MODE_PLAIN) control_loop<BK_MODE_PLAIN>(P, blockIdx.x, tune, A, max_phases, sh.ctl);
       else if (mode == BK_MODE_MISSING) control_loop<BK_MODE_MISSING>(P, blockIdx.x, tune, A, max_phases, sh.ctl);
@@ -2319,9 +2400,16 @@ pgbart_step_kernel(const Params P, const int tune, const StepArgs A, const int m
   cold_start_prefetch(P, tune);
 #endif
   GroupShared& gs = reinterpret_cast<GroupShared*>(bk_dyn_smem)[g];
-  if (mode == BK_MODE_PLAIN) worker_loop<BK_MODE_PLAIN>(P, gs, g, A.epoch_base);
-  else if (mode == BK_MODE_MISSING) worker_loop<BK_MODE_MISSING>(P, gs, g, A.epoch_base);
-  else worker_loop<BK_MODE_MULTI>(P, gs, g, A.epoch_base);
+  static_assert(BK_NGROUPS == 4, "staging regions are laid out for four worker groups");
+  static_assert(sizeof(KernelShared) >= 2 * BK_STAGE_GROUP_BYTES, "groups 0-1 stage in the static control area");
+  static_assert(sizeof(GroupShared) % 16 == 0, "the dynamic staging tail must stay 16-byte aligned");
+  static_assert(sizeof(GroupShared) * BK_NGROUPS + 2 * BK_STAGE_GROUP_BYTES + sizeof(KernelShared) + 2048 <= 227 * 1024,
+                "worker groups + staging tail + static area must fit the 227 KB of shared memory of an SM");
+  unsigned char* const stage_group = g < 2 ? reinterpret_cast<unsigned char*>(&sh) + g * BK_STAGE_GROUP_BYTES
+                                           : bk_dyn_smem + sizeof(GroupShared) * BK_NGROUPS + (g - 2) * BK_STAGE_GROUP_BYTES;
+  if (mode == BK_MODE_PLAIN) worker_loop<BK_MODE_PLAIN>(P, gs, g, A.epoch_base, stage_group);
+  else if (mode == BK_MODE_MISSING) worker_loop<BK_MODE_MISSING>(P, gs, g, A.epoch_base, stage_group);
+  else worker_loop<BK_MODE_MULTI>(P, gs, g, A.epoch_base, stage_group);
 }
 
 // ------------------------------------------------------------------ init kernel
@@ -2647,7 +2735,12 @@ static int create_body(bk_handle* h, const bk_settings* s, const Layout& L, cons
     if (F < 3) { set_err("too many particles for the shared-memory particle store"); return BK_ERR_ARG; }
     P.fastF = F; P.fast_stride = (int)sizeof(PHdr) + F * (int)sizeof(DNode);
     h->dyn_smem = (size_t)2 * P.P * P.fast_stride;
-    if (h->dyn_smem < sizeof(GroupShared) * BK_NGROUPS) h->dyn_smem = sizeof(GroupShared) * BK_NGROUPS;   // worker CTAs carve their groups out of it
+    // worker CTAs carve their groups out of it (-DBK_STAGE: then the staging slots of groups 2-3, round_unit's cp.async ping-pong)
+#ifdef BK_STAGE
+    if (h->dyn_smem < sizeof(GroupShared) * BK_NGROUPS + 2 * BK_STAGE_GROUP_BYTES) h->dyn_smem = sizeof(GroupShared) * BK_NGROUPS + 2 * BK_STAGE_GROUP_BYTES;
+#else
+    if (h->dyn_smem < sizeof(GroupShared) * BK_NGROUPS) h->dyn_smem = sizeof(GroupShared) * BK_NGROUPS;
+#endif
     CK(cudaFuncSetAttribute(pgbart_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
   }
   h->grid = n_sm;  // one persistent CTA per SM (148 on B200): chains control CTAs + workers
