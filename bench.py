@@ -486,7 +486,11 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "frac_dram_traffic": (traffic / (ms_kernel / 1e3) / 1e9 / peak) if traffic else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                     "kernel": "pgbart_step_kernel", "kernel_ms": ms_kernel, "steps_per_launch": steps_per_launch_mean},
+                     "kernel": "pgbart_step_kernel", "kernel_ms": ms_kernel, "steps_per_launch": steps_per_launch_mean,
+                     "note": "achieved / frac use SURVEY 8(d)'s ALGORITHMIC bytes (every grow event is charged the column, both "
+                             "leaf-id rows and the two residual tiles: 14 N); the kernel loads the residual tiles once per row tile "
+                             "and finds much of the rest in L1/L2, so frac can exceed 1 when several chains overlap — "
+                             "frac_dram_traffic (ncu DRAM bytes per launch / launch time / peak) is the hardware figure"},
     })
     if cpu_baseline:
         # ---------------- CPU baseline: the oracle on the host cores, bounded sample of the same workload
