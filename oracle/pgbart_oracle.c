@@ -18,6 +18,8 @@
  *   - split rules "ContinuousSplit"/"OneHotSplit" tests/test_bart.py:143-145; "SubsetSplit" docs/api_reference.rst:16
  *   - variable_inclusion counts .......... pymc_bart/utils.py:1387-1398, tests/test_bart.py:59-64
  *   - VI dominance / prediction self-consistency: tests/test_bart.py:44-64, tests/test_utils.py:24-32
+ * What does pin it: oracle/model_float.py, an independent float64 restatement without bk_spec.h, takes the same decisions
+ * and agrees within 1e-5 on every value (tests/test_independent_model.py).
  * The only exact fixture the reference has for this path — the varint/base64 codec
  * round trip (tests/test_utils.py:101-113) — is checked in tests/test_codec.py.
  *

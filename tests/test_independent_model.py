@@ -1,0 +1,151 @@
+"""The C oracle against an independent float64 statement of the same algorithm (oracle/model_float.py) that uses none of
+include/bk_spec.h: no fixed-point sums, numpy's exp / log / cos, textbook systematic resampling, its own Philox.
+
+north_star's bar, applied to the oracle itself: identical tree topologies and leaf-index assignments for a fixed RNG stream,
+leaf values and log-weights within 1e-5.  Every decision the sampler takes — popped node, split variable, split value,
+child sizes, resampling ancestors, the selected particle, inclusion counts, every row's leaf id — must be THE SAME in both;
+what may differ is rounding (float32 polynomial kernels and 2^-22 fixed point on one side, float64 libm on the other).
+This is the check that a mistake in the shared header would not survive ("what's weak" 3)."""
+import numpy as np
+import pytest
+
+from helpers import friedman
+from oracle.model_float import FloatModelChain, philox4x32_10
+from oracle.oracle_py import OracleChain
+from pymc_bart_b200.settings import make_settings
+
+INT_FIELDS = ("kind", "tree", "round", "particle", "node", "var", "ancestor")
+
+
+LIK_NAMES = {0: "normal", 1: "bernoulli", 2: "normal_hetero", 3: "categorical"}
+
+
+def compare(N, p, m, P, draws, seed, sigma=1.0, depth_offset=0, X=None, y=None, rules=None, split_prior=None, likelihood=0, n_outputs=1):
+    if X is None:
+        X, y, _ = friedman(N, p, seed, kind="bernoulli" if likelihood else "normal")
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=depth_offset, trace_capacity=60000, split_rules=rules,
+                      split_prior=split_prior, likelihood=likelihood, n_outputs=n_outputs)
+    orc = OracleChain(s, X.T.copy(), y)
+    mod = FloatModelChain(X, y, m, P, s.p_leaf, seed=s.seed, split_prior=s.split_prior, split_rules=s.split_rules,
+                          likelihood=LIK_NAMES[likelihood], n_outputs=n_outputs)
+    n_grow = 0
+    for d in range(draws):
+        tune = d < draws // 2
+        vi_o, st_o = orc.step(tune, sigma)
+        vi_m, grow_m = mod.step(tune, sigma)
+        tr = orc.trace()
+        assert len(tr) == len(mod.trace), f"draw {d}: {len(tr)} vs {len(mod.trace)} records"
+        for a, b in zip(tr, mod.trace):
+            ctx = f"draw {d}: oracle {a} model {b}"
+            for k in INT_FIELDS:
+                assert int(a[k]) == int(b[k]), ctx
+            if b["kind"] == 1:
+                assert int(a["n_left"]) == b["n_left"] and int(a["n_right"]) == b["n_right"], ctx
+                assert float(a["split"]) == b["split"], ctx                                  # a value of X / a set of categories: exact
+                assert abs(float(a["val_left"]) - b["val_left"]) < 1e-5 and abs(float(a["val_right"]) - b["val_right"]) < 1e-5, ctx
+            else:
+                assert abs(float(a["aux"]) - b["aux"]) < 1e-5 * max(1.0, abs(b["aux"])), ctx    # running leaf sd after the commit
+            # (heteroscedastic Normal: ((y - f0) / |f1|)^2 in float32 is ill-conditioned for small |f1| — rows near the +-512
+            # saturation carry 2e-7 * 500 each — so its log-weights get 1e-4; every decision must still be the same)
+            # families whose weights are integer sums of per-row terms rounded to 2^-20: N half-steps of absolute slack
+            tol = (1e-4 if likelihood == 2 else 1e-5) * max(1.0, abs(b["log_w"])) + (N * 2.0 ** -20 if likelihood else 0.0)
+            assert abs(float(a["log_w"]) - b["log_w"]) < tol, ctx
+        assert np.array_equal(vi_o, vi_m) and st_o.grow_events == grow_m
+        n_grow += grow_m
+    ids = orc.leaf_ids()
+    nodes, nn = orc.forest()
+    for t in range(m):
+        assert np.array_equal(ids[t], mod.forest[t].ids)
+        assert nn[t] == len(mod.forest[t].nodes)
+        assert [int(v) for v in nodes[t]["var"][: nn[t]]] == [nd.var for nd in mod.forest[t].nodes]
+    np.testing.assert_allclose(np.atleast_2d(orc.sum_trees()), mod.st, rtol=0, atol=5e-5)
+    if n_outputs > 1:      # every output's leaf values, not only the first one the trace carries
+        lv = orc.leaf_values()
+        for t in range(m):
+            for k, nd in enumerate(mod.forest[t].nodes):
+                if nd.var < 0:
+                    np.testing.assert_allclose(lv[t, k], nd.value, rtol=0, atol=1e-5)
+    return n_grow
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors: the model's Philox is its own implementation."""
+    assert ["%08x" % v for v in philox4x32_10(0, 0, 0, 0, 0, 0)] == ["6627e8d5", "e169c58d", "bc57ac4c", "9b00dbd8"]
+    assert ["%08x" % v for v in philox4x32_10(0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)] == [
+        "408f276d", "41c83b0e", "a20bc7c6", "6d5451fd"]
+    assert ["%08x" % v for v in philox4x32_10(0xA4093822, 0x299F31D0, 0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344)] == [
+        "d16cfe09", "94fdcceb", "5001e420", "24126ea1"]
+
+
+def test_config1_same_decisions_120_draws():
+    """BASELINE.json configs[0] (N=200 p=5 m=10 P=20): 120 draws, ~14 000 trace records."""
+    assert compare(200, 5, 10, 20, 120, seed=1) > 2000
+
+
+def test_historical_depth_prior_small_sigma():
+    assert compare(150, 4, 6, 12, 40, seed=5, depth_offset=1, sigma=0.5) > 1000
+
+
+def test_weighted_split_prior_and_tiny():
+    assert compare(300, 6, 5, 10, 30, seed=26, split_prior=[5, 1, 0.5, 3, 0.1, 2]) > 300
+    compare(3, 2, 3, 4, 20, seed=7)
+
+
+def test_onehot_and_subset_rules():
+    rng = np.random.default_rng(12345)
+    Y = np.repeat(np.arange(3), 30).astype(np.float32)
+    X = np.concatenate([Y[:, None], rng.integers(0, 6, size=(90, 4))], axis=1).astype(np.float32)
+    assert compare(90, 5, 4, 10, 40, seed=13, X=X, y=Y, rules=["OneHotSplit"] * 5) > 100
+    cat = rng.integers(0, 6, 400)
+    Xs = np.stack([cat, rng.uniform(0, 1, 400), rng.integers(0, 4, 400)], axis=1).astype(np.float32)
+    ys = (4.0 * np.isin(cat, [0, 3, 5]) + rng.normal(0, 0.3, 400)).astype(np.float32)
+    assert compare(400, 3, 6, 10, 40, seed=61, X=Xs, y=ys, rules=["SubsetSplit", "ContinuousSplit", "SubsetSplit"], sigma=0.3,
+                   depth_offset=1) > 300
+
+
+def test_bernoulli_logit_likelihood():
+    """The float32 polynomial softplus / exp kernels and the 2^-20 fixed-point terms of bk_spec.h against numpy's
+    logaddexp in float64: same decisions, log-weights within 1e-5."""
+    assert compare(300, 5, 6, 10, 40, seed=7, likelihood=1) > 200
+    assert compare(120, 3, 4, 8, 30, seed=27, likelihood=1, depth_offset=1) > 100
+
+
+def _with_missing(N, p, seed, kind="normal", all_nan_col=None):
+    X, y, _ = friedman(N, p, seed, kind=kind)
+    rng = np.random.default_rng(seed + 1000)
+    X = X.copy()
+    X[N // 6: N // 3, 0] = np.nan
+    X[rng.uniform(size=N) < 0.1, 2] = np.nan
+    if all_nan_col is not None:
+        X[:, all_nan_col] = np.nan
+    return X, y
+
+
+def test_missing_covariates():
+    """App. A.4 as the spec defines it: up to four candidate members per split-value draw, rows without the split covariate
+    leave the tree (leaf id 255, predict 0), a column that is missing everywhere cancels the split."""
+    X, y = _with_missing(300, 4, 31)
+    assert compare(300, 4, 5, 10, 40, seed=31, X=X, y=y) > 200
+    X, y = _with_missing(250, 5, 33, all_nan_col=1)
+    assert compare(250, 5, 4, 10, 30, seed=33, X=X, y=y, depth_offset=1) > 200
+    X, y = _with_missing(300, 5, 34, kind="bernoulli")
+    assert compare(300, 5, 5, 8, 30, seed=34, X=X, y=y, likelihood=1) > 100
+    rng = np.random.default_rng(62)
+    cat = rng.integers(0, 6, 300).astype(np.float32)
+    Xs = np.stack([cat, rng.uniform(0, 1, 300).astype(np.float32)], axis=1)
+    ys = (4.0 * np.isin(cat, [0, 3, 5]) + rng.normal(0, 0.3, 300)).astype(np.float32)
+    Xs[rng.uniform(size=300) < 0.15, 0] = np.nan
+    assert compare(300, 2, 5, 10, 30, seed=62, X=Xs, y=ys, rules=["SubsetSplit", None], sigma=0.3, depth_offset=1) > 200
+
+
+def test_shared_tree_multi_output_likelihoods():
+    """K values per leaf, weights from the full (K, N) value: the reference's tested multi-output models
+    (tests/test_bart.py:107-123 heteroscedastic Normal, :140-164 Categorical-softmax) — bk_lik_term's float32 kernels against
+    numpy in float64."""
+    rng = np.random.default_rng(5)
+    X = rng.normal(0, 1, size=(250, 3)).astype(np.float32)
+    y = (rng.normal(0, 1, size=250) + 2 * X[:, 0]).astype(np.float32)
+    assert compare(250, 3, 4, 10, 30, seed=51, X=X, y=y, likelihood=2, n_outputs=2) > 100
+    Yc = np.repeat(np.arange(3), 30).astype(np.float32)
+    Xc = np.concatenate([Yc[:, None], rng.integers(0, 6, size=(90, 4))], axis=1).astype(np.float32)
+    assert compare(90, 5, 5, 8, 40, seed=52, X=Xc, y=Yc, likelihood=3, n_outputs=3, depth_offset=1) > 100
