@@ -288,3 +288,32 @@ class FloatModelChain:
         self.lower = upper if upper < self.m else 0
         self.draw += 1
         return vi, grow_events
+
+
+def predict_tree_float(nodes, x, excluded=None, rules=None):
+    """Out-of-sample value of one tree at the covariate row x (App. A.10), recursively in float64: at a split on an
+    excluded variable both children count, weighted by their shares of the training rows; otherwise the split rule
+    decides (a missing covariate compares false and goes right).  nodes: NODE_DTYPE records of the tree."""
+    def walk(k):
+        nd = nodes[k]
+        v = int(nd["var"])
+        if v < 0:
+            return float(nd["value"])
+        l = int(nd["left"])
+        if excluded is not None and excluded[v]:
+            tot = float(nodes[l]["n"]) + float(nodes[l + 1]["n"])
+            if not tot > 0.0:
+                return 0.0
+            wl = float(nodes[l]["n"]) / tot
+            return wl * walk(l) + (1.0 - wl) * walk(l + 1)
+        xv, s = float(x[v]), float(nd["split"])
+        rule = RULE_CONTINUOUS if rules is None else int(rules[v])
+        if rule == RULE_SUBSET:
+            left = (not math.isnan(xv)) and xv == int(xv) and 0 <= int(xv) < 24 and bool((int(s) >> int(xv)) & 1)
+        elif rule == RULE_ONEHOT:
+            left = xv == s
+        else:
+            left = xv <= s
+        return walk(l if left else l + 1)
+
+    return walk(0)

@@ -149,3 +149,31 @@ def test_shared_tree_multi_output_likelihoods():
     Yc = np.repeat(np.arange(3), 30).astype(np.float32)
     Xc = np.concatenate([Yc[:, None], rng.integers(0, 6, size=(90, 4))], axis=1).astype(np.float32)
     assert compare(90, 5, 5, 8, 40, seed=52, X=Xc, y=Yc, likelihood=3, n_outputs=3, depth_offset=1) > 100
+
+
+def test_prediction_with_excluded_variables():
+    """App. A.10 (the reference's `sample_posterior(X, draw_indices, excluded)`, pymc_bart/utils.py:60-71): the oracle's
+    stack-based weighted descent (which the prediction kernel matches bit for bit, tests/test_gpu_api.py) against a
+    recursive float64 walk, on new rows, with and without excluded variables, Continuous and Subset rules, NaNs in X."""
+    from oracle import oracle_py
+    from oracle.model_float import predict_tree_float
+
+    rng = np.random.default_rng(9)
+    cat = rng.integers(0, 6, 300)
+    X = np.stack([cat, rng.uniform(0, 1, 300), rng.uniform(0, 1, 300)], axis=1).astype(np.float32)
+    y = (4.0 * np.isin(cat, [0, 3, 5]) + 3 * X[:, 1] + rng.normal(0, 0.3, 300)).astype(np.float32)
+    rules = ["SubsetSplit", "ContinuousSplit", "ContinuousSplit"]
+    s = make_settings(X, y, m=8, num_particles=10, seed=9, split_rules=rules, depth_offset=1)
+    orc = OracleChain(s, X.T.copy(), y)
+    for d in range(40):
+        orc.step(d < 20, 0.3)
+    nodes, nn = orc.forest()
+    Xn = np.stack([rng.integers(0, 8, 40), rng.uniform(-0.2, 1.2, 40), rng.uniform(0, 1, 40)], axis=1).astype(np.float32)
+    Xn[3, 0] = np.nan; Xn[5, 1] = np.nan; Xn[7, 0] = 31.0          # missing values and a category code no set contains
+    for excl in (None, [1], [0, 2]):
+        mask = None
+        if excl is not None:
+            mask = np.zeros(3, np.uint8); mask[excl] = 1
+        got = oracle_py.predict(nodes[None], Xn, [0], excluded_mask=mask, rules=s.split_rules)[0]
+        want = [sum(predict_tree_float(nodes[t][: nn[t]], Xn[i], mask, s.split_rules) for t in range(8)) for i in range(40)]
+        np.testing.assert_allclose(got, np.array(want), rtol=0, atol=2e-5)
