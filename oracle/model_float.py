@@ -71,9 +71,10 @@ class _Particle:
 
 class FloatModelChain:
     def __init__(self, X, y, m, num_particles, p_leaf, seed=0, chain=0, batch=(0.1, 0.1), split_prior=None, split_rules=None,
-                 likelihood="normal", n_outputs=1):
+                 likelihood="normal", n_outputs=1, group=0):
         assert likelihood in ("normal", "bernoulli", "normal_hetero", "categorical")
         self.lik, self.K = likelihood, int(n_outputs)
+        self.group = int(group)      # output group of a BART(shape=(k, n), separate_trees=True) variable: its own forest and Philox word
         self.X = np.asarray(X, dtype=np.float32)                  # (N, p)
         self.y = np.asarray(y, dtype=np.float32)
         self.N, self.p = self.X.shape
@@ -97,11 +98,12 @@ class FloatModelChain:
         self.trace = []
 
     # ---- random numbers: addressing as App. A.9
-    def _rng(self, tree, rnd, particle, purpose, group=0):
+    def _rng(self, tree, rnd, particle, purpose, group=None):
+        group = self.group if group is None else group
         return philox4x32_10(self.seed, self.chain, self.draw, ((group << 16) | (tree & 0xFFFF)) & M32,
                              ((rnd << 16) | (particle & 0xFFFF)) & M32, purpose)
 
-    def _normal(self, tree, rnd, particle, purpose, group=0):
+    def _normal(self, tree, rnd, particle, purpose, group=None):
         w = self._rng(tree, rnd, particle, purpose, group)
         u1 = (w[0] + 1.0) / 4294967296.0
         return math.sqrt(-2.0 * math.log(u1)) * math.cos(2.0 * math.pi * (w[1] / 4294967296.0))
@@ -143,7 +145,7 @@ class FloatModelChain:
         if rows.size == 0:
             return out
         for j in range(self.K):
-            z = self._normal(tree, rnd, q, purpose, group=j)
+            z = self._normal(tree, rnd, q, purpose, group=j if self.K > 1 else None)
             mean = float(self.st[j, rows].astype(np.float64).sum()) / self.m / rows.size
             out[j] = np.float32(mean + z * self.leaf_sd[j])
         return out

@@ -177,3 +177,53 @@ def test_prediction_with_excluded_variables():
         got = oracle_py.predict(nodes[None], Xn, [0], excluded_mask=mask, rules=s.split_rules)[0]
         want = [sum(predict_tree_float(nodes[t][: nn[t]], Xn[i], mask, s.split_rules) for t in range(8)) for i in range(40)]
         np.testing.assert_allclose(got, np.array(want), rtol=0, atol=2e-5)
+
+
+def _same_step(orc, mod, tune, sigma, ctx):
+    vi_o, st_o = orc.step(tune, sigma)
+    vi_m, grow_m = mod.step(tune, sigma)
+    tr = orc.trace()
+    assert len(tr) == len(mod.trace), ctx
+    for a, b in zip(tr, mod.trace):
+        for k in INT_FIELDS:
+            assert int(a[k]) == int(b[k]), f"{ctx}: oracle {a} model {b}"
+        assert abs(float(a["log_w"]) - b["log_w"]) < 1e-5 * max(1.0, abs(b["log_w"])), f"{ctx}: oracle {a} model {b}"
+    assert np.array_equal(vi_o, vi_m) and st_o.grow_events == grow_m, ctx
+
+
+def test_separate_trees_groups_and_two_variables_in_one_likelihood():
+    """An output group of BART(shape=(k, n), separate_trees=True) is a chain with its own Philox group word and response row;
+    two BART variables in one Normal likelihood (tests/test_bart.py:167-241) alternate, each seeing the data minus the other's
+    current value: same decisions in the oracle and in the float model."""
+    X, y, _ = friedman(200, 4, 81)
+    Y = np.stack([y, -y, 0.5 * y]).astype(np.float32)
+    s = make_settings(X, Y, m=5, num_particles=8, seed=81, trace_capacity=20000, n_groups=3)
+    for g in (0, 2):
+        orc = OracleChain(s, X.T.copy(), Y, chain=0, group=g)
+        mod = FloatModelChain(X, Y[g], 5, 8, s.p_leaf, seed=s.seed, group=g)
+        mod.init_leaf[:] = np.float32(s.init_leaf); mod.st[:] = np.float32(s.init_sum)      # (one initial value for all groups: bart.py:148)
+        mod.leaf_sd[:] = s.leaf_sd_init
+        for nd in (f.nodes[0] for f in mod.forest):
+            nd.value[:] = np.float32(s.init_leaf)
+        for d in range(20):
+            _same_step(orc, mod, d < 10, 1.0, f"group {g} draw {d}")
+        np.testing.assert_allclose(orc.sum_trees(), mod.st[0], rtol=0, atol=5e-5)
+    # two variables, one likelihood
+    rng = np.random.default_rng(91)
+    X1 = rng.normal(0, 1, size=(150, 2)).astype(np.float32); X2 = rng.normal(0, 1, size=(150, 3)).astype(np.float32)
+    Y1 = (X1[:, 0] + rng.normal(0, 0.1, 150)).astype(np.float32); Y2 = (X2[:, 0] + X2[:, 1] + rng.normal(0, 0.1, 150)).astype(np.float32)
+    Yobs = (Y1 + Y2).astype(np.float32)
+    kw = dict(m=4, num_particles=8, trace_capacity=20000, value_range=float(np.abs(Yobs).max()))
+    sa, sb = make_settings(X1, Y1, seed=91, **kw), make_settings(X2, Y2, seed=92, **kw)
+    oa, ob = OracleChain(sa, X1.T.copy(), Y1.copy()), OracleChain(sb, X2.T.copy(), Y2.copy())
+    ma, mb = FloatModelChain(X1, Y1, 4, 8, sa.p_leaf, seed=91), FloatModelChain(X2, Y2, 4, 8, sb.p_leaf, seed=92)
+    va_o = np.full(150, np.float32(Y1.mean())); vb_o = np.full(150, np.float32(Y2.mean()))
+    va_m, vb_m = va_o.copy(), vb_o.copy()
+    for d in range(20):
+        oa.y[0, :] = Yobs - vb_o; ma.y = (Yobs - vb_m).astype(np.float32)
+        _same_step(oa, ma, d < 10, 0.5, f"variable A draw {d}")
+        va_o, va_m = oa.sum_trees().copy(), ma.st[0].copy()
+        ob.y[0, :] = Yobs - va_o; mb.y = (Yobs - va_m).astype(np.float32)
+        _same_step(ob, mb, d < 10, 0.5, f"variable B draw {d}")
+        vb_o, vb_m = ob.sum_trees().copy(), mb.st[0].copy()
+    np.testing.assert_allclose(va_o + vb_o, va_m + vb_m, rtol=0, atol=1e-4)
