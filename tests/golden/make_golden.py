@@ -35,6 +35,38 @@ BIG_CASES = {
 }
 
 
+# SubsetSplit with missing categories and a single-category column (cancelled draws): name -> (N, m, P, draws, seed, n_cat)
+SUBSET_CASES = {
+    "subset_n500_m5_P12": (500, 5, 12, 40, 73, 6),
+}
+SUBSET_RULES = ["SubsetSplit", "ContinuousSplit", "SubsetSplit", "ContinuousSplit"]
+
+
+def subset_data(N, seed, n_cat):
+    rng = np.random.default_rng(seed)
+    cat = rng.integers(0, n_cat, N)
+    X = np.stack([cat, rng.uniform(0, 1, N), np.full(N, 3.0), rng.uniform(0, 1, N)], axis=1).astype(np.float32)
+    y = (4.0 * np.isin(cat, [0, 3, 5]) + 2.0 * X[:, 1] + rng.normal(0, 0.3, N)).astype(np.float32)
+    X[rng.uniform(size=N) < 0.12, 0] = np.nan
+    X[rng.uniform(size=N) < 0.12, 3] = np.nan
+    return X, y
+
+
+def run_subset_case(N, m, P, draws, seed, n_cat):
+    X, y = subset_data(N, seed, n_cat)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=1, trace_capacity=20000, split_rules=SUBSET_RULES)
+    o = OracleChain(s, X.T.copy(), y)
+    traces, sums, vis = [], [], []
+    for d in range(draws):
+        vi, st = o.step(d < draws // 2, 0.3)
+        traces.append(o.trace().copy())
+        sums.append(o.sum_trees().copy())
+        vis.append(vi.copy())
+    nodes, nn = o.forest()
+    return dict(trace=np.concatenate(traces), trace_len=np.array([len(t) for t in traces]), sum_trees=np.stack(sums),
+                vi=np.stack(vis), forest=nodes, forest_nn=nn, leaf_ids=o.leaf_ids())
+
+
 def _sha(a):
     import hashlib
 
@@ -84,4 +116,9 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         np.savez_compressed(os.path.join(out, name + ".npz"), cfg=np.array(cfg[:7]), **run_big_case(*cfg))
+        print("wrote", name)
+    for name, cfg in SUBSET_CASES.items():
+        if only and name not in only:
+            continue
+        np.savez_compressed(os.path.join(out, name + ".npz"), cfg=np.array(cfg), **run_subset_case(*cfg))
         print("wrote", name)

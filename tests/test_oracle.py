@@ -66,6 +66,32 @@ def test_oracle_matches_big_golden(name):
     assert sha(o.leaf_ids()) == str(g["leaf_ids_sha"])
 
 
+def test_oracle_matches_subset_golden():
+    """SubsetSplit with missing categories and a single-category column (tests/golden/make_golden.py SUBSET_CASES)."""
+    sys.path.insert(0, GOLD)
+    from make_golden import SUBSET_RULES, subset_data
+
+    name = "subset_n500_m5_P12"
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    N, m, P, draws, seed, n_cat = [int(v) for v in g["cfg"]]
+    X, y = subset_data(N, seed, n_cat)
+    s = make_settings(X, y, m=m, num_particles=P, seed=seed, depth_offset=1, trace_capacity=20000, split_rules=SUBSET_RULES)
+    o = OracleChain(s, X.T.copy(), y)
+    pos = 0
+    for d in range(draws):
+        vi, st = o.step(d < draws // 2, 0.3)
+        n = int(g["trace_len"][d])
+        assert_trace_equal(o.trace(), g["trace"][pos:pos + n], f"{name} draw {d}")
+        pos += n
+        assert np.array_equal(o.sum_trees().view(np.uint32), g["sum_trees"][d].view(np.uint32))
+        assert np.array_equal(vi, g["vi"][d])
+    nodes, nn = o.forest()
+    assert np.array_equal(nn, g["forest_nn"]) and np.array_equal(nodes.view(np.uint8), g["forest"].view(np.uint8))
+    assert np.array_equal(o.leaf_ids(), g["leaf_ids"])
+    used = np.concatenate([nodes[t]["var"][: nn[t]] for t in range(m)])
+    assert 0 in used and 2 not in used and (o.leaf_ids() == 255).any()      # sets drawn, the one-category column never, NaN rows dropped
+
+
 def test_oracle_missing_covariates():
     """SURVEY.md App. A.4 in the restatement: NaN candidates are skipped, rows with a missing split covariate go to
     limbo (id 255) and count for neither child, a column that is missing everywhere is never split on."""
