@@ -15,7 +15,7 @@ if _pm is not None:
     from . import pymc_adapter  # noqa: F401  (appends the step class to pm.STEP_METHODS)
 
 __version__ = "0.2.0"
-__all__ = ["BART", "PGBART", "PosteriorSampler", "sample", "compute_variable_importance", "get_variable_inclusion"]
+__all__ = ["BART", "PGBART", "PosteriorSampler", "sample", "sample_joint", "compute_variable_importance", "get_variable_inclusion"]
 
 
 def __getattr__(name):  # PGBART / sample import torch lazily
@@ -23,10 +23,10 @@ def __getattr__(name):  # PGBART / sample import torch lazily
         from .pgbart import PGBART
 
         return PGBART
-    if name == "sample":
-        from .sampling import sample
+    if name in ("sample", "sample_joint"):
+        from . import sampling
 
-        return sample
+        return getattr(sampling, name)
     if name in ("compute_variable_importance", "get_variable_inclusion", "vi_to_kulprit"):
         from . import importance
 

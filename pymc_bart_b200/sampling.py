@@ -104,3 +104,40 @@ def sample(rv, tune=200, draws=200, chains=4, num_particles=10, batch=(0.1, 0.1)
         # the single collective of the run: all-gather of the posterior draws over NVLink
         out["posterior"] = gather_posterior(torch.from_numpy(post).cuda(), world).cpu().numpy()
     return out
+
+
+def sample_joint(rvs, observed, tune=200, draws=200, num_particles=10, batch=(0.1, 0.1), sigma=1.0, seed=0, sigma_fn=None,
+                 **step_kwargs):
+    """Several BART variables in ONE Normal likelihood, ``observed ~ Normal(sum of the variables, sigma)`` — the model of
+    tests/test_bart.py:167-241 (``pm.Normal("y", mu1 + mu2, sigma, observed=Y)``, one PGBART step per variable) without PyMC.
+    One chain; the steps run one after the other on the same point, as pm.sample's compound step does: each sees the data
+    minus the other variables' current values (``PGBART(observed=, offset_names=)``).
+    Returns {"posterior": {name: (draws, N) float32}, "variable_inclusion": {name: [str]}, "steps": {name: PGBART}}."""
+    from .pgbart import PGBART
+
+    names = [rv.name for rv in rvs]
+    if len(set(names)) != len(names):
+        raise ValueError("the BART variables need distinct names")
+    observed = np.asarray(observed, dtype=np.float64)
+    steps, point = {}, {}
+    for k, rv in enumerate(rvs):
+        steps[rv.name] = PGBART([rv], num_particles=num_particles, batch=batch, likelihood="normal", sigma=sigma, seed=seed + k,
+                                observed=observed, offset_names=[n for n in names if n != rv.name], **step_kwargs)
+        op = rv.owner.op
+        point[rv.name] = np.full(observed.shape, float(np.asarray(op.Y, dtype=np.float64).mean()))    # bart.py:148 initial value
+    post = {n: np.empty((draws, *observed.shape), dtype=np.float32) for n in names}
+    vi = {n: [None] * draws for n in names}
+    for d in range(tune + draws):
+        for n in names:
+            st = steps[n]
+            if d == tune:
+                st.stop_tuning()
+            if sigma_fn is not None:
+                st.sigma = sigma_fn(d, point)
+            point, stats = st.step(point)
+            if d >= tune:
+                post[n][d - tune] = point[n]
+                vi[n][d - tune] = stats[0]["variable_inclusion"]
+    for st in steps.values():
+        st.flush_history()
+    return {"posterior": post, "variable_inclusion": vi, "steps": steps}

@@ -234,6 +234,29 @@ def test_two_bart_variables_see_each_other_as_offsets(monkeypatch):
     s1.close(); s2.close()
 
 
+def test_sample_joint_driver_with_a_fake_core(monkeypatch):
+    """pmb.sample_joint([mu1, mu2], observed=Y): the PyMC-free driver of the two-variable model (tests/test_bart.py:167-206) —
+    shapes, one inclusion string per variable and draw, separate histories, every step told the other variable's value."""
+    import pymc_bart_b200 as pmb
+    import pymc_bart_b200.pgbart as pg
+
+    monkeypatch.setattr(pg, "DeviceSampler", _FakeCore)
+    _FakeCore.instances.clear()
+    rng = np.random.default_rng(2)
+    X1 = rng.normal(size=(50, 2)); X2 = rng.normal(size=(50, 3)); Y = rng.normal(size=50)
+    mu1 = BART("mu1", X1, X1[:, 0], m=5); mu2 = BART("mu2", X2, X2[:, 0], m=5)
+    out = pmb.sample_joint([mu1, mu2], Y, tune=4, draws=6, num_particles=5)
+    assert out["posterior"]["mu1"].shape == (6, 50) and out["posterior"]["mu2"].shape == (6, 50)      # idata.posterior["mu1"]: (1, draws, 50)
+    assert len(out["variable_inclusion"]["mu1"]) == 6 and all(isinstance(s, str) for s in out["variable_inclusion"]["mu2"])
+    s1, s2 = out["steps"]["mu1"], out["steps"]["mu2"]
+    assert s1.offset_names == ["mu2"] and s2.offset_names == ["mu1"] and not s1.tune
+    assert len(mu1.owner.op.all_trees) == 1 and len(mu2.owner.op.all_trees) == 1 and mu1.owner.op.all_trees is not mu2.owner.op.all_trees
+    np.testing.assert_allclose(s2.core.response[0], Y - out["posterior"]["mu1"][-1], atol=1e-4)   # the last step of mu2 saw the last mu1
+    with pytest.raises(ValueError):
+        pmb.sample_joint([mu1, mu1], Y)
+    s1.close(); s2.close()
+
+
 def test_pgbart_step_protocol_with_a_fake_core(monkeypatch):
     """Host logic of PGBART.astep without a GPU: value shapes for (chains, output groups), one inclusion string per
     BART variable (groups summed), round-robin tree batches, ONE all_trees entry per chain that grows by one batch per
