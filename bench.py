@@ -135,6 +135,12 @@ def oracle_sample(name, cfg, n_chains, steps, warm, threads):
     s = make_settings(X, y, m=m, num_particles=P, seed=seed, n_chains=1, likelihood=lik, n_groups=groups)
     Xc = np.ascontiguousarray(X.T)
     orcs = [OracleChain(s, Xc, y, chain=c, group=g) for c in range(n_chains) for g in range(groups)]
+    # cores left over after one thread per chain go to the chains' particle loops (independent particles; same results)
+    # (small problems stay sequential: a round of N = 200 rows is shorter than starting the threads)
+    inner = max(1, (os.cpu_count() or 1) // max(1, min(threads, len(orcs)))) if N >= 20000 else 1
+    for o in orcs:
+        o.set_threads(inner)
+    oracle_sample.last_inner = inner
 
     def run_all(n, tune):
         if n <= 0:
@@ -179,9 +185,10 @@ def run_reference(args, cfg):
     if args.config != "C1":
         steps, warm = bounded_cpu_steps(cfg, steps, n_chains, threads), min(warm, 1)
     val, dt, tpd = oracle_sample(args.config, cfg, n_chains, steps, warm, threads)
+    inner = oracle_sample.last_inner
     config = {"workload": workload_name(args.config, cfg, tpd),
               "note": f"CPU restatement oracle/pgbart_oracle.c (bartrs unavailable offline), {n_chains} chains x {groups} output "
-                      f"groups on {threads} host threads (ctypes releases the GIL)"}
+                      f"groups on {threads} host threads (ctypes releases the GIL) x {inner} particle thread(s) per chain"}
     if args.config == "C2" and not args.no_c5:
         c5 = CONFIGS["C5"]
         # bounded sample: one chain per host thread, at most 16 of the workload's chains (a C5 draw takes the oracle ~10 s and a
@@ -189,15 +196,17 @@ def run_reference(args, cfg):
         n5 = max(1, min(c5[4] * max(1, args.gpus), os.cpu_count() or 1, 16))
         th5 = n5
         v5, dt5, tpd5 = oracle_sample("C5", c5, n5, 2, 0, th5)
+        in5 = oracle_sample.last_inner
         config["c5"] = {"workload": workload_name("C5", c5, tpd5), "value": v5, "unit": "draws/s", "ms_per_step": 1e3 * dt5 / 2,
-                        "cpu_baseline": {"value": v5, "unit": "draws/s", "cores": th5, "kind": "port",
-                                         "sample": f"1 tuning + 1 post-tuning draw x {n5} chains, no warm-up"}}
+                        "cpu_baseline": {"value": v5, "unit": "draws/s", "cores": th5 * in5, "kind": "port",
+                                         "sample": f"1 tuning + 1 post-tuning draw x {n5} chains ({in5} particle thread(s) per chain), no warm-up"}}
     line = {
         "impl": "reference", "metric": "PGBART draws/sec", "value": val, "unit": "draws/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+i64", "data": "synthetic", "config": config,
-        "cpu_baseline": {"value": val, "unit": "draws/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps - steps // 2} tuning + {steps // 2} post-tuning draws x {n_chains} chains after {warm} warm-up"},
+        "cpu_baseline": {"value": val, "unit": "draws/s", "cores": threads * inner, "kind": "port",
+                         "sample": f"{steps - steps // 2} tuning + {steps // 2} post-tuning draws x {n_chains} chains after {warm} warm-up, "
+                                   f"{threads} chain threads x {inner} particle thread(s)"},
         "e2e": {"value": val, "unit": "draws/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -498,9 +507,11 @@ def measure(name, steps, warm, args, rank, world, local, clocks, peak, peak_src,
             ncpu = max(1, min((os.cpu_count() or 1) // groups, chains))   # chains sampled; each needs `groups` threads
             nd = args.cpu_draws or bounded_cpu_steps(cfg, 40, ncpu, ncpu * groups)
             v, cdt, _ = oracle_sample(name, cfg, ncpu, nd, 0, ncpu * groups)
-            out["cpu_baseline"] = {"value": v, "unit": "draws/s", "cores": ncpu * groups, "kind": "port",
+            inner = oracle_sample.last_inner
+            out["cpu_baseline"] = {"value": v, "unit": "draws/s", "cores": ncpu * groups * inner, "kind": "port",
                                    "sample": f"{nd - nd // 2} tuning + {nd // 2} post-tuning draws x {ncpu} chains of {name} in {cdt:.1f} s, "
-                                             f"one chain per host thread (oracle/pgbart_oracle.c, gcc -O3; bartrs is not installable offline)"}
+                                             f"one host thread per chain x {inner} particle thread(s) each (oracle/pgbart_oracle.c, gcc -O3; "
+                                             f"bartrs is not installable offline)"}
         except Exception as e:  # noqa
             out["cpu_baseline"] = {"value": None, "unit": "draws/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     return out

@@ -49,6 +49,7 @@ def load():
     lib.bko_export_leaf_values.argtypes = [C.c_void_p, C.c_void_p]
     lib.bko_bytes_touched.argtypes = [C.c_void_p]
     lib.bko_bytes_touched.restype = C.c_longlong
+    lib.bko_set_threads.argtypes = [C.c_void_p, C.c_int]
     lib.bko_leaf_sd.argtypes = [C.c_void_p]
     lib.bko_leaf_sd.restype = C.c_float
     lib.bko_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
@@ -74,6 +75,10 @@ class OracleChain:
         self.h = h
         self.N, self.p, self.m = settings.n_rows, settings.n_cols, settings.n_trees
         self.K = max(1, int(getattr(settings, "n_outputs", 1)))
+
+    def set_threads(self, n: int) -> int:
+        """Host threads for the particle loops of this chain (single-output step); results do not depend on it."""
+        return int(self.lib.bko_set_threads(self.h, int(n)))
 
     def close(self):
         if getattr(self, "h", None):

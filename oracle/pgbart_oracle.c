@@ -53,6 +53,38 @@
 #include "bk_spec.h"
 #include "pgbart_b200.h"
 
+/* The particles of a round are independent (every random number is addressed by its counter, a particle touches only its
+ * own nodes and leaf-id array), so a chain may spread them over host threads (bko_set_threads): same results bit for bit,
+ * and the CPU baseline of bench.py uses every core the box has (chains x particle threads).  Plain pthreads: a handful of
+ * threads per round pull particle indices from an atomic counter (libgomp is not in the image). */
+#include <pthread.h>
+
+typedef struct {
+  void (*fn)(void* ctx, int index);
+  void* ctx;
+  int next, end;   /* next index to hand out (atomic), one past the last */
+} pf_job;
+static void* pf_worker(void* arg) {
+  pf_job* j = (pf_job*)arg;
+  for (;;) {
+    int i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+    if (i >= j->end) return NULL;
+    j->fn(j->ctx, i);
+  }
+}
+/* fn(ctx, i) for i in [lo, hi) on up to `threads` threads (the caller is one of them); returns when all are done */
+static void parallel_for(int threads, int lo, int hi, void (*fn)(void*, int), void* ctx) {
+  pf_job job; job.fn = fn; job.ctx = ctx; job.next = lo; job.end = hi;
+  int extra = threads - 1;
+  if (extra > hi - lo - 1) extra = hi - lo - 1;
+  pthread_t th[64];
+  int started = 0;
+  if (extra > 64) extra = 64;
+  for (int k = 0; k < extra; ++k) if (pthread_create(&th[started], NULL, pf_worker, &job) == 0) started++;
+  pf_worker(&job);
+  for (int k = 0; k < started; ++k) pthread_join(th[k], NULL);
+}
+
 typedef struct {
   int32_t var;   /* -1 leaf */
   float split;
@@ -107,6 +139,7 @@ typedef struct bko_s {
   int32_t* anc;
   double r2_total;  /* Gaussian: sum of squares of all rows' residuals for the tree being updated */
   long long bytes_touched; /* rough algorithmic byte counter for the CPU baseline */
+  int threads;             /* host threads of this chain's particle loops (bko_set_threads; 1 = sequential) */
   /* shared-tree multi-output (K = n_outputs > 1): per-output copies of the row arrays and of the running leaf sd */
   int K;
   float* stk;      /* [K][N] sum of trees */
@@ -141,7 +174,7 @@ int bko_create(const bk_settings* s, const float* X, const float* y, int chain_l
   if (!s || !X || !y || !out) return BK_ERR_ARG;
   if (s->n_particles < 2 || s->n_rows < 1 || s->n_trees < 1) return BK_ERR_ARG;
   bko* o = (bko*)calloc(1, sizeof(bko));
-  o->s = *s; o->chain = chain_local;
+  o->s = *s; o->chain = chain_local; o->threads = 1;
   o->N = s->n_rows; o->p = s->n_cols; o->m = s->n_trees; o->P = s->n_particles;
   o->X = X; o->y = y + (size_t)group * (size_t)s->n_rows; o->group = group;
   memcpy(o->p_leaf, s->p_leaf, sizeof(double) * BK_MAX_DEPTH_TABLE);
@@ -252,7 +285,7 @@ static int draw_variable(const bko* o, double u) {
 }
 
 /* one grow attempt of particle slot `pi` at round `round`; returns 1 if it grew */
-static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* rec) {
+static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* rec, long long* bytes) {
   o_particle* q = &o->parts[pi];
   const int N = o->N;
   if (rec) { rec->node = -1; rec->var = -1; }
@@ -321,7 +354,7 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
     int64_t a = (int64_t)o->qr[i];
     t->n += 1; t->sst += (int64_t)o->qst[i]; t->sr += a;
   }
-  o->bytes_touched += (long long)N * 14;
+  *bytes += (long long)N * 14;
   double zl = bk_normal(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_LEFT));
   double zr = bk_normal(bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)tree, (uint32_t)round, (uint32_t)pi, BK_Z_RIGHT));
   float vl = bk_leaf_value(sl.n, sl.sst, o->inv_qm, zl, o->leaf_sd);
@@ -339,7 +372,7 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
       if (q->ids[i] == (uint8_t)L) ll_l += (int64_t)bk_bern_q(o->y[i], o->noi[i], vl);
       else if (q->ids[i] == (uint8_t)R) ll_r += (int64_t)bk_bern_q(o->y[i], o->noi[i], vr);
     }
-    o->bytes_touched += (long long)N * 9;
+    *bytes += (long long)N * 9;
     nl->ll = ll_l; nr->ll = ll_r;
     q->llq = q->llq - nd->ll + ll_l + ll_r + ll_dropped;
     q->lw = bk_bern_loglik((double)q->llq);
@@ -352,6 +385,23 @@ static int grow(bko* o, int tree, int round, int pi, float sigma, bk_trace_rec* 
 }
 
 static int bko_step_multi(bko* o, int tune, int32_t* vi_counts, bk_step_stats* stats);
+
+/* one round of the particles 1..P-1 and the deep copies of a resampling, as parallel_for bodies */
+typedef struct {
+  bko* o; int tree, round; float sigma;
+  bk_trace_rec** recs;
+  int grew[128], was_root[128];
+  long long bytes[128];
+} round_ctx;
+static void grow_one(void* ctx, int q) {
+  round_ctx* rc = (round_ctx*)ctx;
+  rc->grew[q] = grow(rc->o, rc->tree, rc->round, q, rc->sigma, rc->recs[q], &rc->bytes[q]);
+  if (rc->recs[q]) rc->recs[q]->log_w = rc->o->parts[q].lw;
+}
+static void copy_one(void* ctx, int q) {
+  bko* o = (bko*)ctx;
+  part_copy(&o->tmp[q], &o->parts[o->anc[q - 1] + 1], o->N);
+}
 
 int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* stats) {
   if (o->K > 1) return bko_step_multi(o, tune, vi_counts, stats);
@@ -420,12 +470,19 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
     int round = 0;
     for (;; ++round) {
       int tr0 = o->trace_len;
+      bk_trace_rec* recs[128];   /* (P <= 128) record slots are handed out in particle order first */
       for (int q = 1; q < P; ++q) {
         bk_trace_rec* rec = trace_slot(o);
         if (rec) { rec->kind = 1; rec->tree = t; rec->round = round; rec->particle = q; rec->ancestor = -1; }
-        int was_root = o->parts[q].q_head == 0;
-        if (grow(o, t, round, q, sigma, rec)) { loc.grow_events++; if (was_root) loc.grow_root++; }
-        if (rec) rec->log_w = o->parts[q].lw;
+        recs[q] = rec;
+      }
+      round_ctx rc; rc.o = o; rc.tree = t; rc.round = round; rc.sigma = sigma; rc.recs = recs;
+      memset(rc.grew, 0, sizeof(rc.grew)); memset(rc.bytes, 0, sizeof(rc.bytes));
+      for (int q = 1; q < P; ++q) rc.was_root[q] = o->parts[q].q_head == 0;
+      parallel_for(o->threads, 1, P, grow_one, &rc);
+      for (int q = 1; q < P; ++q) {   /* (per-particle results are gathered in particle order: no shared counter in the loop) */
+        if (rc.grew[q]) { loc.grow_events++; if (rc.was_root[q]) loc.grow_root++; }
+        o->bytes_touched += rc.bytes[q];
       }
       loc.rounds++;
       int live = 0;
@@ -434,7 +491,7 @@ int bko_step(bko* o, int tune, float sigma, int32_t* vi_counts, bk_step_stats* s
       weight_sums(o->parts, 1, P - 1, o->w);
       uint32_t u = bk_rng(S, C, D, (uint32_t)o->group, (uint32_t)t, (uint32_t)round, 0, BK_U_RESAMPLE).v[0];
       systematic(o->w, P - 1, u, o->anc);
-      for (int q = 1; q < P; ++q) part_copy(&o->tmp[q], &o->parts[o->anc[q - 1] + 1], N);
+      parallel_for(o->threads, 1, P, copy_one, o);
       for (int q = 1; q < P; ++q) {
         o_particle sw = o->parts[q]; o->parts[q] = o->tmp[q]; o->tmp[q] = sw;
         if (o->trace && tr0 + q - 1 < o->trace_cap) o->trace[tr0 + q - 1].ancestor = o->anc[q - 1] + 1;
@@ -736,6 +793,11 @@ int bko_export_leaf_ids(const bko* o, uint8_t* ids) {
 }
 
 long long bko_bytes_touched(const bko* o) { return o->bytes_touched; }
+/* host threads for this chain's particle loops (single-output step); returns the number in effect */
+int bko_set_threads(bko* o, int n) {
+  o->threads = n < 1 ? 1 : (n > 65 ? 65 : n);
+  return o->threads;
+}
 float bko_leaf_sd(const bko* o) { return o->leaf_sd; }
 
 /* ------------------------------------------------------------------------

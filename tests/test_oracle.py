@@ -266,3 +266,23 @@ def test_forest_invariants_hold_for_the_oracle():
             o.step(d < 20, 1.0)
         nodes, nn = o.forest()
         check_forest_invariants(nodes, nn, o.leaf_ids(), o.sum_trees(), 3000)
+
+
+def test_particle_threads_do_not_change_the_results():
+    """bko_set_threads: the particles of a round (and the deep copies of a resampling) spread over host threads — every
+    trace record, the sum of trees, the forest and the leaf ids stay bit-identical (Gaussian and Bernoulli, missing values)."""
+    for lik in (0, 1):
+        X, y, _ = friedman(600, 5, 88, kind="bernoulli" if lik else "normal")
+        X = X.copy(); X[50:120, 1] = np.nan
+        s = make_settings(X, y, m=6, num_particles=16, seed=88, trace_capacity=30000, likelihood=lik, depth_offset=1)
+        a, b = OracleChain(s, X.T.copy(), y), OracleChain(s, X.T.copy(), y)
+        assert b.set_threads(5) == 5 and a.set_threads(0) == 1
+        for d in range(24):
+            via, sta = a.step(d < 12, 0.7)
+            vib, stb = b.step(d < 12, 0.7)
+            assert_trace_equal(a.trace(), b.trace(), f"lik {lik} draw {d}")
+            assert np.array_equal(via, vib) and sta.grow_events == stb.grow_events and sta.grow_root == stb.grow_root
+            assert np.array_equal(a.sum_trees().view(np.uint32), b.sum_trees().view(np.uint32))
+        assert np.array_equal(a.leaf_ids(), b.leaf_ids()) and a.bytes_touched() == b.bytes_touched()
+        na, nb = a.forest(), b.forest()
+        assert np.array_equal(na[0].view(np.uint8), nb[0].view(np.uint8)) and np.array_equal(na[1], nb[1])
